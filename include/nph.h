@@ -1,0 +1,233 @@
+/* nph.h — C ABI of the B200-native nanopolish HMM engine (libnph.so).
+ *
+ * This is the drop-in boundary for the ONE hot path this repository accelerates
+ * (SURVEY.md section 8):
+ *
+ *   1. the R9 profile-HMM forward score
+ *        profile_hmm_score            ref: src/hmm/nanopolish_profile_hmm.cpp:23-30
+ *        profile_hmm_score_r9         ref: src/hmm/nanopolish_profile_hmm_r9.cpp:35-65
+ *        profile_hmm_fill_generic_r9  ref: src/hmm/nanopolish_profile_hmm_r9.inl:265-433
+ *        profile_hmm_score_set        ref: src/hmm/nanopolish_profile_hmm.cpp:32-56
+ *   2. the adaptive banded event-to-sequence alignment
+ *        adaptive_banded_simple_event_align   ref: src/nanopolish_raw_loader.cpp:77-379
+ *        estimate_scalings_using_mom          ref: src/nanopolish_raw_loader.cpp:17-60
+ *   3. (section 8f "next" row N1) the Viterbi alignment with the same fill
+ *        profile_hmm_align_r9         ref: src/hmm/nanopolish_profile_hmm_r9.cpp:73-204
+ *
+ * The reference has no FFI layer: its seam is those C++ free functions, called with
+ * HMMInputData / HMMInputSequence / SquiggleRead.  The C++ mirror of that call surface
+ * lives in nanopolish_b200/host/ and lowers onto the functions below; INTEGRATION.md shows
+ * the binding a nanopolish maintainer would add.
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no C++/torch/CUDA types in any signature
+ *     (a CUDA stream is passed as void*).
+ *   - every function returns NPH_OK (0) or a negative nph_status; nothing throws, nothing
+ *     calls exit().  nph_strerror() gives a message, nph_last_error(ctx) the CUDA detail.
+ *   - the caller owns every host buffer for the duration of the call; the context owns
+ *     all device memory.  A context is bound to one device and one stream and must not be
+ *     used from two threads at once (use one context per OpenMP thread, or a mutex).
+ *   - there is NO CPU fallback: without a CUDA device nph_create() fails with
+ *     NPH_ERR_NO_DEVICE and nothing else can be called.
+ *   - results are bit-identical to the reference's float arithmetic (same operation order,
+ *     same quantised table logsum, IEEE add/mul/div, no FMA contraction); see DESIGN.md.
+ */
+#ifndef NPH_H
+#define NPH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPH_VERSION_MAJOR 0
+#define NPH_VERSION_MINOR 1
+
+typedef enum {
+    NPH_OK = 0,
+    NPH_ERR_NO_DEVICE = -1,   /* no usable CUDA device / driver: there is no CPU path */
+    NPH_ERR_CUDA = -2,        /* a CUDA runtime call failed; see nph_last_error */
+    NPH_ERR_INVALID = -3,     /* bad argument (null pointer, out-of-range index, ...) */
+    NPH_ERR_NOMEM = -4,       /* device or host allocation failed */
+    NPH_ERR_STATE = -5,       /* call sequence error (e.g. score before load) */
+    NPH_ERR_UNSUPPORTED = -6  /* a shape the kernels do not handle (documented limits) */
+} nph_status;
+
+/* flags of profile_hmm_score / profile_hmm_align.
+ * ref: src/hmm/nanopolish_profile_hmm.h:34-38 (HAF_ALLOW_PRE_CLIP, HAF_ALLOW_POST_CLIP) */
+#define NPH_HAF_ALLOW_PRE_CLIP  1u
+#define NPH_HAF_ALLOW_POST_CLIP 2u
+
+typedef struct nph_ctx nph_ctx;
+
+/* One strand of one SquiggleRead: the part of it the hot path reads.
+ * ref: SquiggleRead::events[strand] (src/nanopolish_squiggle_read.h:277-299),
+ *      SquiggleScalings (:63-93), events_per_base[strand] (:293). 64 bytes. */
+typedef struct {
+    uint64_t event_off;       /* first event of this read in ev_mean[] / ev_start_time[] */
+    uint32_t n_events;
+    uint32_t reserved;
+    double scale;             /* SquiggleScalings::scale   */
+    double shift;             /*                 ::shift   */
+    double drift;             /*                 ::drift   */
+    double var;               /*                 ::var     */
+    double log_var;           /*                 ::log_var (= log(var), cached by set4/set6) */
+    double events_per_base;   /* SquiggleRead::events_per_base[strand] */
+} nph_read;
+
+/* One profile_hmm_score call == one (HMMInputSequence, HMMInputData, flags) triple.
+ * ref: HMMInputData (src/common/nanopolish_common.h:53-62).  The sequence is passed as the
+ * k-mer ranks HMMInputSequence::get_kmer_rank(ki, k, rc) returns for ki = 0..n_kmers-1
+ * (src/hmm/nanopolish_hmm_input_sequence.h:76-91), i.e. already strand-resolved. 32 bytes. */
+typedef struct {
+    uint64_t rank_off;        /* first k-mer rank of this job in kmer_ranks[] */
+    uint32_t read;            /* index into reads[] */
+    uint32_t model_id;        /* from nph_model_upload: HMMInputData::pore_model */
+    uint32_t event_start;     /* HMMInputData::event_start_idx */
+    uint32_t event_stop;      /* HMMInputData::event_stop_idx (inclusive) */
+    uint32_t n_kmers;         /* sequence.length() - k + 1 */
+    int8_t   stride;          /* HMMInputData::event_stride: +1, or -1 when event_stop < event_start */
+    uint8_t  rc;              /* HMMInputData::rc (informational: ranks are already resolved) */
+    uint8_t  flags;           /* NPH_HAF_* */
+    uint8_t  reserved;
+} nph_hmm_job;
+
+/* One adaptive_banded_simple_event_align call: a whole read against its basecalled sequence. */
+typedef struct {
+    uint64_t rank_off;        /* first k-mer rank (forward strand, alphabet->kmer_rank) in kmer_ranks[] */
+    uint64_t pairs_off;       /* where this read's AlignedPairs go in pairs_out[] (in pairs) */
+    uint32_t read;            /* index into reads[] (scalings as set by the MoM estimate: drift 0, var 1) */
+    uint32_t n_kmers;
+    uint32_t pairs_cap;       /* room at pairs_off, in pairs; n_events + n_kmers always suffices */
+    uint32_t reserved;
+} nph_abea_job;
+
+/* ref: AlignedPair (src/alignment/nanopolish_anchor.h:18-22) */
+typedef struct { int32_t ref_pos; int32_t read_pos; } nph_aligned_pair;
+
+/* status of one ABEA job.  The reference returns an empty vector for every failure
+ * (src/nanopolish_raw_loader.cpp:365-372); n_pairs is 0 in exactly those cases. */
+#define NPH_ABEA_OK              0
+#define NPH_ABEA_LOW_EMISSION    1   /* avg_log_emission < -5.0 */
+#define NPH_ABEA_NOT_SPANNED     2   /* path does not run from k-mer 0 to k-mer n_kmers-1 */
+#define NPH_ABEA_MAX_GAP         4   /* more than 50 consecutive skipped k-mers */
+#define NPH_ABEA_NO_END_CELL     8   /* last k-mer column never inside the band (reference behaviour undefined) */
+#define NPH_ABEA_PAIRS_OVERFLOW 16   /* pairs_cap too small */
+typedef struct {
+    uint32_t n_pairs;         /* 0 when the reference would have returned an empty vector */
+    int32_t  status;          /* bit-or of NPH_ABEA_* */
+    int32_t  max_gap;
+    uint32_t n_aligned;       /* path length before QC (== n_pairs when status == 0) */
+    double   avg_log_emission;
+} nph_abea_result;
+
+/* One Viterbi state of profile_hmm_align.  ref: HMMAlignmentState (src/common/nanopolish_common.h:65-73);
+ * l_posterior and log_transition_probability are left for the host wrapper (section 8f N1). */
+typedef struct {
+    uint32_t event_idx;
+    uint32_t kmer_idx;
+    float    l_fm;
+    char     state;           /* 'M', 'B' (bad event) or 'K' (k-mer skip) */
+    uint8_t  reserved[3];
+} nph_align_state;
+
+/* ---- context ------------------------------------------------------------------------- */
+
+/* Create a context on CUDA device `device` with its own non-blocking stream. */
+int nph_create(nph_ctx** ctx_out, int device);
+/* Same, but run everything on the caller's stream (a cudaStream_t passed as void*; NULL = legacy
+ * default stream).  Lets a host framework time/sequence the kernels with its own events. */
+int nph_create_on_stream(nph_ctx** ctx_out, int device, void* cuda_stream);
+int nph_destroy(nph_ctx* ctx);
+const char* nph_strerror(int status);
+const char* nph_last_error(const nph_ctx* ctx);
+int nph_version(void);                              /* major*1000 + minor */
+int nph_sync(nph_ctx* ctx);                         /* wait for everything queued on the context's stream */
+void* nph_stream(nph_ctx* ctx);                     /* the cudaStream_t the kernels run on */
+
+/* PoreModel::states as three parallel arrays (level_mean, level_stdv, level_log_stdv).
+ * ref: PoreModelStateParams (src/pore_model/nanopolish_poremodel.h:20-36). Uploaded once per model. */
+int nph_model_upload(nph_ctx* ctx, const double* level_mean, const double* level_stdv,
+                     const double* level_log_stdv, uint32_t n_states, uint32_t k,
+                     uint32_t alphabet_size, uint32_t* model_id_out);
+
+/* ---- profile_hmm_score ------------------------------------------------------------------
+ * One-shot form, host buffers in, host scores out (synchronous):
+ *   scores_out[j] == profile_hmm_score(sequence_j, data_j, flags_j)   for j in [0, n_jobs)
+ * with hmm_indel_bias_factor (src/hmm/nanopolish_profile_hmm_r9.cpp:19) == indel_bias.
+ * A job with event range or k-mer count the reference would assert on yields NPH_ERR_INVALID. */
+int nph_hmm_score_batch(nph_ctx* ctx,
+                        const nph_read* reads, size_t n_reads,
+                        const float* ev_mean, const double* ev_start_time, size_t n_events_total,
+                        const uint32_t* kmer_ranks, size_t n_ranks_total,
+                        const nph_hmm_job* jobs, size_t n_jobs,
+                        double indel_bias, float* scores_out);
+
+/* Staged form of the same computation, for callers that keep a batch resident in HBM
+ * (bench.py's device-resident timing, multi-GPU shards, repeated scoring with new jobs):
+ *   nph_reads_load   : H2D of events + scalings, then the per-read device prologue
+ *                      (drift-scaled levels get_drift_scaled_level, squiggle_read.h:149-154;
+ *                       transitions calculate_transitions, profile_hmm_r9.inl:17-76)
+ *   nph_hmm_jobs_load: H2D of ranks + jobs, scheduling order
+ *   nph_hmm_score    : launches the forward kernel(s) on the context's stream (asynchronous);
+ *                      scores go to scores_dev if non-NULL (device pointer, n_jobs floats)
+ *                      else to an internal device buffer
+ *   nph_hmm_scores_fetch: D2H of the internal score buffer + stream sync                    */
+int nph_reads_load(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
+                   const float* ev_mean, const double* ev_start_time, size_t n_events_total);
+int nph_hmm_jobs_load(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_total,
+                      const nph_hmm_job* jobs, size_t n_jobs, double indel_bias);
+int nph_hmm_score(nph_ctx* ctx, float* scores_dev);
+int nph_hmm_scores_fetch(nph_ctx* ctx, float* scores_out, size_t n_jobs);
+
+/* profile_hmm_score_set (ref: src/hmm/nanopolish_profile_hmm.cpp:32-56): combine the per-sequence
+ * scores of each group of n_alt consecutive jobs, host side, in double through the table logsum:
+ *   out[g] = (+)_i ( scores[g*n_alt + i] - log(n_alt) ).  Pure host arithmetic on fetched scores. */
+int nph_score_set_combine(const float* scores, size_t n_groups, uint32_t n_alt, float* out);
+
+/* ---- adaptive_banded_simple_event_align -------------------------------------------------
+ * One-shot, host buffers (synchronous). pairs_out receives, for job j, results[j].n_pairs
+ * AlignedPairs at pairs_out + jobs[j].pairs_off in the reference's order (ascending). */
+int nph_abea_batch(nph_ctx* ctx,
+                   const nph_read* reads, size_t n_reads,
+                   const float* ev_mean, const double* ev_start_time, size_t n_events_total,
+                   const uint32_t* kmer_ranks, size_t n_ranks_total,
+                   const nph_abea_job* jobs, size_t n_jobs, uint32_t model_id,
+                   nph_aligned_pair* pairs_out, size_t pairs_total, nph_abea_result* results);
+/* Staged form (reads via nph_reads_load). */
+int nph_abea_jobs_load(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_total,
+                       const nph_abea_job* jobs, size_t n_jobs, uint32_t model_id, size_t pairs_total);
+int nph_abea_run(nph_ctx* ctx);
+int nph_abea_fetch(nph_ctx* ctx, nph_aligned_pair* pairs_out, size_t pairs_total,
+                   nph_abea_result* results, size_t n_jobs);
+
+/* estimate_scalings_using_mom for each job's read/sequence: out[j] = {shift, scale} (drift 0, var 1). */
+int nph_mom_batch(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
+                  const float* ev_mean, size_t n_events_total,
+                  const uint32_t* kmer_ranks, size_t n_ranks_total,
+                  const nph_abea_job* jobs, size_t n_jobs, uint32_t model_id, double* shift_scale_out);
+
+/* ---- profile_hmm_align (Viterbi; section 8f N1) ------------------------------------------ */
+int nph_hmm_align_batch(nph_ctx* ctx,
+                        const nph_read* reads, size_t n_reads,
+                        const float* ev_mean, const double* ev_start_time, size_t n_events_total,
+                        const uint32_t* kmer_ranks, size_t n_ranks_total,
+                        const nph_hmm_job* jobs, size_t n_jobs, double indel_bias,
+                        nph_align_state* states_out, const uint64_t* states_off,
+                        uint32_t* n_states_out, float* scores_out);
+
+/* ---- measurement hooks (used by bench.py; not part of the reference surface) ------------- */
+/* Device time in ms of the most recent nph_hmm_score / nph_abea_run kernel sequence, measured
+ * with CUDA events on the context's stream (valid after a sync), and the number of kernel
+ * launches it issued. */
+int nph_last_kernel_ms(nph_ctx* ctx, float* ms_out, int* launches_out);
+/* Pinned host memory helpers so callers can stage H2D/D2H at full PCIe speed. */
+int nph_host_alloc(void** ptr_out, size_t bytes);
+int nph_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPH_H */

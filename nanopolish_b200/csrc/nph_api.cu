@@ -1,0 +1,443 @@
+// nph_api.cu — the C ABI of libnph.so (include/nph.h): context, uploads, scheduling, fetches.
+// All device work is launched from here; there is no CPU implementation of any entry point.
+#include "nph_internal.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+int nph_set_cuda_error(nph_ctx* ctx, cudaError_t e, const char* what)
+{
+    if (ctx) {
+        ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    }
+    if (e == cudaErrorMemoryAllocation) return NPH_ERR_NOMEM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return NPH_ERR_NO_DEVICE;
+    return NPH_ERR_CUDA;
+}
+
+template <typename T>
+int nph_reserve(nph_ctx* ctx, DevBuf<T>& b, size_t n)
+{
+    if (n <= b.cap && b.p) return NPH_OK;
+    if (b.p) { NPH_CUDA(ctx, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = n + n / 8 + 16;
+    NPH_CUDA(ctx, cudaMalloc((void**)&b.p, want * sizeof(T)));
+    b.cap = want;
+    return NPH_OK;
+}
+template int nph_reserve<float>(nph_ctx*, DevBuf<float>&, size_t);
+template int nph_reserve<double>(nph_ctx*, DevBuf<double>&, size_t);
+template int nph_reserve<uint32_t>(nph_ctx*, DevBuf<uint32_t>&, size_t);
+template int nph_reserve<uint8_t>(nph_ctx*, DevBuf<uint8_t>&, size_t);
+template int nph_reserve<DevRead>(nph_ctx*, DevBuf<DevRead>&, size_t);
+template int nph_reserve<DevModelView>(nph_ctx*, DevBuf<DevModelView>&, size_t);
+template int nph_reserve<nph_hmm_job>(nph_ctx*, DevBuf<nph_hmm_job>&, size_t);
+template int nph_reserve<float2>(nph_ctx*, DevBuf<float2>&, size_t);
+template int nph_reserve<nph_abea_job>(nph_ctx*, DevBuf<nph_abea_job>&, size_t);
+template int nph_reserve<nph_aligned_pair>(nph_ctx*, DevBuf<nph_aligned_pair>&, size_t);
+template int nph_reserve<nph_abea_result>(nph_ctx*, DevBuf<nph_abea_result>&, size_t);
+
+#define NPH_TRY(expr) do { int rc__ = (expr); if (rc__ != NPH_OK) return rc__; } while (0)
+
+namespace {
+
+template <typename T>
+void free_buf(DevBuf<T>& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+// clip-penalty table (see np_oracle.c:npo_flank_table for the derivation; ref profile_hmm_r9.inl:200-260)
+int ensure_flank(nph_ctx* ctx, size_t n)
+{
+    if (ctx->h_flank.size() >= n && ctx->d_flank.p) return NPH_OK;
+    size_t want = std::max<size_t>(n + n / 2, 4096);
+    std::vector<float>& f = ctx->h_flank;
+    f.resize(want);
+    const double start_to_clip = 0.5, clip_self = 0.9;
+    const float bg = -3.0f;
+    f[0] = (float)log(1 - start_to_clip);
+    f[1] = (float)(log(start_to_clip) + bg + log(1 - clip_self));
+    for (size_t i = 2; i < want; ++i) f[i] = (float)(log(clip_self) + bg + f[i - 1]);
+    NPH_TRY(nph_reserve(ctx, ctx->d_flank, want));
+    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_flank.p, f.data(), want * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    return NPH_OK;
+}
+
+// calculate_transitions (ref: profile_hmm_r9.inl:17-76).  The reference evaluates log() on float
+// probabilities in C++, i.e. std::log(float) == logf of the host libm; we call the same function so
+// the values are the ones the reference would use on this machine.
+void const_transitions(HmmConsts& c)
+{
+    float p_skip = 0.0025;
+    float p_bad = 0.001;
+    float p_bad_self = p_bad;
+    float p_skip_self = 0.3;
+    float p_third = (1.0f - p_bad_self) / 3;
+    float p_km = 1.0f - p_skip_self;
+    c.lp_mk = logf(p_skip);
+    c.lp_mb = logf(p_bad);
+    c.lp_bb = logf(p_bad_self);
+    c.lp_bk = logf(p_third);
+    c.lp_bm_next = logf(p_third);
+    c.lp_bm_self = logf(p_third);
+    c.lp_kk = logf(p_skip_self);
+    c.lp_km = logf(p_km);
+    c.log_inv_sqrt_2pi = (float)log(0.3989422804014327);
+}
+
+inline float2 read_transitions(double events_per_base, double indel_bias)
+{
+    double epb = events_per_base * indel_bias;
+    epb = std::max(1.25, epb);
+    float p_stay = (float)(1 - (1 / epb));
+    float p_skip = 0.0025;
+    float p_bad = 0.001;
+    float p_mm_next = 1.0f - p_stay - p_skip - p_bad;
+    return make_float2(logf(p_stay), logf(p_mm_next));
+}
+
+// Which kernel class (columns per lane) runs a job: minimise modelled steps x work per step.
+inline int choose_cols(uint32_t K, uint32_t E)
+{
+    static const int cand[] = {1, 2, 3, 4, 5, 6, 8};
+    double best = 1e300;
+    int best_c = 1;
+    for (int C : cand) {
+        uint32_t strip = 32u * C;
+        uint32_t n_strips = (K + strip - 1) / strip;
+        uint32_t P = n_strips > 1 ? std::max<uint32_t>(E, 40) : E;
+        uint32_t last_cols = K - (n_strips - 1) * strip;
+        uint32_t end_lane = (last_cols - 1) / C;
+        double steps = (double)(n_strips - 1) * P + E + end_lane;
+        double cost = steps * (C + 0.6);
+        if (cost < best) { best = cost; best_c = C; }
+    }
+    return best_c;
+}
+
+int class_index(int C)
+{
+    switch (C) { case 1: return 0; case 2: return 1; case 3: return 2; case 4: return 3; case 5: return 4; case 6: return 5; case 8: return 6; }
+    return -1;
+}
+const int kClassCols[] = {1, 2, 3, 4, 5, 6, 8};
+const int kNumClasses = 7;
+
+int create_common(nph_ctx** out, int device, bool own_stream, cudaStream_t stream)
+{
+    if (!out) return NPH_ERR_INVALID;
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev <= 0) return NPH_ERR_NO_DEVICE;
+    if (device < 0 || device >= n_dev) return NPH_ERR_INVALID;
+    nph_ctx* ctx = new (std::nothrow) nph_ctx();
+    if (!ctx) return NPH_ERR_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return NPH_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return NPH_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (own_stream) {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return NPH_ERR_CUDA; }
+        ctx->own_stream = true;
+    } else {
+        ctx->stream = stream;
+    }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+
+    // quantised log-sum table, built exactly like p7_FLogsumInit (ref: src/common/logsum.cpp:57-69)
+    std::vector<float> tbl(NPH_TBL_SMEM);
+    for (int i = 0; i < NPH_LOGSUM_CUT; ++i) tbl[i] = (float)log(1. + exp((double)-i / 1000.f));
+    tbl[NPH_LOGSUM_CUT] = 0.0f;
+    if (cudaMalloc((void**)&ctx->d_logsum, sizeof(float) * NPH_TBL_SMEM) != cudaSuccess) { delete ctx; return NPH_ERR_NOMEM; }
+    cudaMemcpy(ctx->d_logsum, tbl.data(), sizeof(float) * NPH_TBL_SMEM, cudaMemcpyHostToDevice);
+    const_transitions(ctx->consts);
+    if (nph_reserve(ctx, ctx->d_counters, 16) != NPH_OK) { delete ctx; return NPH_ERR_NOMEM; }
+    if (ensure_flank(ctx, 4096) != NPH_OK) { delete ctx; return NPH_ERR_CUDA; }
+    *out = ctx;
+    return NPH_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int nph_version(void) { return NPH_VERSION_MAJOR * 1000 + NPH_VERSION_MINOR; }
+
+const char* nph_strerror(int status)
+{
+    switch (status) {
+        case NPH_OK: return "ok";
+        case NPH_ERR_NO_DEVICE: return "no usable CUDA device (libnph has no CPU path)";
+        case NPH_ERR_CUDA: return "CUDA runtime error (see nph_last_error)";
+        case NPH_ERR_INVALID: return "invalid argument";
+        case NPH_ERR_NOMEM: return "out of memory";
+        case NPH_ERR_STATE: return "call sequence error";
+        case NPH_ERR_UNSUPPORTED: return "unsupported shape";
+    }
+    return "unknown status";
+}
+
+const char* nph_last_error(const nph_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int nph_create(nph_ctx** ctx_out, int device) { return create_common(ctx_out, device, true, nullptr); }
+int nph_create_on_stream(nph_ctx** ctx_out, int device, void* cuda_stream)
+{
+    return create_common(ctx_out, device, false, (cudaStream_t)cuda_stream);
+}
+
+int nph_destroy(nph_ctx* ctx)
+{
+    if (!ctx) return NPH_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_logsum) cudaFree(ctx->d_logsum);
+    free_buf(ctx->d_flank); free_buf(ctx->d_models); free_buf(ctx->d_reads); free_buf(ctx->d_ev_mean);
+    free_buf(ctx->d_ev_time); free_buf(ctx->d_level); free_buf(ctx->d_drift); free_buf(ctx->d_ranks);
+    free_buf(ctx->d_jobs); free_buf(ctx->d_trans); free_buf(ctx->d_order); free_buf(ctx->d_scores);
+    free_buf(ctx->d_counters); free_buf(ctx->d_scratch); free_buf(ctx->d_abea_jobs); free_buf(ctx->d_abea_ranks);
+    free_buf(ctx->d_pairs); free_buf(ctx->d_abea_res); free_buf(ctx->d_abea_scratch); free_buf(ctx->d_abea_order);
+    for (auto& m : ctx->models) { cudaFree(m.mean); cudaFree(m.stdv); cudaFree(m.log_stdv); }
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    delete ctx;
+    return NPH_OK;
+}
+
+int nph_sync(nph_ctx* ctx)
+{
+    if (!ctx) return NPH_ERR_INVALID;
+    NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NPH_OK;
+}
+
+void* nph_stream(nph_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int nph_model_upload(nph_ctx* ctx, const double* level_mean, const double* level_stdv,
+                     const double* level_log_stdv, uint32_t n_states, uint32_t k,
+                     uint32_t alphabet_size, uint32_t* model_id_out)
+{
+    if (!ctx || !level_mean || !level_stdv || !level_log_stdv || !model_id_out || n_states == 0) return NPH_ERR_INVALID;
+    uint64_t expect = 1;
+    for (uint32_t i = 0; i < k; ++i) expect *= alphabet_size;
+    if (expect != n_states) return NPH_ERR_INVALID;   // ref asserts states.size() == alphabet^k (profile_hmm_r9.inl:305)
+    NPH_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevModel m;
+    const size_t bytes = sizeof(double) * n_states;
+    NPH_CUDA(ctx, cudaMalloc((void**)&m.mean, bytes));
+    NPH_CUDA(ctx, cudaMalloc((void**)&m.stdv, bytes));
+    NPH_CUDA(ctx, cudaMalloc((void**)&m.log_stdv, bytes));
+    NPH_CUDA(ctx, cudaMemcpyAsync(m.mean, level_mean, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(m.stdv, level_stdv, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(m.log_stdv, level_log_stdv, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    m.n_states = n_states; m.k = k; m.alphabet_size = alphabet_size;
+    ctx->models.push_back(m);
+    std::vector<DevModelView> views(ctx->models.size());
+    for (size_t i = 0; i < views.size(); ++i)
+        views[i] = DevModelView{ctx->models[i].mean, ctx->models[i].stdv, ctx->models[i].log_stdv, ctx->models[i].n_states, 0};
+    NPH_TRY(nph_reserve(ctx, ctx->d_models, views.size()));
+    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_models.p, views.data(), sizeof(DevModelView) * views.size(), cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *model_id_out = (uint32_t)ctx->models.size() - 1;
+    return NPH_OK;
+}
+
+int nph_reads_load(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
+                   const float* ev_mean, const double* ev_start_time, size_t n_events_total)
+{
+    if (!ctx || !reads || !ev_mean || n_reads == 0) return NPH_ERR_INVALID;
+    NPH_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<DevRead> hr(n_reads);
+    std::vector<double> hd(n_reads);
+    ctx->h_events_per_base.resize(n_reads);
+    ctx->h_read_n_events.resize(n_reads);
+    bool any_drift = false;
+    for (size_t i = 0; i < n_reads; ++i) {
+        const nph_read& r = reads[i];
+        if (r.n_events == 0 || r.event_off + r.n_events > n_events_total) return NPH_ERR_INVALID;
+        hr[i].event_off = r.event_off; hr[i].n_events = r.n_events; hr[i].pad = 0;
+        hr[i].scale = r.scale; hr[i].shift = r.shift; hr[i].var = r.var; hr[i].log_var = r.log_var;
+        hd[i] = r.drift;
+        any_drift |= (r.drift != 0.0);
+        ctx->h_events_per_base[i] = r.events_per_base;
+        ctx->h_read_n_events[i] = r.n_events;
+    }
+    if (any_drift && !ev_start_time) return NPH_ERR_INVALID;
+    NPH_TRY(nph_reserve(ctx, ctx->d_reads, n_reads));
+    NPH_TRY(nph_reserve(ctx, ctx->d_drift, n_reads));
+    NPH_TRY(nph_reserve(ctx, ctx->d_ev_mean, n_events_total));
+    NPH_TRY(nph_reserve(ctx, ctx->d_level, n_events_total));
+    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_reads.p, hr.data(), sizeof(DevRead) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_drift.p, hd.data(), sizeof(double) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ev_mean.p, ev_mean, sizeof(float) * n_events_total, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n_reads = n_reads;
+    ctx->n_events_total = n_events_total;
+    if (any_drift) {
+        NPH_TRY(nph_reserve(ctx, ctx->d_ev_time, n_events_total));
+        NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ev_time.p, ev_start_time, sizeof(double) * n_events_total, cudaMemcpyHostToDevice, ctx->stream));
+        NPH_TRY(nph_launch_read_prologue(ctx));
+    } else {
+        // drift == 0 for every read: level - time*0.0 narrows back to level exactly, so the
+        // drift-scaled level IS the event mean and the start times need not cross PCIe at all.
+        NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_level.p, ctx->d_ev_mean.p, sizeof(float) * n_events_total, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    // the host staging vectors above must outlive the async copies
+    NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->reads_loaded = true;
+    ctx->jobs_loaded = false;
+    ctx->abea_loaded = false;
+    return NPH_OK;
+}
+
+int nph_hmm_jobs_load(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_total,
+                      const nph_hmm_job* jobs, size_t n_jobs, double indel_bias)
+{
+    if (!ctx || !kmer_ranks || !jobs || n_jobs == 0) return NPH_ERR_INVALID;
+    if (!ctx->reads_loaded) return NPH_ERR_STATE;
+    NPH_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    // validate + classify + schedule (heaviest first inside each class, by coarse cost buckets)
+    std::vector<uint8_t> cls(n_jobs);
+    std::vector<uint32_t> bucket(n_jobs);
+    uint32_t max_kpad = 32, max_period = 40, max_E = 1;
+    constexpr int kBuckets = 64;
+    std::vector<size_t> hist((size_t)kNumClasses * kBuckets, 0);
+    for (size_t j = 0; j < n_jobs; ++j) {
+        const nph_hmm_job& jb = jobs[j];
+        if (jb.read >= ctx->n_reads || jb.model_id >= ctx->models.size() || jb.n_kmers == 0) return NPH_ERR_INVALID;
+        if (jb.rank_off + jb.n_kmers > n_ranks_total) return NPH_ERR_INVALID;
+        const uint32_t ne = ctx->h_read_n_events[jb.read];
+        if (jb.event_start >= ne || jb.event_stop >= ne) return NPH_ERR_INVALID;
+        if (jb.stride != 1 && jb.stride != -1) return NPH_ERR_INVALID;
+        if ((jb.event_stop > jb.event_start && jb.stride != 1) || (jb.event_stop < jb.event_start && jb.stride != -1)) return NPH_ERR_INVALID;
+        const uint32_t E = (jb.event_stop > jb.event_start ? jb.event_stop - jb.event_start : jb.event_start - jb.event_stop) + 1;
+        const uint32_t K = jb.n_kmers;
+        const int C = choose_cols(K, E);
+        const int ci = class_index(C);
+        cls[j] = (uint8_t)ci;
+        const uint32_t strip = 32u * C;
+        const uint32_t n_strips = (K + strip - 1) / strip;
+        max_kpad = std::max(max_kpad, n_strips * strip);
+        max_period = std::max(max_period, std::max<uint32_t>(E, 40));
+        max_E = std::max(max_E, E);
+        // cost bucket: log2 of block-cells, 64 buckets, larger first
+        const double cells = (double)E * K;
+        int b = (int)(log2(cells + 1.0) * 1.6);
+        b = std::min(kBuckets - 1, std::max(0, b));
+        bucket[j] = (uint32_t)(kBuckets - 1 - b);
+        hist[(size_t)ci * kBuckets + bucket[j]]++;
+    }
+    std::vector<size_t> start((size_t)kNumClasses * kBuckets);
+    size_t acc = 0;
+    ctx->classes.clear();
+    for (int ci = 0; ci < kNumClasses; ++ci) {
+        size_t first = acc;
+        for (int b = 0; b < kBuckets; ++b) { start[(size_t)ci * kBuckets + b] = acc; acc += hist[(size_t)ci * kBuckets + b]; }
+        ctx->classes.push_back(nph_ctx::ClassLaunch{kClassCols[ci], 32, first, acc - first});
+    }
+    std::vector<uint32_t> order(n_jobs);
+    for (size_t j = 0; j < n_jobs; ++j) order[start[(size_t)cls[j] * kBuckets + bucket[j]]++] = (uint32_t)j;
+
+    std::vector<float2> trans(ctx->n_reads);
+    for (size_t i = 0; i < ctx->n_reads; ++i) trans[i] = read_transitions(ctx->h_events_per_base[i], indel_bias);
+
+    ctx->max_kpad = max_kpad;
+    ctx->max_period = max_period;
+    NPH_TRY(ensure_flank(ctx, (size_t)max_E + 2));
+    NPH_TRY(nph_reserve(ctx, ctx->d_ranks, n_ranks_total));
+    NPH_TRY(nph_reserve(ctx, ctx->d_jobs, n_jobs));
+    NPH_TRY(nph_reserve(ctx, ctx->d_order, n_jobs));
+    NPH_TRY(nph_reserve(ctx, ctx->d_trans, ctx->n_reads));
+    NPH_TRY(nph_reserve(ctx, ctx->d_scores, n_jobs));
+    NPH_TRY(nph_reserve(ctx, ctx->d_scratch, nph_hmm_scratch_bytes(ctx, nullptr)));
+    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ranks.p, kmer_ranks, sizeof(uint32_t) * n_ranks_total, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_jobs.p, jobs, sizeof(nph_hmm_job) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_order.p, order.data(), sizeof(uint32_t) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_trans.p, trans.data(), sizeof(float2) * ctx->n_reads, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_jobs = n_jobs;
+    ctx->n_ranks = n_ranks_total;
+    ctx->jobs_loaded = true;
+    return NPH_OK;
+}
+
+int nph_hmm_score(nph_ctx* ctx, float* scores_dev)
+{
+    if (!ctx) return NPH_ERR_INVALID;
+    if (!ctx->reads_loaded || !ctx->jobs_loaded) return NPH_ERR_STATE;
+    NPH_CUDA(ctx, cudaSetDevice(ctx->device));
+    return nph_launch_hmm_forward(ctx, scores_dev);
+}
+
+int nph_hmm_scores_fetch(nph_ctx* ctx, float* scores_out, size_t n_jobs)
+{
+    if (!ctx || !scores_out) return NPH_ERR_INVALID;
+    if (!ctx->jobs_loaded || n_jobs > ctx->n_jobs) return NPH_ERR_STATE;
+    NPH_CUDA(ctx, cudaMemcpyAsync(scores_out, ctx->d_scores.p, sizeof(float) * n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
+    NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NPH_OK;
+}
+
+int nph_hmm_score_batch(nph_ctx* ctx,
+                        const nph_read* reads, size_t n_reads,
+                        const float* ev_mean, const double* ev_start_time, size_t n_events_total,
+                        const uint32_t* kmer_ranks, size_t n_ranks_total,
+                        const nph_hmm_job* jobs, size_t n_jobs,
+                        double indel_bias, float* scores_out)
+{
+    NPH_TRY(nph_reads_load(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total));
+    NPH_TRY(nph_hmm_jobs_load(ctx, kmer_ranks, n_ranks_total, jobs, n_jobs, indel_bias));
+    NPH_TRY(nph_hmm_score(ctx, nullptr));
+    return nph_hmm_scores_fetch(ctx, scores_out, n_jobs);
+}
+
+// profile_hmm_score_set's combination step (ref: src/hmm/nanopolish_profile_hmm.cpp:32-56): host
+// arithmetic on already-computed scores, in double through the quantised table logsum.
+int nph_score_set_combine(const float* scores, size_t n_groups, uint32_t n_alt, float* out)
+{
+    if (!scores || !out || n_alt == 0) return NPH_ERR_INVALID;
+    static float tbl[NPH_LOGSUM_TBL];
+    static bool init = false;
+    if (!init) { for (int i = 0; i < NPH_LOGSUM_TBL; ++i) tbl[i] = (float)log(1. + exp((double)-i / 1000.f)); init = true; }
+    const double pen = log((double)n_alt);
+    for (size_t g = 0; g < n_groups; ++g) {
+        double score = scores[g * n_alt] - pen;
+        for (uint32_t i = 1; i < n_alt; ++i) {
+            const double alt = scores[g * n_alt + i] - pen;
+            const float a = (float)score, b = (float)alt;
+            const float mx = a > b ? a : b, mn = a < b ? a : b;
+            score = (mn == -INFINITY || (mx - mn) >= 15.7f) ? mx : mx + tbl[(int)((mx - mn) * 1000.f)];
+        }
+        out[g] = (float)score;
+    }
+    return NPH_OK;
+}
+
+int nph_last_kernel_ms(nph_ctx* ctx, float* ms_out, int* launches_out)
+{
+    if (!ctx || !ms_out) return NPH_ERR_INVALID;
+    if (!ctx->timing_valid) return NPH_ERR_STATE;
+    NPH_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    NPH_CUDA(ctx, cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+    if (launches_out) *launches_out = ctx->last_launches;
+    return NPH_OK;
+}
+
+int nph_host_alloc(void** ptr_out, size_t bytes)
+{
+    if (!ptr_out) return NPH_ERR_INVALID;
+    cudaError_t e = cudaMallocHost(ptr_out, bytes);
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? NPH_ERR_NOMEM : NPH_ERR_NO_DEVICE;
+    return NPH_OK;
+}
+
+int nph_host_free(void* ptr)
+{
+    return cudaFreeHost(ptr) == cudaSuccess ? NPH_OK : NPH_ERR_CUDA;
+}
+
+} // extern "C"

@@ -1,0 +1,119 @@
+// nph_internal.cuh — shared declarations of libnph.so (not installed; the public surface is include/nph.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include "../../include/nph.h"
+
+#define NPH_LOGSUM_TBL 16000        // ref: p7_LOGSUM_TBL, src/common/logsum.h:20
+#define NPH_LOGSUM_CUT 15700        // (max-min) >= 15.7f returns max: entries >= 15700 are never read
+#define NPH_TBL_SMEM   (NPH_LOGSUM_CUT + 1)   // +1: a zero entry that the clamped index lands on
+
+// Per-read record on the device (what the kernels need of nph_read after the prologue).
+struct DevRead {
+    uint64_t event_off;
+    uint32_t n_events;
+    uint32_t pad;
+    double scale, shift, var, log_var;
+};
+
+// The eight read-independent transition log-probabilities + Gaussian constant, computed on the host
+// with libm exactly as the reference does (logf of float probabilities).
+struct HmmConsts {
+    float lp_mk, lp_mb, lp_bb, lp_bk, lp_bm_next, lp_bm_self, lp_kk, lp_km;
+    float log_inv_sqrt_2pi;
+};
+
+struct DevModel {
+    double* mean = nullptr;
+    double* stdv = nullptr;
+    double* log_stdv = nullptr;
+    uint32_t n_states = 0, k = 0, alphabet_size = 0;
+};
+
+// Device-side view of the models for kernels (array of pointers)
+struct DevModelView { const double* mean; const double* stdv; const double* log_stdv; uint32_t n_states; uint32_t pad; };
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+};
+
+struct nph_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    std::string last_error;
+
+    // constant tables
+    float* d_logsum = nullptr;       // NPH_TBL_SMEM floats
+    DevBuf<float> d_flank;           // clip-penalty table, grown on demand
+    std::vector<float> h_flank;
+    HmmConsts consts;
+
+    // models
+    std::vector<DevModel> models;
+    DevBuf<DevModelView> d_models;
+
+    // resident reads
+    size_t n_reads = 0, n_events_total = 0;
+    DevBuf<DevRead> d_reads;
+    DevBuf<float> d_ev_mean;
+    DevBuf<double> d_ev_time;
+    DevBuf<float> d_level;           // drift-scaled levels
+    DevBuf<double> d_drift;          // per read SquiggleScalings::drift (consumed by the read prologue)
+    std::vector<double> h_events_per_base;
+    std::vector<uint32_t> h_read_n_events;
+    bool reads_loaded = false;
+
+    // resident HMM jobs
+    size_t n_jobs = 0, n_ranks = 0;
+    DevBuf<uint32_t> d_ranks;
+    DevBuf<nph_hmm_job> d_jobs;
+    DevBuf<float2> d_trans;          // per read: (lp_mm_self, lp_mm_next)
+    DevBuf<uint32_t> d_order;        // job indices grouped by kernel class, heavy first
+    DevBuf<float> d_scores;
+    DevBuf<unsigned int> d_counters;
+    DevBuf<uint8_t> d_scratch;
+    struct ClassLaunch { int cols_per_lane; int group_width; size_t first; size_t count; };
+    std::vector<ClassLaunch> classes;
+    uint32_t max_kpad = 0, max_period = 0;
+    bool jobs_loaded = false;
+
+    // resident ABEA jobs
+    size_t n_abea_jobs = 0, abea_pairs_total = 0;
+    uint32_t abea_model = 0;
+    DevBuf<nph_abea_job> d_abea_jobs;
+    DevBuf<uint32_t> d_abea_ranks;
+    DevBuf<nph_aligned_pair> d_pairs;
+    DevBuf<nph_abea_result> d_abea_res;
+    DevBuf<uint8_t> d_abea_scratch;
+    DevBuf<uint32_t> d_abea_order;
+    std::vector<uint64_t> h_abea_trace_off;
+    bool abea_loaded = false;
+
+    // measurement
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int last_launches = 0;
+    bool timing_valid = false;
+
+    // staging (pinned) buffers
+    void* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+};
+
+int nph_set_cuda_error(nph_ctx* ctx, cudaError_t e, const char* what);
+#define NPH_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return nph_set_cuda_error((ctx), e__, #call); } while (0)
+
+template <typename T>
+int nph_reserve(nph_ctx* ctx, DevBuf<T>& b, size_t n);
+
+// kernels (defined in hmm_forward.cu / abea.cu)
+int nph_launch_read_prologue(nph_ctx* ctx);
+int nph_launch_hmm_forward(nph_ctx* ctx, float* scores_dev);
+size_t nph_hmm_scratch_bytes(const nph_ctx* ctx, int* warps_total_out);
+int nph_launch_abea(nph_ctx* ctx);

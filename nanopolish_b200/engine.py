@@ -1,0 +1,146 @@
+"""Python driver over the C ABI (include/nph.h) — used by tests/, bench.py and smoke().
+
+The product is libnph.so; this wrapper only marshals numpy buffers (structured arrays with the
+layouts in synth.py) into the C calls.  It never computes a score itself and has no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .synth import ABEA_RES_DT, PAIR_DT
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One nph_ctx (one device, one stream)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = _lib.load()
+        self.ctx = C.c_void_p()
+        if stream is None:
+            rc = self.lib.nph_create(C.byref(self.ctx), device)
+        else:
+            rc = self.lib.nph_create_on_stream(C.byref(self.ctx), device, C.c_void_p(stream))
+        if rc != 0:
+            raise _lib.NphError(rc, "nph_create", self.lib.nph_strerror(rc).decode())
+        self.n_jobs = 0
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise _lib.NphError(rc, what, self.lib.nph_strerror(rc).decode() + " / " +
+                                self.lib.nph_last_error(self.ctx).decode())
+
+    def close(self):
+        if self.ctx:
+            self.lib.nph_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- models / reads / jobs ----------------------------------------------------------
+    def model_upload(self, model) -> int:
+        mid = C.c_uint32()
+        mean = np.ascontiguousarray(model.level_mean, np.float64)
+        sd = np.ascontiguousarray(model.level_stdv, np.float64)
+        lsd = np.ascontiguousarray(model.level_log_stdv, np.float64)
+        self._check(self.lib.nph_model_upload(self.ctx, _p(mean), _p(sd), _p(lsd), mean.shape[0], model.k,
+                                              model.alphabet_size, C.byref(mid)), "nph_model_upload")
+        return mid.value
+
+    def reads_load(self, reads, ev_mean, ev_start_time):
+        self._check(self.lib.nph_reads_load(self.ctx, _p(reads), reads.shape[0], _p(ev_mean),
+                                            _p(ev_start_time), ev_mean.shape[0]), "nph_reads_load")
+
+    def hmm_jobs_load(self, kmer_ranks, jobs, indel_bias: float = 1.0):
+        self._check(self.lib.nph_hmm_jobs_load(self.ctx, _p(kmer_ranks), kmer_ranks.shape[0], _p(jobs),
+                                               jobs.shape[0], indel_bias), "nph_hmm_jobs_load")
+        self.n_jobs = int(jobs.shape[0])
+
+    def hmm_score(self, scores_dev_ptr: int | None = None):
+        self._check(self.lib.nph_hmm_score(self.ctx, C.c_void_p(scores_dev_ptr) if scores_dev_ptr else None),
+                    "nph_hmm_score")
+
+    def hmm_scores_fetch(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.n_jobs, np.float32)
+        self._check(self.lib.nph_hmm_scores_fetch(self.ctx, _p(out), out.shape[0]), "nph_hmm_scores_fetch")
+        return out
+
+    def hmm_score_batch(self, reads, ev_mean, ev_start_time, kmer_ranks, jobs, indel_bias: float = 1.0,
+                        out: np.ndarray | None = None) -> np.ndarray:
+        """== [profile_hmm_score(seq_j, data_j, flags_j) for j]  through the one-shot C call."""
+        if out is None:
+            out = np.empty(jobs.shape[0], np.float32)
+        self._check(self.lib.nph_hmm_score_batch(self.ctx, _p(reads), reads.shape[0], _p(ev_mean),
+                                                 _p(ev_start_time), ev_mean.shape[0], _p(kmer_ranks),
+                                                 kmer_ranks.shape[0], _p(jobs), jobs.shape[0], indel_bias,
+                                                 _p(out)), "nph_hmm_score_batch")
+        self.n_jobs = int(jobs.shape[0])
+        return out
+
+    def score_set_combine(self, scores: np.ndarray, n_alt: int) -> np.ndarray:
+        s = np.ascontiguousarray(scores, np.float32)
+        g = s.shape[0] // n_alt
+        out = np.empty(g, np.float32)
+        self._check(self.lib.nph_score_set_combine(_p(s), g, n_alt, _p(out)), "nph_score_set_combine")
+        return out
+
+    # ---- ABEA ---------------------------------------------------------------------------
+    def abea_batch(self, reads, ev_mean, ev_start_time, kmer_ranks, jobs, model_id: int, pairs_total: int):
+        pairs = np.zeros(pairs_total, PAIR_DT)
+        res = np.zeros(jobs.shape[0], ABEA_RES_DT)
+        self._check(self.lib.nph_abea_batch(self.ctx, _p(reads), reads.shape[0], _p(ev_mean), _p(ev_start_time),
+                                            ev_mean.shape[0], _p(kmer_ranks), kmer_ranks.shape[0], _p(jobs),
+                                            jobs.shape[0], model_id, _p(pairs), pairs_total, _p(res)),
+                    "nph_abea_batch")
+        return pairs, res
+
+    def abea_jobs_load(self, kmer_ranks, jobs, model_id: int, pairs_total: int):
+        self._check(self.lib.nph_abea_jobs_load(self.ctx, _p(kmer_ranks), kmer_ranks.shape[0], _p(jobs),
+                                                jobs.shape[0], model_id, pairs_total), "nph_abea_jobs_load")
+        self._abea_n = int(jobs.shape[0])
+        self._abea_pairs = int(pairs_total)
+
+    def abea_run(self):
+        self._check(self.lib.nph_abea_run(self.ctx), "nph_abea_run")
+
+    def abea_fetch(self):
+        pairs = np.zeros(self._abea_pairs, PAIR_DT)
+        res = np.zeros(self._abea_n, ABEA_RES_DT)
+        self._check(self.lib.nph_abea_fetch(self.ctx, _p(pairs), self._abea_pairs, _p(res), self._abea_n),
+                    "nph_abea_fetch")
+        return pairs, res
+
+    def mom_batch(self, reads, ev_mean, kmer_ranks, jobs, model_id: int) -> np.ndarray:
+        out = np.zeros((jobs.shape[0], 2), np.float64)
+        self._check(self.lib.nph_mom_batch(self.ctx, _p(reads), reads.shape[0], _p(ev_mean), ev_mean.shape[0],
+                                           _p(kmer_ranks), kmer_ranks.shape[0], _p(jobs), jobs.shape[0],
+                                           model_id, _p(out)), "nph_mom_batch")
+        return out
+
+    # ---- measurement ----------------------------------------------------------------------
+    def sync(self):
+        self._check(self.lib.nph_sync(self.ctx), "nph_sync")
+
+    def last_kernel_ms(self):
+        ms, n = C.c_float(), C.c_int()
+        self._check(self.lib.nph_last_kernel_ms(self.ctx, C.byref(ms), C.byref(n)), "nph_last_kernel_ms")
+        return ms.value, n.value
+
+    def stream(self) -> int:
+        return int(self.lib.nph_stream(self.ctx) or 0)

@@ -1,0 +1,333 @@
+"""Deterministic synthetic R9.4 reads and job lists in the C-ABI layout (include/nph.h).
+
+Shapes follow SURVEY.md section 8(d): uniform ACGT sequence, 0-3 events per k-mer
+(mean ~1.7 events/base), event mean ~ N(scale*mu_kmer + shift, (var*sigma_kmer)^2),
+duration 0.002 s, per-read shift/scale/var jitter.  The same generator feeds the CUDA path,
+the oracle and the compiled reference, so every arm of a comparison sees identical bytes.
+
+Job builders mirror the callers of profile_hmm_score:
+  * scorereads_jobs   -> 500-event segments, flags 0   (ref: src/nanopolish_scorereads.cpp:116-203)
+  * methylation_jobs  -> one window per CpG group, both alleles over the cpg alphabet, flags PRE|POST
+                         (ref: src/basemods/nanopolish_basemods.cpp:322-417)
+  * abea_jobs         -> whole read vs its sequence (ref: src/nanopolish_squiggle_read.cpp:270)
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# ---- C-ABI PODs as numpy dtypes (must match include/nph.h) --------------------------------
+READ_DT = np.dtype([
+    ("event_off", "<u8"), ("n_events", "<u4"), ("reserved", "<u4"),
+    ("scale", "<f8"), ("shift", "<f8"), ("drift", "<f8"), ("var", "<f8"), ("log_var", "<f8"),
+    ("events_per_base", "<f8"),
+], align=True)
+HMM_JOB_DT = np.dtype([
+    ("rank_off", "<u8"), ("read", "<u4"), ("model_id", "<u4"), ("event_start", "<u4"),
+    ("event_stop", "<u4"), ("n_kmers", "<u4"), ("stride", "i1"), ("rc", "u1"), ("flags", "u1"),
+    ("reserved", "u1"),
+], align=True)
+ABEA_JOB_DT = np.dtype([
+    ("rank_off", "<u8"), ("pairs_off", "<u8"), ("read", "<u4"), ("n_kmers", "<u4"),
+    ("pairs_cap", "<u4"), ("reserved", "<u4"),
+], align=True)
+PAIR_DT = np.dtype([("ref_pos", "<i4"), ("read_pos", "<i4")], align=True)
+ABEA_RES_DT = np.dtype([
+    ("n_pairs", "<u4"), ("status", "<i4"), ("max_gap", "<i4"), ("n_aligned", "<u4"),
+    ("avg_log_emission", "<f8"),
+], align=True)
+assert READ_DT.itemsize == 64 and HMM_JOB_DT.itemsize == 32 and ABEA_JOB_DT.itemsize == 32
+assert PAIR_DT.itemsize == 8 and ABEA_RES_DT.itemsize == 24
+
+HAF_ALLOW_PRE_CLIP = 1
+HAF_ALLOW_POST_CLIP = 2
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+@dataclass
+class PoreModel:
+    """PoreModel::states as SoA (ref: src/pore_model/nanopolish_poremodel.h:20-36, 70-110)."""
+    name: str
+    k: int
+    alphabet: str            # "nucleotide" (ACGT) or "cpg" (ACGMT)
+    level_mean: np.ndarray   # f64[n_states]
+    level_stdv: np.ndarray
+    level_log_stdv: np.ndarray
+
+    @property
+    def alphabet_size(self) -> int:
+        return 4 if self.alphabet == "nucleotide" else 5
+
+    @property
+    def n_states(self) -> int:
+        return int(self.level_mean.shape[0])
+
+
+def synthetic_model(alphabet: str = "nucleotide", k: int = 6, seed: int = 7) -> PoreModel:
+    """A plausible random pore model (levels 60-125 pA, stdv 1.2-3.5) for runs without fixtures."""
+    a = 4 if alphabet == "nucleotide" else 5
+    rng = np.random.default_rng(seed + a)
+    n = a ** k
+    mean = rng.uniform(60.0, 125.0, n)
+    stdv = rng.uniform(1.2, 3.5, n)
+    return PoreModel(f"synthetic.{alphabet}.{k}mer", k, alphabet, mean, stdv, np.log(stdv))
+
+
+def load_model(alphabet: str = "nucleotide") -> PoreModel:
+    """The built-in r9.4_450bps 6-mer template table dumped from the compiled reference by
+    scripts/make_golden.py (tests/golden/r9.4_450bps.<alphabet>.6mer.template.npz); falls back to
+    synthetic_model() if the fixture is absent."""
+    path = os.path.join(_GOLDEN, f"r9.4_450bps.{alphabet}.6mer.template.npz")
+    if os.path.exists(path):
+        z = np.load(path)
+        return PoreModel(f"r9.4_450bps.{alphabet}.6mer.template", int(z["k"]), alphabet,
+                         z["level_mean"].astype(np.float64), z["level_stdv"].astype(np.float64),
+                         z["level_log_stdv"].astype(np.float64))
+    return synthetic_model(alphabet)
+
+
+# ---- k-mer ranks (numpy restatement for DNA / CpG strings already encoded as base codes) ----
+_DNA_CODE = np.full(256, 255, np.uint8)
+for _i, _c in enumerate(b"ACGT"):
+    _DNA_CODE[_c] = _i
+_CPG_CODE = np.full(256, 255, np.uint8)
+for _i, _c in enumerate(b"ACGMT"):
+    _CPG_CODE[_c] = _i
+
+
+def encode(seq: bytes | str, alphabet: str) -> np.ndarray:
+    b = np.frombuffer(seq.encode() if isinstance(seq, str) else seq, np.uint8)
+    codes = (_DNA_CODE if alphabet == "nucleotide" else _CPG_CODE)[b]
+    if (codes == 255).any():
+        raise ValueError("sequence has symbols outside the alphabet")
+    return codes
+
+
+def kmer_ranks_from_codes(codes: np.ndarray, k: int, asize: int) -> np.ndarray:
+    """rank of k-mer i = sum_j code[i+j] * asize^(k-1-j)  (ref: Alphabet::kmer_rank,
+    src/common/nanopolish_alphabet.h:78-89)."""
+    n = codes.shape[0] - k + 1
+    if n <= 0:
+        return np.zeros(0, np.uint32)
+    r = np.zeros(n, np.uint32)
+    for j in range(k):
+        r = r * np.uint32(asize) + codes[j:j + n].astype(np.uint32)
+    return r
+
+
+def dna_rc_kmer_ranks(codes: np.ndarray, k: int) -> np.ndarray:
+    """HMMInputSequence::_rc_kmer_rank for the plain DNA alphabet: rank of the reverse complement of
+    k-mer i (ref: src/hmm/nanopolish_hmm_input_sequence.h:88-91)."""
+    n = codes.shape[0] - k + 1
+    r = np.zeros(n, np.uint32)
+    for j in range(k):
+        r = r * np.uint32(4) + (3 - codes[k - 1 - j:k - 1 - j + n]).astype(np.uint32)
+    return r
+
+
+@dataclass
+class ReadSet:
+    reads: np.ndarray                 # READ_DT[n_reads]
+    ev_mean: np.ndarray               # f32[total events]
+    ev_start_time: np.ndarray         # f64[total events]
+    seq_codes: list                   # per read: u8 base codes (ACGT = 0..3) of the true sequence
+    ev_kmer: list                     # per read: i4[n_events] index of the k-mer that emitted each event
+    kmer_first_event: list = field(default_factory=list)  # per read: i4[n_kmers] first event >= that k-mer
+    k: int = 6
+
+    @property
+    def n_reads(self) -> int:
+        return int(self.reads.shape[0])
+
+    @property
+    def total_events(self) -> int:
+        return int(self.ev_mean.shape[0])
+
+
+def gen_reads(n_reads: int, n_events: int, model: PoreModel, seed: int = 42, drift: bool = False,
+              rng_scalings: bool = True, cpg_keep: float = 1.0) -> ReadSet:
+    """n_reads reads of ~n_events events each (exactly n_events: the sequence is extended until the
+    event budget is reached).  Events are emitted from `model` (nucleotide alphabet)."""
+    assert model.alphabet == "nucleotide"
+    k = model.k
+    reads = np.zeros(n_reads, READ_DT)
+    means, times, seqs, evk, kfe = [], [], [], [], []
+    off = 0
+    p_nev = np.array([0.03, 0.35, 0.45, 0.17])
+    for r in range(n_reads):
+        rng = np.random.default_rng(seed + r)
+        # enough k-mers to cover the budget with margin, then trim
+        nk_guess = int(n_events / 1.76 * 1.15) + 8
+        codes = rng.integers(0, 4, nk_guess + k - 1, dtype=np.uint8)
+        if cpg_keep < 1.0:
+            # CpG depletion: turn most CG into CA so motif groups are ~60 bp apart (cfg 3)
+            cg = np.flatnonzero((codes[:-1] == 1) & (codes[1:] == 2))
+            drop = cg[rng.random(cg.shape[0]) >= cpg_keep]
+            codes[drop + 1] = 0
+        nev = rng.choice(4, nk_guess, p=p_nev)
+        csum = np.cumsum(nev)
+        nk = int(np.searchsorted(csum, n_events, side="left")) + 1
+        nk = min(nk, nk_guess)
+        nev = nev[:nk].copy()
+        extra = int(nev.sum()) - n_events
+        if extra > 0:
+            nev[-1] -= extra
+        elif extra < 0:
+            nev[-1] += -extra
+        codes = codes[:nk + k - 1]
+        ranks = kmer_ranks_from_codes(codes, k, 4)
+        which = np.repeat(np.arange(nk, dtype=np.int32), nev)
+        E = which.shape[0]
+        if rng_scalings:
+            shift = rng.uniform(-5.0, 5.0)
+            scale = rng.uniform(0.9, 1.1)
+            var = rng.uniform(0.9, 1.3)
+        else:
+            shift, scale, var = 0.0, 1.0, 1.0
+        dr = rng.uniform(-0.002, 0.002) if drift else 0.0
+        t = (np.arange(E, dtype=np.float64) * 0.002) + rng.uniform(0.0, 100.0)
+        mu = scale * model.level_mean[ranks[which]] + shift + (t - t[0]) * dr
+        sd = var * model.level_stdv[ranks[which]]
+        m = (mu + sd * rng.standard_normal(E)).astype(np.float32)
+        reads[r]["event_off"] = off
+        reads[r]["n_events"] = E
+        reads[r]["scale"], reads[r]["shift"], reads[r]["drift"], reads[r]["var"] = scale, shift, dr, var
+        reads[r]["log_var"] = np.log(var)
+        reads[r]["events_per_base"] = E / float(nk)
+        first = np.searchsorted(which, np.arange(nk), side="left").astype(np.int32)
+        means.append(m); times.append(t); seqs.append(codes); evk.append(which); kfe.append(first)
+        off += E
+    return ReadSet(reads, np.concatenate(means), np.concatenate(times), seqs, evk, kfe, k)
+
+
+@dataclass
+class HmmJobs:
+    jobs: np.ndarray          # HMM_JOB_DT[n_jobs]
+    kmer_ranks: np.ndarray    # u4[total]
+    scored_events: int        # sum over jobs of DP rows (the metric's unit)
+    block_cells: int          # sum over jobs of E*K
+    seqs: list | None = None  # optional per-job sequence strings (bytes) for the reference harness
+
+
+def _finish_jobs(rows, ranks_list, seqs=None) -> HmmJobs:
+    jobs = np.zeros(len(rows), HMM_JOB_DT)
+    off = 0
+    ev = 0
+    cells = 0
+    for j, (read, model_id, e0, e1, rc, flags) in enumerate(rows):
+        nk = ranks_list[j].shape[0]
+        jobs[j] = (off, read, model_id, e0, e1, nk, 1 if e1 >= e0 else -1, rc, flags, 0)
+        off += nk
+        E = abs(int(e1) - int(e0)) + 1
+        ev += E
+        cells += E * nk
+    kr = np.concatenate(ranks_list).astype(np.uint32) if ranks_list else np.zeros(0, np.uint32)
+    return HmmJobs(jobs, kr, ev, cells, seqs)
+
+
+_CODE2DNA = np.frombuffer(b"ACGT", np.uint8)
+
+
+def scorereads_jobs(rs: ReadSet, events_per_segment: int = 500, model_id: int = 0, rc_every: int = 0,
+                    keep_seqs: bool = False) -> HmmJobs:
+    """500-event segments [i*seg, (i+1)*seg] for i >= 1 while (i+1)*seg < n_events - ... , sequence =
+    bases spanned by the true alignment of the two boundary events, flags 0
+    (ref: model_score, src/nanopolish_scorereads.cpp:116-203).  rc_every=n makes every n-th read a
+    reverse-strand job (events walked backwards, rc k-mer ranks) to cover stride -1."""
+    rows, ranks_list, seqs = [], [], []
+    k = rs.k
+    for r in range(rs.n_reads):
+        E = int(rs.reads[r]["n_events"])
+        which = rs.ev_kmer[r]
+        codes = rs.seq_codes[r]
+        rc = 1 if (rc_every and r % rc_every == rc_every - 1) else 0
+        s = events_per_segment
+        while s < E - events_per_segment:
+            e0, e1 = s, s + events_per_segment
+            k0, k1 = int(which[e0]), int(which[e1])
+            sub = codes[k0:k1 + k]           # bases of k-mers k0..k1
+            if sub.shape[0] > k:
+                if not rc:
+                    ranks_list.append(kmer_ranks_from_codes(sub, k, 4))
+                    rows.append((r, model_id, e0, e1, 0, 0))
+                    if keep_seqs:
+                        seqs.append(_CODE2DNA[sub].tobytes())
+                else:
+                    # reverse-strand read: the HMM sequence is the reverse complement of the bases the
+                    # events were emitted from; events are walked from e1 down to e0.
+                    rcsub = (3 - sub[::-1]).astype(np.uint8)
+                    ranks_list.append(dna_rc_kmer_ranks(rcsub, k))
+                    rows.append((r, model_id, e1, e0, 1, 0))
+                    if keep_seqs:
+                        seqs.append(_CODE2DNA[rcsub].tobytes())
+            s += events_per_segment
+    return _finish_jobs(rows, ranks_list, seqs if keep_seqs else None)
+
+
+def abea_jobs(rs: ReadSet) -> tuple[np.ndarray, np.ndarray, int]:
+    """One ABEA job per read over its full true sequence. Returns (jobs, kmer_ranks, pairs_total)."""
+    jobs = np.zeros(rs.n_reads, ABEA_JOB_DT)
+    ranks_list = []
+    roff = poff = 0
+    for r in range(rs.n_reads):
+        ranks = kmer_ranks_from_codes(rs.seq_codes[r], rs.k, 4)
+        nk = ranks.shape[0]
+        cap = int(rs.reads[r]["n_events"]) + nk
+        jobs[r] = (roff, poff, r, nk, cap, 0)
+        ranks_list.append(ranks)
+        roff += nk
+        poff += cap
+    return jobs, np.concatenate(ranks_list).astype(np.uint32), poff
+
+
+_CODE2CPG = np.frombuffer(b"ACGMT", np.uint8)
+_DNA2CPG = np.array([0, 1, 2, 4], np.uint8)       # A C G T -> ranks in "ACGMT"
+
+
+def methylation_jobs(rs: ReadSet, model_id: int = 0, min_separation: int = 10, min_flank: int = 10,
+                     max_span: int = 200, keep_seqs: bool = False, max_groups_per_read: int | None = None) -> HmmJobs:
+    """call-methylation windows on forward-strand reads: CG motif scan -> groups (sites <= 10 bp apart)
+    -> window = [first-10, last+10] -> two jobs per group (unmethylated, methylated), both over the
+    cpg alphabet (ACGMT, 5^6 states), flags PRE|POST clip.  Jobs 2g, 2g+1 are the u/m pair of group g.
+    (ref: calculate_methylation_for_read, src/basemods/nanopolish_basemods.cpp:238-457)"""
+    rows, ranks_list, seqs = [], [], []
+    k = rs.k
+    flags = HAF_ALLOW_PRE_CLIP | HAF_ALLOW_POST_CLIP
+    for r in range(rs.n_reads):
+        codes = rs.seq_codes[r]
+        nk = codes.shape[0] - k + 1
+        kfe = rs.kmer_first_event[r]
+        E = int(rs.reads[r]["n_events"])
+        sites = np.flatnonzero((codes[:-1] == 1) & (codes[1:] == 2))
+        if sites.shape[0] == 0:
+            continue
+        brk = np.flatnonzero(np.diff(sites) > min_separation) + 1
+        starts = np.concatenate([[0], brk]); ends = np.concatenate([brk, [sites.shape[0]]])
+        n_done = 0
+        for gs, ge in zip(starts, ends):
+            first, last = int(sites[gs]), int(sites[ge - 1])
+            sub_start, sub_end = first - min_flank, last + min_flank
+            span = last - first
+            if sub_start <= min_separation or span > max_span or sub_end >= codes.shape[0]:
+                continue
+            k_lo, k_hi = sub_start, min(sub_end, nk - 1)
+            e1, e2 = int(min(kfe[k_lo], E - 1)), int(min(kfe[k_hi], E - 1))
+            if abs(e2 - e1) <= 10:
+                continue
+            sub = codes[sub_start:sub_end + 1]
+            u = _DNA2CPG[sub]
+            m = u.copy()
+            cg = np.flatnonzero((sub[:-1] == 1) & (sub[1:] == 2))
+            m[cg] = 3                                    # Alphabet::methylate: CG -> MG
+            for arr in (u, m):
+                ranks_list.append(kmer_ranks_from_codes(arr, k, 5))
+                rows.append((r, model_id, e1, e2, 0, flags))
+                if keep_seqs:
+                    seqs.append(_CODE2CPG[arr].tobytes())
+            n_done += 1
+            if max_groups_per_read and n_done >= max_groups_per_read:
+                break
+    return _finish_jobs(rows, ranks_list, seqs if keep_seqs else None)

@@ -1,0 +1,526 @@
+/* np_oracle.c — TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C, CPU restatement of the reference algorithm of the hot path, written from the
+ * behaviour of the reference sources (cited per function, paths relative to /root/reference).
+ * It exists so that tests/ can check the CUDA path on a box that has no /root/reference, and so
+ * that the restatement itself can be pinned against the compiled reference (oracle/_ref) here.
+ *
+ * PARITY PIN: the reference's own unit tests hold no known-answer vector for
+ * profile_hmm_score_r9 / ABEA (the only HMM test is compiled out, src/test/nanopolish_test.cpp:389-455),
+ * so this file is pinned against OUTPUTS OF THE REFERENCE ITSELF RUN HERE: tests/test_oracle_vs_ref.py
+ * requires bit-identical floats and identical AlignedPair lists from oracle/_ref/libnpref.so, and
+ * tests/golden/ holds vectors generated from the compiled reference by scripts/make_golden.py.
+ * The pieces the reference's tests do pin (Gaussian pdf known answer, scalings, kmer_rank) are
+ * checked in tests/test_oracle_known_answers.py.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this.  The product (libnph.so) never does: it has no CPU path at all.
+ *
+ * Build: gcc -O2 -std=c99 -ffp-contract=off (no FMA contraction: the reference is built for
+ * baseline x86-64, which has no FMA, so every float op is a separately rounded IEEE op).
+ */
+#include "np_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Table-driven log-sum (HMMER's p7_FLogsum as vendored by the reference).
+ * ref: src/common/logsum.h:20-21 (16000 entries, scale 1000), :55-66 (lookup rule),
+ *      src/common/logsum.cpp:57-69 (table entry = log(1 + exp(-i/1000)) in double -> float).
+ * ---------------------------------------------------------------------------------------- */
+#define NPO_TBL 16000
+static float g_tbl[NPO_TBL];
+static int g_init = 0;
+
+void npo_init(void)
+{
+    if (g_init) return;
+    for (int i = 0; i < NPO_TBL; ++i)
+        g_tbl[i] = (float)log(1. + exp((double)-i / 1000.f));
+    g_init = 1;
+}
+
+void npo_logsum_table(float* out) { npo_init(); memcpy(out, g_tbl, sizeof(g_tbl)); }
+
+float npo_logsum(float a, float b)
+{
+    const float hi = a > b ? a : b;
+    const float lo = a < b ? a : b;
+    if (lo == -INFINITY || (hi - lo) >= 15.7f) return hi;
+    return hi + g_tbl[(int)((hi - lo) * 1000.f)];
+}
+
+/* add_logs takes doubles, narrows to float for the lookup, returns double
+ * (src/common/nanopolish_common.h:97-104).  Callers store the result in a float. */
+static inline float add_logs_f(float a, float b) { return (float)(double)npo_logsum((float)(double)a, (float)(double)b); }
+
+/* ------------------------------------------------------------------------------------------
+ * Emissions.  ref: src/hmm/nanopolish_emissions.h:43-68, src/nanopolish_squiggle_read.h:149-154,
+ * :168-171, :217-226.
+ * ---------------------------------------------------------------------------------------- */
+float npo_log_normal_pdf(float x, float mean, float stdv, float log_stdv)
+{
+    static const double inv_sqrt_2pi = 0.3989422804014327;
+    const float log_inv_sqrt_2pi = (float)log(inv_sqrt_2pi);
+    float a = (x - mean) / stdv;
+    return log_inv_sqrt_2pi - log_stdv + (-0.5f * a * a);
+}
+
+float npo_drift_scaled_level(const nph_read* read, const float* ev_mean, const double* ev_start_time, uint32_t event_idx)
+{
+    const float* m = ev_mean + read->event_off;
+    const double* t = ev_start_time + read->event_off;
+    float level = m[event_idx];
+    float time = (float)(t[event_idx] - t[0]);
+    return (float)(level - time * read->drift);   /* float - (float*double) : evaluated in double, narrowed */
+}
+
+static inline void scaled_gaussian(const nph_read* read, const npo_model* model, uint32_t rank,
+                                   float* mean, float* stdv, float* log_stdv)
+{
+    *mean = (float)(read->scale * model->level_mean[rank] + read->shift);
+    *stdv = (float)(model->level_stdv[rank] * read->var);
+    *log_stdv = (float)(model->level_log_stdv[rank] + read->log_var);
+}
+
+float npo_log_probability_match(const nph_read* read, const float* ev_mean, const double* ev_start_time,
+                                const npo_model* model, uint32_t rank, uint32_t event_idx)
+{
+    float level = npo_drift_scaled_level(read, ev_mean, ev_start_time, event_idx);
+    float gm, gs, gl;
+    scaled_gaussian(read, model, rank, &gm, &gs, &gl);
+    return npo_log_normal_pdf(level, gm, gs, gl);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Transitions.  ref: calculate_transitions, src/hmm/nanopolish_profile_hmm_r9.inl:17-76.
+ * Order of out10: mk, mb, mm_self, mm_next, bb, bk, bm_next, bm_self, kk, km.
+ * ---------------------------------------------------------------------------------------- */
+void npo_transitions(double events_per_base, double indel_bias, float out[10])
+{
+    double epb = events_per_base * indel_bias;
+    if (epb < 1.25) epb = 1.25;
+    float p_stay = (float)(1 - (1 / epb));
+    float p_skip = 0.0025;
+    float p_bad = 0.001;
+    float p_bad_self = p_bad;
+    float p_skip_self = 0.3;
+
+    float p_mk = p_skip, p_mb = p_bad, p_mm_self = p_stay;
+    float p_mm_next = 1.0f - p_mm_self - p_mk - p_mb;
+    float p_bb = p_bad_self;
+    float p_third = (1.0f - p_bb) / 3;
+    float p_kk = p_skip_self;
+    float p_km = 1.0f - p_kk;
+
+    /* The reference writes log(p) with a float argument in C++, which selects the float overload
+     * std::log(float) == logf, not the double log. */
+    out[0] = logf(p_mk);
+    out[1] = logf(p_mb);
+    out[2] = logf(p_mm_self);
+    out[3] = logf(p_mm_next);
+    out[4] = logf(p_bb);
+    out[5] = logf(p_third);   /* bk */
+    out[6] = logf(p_third);   /* bm_next */
+    out[7] = logf(p_third);   /* bm_self */
+    out[8] = logf(p_kk);
+    out[9] = logf(p_km);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Clip penalties.  ref: make_pre_flanking / make_post_flanking, profile_hmm_r9.inl:200-260,
+ * background emission -3.0f (emissions.h:98-103).  Because the background log-density is a
+ * constant, pre_flank[i] depends on i only and post_flank[i] == pre_flank[n-1-i]; one table serves both.
+ * ---------------------------------------------------------------------------------------- */
+void npo_flank_table(float* out, size_t n)
+{
+    const double start_to_clip = 0.5, clip_self = 0.9;
+    const float bg = -3.0f;
+    if (n > 0) out[0] = (float)log(1 - start_to_clip);
+    if (n > 1) out[1] = (float)(log(start_to_clip) + bg + log(1 - clip_self));
+    for (size_t i = 2; i < n; ++i)
+        out[i] = (float)(log(clip_self) + bg + out[i - 1]);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Forward fill.  ref: profile_hmm_score_r9 (src/hmm/nanopolish_profile_hmm_r9.cpp:35-65),
+ * profile_hmm_forward_initialize_r9 (:21-33), profile_hmm_fill_generic_r9
+ * (src/hmm/nanopolish_profile_hmm_r9.inl:265-433), ProfileHMMForwardOutputR9 (:79-127).
+ * Column layout: 3*block + {0: k-mer skip, 1: bad event, 2: match} (profile_hmm_r9.h:52-59).
+ * ---------------------------------------------------------------------------------------- */
+enum { ST_K = 0, ST_B = 1, ST_M = 2, NST = 3 };
+
+static float fold6(const float x[6])
+{
+    float s = x[0];
+    for (int i = 1; i < 6; ++i) s = add_logs_f(s, x[i]);
+    return s;
+}
+
+static float hmm_fill(const nph_read* reads, const float* ev_mean, const double* ev_start_time,
+                      const npo_model* models, const uint32_t* kmer_ranks, const nph_hmm_job* job,
+                      double indel_bias, float* fm, int viterbi, uint8_t* bm,
+                      uint32_t* end_row, uint32_t* end_col)
+{
+    const nph_read* read = &reads[job->read];
+    const npo_model* model = &models[job->model_id];
+    const uint32_t* ranks = kmer_ranks + job->rank_off;
+    const uint32_t n_kmers = job->n_kmers;
+    const uint32_t n_blocks = n_kmers + 2;
+    const uint32_t n_cols = NST * n_blocks;
+    const uint32_t e_start = job->event_start;
+    const uint32_t n_events = (job->event_stop > e_start ? job->event_stop - e_start : e_start - job->event_stop) + 1;
+    const uint32_t n_rows = n_events + 1;
+    const int stride = job->stride;
+    const uint32_t flags = job->flags;
+
+    /* initialise: row 0 and block 0 are -inf, the rest is zero-filled by the reference's
+     * allocate_matrix (memset) and then overwritten (nanopolish_matrix.h:35-44). */
+    for (size_t i = 0; i < (size_t)n_rows * n_cols; ++i) fm[i] = 0.0f;
+    for (uint32_t c = 0; c < n_cols; ++c) fm[c] = -INFINITY;
+    for (uint32_t r = 0; r < n_rows; ++r) {
+        fm[(size_t)r * n_cols + ST_K] = -INFINITY;
+        fm[(size_t)r * n_cols + ST_B] = -INFINITY;
+        fm[(size_t)r * n_cols + ST_M] = -INFINITY;
+    }
+
+    float t[10];
+    npo_transitions(read->events_per_base, indel_bias, t);
+    const float lp_mk = t[0], lp_mb = t[1], lp_mm_self = t[2], lp_mm_next = t[3], lp_bb = t[4];
+    const float lp_bk = t[5], lp_bm_next = t[6], lp_bm_self = t[7], lp_kk = t[8], lp_km = t[9];
+
+    float* pre = (float*)malloc(sizeof(float) * (n_events + 1));
+    float* post = (float*)malloc(sizeof(float) * n_events);
+    npo_flank_table(pre, n_events + 1);
+    for (uint32_t i = 0; i < n_events; ++i) post[i] = pre[n_events - 1 - i];
+
+    const float lp_sm = 0.0f, lp_ms = 0.0f;
+    float lp_end = -INFINITY;
+    const uint32_t last_kmer = n_kmers - 1;
+    const uint32_t last_row = n_rows - 1;
+
+    for (uint32_t row = 1; row < n_rows; ++row) {
+        const uint32_t event_idx = e_start + (row - 1) * stride;
+        float* cur = fm + (size_t)row * n_cols;
+        const float* prv = fm + (size_t)(row - 1) * n_cols;
+        for (uint32_t block = 1; block < n_blocks - 1; ++block) {
+            const uint32_t ki = block - 1;
+            const uint32_t pb = NST * (block - 1), cb = NST * block;
+            const float em = npo_log_probability_match(read, ev_mean, ev_start_time, model, ranks[ki], event_idx);
+            float x[6];
+
+            x[0] = lp_mm_self + prv[cb + ST_M];
+            x[1] = lp_mm_next + prv[pb + ST_M];
+            x[2] = lp_bm_self + prv[cb + ST_B];
+            x[3] = lp_bm_next + prv[pb + ST_B];
+            x[4] = lp_km + prv[pb + ST_K];
+            x[5] = (ki == 0 && (event_idx == e_start || (flags & NPH_HAF_ALLOW_PRE_CLIP))) ? lp_sm + pre[row - 1] : -INFINITY;
+            if (!viterbi) {
+                cur[cb + ST_M] = fold6(x) + em;
+            } else {
+                float mx = x[0]; uint8_t from = 0;
+                for (int i = 1; i < 6; ++i) { mx = x[i] > mx ? x[i] : mx; from = mx == x[i] ? (uint8_t)i : from; }
+                cur[cb + ST_M] = mx + em; bm[(size_t)row * n_cols + cb + ST_M] = from;
+            }
+
+            x[0] = lp_mb + prv[cb + ST_M];
+            x[1] = -INFINITY;
+            x[2] = lp_bb + prv[cb + ST_B];
+            x[3] = x[4] = x[5] = -INFINITY;
+            if (!viterbi) {
+                cur[cb + ST_B] = fold6(x) + 0.0f;
+            } else {
+                float mx = x[0]; uint8_t from = 0;
+                for (int i = 1; i < 6; ++i) { mx = x[i] > mx ? x[i] : mx; from = mx == x[i] ? (uint8_t)i : from; }
+                cur[cb + ST_B] = mx + 0.0f; bm[(size_t)row * n_cols + cb + ST_B] = from;
+            }
+
+            x[0] = -INFINITY;
+            x[1] = lp_mk + cur[pb + ST_M];
+            x[2] = -INFINITY;
+            x[3] = lp_bk + cur[pb + ST_B];
+            x[4] = lp_kk + cur[pb + ST_K];
+            x[5] = -INFINITY;
+            if (!viterbi) {
+                cur[cb + ST_K] = fold6(x) + 0.0f;
+            } else {
+                float mx = x[0]; uint8_t from = 0;
+                for (int i = 1; i < 6; ++i) { mx = x[i] > mx ? x[i] : mx; from = mx == x[i] ? (uint8_t)i : from; }
+                cur[cb + ST_K] = mx + 0.0f; bm[(size_t)row * n_cols + cb + ST_K] = from;
+            }
+
+            if (ki == last_kmer && ((flags & NPH_HAF_ALLOW_POST_CLIP) || row == last_row)) {
+                const int order[3] = { ST_M, ST_B, ST_K };
+                for (int s = 0; s < 3; ++s) {
+                    float v = lp_ms + cur[cb + order[s]] + post[row - 1];
+                    if (!viterbi) {
+                        lp_end = add_logs_f(lp_end, v);
+                    } else if (v > lp_end) {
+                        lp_end = v; *end_row = row; *end_col = cb + order[s];
+                    }
+                }
+            }
+        }
+    }
+    free(pre);
+    free(post);
+    return lp_end;
+}
+
+static size_t job_rows(const nph_hmm_job* job)
+{
+    uint32_t n_events = (job->event_stop > job->event_start ? job->event_stop - job->event_start
+                                                            : job->event_start - job->event_stop) + 1;
+    return (size_t)n_events + 1;
+}
+
+float npo_hmm_score_dump(const nph_read* reads, const float* ev_mean, const double* ev_start_time,
+                         const npo_model* models, const uint32_t* kmer_ranks, const nph_hmm_job* job,
+                         double indel_bias, float* fm)
+{
+    npo_init();
+    return hmm_fill(reads, ev_mean, ev_start_time, models, kmer_ranks, job, indel_bias, fm, 0, NULL, NULL, NULL);
+}
+
+float npo_hmm_score(const nph_read* reads, const float* ev_mean, const double* ev_start_time,
+                    const npo_model* models, const uint32_t* kmer_ranks, const nph_hmm_job* job,
+                    double indel_bias)
+{
+    npo_init();
+    size_t cells = job_rows(job) * (size_t)(NST * (job->n_kmers + 2));
+    float* fm = (float*)malloc(sizeof(float) * cells);
+    float s = hmm_fill(reads, ev_mean, ev_start_time, models, kmer_ranks, job, indel_bias, fm, 0, NULL, NULL, NULL);
+    free(fm);
+    return s;
+}
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+double npo_hmm_score_batch(const nph_read* reads, const float* ev_mean, const double* ev_start_time,
+                           const npo_model* models, const uint32_t* kmer_ranks,
+                           const nph_hmm_job* jobs, size_t n_jobs, double indel_bias, int threads,
+                           float* scores_out)
+{
+    npo_init();
+    if (threads < 1) threads = 1;
+    double t0 = now_s();
+    #pragma omp parallel for schedule(dynamic) num_threads(threads)
+    for (size_t j = 0; j < n_jobs; ++j)
+        scores_out[j] = npo_hmm_score(reads, ev_mean, ev_start_time, models, kmer_ranks, &jobs[j], indel_bias);
+    return now_s() - t0;
+}
+
+/* profile_hmm_score_set: score_i - log(n) in double, folded through the table logsum.
+ * ref: src/hmm/nanopolish_profile_hmm.cpp:32-56. */
+float npo_score_set_combine(const float* scores, uint32_t n_alt)
+{
+    npo_init();
+    double pen = log((double)n_alt);
+    double score = scores[0] - pen;
+    for (uint32_t i = 1; i < n_alt; ++i) {
+        double alt = scores[i] - pen;
+        score = (double)npo_logsum((float)score, (float)alt);
+    }
+    return (float)score;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Method-of-moments scaling.  ref: estimate_scalings_using_mom, src/nanopolish_raw_loader.cpp:17-60.
+ * (scale is a ratio of second moments, as in the reference.)
+ * ---------------------------------------------------------------------------------------- */
+void npo_mom(const nph_read* reads, const float* ev_mean, const npo_model* model,
+             const uint32_t* kmer_ranks, const nph_abea_job* job, double* shift_out, double* scale_out)
+{
+    const nph_read* read = &reads[job->read];
+    const float* m = ev_mean + read->event_off;
+    const uint32_t* ranks = kmer_ranks + job->rank_off;
+    size_t n = read->n_events, nk = job->n_kmers;
+    double ev_sum = 0.0;
+    for (size_t i = 0; i < n; ++i) ev_sum += m[i];
+    double k_sum = 0.0, k_sq = 0.0;
+    for (size_t i = 0; i < nk; ++i) {
+        double l = model->level_mean[ranks[i]];
+        k_sum += l;
+        k_sq += pow(l, 2.0f);
+    }
+    double shift = ev_sum / n - k_sum / nk;
+    double ev_sq = 0.0;
+    for (size_t i = 0; i < n; ++i) ev_sq += pow(m[i] - shift, 2.0);
+    *shift_out = shift;
+    *scale_out = (ev_sq / n) / (k_sq / nk);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Adaptive banded event alignment (Suzuki-Kasahara band, width 100, Viterbi over
+ * diag=step / up=stay / left=skip).  ref: src/nanopolish_raw_loader.cpp:77-379; band coordinate
+ * algebra :62-75.
+ * ---------------------------------------------------------------------------------------- */
+#define BW 100
+enum { FROM_D = 0, FROM_U = 1, FROM_L = 2 };
+
+int64_t npo_abea(const nph_read* reads, const float* ev_mean, const double* ev_start_time,
+                 const npo_model* model, const uint32_t* kmer_ranks, const nph_abea_job* job,
+                 nph_aligned_pair* pairs_out, nph_abea_result* res)
+{
+    const nph_read* read = &reads[job->read];
+    const uint32_t* ranks = kmer_ranks + job->rank_off;
+    const long n_events = read->n_events;
+    const long n_kmers = job->n_kmers;
+    const int half_bw = BW / 2;
+
+    const double min_average_log_emission = -5.0;
+    const int max_gap_threshold = 50;
+
+    double events_per_kmer = (double)n_events / n_kmers;
+    double p_stay = 1 - (1 / (events_per_kmer + 1));
+    double epsilon = 1e-10;
+    double lp_skip = log(epsilon);
+    double lp_stay = log(p_stay);
+    double lp_step = log(1.0 - exp(lp_skip) - exp(lp_stay));
+    double lp_trim = log(0.01);
+
+    const long n_rows = n_events + 1, n_cols = n_kmers + 1, n_bands = n_rows + n_cols;
+
+    float* bands = (float*)malloc(sizeof(float) * n_bands * BW);
+    uint8_t* trace = (uint8_t*)malloc((size_t)n_bands * BW);
+    int* ll_e = (int*)malloc(sizeof(int) * n_bands);   /* event index of each band's lower-left cell */
+    int* ll_k = (int*)malloc(sizeof(int) * n_bands);   /* k-mer index of it */
+    for (long i = 0; i < n_bands * BW; ++i) { bands[i] = -INFINITY; trace[i] = 0; }
+#define BAND(b, o) bands[(size_t)(b) * BW + (o)]
+#define TRACE(b, o) trace[(size_t)(b) * BW + (o)]
+
+    ll_e[0] = half_bw - 1;
+    ll_k[0] = -1 - half_bw;
+    ll_e[1] = ll_e[0] + 1;
+    ll_k[1] = ll_k[0];
+
+    BAND(0, -1 - ll_k[0]) = 0.0f;                         /* start cell (event -1, kmer -1) */
+    { int o = ll_e[1] - 0; BAND(1, o) = (float)lp_trim; TRACE(1, o) = FROM_U; }
+
+    for (long bi = 2; bi < n_bands; ++bi) {
+        float ll = BAND(bi - 1, 0), ur = BAND(bi - 1, BW - 1);
+        int right;
+        if (ll == -INFINITY && ur == -INFINITY) right = (bi % 2 == 1);
+        else right = ll < ur;
+        if (right) { ll_e[bi] = ll_e[bi - 1]; ll_k[bi] = ll_k[bi - 1] + 1; }
+        else       { ll_e[bi] = ll_e[bi - 1] + 1; ll_k[bi] = ll_k[bi - 1]; }
+
+        int trim_offset = -1 - ll_k[bi];
+        if (trim_offset >= 0 && trim_offset < BW) {
+            long e = ll_e[bi] - trim_offset;
+            if (e >= 0 && e < n_events) { BAND(bi, trim_offset) = (float)(lp_trim * (e + 1)); TRACE(bi, trim_offset) = FROM_U; }
+            else BAND(bi, trim_offset) = -INFINITY;
+        }
+
+        long kmer_min_offset = 0 - ll_k[bi];
+        long kmer_max_offset = n_kmers - ll_k[bi];
+        long event_min_offset = ll_e[bi] - (n_events - 1);
+        long event_max_offset = ll_e[bi] - (-1);
+        long min_offset = kmer_min_offset > event_min_offset ? kmer_min_offset : event_min_offset;
+        if (min_offset < 0) min_offset = 0;
+        long max_offset = kmer_max_offset < event_max_offset ? kmer_max_offset : event_max_offset;
+        if (max_offset > BW) max_offset = BW;
+
+        for (long o = min_offset; o < max_offset; ++o) {
+            long e = ll_e[bi] - o, k = ll_k[bi] + o;
+            long o_up = ll_e[bi - 1] - (e - 1);
+            long o_left = (k - 1) - ll_k[bi - 1];
+            long o_diag = (k - 1) - ll_k[bi - 2];
+            float up = (o_up >= 0 && o_up < BW) ? BAND(bi - 1, o_up) : -INFINITY;
+            float left = (o_left >= 0 && o_left < BW) ? BAND(bi - 1, o_left) : -INFINITY;
+            float diag = (o_diag >= 0 && o_diag < BW) ? BAND(bi - 2, o_diag) : -INFINITY;
+            float em = npo_log_probability_match(read, ev_mean, ev_start_time, model, ranks[k], (uint32_t)e);
+            float score_d = (float)(diag + lp_step + em);
+            float score_u = (float)(up + lp_stay + em);
+            float score_l = (float)(left + lp_skip);
+            float mx = score_d; uint8_t from = FROM_D;
+            mx = score_u > mx ? score_u : mx;  from = mx == score_u ? FROM_U : from;
+            mx = score_l > mx ? score_l : mx;  from = mx == score_l ? FROM_L : from;
+            BAND(bi, o) = mx; TRACE(bi, o) = from;
+        }
+    }
+
+    /* best end cell: any event against the last k-mer, remaining events trimmed (:309-324) */
+    float max_score = -INFINITY;
+    long cur_e = 0, cur_k = n_kmers - 1;
+    int found = 0;
+    for (long e = 0; e < n_events; ++e) {
+        long bi = (e + 1) + (cur_k + 1);
+        long o = ll_e[bi] - e;
+        if (o >= 0 && o < BW) {
+            float s = (float)(BAND(bi, o) + (double)(unsigned long)(n_events - e) * lp_trim);
+            if (s > max_score) { max_score = s; cur_e = e; found = 1; }
+        }
+    }
+
+    int64_t n_out = 0;
+    double sum_emission = 0, n_aligned = 0;
+    int cur_gap = 0, max_gap = 0, status = found ? 0 : NPH_ABEA_NO_END_CELL;
+    while (cur_k >= 0 && cur_e >= 0) {
+        if ((uint64_t)n_out < job->pairs_cap) { pairs_out[n_out].ref_pos = (int32_t)cur_k; pairs_out[n_out].read_pos = (int32_t)cur_e; }
+        else status |= NPH_ABEA_PAIRS_OVERFLOW;
+        n_out++;
+        sum_emission += npo_log_probability_match(read, ev_mean, ev_start_time, model, ranks[cur_k], (uint32_t)cur_e);
+        n_aligned += 1;
+        long bi = (cur_e + 1) + (cur_k + 1);
+        long o = ll_e[bi] - cur_e;
+        uint8_t from = (o >= 0 && o < BW) ? TRACE(bi, o) : FROM_D;  /* out of band: reference reads out of row */
+        if (from == FROM_D) { cur_k -= 1; cur_e -= 1; cur_gap = 0; }
+        else if (from == FROM_U) { cur_e -= 1; cur_gap = 0; }
+        else { cur_k -= 1; cur_gap += 1; if (cur_gap > max_gap) max_gap = cur_gap; }
+    }
+    if (!(status & NPH_ABEA_PAIRS_OVERFLOW)) {
+        for (int64_t i = 0, j = n_out - 1; i < j; ++i, --j) { nph_aligned_pair t = pairs_out[i]; pairs_out[i] = pairs_out[j]; pairs_out[j] = t; }
+    }
+
+    double avg = sum_emission / n_aligned;
+    int spanned = 0;
+    if (n_out > 0 && !(status & NPH_ABEA_PAIRS_OVERFLOW))
+        spanned = pairs_out[0].ref_pos == 0 && pairs_out[n_out - 1].ref_pos == n_kmers - 1;
+    if (avg < min_average_log_emission) status |= NPH_ABEA_LOW_EMISSION;
+    if (!spanned) status |= NPH_ABEA_NOT_SPANNED;
+    if (max_gap > max_gap_threshold) status |= NPH_ABEA_MAX_GAP;
+
+    if (res) {
+        res->n_aligned = (uint32_t)n_out;
+        res->n_pairs = status ? 0 : (uint32_t)n_out;
+        res->status = status;
+        res->max_gap = max_gap;
+        res->avg_log_emission = avg;
+    }
+    free(bands); free(trace); free(ll_e); free(ll_k);
+    return status ? 0 : n_out;
+#undef BAND
+#undef TRACE
+}
+
+double npo_abea_batch(const nph_read* reads, const float* ev_mean, const double* ev_start_time,
+                      const npo_model* model, const uint32_t* kmer_ranks, const nph_abea_job* jobs,
+                      size_t n_jobs, int threads, nph_aligned_pair* pairs_out, nph_abea_result* res)
+{
+    if (threads < 1) threads = 1;
+    double t0 = now_s();
+    #pragma omp parallel for schedule(dynamic) num_threads(threads)
+    for (size_t j = 0; j < n_jobs; ++j)
+        npo_abea(reads, ev_mean, ev_start_time, model, kmer_ranks, &jobs[j], pairs_out + jobs[j].pairs_off, &res[j]);
+    return now_s() - t0;
+}
+
+int npo_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

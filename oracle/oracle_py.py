@@ -1,0 +1,233 @@
+"""ctypes bindings of the two CPU checkers — TEST INFRASTRUCTURE ONLY.
+
+  * PortOracle : oracle/libnporacle.so, our plain-C restatement (np_oracle.c)
+  * RefOracle  : oracle/_ref/libnpref.so, the unmodified reference TUs behind ref_harness.cpp
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  Nothing under nanopolish_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "libnporacle.so")
+REF_SO = os.path.join(HERE, "_ref", "libnpref.so")
+
+
+def build(ref: bool = True) -> None:
+    """Compile the checkers (port always; the reference build only where /root/reference exists)."""
+    subprocess.run(["make", "-C", HERE, "port"], check=True, stdout=subprocess.DEVNULL)
+    if ref:
+        subprocess.run(["make", "-C", HERE, "-j8", "ref"], check=True, stdout=subprocess.DEVNULL)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class _NpoModel(C.Structure):
+    _fields_ = [("level_mean", C.c_void_p), ("level_stdv", C.c_void_p),
+                ("level_log_stdv", C.c_void_p), ("n_states", C.c_uint32)]
+
+
+class PortOracle:
+    def __init__(self):
+        if not os.path.exists(PORT_SO):
+            build(ref=False)
+        self.lib = L = C.CDLL(PORT_SO)
+        L.npo_logsum.restype = C.c_float
+        L.npo_logsum.argtypes = [C.c_float, C.c_float]
+        L.npo_log_normal_pdf.restype = C.c_float
+        L.npo_log_normal_pdf.argtypes = [C.c_float] * 4
+        L.npo_hmm_score_batch.restype = C.c_double
+        L.npo_hmm_score_dump.restype = C.c_float
+        L.npo_abea_batch.restype = C.c_double
+        L.npo_score_set_combine.restype = C.c_float
+        L.npo_init()
+        self._keep = []
+
+    def models(self, model_list):
+        arr = (_NpoModel * len(model_list))()
+        for i, m in enumerate(model_list):
+            mean = np.ascontiguousarray(m.level_mean, np.float64)
+            sd = np.ascontiguousarray(m.level_stdv, np.float64)
+            lsd = np.ascontiguousarray(m.level_log_stdv, np.float64)
+            self._keep += [mean, sd, lsd]
+            arr[i] = _NpoModel(mean.ctypes.data, sd.ctypes.data, lsd.ctypes.data, mean.shape[0])
+        return arr
+
+    def logsum_table(self):
+        t = np.zeros(16000, np.float32)
+        self.lib.npo_logsum_table(_p(t))
+        return t
+
+    def flank_table(self, n):
+        t = np.zeros(n, np.float32)
+        self.lib.npo_flank_table(_p(t), C.c_size_t(n))
+        return t
+
+    def transitions(self, events_per_base, indel_bias=1.0):
+        t = np.zeros(10, np.float32)
+        self.lib.npo_transitions(C.c_double(events_per_base), C.c_double(indel_bias), _p(t))
+        return t
+
+    def hmm_score_batch(self, reads, ev_mean, ev_start, model_list, kmer_ranks, jobs, indel_bias=1.0,
+                        threads=1):
+        out = np.zeros(jobs.shape[0], np.float32)
+        marr = self.models(model_list)
+        secs = self.lib.npo_hmm_score_batch(_p(reads), _p(ev_mean), _p(ev_start), marr, _p(kmer_ranks),
+                                            _p(jobs), C.c_size_t(jobs.shape[0]), C.c_double(indel_bias),
+                                            C.c_int(threads), _p(out))
+        return out, secs
+
+    def hmm_score_dump(self, reads, ev_mean, ev_start, model_list, kmer_ranks, job, indel_bias=1.0):
+        E = abs(int(job["event_stop"]) - int(job["event_start"])) + 1
+        K = int(job["n_kmers"])
+        fm = np.zeros((E + 1, 3 * (K + 2)), np.float32)
+        marr = self.models(model_list)
+        jb = np.array([job], dtype=job.dtype)
+        s = self.lib.npo_hmm_score_dump(_p(reads), _p(ev_mean), _p(ev_start), marr, _p(kmer_ranks), _p(jb),
+                                        C.c_double(indel_bias), _p(fm))
+        return s, fm
+
+    def score_set_combine(self, scores):
+        s = np.ascontiguousarray(scores, np.float32)
+        return self.lib.npo_score_set_combine(_p(s), C.c_uint32(s.shape[0]))
+
+    def abea_batch(self, reads, ev_mean, ev_start, model, kmer_ranks, jobs, pairs_total, threads=1):
+        from nanopolish_b200.synth import PAIR_DT, ABEA_RES_DT
+        pairs = np.zeros(pairs_total, PAIR_DT)
+        res = np.zeros(jobs.shape[0], ABEA_RES_DT)
+        marr = self.models([model])
+        secs = self.lib.npo_abea_batch(_p(reads), _p(ev_mean), _p(ev_start), marr, _p(kmer_ranks), _p(jobs),
+                                       C.c_size_t(jobs.shape[0]), C.c_int(threads), _p(pairs), _p(res))
+        return pairs, res, secs
+
+    def mom(self, reads, ev_mean, model, kmer_ranks, job):
+        marr = self.models([model])
+        sh, sc = C.c_double(), C.c_double()
+        jb = np.array([job], dtype=job.dtype)
+        self.lib.npo_mom(_p(reads), _p(ev_mean), marr, _p(kmer_ranks), _p(jb), C.byref(sh), C.byref(sc))
+        return sh.value, sc.value
+
+    def max_threads(self):
+        return int(self.lib.npo_max_threads())
+
+
+class RefOracle:
+    """The compiled reference.  Reads are registered once (npref_read_create) and addressed by handle."""
+
+    def __init__(self):
+        if not os.path.exists(REF_SO):
+            raise FileNotFoundError(REF_SO + " (run `make -C oracle ref` where /root/reference exists)")
+        self.lib = L = C.CDLL(REF_SO)
+        L.npref_score_batch.restype = C.c_double
+        L.npref_abea_batch.restype = C.c_double
+        L.npref_abea.restype = C.c_int64
+        L.npref_add_logs.restype = C.c_float
+        L.npref_add_logs.argtypes = [C.c_float, C.c_float]
+        L.npref_log_probability_match_r9.restype = C.c_float
+        L.npref_log_normal_pdf.restype = C.c_float
+        L.npref_log_normal_pdf.argtypes = [C.c_float] * 3
+        L.npref_kmer_rank.restype = C.c_uint32
+        self._models = {}
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_SO)
+
+    def builtin_model(self, alphabet="nucleotide", kit="r9.4_450bps", strand="template", k=6):
+        key = (kit, alphabet, strand, k)
+        if key not in self._models:
+            h = self.lib.npref_model_builtin(kit.encode(), alphabet.encode(), strand.encode(), k)
+            if h < 0:
+                raise KeyError(key)
+            self._models[key] = h
+        return self._models[key]
+
+    def custom_model(self, model):
+        mean = np.ascontiguousarray(model.level_mean, np.float64)
+        sd = np.ascontiguousarray(model.level_stdv, np.float64)
+        return self.lib.npref_model_custom(model.alphabet.encode(), model.k, C.c_uint32(mean.shape[0]), _p(mean), _p(sd))
+
+    def model_dump(self, h):
+        k, n, a = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self.lib.npref_model_info(h, C.byref(k), C.byref(n), C.byref(a))
+        mean = np.zeros(n.value); sd = np.zeros(n.value); lsd = np.zeros(n.value)
+        self.lib.npref_model_dump(h, _p(mean), _p(sd), _p(lsd))
+        return k.value, a.value, mean, sd, lsd
+
+    def register_reads(self, reads, ev_mean, ev_start, base_model_h):
+        hs = np.zeros(reads.shape[0], np.int32)
+        for i, r in enumerate(reads):
+            o, n = int(r["event_off"]), int(r["n_events"])
+            m = np.ascontiguousarray(ev_mean[o:o + n]); t = np.ascontiguousarray(ev_start[o:o + n])
+            hs[i] = self.lib.npref_read_create(C.c_uint32(n), _p(m), _p(t), C.c_double(r["shift"]),
+                                               C.c_double(r["scale"]), C.c_double(r["drift"]),
+                                               C.c_double(r["var"]), C.c_double(r["events_per_base"]),
+                                               base_model_h)
+        return hs
+
+    def clear_reads(self):
+        self.lib.npref_reads_clear()
+
+    def score_batch(self, read_handles, jobs, seqs, model_handles, indel_bias=1.0, threads=1):
+        n = jobs.shape[0]
+        rh = np.ascontiguousarray(read_handles[jobs["read"]], np.int32)
+        mh = np.ascontiguousarray(np.asarray(model_handles, np.int32)[jobs["model_id"]], np.int32)
+        es = np.ascontiguousarray(jobs["event_start"], np.uint32)
+        ee = np.ascontiguousarray(jobs["event_stop"], np.uint32)
+        rc = np.ascontiguousarray(jobs["rc"], np.uint8)
+        fl = np.ascontiguousarray(jobs["flags"], np.uint32)
+        buf = b"".join(seqs)
+        off = np.zeros(n + 1, np.uint64)
+        off[1:] = np.cumsum([len(s) for s in seqs])
+        out = np.zeros(n, np.float32)
+        secs = self.lib.npref_score_batch(C.c_size_t(n), _p(rh), _p(mh), _p(es), _p(ee), _p(rc), _p(fl),
+                                          C.c_char_p(buf), _p(off), C.c_double(indel_bias), C.c_int(threads), _p(out))
+        return out, secs
+
+    def kmer_ranks(self, model_h, seq: bytes, rc: bool):
+        out = np.zeros(max(len(seq), 1), np.uint32)
+        n = self.lib.npref_kmer_ranks(model_h, C.c_char_p(seq), int(rc), _p(out))
+        return out[:n].copy()
+
+    def alphabet_op(self, alphabet: str, op: int, s: bytes) -> bytes:
+        out = C.create_string_buffer(len(s) + 16)
+        n = self.lib.npref_alphabet_op(alphabet.encode(), op, C.c_char_p(s), out)
+        return out.raw[:n]
+
+    def abea(self, read_h, model_h, seq: bytes, cap: int):
+        pairs = np.zeros((cap, 2), np.int32)
+        n = self.lib.npref_abea(int(read_h), model_h, C.c_char_p(seq), _p(pairs), C.c_size_t(cap))
+        return pairs[:max(n, 0)].copy(), n
+
+    def abea_batch(self, read_handles, model_h, seqs, caps, threads=1):
+        n = len(seqs)
+        buf = b"".join(seqs)
+        off = np.zeros(n + 1, np.uint64); off[1:] = np.cumsum([len(s) for s in seqs])
+        poff = np.zeros(n + 1, np.uint64); poff[1:] = np.cumsum(caps)
+        pairs = np.zeros((int(poff[-1]), 2), np.int32)
+        npairs = np.zeros(n, np.int64)
+        rh = np.ascontiguousarray(read_handles, np.int32)
+        secs = self.lib.npref_abea_batch(C.c_size_t(n), _p(rh), model_h, C.c_char_p(buf), _p(off), C.c_int(threads),
+                                         _p(pairs), _p(poff), _p(npairs))
+        return pairs, poff, npairs, secs
+
+    def mom(self, read_h, model_h, seq: bytes):
+        out = np.zeros(4)
+        self.lib.npref_mom(int(read_h), model_h, C.c_char_p(seq), _p(out))
+        return out
+
+    def logsum_table(self):
+        t = np.zeros(16000, np.float32)
+        self.lib.npref_logsum_table(_p(t))
+        return t
+
+    def max_threads(self):
+        return int(self.lib.npref_max_threads())

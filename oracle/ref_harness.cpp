@@ -1,0 +1,256 @@
+// oracle/ref_harness.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// A thin C-callable shell around the UNMODIFIED reference translation units of the
+// hot path (compiled in place from /root/reference by oracle/Makefile into
+// oracle/_ref/libnpref.so).  It lets tests/ and bench.py's cpu_baseline leg drive
+//   profile_hmm_score                      (src/hmm/nanopolish_profile_hmm.cpp:23-30)
+//   adaptive_banded_simple_event_align     (src/nanopolish_raw_loader.cpp:77-379)
+//   estimate_scalings_using_mom            (src/nanopolish_raw_loader.cpp:17-60)
+//   HMMInputSequence::get_kmer_rank        (src/hmm/nanopolish_hmm_input_sequence.h:76-91)
+//   Alphabet::{reverse_complement,methylate,unmethylate,disambiguate}
+// on flat arrays.  Reads are assembled by hand exactly like the reference's own
+// "scalings" unit test does (src/test/nanopolish_test.cpp:279-311): default-construct a
+// SquiggleRead, set pore_type / base_model / scalings / events_per_base, push events.
+//
+// The product (nanopolish_b200/, include/) never links or loads this file.
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <memory>
+#include <string>
+#include <vector>
+#include <chrono>
+#include <omp.h>
+
+#include "nanopolish_common.h"
+#include "nanopolish_squiggle_read.h"
+#include "nanopolish_pore_model_set.h"
+#include "nanopolish_profile_hmm.h"
+#include "nanopolish_raw_loader.h"
+#include "nanopolish_alphabet.h"
+#include "nanopolish_emissions.h"
+#include "logsum.h"
+
+extern double hmm_indel_bias_factor;   // src/hmm/nanopolish_profile_hmm_r9.cpp:19
+
+// Out-of-line members that live in nanopolish_squiggle_read.cpp, which we do not link
+// (it needs HDF5 + Eigen).  Semantics follow src/nanopolish_squiggle_read.cpp:38-65, :155-158.
+void SquiggleScalings::set6(double _shift, double _scale, double _drift, double _var,
+                            double _scale_sd, double _var_sd)
+{
+    shift = _shift; scale = _scale; drift = _drift; var = _var;
+    scale_sd = _scale_sd; var_sd = _var_sd;
+    log_var = log(var);
+    scaled_var = var / scale;
+    log_scaled_var = log(scaled_var);
+}
+void SquiggleScalings::set4(double _shift, double _scale, double _drift, double _var)
+{
+    set6(_shift, _scale, _drift, _var, 1.0, 1.0);
+}
+SquiggleRead::~SquiggleRead() {}
+
+namespace {
+std::vector<const PoreModel*> g_models;
+std::vector<std::unique_ptr<PoreModel>> g_owned_models;
+std::vector<std::unique_ptr<SquiggleRead>> g_reads;
+}
+
+extern "C" {
+
+int npref_model_builtin(const char* kit, const char* alphabet, const char* strand, int k)
+{
+    if(!PoreModelSet::has_model(kit, alphabet, strand, k)) return -1;
+    const PoreModel* pm = PoreModelSet::get_model(kit, alphabet, strand, k);
+    if(pm == NULL) return -1;
+    g_models.push_back(pm);
+    return (int)g_models.size() - 1;
+}
+
+// A hand-made model: level_log_stdv = log(level_stdv) as PoreModelStateParams::update_logs does
+// (src/pore_model/nanopolish_poremodel.h:61-65).
+int npref_model_custom(const char* alphabet, int k, uint32_t n_states, const double* mean, const double* stdv)
+{
+    std::unique_ptr<PoreModel> pm(new PoreModel(k));
+    pm->pmalphabet = get_alphabet_by_name(alphabet);
+    pm->states.resize(n_states);
+    for(uint32_t i = 0; i < n_states; ++i)
+        pm->states[i] = PoreModelStateParams(mean[i], stdv[i], 1.0, 1.0);
+    g_models.push_back(pm.get());
+    g_owned_models.push_back(std::move(pm));
+    return (int)g_models.size() - 1;
+}
+
+int npref_model_info(int h, uint32_t* k, uint32_t* n_states, uint32_t* alphabet_size)
+{
+    const PoreModel* pm = g_models[h];
+    *k = pm->k; *n_states = pm->states.size(); *alphabet_size = pm->pmalphabet->size();
+    return 0;
+}
+
+int npref_model_dump(int h, double* mean, double* stdv, double* log_stdv)
+{
+    const PoreModel* pm = g_models[h];
+    for(size_t i = 0; i < pm->states.size(); ++i) {
+        mean[i] = pm->states[i].level_mean;
+        stdv[i] = pm->states[i].level_stdv;
+        log_stdv[i] = pm->states[i].level_log_stdv;
+    }
+    return 0;
+}
+
+int npref_read_create(uint32_t n_events, const float* mean, const double* start_time,
+                      double shift, double scale, double drift, double var,
+                      double events_per_base, int base_model)
+{
+    std::unique_ptr<SquiggleRead> sr(new SquiggleRead());
+    sr->pore_type = PORETYPE_R9;
+    sr->read_type = SRT_TEMPLATE;
+    sr->nucleotide_type = SRNT_DNA;
+    sr->base_model[0] = g_models[base_model];
+    sr->base_model[1] = NULL;
+    sr->scalings[0].set4(shift, scale, drift, var);
+    sr->events_per_base[0] = events_per_base;
+    sr->events[0].resize(n_events);
+    for(uint32_t i = 0; i < n_events; ++i) {
+        SquiggleEvent& e = sr->events[0][i];
+        e.mean = mean[i];
+        e.stdv = 1.0f;
+        e.start_time = start_time[i];
+        e.duration = 0.0f;
+        e.log_stdv = 0.0f;
+    }
+    g_reads.push_back(std::move(sr));
+    return (int)g_reads.size() - 1;
+}
+
+void npref_read_set_scalings(int h, double shift, double scale, double drift, double var, double events_per_base)
+{
+    g_reads[h]->scalings[0].set4(shift, scale, drift, var);
+    g_reads[h]->events_per_base[0] = events_per_base;
+}
+
+void npref_reads_clear(void) { g_reads.clear(); }
+
+// profile_hmm_score over a batch of jobs; OpenMP over jobs the way the reference parallelises
+// over reads (src/common/nanopolish_bam_processor.cpp:99).  Returns elapsed seconds of the scoring loop.
+double npref_score_batch(size_t n_jobs, const int32_t* read_h, const int32_t* model_h,
+                         const uint32_t* e_start, const uint32_t* e_stop, const uint8_t* rc,
+                         const uint32_t* flags, const char* seq_buf, const uint64_t* seq_off,
+                         double indel_bias, int threads, float* out)
+{
+    hmm_indel_bias_factor = indel_bias;
+    if(threads < 1) threads = 1;
+    auto t0 = std::chrono::steady_clock::now();
+    #pragma omp parallel for schedule(dynamic) num_threads(threads)
+    for(size_t j = 0; j < n_jobs; ++j) {
+        const PoreModel* pm = g_models[model_h[j]];
+        std::string seq(seq_buf + seq_off[j], seq_buf + seq_off[j + 1]);
+        HMMInputSequence hseq(seq, pm->pmalphabet);
+        HMMInputData data;
+        data.read = g_reads[read_h[j]].get();
+        data.pore_model = pm;
+        data.event_start_idx = e_start[j];
+        data.event_stop_idx = e_stop[j];
+        data.strand = 0;
+        data.rc = rc[j];
+        data.event_stride = rc[j] ? -1 : 1;
+        out[j] = profile_hmm_score(hseq, data, flags[j]);
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+int npref_kmer_ranks(int model_h, const char* seq, int rc, uint32_t* out)
+{
+    const PoreModel* pm = g_models[model_h];
+    HMMInputSequence hseq(std::string(seq), pm->pmalphabet);
+    uint32_t k = pm->k;
+    if(hseq.length() < k) return 0;
+    uint32_t n = hseq.length() - k + 1;
+    for(uint32_t i = 0; i < n; ++i) out[i] = hseq.get_kmer_rank(i, k, rc != 0);
+    return (int)n;
+}
+
+// op: 0 reverse_complement, 1 methylate, 2 unmethylate, 3 disambiguate
+int npref_alphabet_op(const char* alphabet, int op, const char* in, char* out)
+{
+    const Alphabet* a = get_alphabet_by_name(alphabet);
+    std::string s(in), r;
+    switch(op) {
+        case 0: r = a->reverse_complement(s); break;
+        case 1: r = a->methylate(s); break;
+        case 2: r = a->unmethylate(s); break;
+        case 3: r = a->disambiguate(s); break;
+        default: return -1;
+    }
+    memcpy(out, r.c_str(), r.size() + 1);
+    return (int)r.size();
+}
+
+uint32_t npref_kmer_rank(const char* alphabet, const char* kmer, uint32_t k)
+{
+    return get_alphabet_by_name(alphabet)->kmer_rank(kmer, k);
+}
+
+// adaptive_banded_simple_event_align on one read; pairs_out = (ref_pos, read_pos) interleaved.
+// Returns the number of pairs (0 == the reference's "failed QC" empty vector), or -1 if cap too small.
+int64_t npref_abea(int read_h, int model_h, const char* seq, int32_t* pairs_out, size_t cap)
+{
+    std::vector<AlignedPair> p =
+        adaptive_banded_simple_event_align(*g_reads[read_h], *g_models[model_h], std::string(seq));
+    if(p.size() > cap) return -1;
+    for(size_t i = 0; i < p.size(); ++i) {
+        pairs_out[2 * i] = p[i].ref_pos;
+        pairs_out[2 * i + 1] = p[i].read_pos;
+    }
+    return (int64_t)p.size();
+}
+
+// ABEA over many reads, OpenMP over reads; returns elapsed seconds. n_pairs_out[i] = pairs of read i.
+double npref_abea_batch(size_t n_reads, const int32_t* read_h, int model_h, const char* seq_buf,
+                        const uint64_t* seq_off, int threads, int32_t* pairs_out,
+                        const uint64_t* pairs_off, int64_t* n_pairs_out)
+{
+    if(threads < 1) threads = 1;
+    auto t0 = std::chrono::steady_clock::now();
+    #pragma omp parallel for schedule(dynamic) num_threads(threads)
+    for(size_t r = 0; r < n_reads; ++r) {
+        std::string seq(seq_buf + seq_off[r], seq_buf + seq_off[r + 1]);
+        std::vector<AlignedPair> p =
+            adaptive_banded_simple_event_align(*g_reads[read_h[r]], *g_models[model_h], seq);
+        size_t cap = pairs_off[r + 1] - pairs_off[r];
+        if(p.size() > cap) { n_pairs_out[r] = -1; continue; }
+        int32_t* o = pairs_out + 2 * pairs_off[r];
+        for(size_t i = 0; i < p.size(); ++i) { o[2 * i] = p[i].ref_pos; o[2 * i + 1] = p[i].read_pos; }
+        n_pairs_out[r] = (int64_t)p.size();
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// estimate_scalings_using_mom on the events of a read; out = {shift, scale, drift, var}
+void npref_mom(int read_h, int model_h, const char* seq, double* out)
+{
+    SquiggleRead& sr = *g_reads[read_h];
+    std::vector<event_t> ev(sr.events[0].size());
+    for(size_t i = 0; i < ev.size(); ++i) { ev[i].mean = sr.events[0][i].mean; ev[i].start = 0; ev[i].length = 0; ev[i].stdv = 1; ev[i].pos = 0; ev[i].state = 0; }
+    event_table et; et.n = ev.size(); et.start = 0; et.end = ev.size(); et.event = ev.data();
+    SquiggleScalings s = estimate_scalings_using_mom(std::string(seq), *g_models[model_h], et);
+    out[0] = s.shift; out[1] = s.scale; out[2] = s.drift; out[3] = s.var;
+}
+
+void npref_logsum_table(float* out) { p7_FLogsumInit(); extern float flogsum_lookup[]; memcpy(out, flogsum_lookup, sizeof(float) * p7_LOGSUM_TBL); }
+float npref_add_logs(float a, float b) { return add_logs(a, b); }
+float npref_log_probability_match_r9(int read_h, int model_h, uint32_t rank, uint32_t event_idx)
+{
+    return log_probability_match_r9(*g_reads[read_h], *g_models[model_h], rank, event_idx, 0);
+}
+float npref_log_normal_pdf(float x, float mean, float stdv)
+{
+    GaussianParameters g(mean, stdv);
+    return log_normal_pdf(x, g);
+}
+int npref_max_threads(void) { return omp_get_max_threads(); }
+
+} // extern "C"

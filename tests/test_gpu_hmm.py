@@ -1,0 +1,132 @@
+"""Parity of the CUDA forward kernel (through the C ABI) with the oracle: bit-exact floats.
+north_star's bar is 1e-4 relative; we hold the stronger one because the kernel reproduces the
+reference's operation order, quantised logsum and IEEE roundings exactly."""
+import os
+
+import numpy as np
+import pytest
+
+from nanopolish_b200 import synth
+from tests.golden_cases import make_hmm_cases
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REL_TOL = 1e-4   # north_star tolerance (we additionally assert bit equality)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _check(got, want):
+    assert got.shape == want.shape
+    rel = np.abs(got - want) / np.maximum(1e-30, np.abs(want))
+    assert np.nanmax(rel) <= REL_TOL, f"max rel err {np.nanmax(rel)}"
+    mism = np.flatnonzero(_bits(got) != _bits(want))
+    assert mism.size == 0, f"{mism.size} of {got.size} scores differ in bits, first {mism[:5]}: {got[mism[:5]]} vs {want[mism[:5]]}"
+
+
+@pytest.fixture(scope="module")
+def models(engine):
+    nuc, cpg = synth.load_model("nucleotide"), synth.load_model("cpg")
+    return {"nucleotide": (nuc, engine.model_upload(nuc)), "cpg": (cpg, engine.model_upload(cpg))}
+
+
+@pytest.mark.parametrize("name", ["segments", "short_bias08", "methylation"])
+def test_golden_cases(engine, models, port_oracle, name):
+    case = make_hmm_cases()[name]
+    rs, jobs = case["rs"], case["jobs"]
+    mlist = [models[a][0] for a in case["alphabets"]]
+    # golden_cases uses model ids 0 (nucleotide) / 1 (cpg) == upload order in the `models` fixture
+    got = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, jobs.jobs,
+                                 indel_bias=case["indel_bias"])
+    gold = np.load(os.path.join(GOLD, "hmm_golden.npz"))[name]
+    _check(got, gold)                          # the compiled reference's recorded output
+    want, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, mlist, jobs.kmer_ranks,
+                                          jobs.jobs, indel_bias=case["indel_bias"])
+    _check(got, want)
+
+
+def _random_jobs(rs, rng, n_jobs, kmin, kmax, emin, emax, flags_choices, model_id=0):
+    rows, ranks = [], []
+    for _ in range(n_jobs):
+        r = int(rng.integers(0, rs.n_reads))
+        E = int(rs.reads[r]["n_events"])
+        nk_all = rs.seq_codes[r].shape[0] - rs.k + 1
+        K = int(rng.integers(kmin, min(kmax, nk_all) + 1))
+        k0 = int(rng.integers(0, nk_all - K + 1))
+        ne = int(rng.integers(emin, min(emax, E) + 1))
+        e0 = int(rng.integers(0, E - ne + 1))
+        e1 = e0 + ne - 1
+        sub = rs.seq_codes[r][k0:k0 + K + rs.k - 1]
+        rc = int(rng.integers(0, 2)) if ne > 1 else 0
+        fl = int(rng.choice(flags_choices))
+        if rc:
+            rcsub = (3 - sub[::-1]).astype(np.uint8)
+            ranks.append(synth.dna_rc_kmer_ranks(rcsub, rs.k)); rows.append((r, model_id, e1, e0, 1, fl))
+        else:
+            ranks.append(synth.kmer_ranks_from_codes(sub, rs.k, 4)); rows.append((r, model_id, e0, e1, 0, fl))
+    return synth._finish_jobs(rows, ranks)
+
+
+@pytest.mark.parametrize("shape", [
+    dict(kmin=1, kmax=40, emin=1, emax=60, n=400),       # tiny, includes K=1 and E=1
+    dict(kmin=16, kmax=220, emin=11, emax=400, n=300),   # call-methylation window range
+    dict(kmin=250, kmax=330, emin=450, emax=520, n=40),  # scorereads segments
+    dict(kmin=600, kmax=1100, emin=20, emax=45, n=30),   # many strips, fewer rows than the chain period
+    dict(kmin=900, kmax=1400, emin=700, emax=1200, n=12) # wide and tall
+])
+def test_random_shapes_bit_exact(engine, models, port_oracle, shape):
+    nuc = models["nucleotide"][0]
+    rs = synth.gen_reads(8, 2600, nuc, seed=900 + shape["kmin"], drift=True)
+    rng = np.random.default_rng(shape["kmin"] * 7 + 1)
+    jobs = _random_jobs(rs, rng, shape["n"], shape["kmin"], shape["kmax"], shape["emin"], shape["emax"], [0, 1, 2, 3])
+    got = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, jobs.jobs, indel_bias=0.9)
+    want, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [nuc], jobs.kmer_ranks, jobs.jobs,
+                                          indel_bias=0.9, threads=8)
+    _check(got, want)
+
+
+def test_methylation_calls_identical(engine, models, port_oracle):
+    """LLR = ll_m - ll_u per site, call rule abs(LLR) >= 2.0*n_motif (scripts/calculate_methylation_frequency.py:26,45,49)."""
+    nuc, cpg = models["nucleotide"][0], models["cpg"][0]
+    rs = synth.gen_reads(30, 3000, nuc, seed=4242, cpg_keep=0.3)
+    jobs = synth.methylation_jobs(rs, model_id=models["cpg"][1])
+    got = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, jobs.jobs)
+    want, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [nuc, cpg], jobs.kmer_ranks, jobs.jobs, threads=8)
+    _check(got, want)
+    llr_g = got[1::2].astype(np.float64) - got[0::2]
+    llr_w = want[1::2].astype(np.float64) - want[0::2]
+    assert np.array_equal(np.round(llr_g, 2), np.round(llr_w, 2))
+    assert np.array_equal(np.abs(llr_g) >= 2.0, np.abs(llr_w) >= 2.0)
+
+
+def test_staged_api_and_rescoring(engine, models, port_oracle):
+    """reads stay resident; new job lists (and a new indel bias) are scored against them."""
+    nuc = models["nucleotide"][0]
+    rs = synth.gen_reads(5, 1500, nuc, seed=31)
+    engine.reads_load(rs.reads, rs.ev_mean, rs.ev_start_time)
+    for seg, bias in [(200, 1.0), (120, 0.8)]:
+        jobs = synth.scorereads_jobs(rs, seg, rc_every=2)
+        engine.hmm_jobs_load(jobs.kmer_ranks, jobs.jobs, bias)
+        engine.hmm_score()
+        got = engine.hmm_scores_fetch()
+        want, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [nuc], jobs.kmer_ranks, jobs.jobs, indel_bias=bias, threads=8)
+        _check(got, want)
+        ms, launches = engine.last_kernel_ms()
+        assert ms > 0 and launches >= 1
+
+
+def test_invalid_jobs_are_rejected(engine, models):
+    from nanopolish_b200._lib import NphError
+    nuc = models["nucleotide"][0]
+    rs = synth.gen_reads(1, 300, nuc, seed=5)
+    jobs = synth.scorereads_jobs(rs, 100)
+    bad = jobs.jobs.copy()
+    bad[0]["event_stop"] = 10_000            # beyond the read: the reference would read out of bounds
+    with pytest.raises(NphError):
+        engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, bad)
+    bad = jobs.jobs.copy()
+    bad[0]["stride"] = -1                    # stride must follow the event order (assert in profile_hmm_r9.inl:275)
+    with pytest.raises(NphError):
+        engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, bad)

@@ -1,0 +1,109 @@
+"""Pin the plain-C oracle (oracle/np_oracle.c) to the COMPILED REFERENCE (oracle/_ref/libnpref.so),
+bit for bit.  Runs only where the reference could be compiled (the build container); the GPU box
+replays the recorded outputs instead (test_oracle_golden.py)."""
+import numpy as np
+import pytest
+
+from nanopolish_b200 import synth
+from tests.golden_cases import make_abea_cases, make_hmm_cases
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_logsum_table_and_samples(port_oracle, ref_oracle):
+    assert np.array_equal(_bits(port_oracle.logsum_table()), _bits(ref_oracle.logsum_table()))
+    rng = np.random.default_rng(0)
+    a = rng.uniform(-50, 0, 20000).astype(np.float32)
+    b = (a + rng.uniform(-20, 20, 20000)).astype(np.float32)
+    a[:50] = -np.inf
+    b[25:75] = -np.inf
+    for x, y in zip(a, b):
+        r = ref_oracle.lib.npref_add_logs(float(x), float(y))
+        p = port_oracle.lib.npo_logsum(float(x), float(y))
+        assert np.float32(r).view(np.uint32) == np.float32(p).view(np.uint32)
+
+
+@pytest.mark.parametrize("name", ["segments", "short_bias08", "methylation"])
+def test_hmm_score_bit_identical(port_oracle, ref_oracle, name):
+    case = make_hmm_cases()[name]
+    rs, jobs = case["rs"], case["jobs"]
+    ref_oracle.clear_reads()
+    handles = [ref_oracle.builtin_model(a) for a in case["alphabets"]]
+    rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, handles[0])
+    s_ref, _ = ref_oracle.score_batch(rh, jobs.jobs, jobs.seqs, handles, indel_bias=case["indel_bias"])
+    models = [synth.load_model(a) for a in case["alphabets"]]
+    s_port, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, models, jobs.kmer_ranks,
+                                            jobs.jobs, indel_bias=case["indel_bias"])
+    assert np.isfinite(s_ref).all()
+    assert np.array_equal(_bits(s_ref), _bits(s_port))
+
+
+def test_kmer_ranks_match_reference(ref_oracle):
+    """synth's numpy rank arithmetic == HMMInputSequence::get_kmer_rank (both strands, both alphabets)."""
+    case = make_hmm_cases()["segments"]
+    h = ref_oracle.builtin_model("nucleotide")
+    jobs = case["jobs"]
+    for j in range(jobs.jobs.shape[0]):
+        jb = jobs.jobs[j]
+        want = ref_oracle.kmer_ranks(h, jobs.seqs[j], bool(jb["rc"]))
+        got = jobs.kmer_ranks[int(jb["rank_off"]):int(jb["rank_off"]) + int(jb["n_kmers"])]
+        assert np.array_equal(want, got)
+    case = make_hmm_cases()["methylation"]
+    hc = ref_oracle.builtin_model("cpg")
+    jobs = case["jobs"]
+    for j in range(0, jobs.jobs.shape[0], 7):
+        jb = jobs.jobs[j]
+        want = ref_oracle.kmer_ranks(hc, jobs.seqs[j], False)
+        got = jobs.kmer_ranks[int(jb["rank_off"]):int(jb["rank_off"]) + int(jb["n_kmers"])]
+        assert np.array_equal(want, got)
+
+
+@pytest.mark.parametrize("name", ["reads_2k", "reads_short"])
+def test_abea_identical(port_oracle, ref_oracle, name):
+    rs = make_abea_cases()[name]["rs"]
+    model = synth.load_model("nucleotide")
+    ref_oracle.clear_reads()
+    h = ref_oracle.builtin_model("nucleotide")
+    rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, h)
+    seqs = [synth._CODE2DNA[c].tobytes() for c in rs.seq_codes]
+    jobs, ranks, total = synth.abea_jobs(rs)
+    caps = [int(j["pairs_cap"]) for j in jobs]
+    pr, poff, npairs, _ = ref_oracle.abea_batch(rh, h, seqs, caps)
+    pp, res, _ = port_oracle.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, model, ranks, jobs, total)
+    for i in range(len(seqs)):
+        n = int(npairs[i])
+        assert n == int(res[i]["n_pairs"]) and n > 0
+        a = pr[int(poff[i]):int(poff[i]) + n]
+        b = pp[int(jobs[i]["pairs_off"]):int(jobs[i]["pairs_off"]) + n]
+        assert np.array_equal(a[:, 0], b["ref_pos"]) and np.array_equal(a[:, 1], b["read_pos"])
+
+
+def test_abea_qc_failure_matches(port_oracle, ref_oracle):
+    """Events unrelated to the sequence: the reference returns an empty vector; so must the oracle."""
+    model = synth.load_model("nucleotide")
+    rs = synth.gen_reads(2, 400, model, seed=9, rng_scalings=False)
+    rng = np.random.default_rng(5)
+    rs.ev_mean[:] = rng.uniform(60, 120, rs.ev_mean.shape[0]).astype(np.float32)
+    ref_oracle.clear_reads()
+    h = ref_oracle.builtin_model("nucleotide")
+    rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, h)
+    seqs = [synth._CODE2DNA[c].tobytes() for c in rs.seq_codes]
+    jobs, ranks, total = synth.abea_jobs(rs)
+    _, _, npairs, _ = ref_oracle.abea_batch(rh, h, seqs, [int(j["pairs_cap"]) for j in jobs])
+    _, res, _ = port_oracle.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, model, ranks, jobs, total)
+    assert list(npairs) == [int(x) for x in res["n_pairs"]]
+
+
+def test_mom_matches(port_oracle, ref_oracle):
+    model = synth.load_model("nucleotide")
+    rs = synth.gen_reads(3, 800, model, seed=77)
+    ref_oracle.clear_reads()
+    h = ref_oracle.builtin_model("nucleotide")
+    rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, h)
+    jobs, ranks, _ = synth.abea_jobs(rs)
+    for i in range(rs.n_reads):
+        want = ref_oracle.mom(rh[i], h, synth._CODE2DNA[rs.seq_codes[i]].tobytes())
+        sh, sc = port_oracle.mom(rs.reads, rs.ev_mean, model, ranks, jobs[i])
+        assert want[0] == sh and want[1] == sc and want[2] == 0.0 and want[3] == 1.0
