@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py — HMM-scored events/sec through profile_hmm_score on synthetic R9.4 reads.
+
+    python bench.py --gpus N --steps K --warmup W                 # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's CPU path on host cores
+
+Workload (BASELINE.json configs[1]): scorereads-shaped jobs — synthetic reads x 4000 events, k=6
+r9.4_450bps nucleotide model, 500-event segments (E=501, K~290), flags 0; --reads per GPU (default
+10000 => ~60k jobs, 3.0e7 scored events per step).  One "step" = one pass of the forward kernel over
+the whole resident batch.  Weak scaling: every rank owns its own --reads reads (seeded by rank) and
+the per-job scores are gathered to rank 0 with one NCCL gather per step.
+
+JSON line keys follow the driver's contract; see DESIGN.md "Measurement" for what each means here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hmm_scored_events_per_sec"
+UNIT = "events/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="scorereads", choices=["scorereads", "methylation"])
+    ap.add_argument("--reads", type=int, default=10000, help="reads per GPU")
+    ap.add_argument("--events", type=int, default=4000, help="events per read")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.lines = []
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()          # the exact PID we started
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smmax = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smmax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(args, rank):
+    from nanopolish_b200 import synth
+    nuc = synth.load_model("nucleotide")
+    models = [nuc]
+    seed = 42 + 1_000_003 * rank
+    if args.workload == "scorereads":
+        rs = synth.gen_reads(args.reads, args.events, nuc, seed=seed)
+        jobs = synth.scorereads_jobs(rs, 500, model_id=0)
+    else:
+        cpg = synth.load_model("cpg")
+        models.append(cpg)
+        rs = synth.gen_reads(args.reads, args.events, nuc, seed=seed, cpg_keep=0.3)
+        jobs = synth.methylation_jobs(rs, model_id=1)
+    return rs, jobs, models
+
+
+def algorithmic_bytes(jobs, k=6):
+    """B_alg = 4*E + L + 36 bytes per job (event levels as f32, base codes, job record, score)."""
+    j = jobs.jobs
+    E = np.abs(j["event_stop"].astype(np.int64) - j["event_start"].astype(np.int64)) + 1
+    L = j["n_kmers"].astype(np.int64) + (k - 1)
+    return int((4 * E + L + 36).sum())
+
+
+class CpuArm:
+    """The reference's CPU path (oracle/_ref when it was compiled, else the plain-C port) over a bounded
+    sample of the same job list, OpenMP over jobs with all host threads — the way the reference
+    parallelises over reads (src/common/nanopolish_bam_processor.cpp:99)."""
+
+    def __init__(self, rs, jobs, models, want_ref=True):
+        from oracle.oracle_py import PortOracle, RefOracle
+        self.rs, self.jobs, self.models = rs, jobs, models
+        self.cores = os.cpu_count() or 1
+        j = jobs.jobs
+        self.E = np.abs(j["event_stop"].astype(np.int64) - j["event_start"].astype(np.int64)) + 1
+        self.cells = self.E * j["n_kmers"].astype(np.int64)
+        self.use_ref = want_ref and RefOracle.available()
+        if self.use_ref:
+            self.ref = RefOracle()
+            self.mh = [self.ref.builtin_model(m.alphabet) for m in models]
+            max_read = int(min(rs.n_reads, 2048))      # only reads the bounded sample can touch
+            self.rh = self.ref.register_reads(rs.reads[:max_read], rs.ev_mean, rs.ev_start_time, self.mh[0])
+            self.eligible = np.flatnonzero(j["read"] < max_read)
+        else:
+            self.port = PortOracle()
+            self.eligible = np.arange(j.shape[0])
+        self._seq_cache = {}
+
+    def _seq(self, jb):
+        """the harness takes sequences as strings: rebuild one from the job's forward k-mer ranks"""
+        key = int(jb["rank_off"])
+        if key not in self._seq_cache:
+            r = self.jobs.kmer_ranks[key:key + int(jb["n_kmers"])]
+            asz = self.models[int(jb["model_id"])].alphabet_size
+            first = [(int(r[0]) // asz ** (5 - i)) % asz for i in range(6)]
+            alpha = b"ACGT" if asz == 4 else b"ACGMT"
+            self._seq_cache[key] = bytes(alpha[c] for c in first + (r[1:] % asz).tolist())
+        return self._seq_cache[key]
+
+    def time(self, idx):
+        sub = np.ascontiguousarray(self.jobs.jobs[idx])
+        if self.use_ref:
+            seqs = [self._seq(jb) for jb in sub]
+            _, secs = self.ref.score_batch(self.rh, sub, seqs, self.mh, threads=self.cores)
+        else:
+            _, secs = self.port.hmm_score_batch(self.rs.reads, self.rs.ev_mean, self.rs.ev_start_time, self.models,
+                                                self.jobs.kmer_ranks, sub, threads=self.cores)
+        return secs
+
+    def sample_for(self, seconds_target):
+        cal = self.eligible[:max(2 * self.cores, 16)]
+        t_cal = self.time(cal)
+        rate = self.cells[cal].sum() / max(t_cal, 1e-6)
+        csum = np.cumsum(self.cells[self.eligible])
+        m = int(np.searchsorted(csum, rate * seconds_target)) + 1
+        return self.eligible[:min(m, self.eligible.shape[0])]
+
+    def report(self, idx, secs):
+        ev = int(self.E[idx].sum())
+        return {"value": ev / secs, "unit": UNIT, "cores": self.cores,
+                "kind": "reference" if self.use_ref else "port",
+                "sample": f"{idx.shape[0]} jobs ({ev} scored events, {int(self.cells[idx].sum())} block-cells) of the "
+                          f"same job list, {secs:.2f} s per pass, OpenMP over jobs with {self.cores} threads",
+                "block_cells_per_sec": float(self.cells[idx].sum() / secs)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores.
+    Rank 0 alone runs it; each step is one pass over a bounded sample of the workload's job list."""
+    if rank != 0:
+        return
+    small = argparse.Namespace(**{**vars(args), "reads": min(args.reads, 2048)})
+    rs, jobs, models = build_workload(small, 0)
+    arm = CpuArm(rs, jobs, models)
+    steps, warm = args.steps, args.warmup
+    per_step = max(0.5, min(6.0, 120.0 / max(1, steps + warm)))   # whole run within a few minutes
+    idx = arm.sample_for(per_step)
+    for _ in range(warm):
+        arm.time(idx)
+    secs = [arm.time(idx) for _ in range(steps)]
+    mean_s = float(np.mean(secs))
+    base = arm.report(idx, mean_s)
+    full = argparse.Namespace(**vars(args))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": mean_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(full, jobs, reads_override=args.reads),
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, jobs, reads_override=None):
+    j = jobs.jobs
+    E = np.abs(j["event_stop"].astype(np.int64) - j["event_start"].astype(np.int64)) + 1
+    return {"workload": f"{args.workload}: synthetic R9.4 reads x {args.events} events, k=6 r9.4_450bps "
+                        + ("nucleotide model, 500-event segments, flags 0" if args.workload == "scorereads"
+                           else "cpg model, CpG-group windows u/m pairs, flags PRE|POST"),
+            "reads_per_gpu": reads_override or args.reads, "events_per_read": args.events,
+            "mean_E": float(E.mean()), "mean_K": float(j["n_kmers"].mean()),
+            "parallelism": f"read-shard x{args.gpus}", "l2": "inputs larger than L2 (levels+ranks+scratch > 126 MB)"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from nanopolish_b200.engine import Engine
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    rs, jobs, models = build_workload(args, rank)
+    n_jobs = int(jobs.jobs.shape[0])
+    stream = torch.cuda.current_stream().cuda_stream
+    eng = Engine(local, stream=stream)
+    for m in models:
+        eng.model_upload(m)
+
+    # pinned host copies (the caller-owned host buffers of the e2e path)
+    def pin(a):
+        t = torch.from_numpy(a).pin_memory()
+        return t, t.numpy()
+    keep = []
+    t_reads, h_reads = pin(rs.reads.view(np.uint8)); keep.append(t_reads); h_reads = h_reads.view(rs.reads.dtype)
+    t_mean, h_mean = pin(rs.ev_mean); keep.append(t_mean)
+    t_time, h_time = pin(rs.ev_start_time); keep.append(t_time)
+    t_ranks, h_ranks = pin(jobs.kmer_ranks); keep.append(t_ranks)
+    t_jobs, h_jobs = pin(jobs.jobs.view(np.uint8)); keep.append(t_jobs); h_jobs = h_jobs.view(jobs.jobs.dtype)
+    t_out = torch.empty(n_jobs, dtype=torch.float32).pin_memory(); h_out = t_out.numpy()
+
+    # ---- device-resident arm: inputs already in HBM when the timed region starts ----------
+    eng.reads_load(h_reads, h_mean, h_time)
+    eng.hmm_jobs_load(h_ranks, h_jobs)
+    scores = torch.empty(n_jobs, dtype=torch.float32, device=dev)
+    counts = None
+    gathered = None
+    if world > 1:
+        cnt = torch.tensor([n_jobs], dtype=torch.int64, device=dev)
+        allc = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(allc, cnt)
+        counts = [int(c.item()) for c in allc]
+        maxc = max(counts)
+        scores = torch.zeros(maxc, dtype=torch.float32, device=dev)   # padded so one ncclGather suffices
+        gathered = [torch.empty(maxc, dtype=torch.float32, device=dev) for _ in range(world)] if rank == 0 else None
+
+    def step():
+        eng.hmm_score(scores.data_ptr())
+        if world > 1:
+            dist.gather(scores, gathered, dst=0)      # one NCCL gather of per-job log-likelihoods over NVLink
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    km, launches_per_step = eng.last_kernel_ms()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # kernel-only duration for the roofline: CUDA events around each kernel sequence, on its stream
+    for _ in range(5):
+        eng.hmm_score(scores.data_ptr()); eng.sync()
+        kern_ms.append(eng.last_kernel_ms()[0])
+    kernel_ms = float(np.mean(kern_ms))
+
+    ev_local = int(jobs.scored_events)
+    ev_t = torch.tensor([ev_local], dtype=torch.float64, device=dev)
+    cells_t = torch.tensor([float(jobs.block_cells)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ev_t); dist.all_reduce(cells_t)
+    ev_all, cells_all = float(ev_t.item()), float(cells_t.item())
+    value = ev_all * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e arm: the one-shot C-ABI call with HOST buffers, H2D + D2H inside the timed region ----
+    def e2e_step():
+        eng.hmm_score_batch(h_reads, h_mean, h_time, h_ranks, h_jobs, out=h_out)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = ev_all * e2e_steps / e2e_s
+    any_drift = bool((rs.reads["drift"] != 0).any())
+    h2d = rs.reads.nbytes + rs.ev_mean.nbytes + (rs.ev_start_time.nbytes if any_drift else 0) + jobs.kmer_ranks.nbytes \
+        + jobs.jobs.nbytes + 4 * n_jobs + 8 * rs.n_reads
+    d2h = 4 * n_jobs
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        b_alg = algorithmic_bytes(jobs)
+        achieved = b_alg / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_hmm_forward_traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                if tj.get("workload") == args.workload and tj.get("reads") == args.reads:
+                    traffic = tj.get("dram_bytes_per_step")
+            except Exception:
+                pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {**workload_config(args, jobs), "jobs_per_gpu": n_jobs,
+                       "scored_events_per_step": ev_all},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "api": "nph_hmm_score_batch (host buffers in, host scores out)"},
+            "gpu_launches": int(launches_per_step) * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "hmm_forward_kernel<C>",
+                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_step": b_alg,
+                         "note": "scalar log-semiring DP: issue/shared-memory bound, not HBM bound (DESIGN.md); "
+                                 "block-cells/s below is the figure that moves",
+                         "block_cells_per_sec_per_gpu": float(jobs.block_cells) / (kernel_ms * 1e-3),
+                         "issue_bound_estimate_cells_per_sec": 2.5e11},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                arm = CpuArm(rs, jobs, models)
+                idx = arm.sample_for(12.0)
+                line["cpu_baseline"] = arm.report(idx, arm.time(idx))
+            except Exception as ex:   # the baseline is a reported extra; never lose the GPU line over it
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable",
+                                        "sample": f"failed: {ex}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,7 @@
 //     intrinsics (no FMA contraction), IEEE division included, so scores are bit-identical.
 //   * persistent CTAs (one per SM), warps pull jobs (heaviest first) from an atomic counter.
 #include "nph_internal.cuh"
+#include "exact_math.cuh"
 #include <math_constants.h>
 #include <algorithm>
 #include <cmath>
@@ -48,27 +49,13 @@ struct FwdParams {
     const float* logsum_g;
     const float* flank;
     float* scores;
-    float4* scratch_params;       // per warp: kpad_stride float4 {mu', sigma', log(1/sqrt(2pi)) - log sigma', 0}
+    float4* scratch_params;       // per warp: kpad_stride float4 {mu', sigma', log(1/sqrt(2pi)) - log sigma', RN(1/sigma')}
     float* scratch_edge;          // per warp: 3 * edge_stride floats
     uint32_t kpad_stride;
     uint32_t edge_stride;
+    uint32_t lsum_bias;           // NPH_LOGSUM_ADDR_BIAS, passed at run time on purpose (exact_math.cuh)
     HmmConsts c;
 };
-
-// Quantised log-sum: max + tbl[(int)((max-min)*1000)], or max when min == -inf or max-min >= 15.7.
-// The clamp to 15700 lands on a zero table entry, which also covers min == -inf (difference +inf)
-// and both -inf (difference NaN -> fminf picks 15700 -> -inf + 0).  floor() of the non-negative
-// scaled difference is taken by adding 2^23 with round-down: the integer appears in the mantissa.
-__device__ __forceinline__ float lsum(float a, float b, const float* __restrict__ tbl)
-{
-    const float mx = fmaxf(a, b);
-    const float mn = fminf(a, b);
-    const float d = __fsub_rn(mx, mn);
-    const float t = fminf(__fmul_rn(d, 1000.0f), (float)NPH_LOGSUM_CUT);
-    const float u = __fadd_rd(t, 8388608.0f);
-    const int idx = __float_as_int(u) & 0x7fffff;
-    return __fadd_rn(mx, tbl[idx]);
-}
 
 template <int C>
 __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdParams p)
@@ -76,6 +63,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
     extern __shared__ float s_tbl[];
     for (int i = threadIdx.x; i < NPH_TBL_SMEM; i += kCtaThreads) s_tbl[i] = p.logsum_g[i];
     __syncthreads();
+    const LogsumTable tb = make_logsum_table(s_tbl, p.lsum_bias);
 
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
@@ -116,13 +104,13 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
         {
             const uint32_t* rk = p.ranks + job.rank_off;
             for (int i = lane; i < kpad; i += 32) {
-                float4 g = make_float4(0.f, 1.f, 0.f, 0.f);
+                float4 g = make_float4(0.f, 1.f, 0.f, 1.f);
                 if (i < K) {
                     const uint32_t r = rk[i];
                     const float mu = (float)__dadd_rn(__dmul_rn(rd.scale, mv.mean[r]), rd.shift);
                     const float sd = (float)__dmul_rn(mv.stdv[r], rd.var);
                     const float lsd = (float)__dadd_rn(mv.log_stdv[r], rd.log_var);
-                    g = make_float4(mu, sd, __fsub_rn(p.c.log_inv_sqrt_2pi, lsd), 0.f);
+                    g = make_float4(mu, sd, __fsub_rn(p.c.log_inv_sqrt_2pi, lsd), __frcp_rn(sd));
                 }
                 my_params[i] = g;
             }
@@ -139,10 +127,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
         const int end_slot = (last_col - last_strip * strip_cols) % C;
         const int total_steps = last_strip * P + E + end_lane;   // lanes beyond end_lane own no column of the last strip
 
-        float mu[C], sd[C], cc[C];
+        float mu[C], sd[C], cc[C], ry[C];
         float Mp[C], Bp[C], Kp[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) { mu[c] = 0.f; sd[c] = 1.f; cc[c] = 0.f; Mp[c] = NEG; Bp[c] = NEG; Kp[c] = NEG; }
+        for (int c = 0; c < C; ++c) { mu[c] = 0.f; sd[c] = 1.f; cc[c] = 0.f; ry[c] = 1.f; Mp[c] = NEG; Bp[c] = NEG; Kp[c] = NEG; }
         float Lm_prev = NEG, Lb_prev = NEG, Lk_prev = NEG;
         float lp_end = NEG;
         int r = 1 - lane;      // row of this lane at the current step (rows 1..P; <1 = not started)
@@ -172,7 +160,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         const float4 g4 = my_params[col0 + c];
-                        mu[c] = g4.x; sd[c] = g4.y; cc[c] = g4.z;
+                        mu[c] = g4.x; sd[c] = g4.y; cc[c] = g4.z; ry[c] = g4.w;
                     }
                 }
             }
@@ -196,37 +184,38 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
 
                 float lm_prev = Lm_prev, lb_prev = Lb_prev, lk_prev = Lk_prev;   // left column, row r-1
                 float lm_cur = Lm, lb_cur = Lb, lk_cur = Lk;                      // left column, row r
-                float Me = NEG, Be = NEG, Ke = NEG;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     // Gaussian log-density, reference operation order (emissions.h:51-55)
-                    const float a = __fdiv_rn(__fsub_rn(x, mu[c]), sd[c]);
+                    const float a = div_by_cached_rcp(__fsub_rn(x, mu[c]), sd[c], ry[c]);
                     const float em = __fadd_rn(cc[c], __fmul_rn(__fmul_rn(-0.5f, a), a));
                     // match: left fold over {same M, prev M, same B, prev B, prev K, soft}
                     float m = __fadd_rn(lp_mm_self, Mp[c]);
-                    m = lsum(m, __fadd_rn(lp_mm_next, lm_prev), s_tbl);
-                    m = lsum(m, __fadd_rn(lp_bm_self, Bp[c]), s_tbl);
-                    m = lsum(m, __fadd_rn(lp_bm_next, lb_prev), s_tbl);
-                    m = lsum(m, __fadd_rn(lp_km, lk_prev), s_tbl);
-                    if (c == 0) m = lsum(m, soft, s_tbl);
+                    m = lsum(m, __fadd_rn(lp_mm_next, lm_prev), tb);
+                    m = lsum(m, __fadd_rn(lp_bm_self, Bp[c]), tb);
+                    m = lsum(m, __fadd_rn(lp_bm_next, lb_prev), tb);
+                    m = lsum(m, __fadd_rn(lp_km, lk_prev), tb);
+                    if (c == 0) m = lsum(m, soft, tb);
                     m = __fadd_rn(m, em);
                     // bad event: {same M, same B}
-                    const float b = lsum(__fadd_rn(lp_mb, Mp[c]), __fadd_rn(lp_bb, Bp[c]), s_tbl);
+                    const float b = lsum(__fadd_rn(lp_mb, Mp[c]), __fadd_rn(lp_bb, Bp[c]), tb);
                     // k-mer skip: {prev M, prev B, prev K} of the SAME row
-                    float kk = lsum(__fadd_rn(lp_mk, lm_cur), __fadd_rn(lp_bk, lb_cur), s_tbl);
-                    kk = lsum(kk, __fadd_rn(lp_kk, lk_cur), s_tbl);
+                    float kk = lsum(__fadd_rn(lp_mk, lm_cur), __fadd_rn(lp_bk, lb_cur), tb);
+                    kk = lsum(kk, __fadd_rn(lp_kk, lk_cur), tb);
 
                     lm_prev = Mp[c]; lb_prev = Bp[c]; lk_prev = Kp[c];
                     lm_cur = m; lb_cur = b; lk_cur = kk;
                     Mp[c] = m; Bp[c] = b; Kp[c] = kk;
-                    if (c == end_slot) { Me = m; Be = b; Ke = kk; }
                 }
                 Lm_prev = Lm; Lb_prev = Lb; Lk_prev = Lk;
 
                 if (do_end) {
-                    lp_end = lsum(lp_end, __fadd_rn(Me, post), s_tbl);
-                    lp_end = lsum(lp_end, __fadd_rn(Be, post), s_tbl);
-                    lp_end = lsum(lp_end, __fadd_rn(Ke, post), s_tbl);
+                    float Me = Mp[0], Be = Bp[0], Ke = Kp[0];
+#pragma unroll
+                    for (int c = 1; c < C; ++c) if (c == end_slot) { Me = Mp[c]; Be = Bp[c]; Ke = Kp[c]; }
+                    lp_end = lsum(lp_end, __fadd_rn(Me, post), tb);
+                    lp_end = lsum(lp_end, __fadd_rn(Be, post), tb);
+                    lp_end = lsum(lp_end, __fadd_rn(Ke, post), tb);
                 }
                 if (lane == 31 && s < last_strip) {
                     edge_m[r] = Mp[C - 1]; edge_b[r] = Bp[C - 1]; edge_k[r] = Kp[C - 1];
@@ -236,7 +225,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
             // advance
             r += 1;
             if (r > P) { r = 1; s += 1; }
-            __syncwarp();
+            if (n_strips > 1) __syncwarp();   // orders lane 31's edge stores before lane 0's later loads
         }
 
         const float result = __shfl_sync(kFull, lp_end, end_lane);
@@ -322,6 +311,7 @@ int nph_launch_hmm_forward(nph_ctx* ctx, float* scores_dev)
     p.edge_stride = ctx->max_period + 8;
     p.scratch_edge = reinterpret_cast<float*>(ctx->d_scratch.p + sizeof(float4) * (size_t)ctx->max_kpad * warps);
     p.c = ctx->consts;
+    p.lsum_bias = NPH_LOGSUM_ADDR_BIAS;
 
     NPH_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned int) * 16, ctx->stream));
     NPH_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -337,7 +327,10 @@ int nph_launch_hmm_forward(nph_ctx* ctx, float* scores_dev)
             case 4: rc = launch_class<4>(ctx, p, cl, (int)ci); break;
             case 5: rc = launch_class<5>(ctx, p, cl, (int)ci); break;
             case 6: rc = launch_class<6>(ctx, p, cl, (int)ci); break;
+            case 7: rc = launch_class<7>(ctx, p, cl, (int)ci); break;
             case 8: rc = launch_class<8>(ctx, p, cl, (int)ci); break;
+            case 9: rc = launch_class<9>(ctx, p, cl, (int)ci); break;
+            case 10: rc = launch_class<10>(ctx, p, cl, (int)ci); break;
             default: return NPH_ERR_STATE;
         }
         if (rc != NPH_OK) return rc;

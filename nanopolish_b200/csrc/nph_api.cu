@@ -96,32 +96,29 @@ inline float2 read_transitions(double events_per_base, double indel_bias)
     return make_float2(logf(p_stay), logf(p_mm_next));
 }
 
-// Which kernel class (columns per lane) runs a job: minimise modelled steps x work per step.
+// Which kernel class (columns per lane, C) runs a job: minimise modelled issue slots =
+// steps x (per-step overhead + C x per-cell cost).  Constants from the ncu instruction counts
+// (profiles/): ~90 instructions per block-cell, ~110 per warp step of bookkeeping.
+const int kClassCols[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10};
+const int kNumClasses = 10;
+inline int class_index(int C) { return C - 1; }
+
 inline int choose_cols(uint32_t K, uint32_t E)
 {
-    static const int cand[] = {1, 2, 3, 4, 5, 6, 8};
     double best = 1e300;
     int best_c = 1;
-    for (int C : cand) {
+    for (int C : kClassCols) {
         uint32_t strip = 32u * C;
         uint32_t n_strips = (K + strip - 1) / strip;
         uint32_t P = n_strips > 1 ? std::max<uint32_t>(E, 40) : E;
         uint32_t last_cols = K - (n_strips - 1) * strip;
         uint32_t end_lane = (last_cols - 1) / C;
         double steps = (double)(n_strips - 1) * P + E + end_lane;
-        double cost = steps * (C + 0.6);
+        double cost = steps * (110.0 + 90.0 * C);
         if (cost < best) { best = cost; best_c = C; }
     }
     return best_c;
 }
-
-int class_index(int C)
-{
-    switch (C) { case 1: return 0; case 2: return 1; case 3: return 2; case 4: return 3; case 5: return 4; case 6: return 5; case 8: return 6; }
-    return -1;
-}
-const int kClassCols[] = {1, 2, 3, 4, 5, 6, 8};
-const int kNumClasses = 7;
 
 int create_common(nph_ctx** out, int device, bool own_stream, cudaStream_t stream)
 {
