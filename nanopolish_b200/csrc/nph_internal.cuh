@@ -93,7 +93,9 @@ struct nph_ctx {
     DevBuf<nph_abea_result> d_abea_res;
     DevBuf<uint8_t> d_abea_scratch;
     DevBuf<uint32_t> d_abea_order;
-    std::vector<uint64_t> h_abea_trace_off;
+    DevBuf<double> d_abea_consts;    // per job (lp_stay, lp_step); also the MoM output buffer
+    uint32_t abea_kmax = 0;
+    uint64_t abea_trace_stride = 0;
     bool abea_loaded = false;
 
     // measurement

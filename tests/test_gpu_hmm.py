@@ -37,8 +37,10 @@ def test_golden_cases(engine, models, port_oracle, name):
     case = make_hmm_cases()[name]
     rs, jobs = case["rs"], case["jobs"]
     mlist = [models[a][0] for a in case["alphabets"]]
-    # golden_cases uses model ids 0 (nucleotide) / 1 (cpg) == upload order in the `models` fixture
-    got = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, jobs.jobs,
+    # golden_cases numbers models 0 (nucleotide) / 1 (cpg); map to the ids this context handed out
+    dev_jobs = jobs.jobs.copy()
+    dev_jobs["model_id"] = np.array([models[a][1] for a in case["alphabets"]], np.uint32)[jobs.jobs["model_id"]]
+    got = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, dev_jobs,
                                  indel_bias=case["indel_bias"])
     gold = np.load(os.path.join(GOLD, "hmm_golden.npz"))[name]
     _check(got, gold)                          # the compiled reference's recorded output
@@ -81,7 +83,8 @@ def test_random_shapes_bit_exact(engine, models, port_oracle, shape):
     rs = synth.gen_reads(8, 2600, nuc, seed=900 + shape["kmin"], drift=True)
     rng = np.random.default_rng(shape["kmin"] * 7 + 1)
     jobs = _random_jobs(rs, rng, shape["n"], shape["kmin"], shape["kmax"], shape["emin"], shape["emax"], [0, 1, 2, 3])
-    got = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, jobs.jobs, indel_bias=0.9)
+    dev_jobs = jobs.jobs.copy(); dev_jobs["model_id"] = models["nucleotide"][1]
+    got = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, dev_jobs, indel_bias=0.9)
     want, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [nuc], jobs.kmer_ranks, jobs.jobs,
                                           indel_bias=0.9, threads=8)
     _check(got, want)
@@ -91,8 +94,9 @@ def test_methylation_calls_identical(engine, models, port_oracle):
     """LLR = ll_m - ll_u per site, call rule abs(LLR) >= 2.0*n_motif (scripts/calculate_methylation_frequency.py:26,45,49)."""
     nuc, cpg = models["nucleotide"][0], models["cpg"][0]
     rs = synth.gen_reads(30, 3000, nuc, seed=4242, cpg_keep=0.3)
-    jobs = synth.methylation_jobs(rs, model_id=models["cpg"][1])
-    got = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, jobs.jobs)
+    jobs = synth.methylation_jobs(rs, model_id=1)
+    dev_jobs = jobs.jobs.copy(); dev_jobs["model_id"] = models["cpg"][1]
+    got = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, dev_jobs)
     want, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [nuc, cpg], jobs.kmer_ranks, jobs.jobs, threads=8)
     _check(got, want)
     llr_g = got[1::2].astype(np.float64) - got[0::2]
@@ -108,7 +112,8 @@ def test_staged_api_and_rescoring(engine, models, port_oracle):
     engine.reads_load(rs.reads, rs.ev_mean, rs.ev_start_time)
     for seg, bias in [(200, 1.0), (120, 0.8)]:
         jobs = synth.scorereads_jobs(rs, seg, rc_every=2)
-        engine.hmm_jobs_load(jobs.kmer_ranks, jobs.jobs, bias)
+        dev_jobs = jobs.jobs.copy(); dev_jobs["model_id"] = models["nucleotide"][1]
+        engine.hmm_jobs_load(jobs.kmer_ranks, dev_jobs, bias)
         engine.hmm_score()
         got = engine.hmm_scores_fetch()
         want, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [nuc], jobs.kmer_ranks, jobs.jobs, indel_bias=bias, threads=8)
@@ -121,7 +126,7 @@ def test_invalid_jobs_are_rejected(engine, models):
     from nanopolish_b200._lib import NphError
     nuc = models["nucleotide"][0]
     rs = synth.gen_reads(1, 300, nuc, seed=5)
-    jobs = synth.scorereads_jobs(rs, 100)
+    jobs = synth.scorereads_jobs(rs, 100, model_id=models["nucleotide"][1])
     bad = jobs.jobs.copy()
     bad[0]["event_stop"] = 10_000            # beyond the read: the reference would read out of bounds
     with pytest.raises(NphError):
