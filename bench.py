@@ -192,7 +192,7 @@ class CpuArm:
                 "block_cells_per_sec": float(self.cells[idx].sum() / secs)}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, saved_stdout):
     """--impl reference: the reference's own CPU implementation of the path on this box's host cores.
     Rank 0 alone runs it; each step is one pass over a bounded sample of the workload's job list."""
     if rank != 0:
@@ -216,7 +216,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line, saved_stdout)
 
 
 def workload_config(args, jobs, reads_override=None):
@@ -230,13 +230,22 @@ def workload_config(args, jobs, reads_override=None):
             "parallelism": f"read-shard x{args.gpus}", "l2": "inputs larger than L2 (levels+ranks+scratch > 126 MB)"}
 
 
+def emit(line: dict, saved_stdout: int) -> None:
+    """Exactly one JSON line on the real stdout (libraries such as NCCL print banners to fd 1)."""
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)            # anything a library prints goes to stderr; the JSON line is emitted via emit()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, saved_stdout)
         return
 
     import torch
@@ -281,12 +290,12 @@ def main():
         counts = [int(c.item()) for c in allc]
         maxc = max(counts)
         scores = torch.zeros(maxc, dtype=torch.float32, device=dev)   # padded so one ncclGather suffices
-        gathered = [torch.empty(maxc, dtype=torch.float32, device=dev) for _ in range(world)] if rank == 0 else None
+    from nanopolish_b200.dist import gather_to_rank0
 
     def step():
         eng.hmm_score(scores.data_ptr())
         if world > 1:
-            dist.gather(scores, gathered, dst=0)      # one NCCL gather of per-job log-likelihoods over NVLink
+            gather_to_rank0(scores, counts)           # one NCCL gather of per-job log-likelihoods over NVLink
 
     def barrier():
         if world > 1:
@@ -391,7 +400,7 @@ def main():
             except Exception as ex:   # the baseline is a reported extra; never lose the GPU line over it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable",
                                         "sample": f"failed: {ex}"}
-        print(json.dumps(line))
+        emit(line, saved_stdout)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -1,0 +1,65 @@
+"""The N>1 path on CPU: world_size-2 gloo.  Each rank scores its shard of reads (with the oracle here —
+there is no GPU in this container; on the GPU box the same plumbing carries the CUDA scores over NCCL),
+rank 0 gathers with ONE padded gather and must reproduce the single-process job order and values."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nanopolish_b200 import synth
+from nanopolish_b200.dist import gather_to_rank0, job_owner, partition_reads, scatter_results
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle_py import PortOracle
+    model = synth.load_model("nucleotide")
+    rs = synth.gen_reads(7, 900, model, seed=3)
+    rs.reads["n_events"]  # same data on every rank (deterministic); each scores only its shard
+    jobs = synth.scorereads_jobs(rs, 150, rc_every=3)
+    parts = partition_reads(rs.reads["n_events"], world)
+    owner = job_owner(jobs.jobs["read"], parts)
+    mine = np.flatnonzero(owner == rank)
+    port_o = PortOracle()
+    local, _ = port_o.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [model], jobs.kmer_ranks,
+                                      np.ascontiguousarray(jobs.jobs[mine]))
+    got = gather_to_rank0(torch.from_numpy(local))
+    if rank == 0:
+        full = scatter_results(got, owner)
+        want, _ = port_o.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [model], jobs.kmer_ranks, jobs.jobs)
+        np.save(out_path, np.stack([full, want]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_partition_is_balanced_and_complete():
+    rng = np.random.default_rng(0)
+    n = rng.integers(500, 9000, 1000)
+    for world in (1, 2, 4, 8):
+        parts = partition_reads(n, world)
+        allidx = np.sort(np.concatenate(parts))
+        assert np.array_equal(allidx, np.arange(1000))
+        loads = np.array([n[p].sum() for p in parts])
+        assert loads.max() - loads.min() <= n.max()
+        for p in parts:
+            assert np.all(np.diff(p) > 0)
+
+
+def test_two_rank_gather_matches_single_process(tmp_path):
+    out = str(tmp_path / "res.npy")
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    full, want = np.load(out)
+    assert np.array_equal(full.view(np.uint32), want.view(np.uint32))
