@@ -1,0 +1,448 @@
+// nph_host.cpp — implementation of the C++ host mirror (see nph_host.hpp).
+#include "nph_host.hpp"
+
+#include <algorithm>
+#include <cctype>
+#include <cstdlib>
+#include <cstring>
+
+namespace nph {
+
+double hmm_indel_bias_factor = 1.0;
+
+// ---------------------------------------------------------------------------------------------
+// Alphabet.  Behaviour follows src/common/nanopolish_alphabet.h:27-330 (match_to_site, reverse_complement,
+// disambiguate, methylate, unmethylate, is_motif_match) and the tables of nanopolish_alphabet.cpp:15-194.
+// ---------------------------------------------------------------------------------------------
+Alphabet::Alphabet(const char* name, const char* bases, const char* complements,
+                   std::vector<std::string> sites, std::vector<std::string> sites_methylated,
+                   std::vector<std::string> sites_methylated_complement)
+    : m_name(name), m_bases(bases), m_complement(complements), m_sites(std::move(sites)),
+      m_sites_m(std::move(sites_methylated)), m_sites_mc(std::move(sites_methylated_complement))
+{
+    std::memset(m_rank, 0, sizeof(m_rank));          // unknown symbols rank 0, like the reference's tables
+    for (size_t i = 0; i < m_bases.size(); ++i) m_rank[(unsigned char)m_bases[i]] = (uint8_t)i;
+}
+
+const Alphabet gDNAAlphabet("nucleotide", "ACGT", "TGCA", {}, {}, {});
+const Alphabet gUtoTRNAAlphabet("u_to_t_rna", "ACGT", "TGCA", {}, {}, {});
+const Alphabet gMCpGAlphabet("cpg", "ACGMT", "TGCGA", {"CG"}, {"MG"}, {"GM"});
+const Alphabet gMethylGpCAlphabet("gpc", "ACGMT", "TGCGA", {"GC"}, {"GM"}, {"MG"});
+const Alphabet gMethylDamAlphabet("dam", "ACGMT", "TGCTA", {"GATC"}, {"GMTC"}, {"CTMG"});
+const Alphabet gMethylDcmAlphabet("dcm", "ACGMT", "TGCGA", {"CCAGG", "CCTGG"}, {"CMAGG", "CMTGG"}, {"GGTMC", "GGAMC"});
+
+static const Alphabet* const kAlphabets[] = {&gDNAAlphabet, &gMCpGAlphabet, &gMethylGpCAlphabet,
+                                             &gMethylDamAlphabet, &gMethylDcmAlphabet, &gUtoTRNAAlphabet};
+
+const Alphabet* get_alphabet_by_name(const std::string& name)
+{
+    for (const Alphabet* a : kAlphabets)
+        if (name == a->get_name()) return a;
+    throw Error(NPH_ERR_INVALID, "unknown alphabet name: " + name);   // the reference exits here
+}
+
+const Alphabet* best_alphabet(const char* bases)
+{
+    for (const Alphabet* a : kAlphabets)
+        if (a->contains_all(bases)) return a;
+    return nullptr;
+}
+
+bool Alphabet::contains_all(const char* bases) const
+{
+    return std::strspn(bases, m_bases.c_str()) == std::strlen(bases);
+}
+
+void Alphabet::lexicographic_next(std::string& str) const
+{
+    int carry = 1;
+    int i = (int)str.size() - 1;
+    do {
+        uint32_t r = rank(str[i]) + carry;
+        str[i] = base((uint8_t)(r % size()));
+        carry = (int)(r / size());
+        i -= 1;
+    } while (carry > 0 && i >= 0);
+}
+
+// Does a recognition site start at position i of str?  Two cases, as in the reference:
+//  (1) i == 0 and the whole string is a substring of the site; (2) the suffix str[i..] starts with a
+//  prefix of the site (a site cut off by the end of the string still matches).
+Alphabet::Match Alphabet::match_to_site(const std::string& str, size_t i, const std::string& site) const
+{
+    Match m;
+    const size_t rl = recognition_length();
+    const char* p = std::strstr(site.c_str(), str.c_str());
+    if (i == 0 && p != nullptr) {
+        m.offset = (unsigned)(p - site.c_str());
+        m.length = (unsigned)str.length();
+    } else {
+        size_t cl = std::min(rl, str.length() - i);
+        if (str.compare(i, cl, site, 0, cl) == 0) {
+            m.offset = 0;
+            m.length = (unsigned)cl;
+        }
+    }
+    if (m.length > 0)
+        m.covers_methylated_site = str.substr(i, m.length).find_first_of(METHYLATED_SYMBOL) != std::string::npos;
+    return m;
+}
+
+std::string Alphabet::reverse_complement(const std::string& str) const
+{
+    std::string out(str.length(), 'A');
+    size_t i = 0;
+    int j = (int)str.length() - 1;
+    while (i < str.length()) {
+        int site = -1;
+        Match m;
+        for (size_t s = 0; s < num_recognition_sites(); ++s) {
+            m = match_to_site(str, i, m_sites_m[s]);
+            if (m.length > 0 && m.covers_methylated_site) { site = (int)s; break; }
+        }
+        if (site != -1) {
+            // a methylated site: emit the methylated complement of the matched part
+            for (size_t t = m.offset; t < m.offset + m.length; ++t) {
+                out[j--] = m_sites_mc[site][t];
+                i += 1;
+            }
+        } else {
+            out[j--] = complement(str[i++]);
+        }
+    }
+    return out;
+}
+
+static char iupac_first(char c)
+{
+    switch (c) {
+        case 'A': case 'M': case 'R': case 'W': case 'V': case 'H': case 'D': case 'N': return 'A';
+        case 'C': case 'S': case 'Y': case 'B': return 'C';
+        case 'G': case 'K': return 'G';
+        case 'T': return 'T';
+    }
+    throw Error(NPH_ERR_INVALID, std::string("invalid IUPAC symbol: ") + c);   // the reference asserts
+}
+
+std::string Alphabet::disambiguate(const std::string& str) const
+{
+    std::string out(str);
+    std::transform(out.begin(), out.end(), out.begin(), [](unsigned char c) { return (char)std::toupper(c); });
+    size_t i = 0;
+    while (i < out.length()) {
+        size_t stride = 1;
+        bool is_site = false;
+        for (size_t s = 0; s < num_recognition_sites(); ++s) {
+            Match m = match_to_site(out, i, m_sites_m[s]);
+            if (m.length > 0) { stride = m.length; is_site = true; break; }
+        }
+        if (!is_site) { out[i] = iupac_first(out[i]); stride = 1; }
+        i += stride;
+    }
+    return out;
+}
+
+std::string Alphabet::methylate(const std::string& str) const
+{
+    std::string out(str);
+    size_t i = 0;
+    while (i < out.length()) {
+        size_t stride = 1;
+        for (size_t s = 0; s < num_recognition_sites(); ++s) {
+            Match m = match_to_site(str, i, m_sites[s]);
+            if (m.length == recognition_length()) {     // only complete sites are methylated
+                out.replace(i, recognition_length(), m_sites_m[s]);
+                stride = m.length;
+                break;
+            }
+        }
+        i += stride;
+    }
+    return out;
+}
+
+std::string Alphabet::unmethylate(const std::string& str) const
+{
+    std::string out(str);
+    size_t i = 0;
+    while (i < out.length()) {
+        size_t stride = 1;
+        for (size_t s = 0; s < num_recognition_sites(); ++s) {
+            Match m = match_to_site(str, i, m_sites_m[s]);
+            if (m.length > 0) {
+                out.replace(i, m.length, m_sites[s].c_str() + m.offset, m.length);
+                stride = m.length;
+                break;
+            }
+        }
+        i += stride;
+    }
+    return out;
+}
+
+bool Alphabet::is_motif_match(const std::string& str, size_t i) const
+{
+    for (size_t s = 0; s < num_recognition_sites(); ++s) {
+        Match m = match_to_site(str, i, m_sites[s]);
+        if (m.length == recognition_length()) return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Engine
+// ---------------------------------------------------------------------------------------------
+void Engine::check(int status, const char* what) const
+{
+    if (status != NPH_OK)
+        throw Error(status, std::string(what) + ": " + nph_strerror(status) + (m_ctx ? std::string(" / ") + nph_last_error(m_ctx) : ""));
+}
+
+Engine::Engine(int device)
+{
+    int rc = nph_create(&m_ctx, device);
+    if (rc != NPH_OK) { m_ctx = nullptr; check(rc, "nph_create"); }
+}
+
+Engine::~Engine()
+{
+    if (m_ctx) nph_destroy(m_ctx);
+}
+
+Engine& Engine::thread_default()
+{
+    thread_local std::unique_ptr<Engine> eng;
+    if (!eng) {
+        const char* d = std::getenv("NPH_DEVICE");
+        eng.reset(new Engine(d ? std::atoi(d) : 0));
+    }
+    return *eng;
+}
+
+uint32_t Engine::model_id(const PoreModel* model)
+{
+    auto it = m_models.find(model);
+    if (it != m_models.end()) return it->second;
+    const size_t n = model->states.size();
+    std::vector<double> mean(n), sd(n), lsd(n);
+    for (size_t i = 0; i < n; ++i) {
+        mean[i] = model->states[i].level_mean;
+        sd[i] = model->states[i].level_stdv;
+        lsd[i] = model->states[i].level_log_stdv;
+    }
+    uint32_t id = 0;
+    check(nph_model_upload(m_ctx, mean.data(), sd.data(), lsd.data(), (uint32_t)n, model->k, model->pmalphabet->size(), &id),
+          "nph_model_upload");
+    m_models[model] = id;
+    return id;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batches
+// ---------------------------------------------------------------------------------------------
+static void flatten_reads(const std::vector<std::pair<const SquiggleRead*, uint8_t>>& reads, std::vector<nph_read>& out,
+                          std::vector<float>& mean, std::vector<double>& time)
+{
+    out.resize(reads.size());
+    size_t total = 0;
+    for (auto& r : reads) total += r.first->events[r.second].size();
+    mean.resize(total);
+    time.resize(total);
+    size_t off = 0;
+    for (size_t i = 0; i < reads.size(); ++i) {
+        const SquiggleRead* sr = reads[i].first;
+        const uint8_t st = reads[i].second;
+        const std::vector<SquiggleEvent>& ev = sr->events[st];
+        nph_read& o = out[i];
+        o.event_off = off;
+        o.n_events = (uint32_t)ev.size();
+        o.reserved = 0;
+        const SquiggleScalings& s = sr->scalings[st];
+        o.scale = s.scale; o.shift = s.shift; o.drift = s.drift; o.var = s.var; o.log_var = s.log_var;
+        o.events_per_base = sr->events_per_base[st];
+        for (size_t e = 0; e < ev.size(); ++e) { mean[off + e] = ev[e].mean; time[off + e] = ev[e].start_time; }
+        off += ev.size();
+    }
+}
+
+size_t HmmBatch::add(const HMMInputSequence& sequence, const HMMInputData& data, uint32_t flags)
+{
+    if (!data.read || !data.pore_model) throw Error(NPH_ERR_INVALID, "HMMInputData without read or pore_model");
+    if (data.read->pore_type != PORETYPE_R9) throw Error(NPH_ERR_UNSUPPORTED, "only R9 reads are supported (load_from_raw always makes R9)");
+    const uint32_t k = data.pore_model->k;
+    if (data.pore_model->states.size() != sequence.get_num_kmer_ranks(k))
+        throw Error(NPH_ERR_INVALID, "sequence alphabet does not match the pore model's state space");   // ref asserts (profile_hmm_r9.inl:305)
+    if (!((data.rc && data.event_stride == -1) || (!data.rc && data.event_stride == 1)))
+        throw Error(NPH_ERR_INVALID, "rc and event_stride disagree");                                       // ref asserts (profile_hmm_r9.inl:275)
+    if (sequence.length() < k) throw Error(NPH_ERR_INVALID, "sequence shorter than k");
+    ReadKey key{data.read, data.strand};
+    auto it = m_read_index.find(key);
+    uint32_t ridx;
+    if (it == m_read_index.end()) {
+        ridx = (uint32_t)m_reads.size();
+        m_read_index[key] = ridx;
+        m_reads.push_back(key);
+    } else {
+        ridx = it->second;
+    }
+    const uint32_t n_kmers = (uint32_t)(sequence.length() - k + 1);
+    nph_hmm_job j;
+    j.rank_off = m_ranks.size();
+    j.read = ridx;
+    j.model_id = 0;   // resolved against the engine in run()
+    j.event_start = data.event_start_idx;
+    j.event_stop = data.event_stop_idx;
+    j.n_kmers = n_kmers;
+    j.stride = data.event_stride;
+    j.rc = data.rc;
+    j.flags = (uint8_t)flags;
+    j.reserved = 0;
+    for (uint32_t ki = 0; ki < n_kmers; ++ki) m_ranks.push_back(sequence.get_kmer_rank(ki, k, data.rc != 0));
+    m_jobs.push_back(j);
+    m_job_models.push_back(data.pore_model);
+    return m_jobs.size() - 1;
+}
+
+void HmmBatch::clear()
+{
+    m_read_index.clear(); m_reads.clear(); m_job_models.clear(); m_jobs.clear(); m_ranks.clear();
+}
+
+std::vector<float> HmmBatch::run(Engine& engine, double indel_bias)
+{
+    std::vector<float> scores(m_jobs.size());
+    if (m_jobs.empty()) return scores;
+    for (size_t j = 0; j < m_jobs.size(); ++j) m_jobs[j].model_id = engine.model_id(m_job_models[j]);
+    std::vector<std::pair<const SquiggleRead*, uint8_t>> rl;
+    for (auto& r : m_reads) rl.push_back({r.read, r.strand});
+    std::vector<nph_read> reads;
+    std::vector<float> mean;
+    std::vector<double> time;
+    flatten_reads(rl, reads, mean, time);
+    engine.check(nph_hmm_score_batch(engine.ctx(), reads.data(), reads.size(), mean.data(), time.data(), mean.size(),
+                                     m_ranks.data(), m_ranks.size(), m_jobs.data(), m_jobs.size(), indel_bias, scores.data()),
+                 "nph_hmm_score_batch");
+    return scores;
+}
+
+size_t AbeaBatch::add(SquiggleRead& read, const PoreModel& pore_model, const std::string& sequence)
+{
+    if (m_model && m_model != &pore_model) throw Error(NPH_ERR_INVALID, "one pore model per AbeaBatch");
+    m_model = &pore_model;
+    const uint32_t k = pore_model.k;
+    if (sequence.size() < k || read.events[0].empty()) throw Error(NPH_ERR_INVALID, "empty read or sequence shorter than k");
+    const uint32_t n_kmers = (uint32_t)(sequence.size() - k + 1);
+    nph_abea_job j;
+    j.rank_off = m_ranks.size();
+    j.pairs_off = m_pairs_total;
+    j.read = (uint32_t)m_reads.size();
+    j.n_kmers = n_kmers;
+    j.pairs_cap = (uint32_t)read.events[0].size() + n_kmers;
+    j.reserved = 0;
+    for (uint32_t i = 0; i < n_kmers; ++i) m_ranks.push_back(pore_model.pmalphabet->kmer_rank(sequence.c_str() + i, k));
+    m_pairs_total += j.pairs_cap;
+    m_reads.push_back(&read);
+    m_jobs.push_back(j);
+    return m_jobs.size() - 1;
+}
+
+void AbeaBatch::clear()
+{
+    m_reads.clear(); m_jobs.clear(); m_ranks.clear(); m_pairs_total = 0; m_model = nullptr;
+}
+
+std::vector<std::vector<AlignedPair>> AbeaBatch::run(Engine& engine)
+{
+    std::vector<std::vector<AlignedPair>> out(m_jobs.size());
+    if (m_jobs.empty()) return out;
+    std::vector<std::pair<const SquiggleRead*, uint8_t>> rl;
+    for (auto* r : m_reads) rl.push_back({r, (uint8_t)0});    // strand 0, like the reference (raw_loader.cpp:79)
+    std::vector<nph_read> reads;
+    std::vector<float> mean;
+    std::vector<double> time;
+    flatten_reads(rl, reads, mean, time);
+    std::vector<nph_aligned_pair> pairs(m_pairs_total);
+    std::vector<nph_abea_result> res(m_jobs.size());
+    engine.check(nph_abea_batch(engine.ctx(), reads.data(), reads.size(), mean.data(), time.data(), mean.size(),
+                                m_ranks.data(), m_ranks.size(), m_jobs.data(), m_jobs.size(), engine.model_id(m_model),
+                                pairs.data(), pairs.size(), res.data()),
+                 "nph_abea_batch");
+    for (size_t j = 0; j < m_jobs.size(); ++j) {
+        out[j].resize(res[j].n_pairs);     // 0 == the reference's empty vector (failed QC)
+        for (uint32_t i = 0; i < res[j].n_pairs; ++i) {
+            const nph_aligned_pair& p = pairs[m_jobs[j].pairs_off + i];
+            out[j][i] = AlignedPair{p.ref_pos, p.read_pos};
+        }
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The reference's free functions
+// ---------------------------------------------------------------------------------------------
+float profile_hmm_score(const HMMInputSequence& sequence, const HMMInputData& data, const uint32_t flags)
+{
+    HmmBatch b;
+    b.add(sequence, data, flags);
+    return b.run(Engine::thread_default())[0];
+}
+
+float profile_hmm_score(const HMMInputSequence& sequence, const std::vector<HMMInputData>& data, const uint32_t flags)
+{
+    HmmBatch b;
+    for (const HMMInputData& d : data) b.add(sequence, d, flags);
+    std::vector<float> s = b.run(Engine::thread_default());
+    float score = 0.0f;
+    for (float v : s) score += v;        // float sum in input order, like the reference's loop
+    return score;
+}
+
+float profile_hmm_score_set(const std::vector<HMMInputSequence>& sequences, const HMMInputData& data, const uint32_t flags)
+{
+    if (sequences.empty()) throw Error(NPH_ERR_INVALID, "profile_hmm_score_set: no sequences");
+    HmmBatch b;
+    b.add(sequences[0], data, flags);
+    for (size_t i = 1; i < sequences.size(); ++i) {
+        HMMInputData alt = data;
+        const std::string name = sequences[i].get_alphabet()->get_name();
+        auto it = data.read->alt_models[data.strand].find(name);
+        if (it == data.read->alt_models[data.strand].end())
+            throw Error(NPH_ERR_INVALID, "read has no pore model for alphabet " + name);   // the reference asserts alt model != NULL
+        alt.pore_model = it->second;
+        b.add(sequences[i], alt, flags);
+    }
+    std::vector<float> s = b.run(Engine::thread_default());
+    float out = 0.0f;
+    Engine::thread_default().check(nph_score_set_combine(s.data(), 1, (uint32_t)s.size(), &out), "nph_score_set_combine");
+    return out;
+}
+
+std::vector<AlignedPair> adaptive_banded_simple_event_align(SquiggleRead& read, const PoreModel& pore_model, const std::string& sequence)
+{
+    AbeaBatch b;
+    b.add(read, pore_model, sequence);
+    return b.run(Engine::thread_default())[0];
+}
+
+SquiggleScalings estimate_scalings_using_mom(const std::string& sequence, const PoreModel& pore_model, const std::vector<float>& event_means)
+{
+    Engine& eng = Engine::thread_default();
+    const uint32_t k = pore_model.k;
+    if (sequence.size() < k || event_means.empty()) throw Error(NPH_ERR_INVALID, "empty events or sequence shorter than k");
+    const uint32_t n_kmers = (uint32_t)(sequence.size() - k + 1);
+    std::vector<uint32_t> ranks(n_kmers);
+    for (uint32_t i = 0; i < n_kmers; ++i) ranks[i] = pore_model.pmalphabet->kmer_rank(sequence.c_str() + i, k);
+    nph_read r{};
+    r.event_off = 0; r.n_events = (uint32_t)event_means.size(); r.scale = 1.0; r.var = 1.0;
+    nph_abea_job j{};
+    j.rank_off = 0; j.pairs_off = 0; j.read = 0; j.n_kmers = n_kmers; j.pairs_cap = 0;
+    double ss[2] = {0, 1};
+    eng.check(nph_mom_batch(eng.ctx(), &r, 1, event_means.data(), event_means.size(), ranks.data(), ranks.size(), &j, 1,
+                            eng.model_id(&pore_model), ss),
+              "nph_mom_batch");
+    SquiggleScalings out;
+    out.set4(ss[0], ss[1], 0.0, 1.0);
+    return out;
+}
+
+} // namespace nph

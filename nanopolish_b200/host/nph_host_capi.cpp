@@ -1,0 +1,186 @@
+// nph_host_capi.cpp — a thin extern "C" shim over the C++ host mirror so that the Python tests can
+// drive HMMInputData / HMMInputSequence / SquiggleRead / Alphabet exactly as a C++ caller would.
+#include "nph_host.hpp"
+#include <cstring>
+#include <memory>
+
+using namespace nph;
+
+namespace {
+std::vector<std::unique_ptr<PoreModel>> g_models;
+std::vector<std::unique_ptr<SquiggleRead>> g_reads;
+thread_local std::string g_err;
+template <typename F> int guard(F f) { try { f(); return 0; } catch (const Error& e) { g_err = e.what(); return e.status; } catch (const std::exception& e) { g_err = e.what(); return NPH_ERR_INVALID; } }
+}
+
+extern "C" {
+
+const char* nphh_last_error() { return g_err.c_str(); }
+
+int nphh_alphabet_op(const char* alphabet, int op, const char* in, char* out)
+{
+    int n = -1;
+    int rc = guard([&] {
+        const Alphabet* a = get_alphabet_by_name(alphabet);
+        std::string s(in), r;
+        switch (op) {
+            case 0: r = a->reverse_complement(s); break;
+            case 1: r = a->methylate(s); break;
+            case 2: r = a->unmethylate(s); break;
+            case 3: r = a->disambiguate(s); break;
+            default: throw Error(NPH_ERR_INVALID, "bad op");
+        }
+        std::memcpy(out, r.c_str(), r.size() + 1);
+        n = (int)r.size();
+    });
+    return rc ? rc : n;
+}
+
+int nphh_is_motif_match(const char* alphabet, const char* seq, size_t i)
+{
+    return get_alphabet_by_name(alphabet)->is_motif_match(seq, i) ? 1 : 0;
+}
+
+uint32_t nphh_kmer_rank(const char* alphabet, const char* kmer, uint32_t k) { return get_alphabet_by_name(alphabet)->kmer_rank(kmer, k); }
+
+int nphh_lexicographic_next(const char* alphabet, const char* in, char* out)
+{
+    std::string s(in);
+    get_alphabet_by_name(alphabet)->lexicographic_next(s);
+    std::memcpy(out, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+// HMMInputSequence::get_kmer_rank for ki = 0..n-1
+int nphh_kmer_ranks(const char* alphabet, const char* seq, uint32_t k, int rc, uint32_t* out)
+{
+    int n = 0;
+    int st = guard([&] {
+        HMMInputSequence hs(std::string(seq), get_alphabet_by_name(alphabet));
+        if (hs.length() < k) return;
+        n = (int)(hs.length() - k + 1);
+        for (int i = 0; i < n; ++i) out[i] = hs.get_kmer_rank(i, k, rc != 0);
+    });
+    return st ? st : n;
+}
+
+int nphh_model_create(const char* alphabet, uint32_t k, uint32_t n_states, const double* mean, const double* stdv, const double* log_stdv)
+{
+    int h = -1;
+    int rc = guard([&] {
+        std::unique_ptr<PoreModel> pm(new PoreModel(k));
+        pm->pmalphabet = get_alphabet_by_name(alphabet);
+        pm->states.resize(n_states);
+        for (uint32_t i = 0; i < n_states; ++i) {
+            pm->states[i].level_mean = mean[i];
+            pm->states[i].level_stdv = stdv[i];
+            pm->states[i].level_log_stdv = log_stdv ? log_stdv[i] : std::log(stdv[i]);
+        }
+        g_models.push_back(std::move(pm));
+        h = (int)g_models.size() - 1;
+    });
+    return rc ? rc : h;
+}
+
+int nphh_read_create(uint32_t n_events, const float* mean, const double* start_time, double shift, double scale, double drift,
+                     double var, double events_per_base, int base_model)
+{
+    std::unique_ptr<SquiggleRead> sr(new SquiggleRead());
+    sr->pore_type = PORETYPE_R9;
+    sr->base_model[0] = g_models[base_model].get();
+    sr->scalings[0].set4(shift, scale, drift, var);
+    sr->events_per_base[0] = events_per_base;
+    sr->events[0].resize(n_events);
+    for (uint32_t i = 0; i < n_events; ++i) sr->events[0][i] = SquiggleEvent{mean[i], 1.0f, start_time[i], 0.0f, 0.0f};
+    g_reads.push_back(std::move(sr));
+    return (int)g_reads.size() - 1;
+}
+
+void nphh_read_add_model(int read, const char* alphabet, int model) { g_reads[read]->alt_models[0][alphabet] = g_models[model].get(); }
+void nphh_clear() { g_reads.clear(); }
+void nphh_set_indel_bias(double v) { hmm_indel_bias_factor = v; }
+
+// profile_hmm_score(sequence, data, flags) exactly as a nanopolish caller writes it
+int nphh_profile_hmm_score(int read, int model, const char* seq, uint32_t e_start, uint32_t e_stop, int rc, uint32_t flags, float* out)
+{
+    return guard([&] {
+        const PoreModel* pm = g_models[model].get();
+        HMMInputSequence sequence(std::string(seq), pm->pmalphabet);
+        HMMInputData data;
+        data.read = g_reads[read].get();
+        data.pore_model = pm;
+        data.event_start_idx = e_start;
+        data.event_stop_idx = e_stop;
+        data.strand = 0;
+        data.rc = rc;
+        data.event_stride = rc ? -1 : 1;
+        *out = profile_hmm_score(sequence, data, flags);
+    });
+}
+
+// one HmmBatch over many calls (the intended integration)
+int nphh_profile_hmm_score_many(size_t n, const int32_t* read, const int32_t* model, const char* seq_buf, const uint64_t* seq_off,
+                                const uint32_t* e_start, const uint32_t* e_stop, const uint8_t* rc, const uint32_t* flags, float* out)
+{
+    return guard([&] {
+        HmmBatch b;
+        for (size_t j = 0; j < n; ++j) {
+            const PoreModel* pm = g_models[model[j]].get();
+            HMMInputSequence sequence(std::string(seq_buf + seq_off[j], seq_buf + seq_off[j + 1]), pm->pmalphabet);
+            HMMInputData data;
+            data.read = g_reads[read[j]].get();
+            data.pore_model = pm;
+            data.event_start_idx = e_start[j];
+            data.event_stop_idx = e_stop[j];
+            data.strand = 0;
+            data.rc = rc[j];
+            data.event_stride = rc[j] ? -1 : 1;
+            b.add(sequence, data, flags[j]);
+        }
+        std::vector<float> s = b.run(Engine::thread_default());
+        std::memcpy(out, s.data(), sizeof(float) * n);
+    });
+}
+
+// profile_hmm_score_set over {nucleotide sequence, methylated sequence(s)}
+int nphh_profile_hmm_score_set(int read, int model, int n_seqs, const char** seqs, const char** alphabets, uint32_t e_start,
+                               uint32_t e_stop, int rc, uint32_t flags, float* out)
+{
+    return guard([&] {
+        std::vector<HMMInputSequence> ss;
+        for (int i = 0; i < n_seqs; ++i) ss.emplace_back(std::string(seqs[i]), get_alphabet_by_name(alphabets[i]));
+        HMMInputData data;
+        data.read = g_reads[read].get();
+        data.pore_model = g_models[model].get();
+        data.event_start_idx = e_start;
+        data.event_stop_idx = e_stop;
+        data.strand = 0;
+        data.rc = rc;
+        data.event_stride = rc ? -1 : 1;
+        *out = profile_hmm_score_set(ss, data, flags);
+    });
+}
+
+long long nphh_abea(int read, int model, const char* seq, int32_t* pairs_out, size_t cap)
+{
+    long long n = -1;
+    int rc = guard([&] {
+        std::vector<AlignedPair> p = adaptive_banded_simple_event_align(*g_reads[read], *g_models[model], std::string(seq));
+        if (p.size() > cap) throw Error(NPH_ERR_INVALID, "cap");
+        for (size_t i = 0; i < p.size(); ++i) { pairs_out[2 * i] = p[i].ref_pos; pairs_out[2 * i + 1] = p[i].read_pos; }
+        n = (long long)p.size();
+    });
+    return rc ? rc : n;
+}
+
+int nphh_mom(int read, int model, const char* seq, double* out4)
+{
+    return guard([&] {
+        std::vector<float> m;
+        for (const SquiggleEvent& e : g_reads[read]->events[0]) m.push_back(e.mean);
+        SquiggleScalings s = estimate_scalings_using_mom(std::string(seq), *g_models[model], m);
+        out4[0] = s.shift; out4[1] = s.scale; out4[2] = s.drift; out4[3] = s.var;
+    });
+}
+
+} // extern "C"

@@ -135,3 +135,12 @@ def test_invalid_jobs_are_rejected(engine, models):
     bad[0]["stride"] = -1                    # stride must follow the event order (assert in profile_hmm_r9.inl:275)
     with pytest.raises(NphError):
         engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, bad)
+
+
+def test_exact_math_primitives_on_device():
+    """div_by_cached_rcp == __fdiv_rn and the 8-instruction logsum == p7_FLogsum, bit for bit (2e8 pairs each)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda", "check_exact_math")
+    r = subprocess.run([exe, "200"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 mismatches" in r.stdout

@@ -1,0 +1,214 @@
+"""The C++ host mirror of the reference call surface (nanopolish_b200/host/): Alphabet known answers
+copied from the reference's own unit test expectations (src/test/nanopolish_test.cpp:27-237),
+randomised agreement with the compiled reference, and — on the GPU — profile_hmm_score /
+profile_hmm_score_set / adaptive_banded_simple_event_align called exactly like a nanopolish caller."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from nanopolish_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST_SO = os.path.join(ROOT, "nanopolish_b200", "libnph_host.so")
+OPS = {"reverse_complement": 0, "methylate": 1, "unmethylate": 2, "disambiguate": 3}
+
+
+@pytest.fixture(scope="module")
+def host():
+    lib = C.CDLL(HOST_SO)
+    lib.nphh_last_error.restype = C.c_char_p
+    lib.nphh_kmer_rank.restype = C.c_uint32
+    lib.nphh_abea.restype = C.c_longlong
+    return lib
+
+
+def _op(lib, alphabet, op, s):
+    out = C.create_string_buffer(len(s) + 16)
+    n = lib.nphh_alphabet_op(alphabet.encode(), OPS[op], s.encode(), out)
+    assert n >= 0, lib.nphh_last_error()
+    return out.raw[:n].decode()
+
+
+KNOWN = [
+    ("cpg", "methylate", "C", "C"), ("cpg", "methylate", "CG", "MG"), ("cpg", "methylate", "GC", "GC"),
+    ("cpg", "methylate", "CGCG", "MGMG"), ("cpg", "methylate", "AAGCGT", "AAGMGT"), ("cpg", "methylate", "CGGCGT", "MGGMGT"),
+    ("cpg", "methylate", "CGCGC", "MGMGC"),
+    ("cpg", "unmethylate", "C", "C"), ("cpg", "unmethylate", "M", "C"), ("cpg", "unmethylate", "MG", "CG"), ("cpg", "unmethylate", "MT", "MT"),
+    ("cpg", "disambiguate", "", ""), ("cpg", "disambiguate", "M", "M"), ("cpg", "disambiguate", "MT", "AT"),
+    ("cpg", "disambiguate", "MG", "MG"), ("cpg", "disambiguate", "AMG", "AMG"), ("cpg", "disambiguate", "CAM", "CAM"),
+    ("cpg", "reverse_complement", "M", "G"), ("cpg", "reverse_complement", "C", "G"), ("cpg", "reverse_complement", "MG", "MG"),
+    ("cpg", "reverse_complement", "CG", "CG"), ("cpg", "reverse_complement", "AM", "GT"), ("cpg", "reverse_complement", "AMG", "MGT"),
+    ("cpg", "reverse_complement", "AAAMG", "MGTTT"), ("cpg", "reverse_complement", "MGMG", "MGMG"),
+    ("cpg", "reverse_complement", "MGAMG", "MGTMG"),
+    ("dam", "methylate", "GAT", "GAT"), ("dam", "methylate", "GATC", "GMTC"), ("dam", "methylate", "GATCGATC", "GMTCGMTC"),
+    ("dam", "methylate", "GMTCGATC", "GMTCGMTC"),
+    ("dam", "unmethylate", "M", "A"), ("dam", "unmethylate", "MTC", "ATC"), ("dam", "unmethylate", "GMTCGM", "GATCGA"),
+    ("dam", "unmethylate", "MA", "MA"), ("dam", "unmethylate", "CM", "CM"),
+    ("dam", "disambiguate", "GMTC", "GMTC"), ("dam", "disambiguate", "GMA", "GAA"), ("dam", "disambiguate", "MT", "MT"),
+    ("dam", "reverse_complement", "M", "T"), ("dam", "reverse_complement", "GM", "TC"), ("dam", "reverse_complement", "GMT", "MTC"),
+    ("dam", "reverse_complement", "GMTC", "GMTC"), ("dam", "reverse_complement", "MTC", "GMT"), ("dam", "reverse_complement", "GAT", "ATC"),
+    ("dcm", "methylate", "CCAGG", "CMAGG"), ("dcm", "methylate", "CCTGG", "CMTGG"), ("dcm", "methylate", "CCAG", "CCAG"),
+    ("dcm", "methylate", "CCAGGCCTGG", "CMAGGCMTGG"), ("dcm", "methylate", "CCAGGCCTG", "CMAGGCCTG"),
+    ("dcm", "unmethylate", "M", "C"), ("dcm", "unmethylate", "MAGG", "CAGG"), ("dcm", "unmethylate", "MTG", "CTG"),
+]
+
+
+@pytest.mark.parametrize("alphabet,op,inp,want", KNOWN)
+def test_alphabet_known_answers(host, alphabet, op, inp, want):
+    assert _op(host, alphabet, op, inp) == want
+
+
+def test_ranks_and_lexicographic_order(host):
+    assert host.nphh_kmer_rank(b"nucleotide", b"GATGA", 5) == 568          # "string functions" test
+    for a, bases in (("nucleotide", "ACGT"), ("cpg", "ACGMT")):
+        kmer = bases[0] * 3
+        out = C.create_string_buffer(8)
+        n = len(bases) ** 3
+        for i in range(n - 1):
+            host.nphh_lexicographic_next(a.encode(), kmer.encode(), out)
+            nxt = out.value.decode()
+            assert host.nphh_kmer_rank(a.encode(), nxt.encode(), 3) - host.nphh_kmer_rank(a.encode(), kmer.encode(), 3) == 1
+            kmer = nxt
+        assert kmer == bases[-1] * 3
+
+
+def test_alphabet_ops_match_compiled_reference(host, ref_oracle):
+    rng = np.random.default_rng(12)
+    for alphabet, motif, meth in (("cpg", "CG", "MG"), ("gpc", "GC", "GM"), ("dam", "GATC", "GMTC"), ("dcm", "CCAGG", "CMAGG")):
+        for _ in range(150):
+            n = int(rng.integers(1, 40))
+            s = "".join(rng.choice(list("ACGT"), n))
+            for _ in range(int(rng.integers(0, 3))):         # plant (possibly overlapping / truncated) motifs
+                p = int(rng.integers(0, n))
+                s = (s[:p] + motif + s[p:])[:n + 3]
+            m = _op(host, alphabet, "methylate", s)
+            assert m == ref_oracle.alphabet_op(alphabet, 1, s.encode()).decode()
+            for op, code in (("reverse_complement", 0), ("unmethylate", 2), ("disambiguate", 3)):
+                for x in (s, m):
+                    assert _op(host, alphabet, op, x) == ref_oracle.alphabet_op(alphabet, code, x.encode()).decode(), (alphabet, op, x)
+
+
+def test_kmer_ranks_match_compiled_reference(host, ref_oracle):
+    rng = np.random.default_rng(5)
+    hn, hc = ref_oracle.builtin_model("nucleotide"), ref_oracle.builtin_model("cpg")
+    for _ in range(60):
+        n = int(rng.integers(6, 80))
+        s = "".join(rng.choice(list("ACGT"), n))
+        for rc in (0, 1):
+            out = np.zeros(n, np.uint32)
+            k = host.nphh_kmer_ranks(b"nucleotide", s.encode(), 6, rc, out.ctypes.data_as(C.c_void_p))
+            assert np.array_equal(out[:k], ref_oracle.kmer_ranks(hn, s.encode(), bool(rc)))
+            m = _op(host, "cpg", "methylate", s)
+            k = host.nphh_kmer_ranks(b"cpg", m.encode(), 6, rc, out.ctypes.data_as(C.c_void_p))
+            assert np.array_equal(out[:k], ref_oracle.kmer_ranks(hc, m.encode(), bool(rc)))
+
+
+# ---- GPU: the reference's free functions through the mirror -----------------------------------
+def _register(host, model):
+    mean = np.ascontiguousarray(model.level_mean); sd = np.ascontiguousarray(model.level_stdv)
+    lsd = np.ascontiguousarray(model.level_log_stdv)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    return host.nphh_model_create(model.alphabet.encode(), model.k, mean.shape[0], p(mean), p(sd), p(lsd))
+
+
+def _register_reads(host, rs, mh):
+    hs = []
+    for r in rs.reads:
+        o, n = int(r["event_off"]), int(r["n_events"])
+        m = np.ascontiguousarray(rs.ev_mean[o:o + n]); t = np.ascontiguousarray(rs.ev_start_time[o:o + n])
+        hs.append(host.nphh_read_create(n, m.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), C.c_double(r["shift"]),
+                                        C.c_double(r["scale"]), C.c_double(r["drift"]), C.c_double(r["var"]),
+                                        C.c_double(r["events_per_base"]), mh))
+    return hs
+
+
+@pytest.mark.gpu
+def test_profile_hmm_score_like_a_caller(host, port_oracle):
+    nuc = synth.load_model("nucleotide")
+    rs = synth.gen_reads(3, 900, nuc, seed=61, drift=True)
+    jobs = synth.scorereads_jobs(rs, 200, rc_every=2, keep_seqs=True)
+    want, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [nuc], jobs.kmer_ranks, jobs.jobs)
+    mh = _register(host, nuc)
+    rh = _register_reads(host, rs, mh)
+    host.nphh_set_indel_bias(C.c_double(1.0))
+    # one call per job, exactly the reference's signature
+    for j in range(min(4, jobs.jobs.shape[0])):
+        jb = jobs.jobs[j]
+        out = C.c_float()
+        rc = host.nphh_profile_hmm_score(rh[int(jb["read"])], mh, jobs.seqs[j], int(jb["event_start"]), int(jb["event_stop"]),
+                                         int(jb["rc"]), int(jb["flags"]), C.byref(out))
+        assert rc == 0, host.nphh_last_error()
+        assert np.float32(out.value).view(np.uint32) == want[j].view(np.uint32)
+    # one HmmBatch for all of them
+    n = jobs.jobs.shape[0]
+    buf = b"".join(jobs.seqs)
+    off = np.zeros(n + 1, np.uint64); off[1:] = np.cumsum([len(s) for s in jobs.seqs])
+    got = np.zeros(n, np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    reads = np.ascontiguousarray(np.array(rh, np.int32)[jobs.jobs["read"]])
+    models = np.full(n, mh, np.int32)
+    rc = host.nphh_profile_hmm_score_many(C.c_size_t(n), p(reads), p(models), C.c_char_p(buf), p(off),
+                                          p(np.ascontiguousarray(jobs.jobs["event_start"])), p(np.ascontiguousarray(jobs.jobs["event_stop"])),
+                                          p(np.ascontiguousarray(jobs.jobs["rc"])), p(np.ascontiguousarray(jobs.jobs["flags"].astype(np.uint32))), p(got))
+    assert rc == 0, host.nphh_last_error()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # rc / stride mismatch is rejected where the reference asserts
+    out = C.c_float()
+    jb = jobs.jobs[0]
+    assert host.nphh_profile_hmm_score(rh[0], mh, jobs.seqs[0], int(jb["event_stop"]), int(jb["event_start"]), 0, 0, C.byref(out)) != 0
+
+
+@pytest.mark.gpu
+def test_profile_hmm_score_set_like_a_caller(host, port_oracle):
+    nuc, cpg = synth.load_model("nucleotide"), synth.load_model("cpg")
+    rs = synth.gen_reads(2, 600, nuc, seed=88, cpg_keep=0.4)
+    mj = synth.methylation_jobs(rs, model_id=1, keep_seqs=True, max_groups_per_read=3)
+    mh, ch = _register(host, nuc), _register(host, cpg)
+    rh = _register_reads(host, rs, mh)
+    for r in rh:
+        host.nphh_read_add_model(r, b"cpg", ch)
+    for g in range(mj.jobs.shape[0] // 2):
+        ju = mj.jobs[2 * g]
+        useq = mj.seqs[2 * g]            # unmethylated bases (ACGT only): valid in the nucleotide alphabet too
+        mseq = mj.seqs[2 * g + 1]
+        # oracle: score(nucleotide seq, nucleotide model) (+) score(methylated seq, cpg model), each - log 2
+        k = 6
+        jobs = np.zeros(2, synth.HMM_JOB_DT)
+        r_u = synth.kmer_ranks_from_codes(synth.encode(useq, "nucleotide"), k, 4)
+        r_m = synth.kmer_ranks_from_codes(synth.encode(mseq, "cpg"), k, 5)
+        jobs[0] = (0, ju["read"], 0, ju["event_start"], ju["event_stop"], r_u.shape[0], 1, 0, ju["flags"], 0)
+        jobs[1] = (r_u.shape[0], ju["read"], 1, ju["event_start"], ju["event_stop"], r_m.shape[0], 1, 0, ju["flags"], 0)
+        ranks = np.concatenate([r_u, r_m]).astype(np.uint32)
+        sc, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [nuc, cpg], ranks, jobs)
+        want = np.float32(port_oracle.score_set_combine(sc))
+        out = C.c_float()
+        seqs = (C.c_char_p * 2)(useq, mseq)
+        alphs = (C.c_char_p * 2)(b"nucleotide", b"cpg")
+        rc = host.nphh_profile_hmm_score_set(rh[int(ju["read"])], mh, 2, seqs, alphs, int(ju["event_start"]), int(ju["event_stop"]),
+                                             0, int(ju["flags"]), C.byref(out))
+        assert rc == 0, host.nphh_last_error()
+        assert np.float32(out.value).view(np.uint32) == want.view(np.uint32)
+
+
+@pytest.mark.gpu
+def test_abea_and_mom_like_a_caller(host, port_oracle):
+    nuc = synth.load_model("nucleotide")
+    rs = synth.gen_reads(2, 700, nuc, seed=17, rng_scalings=False)
+    jobs, ranks, total = synth.abea_jobs(rs)
+    po, ro, _ = port_oracle.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, nuc, ranks, jobs, total)
+    mh = _register(host, nuc)
+    rh = _register_reads(host, rs, mh)
+    for i in range(rs.n_reads):
+        seq = synth._CODE2DNA[rs.seq_codes[i]].tobytes()
+        cap = int(jobs[i]["pairs_cap"])
+        pairs = np.zeros((cap, 2), np.int32)
+        n = host.nphh_abea(rh[i], mh, seq, pairs.ctypes.data_as(C.c_void_p), C.c_size_t(cap))
+        assert n == int(ro[i]["n_pairs"]) and n > 0
+        w = po[int(jobs[i]["pairs_off"]):int(jobs[i]["pairs_off"]) + n]
+        assert np.array_equal(pairs[:n, 0], w["ref_pos"]) and np.array_equal(pairs[:n, 1], w["read_pos"])
+        out = np.zeros(4)
+        assert host.nphh_mom(rh[i], mh, seq, out.ctypes.data_as(C.c_void_p)) == 0
+        sh, sc = port_oracle.mom(rs.reads, rs.ev_mean, nuc, ranks, jobs[i])
+        assert out[0] == sh and out[1] == sc and out[2] == 0.0 and out[3] == 1.0
