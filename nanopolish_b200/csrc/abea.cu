@@ -393,7 +393,7 @@ int nph_launch_abea(nph_ctx* ctx)
     p.jobs = ctx->d_abea_jobs.p;
     p.order = ctx->d_abea_order.p;
     p.n_jobs = (uint32_t)ctx->n_abea_jobs;
-    p.counter = ctx->d_counters.p + 15;
+    p.counter = ctx->d_counters.p + (NPH_NUM_COUNTERS - 1);
     p.pairs = ctx->d_pairs.p;
     p.results = ctx->d_abea_res.p;
     const int warps = ctx->sm_count * kWarps;
@@ -405,7 +405,7 @@ int nph_launch_abea(nph_ctx* ctx)
     p.lp_skip = log(1e-10);
     p.lp_trim = log(0.01);
     p.log_inv_sqrt_2pi = ctx->consts.log_inv_sqrt_2pi;
-    NPH_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + 15, 0, sizeof(unsigned int), ctx->stream));
+    NPH_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + (NPH_NUM_COUNTERS - 1), 0, sizeof(unsigned int), ctx->stream));
     NPH_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     int grid = ctx->sm_count;
     if ((size_t)grid * kWarps > ctx->n_abea_jobs) grid = (int)((ctx->n_abea_jobs + kWarps - 1) / kWarps);

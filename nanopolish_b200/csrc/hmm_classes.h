@@ -1,0 +1,60 @@
+// hmm_classes.h — kernel-class choice for forward-HMM jobs, shared by host and device code.
+//
+// A class is (C columns per lane, W lanes per job); 32/W jobs share a warp.  W < 32 classes hold
+// single-strip jobs (K <= W*C); W == 32 also chains strips for wide jobs.  A job goes to the class that
+// minimises modelled issue slots = steps x (per-step overhead + C x per-cell cost) x W/32, with the
+// constants measured by ncu (profiles/): ~88 instructions per block-cell, ~96 per warp step.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define NPH_HD __host__ __device__ __forceinline__
+#else
+#define NPH_HD inline
+#endif
+
+#define NPH_NUM_WIDTHS 4
+#define NPH_MAX_COLS 10
+#define NPH_NUM_CLASSES (NPH_NUM_WIDTHS * NPH_MAX_COLS)
+#define NPH_KEY_BUCKETS 4096          // schedule key: exact step count below 2048, then 16-step bins
+
+NPH_HD uint32_t nph_class_width(int wi) { return 4u << wi; }                 // 4, 8, 16, 32
+NPH_HD int nph_class_index(int C, int wi) { return wi * NPH_MAX_COLS + (C - 1); }
+
+// warp steps one job takes in class (C, W): chained strips of W*C columns, period max(E, 40) when chained
+NPH_HD uint32_t nph_class_steps(uint32_t K, uint32_t E, int C, uint32_t W)
+{
+    const uint32_t strip = W * (uint32_t)C;
+    const uint32_t n_strips = (K + strip - 1) / strip;
+    const uint32_t P = n_strips > 1 ? (E > 40u ? E : 40u) : E;
+    const uint32_t last_cols = K - (n_strips - 1) * strip;
+    return (n_strips - 1) * P + E + (last_cols - 1) / (uint32_t)C;
+}
+
+NPH_HD float nph_class_cost(uint32_t steps, int C, uint32_t W) { return (float)steps * (96.0f + 88.0f * C) * (W * (1.0f / 32.0f)); }
+
+// returns class index; *steps_out = steps in that class
+NPH_HD int nph_choose_class(uint32_t K, uint32_t E, uint32_t* steps_out)
+{
+    float best = 3.0e38f;
+    int best_cls = nph_class_index(1, 3);
+    uint32_t best_steps = 0;
+    for (int wi = 0; wi < NPH_NUM_WIDTHS; ++wi) {
+        const uint32_t W = nph_class_width(wi);
+        for (int C = 1; C <= NPH_MAX_COLS; ++C) {
+            if (W < 32 && K > W * (uint32_t)C) continue;
+            const uint32_t steps = nph_class_steps(K, E, C, W);
+            const float cost = nph_class_cost(steps, C, W);
+            if (cost < best) { best = cost; best_cls = nph_class_index(C, wi); best_steps = steps; }
+        }
+    }
+    *steps_out = best_steps;
+    return best_cls;
+}
+
+NPH_HD uint32_t nph_key_bucket(uint32_t steps)
+{
+    if (steps < 2048u) return steps;
+    const uint32_t b = 2048u + (steps - 2048u) / 16u;
+    return b < (uint32_t)NPH_KEY_BUCKETS ? b : (uint32_t)NPH_KEY_BUCKETS - 1u;
+}

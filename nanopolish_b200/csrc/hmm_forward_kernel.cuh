@@ -1,0 +1,282 @@
+// hmm_forward_kernel.cuh — K1: the R9 profile-HMM forward score on sm_100a (kernel template).
+//
+// Replaces, for a whole batch of (sequence, HMMInputData, flags) jobs at once:
+//   profile_hmm_score_r9            ref: src/hmm/nanopolish_profile_hmm_r9.cpp:35-65
+//   profile_hmm_fill_generic_r9     ref: src/hmm/nanopolish_profile_hmm_r9.inl:265-433
+//   ProfileHMMForwardOutputR9       ref: src/hmm/nanopolish_profile_hmm_r9.inl:79-127
+//   log_probability_match_r9        ref: src/hmm/nanopolish_emissions.h:57-68
+//   get_scaled_gaussian_from_pore_model_state   ref: src/nanopolish_squiggle_read.h:217-226
+//   p7_FLogsum                      ref: src/common/logsum.h:55-66
+//
+// Design (DESIGN.md section 3 has the long form):
+//   * a group of W lanes (W = 4, 8, 16 or 32; 32/W jobs per warp) owns one job; lane j of the group owns C
+//     adjacent k-mer columns (M, B, K states and the read-scaled Gaussian of each in registers) and walks
+//     the event rows one step behind lane j-1 — a systolic wavefront over the anti-diagonals.  The left
+//     neighbour's three states travel by __shfl_up_sync (segment width W); nothing of the
+//     (E+1) x 3(K+2) matrix the reference mallocs per call is ever stored.
+//   * W == 32 only: jobs wider than 32*C columns are cut into strips chained back-to-back (lane 0 starts
+//     strip s+1 while lane 31 is still finishing strip s); only the strip's right-edge column (3 floats
+//     per row) goes through an L1-resident scratch line.  W < 32 classes hold single-strip jobs (K <= W*C).
+//   * the 62.8 KB quantised log-sum table lives in shared memory (exact_math.cuh: 8 instructions per sum).
+//   * every float operation is issued in the reference's order with explicit round-to-nearest
+//     intrinsics (no FMA contraction), IEEE division included, so scores are bit-identical.
+//   * persistent CTAs (one per SM); warps pull 32/W jobs at a time, longest first, from an atomic counter.
+#pragma once
+#include "nph_internal.cuh"
+#include "exact_math.cuh"
+#include <math_constants.h>
+
+namespace nph_fwd {
+
+constexpr int kWarpsPerCta = 16;
+constexpr int kCtaThreads = kWarpsPerCta * 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMinPeriod = 40;   // chained strips: the right edge of row r must be written >32 steps before it is read
+
+struct FwdParams {
+    const float* level;           // drift-scaled event levels, all reads
+    const DevRead* reads;
+    const float2* trans;          // per read (lp_mm_self, lp_mm_next)
+    const DevModelView* models;
+    const uint32_t* ranks;
+    const nph_hmm_job* jobs;
+    const uint32_t* order;        // this class's slice of the schedule
+    uint32_t n_jobs;
+    unsigned int* counter;
+    const float* logsum_g;
+    const float* flank;
+    float* scores;
+    float4* scratch_params;       // per warp: kpad_stride float4 {mu', sigma', log(1/sqrt(2pi)) - log sigma', RN(1/sigma')}
+    float* scratch_edge;          // per warp: 3 * edge_stride floats (W == 32 classes)
+    uint32_t kpad_stride;
+    uint32_t edge_stride;
+    uint32_t lsum_bias;           // NPH_LOGSUM_ADDR_BIAS, passed at run time on purpose (exact_math.cuh)
+    HmmConsts c;
+};
+
+template <int C, int W>
+__global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdParams p)
+{
+    static_assert(W == 4 || W == 8 || W == 16 || W == 32, "group width");
+    constexpr int G = 32 / W;                 // jobs per warp
+    constexpr int STRIP = W * C;              // columns per strip
+    extern __shared__ float s_tbl[];
+    for (int i = threadIdx.x; i < NPH_TBL_SMEM; i += kCtaThreads) s_tbl[i] = p.logsum_g[i];
+    __syncthreads();
+    const LogsumTable tb = make_logsum_table(s_tbl, p.lsum_bias);
+
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (W - 1);            // lane within the group
+    const int grp = lane / W;
+    const int warp_global = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    float4* const my_params = p.scratch_params + (size_t)warp_global * p.kpad_stride + (W < 32 ? grp * STRIP : 0);
+    float* const edge_m = p.scratch_edge + (size_t)warp_global * 3 * p.edge_stride;
+    float* const edge_b = edge_m + p.edge_stride;
+    float* const edge_k = edge_b + p.edge_stride;
+
+    const float NEG = -CUDART_INF_F;
+    const float lp_mk = p.c.lp_mk, lp_mb = p.c.lp_mb, lp_bb = p.c.lp_bb, lp_bk = p.c.lp_bk;
+    const float lp_bm_next = p.c.lp_bm_next, lp_bm_self = p.c.lp_bm_self, lp_kk = p.c.lp_kk, lp_km = p.c.lp_km;
+
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(p.counter, (unsigned)G);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= p.n_jobs) break;
+        const uint32_t slot = base + grp;
+        const bool has_job = slot < p.n_jobs;
+        const uint32_t job_idx = p.order[has_job ? slot : base];
+        const nph_hmm_job job = p.jobs[job_idx];
+        const DevRead rd = p.reads[job.read];
+        const float2 tr = p.trans[job.read];
+        const float lp_mm_self = tr.x, lp_mm_next = tr.y;
+        const DevModelView mv = p.models[job.model_id];
+
+        const int K = (int)job.n_kmers;
+        const int E = has_job ? (int)(job.event_stop > job.event_start ? job.event_stop - job.event_start
+                                                                       : job.event_start - job.event_stop) + 1
+                              : 0;
+        const int stride = job.stride;
+        const bool pre_clip = (job.flags & NPH_HAF_ALLOW_PRE_CLIP) != 0;
+        const bool post_clip = (job.flags & NPH_HAF_ALLOW_POST_CLIP) != 0;
+        const int n_strips = (W == 32) ? (K + STRIP - 1) / STRIP : 1;
+        const int kpad = n_strips * STRIP;
+        const int P = n_strips > 1 ? max(E, kMinPeriod) : E;
+
+        // ---- per-job prologue: read-scaled Gaussian of every k-mer, formed in FP64 exactly as
+        // get_scaled_gaussian_from_pore_model_state does, then narrowed; plus RN(1/sigma') ----
+        if (has_job) {
+            const uint32_t* rk = p.ranks + job.rank_off;
+            for (int i = gl; i < kpad; i += W) {
+                float4 g = make_float4(0.f, 1.f, 0.f, 1.f);
+                if (i < K) {
+                    const uint32_t r = rk[i];
+                    const float mu = (float)__dadd_rn(__dmul_rn(rd.scale, mv.mean[r]), rd.shift);
+                    const float sd = (float)__dmul_rn(mv.stdv[r], rd.var);
+                    const float lsd = (float)__dadd_rn(mv.log_stdv[r], rd.log_var);
+                    g = make_float4(mu, sd, __fsub_rn(p.c.log_inv_sqrt_2pi, lsd), __frcp_rn(sd));
+                }
+                my_params[i] = g;
+            }
+        }
+        __syncwarp();
+
+        const float* lv = p.level + rd.event_off;
+        const long long e_first = (long long)job.event_start;
+
+        // the lane/slot that owns the last k-mer column (end-state fold)
+        const int last_strip = n_strips - 1;
+        const int last_rel = (K - 1) - last_strip * STRIP;
+        const int end_lane = last_rel / C;
+        const int end_slot = last_rel % C;
+        // lanes beyond end_lane own no column of the last strip; the warp runs until its slowest group is done
+        const int my_steps = has_job ? last_strip * P + E + end_lane : 0;
+        const int total_steps = (W == 32) ? my_steps : __reduce_max_sync(kFull, my_steps);
+
+        float mu[C], sd[C], cc[C], ry[C];
+        float Mp[C], Bp[C], Kp[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { mu[c] = 0.f; sd[c] = 1.f; cc[c] = 0.f; ry[c] = 1.f; Mp[c] = NEG; Bp[c] = NEG; Kp[c] = NEG; }
+        float Lm_prev = NEG, Lb_prev = NEG, Lk_prev = NEG;
+        float lp_end = NEG;
+        int r = 1 - gl;        // row of this lane at the current step (rows 1..P; <1 = not started)
+        int s = 0;             // strip of this lane
+        float x_next = 0.f;
+        if (r == 1 && E >= 1) x_next = lv[e_first];
+        float em_next = NEG, eb_next = NEG, ek_next = NEG;   // group lane 0: prefetched right edge of the previous strip
+
+        for (int g = 0; g < total_steps; ++g) {
+            // left neighbour's newest row (its row == my row, computed one step ago)
+            float Lm = __shfl_up_sync(kFull, Mp[C - 1], 1, W);
+            float Lb = __shfl_up_sync(kFull, Bp[C - 1], 1, W);
+            float Lk = __shfl_up_sync(kFull, Kp[C - 1], 1, W);
+            if (gl == 0) { Lm = em_next; Lb = eb_next; Lk = ek_next; }
+
+            const bool in_strip = (r >= 1) && (s < n_strips);
+            const int col0 = s * STRIP + gl * C;
+            const bool live = in_strip && (r <= E) && (col0 < K);
+            const float x = x_next;
+
+            if (in_strip && r == 1) {
+                // entering a strip: row 0 and the start column are -inf
+#pragma unroll
+                for (int c = 0; c < C; ++c) { Mp[c] = NEG; Bp[c] = NEG; Kp[c] = NEG; }
+                Lm_prev = NEG; Lb_prev = NEG; Lk_prev = NEG;
+                if (col0 < K) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const float4 g4 = my_params[col0 + c];
+                        mu[c] = g4.x; sd[c] = g4.y; cc[c] = g4.z; ry[c] = g4.w;
+                    }
+                }
+            }
+
+            // prefetch for the next step: event level and (group lane 0, chained strips) the stored right edge
+            {
+                int rn = r + 1, sn = s;
+                if (rn > P) { rn = 1; sn = s + 1; }
+                if (rn >= 1 && rn <= E && sn < n_strips) {
+                    x_next = lv[e_first + (long long)(rn - 1) * stride];
+                    if (W == 32 && gl == 0 && sn > 0) { em_next = edge_m[rn]; eb_next = edge_b[rn]; ek_next = edge_k[rn]; }
+                }
+            }
+
+            if (live) {
+                float soft = NEG;
+                if (col0 == 0 && (r == 1 || pre_clip)) soft = p.flank[r - 1];
+                float post = 0.f;
+                const bool do_end = (s == last_strip) && (gl == end_lane) && (post_clip || r == E);
+                if (do_end) post = p.flank[E - r];
+
+                float lm_prev = Lm_prev, lb_prev = Lb_prev, lk_prev = Lk_prev;   // left column, row r-1
+                float lm_cur = Lm, lb_cur = Lb, lk_cur = Lk;                      // left column, row r
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    // Gaussian log-density, reference operation order (emissions.h:51-55)
+                    const float a = div_by_cached_rcp(__fsub_rn(x, mu[c]), sd[c], ry[c]);
+                    const float em = __fadd_rn(cc[c], __fmul_rn(__fmul_rn(-0.5f, a), a));
+                    // match: left fold over {same M, prev M, same B, prev B, prev K, soft}
+                    float m = __fadd_rn(lp_mm_self, Mp[c]);
+                    m = lsum(m, __fadd_rn(lp_mm_next, lm_prev), tb);
+                    m = lsum(m, __fadd_rn(lp_bm_self, Bp[c]), tb);
+                    m = lsum(m, __fadd_rn(lp_bm_next, lb_prev), tb);
+                    m = lsum(m, __fadd_rn(lp_km, lk_prev), tb);
+                    if (c == 0) m = lsum(m, soft, tb);
+                    m = __fadd_rn(m, em);
+                    // bad event: {same M, same B}
+                    const float b = lsum(__fadd_rn(lp_mb, Mp[c]), __fadd_rn(lp_bb, Bp[c]), tb);
+                    // k-mer skip: {prev M, prev B, prev K} of the SAME row
+                    float kk = lsum(__fadd_rn(lp_mk, lm_cur), __fadd_rn(lp_bk, lb_cur), tb);
+                    kk = lsum(kk, __fadd_rn(lp_kk, lk_cur), tb);
+
+                    lm_prev = Mp[c]; lb_prev = Bp[c]; lk_prev = Kp[c];
+                    lm_cur = m; lb_cur = b; lk_cur = kk;
+                    Mp[c] = m; Bp[c] = b; Kp[c] = kk;
+                }
+                Lm_prev = Lm; Lb_prev = Lb; Lk_prev = Lk;
+
+                if (do_end) {
+                    float Me = Mp[0], Be = Bp[0], Ke = Kp[0];
+#pragma unroll
+                    for (int c = 1; c < C; ++c) if (c == end_slot) { Me = Mp[c]; Be = Bp[c]; Ke = Kp[c]; }
+                    lp_end = lsum(lp_end, __fadd_rn(Me, post), tb);
+                    lp_end = lsum(lp_end, __fadd_rn(Be, post), tb);
+                    lp_end = lsum(lp_end, __fadd_rn(Ke, post), tb);
+                }
+                if (W == 32 && gl == W - 1 && s < last_strip) {
+                    edge_m[r] = Mp[C - 1]; edge_b[r] = Bp[C - 1]; edge_k[r] = Kp[C - 1];
+                }
+            }
+
+            // advance
+            r += 1;
+            if (r > P) { r = 1; s += 1; }
+            if (W == 32 && n_strips > 1) __syncwarp();   // orders lane 31's edge stores before lane 0's later loads
+        }
+
+        const float result = __shfl_sync(kFull, lp_end, (lane & ~(W - 1)) + end_lane);
+        if (gl == 0 && has_job) p.scores[job_idx] = result;
+        __syncwarp();
+    }
+}
+
+template <int C, int W>
+int launch_class(nph_ctx* ctx, const FwdParams& base, const nph_ctx::ClassLaunch& cl, int class_idx, cudaStream_t stream)
+{
+    FwdParams p = base;
+    p.order = ctx->d_order.p + cl.first;
+    p.n_jobs = (uint32_t)cl.count;
+    p.counter = ctx->d_counters.p + class_idx;
+    const size_t smem = sizeof(float) * NPH_TBL_SMEM;
+    NPH_CUDA(ctx, cudaFuncSetAttribute(hmm_forward_kernel<C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = ctx->sm_count;
+    const size_t warps_needed = (cl.count + (32 / W) - 1) / (32 / W);
+    if ((size_t)grid * kWarpsPerCta > warps_needed) grid = (int)((warps_needed + kWarpsPerCta - 1) / kWarpsPerCta);
+    if (grid < 1) grid = 1;
+    hmm_forward_kernel<C, W><<<grid, kCtaThreads, smem, stream>>>(p);
+    NPH_CUDA(ctx, cudaGetLastError());
+    return NPH_OK;
+}
+
+// one translation unit per group width (parallel compilation); defined in hmm_forward_w*.cu
+template <int W> int launch_width(nph_ctx* ctx, const FwdParams& base, const nph_ctx::ClassLaunch& cl, int class_idx, cudaStream_t stream);
+
+#define NPH_DEFINE_LAUNCH_WIDTH(W)                                                                              \
+    template <> int launch_width<W>(nph_ctx * ctx, const FwdParams& base, const nph_ctx::ClassLaunch& cl, int class_idx, cudaStream_t stream) \
+    {                                                                                                           \
+        switch (cl.cols_per_lane) {                                                                             \
+            case 1: return launch_class<1, W>(ctx, base, cl, class_idx, stream);                                       \
+            case 2: return launch_class<2, W>(ctx, base, cl, class_idx, stream);                                       \
+            case 3: return launch_class<3, W>(ctx, base, cl, class_idx, stream);                                       \
+            case 4: return launch_class<4, W>(ctx, base, cl, class_idx, stream);                                       \
+            case 5: return launch_class<5, W>(ctx, base, cl, class_idx, stream);                                       \
+            case 6: return launch_class<6, W>(ctx, base, cl, class_idx, stream);                                       \
+            case 7: return launch_class<7, W>(ctx, base, cl, class_idx, stream);                                       \
+            case 8: return launch_class<8, W>(ctx, base, cl, class_idx, stream);                                       \
+            case 9: return launch_class<9, W>(ctx, base, cl, class_idx, stream);                                       \
+            case 10: return launch_class<10, W>(ctx, base, cl, class_idx, stream);                                     \
+        }                                                                                                       \
+        return NPH_ERR_STATE;                                                                                   \
+    }
+
+} // namespace nph_fwd

@@ -1,0 +1,143 @@
+// hmm_schedule.cu — device-side validation, classification and scheduling of forward-HMM jobs.
+//
+// call-methylation batches hold ~10^6 tiny jobs; doing the per-job bookkeeping on the host cost more
+// than scoring them.  Three small kernels replace it: (1) validate each job against its read exactly
+// where the reference would assert or read out of bounds (profile_hmm_r9.inl:275, :305), choose its
+// kernel class (hmm_classes.h) and histogram (class, step-count) keys; (2) one-block exclusive scan,
+// longest jobs first inside each class; (3) scatter job indices into the schedule.  The host reads
+// back one small summary (error flag, per-class counts and costs, scratch sizes).
+#include "nph_internal.cuh"
+#include "hmm_classes.h"
+
+namespace {
+
+struct SchedSummary {
+    int error;                 // 0, or 1 + index of the first offending job (any one of them)
+    uint32_t max_kpad, max_period, max_E;
+    unsigned long long class_count[NPH_NUM_CLASSES];
+    float class_cost[NPH_NUM_CLASSES];
+};
+
+__global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n_jobs, const DevRead* __restrict__ reads,
+                                uint32_t n_reads, uint32_t n_models, uint64_t n_ranks, uint8_t* __restrict__ cls,
+                                uint16_t* __restrict__ bkt, unsigned int* __restrict__ hist, SchedSummary* __restrict__ sum)
+{
+    __shared__ unsigned int s_count[NPH_NUM_CLASSES];
+    __shared__ float s_cost[NPH_NUM_CLASSES];
+    __shared__ unsigned int s_kpad, s_period, s_E;
+    for (int i = threadIdx.x; i < NPH_NUM_CLASSES; i += blockDim.x) { s_count[i] = 0; s_cost[i] = 0.f; }
+    if (threadIdx.x == 0) { s_kpad = 0; s_period = 0; s_E = 0; }
+    __syncthreads();
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_jobs; j += gridDim.x * blockDim.x) {
+        const nph_hmm_job jb = jobs[j];
+        bool ok = jb.read < n_reads && jb.model_id < n_models && jb.n_kmers != 0 && jb.rank_off + jb.n_kmers <= n_ranks;
+        ok = ok && (jb.stride == 1 || jb.stride == -1);
+        if (ok) {
+            const uint32_t ne = reads[jb.read].n_events;
+            ok = jb.event_start < ne && jb.event_stop < ne;
+            ok = ok && !(jb.event_stop > jb.event_start && jb.stride != 1) && !(jb.event_stop < jb.event_start && jb.stride != -1);
+        }
+        if (!ok) { atomicCAS(&sum->error, 0, (int)(j + 1)); cls[j] = 0; bkt[j] = 0; continue; }
+        const uint32_t E = (jb.event_stop > jb.event_start ? jb.event_stop - jb.event_start : jb.event_start - jb.event_stop) + 1;
+        const uint32_t K = jb.n_kmers;
+        uint32_t steps;
+        const int c = nph_choose_class(K, E, &steps);
+        const int C = c % NPH_MAX_COLS + 1;
+        const uint32_t W = nph_class_width(c / NPH_MAX_COLS);
+        const uint32_t b = nph_key_bucket(steps);
+        cls[j] = (uint8_t)c;
+        bkt[j] = (uint16_t)b;
+        atomicAdd(&hist[(size_t)c * NPH_KEY_BUCKETS + (NPH_KEY_BUCKETS - 1 - b)], 1u);   // descending by steps
+        atomicAdd(&s_count[c], 1u);
+        atomicAdd(&s_cost[c], nph_class_cost(steps, C, W));
+        const uint32_t strip = W * C;
+        atomicMax(&s_kpad, ((K + strip - 1) / strip) * strip);
+        atomicMax(&s_period, E > 40u ? E : 40u);
+        atomicMax(&s_E, E);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NPH_NUM_CLASSES; i += blockDim.x) {
+        if (s_count[i]) { atomicAdd(&sum->class_count[i], (unsigned long long)s_count[i]); atomicAdd(&sum->class_cost[i], s_cost[i]); }
+    }
+    if (threadIdx.x == 0) { atomicMax(&sum->max_kpad, s_kpad); atomicMax(&sum->max_period, s_period); atomicMax(&sum->max_E, s_E); }
+}
+
+// exclusive scan of the NPH_NUM_CLASSES * NPH_KEY_BUCKETS histogram (class-major), one block
+__global__ void scan_kernel(const unsigned int* __restrict__ hist, unsigned int* __restrict__ offs)
+{
+    constexpr int N = NPH_NUM_CLASSES * NPH_KEY_BUCKETS;
+    constexpr int T = 1024;
+    constexpr int PER = (N + T - 1) / T;
+    __shared__ unsigned int s_part[T];
+    const int t = threadIdx.x;
+    const int lo = t * PER, hi = min(N, lo + PER);
+    unsigned int s = 0;
+    for (int i = lo; i < hi; ++i) s += hist[i];
+    s_part[t] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (int d = 1; d < T; d <<= 1) {
+        unsigned int v = (t >= d) ? s_part[t - d] : 0u;
+        __syncthreads();
+        s_part[t] += v;
+        __syncthreads();
+    }
+    unsigned int run = (t == 0) ? 0u : s_part[t - 1];
+    for (int i = lo; i < hi; ++i) { offs[i] = run; run += hist[i]; }
+}
+
+__global__ void scatter_kernel(uint32_t n_jobs, const uint8_t* __restrict__ cls, const uint16_t* __restrict__ bkt,
+                               unsigned int* __restrict__ offs, uint32_t* __restrict__ order)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_jobs; j += gridDim.x * blockDim.x) {
+        const unsigned int pos = atomicAdd(&offs[(size_t)cls[j] * NPH_KEY_BUCKETS + (NPH_KEY_BUCKETS - 1 - bkt[j])], 1u);
+        order[pos] = j;
+    }
+}
+
+} // namespace
+
+// Runs on ctx->stream after the jobs are on the device.  Fills ctx->classes, max_kpad/max_period, returns
+// NPH_ERR_INVALID if any job failed validation.  One stream synchronisation (the summary read-back).
+int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uint32_t* max_E_out)
+{
+    const size_t hist_n = (size_t)NPH_NUM_CLASSES * NPH_KEY_BUCKETS;
+    int rc;
+    if ((rc = nph_reserve(ctx, ctx->d_sched_cls, n_jobs)) != NPH_OK) return rc;
+    if ((rc = nph_reserve(ctx, ctx->d_sched_bkt, n_jobs)) != NPH_OK) return rc;
+    if ((rc = nph_reserve(ctx, ctx->d_sched_hist, 2 * hist_n + 1024)) != NPH_OK) return rc;
+    unsigned int* hist = ctx->d_sched_hist.p;
+    unsigned int* offs = hist + hist_n;
+    SchedSummary* d_sum = reinterpret_cast<SchedSummary*>(offs + hist_n);
+    static_assert(sizeof(SchedSummary) <= 1024 * sizeof(unsigned int), "summary fits the tail of the buffer");
+    NPH_CUDA(ctx, cudaMemsetAsync(hist, 0, sizeof(unsigned int) * (2 * hist_n + 1024), ctx->stream));
+    const int threads = 256;
+    int blocks = (int)std::min<size_t>((n_jobs + threads - 1) / threads, (size_t)ctx->sm_count * 8);
+    if (blocks < 1) blocks = 1;
+    classify_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->d_jobs.p, (uint32_t)n_jobs, ctx->d_reads.p, (uint32_t)ctx->n_reads,
+                                                        (uint32_t)ctx->models.size(), (uint64_t)n_ranks_total, ctx->d_sched_cls.p,
+                                                        ctx->d_sched_bkt.p, hist, d_sum);
+    NPH_CUDA(ctx, cudaGetLastError());
+    scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, offs);
+    NPH_CUDA(ctx, cudaGetLastError());
+    SchedSummary h{};
+    NPH_CUDA(ctx, cudaMemcpyAsync(&h, d_sum, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    scatter_kernel<<<blocks, threads, 0, ctx->stream>>>((uint32_t)n_jobs, ctx->d_sched_cls.p, ctx->d_sched_bkt.p, offs, ctx->d_order.p);
+    NPH_CUDA(ctx, cudaGetLastError());
+    NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h.error != 0) {
+        ctx->last_error = "job " + std::to_string(h.error - 1) + " fails validation (read/model index, event range, stride, or rank range)";
+        return NPH_ERR_INVALID;
+    }
+    ctx->classes.clear();
+    size_t first = 0;
+    for (int c = 0; c < NPH_NUM_CLASSES; ++c) {
+        ctx->classes.push_back(nph_ctx::ClassLaunch{c % NPH_MAX_COLS + 1, (int)nph_class_width(c / NPH_MAX_COLS), first,
+                                                    (size_t)h.class_count[c], (double)h.class_cost[c]});
+        first += (size_t)h.class_count[c];
+    }
+    ctx->max_kpad = std::max<uint32_t>(h.max_kpad, 32 * NPH_MAX_COLS);
+    ctx->max_period = std::max<uint32_t>(h.max_period, 40);
+    *max_E_out = std::max<uint32_t>(h.max_E, 1);
+    return NPH_OK;
+}

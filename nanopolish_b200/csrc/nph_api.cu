@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
+#include <cstdlib>
 #include <new>
 
 int nph_set_cuda_error(nph_ctx* ctx, cudaError_t e, const char* what)
@@ -31,6 +33,7 @@ template int nph_reserve<float>(nph_ctx*, DevBuf<float>&, size_t);
 template int nph_reserve<double>(nph_ctx*, DevBuf<double>&, size_t);
 template int nph_reserve<uint32_t>(nph_ctx*, DevBuf<uint32_t>&, size_t);
 template int nph_reserve<uint8_t>(nph_ctx*, DevBuf<uint8_t>&, size_t);
+template int nph_reserve<uint16_t>(nph_ctx*, DevBuf<uint16_t>&, size_t);
 template int nph_reserve<DevRead>(nph_ctx*, DevBuf<DevRead>&, size_t);
 template int nph_reserve<DevModelView>(nph_ctx*, DevBuf<DevModelView>&, size_t);
 template int nph_reserve<nph_hmm_job>(nph_ctx*, DevBuf<nph_hmm_job>&, size_t);
@@ -96,30 +99,6 @@ inline float2 read_transitions(double events_per_base, double indel_bias)
     return make_float2(logf(p_stay), logf(p_mm_next));
 }
 
-// Which kernel class (columns per lane, C) runs a job: minimise modelled issue slots =
-// steps x (per-step overhead + C x per-cell cost).  Constants from the ncu instruction counts
-// (profiles/): ~90 instructions per block-cell, ~110 per warp step of bookkeeping.
-const int kClassCols[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10};
-const int kNumClasses = 10;
-inline int class_index(int C) { return C - 1; }
-
-inline int choose_cols(uint32_t K, uint32_t E)
-{
-    double best = 1e300;
-    int best_c = 1;
-    for (int C : kClassCols) {
-        uint32_t strip = 32u * C;
-        uint32_t n_strips = (K + strip - 1) / strip;
-        uint32_t P = n_strips > 1 ? std::max<uint32_t>(E, 40) : E;
-        uint32_t last_cols = K - (n_strips - 1) * strip;
-        uint32_t end_lane = (last_cols - 1) / C;
-        double steps = (double)(n_strips - 1) * P + E + end_lane;
-        double cost = steps * (110.0 + 90.0 * C);
-        if (cost < best) { best = cost; best_c = C; }
-    }
-    return best_c;
-}
-
 int create_common(nph_ctx** out, int device, bool own_stream, cudaStream_t stream)
 {
     if (!out) return NPH_ERR_INVALID;
@@ -143,6 +122,11 @@ int create_common(nph_ctx** out, int device, bool own_stream, cudaStream_t strea
     }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < nph_ctx::kSideStreams; ++i) {
+        cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
+    }
 
     // quantised log-sum table, built exactly like p7_FLogsumInit (ref: src/common/logsum.cpp:57-69)
     std::vector<float> tbl(NPH_TBL_SMEM);
@@ -151,7 +135,7 @@ int create_common(nph_ctx** out, int device, bool own_stream, cudaStream_t strea
     if (cudaMalloc((void**)&ctx->d_logsum, sizeof(float) * NPH_TBL_SMEM) != cudaSuccess) { delete ctx; return NPH_ERR_NOMEM; }
     cudaMemcpy(ctx->d_logsum, tbl.data(), sizeof(float) * NPH_TBL_SMEM, cudaMemcpyHostToDevice);
     const_transitions(ctx->consts);
-    if (nph_reserve(ctx, ctx->d_counters, 16) != NPH_OK) { delete ctx; return NPH_ERR_NOMEM; }
+    if (nph_reserve(ctx, ctx->d_counters, NPH_NUM_COUNTERS) != NPH_OK) { delete ctx; return NPH_ERR_NOMEM; }
     if (ensure_flank(ctx, 4096) != NPH_OK) { delete ctx; return NPH_ERR_CUDA; }
     *out = ctx;
     return NPH_OK;
@@ -194,11 +178,13 @@ int nph_destroy(nph_ctx* ctx)
     free_buf(ctx->d_flank); free_buf(ctx->d_models); free_buf(ctx->d_reads); free_buf(ctx->d_ev_mean);
     free_buf(ctx->d_ev_time); free_buf(ctx->d_level); free_buf(ctx->d_drift); free_buf(ctx->d_ranks);
     free_buf(ctx->d_jobs); free_buf(ctx->d_trans); free_buf(ctx->d_order); free_buf(ctx->d_scores);
-    free_buf(ctx->d_counters); free_buf(ctx->d_scratch); free_buf(ctx->d_abea_jobs); free_buf(ctx->d_abea_ranks);
+    free_buf(ctx->d_counters); free_buf(ctx->d_sched_cls); free_buf(ctx->d_sched_bkt); free_buf(ctx->d_sched_hist); free_buf(ctx->d_scratch); free_buf(ctx->d_abea_jobs); free_buf(ctx->d_abea_ranks);
     free_buf(ctx->d_pairs); free_buf(ctx->d_abea_res); free_buf(ctx->d_abea_scratch); free_buf(ctx->d_abea_order); free_buf(ctx->d_abea_consts);
     for (auto& m : ctx->models) { cudaFree(m.mean); cudaFree(m.stdv); cudaFree(m.log_stdv); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int i = 0; i < nph_ctx::kSideStreams; ++i) { if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     delete ctx;
@@ -297,65 +283,23 @@ int nph_hmm_jobs_load(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_t
     if (!ctx->reads_loaded) return NPH_ERR_STATE;
     NPH_CUDA(ctx, cudaSetDevice(ctx->device));
 
-    // validate + classify + schedule (heaviest first inside each class, by coarse cost buckets)
-    std::vector<uint8_t> cls(n_jobs);
-    std::vector<uint32_t> bucket(n_jobs);
-    uint32_t max_kpad = 32, max_period = 40, max_E = 1;
-    constexpr int kBuckets = 64;
-    std::vector<size_t> hist((size_t)kNumClasses * kBuckets, 0);
-    for (size_t j = 0; j < n_jobs; ++j) {
-        const nph_hmm_job& jb = jobs[j];
-        if (jb.read >= ctx->n_reads || jb.model_id >= ctx->models.size() || jb.n_kmers == 0) return NPH_ERR_INVALID;
-        if (jb.rank_off + jb.n_kmers > n_ranks_total) return NPH_ERR_INVALID;
-        const uint32_t ne = ctx->h_read_n_events[jb.read];
-        if (jb.event_start >= ne || jb.event_stop >= ne) return NPH_ERR_INVALID;
-        if (jb.stride != 1 && jb.stride != -1) return NPH_ERR_INVALID;
-        if ((jb.event_stop > jb.event_start && jb.stride != 1) || (jb.event_stop < jb.event_start && jb.stride != -1)) return NPH_ERR_INVALID;
-        const uint32_t E = (jb.event_stop > jb.event_start ? jb.event_stop - jb.event_start : jb.event_start - jb.event_stop) + 1;
-        const uint32_t K = jb.n_kmers;
-        const int C = choose_cols(K, E);
-        const int ci = class_index(C);
-        cls[j] = (uint8_t)ci;
-        const uint32_t strip = 32u * C;
-        const uint32_t n_strips = (K + strip - 1) / strip;
-        max_kpad = std::max(max_kpad, n_strips * strip);
-        max_period = std::max(max_period, std::max<uint32_t>(E, 40));
-        max_E = std::max(max_E, E);
-        // cost bucket: log2 of block-cells, 64 buckets, larger first
-        const double cells = (double)E * K;
-        int b = (int)(log2(cells + 1.0) * 1.6);
-        b = std::min(kBuckets - 1, std::max(0, b));
-        bucket[j] = (uint32_t)(kBuckets - 1 - b);
-        hist[(size_t)ci * kBuckets + bucket[j]]++;
-    }
-    std::vector<size_t> start((size_t)kNumClasses * kBuckets);
-    size_t acc = 0;
-    ctx->classes.clear();
-    for (int ci = 0; ci < kNumClasses; ++ci) {
-        size_t first = acc;
-        for (int b = 0; b < kBuckets; ++b) { start[(size_t)ci * kBuckets + b] = acc; acc += hist[(size_t)ci * kBuckets + b]; }
-        ctx->classes.push_back(nph_ctx::ClassLaunch{kClassCols[ci], 32, first, acc - first});
-    }
-    std::vector<uint32_t> order(n_jobs);
-    for (size_t j = 0; j < n_jobs; ++j) order[start[(size_t)cls[j] * kBuckets + bucket[j]]++] = (uint32_t)j;
-
+    // per-read transition pair (2 logf with the host libm, see read_transitions)
     std::vector<float2> trans(ctx->n_reads);
     for (size_t i = 0; i < ctx->n_reads; ++i) trans[i] = read_transitions(ctx->h_events_per_base[i], indel_bias);
 
-    ctx->max_kpad = max_kpad;
-    ctx->max_period = max_period;
-    NPH_TRY(ensure_flank(ctx, (size_t)max_E + 2));
     NPH_TRY(nph_reserve(ctx, ctx->d_ranks, n_ranks_total));
     NPH_TRY(nph_reserve(ctx, ctx->d_jobs, n_jobs));
     NPH_TRY(nph_reserve(ctx, ctx->d_order, n_jobs));
     NPH_TRY(nph_reserve(ctx, ctx->d_trans, ctx->n_reads));
     NPH_TRY(nph_reserve(ctx, ctx->d_scores, n_jobs));
-    NPH_TRY(nph_reserve(ctx, ctx->d_scratch, nph_hmm_scratch_bytes(ctx, nullptr)));
-    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ranks.p, kmer_ranks, sizeof(uint32_t) * n_ranks_total, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_jobs.p, jobs, sizeof(nph_hmm_job) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
-    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_order.p, order.data(), sizeof(uint32_t) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ranks.p, kmer_ranks, sizeof(uint32_t) * n_ranks_total, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_trans.p, trans.data(), sizeof(float2) * ctx->n_reads, cudaMemcpyHostToDevice, ctx->stream));
-    NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // validate + classify + schedule on the device (hmm_schedule.cu); synchronises the stream once
+    uint32_t max_E = 1;
+    NPH_TRY(nph_schedule_hmm_jobs(ctx, n_jobs, n_ranks_total, &max_E));
+    NPH_TRY(ensure_flank(ctx, (size_t)max_E + 2));
+    NPH_TRY(nph_reserve(ctx, ctx->d_scratch, nph_hmm_scratch_bytes(ctx, nullptr)));
     ctx->n_jobs = n_jobs;
     ctx->n_ranks = n_ranks_total;
     ctx->jobs_loaded = true;
@@ -386,10 +330,18 @@ int nph_hmm_score_batch(nph_ctx* ctx,
                         const nph_hmm_job* jobs, size_t n_jobs,
                         double indel_bias, float* scores_out)
 {
+    static const bool timing = getenv("NPH_TIMING") != nullptr;   // development aid: per-phase host wall time on stderr
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     NPH_TRY(nph_reads_load(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total));
+    const double t1 = now();
     NPH_TRY(nph_hmm_jobs_load(ctx, kmer_ranks, n_ranks_total, jobs, n_jobs, indel_bias));
+    const double t2 = now();
     NPH_TRY(nph_hmm_score(ctx, nullptr));
-    return nph_hmm_scores_fetch(ctx, scores_out, n_jobs);
+    const int rc = nph_hmm_scores_fetch(ctx, scores_out, n_jobs);
+    const double t3 = now();
+    if (timing) fprintf(stderr, "[nph] reads_load %.2f ms  jobs_load %.2f ms  score+fetch %.2f ms\n", t1 - t0, t2 - t1, t3 - t2);
+    return rc;
 }
 
 // profile_hmm_score_set's combination step (ref: src/hmm/nanopolish_profile_hmm.cpp:32-56): host

@@ -5,11 +5,13 @@
 #include <stddef.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include "../../include/nph.h"
 
 #define NPH_LOGSUM_TBL 16000        // ref: p7_LOGSUM_TBL, src/common/logsum.h:20
 #define NPH_LOGSUM_CUT 15700        // (max-min) >= 15.7f returns max: entries >= 15700 are never read
 #define NPH_TBL_SMEM   (NPH_LOGSUM_CUT + 1)   // +1: a zero entry that the clamped index lands on
+#define NPH_NUM_COUNTERS 64          // work-queue counters: one per forward class (<= 40) + ABEA (last)
 
 // Per-read record on the device (what the kernels need of nph_read after the prologue).
 struct DevRead {
@@ -78,8 +80,11 @@ struct nph_ctx {
     DevBuf<uint32_t> d_order;        // job indices grouped by kernel class, heavy first
     DevBuf<float> d_scores;
     DevBuf<unsigned int> d_counters;
+    DevBuf<uint8_t> d_sched_cls;     // per job: kernel class
+    DevBuf<uint16_t> d_sched_bkt;    // per job: schedule key bucket
+    DevBuf<unsigned int> d_sched_hist;   // histogram + offsets + summary
     DevBuf<uint8_t> d_scratch;
-    struct ClassLaunch { int cols_per_lane; int group_width; size_t first; size_t count; };
+    struct ClassLaunch { int cols_per_lane; int group_width; size_t first; size_t count; double cost; };
     std::vector<ClassLaunch> classes;
     uint32_t max_kpad = 0, max_period = 0;
     bool jobs_loaded = false;
@@ -100,6 +105,10 @@ struct nph_ctx {
 
     // measurement
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // side streams so that the tail of one forward class overlaps the head of the next (fork/join by events)
+    static const int kSideStreams = 4;
+    cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     int last_launches = 0;
     bool timing_valid = false;
 
@@ -119,3 +128,4 @@ int nph_launch_read_prologue(nph_ctx* ctx);
 int nph_launch_hmm_forward(nph_ctx* ctx, float* scores_dev);
 size_t nph_hmm_scratch_bytes(const nph_ctx* ctx, int* warps_total_out);
 int nph_launch_abea(nph_ctx* ctx);
+int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uint32_t* max_E_out);
