@@ -209,7 +209,12 @@ int nph_mom_batch(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
                   const uint32_t* kmer_ranks, size_t n_ranks_total,
                   const nph_abea_job* jobs, size_t n_jobs, uint32_t model_id, double* shift_scale_out);
 
-/* ---- profile_hmm_align (Viterbi; section 8f N1) ------------------------------------------ */
+/* ---- profile_hmm_align (Viterbi; section 8f N1) ------------------------------------------
+ * states_out receives, for job j, n_states_out[j] HMMAlignmentStates at states_out + states_off[j] in ascending
+ * event order; states_off has n_jobs + 1 entries and states_off[j+1] - states_off[j] is the room for job j
+ * (n_events + n_kmers always suffices).  n_states_out[j] == 0 where the reference would trip an assert (fewer
+ * than two events, or the best path runs into a -inf cell).  scores_out (optional) = l_fm of the last state.
+ * ref: profile_hmm_align_r9, src/hmm/nanopolish_profile_hmm_r9.cpp:73-204. */
 int nph_hmm_align_batch(nph_ctx* ctx,
                         const nph_read* reads, size_t n_reads,
                         const float* ev_mean, const double* ev_start_time, size_t n_events_total,

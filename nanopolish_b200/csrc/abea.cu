@@ -532,10 +532,4 @@ int nph_mom_batch(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
     return NPH_OK;
 }
 
-int nph_hmm_align_batch(nph_ctx*, const nph_read*, size_t, const float*, const double*, size_t, const uint32_t*, size_t,
-                        const nph_hmm_job*, size_t, double, nph_align_state*, const uint64_t*, uint32_t*, float*)
-{
-    return NPH_ERR_UNSUPPORTED;   // section 8(f) row N1: lands after the forward + ABEA kernels
-}
-
 } // extern "C"

@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .synth import ABEA_RES_DT, PAIR_DT
+from .synth import ABEA_RES_DT, ALIGN_STATE_DT, PAIR_DT
 
 
 def _p(a):
@@ -99,6 +99,24 @@ class Engine:
         out = np.empty(g, np.float32)
         self._check(self.lib.nph_score_set_combine(_p(s), g, n_alt, _p(out)), "nph_score_set_combine")
         return out
+
+    # ---- Viterbi alignment (profile_hmm_align) -------------------------------------------
+    def hmm_align_batch(self, reads, ev_mean, ev_start_time, kmer_ranks, jobs, indel_bias: float = 1.0):
+        """== [profile_hmm_align(seq_j, data_j, flags_j) for j]: list of ALIGN_STATE_DT arrays (empty where the
+        reference would assert), plus l_fm of each alignment's final state."""
+        n = jobs.shape[0]
+        E = np.abs(jobs["event_stop"].astype(np.int64) - jobs["event_start"].astype(np.int64)) + 1
+        caps = E + jobs["n_kmers"].astype(np.int64) + 2
+        off = np.zeros(n + 1, np.uint64)
+        off[1:] = np.cumsum(caps)
+        states = np.zeros(int(off[-1]), ALIGN_STATE_DT)
+        counts = np.zeros(n, np.uint32)
+        scores = np.zeros(n, np.float32)
+        self._check(self.lib.nph_hmm_align_batch(self.ctx, _p(reads), reads.shape[0], _p(ev_mean), _p(ev_start_time),
+                                                 ev_mean.shape[0], _p(kmer_ranks), kmer_ranks.shape[0], _p(jobs), n,
+                                                 indel_bias, _p(states), _p(off), _p(counts), _p(scores)),
+                    "nph_hmm_align_batch")
+        return [states[int(off[j]):int(off[j]) + int(counts[j])] for j in range(n)], scores
 
     # ---- ABEA ---------------------------------------------------------------------------
     def abea_batch(self, reads, ev_mean, ev_start_time, kmer_ranks, jobs, model_id: int, pairs_total: int):

@@ -38,6 +38,9 @@ ABEA_RES_DT = np.dtype([
     ("n_pairs", "<u4"), ("status", "<i4"), ("max_gap", "<i4"), ("n_aligned", "<u4"),
     ("avg_log_emission", "<f8"),
 ], align=True)
+ALIGN_STATE_DT = np.dtype([("event_idx", "<u4"), ("kmer_idx", "<u4"), ("l_fm", "<f4"), ("state", "S1"),
+                           ("reserved", "u1", (3,))], align=True)
+assert ALIGN_STATE_DT.itemsize == 16
 assert READ_DT.itemsize == 64 and HMM_JOB_DT.itemsize == 32 and ABEA_JOB_DT.itemsize == 32
 assert PAIR_DT.itemsize == 8 and ABEA_RES_DT.itemsize == 24
 

@@ -299,6 +299,63 @@ float npo_hmm_score(const nph_read* reads, const float* ev_mean, const double* e
     return s;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Viterbi alignment.  ref: profile_hmm_align_r9, src/hmm/nanopolish_profile_hmm_r9.cpp:73-204 with
+ * ProfileHMMViterbiOutputR9 (src/hmm/nanopolish_profile_hmm_r9.inl:130-197).  The backtrack starts at
+ * (last row, MATCH of the last k-mer) — not at the best end cell — and stops at a FROM_SOFT movement.
+ * Returns the number of states written (ascending event order), or 0 with *status != 0 where the
+ * reference would hit an assert (n_events < 2, or the path runs into a -inf cell).
+ * ---------------------------------------------------------------------------------------- */
+uint32_t npo_hmm_align(const nph_read* reads, const float* ev_mean, const double* ev_start_time,
+                       const npo_model* models, const uint32_t* kmer_ranks, const nph_hmm_job* job,
+                       double indel_bias, nph_align_state* out, uint32_t cap, int* status)
+{
+    npo_init();
+    *status = 0;
+    const uint32_t n_kmers = job->n_kmers;
+    const size_t n_rows = job_rows(job);
+    const uint32_t n_events = (uint32_t)n_rows - 1;
+    if (n_events < 2) { *status = 1; return 0; }
+    const uint32_t n_cols = NST * (n_kmers + 2);
+    float* vm = (float*)malloc(sizeof(float) * n_rows * n_cols);
+    uint8_t* bm = (uint8_t*)calloc(n_rows * n_cols, 1);
+    uint32_t er = 0, ec = 0;
+    hmm_fill(reads, ev_mean, ev_start_time, models, kmer_ranks, job, indel_bias, vm, 1, bm, &er, &ec);
+
+    const char sym[3] = { 'K', 'B', 'M' };
+    uint32_t row = (uint32_t)n_rows - 1;
+    uint32_t col = NST * n_kmers + ST_M;
+    uint32_t n = 0;
+    while (row > 0) {
+        uint32_t event_idx = job->event_start + (row - 1) * job->stride;
+        uint32_t block = col / NST;
+        uint32_t kmer_idx = block - 1;
+        int ps = (int)(col % NST);
+        if (block == 0 || vm[(size_t)row * n_cols + col] == -INFINITY) { *status = 2; n = 0; break; }
+        if (n < cap) {
+            out[n].event_idx = event_idx; out[n].kmer_idx = kmer_idx;
+            out[n].l_fm = vm[(size_t)row * n_cols + col]; out[n].state = sym[ps];
+            out[n].reserved[0] = out[n].reserved[1] = out[n].reserved[2] = 0;
+        } else { *status = 3; n = 0; break; }
+        n++;
+        int movement = bm[(size_t)row * n_cols + col];
+        if (movement == 5) break;                 /* HMT_FROM_SOFT */
+        int next_ps = ST_M;
+        switch (movement) {
+            case 0: next_ps = ST_M; break;                       /* FROM_SAME_M */
+            case 1: kmer_idx -= 1; next_ps = ST_M; break;        /* FROM_PREV_M */
+            case 2: next_ps = ST_B; break;                       /* FROM_SAME_B */
+            case 3: kmer_idx -= 1; next_ps = ST_B; break;        /* FROM_PREV_B */
+            case 4: kmer_idx -= 1; next_ps = ST_K; break;        /* FROM_PREV_K */
+        }
+        if (ps != ST_K) row -= 1;                 /* a k-mer skip is silent: same row */
+        col = NST * (kmer_idx + 1) + next_ps;
+    }
+    for (uint32_t i = 0, j = n ? n - 1 : 0; i < j; ++i, --j) { nph_align_state t = out[i]; out[i] = out[j]; out[j] = t; }
+    free(vm); free(bm);
+    return n;
+}
+
 static double now_s(void)
 {
     struct timespec ts;

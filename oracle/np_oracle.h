@@ -39,6 +39,10 @@ double npo_hmm_score_batch(const nph_read* reads, const float* ev_mean, const do
                            float* scores_out);
 float npo_score_set_combine(const float* scores, uint32_t n_alt);
 
+uint32_t npo_hmm_align(const nph_read* reads, const float* ev_mean, const double* ev_start_time,
+                       const npo_model* models, const uint32_t* kmer_ranks, const nph_hmm_job* job,
+                       double indel_bias, nph_align_state* out, uint32_t cap, int* status);
+
 int64_t npo_abea(const nph_read* reads, const float* ev_mean, const double* ev_start_time,
                  const npo_model* model, const uint32_t* kmer_ranks, const nph_abea_job* job,
                  nph_aligned_pair* pairs_out, nph_abea_result* res);

@@ -95,6 +95,19 @@ class PortOracle:
                                         C.c_double(indel_bias), _p(fm))
         return s, fm
 
+    def hmm_align(self, reads, ev_mean, ev_start, model_list, kmer_ranks, job, indel_bias=1.0):
+        from nanopolish_b200.synth import ALIGN_STATE_DT
+        E = abs(int(job["event_stop"]) - int(job["event_start"])) + 1
+        cap = E + int(job["n_kmers"]) + 4
+        out = np.zeros(cap, ALIGN_STATE_DT)
+        marr = self.models(model_list)
+        jb = np.array([job], dtype=job.dtype)
+        st = C.c_int()
+        self.lib.npo_hmm_align.restype = C.c_uint32
+        n = self.lib.npo_hmm_align(_p(reads), _p(ev_mean), _p(ev_start), marr, _p(kmer_ranks), _p(jb), C.c_double(indel_bias),
+                                   _p(out), C.c_uint32(cap), C.byref(st))
+        return out[:n].copy(), st.value
+
     def score_set_combine(self, scores):
         s = np.ascontiguousarray(scores, np.float32)
         return self.lib.npo_score_set_combine(_p(s), C.c_uint32(s.shape[0]))
@@ -191,6 +204,13 @@ class RefOracle:
         secs = self.lib.npref_score_batch(C.c_size_t(n), _p(rh), _p(mh), _p(es), _p(ee), _p(rc), _p(fl),
                                           C.c_char_p(buf), _p(off), C.c_double(indel_bias), C.c_int(threads), _p(out))
         return out, secs
+
+    def align(self, read_h, model_h, seq: bytes, e_start, e_stop, rc, flags, indel_bias=1.0):
+        cap = abs(int(e_stop) - int(e_start)) + 1 + len(seq) + 4
+        ek = np.zeros((cap, 2), np.uint32); lfm = np.zeros(cap, np.float32); st = C.create_string_buffer(cap)
+        n = self.lib.npref_align(int(read_h), model_h, C.c_char_p(seq), C.c_uint32(int(e_start)), C.c_uint32(int(e_stop)), int(rc),
+                                 C.c_uint32(int(flags)), C.c_double(indel_bias), _p(ek), _p(lfm), st, C.c_uint32(cap))
+        return ek[:n].copy(), lfm[:n].copy(), st.raw[:n]
 
     def kmer_ranks(self, model_h, seq: bytes, rc: bool):
         out = np.zeros(max(len(seq), 1), np.uint32)

@@ -161,6 +161,31 @@ double npref_score_batch(size_t n_jobs, const int32_t* read_h, const int32_t* mo
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// profile_hmm_align on one job; out = (event_idx, kmer_idx) u32 pairs, l_fm floats, state chars.
+// Guards the conditions the reference asserts on so the harness does not abort the test process.
+int npref_align(int read_h, int model_h, const char* seq, uint32_t e_start, uint32_t e_stop, int rc, uint32_t flags,
+                double indel_bias, uint32_t* ev_kmer_out, float* lfm_out, char* state_out, uint32_t cap)
+{
+    hmm_indel_bias_factor = indel_bias;
+    const PoreModel* pm = g_models[model_h];
+    HMMInputSequence hseq(std::string(seq), pm->pmalphabet);
+    HMMInputData data;
+    data.read = g_reads[read_h].get();
+    data.pore_model = pm;
+    data.event_start_idx = e_start;
+    data.event_stop_idx = e_stop;
+    data.strand = 0;
+    data.rc = rc;
+    data.event_stride = rc ? -1 : 1;
+    std::vector<HMMAlignmentState> a = profile_hmm_align(hseq, data, flags);
+    if (a.size() > cap) return -1;
+    for (size_t i = 0; i < a.size(); ++i) {
+        ev_kmer_out[2 * i] = a[i].event_idx; ev_kmer_out[2 * i + 1] = a[i].kmer_idx;
+        lfm_out[i] = (float)a[i].l_fm; state_out[i] = a[i].state;
+    }
+    return (int)a.size();
+}
+
 int npref_kmer_ranks(int model_h, const char* seq, int rc, uint32_t* out)
 {
     const PoreModel* pm = g_models[model_h];

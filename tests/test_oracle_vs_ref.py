@@ -107,3 +107,21 @@ def test_mom_matches(port_oracle, ref_oracle):
         want = ref_oracle.mom(rh[i], h, synth._CODE2DNA[rs.seq_codes[i]].tobytes())
         sh, sc = port_oracle.mom(rs.reads, rs.ev_mean, model, ranks, jobs[i])
         assert want[0] == sh and want[1] == sc and want[2] == 0.0 and want[3] == 1.0
+
+
+def test_viterbi_align_identical(port_oracle, ref_oracle):
+    """profile_hmm_align: identical paths, states and bit-identical l_fm (both strands, flags 0 and PRE|POST)."""
+    nuc = synth.load_model("nucleotide")
+    rs = synth.gen_reads(3, 900, nuc, seed=21, drift=True)
+    jobs = synth.scorereads_jobs(rs, 170, rc_every=2, keep_seqs=True)
+    ref_oracle.clear_reads()
+    h = ref_oracle.builtin_model("nucleotide")
+    rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, h)
+    for j in range(jobs.jobs.shape[0]):
+        for flags in (0, 3):
+            jb = jobs.jobs[j].copy(); jb["flags"] = flags
+            ek, lfm, st = ref_oracle.align(rh[int(jb["read"])], h, jobs.seqs[j], jb["event_start"], jb["event_stop"], jb["rc"], flags)
+            out, status = port_oracle.hmm_align(rs.reads, rs.ev_mean, rs.ev_start_time, [nuc], jobs.kmer_ranks, jb)
+            assert status == 0 and out.shape[0] == ek.shape[0] > 0
+            assert np.array_equal(out["event_idx"], ek[:, 0]) and np.array_equal(out["kmer_idx"], ek[:, 1])
+            assert np.array_equal(out["l_fm"].view(np.uint32), lfm.view(np.uint32)) and out["state"].tobytes() == st
