@@ -143,12 +143,12 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
 
         for (int bi = 2; bi < n_bands; ++bi) {
             // Suzuki's rule on the two ends of band bi-1 (offset 0 = column lo, offset 99 = column lo+99)
+            bool right;
             {
                 const int u0 = lo + 128, u1 = lo + 128 + (kBW - 1);
                 const float ll = __shfl_sync(kFull, sel4(b1, (u0 >> 5) & 3), u0 & 31);
                 const float ur = __shfl_sync(kFull, sel4(b1, (u1 >> 5) & 3), u1 & 31);
-                const bool right = (ll == NEG && ur == NEG) ? ((bi & 1) == 1) : (ll < ur);
-                if (right) lo += 1;
+                right = (ll == NEG && ur == NEG) ? ((bi & 1) == 1) : (ll < ur);
             }
             // left neighbour column in band bi-1 (lane 0's neighbour lives in lane 31, previous slot)
             float lf[4];
@@ -157,25 +157,32 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
                 const float send = (lane == 31) ? b1[(s + 3) & 3] : b1[s];
                 lf[s] = __shfl_sync(kFull, send, (lane + 31) & 31);
             }
+            if (right) {
+                // column `lo` leaves the band for good: exactly one (lane, slot) owns it; that slot now follows
+                // column lo+128 (not yet in band: everything about it is -inf until the band reaches it)
+                const int u = lo + 128;
+                if (lane == (u & 31)) {
+                    const int sl = (u >> 5) & 3;
+                    const int cn = lo + 128;
+                    float4 g = make_float4(0.f, 1.f, 0.f, 1.f);
+                    if (cn <= K) g = prm[cn - 1];
+                    const int en = bi - 1 - cn;
+                    const float xv = lv[min(max(en, 0), E - 1)];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        if (s == sl) { cs[s] = cn; b1[s] = NEG; dg[s] = NEG; lf[s] = NEG; mu[s] = g.x; sd[s] = g.y; cc[s] = g.z; ry[s] = g.w; xn[s] = xv; }
+                    }
+                }
+                lo += 1;
+            }
             uint32_t tbyte = 0;
             const int hi = lo + (kBW - 1);
+            const unsigned col_lim = (unsigned)min(hi, K);     // a real cell needs 1 <= c <= min(hi, K)
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-                if (cs[s] < lo) {
-                    // the column left the band for good: this slot now follows column c+128 (not yet in band)
-                    cs[s] += 128;
-                    b1[s] = NEG; dg[s] = NEG; lf[s] = NEG;
-                    if (cs[s] <= K) {
-                        const float4 g = prm[cs[s] - 1];
-                        mu[s] = g.x; sd[s] = g.y; cc[s] = g.z; ry[s] = g.w;
-                    }
-                    const int en = bi - 1 - cs[s];
-                    xn[s] = (en >= 0 && en < E) ? lv[en] : 0.f;
-                }
                 const int c = cs[s];
                 const int e = bi - 1 - c;
-                const bool in_band = c <= hi;
-                const bool ev_ok = (e >= 0) && (e < E);
+                const bool cell = ((unsigned)e < (unsigned)E) && ((unsigned)(c - 1) < col_lim);
                 const float x = xn[s];
                 // emission (emissions.h:51-55) — computed for every slot, used where the cell exists
                 const float a = div_by_cached_rcp(__fsub_rn(x, mu[s]), sd[s], ry[s]);
@@ -190,19 +197,19 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
                 from = (mx == score_u) ? kFromU : from;
                 mx = score_l > mx ? score_l : mx;
                 from = (mx == score_l) ? kFromL : from;
-
-                float nv = NEG;
-                int nf = 0;
-                if (in_band && ev_ok) {
-                    if (c >= 1 && c <= K) { nv = mx; nf = from; }
-                    else if (c == 0) { nv = (float)__dmul_rn(lp_trim, (double)(e + 1)); nf = kFromU; }
-                }
                 dg[s] = lf[s];
-                b1[s] = nv;
-                tbyte |= (uint32_t)nf << (2 * s);
-                // next band's event for this column
-                const int en = e + 1;
-                xn[s] = (en >= 0 && en < E) ? lv[en] : 0.f;
+                b1[s] = cell ? mx : NEG;
+                tbyte |= (uint32_t)(cell ? from : 0) << (2 * s);
+                // next band's event for this column (clamped: the value is unused when the cell does not exist)
+                xn[s] = lv[min(max(e + 1, 0), E - 1)];
+            }
+            if (lo <= 0) {
+                // the trim column (c == 0, k-mer -1) is still inside the band: lp_trim * (event + 1), from = U (:206-216)
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int e = bi - 1;
+                    if (cs[s] == 0 && e < E) { b1[s] = (float)__dmul_rn(lp_trim, (double)(e + 1)); tbyte |= (uint32_t)kFromU << (2 * s); }
+                }
             }
             trace[(size_t)bi * 32 + lane] = (uint8_t)tbyte;
 
@@ -497,6 +504,7 @@ int nph_abea_batch(nph_ctx* ctx,
                    const nph_abea_job* jobs, size_t n_jobs, uint32_t model_id,
                    nph_aligned_pair* pairs_out, size_t pairs_total, nph_abea_result* results)
 {
+    if (n_jobs == 0) return ctx ? NPH_OK : NPH_ERR_INVALID;      // empty batch
     NPH_TRY(nph_reads_load(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total));
     NPH_TRY(nph_abea_jobs_load(ctx, kmer_ranks, n_ranks_total, jobs, n_jobs, model_id, pairs_total));
     NPH_TRY(nph_abea_run(ctx));

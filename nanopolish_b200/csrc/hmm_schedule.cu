@@ -19,7 +19,8 @@ struct SchedSummary {
 };
 
 __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n_jobs, const DevRead* __restrict__ reads,
-                                uint32_t n_reads, uint32_t n_models, uint64_t n_ranks, uint8_t* __restrict__ cls,
+                                uint32_t n_reads, const DevModelView* __restrict__ models, const uint32_t* __restrict__ ranks,
+                                uint32_t n_models, uint64_t n_ranks, uint8_t* __restrict__ cls,
                                 uint16_t* __restrict__ bkt, unsigned int* __restrict__ hist, SchedSummary* __restrict__ sum)
 {
     __shared__ unsigned int s_count[NPH_NUM_CLASSES];
@@ -36,6 +37,14 @@ __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n
             const uint32_t ne = reads[jb.read].n_events;
             ok = jb.event_start < ne && jb.event_stop < ne;
             ok = ok && !(jb.event_stop > jb.event_start && jb.stride != 1) && !(jb.event_stop < jb.event_start && jb.stride != -1);
+        }
+        if (ok) {
+            // every k-mer rank must index the job's model table (the reference would read past PoreModel::states)
+            const uint32_t ns = models[jb.model_id].n_states;
+            const uint32_t* rk = ranks + jb.rank_off;
+            uint32_t worst = 0;
+            for (uint32_t i = 0; i < jb.n_kmers; ++i) worst = max(worst, rk[i]);
+            ok = worst < ns;
         }
         if (!ok) { atomicCAS(&sum->error, 0, (int)(j + 1)); cls[j] = 0; bkt[j] = 0; continue; }
         const uint32_t E = (jb.event_stop > jb.event_start ? jb.event_stop - jb.event_start : jb.event_start - jb.event_stop) + 1;
@@ -115,7 +124,7 @@ int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uin
     int blocks = (int)std::min<size_t>((n_jobs + threads - 1) / threads, (size_t)ctx->sm_count * 8);
     if (blocks < 1) blocks = 1;
     classify_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->d_jobs.p, (uint32_t)n_jobs, ctx->d_reads.p, (uint32_t)ctx->n_reads,
-                                                        (uint32_t)ctx->models.size(), (uint64_t)n_ranks_total, ctx->d_sched_cls.p,
+                                                        ctx->d_models.p, ctx->d_ranks.p, (uint32_t)ctx->models.size(), (uint64_t)n_ranks_total, ctx->d_sched_cls.p,
                                                         ctx->d_sched_bkt.p, hist, d_sum);
     NPH_CUDA(ctx, cudaGetLastError());
     scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, offs);
@@ -126,7 +135,7 @@ int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uin
     NPH_CUDA(ctx, cudaGetLastError());
     NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (h.error != 0) {
-        ctx->last_error = "job " + std::to_string(h.error - 1) + " fails validation (read/model index, event range, stride, or rank range)";
+        ctx->last_error = "job " + std::to_string(h.error - 1) + " fails validation (read/model index, event range, stride, rank range or a k-mer rank outside the model)";
         return NPH_ERR_INVALID;
     }
     ctx->classes.clear();

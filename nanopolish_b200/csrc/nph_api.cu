@@ -279,7 +279,9 @@ int nph_reads_load(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
 int nph_hmm_jobs_load(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_total,
                       const nph_hmm_job* jobs, size_t n_jobs, double indel_bias)
 {
-    if (!ctx || !kmer_ranks || !jobs || n_jobs == 0) return NPH_ERR_INVALID;
+    if (!ctx) return NPH_ERR_INVALID;
+    if (n_jobs == 0) { ctx->n_jobs = 0; ctx->classes.clear(); ctx->jobs_loaded = true; return NPH_OK; }   // empty batch: nothing to score
+    if (!kmer_ranks || !jobs) return NPH_ERR_INVALID;
     if (!ctx->reads_loaded) return NPH_ERR_STATE;
     NPH_CUDA(ctx, cudaSetDevice(ctx->device));
 
@@ -309,14 +311,18 @@ int nph_hmm_jobs_load(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_t
 int nph_hmm_score(nph_ctx* ctx, float* scores_dev)
 {
     if (!ctx) return NPH_ERR_INVALID;
-    if (!ctx->reads_loaded || !ctx->jobs_loaded) return NPH_ERR_STATE;
+    if (!ctx->jobs_loaded) return NPH_ERR_STATE;
+    if (ctx->n_jobs == 0) return NPH_OK;
+    if (!ctx->reads_loaded) return NPH_ERR_STATE;
     NPH_CUDA(ctx, cudaSetDevice(ctx->device));
     return nph_launch_hmm_forward(ctx, scores_dev);
 }
 
 int nph_hmm_scores_fetch(nph_ctx* ctx, float* scores_out, size_t n_jobs)
 {
-    if (!ctx || !scores_out) return NPH_ERR_INVALID;
+    if (!ctx) return NPH_ERR_INVALID;
+    if (n_jobs == 0) return NPH_OK;
+    if (!scores_out) return NPH_ERR_INVALID;
     if (!ctx->jobs_loaded || n_jobs > ctx->n_jobs) return NPH_ERR_STATE;
     NPH_CUDA(ctx, cudaMemcpyAsync(scores_out, ctx->d_scores.p, sizeof(float) * n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
     NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -333,6 +339,7 @@ int nph_hmm_score_batch(nph_ctx* ctx,
     static const bool timing = getenv("NPH_TIMING") != nullptr;   // development aid: per-phase host wall time on stderr
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
+    if (n_jobs == 0) return ctx ? NPH_OK : NPH_ERR_INVALID;      // empty batch
     NPH_TRY(nph_reads_load(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total));
     const double t1 = now();
     NPH_TRY(nph_hmm_jobs_load(ctx, kmer_ranks, n_ranks_total, jobs, n_jobs, indel_bias));

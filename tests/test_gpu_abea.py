@@ -110,3 +110,29 @@ def test_staged_abea_timing(engine, nuc):
     assert (res["n_pairs"] > 1900).all()
     ms, launches = engine.last_kernel_ms()
     assert ms > 0 and launches == 1
+
+
+def test_full_size_properties(engine, nuc, port_oracle):
+    """BASELINE config 4 shape (8 000-event reads) on a few thousand reads: every read aligns, pairs are sorted
+    and in range, a random sample equals the oracle's path exactly, and a second run is identical."""
+    model, mid = nuc
+    rs = synth.gen_reads(2400, 8000, model, seed=31337, rng_scalings=False)
+    jobs, ranks, total = synth.abea_jobs(rs)
+    engine.reads_load(rs.reads, rs.ev_mean, rs.ev_start_time)
+    engine.abea_jobs_load(ranks, jobs, mid, total)
+    engine.abea_run(); p1, r1 = engine.abea_fetch()
+    engine.abea_run(); p2, r2 = engine.abea_fetch()
+    assert np.array_equal(r1["n_pairs"], r2["n_pairs"]) and (r1["n_pairs"] >= 8000).all()
+    for i in range(0, rs.n_reads, 97):
+        o, n = int(jobs[i]["pairs_off"]), int(r1[i]["n_pairs"])
+        a = p1[o:o + n]
+        assert np.array_equal(a, p2[o:o + n])
+        assert a["ref_pos"][0] == 0 and a["ref_pos"][-1] == int(jobs[i]["n_kmers"]) - 1
+        assert (np.diff(a["ref_pos"]) >= 0).all() and (np.diff(a["read_pos"]) >= 0).all()
+        assert (np.diff(a["ref_pos"]) + np.diff(a["read_pos"]) >= 1).all()
+    sample = np.array([0, 5, 777, 1234, 2399])
+    sj = jobs[sample].copy()
+    po, ro, _ = port_oracle.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, model, ranks, sj, total, threads=8)
+    for t, i in enumerate(sample):
+        o, n = int(jobs[i]["pairs_off"]), int(ro[t]["n_pairs"])
+        assert n == int(r1[i]["n_pairs"]) and np.array_equal(p1[o:o + n], po[o:o + n])

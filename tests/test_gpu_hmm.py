@@ -144,3 +144,47 @@ def test_exact_math_primitives_on_device():
     r = subprocess.run([exe, "200"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 mismatches" in r.stdout
+
+
+def test_rank_outside_model_is_rejected(engine, models):
+    from nanopolish_b200._lib import NphError
+    nuc = models["nucleotide"][0]
+    rs = synth.gen_reads(1, 400, nuc, seed=6)
+    jobs = synth.scorereads_jobs(rs, 100, model_id=models["nucleotide"][1])
+    bad = jobs.kmer_ranks.copy()
+    bad[7] = 4096                        # 4^6 states: ranks are 0..4095
+    with pytest.raises(NphError):
+        engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, bad, jobs.jobs)
+
+
+def test_empty_batch_is_ok(engine, models):
+    nuc = models["nucleotide"][0]
+    rs = synth.gen_reads(1, 300, nuc, seed=6)
+    out = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, np.zeros(0, np.uint32), np.zeros(0, synth.HMM_JOB_DT))
+    assert out.shape == (0,)
+
+
+def test_full_size_properties(engine, models, port_oracle):
+    """BASELINE configs[1] at full size (10 000 reads x 4 000 events, 60 000 jobs) through size-independent
+    properties: (a) a random sample of jobs equals the oracle bit for bit; (b) scoring a permuted job list
+    permutes the scores (scheduling does not leak into results); (c) a second run is bit-identical."""
+    nuc, mid = models["nucleotide"]
+    rs = synth.gen_reads(10000, 4000, nuc, seed=42)
+    jobs = synth.scorereads_jobs(rs, 500, model_id=mid)
+    assert jobs.jobs.shape[0] == 60000
+    engine.reads_load(rs.reads, rs.ev_mean, rs.ev_start_time)
+    engine.hmm_jobs_load(jobs.kmer_ranks, jobs.jobs)
+    engine.hmm_score(); a = engine.hmm_scores_fetch()
+    engine.hmm_score(); b = engine.hmm_scores_fetch()
+    assert np.array_equal(_bits(a), _bits(b)) and np.isfinite(a).all()
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(jobs.jobs.shape[0])
+    engine.hmm_jobs_load(jobs.kmer_ranks, np.ascontiguousarray(jobs.jobs[perm]))
+    engine.hmm_score(); c = engine.hmm_scores_fetch()
+    assert np.array_equal(_bits(c), _bits(a[perm]))
+    sample = np.sort(rng.choice(jobs.jobs.shape[0], 160, replace=False))
+    oj = np.ascontiguousarray(jobs.jobs[sample]); oj["model_id"] = 0
+    want, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [nuc], jobs.kmer_ranks, oj, threads=64)
+    _check(a[sample], want)
+    # mean log-likelihood per scored event of the whole batch sits where the generator puts it
+    assert abs(a.astype(np.float64).sum() / jobs.scored_events + 2.88) < 0.05
