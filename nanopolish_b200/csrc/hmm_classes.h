@@ -13,12 +13,13 @@
 #define NPH_HD inline
 #endif
 
-#define NPH_NUM_WIDTHS 4
+#define NPH_NUM_WIDTHS 5              // 4, 8, 16, 32 lanes single-strip; 32 lanes with chained strips
 #define NPH_MAX_COLS 10
 #define NPH_NUM_CLASSES (NPH_NUM_WIDTHS * NPH_MAX_COLS)
 #define NPH_KEY_BUCKETS 4096          // schedule key: exact step count below 2048, then 16-step bins
 
-NPH_HD uint32_t nph_class_width(int wi) { return 4u << wi; }                 // 4, 8, 16, 32
+NPH_HD uint32_t nph_class_width(int wi) { return wi >= 3 ? 32u : (4u << wi); }   // 4, 8, 16, 32, 32 (chained)
+NPH_HD bool nph_class_chained(int wi) { return wi == 4; }
 NPH_HD int nph_class_index(int C, int wi) { return wi * NPH_MAX_COLS + (C - 1); }
 
 // warp steps one job takes in class (C, W): chained strips of W*C columns, period max(E, 40) when chained
@@ -37,12 +38,13 @@ NPH_HD float nph_class_cost(uint32_t steps, int C, uint32_t W) { return (float)s
 NPH_HD int nph_choose_class(uint32_t K, uint32_t E, uint32_t* steps_out)
 {
     float best = 3.0e38f;
-    int best_cls = nph_class_index(1, 3);
+    int best_cls = nph_class_index(NPH_MAX_COLS, 4);
     uint32_t best_steps = 0;
     for (int wi = 0; wi < NPH_NUM_WIDTHS; ++wi) {
         const uint32_t W = nph_class_width(wi);
         for (int C = 1; C <= NPH_MAX_COLS; ++C) {
-            if (W < 32 && K > W * (uint32_t)C) continue;
+            const bool fits = K <= W * (uint32_t)C;
+            if (nph_class_chained(wi) ? fits : !fits) continue;       // single-strip classes take jobs that fit, the chained class the rest
             const uint32_t steps = nph_class_steps(K, E, C, W);
             const float cost = nph_class_cost(steps, C, W);
             if (cost < best) { best = cost; best_cls = nph_class_index(C, wi); best_steps = steps; }

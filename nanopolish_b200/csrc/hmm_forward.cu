@@ -97,10 +97,10 @@ int nph_launch_hmm_forward(nph_ctx* ctx, float* scores_dev)
         p.scratch_edge = reinterpret_cast<float*>(base + sizeof(float4) * (size_t)ctx->max_kpad * warps);
         int rc = NPH_ERR_STATE;
         switch (cl.group_width) {
-            case 4: rc = launch_width<4>(ctx, p, cl, (int)ci, st); break;
-            case 8: rc = launch_width<8>(ctx, p, cl, (int)ci, st); break;
-            case 16: rc = launch_width<16>(ctx, p, cl, (int)ci, st); break;
-            case 32: rc = launch_width<32>(ctx, p, cl, (int)ci, st); break;
+            case 4: rc = launch_width<4, false>(ctx, p, cl, (int)ci, st); break;
+            case 8: rc = launch_width<8, false>(ctx, p, cl, (int)ci, st); break;
+            case 16: rc = launch_width<16, false>(ctx, p, cl, (int)ci, st); break;
+            case 32: rc = cl.chained ? launch_width<32, true>(ctx, p, cl, (int)ci, st) : launch_width<32, false>(ctx, p, cl, (int)ci, st); break;
         }
         if (rc != NPH_OK) return rc;
         ++launches;

@@ -54,10 +54,12 @@ struct FwdParams {
     HmmConsts c;
 };
 
-template <int C, int W>
+// CHAIN = false: every job of the class fits one strip (K <= W*C), all strip/edge bookkeeping compiles away.
+template <int C, int W, bool CHAIN>
 __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdParams p)
 {
     static_assert(W == 4 || W == 8 || W == 16 || W == 32, "group width");
+    static_assert(!CHAIN || W == 32, "only full-warp groups chain strips");
     constexpr int G = 32 / W;                 // jobs per warp
     constexpr int STRIP = W * C;              // columns per strip
     extern __shared__ float s_tbl[];
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
         const int stride = job.stride;
         const bool pre_clip = (job.flags & NPH_HAF_ALLOW_PRE_CLIP) != 0;
         const bool post_clip = (job.flags & NPH_HAF_ALLOW_POST_CLIP) != 0;
-        const int n_strips = (W == 32) ? (K + STRIP - 1) / STRIP : 1;
+        const int n_strips = CHAIN ? (K + STRIP - 1) / STRIP : 1;
         const int kpad = n_strips * STRIP;
         const int P = n_strips > 1 ? max(E, kMinPeriod) : E;
 
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
             float Lm = __shfl_up_sync(kFull, Mp[C - 1], 1, W);
             float Lb = __shfl_up_sync(kFull, Bp[C - 1], 1, W);
             float Lk = __shfl_up_sync(kFull, Kp[C - 1], 1, W);
-            if (gl == 0) { Lm = em_next; Lb = eb_next; Lk = ek_next; }
+            if (gl == 0) { Lm = CHAIN ? em_next : NEG; Lb = CHAIN ? eb_next : NEG; Lk = CHAIN ? ek_next : NEG; }
 
             const bool in_strip = (r >= 1) && (s < n_strips);
             const int col0 = s * STRIP + gl * C;
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
                 if (rn > P) { rn = 1; sn = s + 1; }
                 if (rn >= 1 && rn <= E && sn < n_strips) {
                     x_next = lv[e_first + (long long)(rn - 1) * stride];
-                    if (W == 32 && gl == 0 && sn > 0) { em_next = edge_m[rn]; eb_next = edge_b[rn]; ek_next = edge_k[rn]; }
+                    if (CHAIN && gl == 0 && sn > 0) { em_next = edge_m[rn]; eb_next = edge_b[rn]; ek_next = edge_k[rn]; }
                 }
             }
 
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
                     lp_end = lsum(lp_end, __fadd_rn(Be, post), tb);
                     lp_end = lsum(lp_end, __fadd_rn(Ke, post), tb);
                 }
-                if (W == 32 && gl == W - 1 && s < last_strip) {
+                if (CHAIN && gl == W - 1 && s < last_strip) {
                     edge_m[r] = Mp[C - 1]; edge_b[r] = Bp[C - 1]; edge_k[r] = Kp[C - 1];
                 }
             }
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
             // advance
             r += 1;
             if (r > P) { r = 1; s += 1; }
-            if (W == 32 && n_strips > 1) __syncwarp();   // orders lane 31's edge stores before lane 0's later loads
+            if (CHAIN && n_strips > 1) __syncwarp();   // orders lane 31's edge stores before lane 0's later loads
         }
 
         const float result = __shfl_sync(kFull, lp_end, (lane & ~(W - 1)) + end_lane);
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
     }
 }
 
-template <int C, int W>
+template <int C, int W, bool CHAIN>
 int launch_class(nph_ctx* ctx, const FwdParams& base, const nph_ctx::ClassLaunch& cl, int class_idx, cudaStream_t stream)
 {
     FwdParams p = base;
@@ -248,33 +250,33 @@ int launch_class(nph_ctx* ctx, const FwdParams& base, const nph_ctx::ClassLaunch
     p.n_jobs = (uint32_t)cl.count;
     p.counter = ctx->d_counters.p + class_idx;
     const size_t smem = sizeof(float) * NPH_TBL_SMEM;
-    NPH_CUDA(ctx, cudaFuncSetAttribute(hmm_forward_kernel<C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NPH_CUDA(ctx, cudaFuncSetAttribute(hmm_forward_kernel<C, W, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = ctx->sm_count;
     const size_t warps_needed = (cl.count + (32 / W) - 1) / (32 / W);
     if ((size_t)grid * kWarpsPerCta > warps_needed) grid = (int)((warps_needed + kWarpsPerCta - 1) / kWarpsPerCta);
     if (grid < 1) grid = 1;
-    hmm_forward_kernel<C, W><<<grid, kCtaThreads, smem, stream>>>(p);
+    hmm_forward_kernel<C, W, CHAIN><<<grid, kCtaThreads, smem, stream>>>(p);
     NPH_CUDA(ctx, cudaGetLastError());
     return NPH_OK;
 }
 
 // one translation unit per group width (parallel compilation); defined in hmm_forward_w*.cu
-template <int W> int launch_width(nph_ctx* ctx, const FwdParams& base, const nph_ctx::ClassLaunch& cl, int class_idx, cudaStream_t stream);
+template <int W, bool CHAIN> int launch_width(nph_ctx* ctx, const FwdParams& base, const nph_ctx::ClassLaunch& cl, int class_idx, cudaStream_t stream);
 
-#define NPH_DEFINE_LAUNCH_WIDTH(W)                                                                              \
-    template <> int launch_width<W>(nph_ctx * ctx, const FwdParams& base, const nph_ctx::ClassLaunch& cl, int class_idx, cudaStream_t stream) \
+#define NPH_DEFINE_LAUNCH_WIDTH(W, CHAIN)                                                                              \
+    template <> int launch_width<W, CHAIN>(nph_ctx * ctx, const FwdParams& base, const nph_ctx::ClassLaunch& cl, int class_idx, cudaStream_t stream) \
     {                                                                                                           \
         switch (cl.cols_per_lane) {                                                                             \
-            case 1: return launch_class<1, W>(ctx, base, cl, class_idx, stream);                                       \
-            case 2: return launch_class<2, W>(ctx, base, cl, class_idx, stream);                                       \
-            case 3: return launch_class<3, W>(ctx, base, cl, class_idx, stream);                                       \
-            case 4: return launch_class<4, W>(ctx, base, cl, class_idx, stream);                                       \
-            case 5: return launch_class<5, W>(ctx, base, cl, class_idx, stream);                                       \
-            case 6: return launch_class<6, W>(ctx, base, cl, class_idx, stream);                                       \
-            case 7: return launch_class<7, W>(ctx, base, cl, class_idx, stream);                                       \
-            case 8: return launch_class<8, W>(ctx, base, cl, class_idx, stream);                                       \
-            case 9: return launch_class<9, W>(ctx, base, cl, class_idx, stream);                                       \
-            case 10: return launch_class<10, W>(ctx, base, cl, class_idx, stream);                                     \
+            case 1: return launch_class<1, W, CHAIN>(ctx, base, cl, class_idx, stream);                                       \
+            case 2: return launch_class<2, W, CHAIN>(ctx, base, cl, class_idx, stream);                                       \
+            case 3: return launch_class<3, W, CHAIN>(ctx, base, cl, class_idx, stream);                                       \
+            case 4: return launch_class<4, W, CHAIN>(ctx, base, cl, class_idx, stream);                                       \
+            case 5: return launch_class<5, W, CHAIN>(ctx, base, cl, class_idx, stream);                                       \
+            case 6: return launch_class<6, W, CHAIN>(ctx, base, cl, class_idx, stream);                                       \
+            case 7: return launch_class<7, W, CHAIN>(ctx, base, cl, class_idx, stream);                                       \
+            case 8: return launch_class<8, W, CHAIN>(ctx, base, cl, class_idx, stream);                                       \
+            case 9: return launch_class<9, W, CHAIN>(ctx, base, cl, class_idx, stream);                                       \
+            case 10: return launch_class<10, W, CHAIN>(ctx, base, cl, class_idx, stream);                                     \
         }                                                                                                       \
         return NPH_ERR_STATE;                                                                                   \
     }

@@ -1,5 +1,5 @@
-// hmm_forward_w32.cu — forward-kernel instances for groups of 32 lanes per job (C = 1..10 columns per lane).
+// hmm_forward_w32.cu — forward-kernel instances for full-warp jobs that fit one strip (K <= 32*C).
 #include "hmm_forward_kernel.cuh"
 namespace nph_fwd {
-NPH_DEFINE_LAUNCH_WIDTH(32)
+NPH_DEFINE_LAUNCH_WIDTH(32, false)
 }

@@ -141,7 +141,7 @@ int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uin
     ctx->classes.clear();
     size_t first = 0;
     for (int c = 0; c < NPH_NUM_CLASSES; ++c) {
-        ctx->classes.push_back(nph_ctx::ClassLaunch{c % NPH_MAX_COLS + 1, (int)nph_class_width(c / NPH_MAX_COLS), first,
+        ctx->classes.push_back(nph_ctx::ClassLaunch{c % NPH_MAX_COLS + 1, (int)nph_class_width(c / NPH_MAX_COLS), nph_class_chained(c / NPH_MAX_COLS), first,
                                                     (size_t)h.class_count[c], (double)h.class_cost[c]});
         first += (size_t)h.class_count[c];
     }

@@ -84,7 +84,7 @@ struct nph_ctx {
     DevBuf<uint16_t> d_sched_bkt;    // per job: schedule key bucket
     DevBuf<unsigned int> d_sched_hist;   // histogram + offsets + summary
     DevBuf<uint8_t> d_scratch;
-    struct ClassLaunch { int cols_per_lane; int group_width; size_t first; size_t count; double cost; };
+    struct ClassLaunch { int cols_per_lane; int group_width; bool chained; size_t first; size_t count; double cost; };
     std::vector<ClassLaunch> classes;
     uint32_t max_kpad = 0, max_period = 0;
     bool jobs_loaded = false;
