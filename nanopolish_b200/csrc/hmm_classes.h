@@ -16,7 +16,9 @@
 #define NPH_NUM_WIDTHS 5              // 4, 8, 16, 32 lanes single-strip; 32 lanes with chained strips
 #define NPH_MAX_COLS 10
 #define NPH_NUM_CLASSES (NPH_NUM_WIDTHS * NPH_MAX_COLS)
-#define NPH_KEY_BUCKETS 4096          // schedule key: exact step count below 2048, then 16-step bins
+#define NPH_STEP_BUCKETS 1024         // step key: exact below 768, then 32-step bins
+#define NPH_CHUNK_BUCKETS 8           // level chunk of the job's read (one-shot call), major key
+#define NPH_KEY_BUCKETS (NPH_STEP_BUCKETS * NPH_CHUNK_BUCKETS)
 
 NPH_HD uint32_t nph_class_width(int wi) { return wi >= 3 ? 32u : (4u << wi); }   // 4, 8, 16, 32, 32 (chained)
 NPH_HD bool nph_class_chained(int wi) { return wi == 4; }
@@ -54,9 +56,12 @@ NPH_HD int nph_choose_class(uint32_t K, uint32_t E, uint32_t* steps_out)
     return best_cls;
 }
 
-NPH_HD uint32_t nph_key_bucket(uint32_t steps)
+// position inside a class's slice of the schedule: level chunk ascending (so that jobs whose reads land first
+// run first while the rest is still crossing PCIe), then steps descending (longest first, lockstep neighbours alike)
+NPH_HD uint32_t nph_key_bucket(uint32_t steps, uint32_t chunk)
 {
-    if (steps < 2048u) return steps;
-    const uint32_t b = 2048u + (steps - 2048u) / 16u;
-    return b < (uint32_t)NPH_KEY_BUCKETS ? b : (uint32_t)NPH_KEY_BUCKETS - 1u;
+    uint32_t b = steps < 768u ? steps : 768u + (steps - 768u) / 32u;
+    if (b >= (uint32_t)NPH_STEP_BUCKETS) b = (uint32_t)NPH_STEP_BUCKETS - 1u;
+    if (chunk >= (uint32_t)NPH_CHUNK_BUCKETS) chunk = (uint32_t)NPH_CHUNK_BUCKETS - 1u;
+    return chunk * (uint32_t)NPH_STEP_BUCKETS + ((uint32_t)NPH_STEP_BUCKETS - 1u - b);
 }

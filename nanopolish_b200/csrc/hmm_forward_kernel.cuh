@@ -51,6 +51,8 @@ struct FwdParams {
     uint32_t kpad_stride;
     uint32_t edge_stride;
     uint32_t lsum_bias;           // NPH_LOGSUM_ADDR_BIAS, passed at run time on purpose (exact_math.cuh)
+    const uint32_t* progress;     // one-shot call: number of level chunks landed so far (nullptr: all resident)
+    uint32_t chunk_events;        // events per level chunk (multiple of 32)
     HmmConsts c;
 };
 
@@ -93,6 +95,17 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
         const float2 tr = p.trans[job.read];
         const float lp_mm_self = tr.x, lp_mm_next = tr.y;
         const DevModelView mv = p.models[job.model_id];
+        if (p.progress) {
+            // levels still streaming in behind us: wait until the chunk holding this read's last event has landed
+            // (chunks land in order; the progress word is written by a copy queued behind the chunk's data)
+            uint32_t need = has_job ? (uint32_t)((rd.event_off + rd.n_events - 1) / p.chunk_events) + 1u : 0u;
+            need = __reduce_max_sync(kFull, need);
+            if (lane == 0) {
+                const volatile uint32_t* pr = p.progress;
+                while (*pr < need) __nanosleep(500);
+            }
+            __syncwarp();
+        }
 
         const int K = (int)job.n_kmers;
         const int E = has_job ? (int)(job.event_stop > job.event_start ? job.event_stop - job.event_start

@@ -20,7 +20,7 @@ struct SchedSummary {
 
 __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n_jobs, const DevRead* __restrict__ reads,
                                 uint32_t n_reads, const DevModelView* __restrict__ models, const uint32_t* __restrict__ ranks,
-                                uint32_t n_models, uint64_t n_ranks, uint8_t* __restrict__ cls,
+                                uint32_t n_models, uint64_t n_ranks, uint32_t chunk_events, uint8_t* __restrict__ cls,
                                 uint16_t* __restrict__ bkt, unsigned int* __restrict__ hist, SchedSummary* __restrict__ sum)
 {
     __shared__ unsigned int s_count[NPH_NUM_CLASSES];
@@ -31,10 +31,13 @@ __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n
     __syncthreads();
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_jobs; j += gridDim.x * blockDim.x) {
         const nph_hmm_job jb = jobs[j];
+        uint32_t chunk = 0;
         bool ok = jb.read < n_reads && jb.model_id < n_models && jb.n_kmers != 0 && jb.rank_off + jb.n_kmers <= n_ranks;
         ok = ok && (jb.stride == 1 || jb.stride == -1);
         if (ok) {
-            const uint32_t ne = reads[jb.read].n_events;
+            const DevRead rd = reads[jb.read];
+            const uint32_t ne = rd.n_events;
+            if (chunk_events) chunk = (uint32_t)((rd.event_off + ne - 1) / chunk_events);
             ok = jb.event_start < ne && jb.event_stop < ne;
             ok = ok && !(jb.event_stop > jb.event_start && jb.stride != 1) && !(jb.event_stop < jb.event_start && jb.stride != -1);
         }
@@ -53,10 +56,10 @@ __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n
         const int c = nph_choose_class(K, E, &steps);
         const int C = c % NPH_MAX_COLS + 1;
         const uint32_t W = nph_class_width(c / NPH_MAX_COLS);
-        const uint32_t b = nph_key_bucket(steps);
+        const uint32_t b = nph_key_bucket(steps, chunk);
         cls[j] = (uint8_t)c;
         bkt[j] = (uint16_t)b;
-        atomicAdd(&hist[(size_t)c * NPH_KEY_BUCKETS + (NPH_KEY_BUCKETS - 1 - b)], 1u);   // descending by steps
+        atomicAdd(&hist[(size_t)c * NPH_KEY_BUCKETS + b], 1u);
         atomicAdd(&s_count[c], 1u);
         atomicAdd(&s_cost[c], nph_class_cost(steps, C, W));
         const uint32_t strip = W * C;
@@ -99,7 +102,7 @@ __global__ void scatter_kernel(uint32_t n_jobs, const uint8_t* __restrict__ cls,
                                unsigned int* __restrict__ offs, uint32_t* __restrict__ order)
 {
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_jobs; j += gridDim.x * blockDim.x) {
-        const unsigned int pos = atomicAdd(&offs[(size_t)cls[j] * NPH_KEY_BUCKETS + (NPH_KEY_BUCKETS - 1 - bkt[j])], 1u);
+        const unsigned int pos = atomicAdd(&offs[(size_t)cls[j] * NPH_KEY_BUCKETS + bkt[j]], 1u);
         order[pos] = j;
     }
 }
@@ -124,7 +127,8 @@ int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uin
     int blocks = (int)std::min<size_t>((n_jobs + threads - 1) / threads, (size_t)ctx->sm_count * 8);
     if (blocks < 1) blocks = 1;
     classify_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->d_jobs.p, (uint32_t)n_jobs, ctx->d_reads.p, (uint32_t)ctx->n_reads,
-                                                        ctx->d_models.p, ctx->d_ranks.p, (uint32_t)ctx->models.size(), (uint64_t)n_ranks_total, ctx->d_sched_cls.p,
+                                                        ctx->d_models.p, ctx->d_ranks.p, (uint32_t)ctx->models.size(), (uint64_t)n_ranks_total,
+                                                        (uint32_t)(ctx->levels_inflight ? ctx->level_chunk_events : 0), ctx->d_sched_cls.p,
                                                         ctx->d_sched_bkt.p, hist, d_sum);
     NPH_CUDA(ctx, cudaGetLastError());
     scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, offs);

@@ -123,6 +123,11 @@ int create_common(nph_ctx** out, int device, bool own_stream, cudaStream_t strea
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_reset, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking);
+    cudaMalloc((void**)&ctx->d_progress, sizeof(uint32_t));
+    cudaMallocHost((void**)&ctx->h_progress_vals, sizeof(uint32_t) * (nph_ctx::kLevelChunks + 1));
+    for (int i = 0; i <= nph_ctx::kLevelChunks; ++i) ctx->h_progress_vals[i] = (uint32_t)(i + 1);
     for (int i = 0; i < nph_ctx::kSideStreams; ++i) {
         cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
@@ -184,6 +189,10 @@ int nph_destroy(nph_ctx* ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_reset) cudaEventDestroy(ctx->ev_reset);
+    if (ctx->cstream) { cudaStreamSynchronize(ctx->cstream); cudaStreamDestroy(ctx->cstream); }
+    if (ctx->d_progress) cudaFree(ctx->d_progress);
+    if (ctx->h_progress_vals) cudaFreeHost(ctx->h_progress_vals);
     for (int i = 0; i < nph_ctx::kSideStreams; ++i) { if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -229,13 +238,18 @@ int nph_model_upload(nph_ctx* ctx, const double* level_mean, const double* level
     return NPH_OK;
 }
 
-int nph_reads_load(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
-                   const float* ev_mean, const double* ev_start_time, size_t n_events_total)
+// Shared by the staged call (pipelined = false: everything on the context's stream, synchronous) and by the
+// one-shot call (pipelined = true: read records on the main stream, event levels in chunks on the copy stream,
+// each chunk followed by a progress word the forward kernel polls — so scoring starts while levels still arrive).
+static int reads_load_impl(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
+                           const float* ev_mean, const double* ev_start_time, size_t n_events_total, bool pipelined)
 {
     if (!ctx || !reads || !ev_mean || n_reads == 0) return NPH_ERR_INVALID;
     NPH_CUDA(ctx, cudaSetDevice(ctx->device));
-    std::vector<DevRead> hr(n_reads);
-    std::vector<double> hd(n_reads);
+    std::vector<DevRead>& hr = ctx->h_stage_reads;
+    std::vector<double>& hd = ctx->h_stage_drift;
+    hr.resize(n_reads);
+    hd.resize(n_reads);
     ctx->h_events_per_base.resize(n_reads);
     ctx->h_read_n_events.resize(n_reads);
     bool any_drift = false;
@@ -252,13 +266,26 @@ int nph_reads_load(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
     if (any_drift && !ev_start_time) return NPH_ERR_INVALID;
     NPH_TRY(nph_reserve(ctx, ctx->d_reads, n_reads));
     NPH_TRY(nph_reserve(ctx, ctx->d_drift, n_reads));
-    NPH_TRY(nph_reserve(ctx, ctx->d_ev_mean, n_events_total));
     NPH_TRY(nph_reserve(ctx, ctx->d_level, n_events_total));
-    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_reads.p, hr.data(), sizeof(DevRead) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
-    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_drift.p, hd.data(), sizeof(double) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
-    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ev_mean.p, ev_mean, sizeof(float) * n_events_total, cudaMemcpyHostToDevice, ctx->stream));
     ctx->n_reads = n_reads;
     ctx->n_events_total = n_events_total;
+    ctx->level_chunk_events = 0;
+    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_reads.p, hr.data(), sizeof(DevRead) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
+    if (pipelined && !any_drift && n_events_total >= (size_t)1 << 20) {
+        // drift == 0 everywhere: the drift-scaled level IS the event mean (level - time*0.0 narrows back exactly),
+        // so levels go straight from the caller's buffer into d_level, chunk by chunk, behind progress words.
+        size_t chunk = (n_events_total + nph_ctx::kLevelChunks - 1) / nph_ctx::kLevelChunks;
+        chunk = (chunk + 31) / 32 * 32;                       // 128-byte lines never straddle two chunks
+        ctx->level_chunk_events = chunk;
+        NPH_CUDA(ctx, cudaMemsetAsync(ctx->d_progress, 0, sizeof(uint32_t), ctx->cstream));
+        NPH_CUDA(ctx, cudaEventRecord(ctx->ev_reset, ctx->cstream));
+        NPH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_reset, 0));
+        ctx->levels_inflight = true;
+        return NPH_OK;                                         // chunks are queued by upload_level_chunks()
+    }
+    NPH_TRY(nph_reserve(ctx, ctx->d_ev_mean, n_events_total));
+    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_drift.p, hd.data(), sizeof(double) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ev_mean.p, ev_mean, sizeof(float) * n_events_total, cudaMemcpyHostToDevice, ctx->stream));
     if (any_drift) {
         NPH_TRY(nph_reserve(ctx, ctx->d_ev_time, n_events_total));
         NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ev_time.p, ev_start_time, sizeof(double) * n_events_total, cudaMemcpyHostToDevice, ctx->stream));
@@ -268,25 +295,41 @@ int nph_reads_load(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
         // drift-scaled level IS the event mean and the start times need not cross PCIe at all.
         NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_level.p, ctx->d_ev_mean.p, sizeof(float) * n_events_total, cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    // the host staging vectors above must outlive the async copies
     NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NPH_OK;
+}
+
+static int upload_level_chunks(nph_ctx* ctx, const float* ev_mean)
+{
+    const size_t chunk = ctx->level_chunk_events, total = ctx->n_events_total;
+    uint32_t c = 0;
+    for (size_t off = 0; off < total; off += chunk, ++c) {
+        const size_t n = std::min(chunk, total - off);
+        NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_level.p + off, ev_mean + off, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->cstream));
+        NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_progress, ctx->h_progress_vals + c, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->cstream));
+    }
+    return NPH_OK;
+}
+
+int nph_reads_load(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
+                   const float* ev_mean, const double* ev_start_time, size_t n_events_total)
+{
+    NPH_TRY(reads_load_impl(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total, false));
     ctx->reads_loaded = true;
     ctx->jobs_loaded = false;
     ctx->abea_loaded = false;
     return NPH_OK;
 }
 
-int nph_hmm_jobs_load(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_total,
-                      const nph_hmm_job* jobs, size_t n_jobs, double indel_bias)
+static int jobs_upload_async(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_total,
+                             const nph_hmm_job* jobs, size_t n_jobs, double indel_bias)
 {
-    if (!ctx) return NPH_ERR_INVALID;
-    if (n_jobs == 0) { ctx->n_jobs = 0; ctx->classes.clear(); ctx->jobs_loaded = true; return NPH_OK; }   // empty batch: nothing to score
     if (!kmer_ranks || !jobs) return NPH_ERR_INVALID;
-    if (!ctx->reads_loaded) return NPH_ERR_STATE;
     NPH_CUDA(ctx, cudaSetDevice(ctx->device));
 
     // per-read transition pair (2 logf with the host libm, see read_transitions)
-    std::vector<float2> trans(ctx->n_reads);
+    std::vector<float2>& trans = ctx->h_stage_trans;
+    trans.resize(ctx->n_reads);
     for (size_t i = 0; i < ctx->n_reads; ++i) trans[i] = read_transitions(ctx->h_events_per_base[i], indel_bias);
 
     NPH_TRY(nph_reserve(ctx, ctx->d_ranks, n_ranks_total));
@@ -297,6 +340,11 @@ int nph_hmm_jobs_load(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_t
     NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_jobs.p, jobs, sizeof(nph_hmm_job) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ranks.p, kmer_ranks, sizeof(uint32_t) * n_ranks_total, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_trans.p, trans.data(), sizeof(float2) * ctx->n_reads, cudaMemcpyHostToDevice, ctx->stream));
+    return NPH_OK;
+}
+
+static int jobs_schedule(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total)
+{
     // validate + classify + schedule on the device (hmm_schedule.cu); synchronises the stream once
     uint32_t max_E = 1;
     NPH_TRY(nph_schedule_hmm_jobs(ctx, n_jobs, n_ranks_total, &max_E));
@@ -306,6 +354,16 @@ int nph_hmm_jobs_load(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_t
     ctx->n_ranks = n_ranks_total;
     ctx->jobs_loaded = true;
     return NPH_OK;
+}
+
+int nph_hmm_jobs_load(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_total,
+                      const nph_hmm_job* jobs, size_t n_jobs, double indel_bias)
+{
+    if (!ctx) return NPH_ERR_INVALID;
+    if (n_jobs == 0) { ctx->n_jobs = 0; ctx->classes.clear(); ctx->jobs_loaded = true; return NPH_OK; }   // empty batch: nothing to score
+    if (!ctx->reads_loaded) return NPH_ERR_STATE;
+    NPH_TRY(jobs_upload_async(ctx, kmer_ranks, n_ranks_total, jobs, n_jobs, indel_bias));
+    return jobs_schedule(ctx, n_jobs, n_ranks_total);
 }
 
 int nph_hmm_score(nph_ctx* ctx, float* scores_dev)
@@ -340,14 +398,26 @@ int nph_hmm_score_batch(nph_ctx* ctx,
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
     if (n_jobs == 0) return ctx ? NPH_OK : NPH_ERR_INVALID;      // empty batch
-    NPH_TRY(nph_reads_load(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total));
+    // Order of issue matters: small read records + jobs + ranks first (the scheduler needs only those), then the
+    // event levels in chunks on the copy stream; the forward kernels start as soon as the schedule exists and wait
+    // per job on the progress word of the chunk that holds their read (hmm_forward_kernel.cuh).
+    ctx->levels_inflight = false;
+    int rc = reads_load_impl(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total, true);
+    if (rc == NPH_OK) { ctx->reads_loaded = true; ctx->jobs_loaded = false; ctx->abea_loaded = false; }
     const double t1 = now();
-    NPH_TRY(nph_hmm_jobs_load(ctx, kmer_ranks, n_ranks_total, jobs, n_jobs, indel_bias));
+    if (rc == NPH_OK) rc = jobs_upload_async(ctx, kmer_ranks, n_ranks_total, jobs, n_jobs, indel_bias);
+    if (rc == NPH_OK && ctx->levels_inflight) rc = upload_level_chunks(ctx, ev_mean);
+    if (rc == NPH_OK) rc = jobs_schedule(ctx, n_jobs, n_ranks_total);
     const double t2 = now();
-    NPH_TRY(nph_hmm_score(ctx, nullptr));
-    const int rc = nph_hmm_scores_fetch(ctx, scores_out, n_jobs);
+    if (rc == NPH_OK) rc = nph_hmm_score(ctx, nullptr);
+    if (rc == NPH_OK) rc = nph_hmm_scores_fetch(ctx, scores_out, n_jobs);
+    if (ctx->levels_inflight) {                                  // also on error paths: never leave copies in flight
+        cudaStreamSynchronize(ctx->cstream);
+        ctx->levels_inflight = false;
+        ctx->level_chunk_events = 0;
+    }
     const double t3 = now();
-    if (timing) fprintf(stderr, "[nph] reads_load %.2f ms  jobs_load %.2f ms  score+fetch %.2f ms\n", t1 - t0, t2 - t1, t3 - t2);
+    if (timing) fprintf(stderr, "[nph] reads %.2f ms  jobs+schedule %.2f ms  score+fetch %.2f ms\n", t1 - t0, t2 - t1, t3 - t2);
     return rc;
 }
 

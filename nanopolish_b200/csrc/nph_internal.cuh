@@ -112,6 +112,18 @@ struct nph_ctx {
     int last_launches = 0;
     bool timing_valid = false;
 
+    // pipelined level upload of the one-shot call: copy stream, progress word polled by the forward kernel
+    static const int kLevelChunks = 8;
+    cudaStream_t cstream = nullptr;
+    cudaEvent_t ev_reset = nullptr;
+    uint32_t* d_progress = nullptr;          // number of level chunks that have landed
+    uint32_t* h_progress_vals = nullptr;     // pinned {1, 2, ...}: sources of the progress writes
+    size_t level_chunk_events = 0;           // 0 = levels fully resident, kernels do not poll
+    bool levels_inflight = false;
+    std::vector<DevRead> h_stage_reads;      // host staging that must outlive async copies
+    std::vector<double> h_stage_drift;
+    std::vector<float2> h_stage_trans;
+
     // staging (pinned) buffers
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
