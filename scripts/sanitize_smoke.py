@@ -1,0 +1,34 @@
+"""Small instances of every kernel for compute-sanitizer (memcheck / racecheck / synccheck / initcheck).
+Usage (GPU box): compute-sanitizer --tool memcheck python scripts/sanitize_smoke.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from nanopolish_b200 import synth
+from nanopolish_b200.engine import Engine
+
+nuc, cpg = synth.load_model("nucleotide"), synth.load_model("cpg")
+eng = Engine(0)
+mid, cid = eng.model_upload(nuc), eng.model_upload(cpg)
+rs = synth.gen_reads(6, 1500, nuc, seed=1, drift=True, cpg_keep=0.3)
+# forward: scorereads segments (W=32 single strip), wide jobs (chained strips), methylation windows (W<32)
+j1 = synth.scorereads_jobs(rs, 250, model_id=mid, rc_every=2)
+a = eng.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, j1.kmer_ranks, j1.jobs)
+j2 = synth.scorereads_jobs(rs, 700, model_id=mid)
+b = eng.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, j2.kmer_ranks, j2.jobs)
+j3 = synth.methylation_jobs(rs, model_id=cid)
+c = eng.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, j3.kmer_ranks, j3.jobs)
+# one-shot pipelined path needs >= 2^20 events and drift 0
+rs2 = synth.gen_reads(300, 3600, nuc, seed=2)
+j4 = synth.scorereads_jobs(rs2, 500, model_id=mid)
+d = eng.hmm_score_batch(rs2.reads, rs2.ev_mean, rs2.ev_start_time, j4.kmer_ranks, j4.jobs)
+# viterbi
+v, _ = eng.hmm_align_batch(rs.reads, rs.ev_mean, rs.ev_start_time, j1.kmer_ranks, j1.jobs)
+# abea + mom
+rs3 = synth.gen_reads(5, 1200, nuc, seed=3, rng_scalings=False)
+aj, ar, total = synth.abea_jobs(rs3)
+pairs, res = eng.abea_batch(rs3.reads, rs3.ev_mean, rs3.ev_start_time, ar, aj, mid, total)
+mom = eng.mom_batch(rs3.reads, rs3.ev_mean, ar, aj, mid)
+assert np.isfinite(a).all() and np.isfinite(b).all() and np.isfinite(c).all() and np.isfinite(d).all()
+assert all(x.shape[0] > 0 for x in v) and (res["n_pairs"] > 0).all()
+print("sanitize smoke ok", a.shape, b.shape, c.shape, d.shape, len(v), res["n_pairs"])
+eng.close()
