@@ -1,6 +1,8 @@
 // nph_host_capi.cpp — a thin extern "C" shim over the C++ host mirror so that the Python tests can
 // drive HMMInputData / HMMInputSequence / SquiggleRead / Alphabet exactly as a C++ caller would.
 #include "nph_host.hpp"
+#include "nph_variants.hpp"
+#include "nph_methylation.hpp"
 #include <cstring>
 #include <memory>
 
@@ -181,6 +183,78 @@ int nphh_mom(int read, int model, const char* seq, double* out4)
         SquiggleScalings s = estimate_scalings_using_mom(std::string(seq), *g_models[model], m);
         out4[0] = s.shift; out4[1] = s.scale; out4[2] = s.drift; out4[3] = s.var;
     });
+}
+
+// ---- N2: variant scoring -------------------------------------------------------------------
+// Haplotype::apply_variants on a reference string; returns the derived sequence (or -1 if a variant was refused)
+int nphh_haplotype_apply(const char* ref, size_t ref_position, int n_var, const size_t* pos, const char** ref_seq, const char** alt_seq,
+                         char* out)
+{
+    Haplotype h("ctg", ref_position, ref);
+    bool good = true;
+    for (int i = 0; i < n_var; ++i) { Variant v; v.ref_name = "ctg"; v.ref_position = pos[i]; v.ref_seq = ref_seq[i]; v.alt_seq = alt_seq[i]; good = h.apply_variant(v) && good; }
+    std::memcpy(out, h.get_sequence().c_str(), h.get_sequence().size() + 1);
+    return good ? (int)h.get_sequence().size() : -1;
+}
+
+// score_variants_thresholded over reads (handles + per-read event window) and a candidate list
+int nphh_score_variants_thresholded(int n_reads, const int32_t* read, const uint32_t* e_start, const uint32_t* e_stop, const uint8_t* rc,
+                                    int model, const char* base_seq, size_t ref_position, int n_var, const size_t* pos,
+                                    const char** ref_seq, const char** alt_seq, uint32_t flags, uint32_t threshold,
+                                    int n_meth, const char** meth_types, double indel_bias, double* quality_out)
+{
+    return guard([&] {
+        std::vector<HMMInputData> input(n_reads);
+        for (int j = 0; j < n_reads; ++j) {
+            input[j].read = g_reads[read[j]].get();
+            input[j].pore_model = g_models[model].get();
+            input[j].event_start_idx = e_start[j];
+            input[j].event_stop_idx = e_stop[j];
+            input[j].strand = 0;
+            input[j].rc = rc[j];
+            input[j].event_stride = rc[j] ? -1 : 1;
+        }
+        std::vector<Variant> vars(n_var);
+        for (int i = 0; i < n_var; ++i) { vars[i].ref_name = "ctg"; vars[i].ref_position = pos[i]; vars[i].ref_seq = ref_seq[i]; vars[i].alt_seq = alt_seq[i]; }
+        std::vector<std::string> mt;
+        for (int i = 0; i < n_meth; ++i) mt.push_back(meth_types[i]);
+        Haplotype base("ctg", ref_position, base_seq);
+        std::vector<Variant> out = score_variants_thresholded(vars, base, input, flags, threshold, mt, Engine::thread_default(), indel_bias);
+        for (int i = 0; i < n_var; ++i) quality_out[i] = out[i].quality;
+    });
+}
+
+// ---- N3: call-methylation for a batch of reads; returns the concatenated TSV ------------------------------
+// aligned pairs are (ref_pos, event_idx) interleaved, pair_off[n_reads+1]
+long long nphh_call_methylation(int n_reads, const int32_t* read, const char** read_names, const uint8_t* is_rev, const uint8_t* rc,
+                                const int32_t* ref_start, const char** ref_seqs, const int32_t* pairs, const uint64_t* pair_off,
+                                const char* contig, double indel_bias, char* tsv_out, size_t cap, uint64_t* n_jobs_out)
+{
+    long long n = -1;
+    int st = guard([&] {
+        MethylationCallingParameters params;
+        MethylationCaller caller(params);
+        for (int i = 0; i < n_reads; ++i) {
+            EventAlignedRead r;
+            r.read = g_reads[read[i]].get();
+            r.read_name = read_names[i];
+            r.is_reverse = is_rev[i];
+            r.contig = contig;
+            r.ref_start_pos = ref_start[i];
+            r.ref_seq = ref_seqs[i];
+            for (uint64_t p = pair_off[i]; p < pair_off[i + 1]; ++p) r.aligned_events[0].push_back(AlignedPair{pairs[2 * p], pairs[2 * p + 1]});
+            r.rc[0] = rc[i];
+            caller.add_read(r);
+        }
+        *n_jobs_out = caller.num_jobs();
+        caller.run(Engine::thread_default(), indel_bias);
+        std::string all;
+        for (int i = 0; i < n_reads; ++i) all += caller.tsv(i);
+        if (all.size() + 1 > cap) throw Error(NPH_ERR_INVALID, "tsv buffer too small");
+        std::memcpy(tsv_out, all.c_str(), all.size() + 1);
+        n = (long long)all.size();
+    });
+    return st ? st : n;
 }
 
 } // extern "C"

@@ -206,6 +206,34 @@ def gen_reads(n_reads: int, n_events: int, model: PoreModel, seed: int = 42, dri
     return ReadSet(reads, np.concatenate(means), np.concatenate(times), seqs, evk, kfe, k)
 
 
+def gen_reads_from_sequence(codes: np.ndarray, n_reads: int, model: PoreModel, seed: int = 42) -> ReadSet:
+    """n_reads reads that all traverse the same base sequence (a pile-up over one reference window), each with its own
+    event counts, noise and scalings — the input shape of variant scoring."""
+    k = model.k
+    nk = codes.shape[0] - k + 1
+    ranks = kmer_ranks_from_codes(codes, k, 4)
+    reads = np.zeros(n_reads, READ_DT)
+    means, times, seqs, evk, kfe = [], [], [], [], []
+    off = 0
+    p_nev = np.array([0.03, 0.35, 0.45, 0.17])
+    for r in range(n_reads):
+        rng = np.random.default_rng(seed + r)
+        nev = rng.choice(4, nk, p=p_nev)
+        nev[0] = max(nev[0], 1); nev[-1] = max(nev[-1], 1)
+        which = np.repeat(np.arange(nk, dtype=np.int32), nev)
+        E = which.shape[0]
+        shift, scale, var = rng.uniform(-5.0, 5.0), rng.uniform(0.9, 1.1), rng.uniform(0.9, 1.3)
+        t = (np.arange(E, dtype=np.float64) * 0.002) + rng.uniform(0.0, 100.0)
+        mu = scale * model.level_mean[ranks[which]] + shift
+        sd = var * model.level_stdv[ranks[which]]
+        m = (mu + sd * rng.standard_normal(E)).astype(np.float32)
+        reads[r] = (off, E, 0, scale, shift, 0.0, var, np.log(var), E / float(nk))
+        first = np.searchsorted(which, np.arange(nk), side="left").astype(np.int32)
+        means.append(m); times.append(t); seqs.append(codes.copy()); evk.append(which); kfe.append(first)
+        off += E
+    return ReadSet(reads, np.concatenate(means), np.concatenate(times), seqs, evk, kfe, k)
+
+
 @dataclass
 class HmmJobs:
     jobs: np.ndarray          # HMM_JOB_DT[n_jobs]
