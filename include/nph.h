@@ -223,6 +223,28 @@ int nph_hmm_align_batch(nph_ctx* ctx,
                         nph_align_state* states_out, const uint64_t* states_off,
                         uint32_t* n_states_out, float* scores_out);
 
+/* ---- event detection (section 8f N4: the step before ABEA) --------------------------------------
+ * scrappie's detect_events as load_from_raw calls it: t-statistics over two windows on prefix sums, a short/long
+ * peak detector, events between consecutive boundaries.
+ * ref: src/thirdparty/scrappie/event_detection.c:35-319, event_detection.h:15-29 (parameters),
+ *      src/nanopolish_squiggle_read.cpp:229-235 (call site). */
+typedef struct {
+    uint32_t window_length1, window_length2;   /* 3, 6 for DNA; 7, 14 for RNA */
+    float threshold1, threshold2, peak_height;  /* 1.4, 9.0, 0.2 for DNA; 2.5, 9.0, 1.0 for RNA */
+} nph_event_params;
+/* scrappie's event_t reduced to what it computes here (pos/state are always -1 there) */
+typedef struct { uint64_t start; float length; float mean; float stdv; uint32_t reserved; } nph_event;
+typedef struct {
+    uint64_t sample_off;      /* first raw sample of this read in raw[] (picoamps as float, like Fast5Data::rt.raw) */
+    uint64_t event_off;       /* where this read's events go in events_out[] */
+    uint32_t n_samples;
+    uint32_t event_cap;       /* room at event_off; n_samples always suffices, n_samples/2 does in practice */
+} nph_raw_read;
+/* events_out[reads[i].event_off ...] receives n_events_out[i] events in scrappie's order; n_events_out[i] == 0 with
+ * NPH_ERR_UNSUPPORTED returned if some event_cap was too small (nothing else can fail: every signal has >= 1 event). */
+int nph_detect_events_batch(nph_ctx* ctx, const float* raw, size_t n_samples_total, const nph_raw_read* reads, size_t n_reads,
+                            const nph_event_params* params, nph_event* events_out, size_t events_total, uint32_t* n_events_out);
+
 /* ---- measurement hooks (used by bench.py; not part of the reference surface) ------------- */
 /* Device time in ms of the most recent nph_hmm_score / nph_abea_run kernel sequence, measured
  * with CUDA events on the context's stream (valid after a sync), and the number of kernel

@@ -1,0 +1,552 @@
+// event_detect.cu — SURVEY.md section 8(f) row N4: scrappie's event detector, the step in front of MoM and ABEA.
+//
+// Replaces, for a batch of raw reads:
+//   detect_events            ref: src/thirdparty/scrappie/event_detection.c:268-319
+//   compute_sum_sumsq        ref: :35-49      compute_tstat   ref: :62-118
+//   short_long_peak_detector ref: :122-201    create_event(s) ref: :216-266
+// as called by SquiggleRead::load_from_raw (src/nanopolish_squiggle_read.cpp:229-235; the trimmed raw_table is
+// discarded there, so the whole signal is segmented).
+//
+// The reference makes five passes over each read and mallocs five arrays (two FP64 prefix sums, two t-statistic
+// vectors, a peak list).  The prefix sums are strictly sequential FP64 accumulations, so the result is only
+// reproducible by walking each read in order; parallelism is across reads.  One thread streams one read in a single
+// pass: the running sums live in registers, a (2*w2+1)-deep ring of the last prefix values per thread lives in shared
+// memory (the two t-statistics at position i only need sums at i-w..i+w), the short/long peak detector is a register
+// state machine, and each boundary emits its event from the sums captured when the peak was set.  HBM traffic is the
+// algorithmic minimum: 4 B per sample in, 24 B per event out.  Every float/double operation mirrors the C source's
+// promotions (float products, double quotient, double sqrt) so boundaries, means and stdvs are bit-identical.
+#include "nph_internal.cuh"
+#include <cfloat>
+#include <algorithm>
+#include <vector>
+#include <cstdlib>
+
+#define NPH_TRY(expr) do { int rc__ = (expr); if (rc__ != NPH_OK) return rc__; } while (0)
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kMaxW2 = 16;
+
+struct DetParams {
+    const float* raw;
+    const nph_raw_read* reads;
+    const uint32_t* order;
+    uint32_t n_reads;
+    nph_event* events;
+    uint32_t* n_events;
+    int* overflow;
+    uint32_t w1, w2;
+    float t1, t2, peak_height;
+    uint32_t ring;         // 2*w2 + 1
+};
+
+struct Detector {
+    float threshold;
+    unsigned long long window_length;
+    unsigned long long masked_to;
+    long long peak_pos;
+    float peak_value;
+    bool valid_peak;
+    double s_at_peak, q_at_peak;      // prefix sums at peak_pos, captured when the peak is set
+};
+
+// t-statistic at position i from prefix values (compute_tstat's loop body, same promotions)
+__device__ __forceinline__ float tstat_at(double s_lo, double q_lo, double s_mid, double q_mid, double s_hi, double q_hi, float wf)
+{
+    const double sum1 = __dsub_rn(s_mid, s_lo);
+    const double sumsq1 = __dsub_rn(q_mid, q_lo);
+    const float sum2 = (float)__dsub_rn(s_hi, s_mid);
+    const float sumsq2 = (float)__dsub_rn(q_hi, q_mid);
+    const float mean1 = (float)__ddiv_rn(sum1, (double)wf);
+    const float mean2 = __fdiv_rn(sum2, wf);
+    double cv = __dsub_rn(__ddiv_rn(sumsq1, (double)wf), (double)__fmul_rn(mean1, mean1));
+    cv = __dadd_rn(cv, (double)__fdiv_rn(sumsq2, wf));
+    cv = __dsub_rn(cv, (double)__fmul_rn(mean2, mean2));
+    float combined_var = fmaxf((float)cv, FLT_MIN);
+    const float delta_mean = __fsub_rn(mean2, mean1);
+    return (float)__ddiv_rn(fabs((double)delta_mean), __dsqrt_rn((double)__fdiv_rn(combined_var, wf)));
+}
+
+__device__ __forceinline__ void emit_event(nph_event* out, uint32_t& count, uint32_t cap, unsigned long long start, unsigned long long end,
+                                           double s0, double q0, double s1, double q1)
+{
+    if (count < cap) {
+        nph_event e;
+        e.start = start;
+        e.length = (float)(end - start);                             // size_t difference, as in create_event
+        e.mean = __fdiv_rn((float)__dsub_rn(s1, s0), e.length);
+        const float deltasqr = (float)__dsub_rn(q1, q0);
+        const float var = __fsub_rn(__fdiv_rn(deltasqr, e.length), __fmul_rn(e.mean, e.mean));
+        e.stdv = __fsqrt_rn(fmaxf(var, 0.0f));
+        e.reserved = 0;
+        out[count] = e;
+    }
+    ++count;
+}
+
+// Fallback for reads whose prefix sums are not provably exact (see ed_guard_kernel): one thread streams one read.
+__global__ void __launch_bounds__(kThreads) detect_events_stream_kernel(const DetParams p)
+{
+    extern __shared__ double s_ring[];                                // [2][ring][kThreads]: S then Q
+    const uint32_t slot_idx = blockIdx.x * kThreads + threadIdx.x;
+    if (slot_idx >= p.n_reads) return;
+    const uint32_t ridx = p.order[slot_idx];
+    const nph_raw_read rd = p.reads[ridx];
+    const float* __restrict__ raw = p.raw + rd.sample_off;
+    const unsigned long long n = rd.n_samples;
+    nph_event* out = p.events + rd.event_off;
+    const uint32_t R = p.ring;
+    double* ringS = s_ring + threadIdx.x;
+    double* ringQ = s_ring + (size_t)R * kThreads + threadIdx.x;
+#define RS(slot) ringS[(size_t)(slot) * kThreads]
+#define RQ(slot) ringQ[(size_t)(slot) * kThreads]
+
+    const uint32_t w1 = p.w1, w2 = p.w2;
+    const float wf1 = (float)w1, wf2 = (float)w2;
+    const bool on1 = !(n < 2ull * w1 || w1 < 2), on2 = !(n < 2ull * w2 || w2 < 2);
+    Detector d0{p.t1, w1, 0ull, -1, FLT_MAX, false, 0.0, 0.0};
+    Detector d1{p.t2, w2, 0ull, -1, FLT_MAX, false, 0.0, 0.0};
+
+    double S = 0.0, Q = 0.0;
+    unsigned long long consumed = 0;          // prefix index available: S == prefix[consumed]
+    RS(0) = 0.0; RQ(0) = 0.0;                 // prefix[0]
+    uint32_t slot_w = 0;                      // ring slot of prefix[consumed]
+    // ring slots of prefix[i - w2], [i - w1], [i], [i + w1], [i + w2]; negative indices are never read
+    int sl_m2 = -(int)w2, sl_m1 = -(int)w1, sl_0 = 0, sl_p1 = (int)w1, sl_p2 = (int)w2;
+    sl_p1 %= (int)R; sl_p2 %= (int)R;
+
+    uint32_t count = 0;
+    unsigned long long prev_pos = 0;
+    double prev_s = 0.0, prev_q = 0.0;
+
+    for (unsigned long long i = 0; i < n; ++i) {
+        // make prefix[min(n, i + w2)] available
+        const unsigned long long need = (i + w2 < n) ? i + w2 : n;
+        while (consumed < need) {
+            const float x = raw[consumed];
+            S = __dadd_rn(S, (double)x);
+            Q = __dadd_rn(Q, (double)__fmul_rn(x, x));
+            ++consumed;
+            slot_w = (slot_w + 1 == R) ? 0 : slot_w + 1;
+            RS(slot_w) = S; RQ(slot_w) = Q;
+        }
+        const double s_mid = RS(sl_0), q_mid = RQ(sl_0);
+        float ts1 = 0.0f, ts2 = 0.0f;
+        if (on1 && i >= w1 && i <= n - w1) ts1 = tstat_at(RS(sl_m1), RQ(sl_m1), s_mid, q_mid, RS(sl_p1), RQ(sl_p1), wf1);
+        if (on2 && i >= w2 && i <= n - w2) ts2 = tstat_at(RS(sl_m2), RQ(sl_m2), s_mid, q_mid, RS(sl_p2), RQ(sl_p2), wf2);
+
+        // short_long_peak_detector, iteration i: short detector first, then long
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            Detector& d = k == 0 ? d0 : d1;
+            if (d.masked_to >= i) continue;
+            const float cur = k == 0 ? ts1 : ts2;
+            if (d.peak_pos == -1) {
+                if (cur < d.peak_value) {
+                    d.peak_value = cur;
+                } else if (__fsub_rn(cur, d.peak_value) > p.peak_height) {
+                    d.peak_value = cur; d.peak_pos = (long long)i; d.s_at_peak = s_mid; d.q_at_peak = q_mid;
+                }
+            } else {
+                if (cur > d.peak_value) { d.peak_value = cur; d.peak_pos = (long long)i; d.s_at_peak = s_mid; d.q_at_peak = q_mid; }
+                if (k == 0 && d.peak_value > d.threshold) {
+                    d1.masked_to = (unsigned long long)d.peak_pos + d.window_length;
+                    d1.peak_pos = -1; d1.peak_value = FLT_MAX; d1.valid_peak = false;
+                }
+                if (__fsub_rn(d.peak_value, cur) > p.peak_height && d.peak_value > d.threshold) d.valid_peak = true;
+                if (d.valid_peak && (i - (unsigned long long)d.peak_pos) > d.window_length / 2) {
+                    const unsigned long long pk = (unsigned long long)d.peak_pos;
+                    emit_event(out, count, rd.event_cap, prev_pos, pk, prev_s, prev_q, d.s_at_peak, d.q_at_peak);
+                    prev_pos = pk; prev_s = d.s_at_peak; prev_q = d.q_at_peak;
+                    d.peak_pos = -1; d.peak_value = cur; d.valid_peak = false;
+                }
+            }
+        }
+        // advance the five ring cursors
+        sl_m2 = (sl_m2 + 1 == (int)R) ? 0 : sl_m2 + 1;
+        sl_m1 = (sl_m1 + 1 == (int)R) ? 0 : sl_m1 + 1;
+        sl_0 = (sl_0 + 1 == (int)R) ? 0 : sl_0 + 1;
+        sl_p1 = (sl_p1 + 1 == (int)R) ? 0 : sl_p1 + 1;
+        sl_p2 = (sl_p2 + 1 == (int)R) ? 0 : sl_p2 + 1;
+    }
+    // last event: previous boundary to the end of the signal (a signal without peaks is one event)
+    emit_event(out, count, rd.event_cap, prev_pos, n, prev_s, prev_q, S, Q);
+    if (count > rd.event_cap) { *p.overflow = 1; p.n_events[ridx] = 0; }
+    else p.n_events[ridx] = count;
+#undef RS
+#undef RQ
+}
+
+
+// =============================================================================================================
+// Fast path.  The reference accumulates FP64 prefix sums of the samples (and of their float squares) sequentially,
+// which no parallel algorithm reproduces in general.  But when every partial sum is EXACTLY representable nothing
+// is ever rounded, so any summation order gives the same doubles, and every quantity the detector derives from
+// the prefix arrays (window sums of the t-statistics, segment sums of the events) equals the exact sum of the
+// samples involved.  ed_guard_kernel proves that per read: all samples are integer multiples of 2^L (L = smallest
+// ulp exponent present) and |partial sum| <= n * max|x| < 2^(ceil(log2 n) + Emax + 1); if that span fits 53 bits
+// (and likewise for the float squares) the read takes the parallel path, otherwise the streaming fallback.
+// Real traces (40-200 pA) pass with ~10 bits to spare.
+//   ed_tstat_kernel : thread per sample, both windows from a 2*w2-sample stencil (exact FP64 window sums)
+//   ed_peaks_kernel : the short/long peak detector, a register state machine; lane per read, the t-statistics of
+//                     32 reads x 32 positions staged through shared memory so global loads stay coalesced
+//   ed_events_kernel: thread per event, exact FP64 segment sums -> start / length / mean / stdv
+// =============================================================================================================
+struct FastParams {
+    const float* raw;
+    const nph_raw_read* reads;
+    const uint32_t* order;       // reads sorted by length (desc)
+    uint32_t n_reads;
+    float* ts1;                  // per sample
+    float* ts2;
+    uint32_t* peaks;             // per read at event_off, event_cap entries
+    uint32_t* n_peaks;           // per read
+    uint8_t* exact;              // per read: 1 = fast path
+    nph_event* events;
+    uint32_t* n_events;
+    int* overflow;
+    uint32_t w1, w2;
+    float t1, t2, peak_height;
+    uint32_t warm;
+};
+
+__device__ __forceinline__ int ulp_exp(float x)      // exponent of ulp(x) for finite nonzero x
+{
+    const int e = (int)((__float_as_uint(x) >> 23) & 0xff);
+    return (e == 0 ? -126 : e - 127) - 23;
+}
+
+__global__ void __launch_bounds__(256) ed_guard_kernel(const FastParams p)
+{
+    __shared__ int s_lx[8], s_ex[8], s_lp[8], s_ep[8], s_bad[8];
+    for (uint32_t r = blockIdx.x; r < p.n_reads; r += gridDim.x) {
+        const nph_raw_read rd = p.reads[r];
+        const float* x = p.raw + rd.sample_off;
+        int lx = 1000, ex = -1000, lp = 1000, ep = -1000, bad = 0;
+        for (uint32_t i = threadIdx.x; i < rd.n_samples; i += blockDim.x) {
+            const float v = x[i];
+            const float q = __fmul_rn(v, v);
+            if (!(fabsf(v) <= FLT_MAX) || !(q <= FLT_MAX)) { bad = 1; continue; }
+            if (v != 0.0f) { lx = min(lx, ulp_exp(v)); ex = max(ex, ulp_exp(v) + 23); }
+            if (q != 0.0f) { lp = min(lp, ulp_exp(q)); ep = max(ep, ulp_exp(q) + 23); }
+        }
+        for (int o = 16; o; o >>= 1) {
+            lx = min(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ex = max(ex, __shfl_xor_sync(0xffffffffu, ex, o));
+            lp = min(lp, __shfl_xor_sync(0xffffffffu, lp, o)); ep = max(ep, __shfl_xor_sync(0xffffffffu, ep, o));
+            bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        }
+        const int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) { s_lx[w] = lx; s_ex[w] = ex; s_lp[w] = lp; s_ep[w] = ep; s_bad[w] = bad; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < 8; ++k) { lx = min(lx, s_lx[k]); ex = max(ex, s_ex[k]); lp = min(lp, s_lp[k]); ep = max(ep, s_ep[k]); bad |= s_bad[k]; }
+            int lg = 0;
+            while ((1ull << lg) < (unsigned long long)rd.n_samples + 1) ++lg;      // ceil(log2(n + 1))
+            const bool okx = (ex < -500) || (lg + ex + 1 - lx <= 53);               // all zero, or span fits 53 bits
+            const bool okp = (ep < -500) || (lg + ep + 1 - lp <= 53);
+            p.exact[r] = (!bad && okx && okp) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+}
+
+// grid: (tiles, reads).  thread -> position i of read blockIdx.y
+__global__ void __launch_bounds__(256) ed_tstat_kernel(const FastParams p)
+{
+    const uint32_t r = blockIdx.y;
+    if (!p.exact[r]) return;
+    const nph_raw_read rd = p.reads[r];
+    const unsigned long long n = rd.n_samples;
+    const float* __restrict__ x = p.raw + rd.sample_off;
+    const uint32_t w1 = p.w1, w2 = p.w2;
+    const bool on1 = !(n < 2ull * w1 || w1 < 2), on2 = !(n < 2ull * w2 || w2 < 2);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        float a = 0.0f, b = 0.0f;
+        const bool v1 = on1 && i >= w1 && i <= n - w1, v2 = on2 && i >= w2 && i <= n - w2;
+        if (v1 || v2) {
+            // exact window sums: left = samples i-1, i-2, ...; right = samples i, i+1, ... (nested: w1 inside w2)
+            double sl = 0.0, ql = 0.0, sr = 0.0, qr = 0.0;
+            double sl1 = 0.0, ql1 = 0.0, sr1 = 0.0, qr1 = 0.0;
+            const uint32_t wmax = v2 ? w2 : w1;
+            for (uint32_t j = 0; j < wmax; ++j) {
+                const float xl = x[i - 1 - j], xr = x[i + j];
+                sl = __dadd_rn(sl, (double)xl); ql = __dadd_rn(ql, (double)__fmul_rn(xl, xl));
+                sr = __dadd_rn(sr, (double)xr); qr = __dadd_rn(qr, (double)__fmul_rn(xr, xr));
+                if (j + 1 == w1) { sl1 = sl; ql1 = ql; sr1 = sr; qr1 = qr; }
+            }
+            if (v1) a = tstat_at(0.0, 0.0, sl1, ql1, __dadd_rn(sl1, sr1), __dadd_rn(ql1, qr1), (float)w1);
+            if (v2) b = tstat_at(0.0, 0.0, sl, ql, __dadd_rn(sl, sr), __dadd_rn(ql, qr), (float)w2);
+        }
+        p.ts1[rd.sample_off + i] = a;
+        p.ts2[rd.sample_off + i] = b;
+    }
+}
+
+// ---- peak detector -------------------------------------------------------------------------------------------
+// short_long_peak_detector (event_detection.c:122-201) is a sequential state machine over the two t-statistic
+// vectors, ~36 000 dependent steps per read.  Its state is tiny and re-synchronises quickly (both detectors reset at
+// every boundary they emit, about every 9 samples), so a warp runs ONE read as 32 segments in parallel: lane k warms
+// up on the kWarm samples before its segment from a fresh state, snapshots the state at its segment start, runs the
+// segment counting boundaries; then every lane's snapshot is compared with its left neighbour's final state.  If all
+// 31 comparisons agree bit for bit, each lane provably started from the true sequential state (induction from lane 0,
+// which starts at sample 0), the counts are scanned and a second pass from the snapshots writes the boundaries in
+// order.  If any comparison fails the read is walked sequentially by one lane — exact either way.
+struct PeakState {
+    uint32_t m0, m1;         // masked_to
+    int pp0, pp1;            // peak_pos (-1 = none yet)
+    float pv0, pv1;          // peak_value
+    int v0, v1;              // valid_peak
+};
+
+__device__ __forceinline__ PeakState fresh_state() { return PeakState{0u, 0u, -1, -1, FLT_MAX, FLT_MAX, 0, 0}; }
+
+__device__ __forceinline__ bool same_state(const PeakState& a, const PeakState& b)
+{
+    return a.m0 == b.m0 && a.m1 == b.m1 && a.pp0 == b.pp0 && a.pp1 == b.pp1 && __float_as_uint(a.pv0) == __float_as_uint(b.pv0) &&
+           __float_as_uint(a.pv1) == __float_as_uint(b.pv1) && a.v0 == b.v0 && a.v1 == b.v1;
+}
+
+struct PeakConsts { float thr0, thr1, ph; uint32_t w0, half0, half1; };
+
+// one step at position i; returns the boundaries emitted (0, 1 or 2) in e0 (short detector) / e1 (long detector)
+__device__ __forceinline__ void peak_step(PeakState& st, const PeakConsts& k, uint32_t i, float ts1, float ts2, int& e0, int& e1)
+{
+    e0 = -1; e1 = -1;
+    {   // short detector
+        const bool act = !(st.m0 >= i);
+        const float cur = ts1;
+        const bool nopeak = st.pp0 < 0;
+        const bool lower = cur < st.pv0;
+        const bool rise = !lower && (__fsub_rn(cur, st.pv0) > k.ph);
+        const bool upd = cur > st.pv0;
+        const float npv = nopeak ? ((lower || rise) ? cur : st.pv0) : (upd ? cur : st.pv0);
+        const int npp = nopeak ? (rise ? (int)i : -1) : (upd ? (int)i : st.pp0);
+        const bool in2 = act && !nopeak;
+        const bool over = npv > k.thr0;
+        const bool dominate = in2 && over;                  // the short detector will fire: silence the long one
+        const bool nvalid = st.v0 || (in2 && over && (__fsub_rn(npv, cur) > k.ph));
+        const bool emit = in2 && nvalid && ((i - (uint32_t)npp) > k.half0);
+        if (emit) e0 = npp;
+        if (dominate) { st.m1 = (uint32_t)npp + k.w0; st.pp1 = -1; st.pv1 = FLT_MAX; st.v1 = 0; }
+        if (act) { st.pv0 = emit ? cur : npv; st.pp0 = emit ? -1 : npp; st.v0 = emit ? 0 : (nvalid ? 1 : 0); }
+    }
+    {   // long detector
+        const bool act = !(st.m1 >= i);
+        const float cur = ts2;
+        const bool nopeak = st.pp1 < 0;
+        const bool lower = cur < st.pv1;
+        const bool rise = !lower && (__fsub_rn(cur, st.pv1) > k.ph);
+        const bool upd = cur > st.pv1;
+        const float npv = nopeak ? ((lower || rise) ? cur : st.pv1) : (upd ? cur : st.pv1);
+        const int npp = nopeak ? (rise ? (int)i : -1) : (upd ? (int)i : st.pp1);
+        const bool in2 = act && !nopeak;
+        const bool nvalid = st.v1 || (in2 && (npv > k.thr1) && (__fsub_rn(npv, cur) > k.ph));
+        const bool emit = in2 && nvalid && ((i - (uint32_t)npp) > k.half1);
+        if (emit) e1 = npp;
+        if (act) { st.pv1 = emit ? cur : npv; st.pp1 = emit ? -1 : npp; st.v1 = emit ? 0 : (nvalid ? 1 : 0); }
+    }
+}
+
+constexpr int kPeakWarps = 4;
+constexpr uint32_t kWarm = 512;      // default warm-up; $NPH_EVENTS_WARMUP overrides (0 forces the sequential walk: test hook)
+
+// walks [from, to) from state st; counts boundaries, and writes them at out[pos++] when WRITE
+template <bool WRITE>
+__device__ __forceinline__ uint32_t peak_walk(PeakState& st, const PeakConsts& k, const float* __restrict__ t1, const float* __restrict__ t2,
+                                              uint32_t from, uint32_t to, uint32_t* out, uint32_t pos, uint32_t cap_peaks)
+{
+    uint32_t cnt = 0;
+    for (uint32_t i = from; i < to; ++i) {
+        int e0, e1;
+        peak_step(st, k, i, t1[i], t2[i], e0, e1);
+        if (e0 >= 0) { if (WRITE && pos + cnt < cap_peaks) out[pos + cnt] = (uint32_t)e0; ++cnt; }
+        if (e1 >= 0) { if (WRITE && pos + cnt < cap_peaks) out[pos + cnt] = (uint32_t)e1; ++cnt; }
+    }
+    return cnt;
+}
+
+__global__ void __launch_bounds__(kPeakWarps * 32) ed_peaks_kernel(const FastParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t slot = blockIdx.x * kPeakWarps + (threadIdx.x >> 5);
+    if (slot >= p.n_reads) return;
+    const uint32_t ridx = p.order[slot];
+    if (!p.exact[ridx]) return;
+    const nph_raw_read rd = p.reads[ridx];
+    const uint32_t n = rd.n_samples;
+    const float* __restrict__ t1 = p.ts1 + rd.sample_off;
+    const float* __restrict__ t2 = p.ts2 + rd.sample_off;
+    uint32_t* peaks = p.peaks + rd.event_off;
+    const uint32_t cap_peaks = rd.event_cap ? rd.event_cap - 1 : 0;       // events = boundaries + 1
+    const PeakConsts k{p.t1, p.t2, p.peak_height, p.w1, p.w1 / 2, p.w2 / 2};
+
+    const uint32_t seg = ((n + 31) / 32 + 31) / 32 * 32;                   // segment length, multiple of 32
+    const uint32_t b0 = min(n, (uint32_t)lane * seg), b1 = min(n, b0 + seg);
+    const bool mine = b0 < n;                                              // lanes past the end of the read own nothing
+    const uint32_t a0 = b0 > p.warm ? b0 - p.warm : 0;
+    PeakState st = fresh_state();
+    if (mine) peak_walk<false>(st, k, t1, t2, a0, b0, nullptr, 0, 0);     // warm-up (lane 0 and early lanes: from sample 0)
+    const PeakState snap = st;
+    const uint32_t cnt = mine ? peak_walk<false>(st, k, t1, t2, b0, b1, nullptr, 0, 0) : 0u;
+    // verification: my snapshot must equal the final state of the lane to my left
+    PeakState left;
+    left.m0 = __shfl_up_sync(0xffffffffu, st.m0, 1); left.m1 = __shfl_up_sync(0xffffffffu, st.m1, 1);
+    left.pp0 = __shfl_up_sync(0xffffffffu, st.pp0, 1); left.pp1 = __shfl_up_sync(0xffffffffu, st.pp1, 1);
+    left.pv0 = __shfl_up_sync(0xffffffffu, st.pv0, 1); left.pv1 = __shfl_up_sync(0xffffffffu, st.pv1, 1);
+    left.v0 = __shfl_up_sync(0xffffffffu, st.v0, 1); left.v1 = __shfl_up_sync(0xffffffffu, st.v1, 1);
+    const bool ok = !mine || (a0 == 0) || same_state(snap, left);
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    uint32_t total;
+    if (all_ok) {
+        uint32_t incl = cnt;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        total = __shfl_sync(0xffffffffu, incl, 31);
+        PeakState s2 = snap;
+        if (mine) peak_walk<true>(s2, k, t1, t2, b0, b1, peaks, incl - cnt, cap_peaks);
+    } else {
+        // some segment did not re-synchronise inside its warm-up: walk the read in order (exact, slow, rare)
+        total = 0;
+        if (lane == 0) { PeakState s2 = fresh_state(); total = peak_walk<true>(s2, k, t1, t2, 0, n, peaks, 0, cap_peaks); }
+        total = __shfl_sync(0xffffffffu, total, 0);
+    }
+    if (lane == 0) {
+        if (total > cap_peaks) { *p.overflow = 1; p.n_peaks[ridx] = 0; p.n_events[ridx] = 0; }
+        else { p.n_peaks[ridx] = total; p.n_events[ridx] = total + 1; }
+    }
+}
+
+// block per read, thread per event
+__global__ void __launch_bounds__(256) ed_events_kernel(const FastParams p)
+{
+    for (uint32_t r = blockIdx.x; r < p.n_reads; r += gridDim.x) {
+        if (!p.exact[r]) continue;
+        const nph_raw_read rd = p.reads[r];
+        const uint32_t ne = p.n_events[r];
+        if (ne == 0) continue;
+        const float* __restrict__ x = p.raw + rd.sample_off;
+        const uint32_t* peaks = p.peaks + rd.event_off;
+        nph_event* out = p.events + rd.event_off;
+        const unsigned long long n = rd.n_samples;
+        for (uint32_t ev = threadIdx.x; ev < ne; ev += blockDim.x) {
+            const unsigned long long start = ev == 0 ? 0ull : peaks[ev - 1];
+            const unsigned long long end = ev == ne - 1 ? n : peaks[ev];
+            // exact segment sums; boundaries emitted out of order give a negative sum, like sums[end] - sums[start]
+            const unsigned long long lo = start < end ? start : end, hi = start < end ? end : start;
+            double s = 0.0, q = 0.0;
+            for (unsigned long long j = lo; j < hi; ++j) { const float v = x[j]; s = __dadd_rn(s, (double)v); q = __dadd_rn(q, (double)__fmul_rn(v, v)); }
+            if (end < start) { s = -s; q = -q; }
+            nph_event e;
+            e.start = start;
+            e.length = (float)(end - start);
+            e.mean = __fdiv_rn((float)s, e.length);
+            const float var = __fsub_rn(__fdiv_rn((float)q, e.length), __fmul_rn(e.mean, e.mean));
+            e.stdv = __fsqrt_rn(fmaxf(var, 0.0f));
+            e.reserved = 0;
+            out[ev] = e;
+        }
+    }
+}
+
+} // namespace
+
+extern "C" int nph_detect_events_batch(nph_ctx* ctx, const float* raw, size_t n_samples_total, const nph_raw_read* reads, size_t n_reads,
+                                       const nph_event_params* params, nph_event* events_out, size_t events_total, uint32_t* n_events_out)
+{
+    if (!ctx || !params) return NPH_ERR_INVALID;
+    if (n_reads == 0) return NPH_OK;
+    if (!raw || !reads || !events_out || !n_events_out) return NPH_ERR_INVALID;
+    if (params->window_length2 > kMaxW2 || params->window_length1 > params->window_length2 || params->window_length1 == 0) return NPH_ERR_UNSUPPORTED;
+    NPH_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<std::pair<uint32_t, uint32_t>> keyed(n_reads);
+    for (size_t i = 0; i < n_reads; ++i) {
+        const nph_raw_read& r = reads[i];
+        if (r.n_samples == 0 || r.sample_off + r.n_samples > n_samples_total || r.event_off + r.event_cap > events_total || r.event_cap == 0)
+            return NPH_ERR_INVALID;
+        keyed[i] = {r.n_samples, (uint32_t)i};
+    }
+    // threads of a warp walk reads of similar length: longest first
+    std::sort(keyed.begin(), keyed.end(), [](const std::pair<uint32_t, uint32_t>& a, const std::pair<uint32_t, uint32_t>& b) {
+        return a.first != b.first ? a.first > b.first : a.second < b.second; });
+    std::vector<uint32_t> order(n_reads);
+    for (size_t i = 0; i < n_reads; ++i) order[i] = keyed[i].second;
+
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t b_raw = al(sizeof(float) * n_samples_total), b_reads = al(sizeof(nph_raw_read) * n_reads), b_order = al(sizeof(uint32_t) * n_reads);
+    const size_t b_ev = al(sizeof(nph_event) * events_total), b_n = al(sizeof(uint32_t) * n_reads);
+    const size_t b_pk = al(sizeof(uint32_t) * events_total), b_ex = al(n_reads);
+    NPH_TRY(nph_reserve(ctx, ctx->d_abea_scratch, 3 * b_raw + b_reads + b_order + b_ev + 2 * b_n + b_pk + b_ex + 256));
+    uint8_t* base = ctx->d_abea_scratch.p;
+    DetParams p{};
+    float* d_raw = reinterpret_cast<float*>(base); base += b_raw;
+    nph_raw_read* d_reads = reinterpret_cast<nph_raw_read*>(base); base += b_reads;
+    uint32_t* d_order = reinterpret_cast<uint32_t*>(base); base += b_order;
+    p.events = reinterpret_cast<nph_event*>(base); base += b_ev;
+    p.n_events = reinterpret_cast<uint32_t*>(base); base += b_n;
+    p.overflow = reinterpret_cast<int*>(base); base += 256;
+    float* d_ts1 = reinterpret_cast<float*>(base); base += b_raw;
+    float* d_ts2 = reinterpret_cast<float*>(base); base += b_raw;
+    uint32_t* d_peaks = reinterpret_cast<uint32_t*>(base); base += b_pk;
+    uint32_t* d_npeaks = reinterpret_cast<uint32_t*>(base); base += b_n;
+    uint8_t* d_exact = reinterpret_cast<uint8_t*>(base);
+    p.raw = d_raw; p.reads = d_reads; p.order = d_order; p.n_reads = (uint32_t)n_reads;
+    p.w1 = params->window_length1; p.w2 = params->window_length2;
+    p.t1 = params->threshold1; p.t2 = params->threshold2; p.peak_height = params->peak_height;
+    p.ring = 2 * p.w2 + 1;
+    NPH_CUDA(ctx, cudaMemcpyAsync(d_raw, raw, sizeof(float) * n_samples_total, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(d_reads, reads, sizeof(nph_raw_read) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(d_order, order.data(), sizeof(uint32_t) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemsetAsync(p.overflow, 0, sizeof(int), ctx->stream));
+    // fast path first (guard -> t-statistics -> peaks -> events); reads that fail the exactness guard take the stream kernel
+    FastParams f{};
+    f.raw = d_raw; f.reads = d_reads; f.order = d_order; f.n_reads = (uint32_t)n_reads;
+    f.ts1 = d_ts1; f.ts2 = d_ts2; f.peaks = d_peaks; f.n_peaks = d_npeaks; f.exact = d_exact;
+    f.events = p.events; f.n_events = p.n_events; f.overflow = p.overflow;
+    f.w1 = p.w1; f.w2 = p.w2; f.t1 = p.t1; f.t2 = p.t2; f.peak_height = p.peak_height;
+    f.warm = getenv("NPH_EVENTS_WARMUP") ? (uint32_t)atoi(getenv("NPH_EVENTS_WARMUP")) : kWarm;
+    NPH_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    int launches = 0;
+    ed_guard_kernel<<<(unsigned)std::min<size_t>(n_reads, (size_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(f); ++launches;
+    NPH_CUDA(ctx, cudaGetLastError());
+    {
+        const uint32_t max_n = keyed[0].first;
+        dim3 grid((unsigned)std::min<size_t>((max_n + 255) / 256, 64), (unsigned)n_reads);
+        if (n_reads <= 65535) { ed_tstat_kernel<<<grid, 256, 0, ctx->stream>>>(f); ++launches; }
+        else {
+            for (size_t r0 = 0; r0 < n_reads; r0 += 65535) {         // gridDim.y limit
+                FastParams g = f; g.reads = d_reads + r0; g.exact = d_exact + r0;
+                dim3 gg(grid.x, (unsigned)std::min<size_t>(65535, n_reads - r0));
+                ed_tstat_kernel<<<gg, 256, 0, ctx->stream>>>(g); ++launches;
+            }
+        }
+        NPH_CUDA(ctx, cudaGetLastError());
+    }
+    ed_peaks_kernel<<<(unsigned)((n_reads + kPeakWarps - 1) / kPeakWarps), kPeakWarps * 32, 0, ctx->stream>>>(f); ++launches;
+    NPH_CUDA(ctx, cudaGetLastError());
+    ed_events_kernel<<<(unsigned)std::min<size_t>(n_reads, (size_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(f); ++launches;
+    NPH_CUDA(ctx, cudaGetLastError());
+    // fallback list
+    std::vector<uint8_t> exact(n_reads);
+    NPH_CUDA(ctx, cudaMemcpyAsync(exact.data(), d_exact, n_reads, cudaMemcpyDeviceToHost, ctx->stream));
+    NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> slow;
+    for (size_t t = 0; t < n_reads; ++t) if (!exact[order[t]] || getenv("NPH_EVENTS_FORCE_STREAM")) slow.push_back(order[t]);
+    if (!slow.empty()) {
+        NPH_CUDA(ctx, cudaMemcpyAsync(d_order, slow.data(), sizeof(uint32_t) * slow.size(), cudaMemcpyHostToDevice, ctx->stream));
+        p.n_reads = (uint32_t)slow.size();
+        const size_t smem = sizeof(double) * 2 * p.ring * kThreads;
+        NPH_CUDA(ctx, cudaFuncSetAttribute(detect_events_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        detect_events_stream_kernel<<<(unsigned)((slow.size() + kThreads - 1) / kThreads), kThreads, smem, ctx->stream>>>(p); ++launches;
+        NPH_CUDA(ctx, cudaGetLastError());
+    }
+    NPH_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->last_launches = launches;
+    ctx->timing_valid = true;
+    int overflow = 0;
+    NPH_CUDA(ctx, cudaMemcpyAsync(events_out, p.events, sizeof(nph_event) * events_total, cudaMemcpyDeviceToHost, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(n_events_out, p.n_events, sizeof(uint32_t) * n_reads, cudaMemcpyDeviceToHost, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(&overflow, p.overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->abea_loaded = false;     // the arena was reused
+    return overflow ? NPH_ERR_UNSUPPORTED : NPH_OK;
+}

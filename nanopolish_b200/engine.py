@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .synth import ABEA_RES_DT, ALIGN_STATE_DT, PAIR_DT
+from .synth import ABEA_RES_DT, ALIGN_STATE_DT, EVENT_DT, PAIR_DT
 
 
 def _p(a):
@@ -150,6 +150,16 @@ class Engine:
                                            _p(kmer_ranks), kmer_ranks.shape[0], _p(jobs), jobs.shape[0],
                                            model_id, _p(out)), "nph_mom_batch")
         return out
+
+    # ---- event detection (scrappie detect_events) ---------------------------------------------
+    def detect_events_batch(self, raw, reads, params):
+        """== [detect_events(read_i)]: list of EVENT_DT arrays, one per raw read."""
+        total = int((reads["event_off"] + reads["event_cap"]).max()) if reads.shape[0] else 0
+        events = np.zeros(total, EVENT_DT)
+        counts = np.zeros(reads.shape[0], np.uint32)
+        self._check(self.lib.nph_detect_events_batch(self.ctx, _p(raw), raw.shape[0], _p(reads), reads.shape[0], _p(params),
+                                                     _p(events), total, _p(counts)), "nph_detect_events_batch")
+        return [events[int(r["event_off"]):int(r["event_off"]) + int(c)] for r, c in zip(reads, counts)]
 
     # ---- measurement ----------------------------------------------------------------------
     def sync(self):

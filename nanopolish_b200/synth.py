@@ -40,6 +40,11 @@ ABEA_RES_DT = np.dtype([
 ], align=True)
 ALIGN_STATE_DT = np.dtype([("event_idx", "<u4"), ("kmer_idx", "<u4"), ("l_fm", "<f4"), ("state", "S1"),
                            ("reserved", "u1", (3,))], align=True)
+EVENT_DT = np.dtype([("start", "<u8"), ("length", "<f4"), ("mean", "<f4"), ("stdv", "<f4"), ("reserved", "<u4")], align=True)
+RAW_READ_DT = np.dtype([("sample_off", "<u8"), ("event_off", "<u8"), ("n_samples", "<u4"), ("event_cap", "<u4")], align=True)
+EVENT_PARAMS_DT = np.dtype([("window_length1", "<u4"), ("window_length2", "<u4"), ("threshold1", "<f4"), ("threshold2", "<f4"),
+                            ("peak_height", "<f4")], align=True)
+assert EVENT_DT.itemsize == 24 and RAW_READ_DT.itemsize == 24 and EVENT_PARAMS_DT.itemsize == 20
 assert ALIGN_STATE_DT.itemsize == 16
 assert READ_DT.itemsize == 64 and HMM_JOB_DT.itemsize == 32 and ABEA_JOB_DT.itemsize == 32
 assert PAIR_DT.itemsize == 8 and ABEA_RES_DT.itemsize == 24
@@ -362,3 +367,32 @@ def methylation_jobs(rs: ReadSet, model_id: int = 0, min_separation: int = 10, m
             if max_groups_per_read and n_done >= max_groups_per_read:
                 break
     return _finish_jobs(rows, ranks_list, seqs if keep_seqs else None)
+
+
+def event_params(rna: bool = False) -> np.ndarray:
+    """scrappie's event_detection_defaults / event_detection_rna (src/thirdparty/scrappie/event_detection.h:15-29)."""
+    p = np.zeros(1, EVENT_PARAMS_DT)
+    p[0] = (7, 14, 2.5, 9.0, 1.0) if rna else (3, 6, 1.4, 9.0, 0.2)
+    return p
+
+
+def gen_raw(n_reads: int, n_samples: int, model: PoreModel, seed: int = 42, mean_dwell: float = 9.0):
+    """Synthetic raw current traces (picoamps, float32): a random sequence's k-mer levels held for a geometric dwell
+    (mean ~9 samples at 4 kHz / 450 bases/s) plus Gaussian noise.  Returns (raw f32[total], RAW_READ_DT[n_reads])."""
+    reads = np.zeros(n_reads, RAW_READ_DT)
+    chunks = []
+    soff = eoff = 0
+    for r in range(n_reads):
+        rng = np.random.default_rng(seed + r)
+        nk = int(n_samples / mean_dwell * 1.3) + 16
+        ranks = kmer_ranks_from_codes(rng.integers(0, 4, nk + model.k - 1, dtype=np.uint8), model.k, 4)
+        dwell = np.maximum(1, rng.geometric(1.0 / mean_dwell, nk))
+        lv = np.repeat(model.level_mean[ranks], dwell)[:n_samples]
+        sd = np.repeat(model.level_stdv[ranks], dwell)[:n_samples]
+        x = (lv + 1.2 * sd * rng.standard_normal(lv.shape[0])).astype(np.float32)
+        cap = x.shape[0] // 2 + 8
+        reads[r] = (soff, eoff, x.shape[0], cap)
+        chunks.append(x)
+        soff += x.shape[0]
+        eoff += cap
+    return np.concatenate(chunks), reads

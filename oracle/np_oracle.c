@@ -573,6 +573,93 @@ double npo_abea_batch(const nph_read* reads, const float* ev_mean, const double*
     return now_s() - t0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Event detection (scrappie, as called by load_from_raw: src/nanopolish_squiggle_read.cpp:229-235 — the trimmed
+ * raw_table is discarded there, so the whole signal is segmented).
+ * ref: src/thirdparty/scrappie/event_detection.c: compute_sum_sumsq :35-49, compute_tstat :62-118,
+ *      short_long_peak_detector :122-201, create_event(s) :216-266, detect_events :268-319.
+ * Returns the number of events (>= 1), events in emission order; -1 if cap is too small.
+ * ---------------------------------------------------------------------------------------- */
+#include <float.h>
+static void tstat_fill(const double* sum, const double* sumsq, size_t n, size_t w, float* t)
+{
+    const float eta = FLT_MIN, wf = (float)w;
+    for (size_t i = 0; i < n; ++i) t[i] = 0.0f;
+    if (n < 2 * w || w < 2) return;
+    for (size_t i = w; i <= n - w; ++i) {
+        double sum1 = sum[i], sumsq1 = sumsq[i];
+        if (i > w) { sum1 -= sum[i - w]; sumsq1 -= sumsq[i - w]; }
+        float sum2 = (float)(sum[i + w] - sum[i]);
+        float sumsq2 = (float)(sumsq[i + w] - sumsq[i]);
+        float mean1 = sum1 / wf;
+        float mean2 = sum2 / wf;
+        float combined_var = sumsq1 / wf - mean1 * mean1 + sumsq2 / wf - mean2 * mean2;
+        combined_var = fmaxf(combined_var, eta);
+        const float delta_mean = mean2 - mean1;
+        t[i] = fabs(delta_mean) / sqrt(combined_var / wf);
+    }
+}
+
+typedef struct { float threshold; size_t window_length; size_t masked_to; long peak_pos; float peak_value; int valid_peak; } npo_detector;
+
+long long npo_detect_events(const float* raw, size_t n, const nph_event_params* prm, nph_event* out, size_t cap)
+{
+    double* sum = (double*)calloc(n + 1, sizeof(double));
+    double* sumsq = (double*)calloc(n + 1, sizeof(double));
+    float* t1 = (float*)calloc(n, sizeof(float));
+    float* t2 = (float*)calloc(n, sizeof(float));
+    size_t* peaks = (size_t*)calloc(n, sizeof(size_t));
+    for (size_t i = 0; i < n; ++i) { sum[i + 1] = sum[i] + raw[i]; sumsq[i + 1] = sumsq[i] + raw[i] * raw[i]; }
+    tstat_fill(sum, sumsq, n, prm->window_length1, t1);
+    tstat_fill(sum, sumsq, n, prm->window_length2, t2);
+    npo_detector det[2] = { { prm->threshold1, prm->window_length1, 0, -1, FLT_MAX, 0 }, { prm->threshold2, prm->window_length2, 0, -1, FLT_MAX, 0 } };
+    const float* sig[2] = { t1, t2 };
+    const float peak_height = prm->peak_height;
+    size_t peak_count = 0;
+    for (size_t i = 0; i < n; ++i) {
+        for (int k = 0; k < 2; ++k) {
+            npo_detector* d = &det[k];
+            if (d->masked_to >= i) continue;
+            float cur = sig[k][i];
+            if (d->peak_pos == -1) {
+                if (cur < d->peak_value) d->peak_value = cur;
+                else if (cur - d->peak_value > peak_height) { d->peak_value = cur; d->peak_pos = (long)i; }
+            } else {
+                if (cur > d->peak_value) { d->peak_value = cur; d->peak_pos = (long)i; }
+                if (k == 0 && d->peak_value > d->threshold) {
+                    det[1].masked_to = d->peak_pos + d->window_length;
+                    det[1].peak_pos = -1; det[1].peak_value = FLT_MAX; det[1].valid_peak = 0;
+                }
+                if (d->peak_value - cur > peak_height && d->peak_value > d->threshold) d->valid_peak = 1;
+                if (d->valid_peak && (i - d->peak_pos) > d->window_length / 2) {
+                    peaks[peak_count++] = (size_t)d->peak_pos;
+                    d->peak_pos = -1; d->peak_value = cur; d->valid_peak = 0;
+                }
+            }
+        }
+    }
+    size_t ne = 1;
+    for (size_t i = 0; i < n; ++i) if (peaks[i] > 0 && peaks[i] < n) ne++;
+    long long ret = (long long)ne;
+    if (ne > cap) ret = -1;
+    else {
+        for (size_t ev = 0; ev < ne; ++ev) {
+            size_t s = ev == 0 ? 0 : peaks[ev - 1];
+            size_t e = ev == ne - 1 ? n : peaks[ev];
+            nph_event x;
+            x.start = (uint64_t)s;
+            x.length = (float)(e - s);
+            x.mean = (float)(sum[e] - sum[s]) / x.length;
+            const float deltasqr = (sumsq[e] - sumsq[s]);
+            const float var = deltasqr / x.length - x.mean * x.mean;
+            x.stdv = sqrtf(fmaxf(var, 0.0f));
+            out[ev] = x;
+        }
+    }
+    free(sum); free(sumsq); free(t1); free(t2); free(peaks);
+    return ret;
+}
+
 int npo_max_threads(void)
 {
 #ifdef _OPENMP

@@ -51,6 +51,7 @@ double npo_abea_batch(const nph_read* reads, const float* ev_mean, const double*
                       size_t n_jobs, int threads, nph_aligned_pair* pairs_out, nph_abea_result* res);
 void npo_mom(const nph_read* reads, const float* ev_mean, const npo_model* model,
              const uint32_t* kmer_ranks, const nph_abea_job* job, double* shift_out, double* scale_out);
+long long npo_detect_events(const float* raw, size_t n, const nph_event_params* prm, nph_event* out, size_t cap);
 int npo_max_threads(void);
 
 #ifdef __cplusplus

@@ -128,6 +128,13 @@ class PortOracle:
         self.lib.npo_mom(_p(reads), _p(ev_mean), marr, _p(kmer_ranks), _p(jb), C.byref(sh), C.byref(sc))
         return sh.value, sc.value
 
+    def detect_events(self, raw, params):
+        from nanopolish_b200.synth import EVENT_DT
+        out = np.zeros(raw.shape[0] + 1, EVENT_DT)
+        self.lib.npo_detect_events.restype = C.c_longlong
+        n = self.lib.npo_detect_events(_p(raw), C.c_size_t(raw.shape[0]), _p(params), _p(out), C.c_size_t(out.shape[0]))
+        return out[:n].copy()
+
     def max_threads(self):
         return int(self.lib.npo_max_threads())
 
@@ -238,6 +245,14 @@ class RefOracle:
         secs = self.lib.npref_abea_batch(C.c_size_t(n), _p(rh), model_h, C.c_char_p(buf), _p(off), C.c_int(threads),
                                          _p(pairs), _p(poff), _p(npairs))
         return pairs, poff, npairs, secs
+
+    def detect_events(self, raw, rna=False):
+        n = raw.shape[0]
+        start = np.zeros(n + 1, np.uint64); length = np.zeros(n + 1, np.float32)
+        mean = np.zeros(n + 1, np.float32); stdv = np.zeros(n + 1, np.float32)
+        self.lib.npref_detect_events.restype = C.c_longlong
+        ne = self.lib.npref_detect_events(_p(raw), C.c_size_t(n), int(rna), _p(start), _p(length), _p(mean), _p(stdv), C.c_size_t(n + 1))
+        return start[:ne], length[:ne], mean[:ne], stdv[:ne]
 
     def mom(self, read_h, model_h, seq: bytes):
         out = np.zeros(4)

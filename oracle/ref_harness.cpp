@@ -30,6 +30,9 @@
 #include "nanopolish_alphabet.h"
 #include "nanopolish_emissions.h"
 #include "logsum.h"
+extern "C" {
+#include "event_detection.h"   // src/thirdparty/scrappie (C99)
+}
 
 extern double hmm_indel_bias_factor;   // src/hmm/nanopolish_profile_hmm_r9.cpp:19
 
@@ -276,6 +279,22 @@ float npref_log_normal_pdf(float x, float mean, float stdv)
     GaussianParameters g(mean, stdv);
     return log_normal_pdf(x, g);
 }
+// detect_events (src/thirdparty/scrappie/event_detection.c:268-319) on one raw signal, the way load_from_raw
+// calls it (src/nanopolish_squiggle_read.cpp:229-235: the trimmed table is discarded, the whole array is segmented).
+long long npref_detect_events(const float* raw, size_t n, int rna, uint64_t* start, float* length, float* mean, float* stdv, size_t cap)
+{
+    raw_table rt;
+    rt.n = n; rt.start = 0; rt.end = n; rt.raw = const_cast<float*>(raw);
+    event_table et = detect_events(rt, rna ? event_detection_rna : event_detection_defaults);
+    if (et.event == NULL) return -2;
+    long long ne = (long long)et.n;
+    if (et.n <= cap) {
+        for (size_t i = 0; i < et.n; ++i) { start[i] = et.event[i].start; length[i] = et.event[i].length; mean[i] = et.event[i].mean; stdv[i] = et.event[i].stdv; }
+    } else ne = -1;
+    free(et.event);
+    return ne;
+}
+
 int npref_max_threads(void) { return omp_get_max_threads(); }
 
 } // extern "C"

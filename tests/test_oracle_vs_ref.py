@@ -125,3 +125,21 @@ def test_viterbi_align_identical(port_oracle, ref_oracle):
             assert status == 0 and out.shape[0] == ek.shape[0] > 0
             assert np.array_equal(out["event_idx"], ek[:, 0]) and np.array_equal(out["kmer_idx"], ek[:, 1])
             assert np.array_equal(out["l_fm"].view(np.uint32), lfm.view(np.uint32)) and out["state"].tobytes() == st
+
+
+@pytest.mark.parametrize("rna", [False, True])
+def test_event_detection_identical(port_oracle, ref_oracle, rna):
+    """scrappie detect_events (compiled C) vs the restatement: identical boundaries, bit-identical mean/stdv."""
+    nuc = synth.load_model("nucleotide")
+    raw, reads = synth.gen_raw(4, 30000, nuc, seed=77, mean_dwell=30.0 if rna else 9.0)
+    prm = synth.event_params(rna)
+    for r in reads:
+        x = np.ascontiguousarray(raw[int(r["sample_off"]):int(r["sample_off"]) + int(r["n_samples"])])
+        st, ln, mn, sd = ref_oracle.detect_events(x, rna)
+        ev = port_oracle.detect_events(x, prm)
+        assert ev.shape[0] == st.shape[0] > 500
+        assert np.array_equal(ev["start"], st) and np.array_equal(ev["length"].view(np.uint32), ln.view(np.uint32))
+        assert np.array_equal(ev["mean"].view(np.uint32), mn.view(np.uint32)) and np.array_equal(ev["stdv"].view(np.uint32), sd.view(np.uint32))
+    # (a signal without any peak makes the reference read peaks[-1]: undefined there, one whole-signal event here)
+    ev = port_oracle.detect_events(raw[:5].copy(), prm)
+    assert ev.shape[0] == 1 and ev["start"][0] == 0 and ev["length"][0] == 5.0
