@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="scorereads", choices=["scorereads", "methylation"])
+    ap.add_argument("--workload", default="scorereads", choices=["scorereads", "methylation", "abea", "events"])
     ap.add_argument("--reads", type=int, default=10000, help="reads per GPU")
     ap.add_argument("--events", type=int, default=4000, help="events per read")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -230,6 +230,79 @@ def workload_config(args, jobs, reads_override=None):
             "parallelism": f"read-shard x{args.gpus}", "l2": "inputs larger than L2 (levels+ranks+scratch > 126 MB)"}
 
 
+def run_aux(args, rank, world, local, saved_stdout):
+    """Auxiliary single-GPU measurements of the other kernels of the path (not the headline metric):
+    --workload abea   : adaptive banded event alignment, reads x 8000 events (BASELINE configs[3] shape), events/s
+    --workload events : scrappie event detection, reads x 36000 raw samples, samples/s"""
+    if rank != 0:
+        return
+    import torch
+    from nanopolish_b200 import synth
+    from nanopolish_b200.engine import Engine
+    nuc = synth.load_model("nucleotide")
+    eng = Engine(local)
+    mid = eng.model_upload(nuc)
+    peak, peak_src = peaks()
+    if args.workload == "abea":
+        n_reads = min(args.reads, 4736)
+        rs = synth.gen_reads(n_reads, 8000, nuc, seed=42, rng_scalings=False)
+        jobs, ranks, total = synth.abea_jobs(rs)
+        eng.reads_load(rs.reads, rs.ev_mean, rs.ev_start_time)
+        eng.abea_jobs_load(ranks, jobs, mid, total)
+        for _ in range(max(3, args.warmup)):
+            eng.abea_run()
+        eng.sync()
+        ms = []
+        for _ in range(args.steps):
+            eng.abea_run(); eng.sync(); ms.append(eng.last_kernel_ms()[0])
+        t = float(np.mean(ms))
+        ev = int(rs.reads["n_events"].sum())
+        b_alg = int((12 * rs.reads["n_events"].astype(np.int64) + 50 * (rs.reads["n_events"].astype(np.int64) + jobs["n_kmers"])).sum())
+        t0 = time.perf_counter(); eng.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ranks, jobs, mid, total); e2e_s = time.perf_counter() - t0
+        line = {"metric": "abea_events_per_sec", "value": ev / (t * 1e-3), "unit": "events/s", "n_gpus": 1, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32+f64", "data": "synthetic",
+                "config": {"workload": f"abea: {n_reads} synthetic R9.4 reads x 8000 events, k=6 nucleotide model, band 100"},
+                "e2e": {"value": ev / e2e_s, "unit": "events/s", "h2d_bytes_per_step": int(rs.ev_mean.nbytes + ranks.nbytes + jobs.nbytes),
+                        "d2h_bytes_per_step": int(total * 8), "steps": 1, "api": "nph_abea_batch"},
+                "gpu_launches": args.steps,
+                "roofline": {"bound": "hbm", "achieved": b_alg / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": b_alg / (t * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel": "abea_kernel",
+                             "note": "sequentially dependent bands: issue/latency bound (DESIGN.md section 5)"}}
+    else:
+        n_reads = min(args.reads, 8192)
+        raw, reads = synth.gen_raw(min(n_reads, 512), 36000, nuc, seed=5)
+        if n_reads > 512:
+            reps = n_reads // 512; per = raw.shape[0]; estride = int(reads["event_off"][-1] + reads["event_cap"][-1])
+            raw = np.tile(raw, reps); reads = np.tile(reads, reps)
+            for r in range(reps):
+                reads["sample_off"][r * 512:(r + 1) * 512] += r * per
+                reads["event_off"][r * 512:(r + 1) * 512] += r * estride
+        prm = synth.event_params(False)
+        ms, e2e = [], []
+        for it in range(max(3, args.warmup) + args.steps):
+            t0 = time.perf_counter(); ev = eng.detect_events_batch(raw, reads, prm); dt = time.perf_counter() - t0
+            if it >= max(3, args.warmup):
+                ms.append(eng.last_kernel_ms()[0]); e2e.append(dt)
+        t = float(np.mean(ms))
+        n_ev = sum(e.shape[0] for e in ev)
+        b_alg = raw.nbytes + 24 * n_ev
+        line = {"metric": "event_detection_samples_per_sec", "value": raw.shape[0] / (t * 1e-3), "unit": "samples/s", "n_gpus": 1,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+                "config": {"workload": f"events: {reads.shape[0]} synthetic raw reads x 36000 samples, scrappie DNA parameters"},
+                "e2e": {"value": raw.shape[0] / float(np.mean(e2e)), "unit": "samples/s", "h2d_bytes_per_step": int(raw.nbytes),
+                        "d2h_bytes_per_step": int(24 * (reads["event_off"][-1] + reads["event_cap"][-1])), "steps": args.steps,
+                        "api": "nph_detect_events_batch"},
+                "gpu_launches": 4 * args.steps,
+                "roofline": {"bound": "hbm", "achieved": b_alg / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": b_alg / (t * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel": "ed_guard+ed_tstat+ed_peaks+ed_events",
+                             "note": "algorithmic bytes = 4 B/sample in + 24 B/event out"}}
+    emit(line, saved_stdout)
+    eng.close()
+
+
 def emit(line: dict, saved_stdout: int) -> None:
     """Exactly one JSON line on the real stdout (libraries such as NCCL print banners to fd 1)."""
     sys.stdout.flush()
@@ -244,6 +317,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload in ("abea", "events"):
+        run_aux(args, rank, world, local, saved_stdout)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world, saved_stdout)
         return

@@ -188,3 +188,36 @@ def test_full_size_properties(engine, models, port_oracle):
     _check(a[sample], want)
     # mean log-likelihood per scored event of the whole batch sits where the generator puts it
     assert abs(a.astype(np.float64).sum() / jobs.scored_events + 2.88) < 0.05
+
+
+def test_two_contexts_from_two_threads(models, port_oracle):
+    """The reference calls profile_hmm_score concurrently from OpenMP workers (bam_processor.cpp:99): one context per
+    thread must work side by side on the same device and give the same bits."""
+    import threading
+    from nanopolish_b200.engine import Engine
+    nuc = models["nucleotide"][0]
+    results, errors = {}, []
+
+    def work(tid):
+        try:
+            eng = Engine(0)
+            mid = eng.model_upload(nuc)
+            rs = synth.gen_reads(40, 1800, nuc, seed=700 + tid)
+            jobs = synth.scorereads_jobs(rs, 300, model_id=mid, rc_every=2)
+            outs = [eng.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, jobs.jobs).copy() for _ in range(6)]
+            results[tid] = (rs, jobs, outs)
+            eng.close()
+        except Exception as ex:      # surfaced below
+            errors.append(ex)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for tid, (rs, jobs, outs) in results.items():
+        oj = jobs.jobs.copy(); oj["model_id"] = 0
+        want, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [nuc], jobs.kmer_ranks, oj, threads=8)
+        for o in outs:
+            _check(o, want)
