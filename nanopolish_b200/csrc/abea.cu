@@ -31,7 +31,7 @@
 
 namespace {
 
-constexpr int kWarps = 16;
+constexpr int kWarps = 20;
 constexpr int kThreads = kWarps * 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kBW = 100;                 // ALN_BANDWIDTH (raw_loader.cpp:72)

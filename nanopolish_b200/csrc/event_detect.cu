@@ -366,8 +366,54 @@ __device__ __forceinline__ uint32_t peak_walk(PeakState& st, const PeakConsts& k
     return cnt;
 }
 
+// Warp-cooperative walk: lane l walks [from_l, to_l) of the read, but the t-statistics are fetched as 32x32 tiles
+// (row rr = the next 32 positions of lane rr's range: one coalesced 128-byte load per row and vector), staged through
+// shared memory, with the next tile already in flight in registers while the state machines consume the current one.
+template <bool WRITE>
+__device__ __forceinline__ uint32_t peak_walk_tiled(PeakState& st, const PeakConsts& k, const float* __restrict__ t1,
+                                                    const float* __restrict__ t2, uint32_t from, uint32_t to, uint32_t* out,
+                                                    uint32_t pos, uint32_t cap_peaks, float (*sa)[33], float (*sb)[33], int lane)
+{
+    const uint32_t len = to > from ? to - from : 0;
+    uint32_t maxlen = len;
+    for (int o = 16; o; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    uint32_t froms[32], lens[32];
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) { froms[rr] = __shfl_sync(0xffffffffu, from, rr); lens[rr] = __shfl_sync(0xffffffffu, len, rr); }
+    float ra[32], rb[32];
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) {
+        ra[rr] = 0.f; rb[rr] = 0.f;
+        if ((uint32_t)lane < lens[rr]) { ra[rr] = t1[froms[rr] + lane]; rb[rr] = t2[froms[rr] + lane]; }
+    }
+    uint32_t cnt = 0;
+    for (uint32_t c = 0; c < maxlen; c += 32) {
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) { sa[rr][lane] = ra[rr]; sb[rr][lane] = rb[rr]; }
+        __syncwarp();
+        if (c + 32 < maxlen) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+                ra[rr] = 0.f; rb[rr] = 0.f;
+                if (c + 32 + lane < lens[rr]) { ra[rr] = t1[froms[rr] + c + 32 + lane]; rb[rr] = t2[froms[rr] + c + 32 + lane]; }
+            }
+        }
+        const uint32_t steps = len > c ? min(32u, len - c) : 0u;
+        for (uint32_t t = 0; t < steps; ++t) {
+            int e0, e1;
+            peak_step(st, k, from + c + t, sa[lane][t], sb[lane][t], e0, e1);
+            if (e0 >= 0) { if (WRITE && pos + cnt < cap_peaks) out[pos + cnt] = (uint32_t)e0; ++cnt; }
+            if (e1 >= 0) { if (WRITE && pos + cnt < cap_peaks) out[pos + cnt] = (uint32_t)e1; ++cnt; }
+        }
+        __syncwarp();
+    }
+    return cnt;
+}
+
 __global__ void __launch_bounds__(kPeakWarps * 32) ed_peaks_kernel(const FastParams p)
 {
+    __shared__ float s_a[kPeakWarps][32][33], s_b[kPeakWarps][32][33];
+    const int wib = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t slot = blockIdx.x * kPeakWarps + (threadIdx.x >> 5);
     if (slot >= p.n_reads) return;
@@ -386,9 +432,10 @@ __global__ void __launch_bounds__(kPeakWarps * 32) ed_peaks_kernel(const FastPar
     const bool mine = b0 < n;                                              // lanes past the end of the read own nothing
     const uint32_t a0 = b0 > p.warm ? b0 - p.warm : 0;
     PeakState st = fresh_state();
-    if (mine) peak_walk<false>(st, k, t1, t2, a0, b0, nullptr, 0, 0);     // warm-up (lane 0 and early lanes: from sample 0)
+    // warm-up (lane 0 and early lanes: from sample 0); lanes past the end get empty ranges
+    peak_walk_tiled<false>(st, k, t1, t2, mine ? a0 : 0u, mine ? b0 : 0u, nullptr, 0, 0, s_a[wib], s_b[wib], lane);
     const PeakState snap = st;
-    const uint32_t cnt = mine ? peak_walk<false>(st, k, t1, t2, b0, b1, nullptr, 0, 0) : 0u;
+    const uint32_t cnt = peak_walk_tiled<false>(st, k, t1, t2, mine ? b0 : 0u, mine ? b1 : 0u, nullptr, 0, 0, s_a[wib], s_b[wib], lane);
     // verification: my snapshot must equal the final state of the lane to my left
     PeakState left;
     left.m0 = __shfl_up_sync(0xffffffffu, st.m0, 1); left.m1 = __shfl_up_sync(0xffffffffu, st.m1, 1);
@@ -403,7 +450,7 @@ __global__ void __launch_bounds__(kPeakWarps * 32) ed_peaks_kernel(const FastPar
         for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
         total = __shfl_sync(0xffffffffu, incl, 31);
         PeakState s2 = snap;
-        if (mine) peak_walk<true>(s2, k, t1, t2, b0, b1, peaks, incl - cnt, cap_peaks);
+        peak_walk_tiled<true>(s2, k, t1, t2, mine ? b0 : 0u, mine ? b1 : 0u, peaks, incl - cnt, cap_peaks, s_a[wib], s_b[wib], lane);
     } else {
         // some segment did not re-synchronise inside its warm-up: walk the read in order (exact, slow, rare)
         total = 0;

@@ -74,28 +74,33 @@ __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n
     if (threadIdx.x == 0) { atomicMax(&sum->max_kpad, s_kpad); atomicMax(&sum->max_period, s_period); atomicMax(&sum->max_E, s_E); }
 }
 
-// exclusive scan of the NPH_NUM_CLASSES * NPH_KEY_BUCKETS histogram (class-major), one block
-__global__ void scan_kernel(const unsigned int* __restrict__ hist, unsigned int* __restrict__ offs)
+// exclusive scan of the histogram, class-major: one block per class scans its NPH_KEY_BUCKETS buckets and adds the
+// class's base (the number of jobs in all earlier classes, from the summary the classify kernel accumulated)
+__global__ void __launch_bounds__(1024) scan_kernel(const unsigned int* __restrict__ hist, unsigned int* __restrict__ offs,
+                                                    const SchedSummary* __restrict__ sum)
 {
-    constexpr int N = NPH_NUM_CLASSES * NPH_KEY_BUCKETS;
     constexpr int T = 1024;
-    constexpr int PER = (N + T - 1) / T;
+    constexpr int PER = (NPH_KEY_BUCKETS + T - 1) / T;
     __shared__ unsigned int s_part[T];
-    const int t = threadIdx.x;
-    const int lo = t * PER, hi = min(N, lo + PER);
+    const int c = blockIdx.x, t = threadIdx.x;
+    unsigned int base = 0;
+    for (int k = 0; k < c; ++k) base += (unsigned int)sum->class_count[k];
+    if (sum->class_count[c] == 0) return;                      // nothing to place
+    const unsigned int* h = hist + (size_t)c * NPH_KEY_BUCKETS;
+    unsigned int* o = offs + (size_t)c * NPH_KEY_BUCKETS;
+    const int lo = t * PER, hi = min((int)NPH_KEY_BUCKETS, lo + PER);
     unsigned int s = 0;
-    for (int i = lo; i < hi; ++i) s += hist[i];
+    for (int i = lo; i < hi; ++i) s += h[i];
     s_part[t] = s;
     __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partials
-    for (int d = 1; d < T; d <<= 1) {
+    for (int d = 1; d < T; d <<= 1) {                          // Hillis-Steele inclusive scan over the 1024 partials
         unsigned int v = (t >= d) ? s_part[t - d] : 0u;
         __syncthreads();
         s_part[t] += v;
         __syncthreads();
     }
-    unsigned int run = (t == 0) ? 0u : s_part[t - 1];
-    for (int i = lo; i < hi; ++i) { offs[i] = run; run += hist[i]; }
+    unsigned int run = base + ((t == 0) ? 0u : s_part[t - 1]);
+    for (int i = lo; i < hi; ++i) { o[i] = run; run += h[i]; }
 }
 
 __global__ void scatter_kernel(uint32_t n_jobs, const uint8_t* __restrict__ cls, const uint16_t* __restrict__ bkt,
@@ -131,7 +136,7 @@ int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uin
                                                         (uint32_t)(ctx->levels_inflight ? ctx->level_chunk_events : 0), ctx->d_sched_cls.p,
                                                         ctx->d_sched_bkt.p, hist, d_sum);
     NPH_CUDA(ctx, cudaGetLastError());
-    scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, offs);
+    scan_kernel<<<NPH_NUM_CLASSES, 1024, 0, ctx->stream>>>(hist, offs, d_sum);
     NPH_CUDA(ctx, cudaGetLastError());
     SchedSummary h{};
     NPH_CUDA(ctx, cudaMemcpyAsync(&h, d_sum, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
