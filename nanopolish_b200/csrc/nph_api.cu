@@ -195,7 +195,6 @@ int nph_destroy(nph_ctx* ctx)
     if (ctx->h_progress_vals) cudaFreeHost(ctx->h_progress_vals);
     for (int i = 0; i < nph_ctx::kSideStreams; ++i) { if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
-    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     delete ctx;
     return NPH_OK;
 }

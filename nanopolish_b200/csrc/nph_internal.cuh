@@ -124,9 +124,6 @@ struct nph_ctx {
     std::vector<double> h_stage_drift;
     std::vector<float2> h_stage_trans;
 
-    // staging (pinned) buffers
-    void* h_stage = nullptr;
-    size_t h_stage_bytes = 0;
 };
 
 int nph_set_cuda_error(nph_ctx* ctx, cudaError_t e, const char* what);
