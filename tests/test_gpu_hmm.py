@@ -221,3 +221,30 @@ def test_two_contexts_from_two_threads(models, port_oracle):
         want, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [nuc], jobs.kmer_ranks, oj, threads=8)
         for o in outs:
             _check(o, want)
+
+
+def test_streamed_inputs_one_shot_call(engine, models, port_oracle):
+    """Batches above 2^20 events take the pipelined one-shot path: levels and k-mer ranks stream in behind progress
+    words while the forward kernels already run; scores must not change, and a bad rank is still rejected."""
+    from nanopolish_b200._lib import NphError
+    nuc, mid = models["nucleotide"]
+    rs = synth.gen_reads(320, 3600, nuc, seed=909)
+    assert rs.total_events > (1 << 20)
+    jobs = synth.scorereads_jobs(rs, 400, model_id=mid, rc_every=2)
+    got = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, jobs.jobs)
+    # same batch through the staged (fully resident) calls
+    engine.reads_load(rs.reads, rs.ev_mean, rs.ev_start_time)
+    engine.hmm_jobs_load(jobs.kmer_ranks, jobs.jobs)
+    engine.hmm_score()
+    resident = engine.hmm_scores_fetch()
+    assert np.array_equal(_bits(got), _bits(resident))
+    sample = np.arange(0, jobs.jobs.shape[0], 37)
+    oj = np.ascontiguousarray(jobs.jobs[sample]); oj["model_id"] = 0
+    want, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [nuc], jobs.kmer_ranks, oj, threads=16)
+    _check(got[sample], want)
+    bad = jobs.kmer_ranks.copy()
+    bad[-5] = 5000
+    with pytest.raises(NphError):
+        engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, bad, jobs.jobs)
+    again = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, jobs.jobs)   # context still usable
+    assert np.array_equal(_bits(again), _bits(got))
