@@ -245,6 +245,45 @@ typedef struct {
 int nph_detect_events_batch(nph_ctx* ctx, const float* raw, size_t n_samples_total, const nph_raw_read* reads, size_t n_reads,
                             const nph_event_params* params, nph_event* events_out, size_t events_total, uint32_t* n_events_out);
 
+/* ---- raw-signal trimming (section 8f N4: the step before event detection) --------------------------
+ * trim_and_segment_raw(rt, trim_start, trim_end, varseg_chunk, varseg_thresh) on a raw_table that starts at
+ * {start 0, end n_samples}: median absolute deviation per chunk, chunks at or below the varseg_thresh quantile of
+ * those MADs dropped from both ends, then the fixed trims.  ranges_out[i] is the surviving [start, end) relative to
+ * reads[i].sample_off; {0, 0} where the reference returns an empty table (or would trip its assert: fewer samples
+ * than one chunk, or no chunk above the threshold).  Only sample_off and n_samples of nph_raw_read are used.
+ * ref: src/thirdparty/scrappie/scrappie_common.c:9-190; call site src/nanopolish_squiggle_read.cpp:226-233
+ *      (trim_start 200, trim_end 10, varseg_chunk 100, varseg_thresh 0.0).  varseg_chunk <= 128. */
+typedef struct { uint32_t start, end; } nph_raw_range;
+int nph_trim_raw_batch(nph_ctx* ctx, const float* raw, size_t n_samples_total, const nph_raw_read* reads, size_t n_reads,
+                       int32_t trim_start, int32_t trim_end, int32_t varseg_chunk, float varseg_thresh,
+                       nph_raw_range* ranges_out);
+
+/* ---- calibration after ABEA (section 8f N4: the step between ABEA and the HMM) ---------------------
+ * For each ABEA job (same jobs[], kmer_ranks[], pairs[] and results[] as nph_abea_batch took and returned):
+ *   base_to_event_out[rank_off + ki] = SquiggleRead::base_to_event_map[ki].indices[strand]   ({-1,-1}: no events)
+ *   events_per_base                   = (max_event - min_event) / n_kmers
+ *   shift, scale, var                 = recalibrate_model(read, model, strand,
+ *                                           get_eventalignment_for_1d_basecalls(...), scale_var=true, scale_drift=false)
+ * and the QC that follows.  reads[] carries the scalings the read has before the call (the MoM estimate); they come
+ * back unchanged when the read is not recalibrated.  base_to_event_out may be NULL.
+ * ref: src/nanopolish_squiggle_read.cpp:270-336,340-391; src/nanopolish_methyltrain.cpp:204-307. */
+typedef struct { int32_t start, stop; } nph_event_range;      /* IndexPair, src/nanopolish_squiggle_read.h:32-37 */
+#define NPH_CAL_OK              0
+#define NPH_CAL_NOT_ALIGNED     1   /* ABEA returned no pairs: events cleared, events_per_base = 0 */
+#define NPH_CAL_TOO_FEW_EVENTS  2   /* fewer than 200 'M' events: not recalibrated, events cleared */
+#define NPH_CAL_HIGH_VAR        4   /* var > MIN_CALIBRATION_VAR (2.5): events cleared */
+#define NPH_CAL_TOO_MANY_STAYS  8   /* events_per_base > 5.0: events cleared */
+typedef struct {
+    double shift, scale, drift, var;   /* arguments of SquiggleScalings::set4 */
+    double events_per_base;
+    uint32_t n_used;                   /* 'M' events that entered the normal equations */
+    int32_t status;                    /* NPH_CAL_*; non-zero = the reference drops the read */
+} nph_calibration;
+int nph_recalibrate_batch(nph_ctx* ctx, const nph_read* reads, size_t n_reads, const float* ev_mean, size_t n_events_total,
+                          const uint32_t* kmer_ranks, size_t n_ranks_total, const nph_abea_job* jobs, size_t n_jobs,
+                          uint32_t model_id, const nph_aligned_pair* pairs, size_t pairs_total,
+                          const nph_abea_result* results, nph_event_range* base_to_event_out, nph_calibration* calibrations_out);
+
 /* ---- measurement hooks (used by bench.py; not part of the reference surface) ------------- */
 /* Device time in ms of the most recent nph_hmm_score / nph_abea_run kernel sequence, measured
  * with CUDA events on the context's stream (valid after a sync), and the number of kernel

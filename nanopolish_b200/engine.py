@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .synth import ABEA_RES_DT, ALIGN_STATE_DT, EVENT_DT, PAIR_DT
+from .synth import ABEA_RES_DT, ALIGN_STATE_DT, CALIBRATION_DT, EVENT_DT, EVENT_RANGE_DT, PAIR_DT, RAW_RANGE_DT
 
 
 def _p(a):
@@ -160,6 +160,23 @@ class Engine:
         self._check(self.lib.nph_detect_events_batch(self.ctx, _p(raw), raw.shape[0], _p(reads), reads.shape[0], _p(params),
                                                      _p(events), total, _p(counts)), "nph_detect_events_batch")
         return [events[int(r["event_off"]):int(r["event_off"]) + int(c)] for r, c in zip(reads, counts)]
+
+    # ---- raw trimming and post-ABEA calibration (the rest of load_from_raw) -----------------------
+    def trim_raw_batch(self, raw, reads, trim_start=200, trim_end=10, varseg_chunk=100, varseg_thresh=0.0):
+        """== trim_and_segment_raw per read: RAW_RANGE_DT[n_reads], {0,0} where nothing survives."""
+        out = np.zeros(reads.shape[0], RAW_RANGE_DT)
+        self._check(self.lib.nph_trim_raw_batch(self.ctx, _p(raw), raw.shape[0], _p(reads), reads.shape[0], trim_start, trim_end,
+                                                varseg_chunk, varseg_thresh, _p(out)), "nph_trim_raw_batch")
+        return out
+
+    def recalibrate_batch(self, reads, ev_mean, kmer_ranks, jobs, model_id, pairs, results):
+        """base_to_event_map + events_per_base + recalibrate_model per ABEA job: (EVENT_RANGE_DT[n_ranks], CALIBRATION_DT[n_jobs])."""
+        b2e = np.zeros(kmer_ranks.shape[0], EVENT_RANGE_DT)
+        cal = np.zeros(jobs.shape[0], CALIBRATION_DT)
+        self._check(self.lib.nph_recalibrate_batch(self.ctx, _p(reads), reads.shape[0], _p(ev_mean), ev_mean.shape[0], _p(kmer_ranks),
+                                                   kmer_ranks.shape[0], _p(jobs), jobs.shape[0], model_id, _p(pairs), pairs.shape[0],
+                                                   _p(results), _p(b2e), _p(cal)), "nph_recalibrate_batch")
+        return b2e, cal
 
     # ---- measurement ----------------------------------------------------------------------
     def sync(self):

@@ -44,7 +44,12 @@ EVENT_DT = np.dtype([("start", "<u8"), ("length", "<f4"), ("mean", "<f4"), ("std
 RAW_READ_DT = np.dtype([("sample_off", "<u8"), ("event_off", "<u8"), ("n_samples", "<u4"), ("event_cap", "<u4")], align=True)
 EVENT_PARAMS_DT = np.dtype([("window_length1", "<u4"), ("window_length2", "<u4"), ("threshold1", "<f4"), ("threshold2", "<f4"),
                             ("peak_height", "<f4")], align=True)
+RAW_RANGE_DT = np.dtype([("start", "<u4"), ("end", "<u4")], align=True)
+EVENT_RANGE_DT = np.dtype([("start", "<i4"), ("stop", "<i4")], align=True)
+CALIBRATION_DT = np.dtype([("shift", "<f8"), ("scale", "<f8"), ("drift", "<f8"), ("var", "<f8"), ("events_per_base", "<f8"),
+                           ("n_used", "<u4"), ("status", "<i4")], align=True)
 assert EVENT_DT.itemsize == 24 and RAW_READ_DT.itemsize == 24 and EVENT_PARAMS_DT.itemsize == 20
+assert RAW_RANGE_DT.itemsize == 8 and EVENT_RANGE_DT.itemsize == 8 and CALIBRATION_DT.itemsize == 48
 assert ALIGN_STATE_DT.itemsize == 16
 assert READ_DT.itemsize == 64 and HMM_JOB_DT.itemsize == 32 and ABEA_JOB_DT.itemsize == 32
 assert PAIR_DT.itemsize == 8 and ABEA_RES_DT.itemsize == 24

@@ -660,6 +660,174 @@ long long npo_detect_events(const float* raw, size_t n, const nph_event_params* 
     return ret;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * trim_and_segment_raw -> trim_raw_by_mad, medianf/madf/quantilef.
+ * ref: src/thirdparty/scrappie/scrappie_common.c:9-190 (pinned against the compiled reference in
+ * tests/test_oracle_vs_ref.py).  Returns 1 and the surviving [start, end) or 0 where the reference returns an empty
+ * table or trips its own assert.
+ * ---------------------------------------------------------------------------------------- */
+static int npo_floatcmp(const void* x, const void* y)
+{
+    float d = *(const float*)x - *(const float*)y;
+    return d > 0 ? 1 : -1;
+}
+
+static float npo_quantilef(const float* x, size_t nx, float p, float* space)
+{
+    memcpy(space, x, nx * sizeof(float));
+    qsort(space, nx, sizeof(float), npo_floatcmp);
+    const size_t idx = p * (nx - 1);
+    const float remf = p * (nx - 1) - idx;
+    float out;
+    if (idx < nx - 1) out = (1.0 - remf) * space[idx] + remf * space[idx + 1];
+    else out = space[idx];
+    return out;
+}
+
+static float npo_madf(const float* x, size_t n, float* space, float* absdiff)
+{
+    const float mad_scaling_factor = 1.4826;
+    if (n == 1) return 0.0f;
+    const float med = npo_quantilef(x, n, 0.5f, space);
+    for (size_t i = 0; i < n; ++i) absdiff[i] = fabsf(x[i] - med);
+    const float mad = npo_quantilef(absdiff, n, 0.5f, space);
+    return mad * mad_scaling_factor;
+}
+
+int npo_trim_raw(const float* raw, size_t n, int trim_start, int trim_end, int varseg_chunk, float varseg_thresh,
+                 uint32_t* start_out, uint32_t* end_out)
+{
+    *start_out = 0; *end_out = 0;
+    const size_t chunk = (size_t)varseg_chunk;
+    const size_t nchunk = n / chunk;
+    if (nchunk == 0) return 0;
+    size_t start = 0, end = nchunk * chunk;
+    float* madarr = (float*)malloc(nchunk * sizeof(float));
+    float* space = (float*)malloc((nchunk > chunk ? nchunk : chunk) * sizeof(float));
+    float* absdiff = (float*)malloc(chunk * sizeof(float));
+    for (size_t i = 0; i < nchunk; ++i) madarr[i] = npo_madf(raw + i * chunk, chunk, space, absdiff);
+    const float thresh = npo_quantilef(madarr, nchunk, varseg_thresh, space);
+    for (size_t i = 0; i < nchunk; ++i) { if (madarr[i] > thresh) break; start += chunk; }
+    for (size_t i = nchunk; i > 0; --i) { if (madarr[i - 1] > thresh) break; end -= chunk; }
+    free(madarr); free(space); free(absdiff);
+    if (!(end > start)) return 0;                /* assert(rt.end > rt.start) */
+    start += (size_t)trim_start;
+    if (end < (size_t)trim_end) return 0;
+    end -= (size_t)trim_end;
+    if (start >= end) return 0;
+    *start_out = (uint32_t)start; *end_out = (uint32_t)end;
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * The tail of SquiggleRead::load_from_raw after ABEA: base_to_event_map + events_per_base
+ * (src/nanopolish_squiggle_read.cpp:273-302), get_eventalignment_for_1d_basecalls (:340-391), recalibrate_model with
+ * scale_var = true, scale_drift = false (src/nanopolish_methyltrain.cpp:204-307) and the QC (:319-336).
+ * PARITY UNPINNED for this function: squiggle_read.cpp / methyltrain.cpp need HDF5 and Eigen 3.3.7 (Makefile:59),
+ * neither present, so the reference cannot be compiled here.  The solve restates Eigen's FullPivLU for a 2x2 system
+ * (largest-entry pivot by row+column swap, rank threshold epsilon*2*maxpivot, unit-lower / upper substitution).
+ * ---------------------------------------------------------------------------------------- */
+static void npo_full_piv_lu_solve_2x2(double a00, double a01, double a11, double b0, double b1, double* x0, double* x1)
+{
+    double m[2][2] = {{a00, a01}, {a01, a11}};
+    double b[2] = {b0, b1};
+    int pr = 0, pc = 0;
+    double big = fabs(m[0][0]);
+    if (fabs(m[1][0]) > big) { big = fabs(m[1][0]); pr = 1; pc = 0; }       /* column-major scan, first maximum wins */
+    if (fabs(m[0][1]) > big) { big = fabs(m[0][1]); pr = 0; pc = 1; }
+    if (fabs(m[1][1]) > big) { big = fabs(m[1][1]); pr = 1; pc = 1; }
+    *x0 = 0.0; *x1 = 0.0;
+    if (big == 0.0) return;
+    double t;
+    if (pr == 1) { t = m[0][0]; m[0][0] = m[1][0]; m[1][0] = t; t = m[0][1]; m[0][1] = m[1][1]; m[1][1] = t; t = b[0]; b[0] = b[1]; b[1] = t; }
+    if (pc == 1) { t = m[0][0]; m[0][0] = m[0][1]; m[0][1] = t; t = m[1][0]; m[1][0] = m[1][1]; m[1][1] = t; }
+    const double l = m[1][0] / m[0][0];
+    const double u11 = m[1][1] - l * m[0][1];
+    const double c1 = b[1] - l * b[0];
+    double maxpivot = big;
+    if (fabs(u11) > maxpivot) maxpivot = fabs(u11);
+    const double thr = 2.220446049250313e-16 * 2.0 * maxpivot;
+    double y0, y1;
+    if (fabs(u11) > thr) { y1 = c1 / u11; y0 = (b[0] - y1 * m[0][1]) / m[0][0]; }
+    else { y1 = 0.0; y0 = b[0] / m[0][0]; }
+    if (pc == 1) { *x0 = y1; *x1 = y0; } else { *x0 = y0; *x1 = y1; }
+}
+
+void npo_recalibrate(const nph_read* reads, const float* ev_mean, const npo_model* model, const uint32_t* kmer_ranks,
+                     const nph_abea_job* job, const nph_aligned_pair* pairs, uint32_t n_pairs,
+                     nph_event_range* b2e /* n_kmers */, nph_calibration* out)
+{
+    const nph_read* read = &reads[job->read];
+    const float* m = ev_mean + read->event_off;
+    const uint32_t* ranks = kmer_ranks + job->rank_off;
+    const size_t n_kmers = job->n_kmers;
+    const nph_aligned_pair* pr = pairs + job->pairs_off;
+    out->shift = read->shift; out->scale = read->scale; out->drift = read->drift; out->var = read->var;
+    out->events_per_base = 0.0; out->n_used = 0; out->status = NPH_CAL_OK;
+    for (size_t k = 0; k < n_kmers; ++k) { b2e[k].start = -1; b2e[k].stop = -1; }
+    if (n_pairs == 0) { out->status = NPH_CAL_NOT_ALIGNED; return; }
+
+    size_t max_event = 0, min_event = (size_t)-1, prev_event_idx = (size_t)-1;
+    for (size_t i = 0; i < n_pairs; ++i) {
+        size_t k_idx = (size_t)pr[i].ref_pos, event_idx = (size_t)pr[i].read_pos;
+        if (event_idx != prev_event_idx) {
+            if (b2e[k_idx].start == -1) b2e[k_idx].start = (int32_t)event_idx;
+            b2e[k_idx].stop = (int32_t)event_idx;
+        }
+        if (event_idx > max_event) max_event = event_idx;
+        if (event_idx < min_event) min_event = event_idx;
+        prev_event_idx = event_idx;
+    }
+    out->events_per_base = (double)(max_event - min_event) / n_kmers;
+
+    /* 'M' events of get_eventalignment_for_1d_basecalls, gathered as recalibrate_model does */
+    double* raw_events = (double*)malloc(n_kmers * sizeof(double));
+    double* level_means = (double*)malloc(n_kmers * sizeof(double));
+    double* level_stdvs = (double*)malloc(n_kmers * sizeof(double));
+    size_t n = 0, prev_kmer_rank = (size_t)-1;
+    for (size_t ki = 0; ki < n_kmers; ++ki) {
+        if (b2e[ki].start == -1) continue;
+        for (size_t event_idx = (size_t)b2e[ki].start; event_idx <= (size_t)b2e[ki].stop; ++event_idx) {
+            size_t kmer_rank = ranks[ki];
+            if (prev_kmer_rank != kmer_rank) {
+                raw_events[n] = m[event_idx];
+                level_means[n] = model->level_mean[kmer_rank];
+                level_stdvs[n] = model->level_stdv[kmer_rank];
+                ++n;
+            }
+            prev_kmer_rank = kmer_rank;
+        }
+    }
+    out->n_used = (uint32_t)n;
+    if (n >= 200) {
+        double A00 = 0., A01 = 0., A11 = 0., B0 = 0., B1 = 0.;
+        for (size_t i = 0; i < n; ++i) {
+            double inv_var = 1. / (level_stdvs[i] * level_stdvs[i]);
+            double mu = level_means[i];
+            double e = raw_events[i];
+            A00 += inv_var; A01 += mu * inv_var;
+            A11 += mu * mu * inv_var;
+            B0 += e * inv_var;
+            B1 += mu * e * inv_var;
+        }
+        double shift, scale;
+        npo_full_piv_lu_solve_2x2(A00, A01, A11, B0, B1, &shift, &scale);
+        double var = 0.;
+        for (size_t i = 0; i < n; ++i) {
+            double yi = (raw_events[i] - shift - scale * level_means[i]);
+            var += yi * yi / (level_stdvs[i] * level_stdvs[i]);
+        }
+        var /= n;
+        var = sqrt(var);
+        out->shift = shift; out->scale = scale; out->drift = 0.0; out->var = var;
+        if (var > 2.5) out->status |= NPH_CAL_HIGH_VAR;
+        else if (out->events_per_base > 5.0) out->status |= NPH_CAL_TOO_MANY_STAYS;
+    } else {
+        out->status = NPH_CAL_TOO_FEW_EVENTS;
+    }
+    free(raw_events); free(level_means); free(level_stdvs);
+}
+
 int npo_max_threads(void)
 {
 #ifdef _OPENMP

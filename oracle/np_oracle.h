@@ -52,6 +52,11 @@ double npo_abea_batch(const nph_read* reads, const float* ev_mean, const double*
 void npo_mom(const nph_read* reads, const float* ev_mean, const npo_model* model,
              const uint32_t* kmer_ranks, const nph_abea_job* job, double* shift_out, double* scale_out);
 long long npo_detect_events(const float* raw, size_t n, const nph_event_params* prm, nph_event* out, size_t cap);
+int npo_trim_raw(const float* raw, size_t n, int trim_start, int trim_end, int varseg_chunk, float varseg_thresh,
+                 uint32_t* start_out, uint32_t* end_out);
+void npo_recalibrate(const nph_read* reads, const float* ev_mean, const npo_model* model, const uint32_t* kmer_ranks,
+                     const nph_abea_job* job, const nph_aligned_pair* pairs, uint32_t n_pairs,
+                     nph_event_range* b2e, nph_calibration* out);
 int npo_max_threads(void);
 
 #ifdef __cplusplus

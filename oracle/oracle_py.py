@@ -135,6 +135,21 @@ class PortOracle:
         n = self.lib.npo_detect_events(_p(raw), C.c_size_t(raw.shape[0]), _p(params), _p(out), C.c_size_t(out.shape[0]))
         return out[:n].copy()
 
+    def trim_raw(self, raw, trim_start=200, trim_end=10, varseg_chunk=100, varseg_thresh=0.0):
+        s, e = C.c_uint32(), C.c_uint32()
+        ok = self.lib.npo_trim_raw(_p(raw), C.c_size_t(raw.shape[0]), C.c_int(trim_start), C.c_int(trim_end), C.c_int(varseg_chunk),
+                                   C.c_float(varseg_thresh), C.byref(s), C.byref(e))
+        return int(ok), s.value, e.value
+
+    def recalibrate(self, reads, ev_mean, model, kmer_ranks, job, pairs, n_pairs):
+        from nanopolish_b200.synth import EVENT_RANGE_DT, CALIBRATION_DT
+        marr = self.models([model])
+        jb = np.array([job], dtype=job.dtype)
+        b2e = np.zeros(int(job["n_kmers"]), EVENT_RANGE_DT)
+        cal = np.zeros(1, CALIBRATION_DT)
+        self.lib.npo_recalibrate(_p(reads), _p(ev_mean), marr, _p(kmer_ranks), _p(jb), _p(pairs), C.c_uint32(int(n_pairs)), _p(b2e), _p(cal))
+        return b2e, cal[0]
+
     def max_threads(self):
         return int(self.lib.npo_max_threads())
 
@@ -253,6 +268,12 @@ class RefOracle:
         self.lib.npref_detect_events.restype = C.c_longlong
         ne = self.lib.npref_detect_events(_p(raw), C.c_size_t(n), int(rna), _p(start), _p(length), _p(mean), _p(stdv), C.c_size_t(n + 1))
         return start[:ne], length[:ne], mean[:ne], stdv[:ne]
+
+    def trim_raw(self, raw, trim_start=200, trim_end=10, varseg_chunk=100, varseg_thresh=0.0):
+        s, e = C.c_uint32(), C.c_uint32()
+        ok = self.lib.npref_trim_raw(_p(raw), C.c_size_t(raw.shape[0]), C.c_int(trim_start), C.c_int(trim_end), C.c_int(varseg_chunk),
+                                     C.c_float(varseg_thresh), C.byref(s), C.byref(e))
+        return int(ok), s.value, e.value
 
     def mom(self, read_h, model_h, seq: bytes):
         out = np.zeros(4)

@@ -295,6 +295,23 @@ long long npref_detect_events(const float* raw, size_t n, int rna, uint64_t* sta
     return ne;
 }
 
+// trim_and_segment_raw (src/thirdparty/scrappie/scrappie_common.c:122-138) on a table covering the whole signal.
+// The function frees rt.raw when nothing survives, so it gets its own copy.  Signals for which the reference would
+// trip its own assert (fewer samples than a chunk, no chunk above the threshold) must not be passed.
+int npref_trim_raw(const float* raw, size_t n, int trim_start, int trim_end, int varseg_chunk, float varseg_thresh,
+                   uint32_t* start_out, uint32_t* end_out)
+{
+    raw_table rt;
+    rt.n = n; rt.start = 0; rt.end = n;
+    rt.raw = (float*)malloc(n * sizeof(float));
+    memcpy(rt.raw, raw, n * sizeof(float));
+    rt = trim_and_segment_raw(rt, trim_start, trim_end, varseg_chunk, varseg_thresh);
+    if (rt.raw == NULL) { *start_out = 0; *end_out = 0; return 0; }
+    *start_out = (uint32_t)rt.start; *end_out = (uint32_t)rt.end;
+    free(rt.raw);
+    return 1;
+}
+
 int npref_max_threads(void) { return omp_get_max_threads(); }
 
 } // extern "C"

@@ -1,0 +1,169 @@
+"""Parity of the remaining load_from_raw steps on the device — raw trimming before event detection and calibration
+after ABEA — with the oracle, through the C ABI.  Integer outputs (ranges, event maps, counts,
+statuses) must be identical; the FP64 calibration is summed in the reference's order, so it is compared bit for bit."""
+import numpy as np
+import pytest
+
+from nanopolish_b200 import synth
+from nanopolish_b200._lib import NphError
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nuc(engine):
+    m = synth.load_model("nucleotide")
+    return m, engine.model_upload(m)
+
+
+def _stalled(model, seed, n, leader=0, tail=0):
+    raw, reads = synth.gen_raw(1, n, model, seed=seed)
+    x = raw[:int(reads[0]["n_samples"])]
+    return np.concatenate([np.full(leader, 210.0, np.float32), x, np.full(tail, 95.5, np.float32)]).astype(np.float32)
+
+
+def _pack(signals):
+    reads = np.zeros(len(signals), synth.RAW_READ_DT)
+    off = 0
+    for i, x in enumerate(signals):
+        reads[i] = (off, 0, x.shape[0], 0)
+        off += x.shape[0]
+    return np.concatenate(signals), reads
+
+
+@pytest.mark.parametrize("perc,chunk", [(0.0, 100), (0.0, 64), (0.3, 100), (0.77, 37), (1.0, 100), (0.5, 128), (0.0, 2)])
+def test_trim_ranges_identical(engine, nuc, port_oracle, perc, chunk):
+    model, _ = nuc
+    signals = [_stalled(model, 5, 12000), _stalled(model, 6, 9000, leader=730), _stalled(model, 7, 9037, leader=300, tail=1250),
+               _stalled(model, 8, 150, leader=100), _stalled(model, 9, 260), _stalled(model, 10, 36000, leader=1100, tail=100),
+               _stalled(model, 11, 57), np.full(1000, 80.0, np.float32)]        # shorter than a chunk; perfectly flat
+    raw, reads = _pack(signals)
+    got = engine.trim_raw_batch(raw, reads, 200, 10, chunk, perc)
+    n_ok = 0
+    for i, x in enumerate(signals):
+        ok, s, e = port_oracle.trim_raw(x, 200, 10, chunk, perc)
+        assert (int(got[i]["start"]), int(got[i]["end"])) == (s, e), f"signal {i}"
+        n_ok += ok
+    assert n_ok >= (0 if perc == 1.0 else 4)
+    assert int(got[7]["end"]) == 0          # flat signal: every MAD equals the threshold, nothing survives
+
+
+def test_trim_rejects_what_the_reference_asserts(engine, nuc):
+    model, _ = nuc
+    raw, reads = _pack([_stalled(model, 5, 3000)])
+    for args in [(200, 10, 1, 0.0), (200, 10, 100, 1.5), (200, 10, 100, -0.1)]:
+        with pytest.raises(NphError):
+            engine.trim_raw_batch(raw, reads, *args)
+    with pytest.raises(NphError):
+        engine.trim_raw_batch(raw, reads, 200, 10, 500, 0.0)       # chunk above what a warp holds: unsupported, not wrong
+
+
+def _check_cal(engine, port_oracle, model, mid, rs, jobs, ranks, pairs, res):
+    b2e, cal = engine.recalibrate_batch(rs.reads, rs.ev_mean, ranks, jobs, mid, pairs, res)
+    for j in range(jobs.shape[0]):
+        wb, wc = port_oracle.recalibrate(rs.reads, rs.ev_mean, model, ranks, jobs[j], pairs, int(res[j]["n_pairs"]))
+        o, nk = int(jobs[j]["rank_off"]), int(jobs[j]["n_kmers"])
+        assert np.array_equal(b2e[o:o + nk], wb), f"job {j}: base_to_event_map differs"
+        assert int(cal[j]["n_used"]) == int(wc["n_used"]) and int(cal[j]["status"]) == int(wc["status"]), f"job {j}"
+        for f in ("shift", "scale", "drift", "var", "events_per_base"):
+            assert np.float64(cal[j][f]).view(np.uint64) == np.float64(wc[f]).view(np.uint64), f"job {j}: {f} {cal[j][f]!r} != {wc[f]!r}"
+    return b2e, cal
+
+
+@pytest.mark.parametrize("n_events,n_reads", [(4000, 6), (900, 8), (250, 12), (8000, 2)])
+def test_calibration_after_abea_identical(engine, nuc, port_oracle, n_events, n_reads):
+    model, mid = nuc
+    rs = synth.gen_reads(n_reads, n_events, model, seed=8100 + n_events, rng_scalings=True)
+    jobs, ranks, total = synth.abea_jobs(rs)
+    pairs, res = engine.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ranks, jobs, mid, total)
+    _, cal = _check_cal(engine, port_oracle, model, mid, rs, jobs, ranks, pairs, res)
+    if n_events >= 900:
+        assert (cal["status"] == 0).all() and (cal["n_used"] >= 200).all()
+        assert np.abs(cal["shift"] - rs.reads["shift"]).max() < 2.5 and np.abs(cal["scale"] - rs.reads["scale"]).max() < 0.03
+    else:
+        assert (cal["status"] == 2).all()                 # fewer than 200 'M' events: left uncalibrated
+        assert np.array_equal(cal["shift"], rs.reads["shift"]) and np.array_equal(cal["var"], rs.reads["var"])
+
+
+def test_calibration_homopolymers_failed_reads_and_odd_pair_lists(engine, nuc, port_oracle):
+    model, mid = nuc
+    # long homopolymer runs: consecutive k-mers share a rank, so only the first of a run is an 'M' event
+    rng = np.random.default_rng(3)
+    codes = rng.integers(0, 4, 1500, dtype=np.uint8)
+    for s in range(40, 1400, 97):
+        codes[s:s + 14] = codes[s]
+    rs = synth.gen_reads_from_sequence(codes, 5, model, seed=12)
+    jobs, ranks, total = synth.abea_jobs(rs)
+    pairs, res = engine.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ranks, jobs, mid, total)
+    assert (res["n_pairs"] > 0).all()
+    # read 1: pretend ABEA failed; read 2: a hand-made list with repeated events, gaps and an out-of-order tail
+    res = res.copy(); pairs = pairs.copy()
+    res[1]["n_pairs"] = 0
+    o = int(jobs[2]["pairs_off"])
+    hand = [(0, 0), (0, 1), (1, 1), (2, 1), (2, 2), (2, 2), (5, 9), (5, 7), (4, 8), (4, 8), (6, 3)]
+    pairs[o:o + len(hand)] = np.array(hand, synth.PAIR_DT)
+    res[2]["n_pairs"] = len(hand)
+    # read 3: noise instead of signal, so the fit's residual variance is far above 2.5
+    e0, ne = int(rs.reads[3]["event_off"]), int(rs.reads[3]["n_events"])
+    ev = rs.ev_mean.copy()
+    ev[e0:e0 + ne] = rng.uniform(60.0, 130.0, ne).astype(np.float32)
+    rs2 = synth.ReadSet(rs.reads, ev, rs.ev_start_time, rs.seq_codes, rs.ev_kmer, rs.kmer_first_event, rs.k)
+    _, cal = _check_cal(engine, port_oracle, model, mid, rs2, jobs, ranks, pairs, res)
+    assert int(cal[1]["status"]) == 1 and cal[1]["events_per_base"] == 0.0
+    assert int(cal[2]["status"]) == 2 and int(cal[2]["n_used"]) < 10
+    assert int(cal[3]["status"]) == 4 and cal[3]["var"] > 2.5
+    assert int(cal[0]["status"]) == 0 and int(cal[0]["n_used"]) < int(jobs[0]["n_kmers"]) - 100   # homopolymer runs collapsed
+    # a pair outside the read is refused
+    bad = pairs.copy(); bad[int(jobs[0]["pairs_off"]) + 3]["read_pos"] = 10 ** 6
+    with pytest.raises(NphError):
+        engine.recalibrate_batch(rs2.reads, rs2.ev_mean, ranks, jobs, mid, bad, res)
+
+
+def test_raw_to_calibrated_read_chain(engine, nuc, port_oracle):
+    """trim -> detect_events -> MoM -> ABEA -> calibration on the device vs the same chain through the oracle: the
+    order SquiggleRead::load_from_raw runs them in (src/nanopolish_squiggle_read.cpp:226-336)."""
+    model, mid = nuc
+    n_reads, sample_rate = 4, 4000.0
+    raw, rreads = synth.gen_raw(n_reads, 30000, model, seed=501)
+    prm = synth.event_params(False)
+    rng = engine.trim_raw_batch(raw, rreads)
+    trimmed = rreads.copy()
+    for i in range(n_reads):
+        ok, s, e = port_oracle.trim_raw(raw[int(rreads[i]["sample_off"]):][:int(rreads[i]["n_samples"])])
+        assert ok and (int(rng[i]["start"]), int(rng[i]["end"])) == (s, e)
+        trimmed[i]["sample_off"] += s
+        trimmed[i]["n_samples"] = e - s
+    events = engine.detect_events_batch(raw, trimmed, prm)
+    # SquiggleEvent conversion (squiggle_read.cpp:243-250): float duration, double running start time
+    reads = np.zeros(n_reads, synth.READ_DT)
+    means, times = [], []
+    off = 0
+    for i, ev in enumerate(events):
+        want = port_oracle.detect_events(np.ascontiguousarray(raw[int(trimmed[i]["sample_off"]):][:int(trimmed[i]["n_samples"])]), prm)
+        assert np.array_equal(ev, want) and ev.shape[0] > 1000
+        dur = (ev["length"].astype(np.float64) / sample_rate).astype(np.float32)
+        t = np.concatenate([[0.0], np.cumsum(dur.astype(np.float64))[:-1]])
+        reads[i] = (off, ev.shape[0], 0, 1.0, 0.0, 0.0, 1.0, 0.0, 0.0)
+        means.append(ev["mean"]); times.append(t); off += ev.shape[0]
+    ev_mean, ev_time = np.concatenate(means), np.concatenate(times)
+    # the basecalled sequence: here the true one (gen_raw draws it from the same seed)
+    seqs = []
+    for r in range(n_reads):
+        g = np.random.default_rng(501 + r)
+        nk = int(30000 / 9.0 * 1.3) + 16
+        codes = g.integers(0, 4, nk + model.k - 1, dtype=np.uint8)
+        dwell = np.maximum(1, g.geometric(1.0 / 9.0, nk))
+        used = int(np.searchsorted(np.cumsum(dwell), int(rreads[r]["n_samples"]))) + 1
+        seqs.append(codes[:used + model.k - 1])
+    rs = synth.ReadSet(reads, ev_mean, ev_time, seqs, [None] * n_reads, [None] * n_reads, model.k)
+    jobs, ranks, total = synth.abea_jobs(rs)
+    ss = engine.mom_batch(rs.reads, rs.ev_mean, ranks, jobs, mid)
+    for i in range(n_reads):
+        assert tuple(ss[i]) == port_oracle.mom(rs.reads, rs.ev_mean, model, ranks, jobs[i])
+        reads[i]["shift"], reads[i]["scale"] = ss[i][0], ss[i][1]
+    pairs, res = engine.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ranks, jobs, mid, total)
+    po, ro, _ = port_oracle.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, model, ranks, jobs, total, threads=4)
+    assert np.array_equal(res["n_pairs"], ro["n_pairs"]) and (res["n_pairs"] > 0).all()
+    _, cal = _check_cal(engine, port_oracle, model, mid, rs, jobs, ranks, pairs, res)
+    assert (cal["status"] == 0).all()
+    assert np.abs(cal["scale"] - 1.0).max() < 0.06 and np.abs(cal["shift"]).max() < 6.0 and (cal["var"] < 2.0).all()

@@ -143,3 +143,73 @@ def test_event_detection_identical(port_oracle, ref_oracle, rna):
     # (a signal without any peak makes the reference read peaks[-1]: undefined there, one whole-signal event here)
     ev = port_oracle.detect_events(raw[:5].copy(), prm)
     assert ev.shape[0] == 1 and ev["start"][0] == 0 and ev["length"][0] == 5.0
+
+
+def _raw_with_stalls(seed, n, leader=0, tail=0):
+    """A synthetic trace with an optional constant (ADC-flat, MAD exactly 0) leader and tail, as a stalled pore gives."""
+    nuc = synth.load_model("nucleotide")
+    raw, reads = synth.gen_raw(1, n, nuc, seed=seed)
+    x = raw[:int(reads[0]["n_samples"])]
+    return np.concatenate([np.full(leader, 210.0, np.float32), x, np.full(tail, 95.5, np.float32)]).astype(np.float32)
+
+
+@pytest.mark.parametrize("perc,chunk", [(0.0, 100), (0.0, 64), (0.3, 100), (0.77, 37), (1.0, 100)])
+def test_trim_and_segment_raw_identical(port_oracle, ref_oracle, perc, chunk):
+    """scrappie trim_and_segment_raw (compiled C) vs the restatement: same surviving range, including the quantile
+    interpolation of the MAD threshold and the flat-leader case the default perc 0.0 actually trims."""
+    cases = [_raw_with_stalls(5, 12000), _raw_with_stalls(6, 9000, leader=730), _raw_with_stalls(7, 9037, leader=300, tail=1250),
+             _raw_with_stalls(8, 150, leader=100), _raw_with_stalls(9, 260)]
+    seen_trim = False
+    for x in cases:
+        if perc == 1.0:
+            # no chunk exceeds the maximum MAD: the reference asserts; the port reports "nothing survives"
+            assert port_oracle.trim_raw(x, 200, 10, chunk, perc)[0] == 0
+            continue
+        want = ref_oracle.trim_raw(x, 200, 10, chunk, perc)
+        got = port_oracle.trim_raw(x, 200, 10, chunk, perc)
+        assert want == got
+        seen_trim |= want[0] == 1 and want[1] > 200
+    if perc != 1.0:
+        assert seen_trim
+
+
+def test_recalibrate_port_solves_the_weighted_least_squares(port_oracle):
+    """recalibrate_model cannot be compiled here (Eigen, HDF5), so the restatement is checked against what the function
+    is defined to compute: the weighted least-squares fit of event level on model level over the 'M' events."""
+    model = synth.load_model("nucleotide")
+    rs = synth.gen_reads(3, 1500, model, seed=31, rng_scalings=True)
+    jobs, ranks, total = synth.abea_jobs(rs)
+    pairs, res, _ = port_oracle.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, model, ranks, jobs, total)
+    for j in range(jobs.shape[0]):
+        n = int(res[j]["n_pairs"])
+        assert n > 0
+        b2e, cal = port_oracle.recalibrate(rs.reads, rs.ev_mean, model, ranks, jobs[j], pairs, n)
+        pr = pairs[int(jobs[j]["pairs_off"]):int(jobs[j]["pairs_off"]) + n]
+        rk = ranks[int(jobs[j]["rank_off"]):int(jobs[j]["rank_off"]) + int(jobs[j]["n_kmers"])]
+        ev = rs.ev_mean[int(rs.reads[j]["event_off"]):][:int(rs.reads[j]["n_events"])]
+        # independent restatement of the bookkeeping
+        first = {}
+        prev = -1
+        for k, e in zip(pr["ref_pos"], pr["read_pos"]):
+            if e != prev:
+                first.setdefault(int(k), [int(e), int(e)])[1] = int(e)
+            prev = e
+        for k in range(rk.shape[0]):
+            assert (int(b2e[k]["start"]), int(b2e[k]["stop"])) == tuple(first.get(k, (-1, -1)))
+        sel, prev_rank = [], -1
+        for k in sorted(first):
+            if rk[k] != prev_rank:
+                sel.append((k, first[k][0]))
+            prev_rank = rk[k]
+        assert int(cal["n_used"]) == len(sel) >= 200
+        mu = model.level_mean[rk[[k for k, _ in sel]]]; sd = model.level_stdv[rk[[k for k, _ in sel]]]
+        e = ev[[i for _, i in sel]].astype(np.float64)
+        w = 1.0 / sd ** 2
+        A = np.array([[w.sum(), (mu * w).sum()], [(mu * w).sum(), (mu * mu * w).sum()]])
+        shift, scale = np.linalg.solve(A, np.array([(e * w).sum(), (mu * e * w).sum()]))
+        var = np.sqrt((((e - shift - scale * mu) / sd) ** 2).mean())
+        assert abs(cal["shift"] - shift) < 1e-8 and abs(cal["scale"] - scale) < 1e-10 and abs(cal["var"] - var) < 1e-10
+        assert cal["drift"] == 0.0 and int(cal["status"]) == 0
+        assert cal["events_per_base"] == (int(pr["read_pos"].max()) - int(pr["read_pos"].min())) / rk.shape[0]
+        # recovered scalings are close to the ones the read was simulated with
+        assert abs(cal["shift"] - rs.reads[j]["shift"]) < 1.5 and abs(cal["scale"] - rs.reads[j]["scale"]) < 0.02
