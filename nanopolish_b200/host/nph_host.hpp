@@ -147,6 +147,14 @@ struct GaussianParameters {
 
 enum PoreType { PORETYPE_R7 = 0, PORETYPE_R9 = 1 };
 
+// ref: src/nanopolish_squiggle_read.h:32-46
+struct IndexPair {
+    int32_t start = -1, stop = -1;      // inclusive
+    IndexPair() {}
+    IndexPair(int32_t a, int32_t b) : start(a), stop(b) {}
+};
+struct EventRangeForBase { IndexPair indices[2]; };
+
 class SquiggleRead {
 public:
     SquiggleRead() { base_model[0] = base_model[1] = nullptr; events_per_base[0] = events_per_base[1] = 0.0; }
@@ -194,6 +202,8 @@ public:
     const PoreModel* base_model[2];
     std::map<std::string, const PoreModel*> alt_models[2];   // alphabet name -> model (cpg, dam, ...)
     double events_per_base[2];
+    std::vector<EventRangeForBase> base_to_event_map;       // filled by nph::load_from_raw (nph_raw.hpp)
+    double sample_rate = 0.0;
 };
 
 // ---------------------------------------------------------------------------------------------

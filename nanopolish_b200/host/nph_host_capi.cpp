@@ -3,6 +3,7 @@
 #include "nph_host.hpp"
 #include "nph_variants.hpp"
 #include "nph_methylation.hpp"
+#include "nph_raw.hpp"
 #include <cstring>
 #include <memory>
 
@@ -255,6 +256,48 @@ long long nphh_call_methylation(int n_reads, const int32_t* read, const char** r
         n = (long long)all.size();
     });
     return st ? st : n;
+}
+
+// ---- N4: load_from_raw over a batch -----------------------------------------------------------
+// seqs: concatenated basecalled sequences (seq_off has n+1 entries); samples likewise.  Outputs per read: n_events
+// (0 = failed), {shift, scale, drift, var, events_per_base} in scal5, and — into the flat arrays at ev_off[i] (room =
+// n_samples/2 + 8 per read) — mean, stdv, start_time, duration.  b2e_out (optional): n_kmers IndexPairs per read at
+// seq_off[i] (room = sequence length).  Returns the reads in g_reads (first handle) or a negative status.
+int nphh_load_from_raw(int model, int n, const float* samples, const uint64_t* sample_off, const char* seqs, const uint64_t* seq_off,
+                       double sample_rate, uint32_t* n_events, double* scal5, const uint64_t* ev_off, float* mean, float* stdv,
+                       double* start_time, float* duration, int32_t* b2e_out, uint64_t* stats5)
+{
+    int first = -1;
+    int rc = guard([&] {
+        std::vector<RawRead> raw(n);
+        for (int i = 0; i < n; ++i) {
+            raw[i].read_name = "read" + std::to_string(i);
+            raw[i].read_sequence.assign(seqs + seq_off[i], seqs + seq_off[i + 1]);
+            raw[i].samples.assign(samples + sample_off[i], samples + sample_off[i + 1]);
+            raw[i].sample_rate = sample_rate;
+        }
+        LoadFromRawStats st;
+        std::vector<std::unique_ptr<SquiggleRead>> rs = load_from_raw(Engine::thread_default(), *g_models[model], raw, &st);
+        stats5[0] = st.total; stats5[1] = st.empty_after_trim; stats5[2] = st.failed_alignment; stats5[3] = st.failed_calibration; stats5[4] = st.qc_fail;
+        first = (int)g_reads.size();
+        for (int i = 0; i < n; ++i) {
+            SquiggleRead& sr = *rs[i];
+            n_events[i] = (uint32_t)sr.events[0].size();
+            const SquiggleScalings& s = sr.scalings[0];
+            scal5[5 * i] = s.shift; scal5[5 * i + 1] = s.scale; scal5[5 * i + 2] = s.drift; scal5[5 * i + 3] = s.var; scal5[5 * i + 4] = sr.events_per_base[0];
+            for (size_t e = 0; e < sr.events[0].size(); ++e) {
+                const SquiggleEvent& ev = sr.events[0][e];
+                mean[ev_off[i] + e] = ev.mean; stdv[ev_off[i] + e] = ev.stdv; start_time[ev_off[i] + e] = ev.start_time; duration[ev_off[i] + e] = ev.duration;
+            }
+            if (b2e_out)
+                for (size_t kk = 0; kk < sr.base_to_event_map.size(); ++kk) {
+                    b2e_out[2 * (seq_off[i] + kk)] = sr.base_to_event_map[kk].indices[0].start;
+                    b2e_out[2 * (seq_off[i] + kk) + 1] = sr.base_to_event_map[kk].indices[0].stop;
+                }
+            g_reads.push_back(std::move(rs[i]));
+        }
+    });
+    return rc ? rc : first;
 }
 
 } // extern "C"

@@ -381,17 +381,22 @@ def event_params(rna: bool = False) -> np.ndarray:
     return p
 
 
-def gen_raw(n_reads: int, n_samples: int, model: PoreModel, seed: int = 42, mean_dwell: float = 9.0):
+def gen_raw(n_reads: int, n_samples: int, model: PoreModel, seed: int = 42, mean_dwell: float = 9.0, return_seqs: bool = False):
     """Synthetic raw current traces (picoamps, float32): a random sequence's k-mer levels held for a geometric dwell
-    (mean ~9 samples at 4 kHz / 450 bases/s) plus Gaussian noise.  Returns (raw f32[total], RAW_READ_DT[n_reads])."""
+    (mean ~9 samples at 4 kHz / 450 bases/s) plus Gaussian noise.  Returns (raw f32[total], RAW_READ_DT[n_reads]) and,
+    with return_seqs, the base codes of the stretch of sequence each trace covers (its "basecall")."""
     reads = np.zeros(n_reads, RAW_READ_DT)
     chunks = []
+    seqs = []
     soff = eoff = 0
     for r in range(n_reads):
         rng = np.random.default_rng(seed + r)
         nk = int(n_samples / mean_dwell * 1.3) + 16
-        ranks = kmer_ranks_from_codes(rng.integers(0, 4, nk + model.k - 1, dtype=np.uint8), model.k, 4)
+        codes = rng.integers(0, 4, nk + model.k - 1, dtype=np.uint8)
+        ranks = kmer_ranks_from_codes(codes, model.k, 4)
         dwell = np.maximum(1, rng.geometric(1.0 / mean_dwell, nk))
+        covered = min(nk, int(np.searchsorted(np.cumsum(dwell), n_samples)) + 1)
+        seqs.append(codes[:covered + model.k - 1])
         lv = np.repeat(model.level_mean[ranks], dwell)[:n_samples]
         sd = np.repeat(model.level_stdv[ranks], dwell)[:n_samples]
         x = (lv + 1.2 * sd * rng.standard_normal(lv.shape[0])).astype(np.float32)
@@ -400,4 +405,6 @@ def gen_raw(n_reads: int, n_samples: int, model: PoreModel, seed: int = 42, mean
         chunks.append(x)
         soff += x.shape[0]
         eoff += cap
+    if return_seqs:
+        return np.concatenate(chunks), reads, seqs
     return np.concatenate(chunks), reads

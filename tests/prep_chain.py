@@ -1,0 +1,43 @@
+"""The load_from_raw chain through the ORACLE (test infrastructure): trim -> detect_events -> SquiggleEvent conversion
+-> MoM -> ABEA -> base_to_event_map / recalibration, in the order src/nanopolish_squiggle_read.cpp:226-336 runs them."""
+import numpy as np
+
+from nanopolish_b200 import synth
+
+
+def squiggle_events(ev, sample_rate):
+    """events -> (duration f32, start_time f64) as squiggle_read.cpp:243-250 computes them (sequential double sum)."""
+    dur = (ev["length"].astype(np.float64) / sample_rate).astype(np.float32)
+    t = np.zeros(ev.shape[0], np.float64)
+    acc = 0.0
+    for i in range(ev.shape[0]):
+        t[i] = acc
+        acc += float(dur[i])
+    return dur, t
+
+
+def oracle_chain(port, model, signals, seqs, sample_rate=4000.0):
+    """Returns per read a dict: events (EVENT_DT), duration, start_time, and — when the read got that far — mom, cal
+    (CALIBRATION_DT record), b2e, n_pairs."""
+    prm = synth.event_params(False)
+    out = []
+    for x, codes in zip(signals, seqs):
+        r = {"events": None}
+        ok, s, e = port.trim_raw(x)
+        out.append(r)
+        if not ok:
+            continue
+        ev = port.detect_events(np.ascontiguousarray(x[s:e]), prm)
+        r["events"] = ev
+        r["duration"], r["start_time"] = squiggle_events(ev, sample_rate)
+        reads = np.zeros(1, synth.READ_DT)
+        reads[0] = (0, ev.shape[0], 0, 1.0, 0.0, 0.0, 1.0, 0.0, 0.0)
+        rs = synth.ReadSet(reads, np.ascontiguousarray(ev["mean"]), r["start_time"], [codes], [None], [None], model.k)
+        jobs, ranks, total = synth.abea_jobs(rs)
+        sh, sc = port.mom(rs.reads, rs.ev_mean, model, ranks, jobs[0])
+        reads[0]["shift"], reads[0]["scale"] = sh, sc
+        r["mom"] = (sh, sc)
+        pairs, res, _ = port.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, model, ranks, jobs, total)
+        r["n_pairs"] = int(res[0]["n_pairs"])
+        r["b2e"], r["cal"] = port.recalibrate(rs.reads, rs.ev_mean, model, ranks, jobs[0], pairs, r["n_pairs"])
+    return out

@@ -120,50 +120,38 @@ def test_calibration_homopolymers_failed_reads_and_odd_pair_lists(engine, nuc, p
 
 
 def test_raw_to_calibrated_read_chain(engine, nuc, port_oracle):
-    """trim -> detect_events -> MoM -> ABEA -> calibration on the device vs the same chain through the oracle: the
+    """trim -> detect_events -> MoM -> ABEA -> calibration through the C ABI vs the same chain through the oracle: the
     order SquiggleRead::load_from_raw runs them in (src/nanopolish_squiggle_read.cpp:226-336)."""
+    from tests.prep_chain import oracle_chain, squiggle_events
     model, mid = nuc
-    n_reads, sample_rate = 4, 4000.0
-    raw, rreads = synth.gen_raw(n_reads, 30000, model, seed=501)
-    prm = synth.event_params(False)
+    n_reads = 4
+    raw, rreads, seqs = synth.gen_raw(n_reads, 30000, model, seed=501, return_seqs=True)
+    signals = [raw[int(r["sample_off"]):int(r["sample_off"]) + int(r["n_samples"])] for r in rreads]
+    want = oracle_chain(port_oracle, model, signals, seqs)
     rng = engine.trim_raw_batch(raw, rreads)
     trimmed = rreads.copy()
-    for i in range(n_reads):
-        ok, s, e = port_oracle.trim_raw(raw[int(rreads[i]["sample_off"]):][:int(rreads[i]["n_samples"])])
-        assert ok and (int(rng[i]["start"]), int(rng[i]["end"])) == (s, e)
-        trimmed[i]["sample_off"] += s
-        trimmed[i]["n_samples"] = e - s
-    events = engine.detect_events_batch(raw, trimmed, prm)
-    # SquiggleEvent conversion (squiggle_read.cpp:243-250): float duration, double running start time
+    trimmed["sample_off"] += rng["start"]
+    trimmed["n_samples"] = rng["end"] - rng["start"]
+    events = engine.detect_events_batch(raw, trimmed, synth.event_params(False))
     reads = np.zeros(n_reads, synth.READ_DT)
     means, times = [], []
     off = 0
     for i, ev in enumerate(events):
-        want = port_oracle.detect_events(np.ascontiguousarray(raw[int(trimmed[i]["sample_off"]):][:int(trimmed[i]["n_samples"])]), prm)
-        assert np.array_equal(ev, want) and ev.shape[0] > 1000
-        dur = (ev["length"].astype(np.float64) / sample_rate).astype(np.float32)
-        t = np.concatenate([[0.0], np.cumsum(dur.astype(np.float64))[:-1]])
+        assert np.array_equal(ev, want[i]["events"]) and ev.shape[0] > 1000
+        _, t = squiggle_events(ev, 4000.0)
         reads[i] = (off, ev.shape[0], 0, 1.0, 0.0, 0.0, 1.0, 0.0, 0.0)
         means.append(ev["mean"]); times.append(t); off += ev.shape[0]
-    ev_mean, ev_time = np.concatenate(means), np.concatenate(times)
-    # the basecalled sequence: here the true one (gen_raw draws it from the same seed)
-    seqs = []
-    for r in range(n_reads):
-        g = np.random.default_rng(501 + r)
-        nk = int(30000 / 9.0 * 1.3) + 16
-        codes = g.integers(0, 4, nk + model.k - 1, dtype=np.uint8)
-        dwell = np.maximum(1, g.geometric(1.0 / 9.0, nk))
-        used = int(np.searchsorted(np.cumsum(dwell), int(rreads[r]["n_samples"]))) + 1
-        seqs.append(codes[:used + model.k - 1])
-    rs = synth.ReadSet(reads, ev_mean, ev_time, seqs, [None] * n_reads, [None] * n_reads, model.k)
+    rs = synth.ReadSet(reads, np.concatenate(means), np.concatenate(times), seqs, [None] * n_reads, [None] * n_reads, model.k)
     jobs, ranks, total = synth.abea_jobs(rs)
     ss = engine.mom_batch(rs.reads, rs.ev_mean, ranks, jobs, mid)
     for i in range(n_reads):
-        assert tuple(ss[i]) == port_oracle.mom(rs.reads, rs.ev_mean, model, ranks, jobs[i])
+        assert tuple(ss[i]) == want[i]["mom"]
         reads[i]["shift"], reads[i]["scale"] = ss[i][0], ss[i][1]
     pairs, res = engine.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ranks, jobs, mid, total)
-    po, ro, _ = port_oracle.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, model, ranks, jobs, total, threads=4)
-    assert np.array_equal(res["n_pairs"], ro["n_pairs"]) and (res["n_pairs"] > 0).all()
-    _, cal = _check_cal(engine, port_oracle, model, mid, rs, jobs, ranks, pairs, res)
+    assert [int(v) for v in res["n_pairs"]] == [w["n_pairs"] for w in want] and (res["n_pairs"] > 0).all()
+    b2e, cal = _check_cal(engine, port_oracle, model, mid, rs, jobs, ranks, pairs, res)
+    for i in range(n_reads):
+        assert cal[i].tobytes() == want[i]["cal"].tobytes()
+        assert np.array_equal(b2e[int(jobs[i]["rank_off"]):][:int(jobs[i]["n_kmers"])], want[i]["b2e"])
     assert (cal["status"] == 0).all()
     assert np.abs(cal["scale"] - 1.0).max() < 0.06 and np.abs(cal["shift"]).max() < 6.0 and (cal["var"] < 2.0).all()

@@ -212,3 +212,67 @@ def test_abea_and_mom_like_a_caller(host, port_oracle):
         assert host.nphh_mom(rh[i], mh, seq, out.ctypes.data_as(C.c_void_p)) == 0
         sh, sc = port_oracle.mom(rs.reads, rs.ev_mean, nuc, ranks, jobs[i])
         assert out[0] == sh and out[1] == sc and out[2] == 0.0 and out[3] == 1.0
+
+
+@pytest.mark.gpu
+def test_load_from_raw_like_a_caller(host, port_oracle):
+    """nph::load_from_raw over a batch (raw samples + basecalls in, SquiggleReads out) against the same chain through
+    the oracle: identical events, bit-identical scalings, identical base_to_event_map and the same reads dropped."""
+    from tests.prep_chain import oracle_chain
+    nuc = synth.load_model("nucleotide")
+    raw, rr, seqs = synth.gen_raw(4, 24000, nuc, seed=901, return_seqs=True)
+    signals = [raw[int(r["sample_off"]):int(r["sample_off"]) + int(r["n_samples"])] for r in rr]
+    g = np.random.default_rng(11)                                                  # homopolymer runs: < 200 'M' events, calibration refuses
+    codes = np.concatenate([np.concatenate([g.integers(0, 4, 8, dtype=np.uint8), np.full(20, g.integers(0, 4), np.uint8)]) for _ in range(14)])
+    ranks = synth.kmer_ranks_from_codes(codes, nuc.k, 4)
+    dwell = np.maximum(1, g.geometric(1.0 / 9.0, ranks.shape[0]))
+    signals.append((np.repeat(nuc.level_mean[ranks], dwell) + 1.2 * np.repeat(nuc.level_stdv[ranks], dwell) * g.standard_normal(int(dwell.sum()))).astype(np.float32))
+    seqs.append(codes)
+    short, _, sq = synth.gen_raw(1, 2400, nuc, seed=77, return_seqs=True)          # too short once trimmed: alignment fails
+    signals.append(short); seqs.append(sq[0])
+    signals.append(np.full(5000, 101.0, np.float32)); seqs.append(seqs[0][:400])   # flat: nothing survives the trim
+    noise = np.random.default_rng(5).uniform(60, 130, 20000).astype(np.float32)    # no sequence signal at all
+    signals.append(noise); seqs.append(seqs[1][:2000])
+    n = len(signals)
+    want = oracle_chain(port_oracle, nuc, signals, seqs)
+    mh = _register(host, nuc)
+    soff = np.zeros(n + 1, np.uint64); soff[1:] = np.cumsum([s.shape[0] for s in signals])
+    qoff = np.zeros(n + 1, np.uint64); qoff[1:] = np.cumsum([c.shape[0] for c in seqs])
+    seqbuf = b"".join(synth._CODE2DNA[c].tobytes() for c in seqs)
+    eoff = np.zeros(n, np.uint64); eoff[1:] = np.cumsum([s.shape[0] // 2 + 8 for s in signals])[:-1]
+    room = int(eoff[-1]) + signals[-1].shape[0] // 2 + 8
+    n_events = np.zeros(n, np.uint32); scal = np.zeros((n, 5)); stats = np.zeros(5, np.uint64)
+    mean = np.zeros(room, np.float32); stdv = np.zeros(room, np.float32); start = np.zeros(room, np.float64); dur = np.zeros(room, np.float32)
+    b2e = np.full((int(qoff[-1]), 2), -7, np.int32)
+    flat = np.concatenate(signals)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = host.nphh_load_from_raw(mh, n, p(flat), p(soff), seqbuf, p(qoff), C.c_double(4000.0), p(n_events), p(scal), p(eoff), p(mean), p(stdv),
+                                 p(start), p(dur), p(b2e), p(stats))
+    assert rc >= 0, host.nphh_last_error()
+    dropped = 0
+    for i in range(n):
+        w = want[i]
+        if w["events"] is None:
+            assert n_events[i] == 0
+            continue
+        keep = w["n_pairs"] > 0 and int(w["cal"]["status"]) == 0
+        dropped += not keep
+        if not keep:
+            assert n_events[i] == 0
+        else:
+            ev = w["events"]; o = int(eoff[i])
+            assert n_events[i] == ev.shape[0]
+            assert np.array_equal(mean[o:o + ev.shape[0]], ev["mean"]) and np.array_equal(stdv[o:o + ev.shape[0]], ev["stdv"])
+            assert np.array_equal(dur[o:o + ev.shape[0]], w["duration"]) and np.array_equal(start[o:o + ev.shape[0]], w["start_time"])
+        if w["n_pairs"] > 0:
+            c = w["cal"]
+            exp = (c["shift"], c["scale"], c["drift"], c["var"]) if not int(c["status"]) & 2 else (w["mom"][0], w["mom"][1], 0.0, 1.0)
+            assert tuple(scal[i][:4]) == tuple(float(v) for v in exp) and scal[i][4] == c["events_per_base"]
+            nk = seqs[i].shape[0] - nuc.k + 1
+            got = b2e[int(qoff[i]):int(qoff[i]) + nk]
+            assert np.array_equal(got[:, 0], w["b2e"]["start"]) and np.array_equal(got[:, 1], w["b2e"]["stop"])
+        else:
+            assert tuple(scal[i][:2]) == w["mom"] and scal[i][4] == 0.0
+    assert [int(v) for v in stats] == [n, 1, stats[2], stats[3], stats[4]] and int(stats[2] + stats[3] + stats[4]) == dropped
+    assert (n_events[:4] > 2000).all() and (n_events[4:] == 0).all()
+    assert int(want[4]["cal"]["status"]) == 2 and want[5]["n_pairs"] == 0 and want[6]["events"] is None and [int(v) for v in stats[1:4]] == [1, 2, 1]
