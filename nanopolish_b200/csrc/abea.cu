@@ -59,6 +59,7 @@ struct AbeaParams {
     uint64_t trace_stride;
     double lp_skip, lp_trim;
     float log_inv_sqrt_2pi;
+    int active_warps;            // warps per CTA that take jobs (small batches are spread over all SMs)
 };
 
 __device__ __forceinline__ float sel4(const float (&v)[4], int s)
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
 
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
+    if (wib >= p.active_warps) return;        // warps are independent: no block-level barrier below
     const int warp_global = blockIdx.x * kWarps + wib;
     float4* const prm = p.scratch_params + (size_t)warp_global * p.kmax_stride;
     uint8_t* const trace = p.scratch_trace + (size_t)warp_global * p.trace_stride;
@@ -414,8 +416,10 @@ int nph_launch_abea(nph_ctx* ctx)
     p.log_inv_sqrt_2pi = ctx->consts.log_inv_sqrt_2pi;
     NPH_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p + (NPH_NUM_COUNTERS - 1), 0, sizeof(unsigned int), ctx->stream));
     NPH_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    int grid = ctx->sm_count;
-    if ((size_t)grid * kWarps > ctx->n_abea_jobs) grid = (int)((ctx->n_abea_jobs + kWarps - 1) / kWarps);
+    // A read is one warp's sequential walk over ~E+K bands, so a BamProcessor-sized batch (512 reads) is latency
+    // bound: give every warp its own scheduler slot across all SMs before stacking warps on one SM.
+    const int grid = (int)std::min<size_t>((size_t)ctx->sm_count, ctx->n_abea_jobs);
+    p.active_warps = (int)std::min<size_t>((size_t)kWarps, (ctx->n_abea_jobs + grid - 1) / grid);
     abea_kernel<<<grid, kThreads, 0, ctx->stream>>>(p);
     NPH_CUDA(ctx, cudaGetLastError());
     NPH_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
