@@ -284,6 +284,31 @@ int nph_recalibrate_batch(nph_ctx* ctx, const nph_read* reads, size_t n_reads, c
                           uint32_t model_id, const nph_aligned_pair* pairs, size_t pairs_total,
                           const nph_abea_result* results, nph_event_range* base_to_event_out, nph_calibration* calibrations_out);
 
+/* ---- the whole read prologue in one call (section 8f N4) ------------------------------------------------
+ * SquiggleRead::load_from_raw for a batch of DNA reads: trim_and_segment_raw (200, 10, 100, 0.0) -> detect_events ->
+ * SquiggleEvent conversion -> estimate_scalings_using_mom -> adaptive_banded_simple_event_align -> base_to_event_map,
+ * events_per_base, recalibrate_model and the QC, chained on the device (the samples cross PCIe once, events never
+ * come back in between).  ref: src/nanopolish_squiggle_read.cpp:226-336.
+ * Outputs, per job j:  events [event_off_out[j], event_off_out[j+1]) of the four event arrays (compact, job order;
+ * SquiggleEvent::log_stdv = logf(stdv) is left to the caller's libm), calibrations_out[j] (status != 0: the reference
+ * clears the read's events; the arrays still hold them), base_to_event_out[rank_off + ki] (optional).
+ * A read that trims to nothing (the reference aborts on it) gets no events and NPH_CAL_EMPTY_AFTER_TRIM.
+ * NPH_ERR_UNSUPPORTED if events_cap is too small (n_samples_total / 3 always suffices). */
+#define NPH_CAL_EMPTY_AFTER_TRIM 16
+typedef struct {
+    uint64_t sample_off;      /* first raw sample (picoamps, float) of this read in raw[] */
+    uint64_t rank_off;        /* first k-mer rank of the basecalled sequence in kmer_ranks[] (forward strand) */
+    uint32_t n_samples;
+    uint32_t n_kmers;         /* read_sequence.length() - k + 1 */
+    double   sample_rate;     /* Fast5Data::channel_params.sample_rate */
+} nph_raw_job;
+int nph_load_from_raw_batch(nph_ctx* ctx, const float* raw, size_t n_samples_total,
+                            const uint32_t* kmer_ranks, size_t n_ranks_total,
+                            const nph_raw_job* jobs, size_t n_jobs, uint32_t model_id, const nph_event_params* params,
+                            uint64_t* event_off_out, float* ev_mean_out, float* ev_stdv_out, double* ev_start_time_out,
+                            float* ev_duration_out, size_t events_cap,
+                            nph_event_range* base_to_event_out, nph_calibration* calibrations_out);
+
 /* ---- measurement hooks (used by bench.py; not part of the reference surface) ------------- */
 /* Device time in ms of the most recent nph_hmm_score / nph_abea_run kernel sequence, measured
  * with CUDA events on the context's stream (valid after a sync), and the number of kernel

@@ -428,6 +428,18 @@ int nph_launch_abea(nph_ctx* ctx)
     return NPH_OK;
 }
 
+// estimate_scalings_using_mom over the loaded ABEA jobs (reads, ranks and jobs already on the device)
+int nph_launch_mom(nph_ctx* ctx, double* d_shift_scale_out)
+{
+    MomParams p{};
+    p.ev_mean = ctx->d_ev_mean.p; p.reads = ctx->d_reads.p; p.models = ctx->d_models.p; p.model_id = ctx->abea_model;
+    p.ranks = ctx->d_abea_ranks.p; p.jobs = ctx->d_abea_jobs.p; p.n_jobs = (uint32_t)ctx->n_abea_jobs; p.out = d_shift_scale_out;
+    const int grid = (int)std::min<size_t>((ctx->n_abea_jobs + kWarps - 1) / kWarps, (size_t)ctx->sm_count * 4);
+    mom_kernel<<<grid, kThreads, 0, ctx->stream>>>(p);
+    NPH_CUDA(ctx, cudaGetLastError());
+    return NPH_OK;
+}
+
 extern "C" {
 
 int nph_abea_jobs_load(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_total,

@@ -497,14 +497,24 @@ __global__ void __launch_bounds__(256) ed_events_kernel(const FastParams p)
 
 } // namespace
 
-extern "C" int nph_detect_events_batch(nph_ctx* ctx, const float* raw, size_t n_samples_total, const nph_raw_read* reads, size_t n_reads,
-                                       const nph_event_params* params, nph_event* events_out, size_t events_total, uint32_t* n_events_out)
+static inline size_t ed_al(size_t v) { return (v + 255) / 256 * 256; }
+
+// Scratch the detector needs next to the raw samples (which the caller keeps on the device).
+size_t nph_ed_scratch_bytes(size_t n_samples_total, size_t n_reads, size_t events_total)
 {
-    if (!ctx || !params) return NPH_ERR_INVALID;
-    if (n_reads == 0) return NPH_OK;
-    if (!raw || !reads || !events_out || !n_events_out) return NPH_ERR_INVALID;
+    const size_t b_raw = ed_al(sizeof(float) * n_samples_total), b_n = ed_al(sizeof(uint32_t) * n_reads);
+    return ed_al(sizeof(nph_raw_read) * n_reads) + b_n /*order*/ + ed_al(sizeof(nph_event) * events_total) + 2 * b_n /*n_events, n_peaks*/ + 256 +
+           2 * b_raw /*ts1, ts2*/ + ed_al(sizeof(uint32_t) * events_total) /*peaks*/ + ed_al(n_reads) /*exact*/;
+}
+
+// Event detection over reads whose samples are already on the device.  Leaves the events (at each read's event_off)
+// and the counts on the device, returns the counts on the host too.  Synchronises the stream (twice: the list of reads
+// that need the sequential fallback, then the counts).
+int nph_detect_events_device(nph_ctx* ctx, const float* d_raw, size_t n_samples_total, const nph_raw_read* reads, size_t n_reads,
+                             const nph_event_params* params, uint8_t* scratch, size_t events_total,
+                             nph_event** d_events_out, uint32_t** d_n_events_out, std::vector<uint32_t>& h_n_events, int* launches_out)
+{
     if (params->window_length2 > kMaxW2 || params->window_length1 > params->window_length2 || params->window_length1 == 0) return NPH_ERR_UNSUPPORTED;
-    NPH_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<std::pair<uint32_t, uint32_t>> keyed(n_reads);
     for (size_t i = 0; i < n_reads; ++i) {
         const nph_raw_read& r = reads[i];
@@ -518,16 +528,12 @@ extern "C" int nph_detect_events_batch(nph_ctx* ctx, const float* raw, size_t n_
     std::vector<uint32_t> order(n_reads);
     for (size_t i = 0; i < n_reads; ++i) order[i] = keyed[i].second;
 
-    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
-    const size_t b_raw = al(sizeof(float) * n_samples_total), b_reads = al(sizeof(nph_raw_read) * n_reads), b_order = al(sizeof(uint32_t) * n_reads);
-    const size_t b_ev = al(sizeof(nph_event) * events_total), b_n = al(sizeof(uint32_t) * n_reads);
-    const size_t b_pk = al(sizeof(uint32_t) * events_total), b_ex = al(n_reads);
-    NPH_TRY(nph_reserve(ctx, ctx->d_abea_scratch, 3 * b_raw + b_reads + b_order + b_ev + 2 * b_n + b_pk + b_ex + 256));
-    uint8_t* base = ctx->d_abea_scratch.p;
+    const size_t b_raw = ed_al(sizeof(float) * n_samples_total), b_reads = ed_al(sizeof(nph_raw_read) * n_reads), b_n = ed_al(sizeof(uint32_t) * n_reads);
+    const size_t b_ev = ed_al(sizeof(nph_event) * events_total), b_pk = ed_al(sizeof(uint32_t) * events_total);
+    uint8_t* base = scratch;
     DetParams p{};
-    float* d_raw = reinterpret_cast<float*>(base); base += b_raw;
     nph_raw_read* d_reads = reinterpret_cast<nph_raw_read*>(base); base += b_reads;
-    uint32_t* d_order = reinterpret_cast<uint32_t*>(base); base += b_order;
+    uint32_t* d_order = reinterpret_cast<uint32_t*>(base); base += b_n;
     p.events = reinterpret_cast<nph_event*>(base); base += b_ev;
     p.n_events = reinterpret_cast<uint32_t*>(base); base += b_n;
     p.overflow = reinterpret_cast<int*>(base); base += 256;
@@ -540,7 +546,6 @@ extern "C" int nph_detect_events_batch(nph_ctx* ctx, const float* raw, size_t n_
     p.w1 = params->window_length1; p.w2 = params->window_length2;
     p.t1 = params->threshold1; p.t2 = params->threshold2; p.peak_height = params->peak_height;
     p.ring = 2 * p.w2 + 1;
-    NPH_CUDA(ctx, cudaMemcpyAsync(d_raw, raw, sizeof(float) * n_samples_total, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(d_reads, reads, sizeof(nph_raw_read) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(d_order, order.data(), sizeof(uint32_t) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemsetAsync(p.overflow, 0, sizeof(int), ctx->stream));
@@ -551,7 +556,6 @@ extern "C" int nph_detect_events_batch(nph_ctx* ctx, const float* raw, size_t n_
     f.events = p.events; f.n_events = p.n_events; f.overflow = p.overflow;
     f.w1 = p.w1; f.w2 = p.w2; f.t1 = p.t1; f.t2 = p.t2; f.peak_height = p.peak_height;
     f.warm = getenv("NPH_EVENTS_WARMUP") ? (uint32_t)atoi(getenv("NPH_EVENTS_WARMUP")) : kWarm;
-    NPH_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     int launches = 0;
     ed_guard_kernel<<<(unsigned)std::min<size_t>(n_reads, (size_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(f); ++launches;
     NPH_CUDA(ctx, cudaGetLastError());
@@ -587,13 +591,42 @@ extern "C" int nph_detect_events_batch(nph_ctx* ctx, const float* raw, size_t n_
         NPH_CUDA(ctx, cudaGetLastError());
     }
     NPH_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->last_launches = launches;
-    ctx->timing_valid = true;
     int overflow = 0;
-    NPH_CUDA(ctx, cudaMemcpyAsync(events_out, p.events, sizeof(nph_event) * events_total, cudaMemcpyDeviceToHost, ctx->stream));
-    NPH_CUDA(ctx, cudaMemcpyAsync(n_events_out, p.n_events, sizeof(uint32_t) * n_reads, cudaMemcpyDeviceToHost, ctx->stream));
+    h_n_events.resize(n_reads);
+    NPH_CUDA(ctx, cudaMemcpyAsync(h_n_events.data(), p.n_events, sizeof(uint32_t) * n_reads, cudaMemcpyDeviceToHost, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(&overflow, p.overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->abea_loaded = false;     // the arena was reused
+    *d_events_out = p.events;
+    *d_n_events_out = p.n_events;
+    if (launches_out) *launches_out = launches;
     return overflow ? NPH_ERR_UNSUPPORTED : NPH_OK;
+}
+
+extern "C" int nph_detect_events_batch(nph_ctx* ctx, const float* raw, size_t n_samples_total, const nph_raw_read* reads, size_t n_reads,
+                                       const nph_event_params* params, nph_event* events_out, size_t events_total, uint32_t* n_events_out)
+{
+    if (!ctx || !params) return NPH_ERR_INVALID;
+    if (n_reads == 0) return NPH_OK;
+    if (!raw || !reads || !events_out || !n_events_out) return NPH_ERR_INVALID;
+    NPH_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t b_raw = ed_al(sizeof(float) * n_samples_total);
+    NPH_TRY(nph_reserve(ctx, ctx->d_abea_scratch, b_raw + nph_ed_scratch_bytes(n_samples_total, n_reads, events_total)));
+    ctx->abea_loaded = false;     // the arena is shared with the ABEA trace
+    float* d_raw = reinterpret_cast<float*>(ctx->d_abea_scratch.p);
+    NPH_CUDA(ctx, cudaMemcpyAsync(d_raw, raw, sizeof(float) * n_samples_total, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    nph_event* d_events = nullptr;
+    uint32_t* d_n = nullptr;
+    std::vector<uint32_t> counts;
+    int launches = 0;
+    const int rc = nph_detect_events_device(ctx, d_raw, n_samples_total, reads, n_reads, params, ctx->d_abea_scratch.p + b_raw, events_total,
+                                            &d_events, &d_n, counts, &launches);
+    if (rc != NPH_OK && rc != NPH_ERR_UNSUPPORTED) return rc;
+    if (!d_events) return rc;                       // parameters refused before anything ran
+    ctx->last_launches = launches;
+    ctx->timing_valid = true;
+    NPH_CUDA(ctx, cudaMemcpyAsync(events_out, d_events, sizeof(nph_event) * events_total, cudaMemcpyDeviceToHost, ctx->stream));
+    NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::copy(counts.begin(), counts.end(), n_events_out);
+    return rc;
 }

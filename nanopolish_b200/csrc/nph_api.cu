@@ -184,7 +184,7 @@ int nph_destroy(nph_ctx* ctx)
     free_buf(ctx->d_ev_time); free_buf(ctx->d_level); free_buf(ctx->d_drift); free_buf(ctx->d_ranks);
     free_buf(ctx->d_jobs); free_buf(ctx->d_trans); free_buf(ctx->d_order); free_buf(ctx->d_scores);
     free_buf(ctx->d_counters); free_buf(ctx->d_sched_cls); free_buf(ctx->d_sched_bkt); free_buf(ctx->d_sched_hist); free_buf(ctx->d_scratch); free_buf(ctx->d_abea_jobs); free_buf(ctx->d_abea_ranks);
-    free_buf(ctx->d_pairs); free_buf(ctx->d_abea_res); free_buf(ctx->d_abea_scratch); free_buf(ctx->d_abea_order); free_buf(ctx->d_abea_consts);
+    free_buf(ctx->d_pairs); free_buf(ctx->d_abea_res); free_buf(ctx->d_abea_scratch); free_buf(ctx->d_abea_order); free_buf(ctx->d_abea_consts); free_buf(ctx->d_prep);
     for (auto& m : ctx->models) { cudaFree(m.mean); cudaFree(m.stdv); cudaFree(m.log_stdv); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -446,8 +446,11 @@ int nph_last_kernel_ms(nph_ctx* ctx, float* ms_out, int* launches_out)
 {
     if (!ctx || !ms_out) return NPH_ERR_INVALID;
     if (!ctx->timing_valid) return NPH_ERR_STATE;
-    NPH_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
-    NPH_CUDA(ctx, cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+    if (ctx->timing_valid == 2) *ms_out = ctx->staged_ms;
+    else {
+        NPH_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        NPH_CUDA(ctx, cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+    }
     if (launches_out) *launches_out = ctx->last_launches;
     return NPH_OK;
 }

@@ -99,6 +99,7 @@ struct nph_ctx {
     DevBuf<uint8_t> d_abea_scratch;
     DevBuf<uint32_t> d_abea_order;
     DevBuf<double> d_abea_consts;    // per job (lp_stay, lp_step); also the MoM output buffer
+    DevBuf<uint8_t> d_prep;          // load_from_raw: event SoA staging, MoM output, calibration buffers
     uint32_t abea_kmax = 0;
     uint64_t abea_trace_stride = 0;
     bool abea_loaded = false;
@@ -110,7 +111,8 @@ struct nph_ctx {
     cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     int last_launches = 0;
-    bool timing_valid = false;
+    int timing_valid = 0;            // 0 none, 1 = ev0..ev1, 2 = staged_ms (a call with host round trips between its kernels)
+    float staged_ms = 0.0f;
 
     // pipelined level upload of the one-shot call: copy stream, progress word polled by the forward kernel
     static const int kLevelChunks = 8;
@@ -138,3 +140,28 @@ int nph_launch_hmm_forward(nph_ctx* ctx, float* scores_dev);
 size_t nph_hmm_scratch_bytes(const nph_ctx* ctx, int* warps_total_out);
 int nph_launch_abea(nph_ctx* ctx);
 int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uint32_t* max_E_out);
+
+// ---- device-level pieces of the raw-read prologue (event_detect.cu, squiggle_prep.cu, abea.cu), chained by
+// load_from_raw.cu without leaving the device.  Inputs named d_* are device pointers; everything runs on ctx->stream.
+size_t nph_ed_scratch_bytes(size_t n_samples_total, size_t n_reads, size_t events_total);
+int nph_detect_events_device(nph_ctx* ctx, const float* d_raw, size_t n_samples_total, const nph_raw_read* reads, size_t n_reads,
+                             const nph_event_params* params, uint8_t* scratch, size_t events_total,
+                             nph_event** d_events_out, uint32_t** d_n_events_out, std::vector<uint32_t>& h_n_events, int* launches_out);
+size_t nph_trim_scratch_bytes(const nph_raw_read* reads, size_t n_reads, int32_t varseg_chunk);
+int nph_trim_device(nph_ctx* ctx, const float* d_raw, size_t n_samples_total, const nph_raw_read* reads, size_t n_reads,
+                    int32_t trim_start, int32_t trim_end, int32_t varseg_chunk, float varseg_thresh, uint8_t* scratch,
+                    nph_raw_range* ranges_out /* host */);
+struct NphCalArgs {
+    const float* ev_mean;
+    const nph_read* reads;
+    const uint32_t* ranks;
+    const nph_abea_job* jobs;
+    const nph_abea_result* results;
+    const nph_aligned_pair* pairs;
+    uint32_t n_jobs, model_id;
+    nph_event_range* b2e;        // n_kmers entries per job at rank_off
+    nph_calibration* out;
+    int* bad_input;
+};
+int nph_launch_recalibrate(nph_ctx* ctx, const NphCalArgs& args);
+int nph_launch_mom(nph_ctx* ctx, double* d_shift_scale_out);     // over the loaded ABEA jobs: 2 doubles per job

@@ -158,18 +158,8 @@ __global__ void __launch_bounds__(kTrimThreads) trim_kernel(const TrimParams p)
 // recalibration
 // ------------------------------------------------------------------------------------------------------------
 struct CalParams {
-    const float* ev_mean;
-    const nph_read* reads;
+    NphCalArgs a;
     const DevModelView* models;
-    uint32_t model_id;
-    const uint32_t* ranks;
-    const nph_abea_job* jobs;
-    const nph_abea_result* results;
-    const nph_aligned_pair* pairs;
-    uint32_t n_jobs;
-    nph_event_range* b2e;        // n_kmers entries per job at rank_off
-    nph_calibration* out;
-    int* bad_input;
 };
 
 // A.fullPivLu().solve(b) for the symmetric 2x2 system, the way Eigen 3.3 computes it: largest |entry| (column-major
@@ -224,14 +214,14 @@ __global__ void __launch_bounds__(kCalWarps * 32) recalibrate_kernel(const CalPa
 {
     __shared__ double s_e[kCalWarps][32], s_mu[kCalWarps][32], s_sd[kCalWarps][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const DevModelView mv = p.models[p.model_id];
-    for (uint32_t j = blockIdx.x * kCalWarps + wib; j < p.n_jobs; j += gridDim.x * kCalWarps) {
-        const nph_abea_job job = p.jobs[j];
-        const nph_read rd = p.reads[job.read];
-        const uint32_t np = p.results[j].n_pairs;
-        const nph_aligned_pair* __restrict__ pr = p.pairs + job.pairs_off;
-        const uint32_t* __restrict__ rk = p.ranks + job.rank_off;
-        nph_event_range* b2e = p.b2e + job.rank_off;
+    const DevModelView mv = p.models[p.a.model_id];
+    for (uint32_t j = blockIdx.x * kCalWarps + wib; j < p.a.n_jobs; j += gridDim.x * kCalWarps) {
+        const nph_abea_job job = p.a.jobs[j];
+        const nph_read rd = p.a.reads[job.read];
+        const uint32_t np = p.a.results[j].n_pairs;
+        const nph_aligned_pair* __restrict__ pr = p.a.pairs + job.pairs_off;
+        const uint32_t* __restrict__ rk = p.a.ranks + job.rank_off;
+        nph_event_range* b2e = p.a.b2e + job.rank_off;
         const int nk = (int)job.n_kmers;
         nph_calibration cal;
         cal.shift = rd.shift; cal.scale = rd.scale; cal.drift = rd.drift; cal.var = rd.var;
@@ -259,8 +249,8 @@ __global__ void __launch_bounds__(kCalWarps * 32) recalibrate_kernel(const CalPa
         __syncwarp();
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { ev_min = min(ev_min, __shfl_xor_sync(kFull, ev_min, o)); ev_max = max(ev_max, __shfl_xor_sync(kFull, ev_max, o)); }
-        if (bad) { if (lane == 0) { *p.bad_input = 1; cal.status = NPH_CAL_NOT_ALIGNED; p.out[j] = cal; } continue; }
-        if (np == 0) { if (lane == 0) { cal.status = NPH_CAL_NOT_ALIGNED; p.out[j] = cal; } continue; }
+        if (bad) { if (lane == 0) { *p.a.bad_input = 1; cal.status = NPH_CAL_NOT_ALIGNED; p.a.out[j] = cal; } continue; }
+        if (np == 0) { if (lane == 0) { cal.status = NPH_CAL_NOT_ALIGNED; p.a.out[j] = cal; } continue; }
         cal.events_per_base = __ddiv_rn((double)(unsigned long long)(ev_max - ev_min), (double)(unsigned long long)nk);
 
         // get_eventalignment_for_1d_basecalls + the extraction loop of recalibrate_model: walking k-mers in order, the
@@ -282,7 +272,7 @@ __global__ void __launch_bounds__(kCalWarps * 32) recalibrate_kernel(const CalPa
             if (hm) carry_rank = __shfl_sync(kFull, rank, 31 - __clz(hm));
             const unsigned mm = __ballot_sync(kFull, is_m);
             if (mm == 0) continue;
-            s_e[wib][lane] = is_m ? (double)p.ev_mean[rd.event_off + (uint32_t)rg.start] : 0.0;
+            s_e[wib][lane] = is_m ? (double)p.a.ev_mean[rd.event_off + (uint32_t)rg.start] : 0.0;
             s_mu[wib][lane] = is_m ? mv.mean[rank] : 0.0;
             s_sd[wib][lane] = is_m ? mv.stdv[rank] : 1.0;
             __syncwarp();
@@ -303,7 +293,7 @@ __global__ void __launch_bounds__(kCalWarps * 32) recalibrate_kernel(const CalPa
         }
         cal.n_used = n_used;
         if (n_used < 200) {                      // minNumEventsToRescale: scalings stay as they were, read fails QC
-            if (lane == 0) { cal.status = NPH_CAL_TOO_FEW_EVENTS; p.out[j] = cal; }
+            if (lane == 0) { cal.status = NPH_CAL_TOO_FEW_EVENTS; p.a.out[j] = cal; }
             continue;
         }
         double shift = 0.0, scale = 0.0;
@@ -330,7 +320,7 @@ __global__ void __launch_bounds__(kCalWarps * 32) recalibrate_kernel(const CalPa
             if (mm == 0) continue;
             double term = 0.0;
             if (is_m) {
-                const double e = (double)p.ev_mean[rd.event_off + (uint32_t)rg.start], mu = mv.mean[rank], sd = mv.stdv[rank];
+                const double e = (double)p.a.ev_mean[rd.event_off + (uint32_t)rg.start], mu = mv.mean[rank], sd = mv.stdv[rank];
                 const double yi = __dsub_rn(__dsub_rn(e, shift), __dmul_rn(scale, mu));
                 term = __ddiv_rn(__dmul_rn(yi, yi), __dmul_rn(sd, sd));
             }
@@ -344,7 +334,7 @@ __global__ void __launch_bounds__(kCalWarps * 32) recalibrate_kernel(const CalPa
             cal.shift = shift; cal.scale = scale; cal.drift = 0.0; cal.var = var;
             if (var > 2.5) cal.status |= NPH_CAL_HIGH_VAR;                              // MIN_CALIBRATION_VAR
             else if (cal.events_per_base > 5.0) cal.status |= NPH_CAL_TOO_MANY_STAYS;   // squiggle_read.cpp:331-336
-            p.out[j] = cal;
+            p.a.out[j] = cal;
         }
     }
 }
@@ -353,16 +343,21 @@ inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
 } // namespace
 
-extern "C" int nph_trim_raw_batch(nph_ctx* ctx, const float* raw, size_t n_samples_total, const nph_raw_read* reads, size_t n_reads,
-                                  int32_t trim_start, int32_t trim_end, int32_t varseg_chunk, float varseg_thresh,
-                                  nph_raw_range* ranges_out)
+size_t nph_trim_scratch_bytes(const nph_raw_read* reads, size_t n_reads, int32_t varseg_chunk)
 {
-    if (!ctx) return NPH_ERR_INVALID;
-    if (n_reads == 0) return NPH_OK;
-    if (!raw || !reads || !ranges_out) return NPH_ERR_INVALID;
+    uint64_t n_chunks = 0;
+    for (size_t i = 0; i < n_reads; ++i) n_chunks += reads[i].n_samples / (uint32_t)varseg_chunk;
+    return al256(sizeof(nph_raw_read) * n_reads) + al256(sizeof(uint64_t) * n_reads) + al256(sizeof(float) * (n_chunks + 1)) +
+           al256(sizeof(nph_raw_range) * n_reads);
+}
+
+// trim_and_segment_raw over reads whose samples are on the device; the ranges come back to the host (one sync).
+int nph_trim_device(nph_ctx* ctx, const float* d_raw, size_t n_samples_total, const nph_raw_read* reads, size_t n_reads,
+                    int32_t trim_start, int32_t trim_end, int32_t varseg_chunk, float varseg_thresh, uint8_t* scratch,
+                    nph_raw_range* ranges_out)
+{
     if (varseg_chunk < 2 || !(varseg_thresh >= 0.0f && varseg_thresh <= 1.0f) || trim_start < 0 || trim_end < 0) return NPH_ERR_INVALID;   // reference asserts
     if (varseg_chunk > kMaxChunk) return NPH_ERR_UNSUPPORTED;
-    NPH_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<uint64_t> mad_off(n_reads);
     uint64_t n_chunks = 0;
     for (size_t i = 0; i < n_reads; ++i) {
@@ -370,30 +365,55 @@ extern "C" int nph_trim_raw_batch(nph_ctx* ctx, const float* raw, size_t n_sampl
         mad_off[i] = n_chunks;
         n_chunks += reads[i].n_samples / (uint32_t)varseg_chunk;
     }
-    const size_t b_raw = al256(sizeof(float) * n_samples_total), b_reads = al256(sizeof(nph_raw_read) * n_reads);
-    const size_t b_off = al256(sizeof(uint64_t) * n_reads), b_mad = al256(sizeof(float) * (n_chunks + 1)), b_out = al256(sizeof(nph_raw_range) * n_reads);
-    NPH_TRY(nph_reserve(ctx, ctx->d_abea_scratch, b_raw + b_reads + b_off + b_mad + b_out));
-    ctx->abea_loaded = false;       // the arena is shared with the ABEA trace
-    uint8_t* base = ctx->d_abea_scratch.p;
+    uint8_t* base = scratch;
     TrimParams p{};
-    float* d_raw = reinterpret_cast<float*>(base); base += b_raw;
-    nph_raw_read* d_reads = reinterpret_cast<nph_raw_read*>(base); base += b_reads;
-    uint64_t* d_off = reinterpret_cast<uint64_t*>(base); base += b_off;
-    p.mad = reinterpret_cast<float*>(base); base += b_mad;
+    nph_raw_read* d_reads = reinterpret_cast<nph_raw_read*>(base); base += al256(sizeof(nph_raw_read) * n_reads);
+    uint64_t* d_off = reinterpret_cast<uint64_t*>(base); base += al256(sizeof(uint64_t) * n_reads);
+    p.mad = reinterpret_cast<float*>(base); base += al256(sizeof(float) * (n_chunks + 1));
     p.out = reinterpret_cast<nph_raw_range*>(base);
     p.raw = d_raw; p.reads = d_reads; p.mad_off = d_off; p.n_reads = (uint32_t)n_reads;
     p.trim_start = trim_start; p.trim_end = trim_end; p.chunk = varseg_chunk; p.perc = varseg_thresh;
-    NPH_CUDA(ctx, cudaMemcpyAsync(d_raw, raw, sizeof(float) * n_samples_total, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(d_reads, reads, sizeof(nph_raw_read) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(d_off, mad_off.data(), sizeof(uint64_t) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
-    NPH_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     trim_kernel<<<(unsigned)std::min<size_t>(n_reads, (size_t)ctx->sm_count * 8), kTrimThreads, 0, ctx->stream>>>(p);
     NPH_CUDA(ctx, cudaGetLastError());
     NPH_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->last_launches = 1;
-    ctx->timing_valid = true;
     NPH_CUDA(ctx, cudaMemcpyAsync(ranges_out, p.out, sizeof(nph_raw_range) * n_reads, cudaMemcpyDeviceToHost, ctx->stream));
     NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NPH_OK;
+}
+
+int nph_launch_recalibrate(nph_ctx* ctx, const NphCalArgs& args)
+{
+    CalParams p{};
+    p.a = args;
+    p.models = ctx->d_models.p;
+    NPH_CUDA(ctx, cudaMemsetAsync(args.bad_input, 0, sizeof(int), ctx->stream));
+    const int grid = (int)std::min<size_t>((args.n_jobs + kCalWarps - 1) / kCalWarps, (size_t)ctx->sm_count * 8);
+    recalibrate_kernel<<<grid, kCalWarps * 32, 0, ctx->stream>>>(p);
+    NPH_CUDA(ctx, cudaGetLastError());
+    return NPH_OK;
+}
+
+extern "C" int nph_trim_raw_batch(nph_ctx* ctx, const float* raw, size_t n_samples_total, const nph_raw_read* reads, size_t n_reads,
+                                  int32_t trim_start, int32_t trim_end, int32_t varseg_chunk, float varseg_thresh,
+                                  nph_raw_range* ranges_out)
+{
+    if (!ctx) return NPH_ERR_INVALID;
+    if (n_reads == 0) return NPH_OK;
+    if (!raw || !reads || !ranges_out) return NPH_ERR_INVALID;
+    if (varseg_chunk < 2) return NPH_ERR_INVALID;
+    NPH_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t b_raw = al256(sizeof(float) * n_samples_total);
+    NPH_TRY(nph_reserve(ctx, ctx->d_abea_scratch, b_raw + nph_trim_scratch_bytes(reads, n_reads, varseg_chunk)));
+    ctx->abea_loaded = false;       // the arena is shared with the ABEA trace
+    float* d_raw = reinterpret_cast<float*>(ctx->d_abea_scratch.p);
+    NPH_CUDA(ctx, cudaMemcpyAsync(d_raw, raw, sizeof(float) * n_samples_total, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    NPH_TRY(nph_trim_device(ctx, d_raw, n_samples_total, reads, n_reads, trim_start, trim_end, varseg_chunk, varseg_thresh,
+                            ctx->d_abea_scratch.p + b_raw, ranges_out));
+    ctx->last_launches = 1;
+    ctx->timing_valid = true;
     return NPH_OK;
 }
 
@@ -424,37 +444,34 @@ extern "C" int nph_recalibrate_batch(nph_ctx* ctx, const nph_read* reads, size_t
     NPH_TRY(nph_reserve(ctx, ctx->d_abea_scratch, b_ev + b_reads + b_rk + b_jobs + b_res + b_pairs + b_b2e + b_cal + 256));
     ctx->abea_loaded = false;
     uint8_t* base = ctx->d_abea_scratch.p;
-    CalParams p{};
+    NphCalArgs a{};
     float* d_ev = reinterpret_cast<float*>(base); base += b_ev;
     nph_read* d_reads = reinterpret_cast<nph_read*>(base); base += b_reads;
     uint32_t* d_rk = reinterpret_cast<uint32_t*>(base); base += b_rk;
     nph_abea_job* d_jobs = reinterpret_cast<nph_abea_job*>(base); base += b_jobs;
     nph_abea_result* d_res = reinterpret_cast<nph_abea_result*>(base); base += b_res;
     nph_aligned_pair* d_pairs = reinterpret_cast<nph_aligned_pair*>(base); base += b_pairs;
-    p.b2e = reinterpret_cast<nph_event_range*>(base); base += b_b2e;
-    p.out = reinterpret_cast<nph_calibration*>(base); base += b_cal;
-    p.bad_input = reinterpret_cast<int*>(base);
-    p.ev_mean = d_ev; p.reads = d_reads; p.models = ctx->d_models.p; p.model_id = model_id; p.ranks = d_rk; p.jobs = d_jobs;
-    p.results = d_res; p.pairs = d_pairs; p.n_jobs = (uint32_t)n_jobs;
+    a.b2e = reinterpret_cast<nph_event_range*>(base); base += b_b2e;
+    a.out = reinterpret_cast<nph_calibration*>(base); base += b_cal;
+    a.bad_input = reinterpret_cast<int*>(base);
+    a.ev_mean = d_ev; a.reads = d_reads; a.model_id = model_id; a.ranks = d_rk; a.jobs = d_jobs;
+    a.results = d_res; a.pairs = d_pairs; a.n_jobs = (uint32_t)n_jobs;
     NPH_CUDA(ctx, cudaMemcpyAsync(d_ev, ev_mean, sizeof(float) * n_events_total, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(d_reads, reads, sizeof(nph_read) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(d_rk, kmer_ranks, sizeof(uint32_t) * n_ranks_total, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(d_jobs, jobs, sizeof(nph_abea_job) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(d_res, results, sizeof(nph_abea_result) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
     if (pairs_total) NPH_CUDA(ctx, cudaMemcpyAsync(d_pairs, pairs, sizeof(nph_aligned_pair) * pairs_total, cudaMemcpyHostToDevice, ctx->stream));
-    NPH_CUDA(ctx, cudaMemsetAsync(p.bad_input, 0, sizeof(int), ctx->stream));
     NPH_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    const int grid = (int)std::min<size_t>((n_jobs + kCalWarps - 1) / kCalWarps, (size_t)ctx->sm_count * 8);
-    recalibrate_kernel<<<grid, kCalWarps * 32, 0, ctx->stream>>>(p);
-    NPH_CUDA(ctx, cudaGetLastError());
+    NPH_TRY(nph_launch_recalibrate(ctx, a));
     NPH_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->last_launches = 1;
     ctx->timing_valid = true;
     int bad = 0;
-    NPH_CUDA(ctx, cudaMemcpyAsync(calibrations_out, p.out, sizeof(nph_calibration) * n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(calibrations_out, a.out, sizeof(nph_calibration) * n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
     if (base_to_event_out)
-        NPH_CUDA(ctx, cudaMemcpyAsync(base_to_event_out, p.b2e, sizeof(nph_event_range) * n_ranks_total, cudaMemcpyDeviceToHost, ctx->stream));
-    NPH_CUDA(ctx, cudaMemcpyAsync(&bad, p.bad_input, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        NPH_CUDA(ctx, cudaMemcpyAsync(base_to_event_out, a.b2e, sizeof(nph_event_range) * n_ranks_total, cudaMemcpyDeviceToHost, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(&bad, a.bad_input, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (bad) { ctx->last_error = "nph_recalibrate_batch: an aligned pair lies outside its read or sequence"; return NPH_ERR_INVALID; }
     return NPH_OK;

@@ -178,6 +178,24 @@ class Engine:
                                                    _p(results), _p(b2e), _p(cal)), "nph_recalibrate_batch")
         return b2e, cal
 
+    def load_from_raw_batch(self, raw, kmer_ranks, jobs, model_id, params, events_cap=None, pinned=None):
+        """SquiggleRead::load_from_raw for a batch in one call.  Returns (event_off u64[n+1], mean, stdv, start_time,
+        duration, base_to_event EVENT_RANGE_DT[n_ranks], CALIBRATION_DT[n_jobs]); event arrays are compact, job order."""
+        n = jobs.shape[0]
+        cap = int(events_cap if events_cap is not None else raw.shape[0] // 3 + 16 * n)
+        off = np.zeros(n + 1, np.uint64)
+        if pinned is not None:
+            mean, stdv, start, dur = pinned
+        else:
+            mean = np.zeros(cap, np.float32); stdv = np.zeros(cap, np.float32); start = np.zeros(cap, np.float64); dur = np.zeros(cap, np.float32)
+        b2e = np.zeros(kmer_ranks.shape[0], EVENT_RANGE_DT)
+        cal = np.zeros(n, CALIBRATION_DT)
+        self._check(self.lib.nph_load_from_raw_batch(self.ctx, _p(raw), raw.shape[0], _p(kmer_ranks), kmer_ranks.shape[0], _p(jobs), n, model_id,
+                                                     _p(params), _p(off), _p(mean), _p(stdv), _p(start), _p(dur), cap, _p(b2e), _p(cal)),
+                    "nph_load_from_raw_batch")
+        tot = int(off[-1])
+        return off, mean[:tot], stdv[:tot], start[:tot], dur[:tot], b2e, cal
+
     # ---- measurement ----------------------------------------------------------------------
     def sync(self):
         self._check(self.lib.nph_sync(self.ctx), "nph_sync")

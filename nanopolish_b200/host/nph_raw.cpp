@@ -79,85 +79,41 @@ std::vector<std::unique_ptr<SquiggleRead>> load_from_raw(Engine& engine, const P
         sr.base_model[0] = &base_model;
         sr.sample_rate = raw[i].sample_rate;
     }
-    if (n == 0) { if (stats) *stats = st; return reads; }
-
-    // 1. trim: scrappie's defaults, hard-coded at the call site
-    std::vector<uint64_t> off(n);
-    size_t total = 0;
-    for (size_t i = 0; i < n; ++i) { off[i] = total; total += raw[i].samples.size(); }
-    std::vector<float> flat(total);
-    std::vector<nph_raw_read> rr(n);
-    for (size_t i = 0; i < n; ++i) {
-        std::copy(raw[i].samples.begin(), raw[i].samples.end(), flat.begin() + off[i]);
-        rr[i] = nph_raw_read{off[i], 0, (uint32_t)raw[i].samples.size(), 0};
-    }
-    std::vector<nph_raw_range> range(n, nph_raw_range{0, 0});
-    if (total) engine.check(nph_trim_raw_batch(engine.ctx(), flat.data(), total, rr.data(), n, 200, 10, 100, 0.0f, range.data()), "nph_trim_raw_batch");
-
-    // 2. events
-    std::vector<std::vector<nph_event>> events = detect_batch(engine, flat, off, range, event_detection_defaults);
-
-    // 3. SquiggleEvent conversion; reads that can go on to alignment
-    std::vector<uint32_t> live;
-    for (size_t i = 0; i < n; ++i) {
-        SquiggleRead& sr = *reads[i];
-        const std::vector<nph_event>& et = events[i];
-        if (et.empty() || sr.read_sequence.size() < k) { ++st.empty_after_trim; continue; }
-        sr.events[0].resize(et.size());
-        double start_time = 0;
-        for (size_t e = 0; e < et.size(); ++e) {
-            const float length_in_seconds = (float)(et[e].length / sr.sample_rate);
-            sr.events[0][e] = SquiggleEvent{et[e].mean, et[e].stdv, start_time, length_in_seconds, logf(et[e].stdv)};
-            start_time += length_in_seconds;
-        }
-        live.push_back((uint32_t)i);
-    }
-    if (live.empty()) { if (stats) *stats = st; return reads; }
-
-    // 4. flatten once: events, ranks, jobs shared by MoM, ABEA and the calibration
-    std::vector<nph_read> nr(live.size());
-    std::vector<nph_abea_job> jobs(live.size());
-    std::vector<float> mean;
-    std::vector<double> time;
+    // reads the device call cannot take (no samples, sequence shorter than a k-mer) fail like a read that trims to nothing
+    std::vector<uint32_t> sent;
+    std::vector<nph_raw_job> jobs;
     std::vector<uint32_t> ranks;
-    uint64_t pairs_total = 0;
-    for (size_t t = 0; t < live.size(); ++t) {
-        const SquiggleRead& sr = *reads[live[t]];
-        const std::vector<SquiggleEvent>& ev = sr.events[0];
-        const uint32_t n_kmers = (uint32_t)(sr.read_sequence.size() - k + 1);
-        nr[t] = nph_read{mean.size(), (uint32_t)ev.size(), 0, 1.0, 0.0, 0.0, 1.0, 0.0, 0.0};
-        jobs[t] = nph_abea_job{ranks.size(), pairs_total, (uint32_t)t, n_kmers, (uint32_t)ev.size() + n_kmers, 0};
-        pairs_total += jobs[t].pairs_cap;
-        for (const SquiggleEvent& e : ev) { mean.push_back(e.mean); time.push_back(e.start_time); }
-        for (uint32_t i = 0; i < n_kmers; ++i) ranks.push_back(base_model.pmalphabet->kmer_rank(sr.read_sequence.c_str() + i, k));
+    size_t total = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (raw[i].samples.empty() || raw[i].read_sequence.size() < k || !(raw[i].sample_rate > 0.0)) { ++st.empty_after_trim; continue; }
+        const uint32_t n_kmers = (uint32_t)(raw[i].read_sequence.size() - k + 1);
+        jobs.push_back(nph_raw_job{total, ranks.size(), (uint32_t)raw[i].samples.size(), n_kmers, raw[i].sample_rate});
+        for (uint32_t j = 0; j < n_kmers; ++j) ranks.push_back(base_model.pmalphabet->kmer_rank(raw[i].read_sequence.c_str() + j, k));
+        total += raw[i].samples.size();
+        sent.push_back((uint32_t)i);
     }
-    const uint32_t mid = engine.model_id(&base_model);
+    if (sent.empty()) { if (stats) *stats = st; return reads; }
+    std::vector<float> flat(total);
+    for (size_t t = 0; t < sent.size(); ++t) std::copy(raw[sent[t]].samples.begin(), raw[sent[t]].samples.end(), flat.begin() + jobs[t].sample_off);
 
-    // 5. method-of-moments scalings (drift 0, var 1)
-    std::vector<double> ss(2 * live.size());
-    engine.check(nph_mom_batch(engine.ctx(), nr.data(), nr.size(), mean.data(), mean.size(), ranks.data(), ranks.size(), jobs.data(), jobs.size(),
-                               mid, ss.data()), "nph_mom_batch");
-    for (size_t t = 0; t < live.size(); ++t) {
-        reads[live[t]]->scalings[0].set4(ss[2 * t], ss[2 * t + 1], 0.0, 1.0);
-        nr[t].shift = ss[2 * t]; nr[t].scale = ss[2 * t + 1];
-    }
-
-    // 6. event alignment
-    std::vector<nph_aligned_pair> pairs(pairs_total);
-    std::vector<nph_abea_result> res(live.size());
-    engine.check(nph_abea_batch(engine.ctx(), nr.data(), nr.size(), mean.data(), time.data(), mean.size(), ranks.data(), ranks.size(),
-                                jobs.data(), jobs.size(), mid, pairs.data(), pairs.size(), res.data()), "nph_abea_batch");
-
-    // 7. base-to-event map, events per base, recalibration, QC
+    const size_t cap = total / 3 + 16 * sent.size();
+    std::vector<uint64_t> off(sent.size() + 1);
+    std::vector<float> mean(cap), stdv(cap), dur(cap);
+    std::vector<double> start(cap);
     std::vector<nph_event_range> b2e(ranks.size());
-    std::vector<nph_calibration> cal(live.size());
-    engine.check(nph_recalibrate_batch(engine.ctx(), nr.data(), nr.size(), mean.data(), mean.size(), ranks.data(), ranks.size(), jobs.data(),
-                                       jobs.size(), mid, pairs.data(), pairs.size(), res.data(), b2e.data(), cal.data()), "nph_recalibrate_batch");
-    for (size_t t = 0; t < live.size(); ++t) {
-        SquiggleRead& sr = *reads[live[t]];
+    std::vector<nph_calibration> cal(sent.size());
+    engine.check(nph_load_from_raw_batch(engine.ctx(), flat.data(), flat.size(), ranks.data(), ranks.size(), jobs.data(), jobs.size(),
+                                         engine.model_id(&base_model), &event_detection_defaults, off.data(), mean.data(), stdv.data(),
+                                         start.data(), dur.data(), cap, b2e.data(), cal.data()),
+                 "nph_load_from_raw_batch");
+
+    for (size_t t = 0; t < sent.size(); ++t) {
+        SquiggleRead& sr = *reads[sent[t]];
         const nph_calibration& c = cal[t];
-        if (c.status & NPH_CAL_NOT_ALIGNED) {
-            sr.events[0].clear();
+        if (c.status & NPH_CAL_EMPTY_AFTER_TRIM) { ++st.empty_after_trim; continue; }
+        // scalings: the MoM estimate, replaced by the recalibrated set unless recalibration was refused
+        sr.scalings[0].set4(c.shift, c.scale, c.drift, c.var);
+        if (c.status & NPH_CAL_NOT_ALIGNED) {                      // squiggle_read.cpp:324-329
             sr.events_per_base[0] = 0.0;
             ++st.failed_alignment;
             continue;
@@ -168,9 +124,14 @@ std::vector<std::unique_ptr<SquiggleRead>> load_from_raw(Engine& engine, const P
             sr.base_to_event_map[i].indices[0] = IndexPair{r.start, r.stop};
         }
         sr.events_per_base[0] = c.events_per_base;
-        if (!(c.status & NPH_CAL_TOO_FEW_EVENTS)) sr.scalings[0].set4(c.shift, c.scale, c.drift, c.var);
-        if (c.status & (NPH_CAL_TOO_FEW_EVENTS | NPH_CAL_HIGH_VAR)) { sr.events[0].clear(); ++st.failed_calibration; }
-        else if (c.status & NPH_CAL_TOO_MANY_STAYS) { sr.events[0].clear(); sr.events[1].clear(); ++st.qc_fail; }
+        if (c.status & (NPH_CAL_TOO_FEW_EVENTS | NPH_CAL_HIGH_VAR)) { ++st.failed_calibration; continue; }   // :319-323
+        if (c.status & NPH_CAL_TOO_MANY_STAYS) { ++st.qc_fail; continue; }                                      // :331-336
+        const size_t ne = off[t + 1] - off[t];
+        sr.events[0].resize(ne);
+        for (size_t e = 0; e < ne; ++e) {
+            const size_t g = off[t] + e;
+            sr.events[0][e] = SquiggleEvent{mean[g], stdv[g], start[g], dur[g], logf(stdv[g])};
+        }
     }
     if (stats) *stats = st;
     return reads;

@@ -9,7 +9,7 @@
 //   recalibrate_model + QC                          ref: src/nanopolish_squiggle_read.cpp:304-336
 //
 // The reference does this per read inside the SquiggleRead constructor (one read per OpenMP thread); here the reads
-// of a BamProcessor batch / an AlignmentDB region go through five batched device calls.  DNA reads only: the RNA
+// of a BamProcessor batch / an AlignmentDB region go through one device call (nph_load_from_raw_batch).  DNA reads only: the RNA
 // branch (different kit, event reversal) is not on the accelerated path.
 #pragma once
 #include "nph_host.hpp"

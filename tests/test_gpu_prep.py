@@ -155,3 +155,62 @@ def test_raw_to_calibrated_read_chain(engine, nuc, port_oracle):
         assert np.array_equal(b2e[int(jobs[i]["rank_off"]):][:int(jobs[i]["n_kmers"])], want[i]["b2e"])
     assert (cal["status"] == 0).all()
     assert np.abs(cal["scale"] - 1.0).max() < 0.06 and np.abs(cal["shift"]).max() < 6.0 and (cal["var"] < 2.0).all()
+
+
+def _raw_jobs(signals, seqs, k, sample_rate=4000.0):
+    jobs = np.zeros(len(signals), synth.RAW_JOB_DT)
+    ranks = []
+    soff = roff = 0
+    for i, (x, c) in enumerate(zip(signals, seqs)):
+        rk = synth.kmer_ranks_from_codes(c, k, 4)
+        jobs[i] = (soff, roff, x.shape[0], rk.shape[0], sample_rate)
+        ranks.append(rk)
+        soff += x.shape[0]
+        roff += rk.shape[0]
+    return np.concatenate(signals), np.concatenate(ranks).astype(np.uint32), jobs
+
+
+def test_load_from_raw_in_one_call(engine, nuc, port_oracle):
+    """nph_load_from_raw_batch (raw samples + basecall ranks in; events, event map, scalings and QC out) vs the chain
+    through the oracle, including reads that die at each stage."""
+    from tests.prep_chain import oracle_chain
+    model, mid = nuc
+    raw, rr, seqs = synth.gen_raw(5, 20000, model, seed=640, return_seqs=True)
+    signals = [raw[int(r["sample_off"]):int(r["sample_off"]) + int(r["n_samples"])] for r in rr]
+    signals.insert(2, np.full(3000, 77.0, np.float32)); seqs.insert(2, seqs[0][:300])          # nothing survives the trim
+    short, _, sq = synth.gen_raw(1, 2400, model, seed=77, return_seqs=True)                      # alignment fails
+    signals.append(short); seqs.append(sq[0])
+    signals.append(_stalled(model, 12, 9000, leader=700, tail=400)); seqs.append(synth.gen_raw(1, 9000, model, seed=12, return_seqs=True)[2][0])
+    signals.append(np.full(57, 90.0, np.float32)); seqs.append(seqs[0][:20])                    # shorter than one chunk
+    tiny, _, tq = synth.gen_raw(1, 330, model, seed=5, return_seqs=True)                         # a handful of events
+    signals.append(tiny); seqs.append(tq[0])
+    want = oracle_chain(port_oracle, model, signals, seqs)
+    flat, ranks, jobs = _raw_jobs(signals, seqs, model.k)
+    off, mean, stdv, start, dur, b2e, cal = engine.load_from_raw_batch(flat, ranks, jobs, mid, synth.event_params(False))
+    kinds = set()
+    for i, w in enumerate(want):
+        o, n = int(off[i]), int(off[i + 1] - off[i])
+        if w["events"] is None:
+            assert n == 0 and int(cal[i]["status"]) & 16
+            kinds.add("trim")
+            continue
+        ev = w["events"]
+        assert n == ev.shape[0]
+        assert np.array_equal(mean[o:o + n], ev["mean"]) and np.array_equal(stdv[o:o + n], ev["stdv"])
+        assert np.array_equal(dur[o:o + n], w["duration"]) and np.array_equal(start[o:o + n], w["start_time"])
+        assert cal[i].tobytes() == w["cal"].tobytes(), f"read {i}: {cal[i]} != {w['cal']}"
+        assert np.array_equal(b2e[int(jobs[i]["rank_off"]):][:int(jobs[i]["n_kmers"])], w["b2e"])
+        kinds.add(int(w["cal"]["status"]))
+    assert {"trim", 0, 1} <= kinds
+    ms, launches = engine.last_kernel_ms()
+    assert ms > 0 and launches >= 9
+    # capacity too small for the events is reported, not overrun
+    with pytest.raises(NphError):
+        engine.load_from_raw_batch(flat, ranks, jobs, mid, synth.event_params(False), events_cap=1000)
+    # a context that just ran the chain still scores (resident state was invalidated, not corrupted)
+    rs = synth.gen_reads(3, 600, model, seed=2)
+    hj = synth.scorereads_jobs(rs, 200, model_id=mid)
+    got = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, hj.kmer_ranks, hj.jobs)
+    oj = hj.jobs.copy(); oj["model_id"] = 0
+    wantS, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [model], hj.kmer_ranks, oj)
+    assert np.array_equal(got.view(np.uint32), wantS.view(np.uint32))
