@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="scorereads", choices=["scorereads", "methylation", "abea", "events"])
+    ap.add_argument("--workload", default="scorereads", choices=["scorereads", "methylation", "abea", "events", "prologue"])
     ap.add_argument("--reads", type=int, default=10000, help="reads per GPU")
     ap.add_argument("--events", type=int, default=4000, help="events per read")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -233,7 +233,8 @@ def workload_config(args, jobs, reads_override=None):
 def run_aux(args, rank, world, local, saved_stdout):
     """Auxiliary single-GPU measurements of the other kernels of the path (not the headline metric):
     --workload abea   : adaptive banded event alignment, reads x 8000 events (BASELINE configs[3] shape), events/s
-    --workload events : scrappie event detection, reads x 36000 raw samples, samples/s"""
+    --workload events : scrappie event detection, reads x 36000 raw samples, samples/s
+    --workload prologue : SquiggleRead::load_from_raw in one call (trim, events, MoM, ABEA, calibration), samples/s"""
     if rank != 0:
         return
     import torch
@@ -269,6 +270,68 @@ def run_aux(args, rank, world, local, saved_stdout):
                 "roofline": {"bound": "hbm", "achieved": b_alg / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": b_alg / (t * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel": "abea_kernel",
                              "note": "sequentially dependent bands: issue/latency bound (DESIGN.md section 5)"}}
+    elif args.workload == "prologue":
+        n_reads = min(args.reads, 2048)
+        base = min(n_reads, 256)
+        raw, rr, seqs = synth.gen_raw(base, 36000, nuc, seed=5, return_seqs=True)
+        signals = [raw[int(r["sample_off"]):int(r["sample_off"]) + int(r["n_samples"])] for r in rr]
+        reps = max(1, n_reads // base)
+        jobs = np.zeros(base * reps, synth.RAW_JOB_DT)
+        rk = [synth.kmer_ranks_from_codes(c, nuc.k, 4) for c in seqs]
+        soff = roff = 0
+        for i in range(base * reps):
+            b = i % base
+            jobs[i] = (soff, roff, signals[b].shape[0], rk[b].shape[0], 4000.0)
+            soff += signals[b].shape[0]; roff += rk[b].shape[0]
+        flat = torch.from_numpy(np.tile(raw, reps)).pin_memory().numpy()          # pinned host buffers, like a caller staging a batch
+        ranks = torch.from_numpy(np.tile(np.concatenate(rk).astype(np.uint32), reps).view(np.int32)).pin_memory().numpy().view(np.uint32)
+        cap = flat.shape[0] // 3 + 16 * jobs.shape[0]
+        pin = lambda n, dt: torch.empty(n, dtype=dt).pin_memory().numpy()
+        pinned = (pin(cap, torch.float32), pin(cap, torch.float32), pin(cap, torch.float64), pin(cap, torch.float32),
+                  pin(2 * ranks.shape[0], torch.int32).view(synth.EVENT_RANGE_DT), pin(48 * jobs.shape[0], torch.uint8).view(synth.CALIBRATION_DT))
+        prm = synth.event_params(False)
+        ms, e2e = [], []
+        for it in range(max(3, args.warmup) + args.steps):
+            t0 = time.perf_counter()
+            off, mean, stdv, start, dur, b2e, cal = eng.load_from_raw_batch(flat, ranks, jobs, mid, prm, events_cap=cap, pinned=pinned)
+            dt = time.perf_counter() - t0
+            if it >= max(3, args.warmup):
+                m, nl = eng.last_kernel_ms(); ms.append(m); e2e.append(dt)
+        t = float(np.mean(ms))
+        n_ev = int(off[-1])
+        ok = int((cal["status"] == 0).sum())
+        b_alg = flat.nbytes + 20 * n_ev + 8 * ranks.shape[0] + 48 * jobs.shape[0]
+        cpu = None
+        if not args.no_cpu_baseline:
+            from concurrent.futures import ThreadPoolExecutor
+            from oracle.oracle_py import PortOracle
+            from oracle.prep_chain import oracle_chain
+            port = PortOracle()
+            cores = os.cpu_count() or 1
+            ns = min(base, max(cores, 32))
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(cores) as ex:       # the C restatement releases the GIL inside each call
+                list(ex.map(lambda i: oracle_chain(port, nuc, [signals[i]], [seqs[i]]), range(ns)))
+            cs = time.perf_counter() - t0
+            cpu = {"value": sum(signals[i].shape[0] for i in range(ns)) / cs, "unit": "samples/s", "cores": cores, "kind": "port",
+                   "sample": f"{ns} of the {jobs.shape[0]} reads through oracle/ (trim, events, MoM, ABEA, calibration), one read per thread"}
+        line = {"metric": "load_from_raw_samples_per_sec", "value": flat.shape[0] / (t * 1e-3), "unit": "samples/s", "n_gpus": 1,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+                "config": {"workload": f"prologue: {jobs.shape[0]} synthetic raw reads x 36000 samples -> calibrated SquiggleReads "
+                                       f"({n_ev} events, {ok} reads pass QC), scrappie DNA parameters, k=6 nucleotide model",
+                           "reads_per_sec_device": jobs.shape[0] / (t * 1e-3), "reads_per_sec_e2e": jobs.shape[0] / float(np.mean(e2e))},
+                "e2e": {"value": flat.shape[0] / float(np.mean(e2e)), "unit": "samples/s", "h2d_bytes_per_step": int(flat.nbytes + ranks.nbytes + jobs.nbytes),
+                        "d2h_bytes_per_step": int(20 * n_ev + 8 * ranks.shape[0] + 48 * jobs.shape[0]), "steps": args.steps,
+                        "api": "nph_load_from_raw_batch"},
+                "gpu_launches": int(nl) * args.steps,
+                "roofline": {"bound": "hbm", "achieved": b_alg / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": b_alg / (t * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel": "trim + ed_* + convert + mom + abea + recalibrate (summed device time of the stages)",
+                             "note": "algorithmic bytes = 4 B/sample in + 20 B/event + 8 B/k-mer + 48 B/read out; dominated by the "
+                                     "latency-bound ABEA walk at this batch size"}}
+        if cpu:
+            line["cpu_baseline"] = cpu
     else:
         n_reads = min(args.reads, 8192)
         raw, reads = synth.gen_raw(min(n_reads, 512), 36000, nuc, seed=5)
@@ -317,7 +380,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.workload in ("abea", "events"):
+    if args.workload in ("abea", "events", "prologue"):
         run_aux(args, rank, world, local, saved_stdout)
         return
     if args.impl == "reference":

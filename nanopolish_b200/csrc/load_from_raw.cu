@@ -109,8 +109,9 @@ extern "C" int nph_load_from_raw_batch(nph_ctx* ctx, const float* raw, size_t n_
         if (jb.sample_off + jb.n_samples > n_samples_total || jb.n_kmers == 0 || jb.rank_off + jb.n_kmers > n_ranks_total || !(jb.sample_rate > 0.0))
             return NPH_ERR_INVALID;
     }
-    for (size_t i = 0; i < n_ranks_total; ++i)
-        if (kmer_ranks[i] >= n_states) return NPH_ERR_INVALID;
+    uint32_t max_rank = 0;
+    for (size_t i = 0; i < n_ranks_total; ++i) max_rank = std::max(max_rank, kmer_ranks[i]);     // branch-free: vectorises
+    if (max_rank >= n_states) return NPH_ERR_INVALID;
     NPH_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->reads_loaded = false; ctx->jobs_loaded = false; ctx->abea_loaded = false;    // resident batches are replaced
 
@@ -142,8 +143,8 @@ extern "C" int nph_load_from_raw_batch(nph_ctx* ctx, const float* raw, size_t n_
     }
     std::vector<uint32_t> live;
     for (size_t j = 0; j < n_jobs; ++j) if (range[j].end > range[j].start) live.push_back((uint32_t)j);
-    if (base_to_event_out) for (size_t i = 0; i < n_ranks_total; ++i) base_to_event_out[i] = nph_event_range{-1, -1};
     if (live.empty()) {
+        if (base_to_event_out) for (size_t i = 0; i < n_ranks_total; ++i) base_to_event_out[i] = nph_event_range{-1, -1};
         for (size_t j = 0; j <= n_jobs; ++j) event_off_out[j] = 0;
         ctx->last_launches = launches; ctx->staged_ms = staged_ms; ctx->timing_valid = 2;
         return NPH_OK;

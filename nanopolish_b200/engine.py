@@ -184,12 +184,12 @@ class Engine:
         n = jobs.shape[0]
         cap = int(events_cap if events_cap is not None else raw.shape[0] // 3 + 16 * n)
         off = np.zeros(n + 1, np.uint64)
-        if pinned is not None:
-            mean, stdv, start, dur = pinned
+        if pinned is not None:            # caller-staged output buffers (e.g. page-locked): mean, stdv, start_time, duration, b2e, cal
+            mean, stdv, start, dur, b2e, cal = pinned
         else:
             mean = np.zeros(cap, np.float32); stdv = np.zeros(cap, np.float32); start = np.zeros(cap, np.float64); dur = np.zeros(cap, np.float32)
-        b2e = np.zeros(kmer_ranks.shape[0], EVENT_RANGE_DT)
-        cal = np.zeros(n, CALIBRATION_DT)
+            b2e = np.zeros(kmer_ranks.shape[0], EVENT_RANGE_DT)
+            cal = np.zeros(n, CALIBRATION_DT)
         self._check(self.lib.nph_load_from_raw_batch(self.ctx, _p(raw), raw.shape[0], _p(kmer_ranks), kmer_ranks.shape[0], _p(jobs), n, model_id,
                                                      _p(params), _p(off), _p(mean), _p(stdv), _p(start), _p(dur), cap, _p(b2e), _p(cal)),
                     "nph_load_from_raw_batch")

@@ -1,4 +1,4 @@
-"""The load_from_raw chain through the ORACLE (test infrastructure): trim -> detect_events -> SquiggleEvent conversion
+"""TEST INFRASTRUCTURE ONLY.  The load_from_raw chain through the ORACLE: trim -> detect_events -> SquiggleEvent conversion
 -> MoM -> ABEA -> base_to_event_map / recalibration, in the order src/nanopolish_squiggle_read.cpp:226-336 runs them."""
 import numpy as np
 
@@ -8,11 +8,7 @@ from nanopolish_b200 import synth
 def squiggle_events(ev, sample_rate):
     """events -> (duration f32, start_time f64) as squiggle_read.cpp:243-250 computes them (sequential double sum)."""
     dur = (ev["length"].astype(np.float64) / sample_rate).astype(np.float32)
-    t = np.zeros(ev.shape[0], np.float64)
-    acc = 0.0
-    for i in range(ev.shape[0]):
-        t[i] = acc
-        acc += float(dur[i])
+    t = np.concatenate([[0.0], np.cumsum(dur.astype(np.float64))[:-1]]) if ev.shape[0] else np.zeros(0)   # cumsum folds left to right
     return dur, t
 
 

@@ -122,7 +122,7 @@ def test_calibration_homopolymers_failed_reads_and_odd_pair_lists(engine, nuc, p
 def test_raw_to_calibrated_read_chain(engine, nuc, port_oracle):
     """trim -> detect_events -> MoM -> ABEA -> calibration through the C ABI vs the same chain through the oracle: the
     order SquiggleRead::load_from_raw runs them in (src/nanopolish_squiggle_read.cpp:226-336)."""
-    from tests.prep_chain import oracle_chain, squiggle_events
+    from oracle.prep_chain import oracle_chain, squiggle_events
     model, mid = nuc
     n_reads = 4
     raw, rreads, seqs = synth.gen_raw(n_reads, 30000, model, seed=501, return_seqs=True)
@@ -173,7 +173,7 @@ def _raw_jobs(signals, seqs, k, sample_rate=4000.0):
 def test_load_from_raw_in_one_call(engine, nuc, port_oracle):
     """nph_load_from_raw_batch (raw samples + basecall ranks in; events, event map, scalings and QC out) vs the chain
     through the oracle, including reads that die at each stage."""
-    from tests.prep_chain import oracle_chain
+    from oracle.prep_chain import oracle_chain
     model, mid = nuc
     raw, rr, seqs = synth.gen_raw(5, 20000, model, seed=640, return_seqs=True)
     signals = [raw[int(r["sample_off"]):int(r["sample_off"]) + int(r["n_samples"])] for r in rr]

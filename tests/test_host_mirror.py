@@ -218,7 +218,7 @@ def test_abea_and_mom_like_a_caller(host, port_oracle):
 def test_load_from_raw_like_a_caller(host, port_oracle):
     """nph::load_from_raw over a batch (raw samples + basecalls in, SquiggleReads out) against the same chain through
     the oracle: identical events, bit-identical scalings, identical base_to_event_map and the same reads dropped."""
-    from tests.prep_chain import oracle_chain
+    from oracle.prep_chain import oracle_chain
     nuc = synth.load_model("nucleotide")
     raw, rr, seqs = synth.gen_raw(4, 24000, nuc, seed=901, return_seqs=True)
     signals = [raw[int(r["sample_off"]):int(r["sample_off"]) + int(r["n_samples"])] for r in rr]
