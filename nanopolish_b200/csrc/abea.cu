@@ -31,11 +31,17 @@
 
 namespace {
 
-constexpr int kWarps = 20;
+#ifndef NPH_ABEA_WARPS
+#define NPH_ABEA_WARPS 20
+#endif
+constexpr int kWarps = NPH_ABEA_WARPS;
 constexpr int kThreads = kWarps * 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kBW = 100;                 // ALN_BANDWIDTH (raw_loader.cpp:72)
-constexpr int kTraceBlockRows = 64;      // band rows fetched per backtrack block
+#ifndef NPH_ABEA_TRACE_ROWS
+#define NPH_ABEA_TRACE_ROWS 64
+#endif
+constexpr int kTraceBlockRows = NPH_ABEA_TRACE_ROWS;      // band rows fetched per backtrack block
 constexpr int kFromD = 0, kFromU = 1, kFromL = 2;
 
 struct AbeaJobConsts { double lp_stay; double lp_step; };
@@ -143,6 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
         const int uK = K + 128;
         const int laneK = uK & 31, slotK = (uK >> 5) & 3;
 
+        float4 g_next = (lo + 128 <= K) ? prm[lo + 128 - 1] : make_float4(0.f, 1.f, 0.f, 1.f);   // Gaussian of the next column to enter a slot
         for (int bi = 2; bi < n_bands; ++bi) {
             // Suzuki's rule on the two ends of band bi-1 (offset 0 = column lo, offset 99 = column lo+99)
             bool right;
@@ -162,20 +169,20 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
             if (right) {
                 // column `lo` leaves the band for good: exactly one (lane, slot) owns it; that slot now follows
                 // column lo+128 (not yet in band: everything about it is -inf until the band reaches it)
+                // (its Gaussian was fetched at the previous right move, so no load sits on this band's critical path; the
+                // slot's event level is refreshed below like every other slot's and is not used before the band arrives)
                 const int u = lo + 128;
                 if (lane == (u & 31)) {
                     const int sl = (u >> 5) & 3;
                     const int cn = lo + 128;
-                    float4 g = make_float4(0.f, 1.f, 0.f, 1.f);
-                    if (cn <= K) g = prm[cn - 1];
-                    const int en = bi - 1 - cn;
-                    const float xv = lv[min(max(en, 0), E - 1)];
+                    const float4 g = g_next;
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
-                        if (s == sl) { cs[s] = cn; b1[s] = NEG; dg[s] = NEG; lf[s] = NEG; mu[s] = g.x; sd[s] = g.y; cc[s] = g.z; ry[s] = g.w; xn[s] = xv; }
+                        if (s == sl) { cs[s] = cn; b1[s] = NEG; dg[s] = NEG; lf[s] = NEG; mu[s] = g.x; sd[s] = g.y; cc[s] = g.z; ry[s] = g.w; }
                     }
                 }
                 lo += 1;
+                g_next = (lo + 128 <= K) ? prm[lo + 128 - 1] : make_float4(0.f, 1.f, 0.f, 1.f);
             }
             uint32_t tbyte = 0;
             const int hi = lo + (kBW - 1);

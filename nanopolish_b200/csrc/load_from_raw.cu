@@ -12,6 +12,8 @@
 #include "nph_internal.cuh"
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #define NPH_TRY(expr) do { int rc__ = (expr); if (rc__ != NPH_OK) return rc__; } while (0)
@@ -133,6 +135,8 @@ extern "C" int nph_load_from_raw_batch(nph_ctx* ctx, const float* raw, size_t n_
     std::vector<nph_raw_range> range(n_jobs);
     NPH_TRY(nph_trim_device(ctx, d_raw, n_samples_total, rr.data(), n_jobs, 200, 10, 100, 0.0f, arena, range.data())); ++launches;
     NPH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); staged_ms += ms;
+    const bool verbose = getenv("NPH_TIMING") != nullptr;
+    if (verbose) fprintf(stderr, "[nph] load_from_raw: trim %.2f ms", ms);
 
     // outputs of the reads that do not get as far as alignment
     for (size_t j = 0; j < n_jobs; ++j) {
@@ -169,6 +173,7 @@ extern "C" int nph_load_from_raw_batch(nph_ctx* ctx, const float* raw, size_t n_
     NPH_TRY(nph_detect_events_device(ctx, d_raw, n_samples_total, tr.data(), nl, params, arena, room, &d_events, &d_counts, counts, &ed_launches));
     launches += ed_launches;
     NPH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); staged_ms += ms;
+    if (verbose) fprintf(stderr, "  events %.2f ms", ms);
 
     // ---- 3. compact layout, SquiggleEvent conversion, outputs of the event arrays ----
     std::vector<uint64_t> out_off(nl + 1, 0);
@@ -234,6 +239,7 @@ extern "C" int nph_load_from_raw_batch(nph_ctx* ctx, const float* raw, size_t n_
         NPH_CUDA(ctx, cudaMemcpyAsync(ev_duration_out, d_dur, sizeof(float) * n_events_total, cudaMemcpyDeviceToHost, ctx->stream));
         NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         NPH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); staged_ms += ms;
+        if (verbose) fprintf(stderr, "  convert %.2f ms", ms);
     }
 
     // ---- 4. MoM scalings and event alignment (the arena becomes ABEA's band storage) ----
@@ -268,6 +274,7 @@ extern "C" int nph_load_from_raw_batch(nph_ctx* ctx, const float* raw, size_t n_
     NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (size_t t = 0; t < nl; ++t) calibrations_out[live[t]] = cal[t];
     NPH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); staged_ms += ms;     // ev0 was recorded at the ABEA launch
+    if (verbose) fprintf(stderr, "  abea+calibration %.2f ms  (total %.2f ms, %zu of %zu reads aligned)\n", ms, staged_ms, nl, n_jobs);
     ctx->last_launches = launches;
     ctx->staged_ms = staged_ms;
     ctx->timing_valid = 2;
