@@ -529,7 +529,14 @@ def main():
                          "note": "scalar log-semiring DP: issue/shared-memory bound, not HBM bound (DESIGN.md); "
                                  "block-cells/s below is the figure that moves",
                          "block_cells_per_sec_per_gpu": float(jobs.block_cells) / (kernel_ms * 1e-3),
-                         "issue_bound_estimate_cells_per_sec": 2.5e11},
+                         "issue_bound_estimate_cells_per_sec": 2.5e11,
+                         # the roofline that does bound this kernel: warp-instruction issue.  81 SASS instructions per block-cell is
+                         # the structural count of the steady-state loop (7 table log-sums x 8 + 13 FADD + 3 FMUL + 4 FFMA + 1, DESIGN.md
+                         # section 4; profiles/r01_hmm_forward_summary.md has ncu's measured issue-active figure)
+                         "issue": {"achieved": float(jobs.block_cells) / (kernel_ms * 1e-3) * 81 / 32, "unit": "warp-instructions/s",
+                                   "peak": 148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6,
+                                   "frac": float(jobs.block_cells) / (kernel_ms * 1e-3) * 81 / 32 / (148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
+                                   "instructions_per_block_cell": 81}},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
