@@ -31,4 +31,19 @@ mom = eng.mom_batch(rs3.reads, rs3.ev_mean, ar, aj, mid)
 assert np.isfinite(a).all() and np.isfinite(b).all() and np.isfinite(c).all() and np.isfinite(d).all()
 assert all(x.shape[0] > 0 for x in v) and (res["n_pairs"] > 0).all()
 print("sanitize smoke ok", a.shape, b.shape, c.shape, d.shape, len(v), res["n_pairs"])
+# raw-read prologue: trim, event detection (fast path + fallback), calibration, and the fused call
+raw, rr, seqs = synth.gen_raw(3, 6000, nuc, seed=9, return_seqs=True)
+sig = [raw[int(r["sample_off"]):int(r["sample_off"]) + int(r["n_samples"])] for r in rr]
+sig.append(np.full(900, 70.0, np.float32)); seqs.append(seqs[0][:80])
+flat = np.concatenate(sig)
+jobs = np.zeros(len(sig), synth.RAW_JOB_DT); rk = []
+so = ro = 0
+for i, (x, c) in enumerate(zip(sig, seqs)):
+    r_ = synth.kmer_ranks_from_codes(c, nuc.k, 4); jobs[i] = (so, ro, x.shape[0], r_.shape[0], 4000.0); rk.append(r_); so += x.shape[0]; ro += r_.shape[0]
+ranks = np.concatenate(rk).astype(np.uint32)
+rng = eng.trim_raw_batch(raw, rr)
+evs = eng.detect_events_batch(raw, rr, synth.event_params(False))
+out = eng.load_from_raw_batch(flat, ranks, jobs, mid, synth.event_params(False))
+b2e, cal = eng.recalibrate_batch(rs3.reads, rs3.ev_mean, ar, aj, mid, pairs, res)
+print("prologue ok", [int(c) for c in out[6]["status"]], int(out[0][-1]))
 eng.close()
