@@ -13,6 +13,11 @@
  *        estimate_scalings_using_mom          ref: src/nanopolish_raw_loader.cpp:17-60
  *   3. (section 8f "next" row N1) the Viterbi alignment with the same fill
  *        profile_hmm_align_r9         ref: src/hmm/nanopolish_profile_hmm_r9.cpp:73-204
+ *   4. (row N4) the raw-signal prologue that produces the reads the calls above consume
+ *        SquiggleRead::load_from_raw  ref: src/nanopolish_squiggle_read.cpp:226-336
+ *        trim_and_segment_raw         ref: src/thirdparty/scrappie/scrappie_common.c:122-190
+ *        detect_events                ref: src/thirdparty/scrappie/event_detection.c:268-319
+ *        recalibrate_model            ref: src/nanopolish_methyltrain.cpp:204-307
  *
  * The reference has no FFI layer: its seam is those C++ free functions, called with
  * HMMInputData / HMMInputSequence / SquiggleRead.  The C++ mirror of that call surface

@@ -7,7 +7,8 @@
 //                        get_eventalignment_for_1d_basecalls              ref: src/nanopolish_squiggle_read.cpp:340-391
 //                        recalibrate_model(scale_var=true, scale_drift=false)   ref: src/nanopolish_methyltrain.cpp:204-307
 //
-// Both are bit-exact restatements: medians are order statistics (found by rank counting, so no sort order matters),
+// Both are bit-exact restatements: medians are order statistics (only values at sorted positions are read, so no sort
+// order among equal samples can matter),
 // interpolated with the reference's float/double mix; the normal equations are summed in k-mer order by one lane
 // (FP64, no contraction), and the 2x2 solve is Eigen's full-pivot LU written out.
 #include "nph_internal.cuh"
@@ -50,35 +51,57 @@ __device__ __forceinline__ float quantile_mix(const QuantilePos q, float lo, flo
     return __double2float_rn(__dadd_rn(a, b));
 }
 
-// Order statistics q.idx and q.idx+1 of the n (<= 128) values a warp holds four per lane (slot s of lane l is
-// element l + 32 s; slots past n are ignored).  Rank = number of smaller elements, ties broken by index.
-__device__ __forceinline__ void warp_order_stats(const float (&v)[4], int n, const QuantilePos q, int lane, float& lo, float& hi)
+__device__ __forceinline__ float sel_slot(const float (&v)[4], int s)
 {
-    int rank[4] = {0, 0, 0, 0};
+    float r = v[0];
+    r = (s == 1) ? v[1] : r;
+    r = (s == 2) ? v[2] : r;
+    r = (s == 3) ? v[3] : r;
+    return r;
+}
+
+// Order statistics q.idx and q.idx+1 of the n (<= 128) values a warp holds four per lane (slot s of lane l is element
+// l + 32 s; slots past n must hold +inf).  A bitonic sorting network over the 128 slots: partners 1..16 apart sit in
+// another lane (shuffle), partners 32 or 64 apart in another slot of the same lane.  Only VALUES at sorted positions are
+// read, so how equal elements are ordered cannot matter (the reference's qsort comparator never reports equality
+// either).  ~300 instructions per sort instead of ~1500 for rank counting.
+__device__ __forceinline__ void warp_sort128(float (&v)[4], int lane)
+{
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const int cnt = min(32, n - 32 * s);
-        for (int l = 0; l < cnt; ++l) {
-            const float o = __shfl_sync(kFull, v[s], l);
-            const int oj = l + 32 * s;
+    for (int k = 2; k <= 128; k <<= 1) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int me = lane + 32 * t;
-                rank[t] += (o < v[t] || (o == v[t] && oj < me)) ? 1 : 0;
+        for (int j = k >> 1; j >= 1; j >>= 1) {
+            if (j >= 32) {
+                const int js = j >> 5;                         // partner slot distance: 1 or 2
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    if ((s & js) == 0) {
+                        const bool up = (((s << 5) & k) == 0);   // k is 64 or 128 here: direction depends on the slot only
+                        const float lo = fminf(v[s], v[s | js]), hi = fmaxf(v[s], v[s | js]);
+                        v[s] = up ? lo : hi;
+                        v[s | js] = up ? hi : lo;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const float o = __shfl_xor_sync(kFull, v[s], j);
+                    const int i = (s << 5) | lane;
+                    const bool up = ((i & k) == 0);
+                    const bool take_min = (((lane & j) == 0) == up);
+                    v[s] = take_min ? fminf(v[s], o) : fmaxf(v[s], o);
+                }
             }
         }
     }
-    float mine_lo = 0.0f, mine_hi = 0.0f;
-    bool have_lo = false, have_hi = false;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const bool valid = lane + 32 * t < n;
-        if (valid && rank[t] == (int)q.idx) { mine_lo = v[t]; have_lo = true; }
-        if (valid && rank[t] == (int)q.idx + 1) { mine_hi = v[t]; have_hi = true; }
-    }
-    const unsigned b_lo = __ballot_sync(kFull, have_lo), b_hi = __ballot_sync(kFull, have_hi);
-    lo = __shfl_sync(kFull, mine_lo, b_lo ? __ffs(b_lo) - 1 : 0);
-    hi = __shfl_sync(kFull, mine_hi, b_hi ? __ffs(b_hi) - 1 : 0);
+}
+
+__device__ __forceinline__ void warp_order_stats(float (&v)[4], const QuantilePos q, int lane, float& lo, float& hi)
+{
+    warp_sort128(v, lane);
+    const int p0 = (int)q.idx, p1 = min((int)q.idx + 1, 127);
+    lo = __shfl_sync(kFull, sel_slot(v, p0 >> 5), p0 & 31);
+    hi = __shfl_sync(kFull, sel_slot(v, p1 >> 5), p1 & 31);
 }
 
 struct TrimParams {
@@ -110,15 +133,16 @@ __global__ void __launch_bounds__(kTrimThreads) trim_kernel(const TrimParams p)
         // madf of every chunk (scrappie_common.c:98-119): median, absolute deviations, median again, * 1.4826f
         for (uint32_t c = wib; c < nchunk; c += kTrimWarps) {
             const float* xc = x + (size_t)c * p.chunk;
-            float v[4];
+            const float inf = __int_as_float(0x7f800000);
+            float x4[4], v[4];
 #pragma unroll
-            for (int s = 0; s < 4; ++s) v[s] = (lane + 32 * s < p.chunk) ? xc[lane + 32 * s] : 0.0f;
+            for (int s = 0; s < 4; ++s) { x4[s] = (lane + 32 * s < p.chunk) ? xc[lane + 32 * s] : inf; v[s] = x4[s]; }
             float lo, hi;
-            warp_order_stats(v, p.chunk, qc, lane, lo, hi);
+            warp_order_stats(v, qc, lane, lo, hi);
             const float med = quantile_mix(qc, lo, hi);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) v[s] = fabsf(__fsub_rn(v[s], med));
-            warp_order_stats(v, p.chunk, qc, lane, lo, hi);
+            for (int s = 0; s < 4; ++s) v[s] = (lane + 32 * s < p.chunk) ? fabsf(__fsub_rn(x4[s], med)) : inf;
+            warp_order_stats(v, qc, lane, lo, hi);
             if (lane == 0) mad[c] = __fmul_rn(quantile_mix(qc, lo, hi), 1.4826f);
         }
         if (threadIdx.x == 0) { s_first = (int)nchunk; s_last = -1; }
