@@ -227,6 +227,14 @@ int nph_hmm_align_batch(nph_ctx* ctx,
                         const nph_hmm_job* jobs, size_t n_jobs, double indel_bias,
                         nph_align_state* states_out, const uint64_t* states_off,
                         uint32_t* n_states_out, float* scores_out);
+/* The same against the reads a preceding nph_reads_load left resident in HBM: eventalign re-aligns one ~100-base
+ * segment per read per round (align_read_to_ref, src/alignment/nanopolish_eventalign.cpp:691-823), each round's
+ * jobs depending on the previous round's paths, so the events go up once and only jobs/states travel per round. */
+int nph_hmm_align(nph_ctx* ctx,
+                  const uint32_t* kmer_ranks, size_t n_ranks_total,
+                  const nph_hmm_job* jobs, size_t n_jobs, double indel_bias,
+                  nph_align_state* states_out, const uint64_t* states_off,
+                  uint32_t* n_states_out, float* scores_out);
 
 /* ---- event detection (section 8f N4: the step before ABEA) --------------------------------------
  * scrappie's detect_events as load_from_raw calls it: t-statistics over two windows on prefix sums, a short/long

@@ -330,6 +330,17 @@ extern "C" int nph_hmm_align_batch(nph_ctx* ctx,
 {
     if (!ctx || !jobs || !states_out || !states_off || !n_states_out || n_jobs == 0) return NPH_ERR_INVALID;
     NPH_TRY(nph_reads_load(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total));
+    return nph_hmm_align(ctx, kmer_ranks, n_ranks_total, jobs, n_jobs, indel_bias, states_out, states_off, n_states_out, scores_out);
+}
+
+extern "C" int nph_hmm_align(nph_ctx* ctx,
+                             const uint32_t* kmer_ranks, size_t n_ranks_total,
+                             const nph_hmm_job* jobs, size_t n_jobs, double indel_bias,
+                             nph_align_state* states_out, const uint64_t* states_off,
+                             uint32_t* n_states_out, float* scores_out)
+{
+    if (!ctx || !jobs || !states_out || !states_off || !n_states_out || n_jobs == 0) return NPH_ERR_INVALID;
+    if (!ctx->reads_loaded) return NPH_ERR_STATE;
     // jobs, ranks, transitions and validation go through the forward path's loader (same job semantics)
     NPH_TRY(nph_hmm_jobs_load(ctx, kmer_ranks, n_ranks_total, jobs, n_jobs, indel_bias));
 

@@ -118,6 +118,19 @@ class Engine:
                     "nph_hmm_align_batch")
         return [states[int(off[j]):int(off[j]) + int(counts[j])] for j in range(n)], scores
 
+    def hmm_align(self, kmer_ranks, jobs, indel_bias: float = 1.0):
+        """hmm_align_batch against the reads a preceding reads_load() left resident (eventalign's chained rounds)."""
+        n = jobs.shape[0]
+        E = np.abs(jobs["event_stop"].astype(np.int64) - jobs["event_start"].astype(np.int64)) + 1
+        off = np.zeros(n + 1, np.uint64)
+        off[1:] = np.cumsum(E + jobs["n_kmers"].astype(np.int64) + 2)
+        states = np.zeros(int(off[-1]), ALIGN_STATE_DT)
+        counts = np.zeros(n, np.uint32)
+        scores = np.zeros(n, np.float32)
+        self._check(self.lib.nph_hmm_align(self.ctx, _p(kmer_ranks), kmer_ranks.shape[0], _p(jobs), n, indel_bias,
+                                           _p(states), _p(off), _p(counts), _p(scores)), "nph_hmm_align")
+        return [states[int(off[j]):int(off[j]) + int(counts[j])] for j in range(n)], scores
+
     # ---- ABEA ---------------------------------------------------------------------------
     def abea_batch(self, reads, ev_mean, ev_start_time, kmer_ranks, jobs, model_id: int, pairs_total: int):
         pairs = np.zeros(pairs_total, PAIR_DT)

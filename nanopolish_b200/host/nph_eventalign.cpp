@@ -1,0 +1,513 @@
+// nph_eventalign.cpp — see nph_eventalign.hpp.
+#include "nph_eventalign.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+namespace nph {
+
+// ---------------------------------------------------------------------------------------------
+// AlignBatch / profile_hmm_align
+// ---------------------------------------------------------------------------------------------
+size_t AlignBatch::add(const HMMInputSequence& sequence, const HMMInputData& data, uint32_t flags)
+{
+    if (!data.read || !data.pore_model) throw Error(NPH_ERR_INVALID, "HMMInputData without read or pore_model");
+    if (data.read->pore_type != PORETYPE_R9) throw Error(NPH_ERR_UNSUPPORTED, "only R9 reads are supported (load_from_raw always makes R9)");
+    const uint32_t k = data.pore_model->k;
+    if (data.pore_model->states.size() != sequence.get_num_kmer_ranks(k))
+        throw Error(NPH_ERR_INVALID, "sequence alphabet does not match the pore model's state space");
+    if (!((data.rc && data.event_stride == -1) || (!data.rc && data.event_stride == 1)))
+        throw Error(NPH_ERR_INVALID, "rc and event_stride disagree");                                       // ref asserts (profile_hmm_r9.inl:275)
+    if (sequence.length() < k) throw Error(NPH_ERR_INVALID, "sequence shorter than k");
+    ReadKey key{data.read, data.strand};
+    auto it = m_read_index.find(key);
+    uint32_t ridx;
+    if (it == m_read_index.end()) {
+        ridx = (uint32_t)m_reads.size();
+        m_read_index[key] = ridx;
+        m_reads.push_back(key);
+    } else {
+        ridx = it->second;
+    }
+    const uint32_t n_kmers = (uint32_t)(sequence.length() - k + 1);
+    nph_hmm_job j;
+    j.rank_off = m_ranks.size();
+    j.read = ridx;
+    j.model_id = 0;   // resolved against the engine in run()
+    j.event_start = data.event_start_idx;
+    j.event_stop = data.event_stop_idx;
+    j.n_kmers = n_kmers;
+    j.stride = data.event_stride;
+    j.rc = data.rc;
+    j.flags = (uint8_t)flags;
+    j.reserved = 0;
+    for (uint32_t ki = 0; ki < n_kmers; ++ki) m_ranks.push_back(sequence.get_kmer_rank(ki, k, data.rc != 0));
+    m_jobs.push_back(j);
+    m_job_models.push_back(data.pore_model);
+    return m_jobs.size() - 1;
+}
+
+void AlignBatch::clear_jobs()
+{
+    m_job_models.clear(); m_jobs.clear(); m_ranks.clear();
+}
+
+void AlignBatch::clear()
+{
+    clear_jobs();
+    m_read_index.clear(); m_reads.clear(); m_reads_uploaded = 0;
+}
+
+std::vector<std::vector<HMMAlignmentState>> AlignBatch::run(Engine& engine, double indel_bias, bool reads_resident)
+{
+    std::vector<std::vector<HMMAlignmentState>> out(m_jobs.size());
+    if (m_jobs.empty()) return out;
+    for (size_t j = 0; j < m_jobs.size(); ++j) m_jobs[j].model_id = engine.model_id(m_job_models[j]);
+    if (!reads_resident || m_reads_uploaded != m_reads.size()) {
+        std::vector<std::pair<const SquiggleRead*, uint8_t>> rl;
+        for (auto& r : m_reads) rl.push_back({r.read, r.strand});
+        std::vector<nph_read> reads;
+        std::vector<float> mean;
+        std::vector<double> time;
+        detail::flatten_reads(rl, reads, mean, time);
+        engine.check(nph_reads_load(engine.ctx(), reads.data(), reads.size(), mean.data(), time.data(), mean.size()), "nph_reads_load");
+        m_reads_uploaded = m_reads.size();
+    }
+    std::vector<uint64_t> off(m_jobs.size() + 1, 0);
+    for (size_t j = 0; j < m_jobs.size(); ++j) {
+        const nph_hmm_job& jb = m_jobs[j];
+        const uint64_t E = (jb.event_stop > jb.event_start ? jb.event_stop - jb.event_start : jb.event_start - jb.event_stop) + 1;
+        off[j + 1] = off[j] + E + jb.n_kmers + 2;
+    }
+    std::vector<nph_align_state> states(off.back());
+    std::vector<uint32_t> counts(m_jobs.size());
+    engine.check(nph_hmm_align(engine.ctx(), m_ranks.data(), m_ranks.size(), m_jobs.data(), m_jobs.size(), indel_bias,
+                               states.data(), off.data(), counts.data(), nullptr), "nph_hmm_align");
+    for (size_t j = 0; j < m_jobs.size(); ++j) {
+        out[j].resize(counts[j]);
+        for (uint32_t i = 0; i < counts[j]; ++i) {
+            const nph_align_state& s = states[off[j] + i];
+            HMMAlignmentState& as = out[j][i];
+            as.event_idx = s.event_idx;
+            as.kmer_idx = s.kmer_idx;
+            as.l_posterior = -INFINITY;
+            as.l_fm = s.l_fm;
+            as.log_transition_probability = -INFINITY;
+            as.state = s.state;
+        }
+    }
+    return out;
+}
+
+std::vector<HMMAlignmentState> profile_hmm_align(const HMMInputSequence& sequence, const HMMInputData& data, const uint32_t flags)
+{
+    AlignBatch b;
+    b.add(sequence, data, flags);
+    return b.run(Engine::thread_default())[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// aligned pairs from the CIGAR
+// ---------------------------------------------------------------------------------------------
+std::vector<AlignedSegment> get_aligned_segments(int ref_pos, const std::vector<uint32_t>& cigar, int read_stride)
+{
+    std::vector<AlignedSegment> out(1);
+    int read_pos = 0;
+    for (uint32_t c : cigar) {
+        const int len = (int)(c >> 4), op = (int)(c & 0xf);
+        int read_inc = 0, ref_inc = 0;
+        bool is_aligned = false;
+        switch (op) {
+            case NPH_CIGAR_M: case NPH_CIGAR_EQ: case NPH_CIGAR_X: is_aligned = true; read_inc = read_stride; ref_inc = 1; break;
+            case NPH_CIGAR_D: ref_inc = 1; break;
+            case NPH_CIGAR_N: out.push_back(AlignedSegment()); ref_inc = 1; break;     // a reference skip starts a new segment
+            case NPH_CIGAR_I: read_inc = read_stride; break;
+            case NPH_CIGAR_S: read_inc = 1; break;                                     // soft clips ignore read_stride
+            case NPH_CIGAR_H: break;
+            default: throw Error(NPH_ERR_INVALID, "unhandled CIGAR operation");        // the reference asserts
+        }
+        for (int j = 0; j < len; ++j) {
+            if (is_aligned) out.back().push_back({ref_pos, read_pos});
+            read_pos += read_inc;
+            ref_pos += ref_inc;
+        }
+    }
+    return out;
+}
+
+void trim_aligned_pairs_to_kmer(std::vector<AlignedPair>& aligned_pairs, int max_kmer_idx)
+{
+    int idx = (int)aligned_pairs.size() - 1;
+    while (idx >= 0 && aligned_pairs[idx].read_pos > max_kmer_idx) idx -= 1;
+    if (idx < 0) aligned_pairs.clear();
+    else aligned_pairs.resize(idx + 1);
+}
+
+void trim_aligned_pairs_to_ref_region(std::vector<AlignedPair>& aligned_pairs, int ref_start, int ref_end)
+{
+    std::vector<AlignedPair> trimmed;
+    for (const AlignedPair& p : aligned_pairs)
+        if (p.ref_pos >= ref_start && p.ref_pos <= ref_end) trimmed.push_back(p);
+    aligned_pairs.swap(trimmed);
+}
+
+// index of the pair with the highest ref_pos not above ref_pos_max, searching from pair_idx
+int get_end_pair(const std::vector<AlignedPair>& aligned_pairs, int ref_pos_max, int pair_idx)
+{
+    while (pair_idx < (int)aligned_pairs.size()) {
+        if (aligned_pairs[pair_idx].ref_pos > ref_pos_max) return pair_idx - 1;
+        pair_idx += 1;
+    }
+    return (int)aligned_pairs.size() - 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// EventAligner
+// ---------------------------------------------------------------------------------------------
+static const int ALIGN_STRIDE = 100;     // approximately how many reference bases to align to at once (eventalign.cpp:666)
+static const int OUTPUT_STRIDE = 50;     // approximately how many event alignments to output at once (:667)
+
+void EventAligner::clear()
+{
+    m_reads.clear(); m_round.clear(); m_batch.clear();
+}
+
+size_t EventAligner::add_read(const EventAlignmentParameters& params)
+{
+    if (!params.sr) throw Error(NPH_ERR_INVALID, "EventAlignmentParameters without a read");
+    if (params.strand_idx >= 2) throw Error(NPH_ERR_INVALID, "strand_idx out of range");
+    if (!((params.region_start == -1 && params.region_end == -1) || params.region_start <= params.region_end))
+        throw Error(NPH_ERR_INVALID, "region_start > region_end");
+    m_reads.emplace_back();
+    ReadState& rs = m_reads.back();
+    rs.params = params;
+    rs.pore_model = params.get_model();
+    if (!rs.pore_model) throw Error(NPH_ERR_INVALID, "the read has no model for this strand / alphabet");
+    rs.k = rs.pore_model->k;
+    // upper case, ambiguity codes to their lexicographically lowest base (Alphabet::disambiguate upper-cases)
+    rs.ref_seq = rs.pore_model->pmalphabet->disambiguate(params.ref_seq);
+    rs.rc_ref_seq = rs.pore_model->pmalphabet->reverse_complement(rs.ref_seq);
+    if ((params.flag & NPH_BAM_FUNMAP) != 0) { rs.done = true; return m_reads.size() - 1; }
+    rs.segments = get_aligned_segments(params.ref_pos, params.cigar);
+    rs.do_base_rc = (params.flag & NPH_BAM_FREVERSE) != 0;
+    return m_reads.size() - 1;
+}
+
+// Start on segments[segment_idx] (the head of the reference's per-segment loop body, eventalign.cpp:654-689).
+bool EventAligner::enter_segment(ReadState& rs)
+{
+    if (rs.segment_idx >= rs.segments.size()) return false;
+    AlignedSegment& aligned_pairs = rs.segments[rs.segment_idx];
+    const EventAlignmentParameters& p = rs.params;
+    if (p.region_start != -1 && p.region_end != -1) trim_aligned_pairs_to_ref_region(aligned_pairs, p.region_start, p.region_end);
+    const int max_kmer_idx = (int)p.sr->read_sequence.size() - (int)rs.k;
+    trim_aligned_pairs_to_kmer(aligned_pairs, max_kmer_idx);
+    if (aligned_pairs.empty()) return false;                 // the reference returns from the whole function here
+    int read_kidx_start = aligned_pairs.front().read_pos;
+    int read_kidx_end = aligned_pairs.back().read_pos;
+    if (rs.do_base_rc) {
+        read_kidx_start = p.sr->flip_k_strand(read_kidx_start, rs.k);
+        read_kidx_end = p.sr->flip_k_strand(read_kidx_end, rs.k);
+    }
+    const int n_map = (int)p.sr->base_to_event_map.size();
+    if (read_kidx_start < 0 || read_kidx_end < 0 || read_kidx_start >= n_map || read_kidx_end >= n_map)
+        throw Error(NPH_ERR_INVALID, "aligned read position outside the base-to-event map");      // the reference asserts / reads out of bounds
+    const int first_event = p.sr->get_closest_event_to(read_kidx_start, (uint32_t)p.strand_idx);
+    rs.last_event = p.sr->get_closest_event_to(read_kidx_end, (uint32_t)p.strand_idx);
+    rs.forward = first_event < rs.last_event;
+    rs.curr_start_event = first_event;
+    rs.curr_start_ref = aligned_pairs.front().ref_pos;
+    rs.curr_pair_idx = 0;
+    rs.in_segment = true;
+    return true;
+}
+
+// The part of one iteration of the reference's while loop that comes before profile_hmm_align (eventalign.cpp:691-743).
+bool EventAligner::prepare(ReadState& rs, AlignBatch& batch)
+{
+    while (!rs.done) {
+        if (!rs.in_segment) {
+            if (!enter_segment(rs)) { rs.done = true; break; }
+        }
+        const EventAlignmentParameters& p = rs.params;
+        const AlignedSegment& aligned_pairs = rs.segments[rs.segment_idx];
+        bool issued = false;
+        if ((rs.forward && rs.curr_start_event < rs.last_event) || (!rs.forward && rs.curr_start_event > rs.last_event)) {
+            const int end_pair_idx = get_end_pair(aligned_pairs, rs.curr_start_ref + ALIGN_STRIDE, rs.curr_pair_idx);
+            if (end_pair_idx >= 0) {                              // (-1: the reference would index aligned_pairs[-1])
+                const int curr_end_ref = aligned_pairs[end_pair_idx].ref_pos;
+                int curr_end_read = aligned_pairs[end_pair_idx].read_pos;
+                if (rs.do_base_rc) curr_end_read = p.sr->flip_k_strand(curr_end_read, rs.k);
+                const int s = rs.curr_start_ref - p.ref_pos;
+                const int l = curr_end_ref - rs.curr_start_ref + 1;
+                const int n = (int)rs.ref_seq.length();
+                if (curr_end_read >= 0 && s >= 0 && l >= 0 && s + l <= n) {   // (outside: std::string::substr would throw in the reference)
+                    rs.fwd_subseq = rs.ref_seq.substr(s, l);
+                    rs.rc_subseq = rs.rc_ref_seq.substr(n - s - l, l);
+                    // require a minimum amount of sequence to align to
+                    if (rs.fwd_subseq.length() >= 2 * rs.k) {
+                        const int event_stop = p.sr->get_closest_event_to(curr_end_read, (uint32_t)p.strand_idx);
+                        // segments with very few alignable events (large deletions) end the chain
+                        if (event_stop >= 0 && rs.curr_start_event >= 0 && std::abs(rs.curr_start_event - event_stop) >= 2) {
+                            HMMInputData input;
+                            input.read = p.sr;
+                            input.pore_model = rs.pore_model;
+                            input.event_start_idx = (uint32_t)rs.curr_start_event;
+                            input.event_stop_idx = (uint32_t)event_stop;
+                            input.strand = (uint8_t)p.strand_idx;
+                            input.event_stride = input.event_start_idx < input.event_stop_idx ? 1 : -1;
+                            input.rc = p.strand_idx == 0 ? rs.do_base_rc : !rs.do_base_rc;      // rc_flags[strand]
+                            HMMInputSequence hmm_sequence(rs.fwd_subseq, rs.rc_subseq, rs.pore_model->pmalphabet);
+                            batch.add(hmm_sequence, input, 0);
+                            rs.end_pair_idx = end_pair_idx;
+                            rs.job_rc = input.rc;
+                            rs.pending = true;
+                            issued = true;
+                        }
+                    }
+                }
+            }
+        }
+        if (issued) return true;
+        // the while loop of this BAM segment is over (condition false or a break): next segment
+        rs.in_segment = false;
+        rs.segment_idx += 1;
+    }
+    return false;
+}
+
+bool EventAligner::next_round(AlignBatch& batch)
+{
+    batch.clear_jobs();
+    m_round.clear();
+    for (size_t i = 0; i < m_reads.size(); ++i) {
+        if (m_reads[i].done) continue;
+        if (prepare(m_reads[i], batch)) m_round.push_back(i);
+    }
+    return !m_round.empty();
+}
+
+// The part after profile_hmm_align (eventalign.cpp:745-823).
+void EventAligner::consume(const std::vector<std::vector<HMMAlignmentState>>& paths)
+{
+    if (paths.size() != m_round.size()) throw Error(NPH_ERR_STATE, "consume(): one path per job of the round");
+    for (size_t j = 0; j < m_round.size(); ++j) {
+        ReadState& rs = m_reads[m_round[j]];
+        const std::vector<HMMAlignmentState>& event_alignment = paths[j];
+        const AlignedSegment& aligned_pairs = rs.segments[rs.segment_idx];
+        const EventAlignmentParameters& p = rs.params;
+        HMMInputSequence hmm_sequence(rs.fwd_subseq, rs.rc_subseq, rs.pore_model->pmalphabet);
+        rs.pending = false;
+        rs.segments_aligned += 1;
+
+        size_t num_output = 0;
+        // if we aligned to the last pair, output everything and stop
+        const bool last_section = rs.end_pair_idx == (int)aligned_pairs.size() - 1;
+        int last_event_output = 0;
+        int last_ref_kmer_output = 0;
+        for (size_t idx = 0; idx < event_alignment.size() && (num_output < (size_t)OUTPUT_STRIDE || last_section); idx++) {
+            const HMMAlignmentState& as = event_alignment[idx];
+            if (as.state != 'K' && (int)as.event_idx != rs.curr_start_event) {
+                EventAlignment ea;
+                ea.ref_name = p.ref_name;
+                ea.ref_position = rs.curr_start_ref + (int)as.kmer_idx;
+                const size_t rp = (size_t)(ea.ref_position - p.ref_pos);
+                ea.ref_kmer = rp <= rs.ref_seq.size() ? rs.ref_seq.substr(rp, rs.k) : std::string();
+                ea.read_idx = (size_t)p.read_idx;
+                ea.strand_idx = (int)p.strand_idx;
+                ea.event_idx = (int)as.event_idx;
+                ea.rc = rs.job_rc != 0;
+                ea.hmm_state = as.state;
+                ea.model_kmer = ea.hmm_state != 'B' ? hmm_sequence.get_kmer(as.kmer_idx, rs.k, ea.rc) : std::string(rs.k, 'N');
+                rs.output.push_back(ea);
+                last_event_output = (int)as.event_idx;
+                last_ref_kmer_output = rs.curr_start_ref + (int)as.kmer_idx;
+                num_output += 1;
+            }
+        }
+        // advance the cursor to where the output stopped
+        rs.curr_start_event = last_event_output;
+        rs.curr_start_ref = last_ref_kmer_output;
+        rs.curr_pair_idx = get_end_pair(aligned_pairs, rs.curr_start_ref, rs.curr_pair_idx);
+        if (num_output == 0) {        // break: on to the next BAM segment
+            rs.in_segment = false;
+            rs.segment_idx += 1;
+        }
+    }
+    m_round.clear();
+}
+
+size_t EventAligner::run(Engine& engine, double indel_bias)
+{
+    size_t rounds = 0;
+    m_batch.clear();
+    while (next_round(m_batch)) {
+        // the read table is complete after the first round only if every read issued a job in it; AlignBatch uploads
+        // again whenever a read shows up that was not resident
+        consume(m_batch.run(engine, indel_bias, rounds > 0));
+        rounds += 1;
+    }
+    m_batch.clear();
+    return rounds;
+}
+
+// ---------------------------------------------------------------------------------------------
+// writers
+// ---------------------------------------------------------------------------------------------
+std::string EventAligner::tsv_header(const EventalignOptions& opt)
+{
+    std::string h = "contig\tposition\treference_kmer\t";
+    h += opt.print_read_names ? "read_name" : "read_index";
+    h += "\tstrand\tevent_index\tevent_level_mean\tevent_stdv\tevent_length\tmodel_kmer\tmodel_mean\tmodel_stdv\tstandardized_level\n";
+    return h;
+}
+
+std::string EventAligner::tsv(size_t read_idx, const EventalignOptions& opt) const
+{
+    const ReadState& rs = m_reads[read_idx];
+    const SquiggleRead& sr = *rs.params.sr;
+    const PoreModel* pore_model = rs.pore_model;
+    const uint32_t k = pore_model->k;
+    std::string out;
+    char buf[1024];
+    for (const EventAlignment& ea : rs.output) {
+        if (!opt.print_read_names)
+            snprintf(buf, sizeof(buf), "%s\t%d\t%s\t%zu\t%c\t", ea.ref_name.c_str(), ea.ref_position, ea.ref_kmer.c_str(), ea.read_idx, "tc"[ea.strand_idx]);
+        else
+            snprintf(buf, sizeof(buf), "%s\t%d\t%s\t%s\t%c\t", ea.ref_name.c_str(), ea.ref_position, ea.ref_kmer.c_str(), sr.read_name.c_str(), "tc"[ea.strand_idx]);
+        out += buf;
+
+        float event_mean = sr.get_unscaled_level(ea.event_idx, ea.strand_idx);
+        const float event_stdv = sr.get_stdv(ea.event_idx, ea.strand_idx);
+        const float event_duration = sr.get_duration(ea.event_idx, ea.strand_idx);
+        const uint32_t rank = pore_model->pmalphabet->kmer_rank(ea.model_kmer.c_str(), k);
+        float model_mean = 0.0, model_stdv = 0.0;
+        if (opt.scale_events) {
+            // scale reads to the model; unscaled model parameters
+            event_mean = sr.get_fully_scaled_level(ea.event_idx, ea.strand_idx);
+            if (ea.hmm_state != 'B') {
+                const PoreModelStateParams model = pore_model->get_parameters(rank);
+                model_mean = (float)model.level_mean;
+                model_stdv = (float)model.level_stdv;
+            }
+        } else if (ea.hmm_state != 'B') {
+            // scale model to the reads
+            const GaussianParameters model = sr.get_scaled_gaussian_from_pore_model_state(*pore_model, ea.strand_idx, rank);
+            model_mean = model.mean;
+            model_stdv = model.stdv;
+        }
+        // float difference over a double product, narrowed to float (a 'B' state divides by zero: inf, like the reference)
+        const float standard_level = (float)((event_mean - model_mean) / (std::sqrt(sr.scalings[ea.strand_idx].var) * model_stdv));
+        snprintf(buf, sizeof(buf), "%d\t%.2lf\t%.3lf\t%.5lf\t", ea.event_idx, event_mean, event_stdv, event_duration);
+        out += buf;
+        snprintf(buf, sizeof(buf), "%s\t%.2lf\t%.2lf\t%.2lf", ea.model_kmer.c_str(), model_mean, model_stdv, standard_level);
+        out += buf;
+        out += "\n";
+    }
+    return out;
+}
+
+std::vector<uint32_t> event_alignment_to_cigar(const std::vector<EventAlignment>& alignments)
+{
+    std::vector<uint32_t> out;
+    if (alignments.empty()) return out;
+    // a soft clip accounts for unaligned events at the beginning of the read
+    if (alignments[0].event_idx > 0) out.push_back((uint32_t)alignments[0].event_idx << 4 | NPH_CIGAR_S);
+    out.push_back(1u << 4 | NPH_CIGAR_M);       // always starts with a match
+    int prev_r_idx = alignments[0].ref_position;
+    int prev_e_idx = alignments[0].event_idx;
+    for (size_t ai = 1; ai < alignments.size(); ++ai) {
+        const int r_idx = alignments[ai].ref_position, e_idx = alignments[ai].event_idx;
+        const int r_step = std::abs(r_idx - prev_r_idx), e_step = std::abs(e_idx - prev_e_idx);
+        uint32_t incoming;
+        if (r_step == 1 && e_step == 1) {
+            incoming = 1u << 4 | NPH_CIGAR_M;
+        } else if (r_step > 1) {
+            // a reference jump of more than one is a deletion followed by a new match (the reference asserts e_step == 1)
+            out.push_back((uint32_t)(r_step - 1) << 4 | NPH_CIGAR_D);
+            incoming = 1u << 4 | NPH_CIGAR_M;
+        } else {
+            incoming = 1u << 4 | NPH_CIGAR_I;   // (the reference asserts e_step == 1 && r_step == 0)
+        }
+        if ((out.back() & 0xf) == (incoming & 0xf)) out.back() = ((out.back() >> 4) + (incoming >> 4)) << 4 | (incoming & 0xf);
+        else out.push_back(incoming);
+        prev_r_idx = r_idx;
+        prev_e_idx = e_idx;
+    }
+    return out;
+}
+
+std::string cigar_ops_to_string(const std::vector<uint32_t>& ops)
+{
+    std::string s;
+    for (uint32_t c : ops) { s += std::to_string(c >> 4); s += "MIDNSHP=XB"[c & 0xf]; }
+    return s;
+}
+
+std::string EventAligner::event_cigar(size_t read_idx) const
+{
+    return cigar_ops_to_string(event_alignment_to_cigar(m_reads[read_idx].output));
+}
+
+std::string EventAligner::sam(size_t read_idx) const
+{
+    const ReadState& rs = m_reads[read_idx];
+    const std::vector<EventAlignment>& al = rs.output;
+    if (al.empty()) return std::string();
+    const std::string qname = rs.params.sr->read_name + (al.front().strand_idx == 0 ? ".template" : ".complement");
+    const int stride = al.front().event_idx < al.back().event_idx ? 1 : -1;
+    // QNAME FLAG RNAME POS MAPQ CIGAR RNEXT PNEXT TLEN SEQ QUAL + the event-stride tag
+    return qname + "\t" + std::to_string(al.front().rc ? 16 : 0) + "\t" + rs.params.ref_name + "\t" + std::to_string(al.front().ref_position + 1) + "\t" +
+           std::to_string((int)rs.params.mapq) + "\t" + event_cigar(read_idx) + "\t*\t0\t0\t*\t*\tES:i:" + std::to_string(stride) + "\n";
+}
+
+EventalignSummary EventAligner::summarize(size_t read_idx) const
+{
+    const ReadState& rs = m_reads[read_idx];
+    const SquiggleRead& sr = *rs.params.sr;
+    EventalignSummary summary;
+    uint64_t prev_ref_pos = ~(uint64_t)0;                  // std::string::npos
+    for (size_t i = 0; i < rs.output.size(); ++i) {
+        const EventAlignment& ea = rs.output[i];
+        summary.num_events += 1;
+        const uint64_t ref_move = (uint64_t)(int64_t)ea.ref_position - prev_ref_pos;    // size_t arithmetic, as the reference
+        if (ref_move == 0) summary.num_stays += 1;
+        else if (i != 0 && ref_move > 1) summary.num_skips += 1;
+        else if (i != 0 && ref_move == 1) summary.num_steps += 1;
+        summary.sum_duration += sr.get_duration(ea.event_idx, ea.strand_idx);
+        if (ea.hmm_state == 'M') {
+            const uint32_t rank = rs.pore_model->pmalphabet->kmer_rank(ea.model_kmer.c_str(), rs.k);
+            // z_score (src/hmm/nanopolish_emissions.h:32-41): float arithmetic
+            const float level = sr.get_drift_scaled_level(ea.event_idx, ea.strand_idx);
+            const GaussianParameters gp = sr.get_scaled_gaussian_from_pore_model_state(*rs.pore_model, ea.strand_idx, rank);
+            const float z = (level - gp.mean) / gp.stdv;
+            summary.sum_z_score += z;
+        }
+        prev_ref_pos = (uint64_t)(int64_t)ea.ref_position;
+    }
+    summary.alignment_edit_distance = rs.params.edit_distance;
+    if (!rs.output.empty()) summary.reference_span = rs.output.back().ref_position - rs.output.front().ref_position + 1;
+    return summary;
+}
+
+std::string EventAligner::summary_row(size_t read_idx, const std::string& fast5_path) const
+{
+    const ReadState& rs = m_reads[read_idx];
+    const EventalignSummary summary = summarize(read_idx);
+    if (summary.num_events <= 0) return std::string();
+    const SquiggleScalings& scalings = rs.params.sr->scalings[rs.params.strand_idx];
+    char buf[2048];
+    std::string out;
+    snprintf(buf, sizeof(buf), "%zu\t%s\t%s\t", (size_t)rs.params.read_idx, rs.params.sr->read_name.c_str(), fast5_path.c_str());
+    out += buf;
+    snprintf(buf, sizeof(buf), "%s\t%s\t", rs.pore_model->name.c_str(), rs.params.strand_idx == 0 ? "template" : "complement");
+    out += buf;
+    snprintf(buf, sizeof(buf), "%d\t%d\t%d\t%d\t", summary.num_events, summary.num_steps, summary.num_skips, summary.num_stays);
+    out += buf;
+    snprintf(buf, sizeof(buf), "%.2lf\t%.3lf\t%.3lf\t%.3lf\t%.3lf\n", summary.sum_duration, scalings.shift, scalings.scale, scalings.drift, scalings.var);
+    out += buf;
+    return out;
+}
+
+} // namespace nph

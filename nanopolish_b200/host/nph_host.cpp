@@ -240,8 +240,9 @@ uint32_t Engine::model_id(const PoreModel* model)
 // ---------------------------------------------------------------------------------------------
 // Batches
 // ---------------------------------------------------------------------------------------------
-static void flatten_reads(const std::vector<std::pair<const SquiggleRead*, uint8_t>>& reads, std::vector<nph_read>& out,
-                          std::vector<float>& mean, std::vector<double>& time)
+namespace detail {
+void flatten_reads(const std::vector<std::pair<const SquiggleRead*, uint8_t>>& reads, std::vector<nph_read>& out,
+                   std::vector<float>& mean, std::vector<double>& time)
 {
     out.resize(reads.size());
     size_t total = 0;
@@ -264,6 +265,8 @@ static void flatten_reads(const std::vector<std::pair<const SquiggleRead*, uint8
         off += ev.size();
     }
 }
+} // namespace detail
+using detail::flatten_reads;
 
 size_t HmmBatch::add(const HMMInputSequence& sequence, const HMMInputData& data, uint32_t flags)
 {

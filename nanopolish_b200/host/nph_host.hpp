@@ -181,6 +181,34 @@ public:
         gp.log_stdv = (float)(p.level_log_stdv + s.log_var);
         return gp;
     }
+    float get_fully_scaled_level(uint32_t event_idx, uint32_t strand) const
+    {
+        return (float)((get_drift_scaled_level(event_idx, strand) - scalings[strand].shift) / scalings[strand].scale);
+    }
+    float get_stdv(uint32_t event_idx, uint32_t strand) const { return events[strand][event_idx].stdv; }
+    float get_duration(uint32_t event_idx, uint32_t strand) const { return events[strand][event_idx].duration; }
+    // ref: src/nanopolish_squiggle_read.h:229-233
+    int32_t flip_k_strand(int32_t k_idx, uint32_t k) const { return (int32_t)read_sequence.size() - k_idx - (int32_t)k; }
+    // index of the event nearest to a k-mer of the basecalled sequence: the first event of the closest k-mer that has
+    // one, looking backwards first, at most 1000 k-mers either way (-1 if none).
+    // ref: src/nanopolish_squiggle_read.cpp:160-186
+    int get_next_event(int start, int stop, int stride, uint32_t strand) const
+    {
+        for (; start != stop; start += stride) {
+            const int ei = base_to_event_map[start].indices[strand].start;
+            if (ei != -1) return ei;
+        }
+        return -1;
+    }
+    int get_closest_event_to(int k_idx, uint32_t strand) const
+    {
+        const int stop_before = k_idx - 1000 > 0 ? k_idx - 1000 : 0;
+        const int last = (int)base_to_event_map.size() - 1;
+        const int stop_after = k_idx + 1000 < last ? k_idx + 1000 : last;
+        const int event_before = get_next_event(k_idx, stop_before, -1, strand);
+        const int event_after = get_next_event(k_idx, stop_after, 1, strand);
+        return event_before == -1 ? event_after : event_before;
+    }
     bool has_events_for_strand(size_t strand_idx) const { return !events[strand_idx].empty(); }
     size_t get_model_k(uint32_t strand) const { return base_model[strand]->k; }
     const PoreModel* get_base_model(uint32_t strand) const { return base_model[strand]; }
@@ -271,6 +299,12 @@ private:
     nph_ctx* m_ctx = nullptr;
     std::unordered_map<const PoreModel*, uint32_t> m_models;
 };
+
+namespace detail {
+// (read, strand) list -> the flat nph_read records + event arrays the C ABI takes
+void flatten_reads(const std::vector<std::pair<const SquiggleRead*, uint8_t>>& reads, std::vector<nph_read>& out,
+                   std::vector<float>& mean, std::vector<double>& time);
+}
 
 // A batch of profile_hmm_score calls.  add() returns the index of the job's score in run()'s result.
 class HmmBatch {

@@ -4,6 +4,7 @@
 #include "nph_variants.hpp"
 #include "nph_methylation.hpp"
 #include "nph_raw.hpp"
+#include "nph_eventalign.hpp"
 #include <cstring>
 #include <memory>
 
@@ -12,6 +13,8 @@ using namespace nph;
 namespace {
 std::vector<std::unique_ptr<PoreModel>> g_models;
 std::vector<std::unique_ptr<SquiggleRead>> g_reads;
+EventAligner g_aligner;
+AlignBatch g_round_batch;
 thread_local std::string g_err;
 template <typename F> int guard(F f) { try { f(); return 0; } catch (const Error& e) { g_err = e.what(); return e.status; } catch (const std::exception& e) { g_err = e.what(); return NPH_ERR_INVALID; } }
 }
@@ -298,6 +301,124 @@ int nphh_load_from_raw(int model, int n, const float* samples, const uint64_t* s
         }
     });
     return rc ? rc : first;
+}
+
+// ---- N1: eventalign (segment chaining around the Viterbi kernel) -------------------------------------------
+// what load_from_raw leaves on a SquiggleRead beyond events and scalings
+int nphh_read_set_eventalign(int read, const char* read_name, const char* read_sequence, const int32_t* map_start, const int32_t* map_stop,
+                             size_t n_map, const float* stdv, const float* duration)
+{
+    return guard([&] {
+        SquiggleRead& sr = *g_reads[read];
+        sr.read_name = read_name;
+        sr.read_sequence = read_sequence;
+        sr.base_to_event_map.resize(n_map);
+        for (size_t i = 0; i < n_map; ++i) sr.base_to_event_map[i].indices[0] = IndexPair(map_start[i], map_stop[i]);
+        for (size_t i = 0; i < sr.events[0].size(); ++i) { sr.events[0][i].stdv = stdv[i]; sr.events[0][i].duration = duration[i]; }
+    });
+}
+
+void nphh_ea_begin() { g_aligner.clear(); g_round_batch.clear(); }
+
+int nphh_ea_add_read(int read, const char* ref_name, int ref_pos, int flag, int mapq, const uint32_t* cigar, int n_cigar, const char* ref_seq,
+                     int read_idx, int region_start, int region_end)
+{
+    int idx = -1;
+    int rc = guard([&] {
+        EventAlignmentParameters p;
+        p.sr = g_reads[read].get();
+        p.strand_idx = 0;
+        p.ref_name = ref_name; p.ref_pos = ref_pos; p.flag = (uint16_t)flag; p.mapq = (uint8_t)mapq;
+        p.cigar.assign(cigar, cigar + n_cigar);
+        p.ref_seq = ref_seq;
+        p.read_idx = read_idx; p.region_start = region_start; p.region_end = region_end;
+        idx = (int)g_aligner.add_read(p);
+    });
+    return rc ? rc : idx;
+}
+
+// everything on the GPU: returns the number of rounds (Viterbi launches)
+long long nphh_ea_run(double indel_bias)
+{
+    long long rounds = -1;
+    int rc = guard([&] { rounds = (long long)g_aligner.run(Engine::thread_default(), indel_bias); });
+    return rc ? rc : rounds;
+}
+
+// One round's job list without running it (host-logic tests feed the paths back through nphh_ea_consume):
+// jobs_out = nph_hmm_job[cap_jobs] (job.read = index of the read in the aligner), ranks_out = uint32[cap_ranks].
+// Returns the number of jobs (0 = all reads finished) or a negative status.
+long long nphh_ea_next_round(void* jobs_out, size_t cap_jobs, uint32_t* ranks_out, size_t cap_ranks, uint64_t* n_ranks_out)
+{
+    long long n = 0;
+    int rc = guard([&] {
+        if (!g_aligner.next_round(g_round_batch)) { n = 0; return; }
+        const std::vector<nph_hmm_job>& jobs = g_round_batch.jobs();
+        if (jobs.size() > cap_jobs || g_round_batch.ranks().size() > cap_ranks) throw Error(NPH_ERR_INVALID, "round buffers too small");
+        nph_hmm_job* out = static_cast<nph_hmm_job*>(jobs_out);
+        for (size_t j = 0; j < jobs.size(); ++j) { out[j] = jobs[j]; out[j].read = (uint32_t)g_aligner.round_reads()[j]; }
+        std::memcpy(ranks_out, g_round_batch.ranks().data(), sizeof(uint32_t) * g_round_batch.ranks().size());
+        *n_ranks_out = g_round_batch.ranks().size();
+        n = (long long)jobs.size();
+    });
+    return rc ? rc : n;
+}
+
+int nphh_ea_consume(size_t n_jobs, const uint64_t* state_off, const nph_align_state* states)
+{
+    return guard([&] {
+        std::vector<std::vector<HMMAlignmentState>> paths(n_jobs);
+        for (size_t j = 0; j < n_jobs; ++j)
+            for (uint64_t i = state_off[j]; i < state_off[j + 1]; ++i)
+                paths[j].push_back(HMMAlignmentState{states[i].event_idx, states[i].kmer_idx, -INFINITY, states[i].l_fm, -INFINITY, states[i].state});
+        g_aligner.consume(paths);
+    });
+}
+
+// what: 0 = TSV rows, 1 = TSV rows with read names, 2 = TSV rows with --scale-events, 3 = SAM line, 4 = event CIGAR, 5 = summary row,
+// 6 = TSV header
+long long nphh_ea_text(int idx, int what, char* out, size_t cap)
+{
+    long long n = -1;
+    int rc = guard([&] {
+        EventalignOptions opt;
+        std::string s;
+        switch (what) {
+            case 0: s = g_aligner.tsv(idx, opt); break;
+            case 1: opt.print_read_names = true; s = g_aligner.tsv(idx, opt); break;
+            case 2: opt.scale_events = true; s = g_aligner.tsv(idx, opt); break;
+            case 3: s = g_aligner.sam(idx); break;
+            case 4: s = g_aligner.event_cigar(idx); break;
+            case 5: s = g_aligner.summary_row(idx, "read.fast5"); break;
+            case 6: s = EventAligner::tsv_header(opt); break;
+            default: throw Error(NPH_ERR_INVALID, "unknown text kind");
+        }
+        if (s.size() + 1 > cap) throw Error(NPH_ERR_INVALID, "text buffer too small");
+        std::memcpy(out, s.c_str(), s.size() + 1);
+        n = (long long)s.size();
+    });
+    return rc ? rc : n;
+}
+
+long long nphh_ea_num_segments(int idx) { return (long long)g_aligner.num_segments(idx); }
+
+// get_aligned_segments on a packed CIGAR: pairs_out = (ref_pos, read_pos) interleaved, seg_off[n_segments + 1]
+long long nphh_aligned_segments(int ref_pos, const uint32_t* cigar, int n_cigar, int32_t* pairs_out, size_t cap_pairs, uint64_t* seg_off, size_t cap_segs)
+{
+    long long n = -1;
+    int rc = guard([&] {
+        std::vector<AlignedSegment> segs = get_aligned_segments(ref_pos, std::vector<uint32_t>(cigar, cigar + n_cigar));
+        if (segs.size() + 1 > cap_segs) throw Error(NPH_ERR_INVALID, "segment buffer too small");
+        size_t o = 0;
+        seg_off[0] = 0;
+        for (size_t i = 0; i < segs.size(); ++i) {
+            if (o + segs[i].size() > cap_pairs) throw Error(NPH_ERR_INVALID, "pair buffer too small");
+            for (const AlignedPair& p : segs[i]) { pairs_out[2 * o] = p.ref_pos; pairs_out[2 * o + 1] = p.read_pos; ++o; }
+            seg_off[i + 1] = o;
+        }
+        n = (long long)segs.size();
+    });
+    return rc ? rc : n;
 }
 
 } // extern "C"

@@ -234,6 +234,26 @@ class RefOracle:
                                  C.c_uint32(int(flags)), C.c_double(indel_bias), _p(ek), _p(lfm), st, C.c_uint32(cap))
         return ek[:n].copy(), lfm[:n].copy(), st.raw[:n]
 
+    def read_set_eventalign(self, read_h, name: str, read_sequence: str, b2e_start, b2e_stop, stdv, duration):
+        a, b = np.ascontiguousarray(b2e_start, np.int32), np.ascontiguousarray(b2e_stop, np.int32)
+        sd, du = np.ascontiguousarray(stdv, np.float32), np.ascontiguousarray(duration, np.float32)
+        self.lib.npref_read_set_eventalign(int(read_h), name.encode(), read_sequence.encode(), _p(a), _p(b), C.c_size_t(a.shape[0]), _p(sd), _p(du))
+
+    def eventalign(self, read_h, contig_name: str, contig: str, ref_pos, flag, cigar, read_idx, region=(-1, -1), want_cigar=True):
+        """align_read_to_ref + emit_event_alignment_tsv (default options) + the SAM writer's event CIGAR.
+        Returns (tsv text, cigar string, int32[n, 3] of (ref_position, event_idx, ord(state)))."""
+        cg = np.ascontiguousarray(cigar, np.uint32)
+        cap = 1 << 22
+        tsv = C.create_string_buffer(cap); cs = C.create_string_buffer(1 << 16)
+        ea = np.zeros((1 << 16, 3), np.int32)
+        self.lib.npref_eventalign.restype = C.c_longlong
+        n = self.lib.npref_eventalign(int(read_h), contig_name.encode(), contig.encode(), int(ref_pos), int(flag), _p(cg), int(cg.shape[0]),
+                                      int(read_idx), int(region[0]), int(region[1]), tsv, C.c_size_t(cap), cs, C.c_size_t((1 << 16) if want_cigar else 0),
+                                      _p(ea), C.c_size_t(ea.size))
+        if n < 0:
+            raise RuntimeError("npref_eventalign: output buffer too small")
+        return tsv.value.decode(), cs.value.decode(), ea[:n].copy()
+
     def kmer_ranks(self, model_h, seq: bytes, rc: bool):
         out = np.zeros(max(len(seq), 1), np.uint32)
         n = self.lib.npref_kmer_ranks(model_h, C.c_char_p(seq), int(rc), _p(out))

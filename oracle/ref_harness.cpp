@@ -30,6 +30,8 @@
 #include "nanopolish_alphabet.h"
 #include "nanopolish_emissions.h"
 #include "logsum.h"
+#include "nanopolish_eventalign.h"   // align_read_to_ref / emit_event_alignment_tsv (8f N1: segment chaining)
+#include "nanopolish_anchor.h"
 extern "C" {
 #include "event_detection.h"   // src/thirdparty/scrappie (C99)
 }
@@ -52,6 +54,54 @@ void SquiggleScalings::set4(double _shift, double _scale, double _drift, double 
     set6(_shift, _scale, _drift, _var, 1.0, 1.0);
 }
 SquiggleRead::~SquiggleRead() {}
+// Two more members of nanopolish_squiggle_read.cpp that eventalign's segment chaining calls; semantics follow
+// src/nanopolish_squiggle_read.cpp:160-186 (nearest k-mer with an event, looking backwards first, 1000 k-mers
+// either way).  The two sample accessors are only reached with --signal-index / --samples, which stay off here.
+int SquiggleRead::get_next_event(int start, int stop, int stride, uint32_t strand) const
+{
+    for(; start != stop; start += stride) {
+        int ei = base_to_event_map[start].indices[strand].start;
+        if(ei != -1) return ei;
+    }
+    return -1;
+}
+int SquiggleRead::get_closest_event_to(int k_idx, uint32_t strand) const
+{
+    int stop_before = std::max(0, k_idx - 1000);
+    int stop_after = std::min(k_idx + 1000, (int)base_to_event_map.size() - 1);
+    int event_before = get_next_event(k_idx, stop_before, -1, strand);
+    int event_after = get_next_event(k_idx, stop_after, 1, strand);
+    return event_before == -1 ? event_after : event_before;
+}
+std::pair<size_t, size_t> SquiggleRead::get_event_sample_idx(size_t, size_t) const { abort(); }
+std::vector<float> SquiggleRead::get_scaled_samples_for_event(size_t, size_t) const { abort(); }
+
+// htslib is not built here; eventalign needs two of its calls.  Test doubles: the "FASTA index" is a contig held
+// in memory, bam_endpos is pos + reference length of the CIGAR (what htslib computes for a mapped record).
+struct NprefContig { std::string name, seq; };
+extern "C" char* faidx_fetch_seq(const faidx_t* fai, const char* c_name, int p_beg_i, int p_end_i, int* len)
+{
+    const NprefContig* c = reinterpret_cast<const NprefContig*>(fai);
+    if(c->name != c_name) { *len = -2; return NULL; }
+    if(p_beg_i < 0) p_beg_i = 0;
+    if(p_end_i >= (int)c->seq.size()) p_end_i = (int)c->seq.size() - 1;     // faidx clips to the contig, end inclusive
+    int l = p_end_i >= p_beg_i ? p_end_i - p_beg_i + 1 : 0;
+    char* out = (char*)malloc(l + 1);
+    memcpy(out, c->seq.data() + p_beg_i, l);
+    out[l] = 0;
+    *len = l;
+    return out;
+}
+extern "C" hts_pos_t bam_endpos(const bam1_t* b)
+{
+    hts_pos_t rlen = 0;
+    const uint32_t* cigar = bam_get_cigar(b);
+    for(uint32_t i = 0; i < b->core.n_cigar; ++i)
+        if(bam_cigar_type(bam_cigar_op(cigar[i])) & 2) rlen += bam_cigar_oplen(cigar[i]);
+    return b->core.pos + (rlen ? rlen : 1);
+}
+std::vector<uint32_t> event_alignment_to_cigar(const std::vector<EventAlignment>& alignments);   // nanopolish_eventalign.cpp:256
+std::string cigar_ops_to_string(const std::vector<uint32_t>& ops);                                 // :246
 
 namespace {
 std::vector<const PoreModel*> g_models;
@@ -313,5 +363,75 @@ int npref_trim_raw(const float* raw, size_t n, int trim_start, int trim_end, int
 }
 
 int npref_max_threads(void) { return omp_get_max_threads(); }
+
+// ---- eventalign: segment chaining + TSV (src/alignment/nanopolish_eventalign.cpp:612-827, :398-484, :256-325) ----
+// What SquiggleRead carries beyond the events once load_from_raw has run: the basecalled sequence, the
+// base-to-event map (one [start, stop] per k-mer, -1 where none), event stdv / duration, the read name.
+void npref_read_set_eventalign(int h, const char* read_name, const char* read_sequence, const int32_t* map_start,
+                               const int32_t* map_stop, size_t n_map, const float* stdv, const float* duration)
+{
+    SquiggleRead& sr = *g_reads[h];
+    sr.read_name = read_name;
+    sr.read_sequence = read_sequence;
+    sr.base_to_event_map.resize(n_map);
+    for(size_t i = 0; i < n_map; ++i) {
+        sr.base_to_event_map[i].indices[0].start = map_start[i];
+        sr.base_to_event_map[i].indices[0].stop = map_stop[i];
+    }
+    for(size_t i = 0; i < sr.events[0].size(); ++i) {
+        sr.events[0][i].stdv = stdv[i];
+        sr.events[0][i].duration = duration[i];
+    }
+}
+
+// align_read_to_ref on a hand-built BAM record (pos, flag, CIGAR), then emit_event_alignment_tsv (default options)
+// into tsv_out and the event CIGAR of the SAM output into cigar_out.  Returns the number of EventAlignments, or -1
+// when tsv_cap is too small.  ea_out (optional) gets (ref_position, event_idx, hmm_state) triples.
+long long npref_eventalign(int read_h, const char* contig_name, const char* contig_seq, int ref_pos, int flag,
+                           const uint32_t* cigar, int n_cigar, int read_idx, int region_start, int region_end,
+                           char* tsv_out, size_t tsv_cap, char* cigar_out, size_t cigar_cap, int32_t* ea_out, size_t ea_cap)
+{
+    NprefContig contig{contig_name, contig_seq};
+    bam_hdr_t hdr;
+    memset(&hdr, 0, sizeof(hdr));
+    char* names[1] = { const_cast<char*>(contig.name.c_str()) };
+    uint32_t lens[1] = { (uint32_t)contig.seq.size() };
+    hdr.n_targets = 1; hdr.target_name = names; hdr.target_len = lens;
+    bam1_t rec;
+    memset(&rec, 0, sizeof(rec));
+    std::vector<uint8_t> data(4 + 4 * (size_t)n_cigar);
+    memcpy(data.data(), "r\0\0\0", 4);
+    memcpy(data.data() + 4, cigar, 4 * (size_t)n_cigar);
+    rec.core.pos = ref_pos; rec.core.tid = 0; rec.core.flag = (uint16_t)flag; rec.core.l_qname = 4; rec.core.l_extranul = 2;
+    rec.core.n_cigar = n_cigar; rec.core.mtid = -1; rec.core.mpos = -1;
+    rec.data = data.data(); rec.l_data = (int)data.size(); rec.m_data = (uint32_t)data.size();
+
+    EventAlignmentParameters params;
+    params.sr = g_reads[read_h].get();
+    params.fai = reinterpret_cast<const faidx_t*>(&contig);
+    params.hdr = &hdr;
+    params.record = &rec;
+    params.strand_idx = 0;
+    params.read_idx = read_idx;
+    params.region_start = region_start;
+    params.region_end = region_end;
+    std::vector<EventAlignment> alignment = align_read_to_ref(params);
+
+    char* buf = NULL; size_t len = 0;
+    FILE* fp = open_memstream(&buf, &len);
+    emit_event_alignment_tsv(fp, *params.sr, 0, params, alignment);
+    fclose(fp);
+    bool ok = len < tsv_cap;
+    if(ok) { memcpy(tsv_out, buf, len); tsv_out[len] = 0; }
+    free(buf);
+    if(!ok) return -1;
+    // (event_alignment_to_cigar asserts on the event jump between two BAM segments: callers skip it for records with an N)
+    std::string cs = (alignment.empty() || cigar_cap == 0) ? std::string() : cigar_ops_to_string(event_alignment_to_cigar(alignment));
+    if(cigar_cap == 0) {} else if(cs.size() < cigar_cap) strcpy(cigar_out, cs.c_str()); else cigar_out[0] = 0;
+    for(size_t i = 0; i < alignment.size() && 3 * i + 2 < ea_cap; ++i) {
+        ea_out[3 * i] = alignment[i].ref_position; ea_out[3 * i + 1] = alignment[i].event_idx; ea_out[3 * i + 2] = alignment[i].hmm_state;
+    }
+    return (long long)alignment.size();
+}
 
 } // extern "C"

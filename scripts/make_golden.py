@@ -7,6 +7,8 @@ Outputs (small, committed):
       reference's PoreModelSet (k, level_mean, level_stdv, level_log_stdv as float64)
   tests/golden/hmm_golden.npz   inputs (seeds + job lists) and the reference's profile_hmm_score floats
   tests/golden/abea_golden.npz  inputs (seeds) and the reference's AlignedPair lists / verdicts
+  tests/golden/eventalign_golden.npz  the reference's align_read_to_ref + emit_event_alignment_tsv output (TSV bytes,
+      event CIGAR) for the seeded cases of tests/eventalign_cases.py        [python scripts/make_golden.py eventalign]
 The GPU box has no /root/reference, so the -m gpu tests compare against these files and against the
 plain-C oracle (which tests/test_oracle_vs_ref.py pins to the compiled reference bit-for-bit here).
 """
@@ -33,10 +35,32 @@ def dump_models(ref):
         print("model", alphabet, k, a, mean.shape)
 
 
+def eventalign_golden(ref):
+    from tests import eventalign_cases as EC
+    model, rs, cases = EC.build_cases()
+    ref.clear_reads()
+    mh = ref.builtin_model("nucleotide")
+    rh = ref.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, mh)
+    out = {}
+    for c in cases:
+        slot, r = EC.read_slot(c, rs.n_reads), c["read"]
+        ref.read_set_eventalign(rh[slot], r.name, r.read_sequence, r.b2e_start, c["b2e_stop"], r.stdv, r.duration)
+        single_segment = not any((int(x) & 15) == 3 for x in c["cigar"])
+        tsv, cigar, ea = ref.eventalign(rh[slot], c["contig_name"], c["contig"], c["ref_pos"], c["flag"], c["cigar"], c["read_idx"],
+                                        c["region"], want_cigar=single_segment)
+        out[f"tsv_{c['read_idx']}"] = np.frombuffer(tsv.encode(), np.uint8)
+        out[f"cigar_{c['read_idx']}"] = np.frombuffer(cigar.encode(), np.uint8)
+        print("eventalign", c["read_idx"], "flag", c["flag"], tsv.count("\n"), "rows", cigar[:40])
+    np.savez_compressed(os.path.join(GOLD, "eventalign_golden.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     build(ref=True)
     ref = RefOracle()
+    if sys.argv[1:] == ["eventalign"]:
+        eventalign_golden(ref)
+        return
     dump_models(ref)
     from tests.golden_cases import make_hmm_cases, make_abea_cases   # shared with the tests
     # ---- HMM golden vectors
@@ -65,6 +89,7 @@ def main():
         out[name + "_npairs"] = npairs
         print("abea", name, npairs)
     np.savez_compressed(os.path.join(GOLD, "abea_golden.npz"), **out)
+    eventalign_golden(ref)
 
 
 if __name__ == "__main__":

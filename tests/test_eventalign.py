@@ -1,0 +1,186 @@
+"""SURVEY.md 8(f) row N1, host half — eventalign's segment chaining around the Viterbi kernel
+(nanopolish_b200/host/nph_eventalign.*: align_read_to_ref, src/alignment/nanopolish_eventalign.cpp:612-827, and its
+TSV / SAM / summary writers).
+
+  * the Python restatement (oracle/eventalign_py.py) against the COMPILED reference's align_read_to_ref +
+    emit_event_alignment_tsv (oracle/_ref, where /root/reference exists) and against the outputs recorded from it
+    (tests/golden/eventalign_golden.npz) anywhere;
+  * the C++ cursor logic on the CPU: rounds are pulled out of EventAligner, the paths come from the plain-C Viterbi
+    oracle and are fed back — the text it then writes must equal the reference's, byte for byte;
+  * on the GPU the same through EventAligner::run (one Viterbi launch per round, events resident after round one).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from nanopolish_b200 import synth
+from oracle import eventalign_py as EP
+from tests import eventalign_cases as EC
+from tests.test_host_mirror import HOST_SO, _register, _register_reads
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eventalign_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def cases():
+    return EC.build_cases()
+
+
+@pytest.fixture(scope="module")
+def golden():
+    z = np.load(GOLD)
+    return {k: z[k].tobytes().decode() for k in z.files}
+
+
+@pytest.fixture(scope="module")
+def restated(cases, port_oracle):
+    model, rs, cs = cases
+    out = []
+    for c in cs:
+        st = {}
+        al = EP.align_read_to_ref(c["read"], c["contig_name"], c["fetched"], c["ref_pos"], c["flag"], c["cigar"], c["read_idx"],
+                                  EC.port_align_fn(port_oracle, rs, model, EC.read_slot(c, rs.n_reads)), *c["region"], stats=st)
+        out.append((al, st.get("segments", 0)))
+    return out
+
+
+def _single_segment(c):
+    return not any((int(x) & 15) == 3 for x in c["cigar"])
+
+
+def test_restatement_matches_compiled_reference(cases, restated, ref_oracle):
+    model, rs, cs = cases
+    ref_oracle.clear_reads()
+    mh = ref_oracle.builtin_model("nucleotide")
+    rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, mh)
+    for c, (al, _) in zip(cs, restated):
+        slot, r = EC.read_slot(c, rs.n_reads), c["read"]
+        ref_oracle.read_set_eventalign(rh[slot], r.name, r.read_sequence, r.b2e_start, c["b2e_stop"], r.stdv, r.duration)
+        tsv, cigar, ea = ref_oracle.eventalign(rh[slot], c["contig_name"], c["contig"], c["ref_pos"], c["flag"], c["cigar"],
+                                               c["read_idx"], c["region"], want_cigar=_single_segment(c))
+        assert EP.tsv(r, al) == tsv
+        assert [(a.ref_position, a.event_idx, ord(a.hmm_state)) for a in al] == [tuple(int(v) for v in row) for row in ea]
+        if _single_segment(c):
+            assert EP.event_cigar(al) == cigar
+    ref_oracle.clear_reads()
+
+
+def test_restatement_matches_golden(cases, restated, golden):
+    model, rs, cs = cases
+    rows = 0
+    for c, (al, segs) in zip(cs, restated):
+        assert EP.tsv(c["read"], al) == golden[f"tsv_{c['read_idx']}"]
+        if _single_segment(c):
+            assert EP.event_cigar(al) == golden[f"cigar_{c['read_idx']}"]
+        rows += len(al)
+    assert rows > 6000                                   # forward, reverse, two-segment, windowed and unmapped records
+    assert golden["tsv_4"] == ""                         # the unmapped record aligns nothing
+
+
+# ---- the C++ host side --------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def host():
+    lib = C.CDLL(HOST_SO)
+    lib.nphh_last_error.restype = C.c_char_p
+    for f in ("nphh_ea_run", "nphh_ea_next_round", "nphh_ea_text", "nphh_ea_num_segments", "nphh_aligned_segments"):
+        getattr(lib, f).restype = C.c_longlong
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _setup(host, cases):
+    model, rs, cs = cases
+    host.nphh_clear()
+    mh = _register(host, model)
+    rh = _register_reads(host, rs, mh)
+    host.nphh_ea_begin()
+    for c in cs:
+        slot, r = EC.read_slot(c, rs.n_reads), c["read"]
+        a, b = np.ascontiguousarray(r.b2e_start, np.int32), np.ascontiguousarray(c["b2e_stop"], np.int32)
+        assert host.nphh_read_set_eventalign(rh[slot], r.name.encode(), r.read_sequence.encode(), _p(a), _p(b), C.c_size_t(a.shape[0]),
+                                             _p(np.ascontiguousarray(r.stdv)), _p(np.ascontiguousarray(r.duration))) == 0
+        idx = host.nphh_ea_add_read(rh[slot], c["contig_name"].encode(), c["ref_pos"], c["flag"], c["mapq"], _p(c["cigar"]),
+                                    int(c["cigar"].shape[0]), c["fetched"].encode(), c["read_idx"], c["region"][0], c["region"][1])
+        assert idx == c["read_idx"], host.nphh_last_error()
+
+
+def _text(host, idx, what):
+    buf = C.create_string_buffer(1 << 21)
+    n = host.nphh_ea_text(idx, what, buf, C.c_size_t(1 << 21))
+    assert n >= 0, host.nphh_last_error()
+    return buf.value.decode()
+
+
+def _check_outputs(host, cases, restated, golden):
+    model, rs, cs = cases
+    for c, (al, segs) in zip(cs, restated):
+        i, r = c["read_idx"], c["read"]
+        assert _text(host, i, 0) == golden[f"tsv_{i}"]                                     # the compiled reference's bytes
+        assert _text(host, i, 1) == EP.tsv(r, al, print_read_names=True)                   # -n
+        assert _text(host, i, 2) == EP.tsv(r, al, scale_events=True)                       # --scale-events
+        assert host.nphh_ea_num_segments(i) == segs
+        assert _text(host, i, 5) == EP.summary_row(r, al, i, "read.fast5").replace(r.model_name, "")   # host test models carry no name
+        if _single_segment(c):
+            assert _text(host, i, 4) == golden[f"cigar_{i}"]
+            assert _text(host, i, 3) == EP.sam(r, al, c["mapq"])
+    assert _text(host, 0, 6) == ("contig\tposition\treference_kmer\tread_index\tstrand\tevent_index\tevent_level_mean\tevent_stdv\t"
+                                 "event_length\tmodel_kmer\tmodel_mean\tmodel_stdv\tstandardized_level\n")
+
+
+def test_host_chaining_logic_on_cpu(host, cases, restated, golden, port_oracle):
+    """EventAligner's cursors, fed with the plain-C Viterbi's paths (no device involved)."""
+    model, rs, cs = cases
+    _setup(host, cases)
+    jobs = np.zeros(len(cs), synth.HMM_JOB_DT)
+    ranks = np.zeros(len(cs) * 400, np.uint32)
+    n_ranks = C.c_uint64()
+    rounds = 0
+    while True:
+        n = host.nphh_ea_next_round(_p(jobs), C.c_size_t(jobs.shape[0]), _p(ranks), C.c_size_t(ranks.shape[0]), C.byref(n_ranks))
+        assert n >= 0, host.nphh_last_error()
+        if n == 0:
+            break
+        paths, off = [], [0]
+        for j in range(n):
+            jb = jobs[j].copy()
+            jb["read"] = EC.read_slot(cs[int(jb["read"])], rs.n_reads)      # aligner index -> synthetic read
+            st, status = port_oracle.hmm_align(rs.reads, rs.ev_mean, rs.ev_start_time, [model], ranks, jb)
+            paths.append(st); off.append(off[-1] + st.shape[0])
+        flat = np.concatenate(paths) if off[-1] else np.zeros(0, synth.ALIGN_STATE_DT)
+        assert host.nphh_ea_consume(C.c_size_t(n), _p(np.array(off, np.uint64)), _p(flat)) == 0, host.nphh_last_error()
+        rounds += 1
+    assert rounds == max(s for _, s in restated)          # launches = the longest read's segment count
+    _check_outputs(host, cases, restated, golden)
+    host.nphh_ea_begin()
+
+
+def test_get_aligned_segments(host):
+    ops = [(5, "S"), (10, "M"), (2, "I"), (3, "D"), (4, "="), (7, "N"), (6, "X"), (3, "H")]
+    cigar = EP.pack_cigar(ops)
+    want = EP.get_aligned_segments(1000, cigar)
+    pairs = np.zeros((64, 2), np.int32)
+    seg_off = np.zeros(8, np.uint64)
+    n = host.nphh_aligned_segments(1000, _p(cigar), int(cigar.shape[0]), _p(pairs), C.c_size_t(64), _p(seg_off), C.c_size_t(8))
+    assert n == len(want) == 2
+    for s in range(n):
+        got = [tuple(int(v) for v in p) for p in pairs[int(seg_off[s]):int(seg_off[s + 1])]]
+        assert got == want[s]
+    assert want[0][0] == (1000, 5) and want[1][0] == (1000 + 10 + 3 + 4 + 7, 5 + 10 + 2 + 4)
+    bad = EP.pack_cigar([(3, "P")])
+    assert host.nphh_aligned_segments(0, _p(bad), 1, _p(pairs), C.c_size_t(64), _p(seg_off), C.c_size_t(8)) < 0     # the reference asserts
+
+
+@pytest.mark.gpu
+def test_eventalign_on_device(host, cases, restated, golden):
+    """The whole thing: every round's segments through hmm_viterbi_kernel, text identical to the reference's."""
+    _setup(host, cases)
+    rounds = host.nphh_ea_run(C.c_double(1.0))
+    assert rounds >= 0, host.nphh_last_error()
+    assert rounds == max(s for _, s in restated)
+    _check_outputs(host, cases, restated, golden)
+    host.nphh_ea_begin()
