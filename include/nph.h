@@ -244,6 +244,8 @@ int nph_hmm_align(nph_ctx* ctx,
 typedef struct {
     uint32_t window_length1, window_length2;   /* 3, 6 for DNA; 7, 14 for RNA */
     float threshold1, threshold2, peak_height;  /* 1.4, 9.0, 0.2 for DNA; 2.5, 9.0, 1.0 for RNA */
+    uint32_t reverse_events;  /* nph_load_from_raw_batch only: 1 for direct RNA, whose events load_from_raw turns
+                                 around to 5'->3' after the MoM estimate (src/nanopolish_squiggle_read.cpp:262-265) */
 } nph_event_params;
 /* scrappie's event_t reduced to what it computes here (pos/state are always -1 there) */
 typedef struct { uint64_t start; float length; float mean; float stdv; uint32_t reserved; } nph_event;
@@ -298,10 +300,13 @@ int nph_recalibrate_batch(nph_ctx* ctx, const nph_read* reads, size_t n_reads, c
                           const nph_abea_result* results, nph_event_range* base_to_event_out, nph_calibration* calibrations_out);
 
 /* ---- the whole read prologue in one call (section 8f N4) ------------------------------------------------
- * SquiggleRead::load_from_raw for a batch of DNA reads: trim_and_segment_raw (200, 10, 100, 0.0) -> detect_events ->
+ * SquiggleRead::load_from_raw for a batch of reads: trim_and_segment_raw (200, 10, 100, 0.0) -> detect_events ->
  * SquiggleEvent conversion -> estimate_scalings_using_mom -> adaptive_banded_simple_event_align -> base_to_event_map,
  * events_per_base, recalibrate_model and the QC, chained on the device (the samples cross PCIe once, events never
  * come back in between).  ref: src/nanopolish_squiggle_read.cpp:226-336.
+ * DNA: params = event_detection_defaults, a 6-mer nucleotide model.  Direct RNA: params = event_detection_rna with
+ * reverse_events = 1, the 5-mer u_to_t_rna model, ranks of the sequence with U replaced by T (:206-213); the events
+ * come back in 5'->3' order, each keeping the start time it had in acquisition order (so start times descend).
  * Outputs, per job j:  events [event_off_out[j], event_off_out[j+1]) of the four event arrays (compact, job order;
  * SquiggleEvent::log_stdv = logf(stdv) is left to the caller's libm), calibrations_out[j] (status != 0: the reference
  * clears the read's events; the arrays still hold them), base_to_event_out[rank_off + ki] (optional).

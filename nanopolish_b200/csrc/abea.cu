@@ -336,6 +336,8 @@ struct MomParams {
     const nph_abea_job* jobs;
     uint32_t n_jobs;
     double* out;     // 2 per job: shift, scale
+    int reversed;    // 1: the event array is stored back to front (direct RNA after load_from_raw's reversal); the sums
+                     // still run in acquisition order, the order the reference's MoM sees (squiggle_read.cpp:237-239)
 };
 
 __global__ void __launch_bounds__(kThreads) mom_kernel(const MomParams p)
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(kThreads) mom_kernel(const MomParams p)
         const int n = (int)rd.n_events, nk = (int)job.n_kmers;
         double ev_sum = 0.0, k_sum = 0.0, k_sq = 0.0, ev_sq = 0.0;
         for (int i0 = 0; i0 < n; i0 += 32) {
-            s_buf[wib][lane] = (i0 + lane < n) ? (double)m[i0 + lane] : 0.0;
+            s_buf[wib][lane] = (i0 + lane < n) ? (double)m[p.reversed ? n - 1 - (i0 + lane) : i0 + lane] : 0.0;
             __syncwarp();
             if (lane == 0) { const int cnt = min(32, n - i0); for (int t = 0; t < cnt; ++t) ev_sum = __dadd_rn(ev_sum, s_buf[wib][t]); }
             __syncwarp();
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(kThreads) mom_kernel(const MomParams p)
         shift = __shfl_sync(kFull, shift, 0);
         for (int i0 = 0; i0 < n; i0 += 32) {
             double d = 0.0;
-            if (i0 + lane < n) { d = __dsub_rn((double)m[i0 + lane], shift); d = __dmul_rn(d, d); }
+            if (i0 + lane < n) { d = __dsub_rn((double)m[p.reversed ? n - 1 - (i0 + lane) : i0 + lane], shift); d = __dmul_rn(d, d); }
             s_buf[wib][lane] = d;
             __syncwarp();
             if (lane == 0) { const int cnt = min(32, n - i0); for (int t = 0; t < cnt; ++t) ev_sq = __dadd_rn(ev_sq, s_buf[wib][t]); }
@@ -436,9 +438,10 @@ int nph_launch_abea(nph_ctx* ctx)
 }
 
 // estimate_scalings_using_mom over the loaded ABEA jobs (reads, ranks and jobs already on the device)
-int nph_launch_mom(nph_ctx* ctx, double* d_shift_scale_out)
+int nph_launch_mom(nph_ctx* ctx, double* d_shift_scale_out, bool reversed)
 {
     MomParams p{};
+    p.reversed = reversed ? 1 : 0;
     p.ev_mean = ctx->d_ev_mean.p; p.reads = ctx->d_reads.p; p.models = ctx->d_models.p; p.model_id = ctx->abea_model;
     p.ranks = ctx->d_abea_ranks.p; p.jobs = ctx->d_abea_jobs.p; p.n_jobs = (uint32_t)ctx->n_abea_jobs; p.out = d_shift_scale_out;
     const int grid = (int)std::min<size_t>((ctx->n_abea_jobs + kWarps - 1) / kWarps, (size_t)ctx->sm_count * 4);

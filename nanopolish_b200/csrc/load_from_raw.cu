@@ -31,6 +31,7 @@ struct ConvParams {
     const uint32_t* n_events;
     const double* sample_rate;
     uint32_t n_reads;
+    int reverse;                     // direct RNA: event i lands at n-1-i (std::reverse, squiggle_read.cpp:262-265)
     float* mean; float* stdv; float* duration; float* level;
     double* start_time;
     DevRead* reads;
@@ -51,11 +52,12 @@ __global__ void __launch_bounds__(kConvWarps * 32) convert_kernel(const ConvPara
         double acc = 0.0;
         for (uint32_t i0 = 0; i0 < n; i0 += 32) {
             const uint32_t i = i0 + lane;
+            const uint64_t oi = o + (p.reverse ? n - 1 - i : i);
             float d = 0.0f;
             if (i < n) {
                 const nph_event e = ev[i];
                 d = (float)__ddiv_rn((double)e.length, rate);
-                p.mean[o + i] = e.mean; p.level[o + i] = e.mean; p.stdv[o + i] = e.stdv; p.duration[o + i] = d;
+                p.mean[oi] = e.mean; p.level[oi] = e.mean; p.stdv[oi] = e.stdv; p.duration[oi] = d;
             }
             s_d[wib][lane] = d;
             __syncwarp();
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(kConvWarps * 32) convert_kernel(const ConvPara
                 if (j == lane) mine = acc;
                 acc = __dadd_rn(acc, (double)s_d[wib][j]);
             }
-            if (i < n) p.start_time[o + i] = mine;
+            if (i < n) p.start_time[oi] = mine;
             __syncwarp();
         }
         if (lane == 0) {
@@ -226,7 +228,7 @@ extern "C" int nph_load_from_raw_batch(nph_ctx* ctx, const float* raw, size_t n_
         NPH_CUDA(ctx, cudaMemcpyAsync(d_out_off, out_off.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, ctx->stream));
         NPH_CUDA(ctx, cudaMemcpyAsync(d_rate, rate.data(), sizeof(double) * nl, cudaMemcpyHostToDevice, ctx->stream));
         ConvParams cp{};
-        cp.events = d_events; cp.cap_off = d_cap_off; cp.out_off = d_out_off; cp.n_events = d_counts; cp.sample_rate = d_rate; cp.n_reads = (uint32_t)nl;
+        cp.events = d_events; cp.cap_off = d_cap_off; cp.out_off = d_out_off; cp.n_events = d_counts; cp.sample_rate = d_rate; cp.n_reads = (uint32_t)nl; cp.reverse = params->reverse_events ? 1 : 0;
         cp.mean = ctx->d_ev_mean.p; cp.stdv = d_stdv; cp.duration = d_dur; cp.level = ctx->d_level.p; cp.start_time = ctx->d_ev_time.p; cp.reads = ctx->d_reads.p;
         NPH_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
         convert_kernel<<<(unsigned)std::min<size_t>((nl + kConvWarps - 1) / kConvWarps, (size_t)ctx->sm_count * 8), kConvWarps * 32, 0, ctx->stream>>>(cp); ++launches;
@@ -248,7 +250,7 @@ extern "C" int nph_load_from_raw_batch(nph_ctx* ctx, const float* raw, size_t n_
     ctx->h_read_n_events.assign(counts.begin(), counts.end());
     ctx->reads_loaded = true;                      // for the staged ABEA calls below; cleared again before returning
     int rc = nph_abea_jobs_load(ctx, kmer_ranks, n_ranks_total, aj.data(), nl, model_id, pairs_total);
-    if (rc == NPH_OK) rc = nph_launch_mom(ctx, d_mom);
+    if (rc == NPH_OK) rc = nph_launch_mom(ctx, d_mom, params->reverse_events != 0);
     if (rc == NPH_OK) {
         apply_mom_kernel<<<(unsigned)((nl + 127) / 128), 128, 0, ctx->stream>>>(d_mom, ctx->d_reads.p, d_views, (uint32_t)nl);
         launches += 2;

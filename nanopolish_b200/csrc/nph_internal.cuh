@@ -164,4 +164,4 @@ struct NphCalArgs {
     int* bad_input;
 };
 int nph_launch_recalibrate(nph_ctx* ctx, const NphCalArgs& args);
-int nph_launch_mom(nph_ctx* ctx, double* d_shift_scale_out);     // over the loaded ABEA jobs: 2 doubles per job
+int nph_launch_mom(nph_ctx* ctx, double* d_shift_scale_out, bool reversed = false);     // over the loaded ABEA jobs: 2 doubles per job

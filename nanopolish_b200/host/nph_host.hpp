@@ -146,6 +146,7 @@ struct GaussianParameters {
 };
 
 enum PoreType { PORETYPE_R7 = 0, PORETYPE_R9 = 1 };
+enum SquiggleReadNucleotideType { SRNT_DNA = 0, SRNT_RNA = 1 };     // ref: src/nanopolish_squiggle_read.h:38-43
 
 // ref: src/nanopolish_squiggle_read.h:32-46
 struct IndexPair {
@@ -223,6 +224,7 @@ public:
 
     std::string read_name;
     PoreType pore_type = PORETYPE_R9;
+    SquiggleReadNucleotideType nucleotide_type = SRNT_DNA;
     uint32_t read_id = 0;
     std::string read_sequence;
     std::vector<SquiggleEvent> events[2];

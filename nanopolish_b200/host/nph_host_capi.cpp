@@ -15,6 +15,7 @@ std::vector<std::unique_ptr<PoreModel>> g_models;
 std::vector<std::unique_ptr<SquiggleRead>> g_reads;
 EventAligner g_aligner;
 AlignBatch g_round_batch;
+bool g_raw_is_rna = false;
 thread_local std::string g_err;
 template <typename F> int guard(F f) { try { f(); return 0; } catch (const Error& e) { g_err = e.what(); return e.status; } catch (const std::exception& e) { g_err = e.what(); return NPH_ERR_INVALID; } }
 }
@@ -105,6 +106,7 @@ int nphh_read_create(uint32_t n_events, const float* mean, const double* start_t
 void nphh_read_add_model(int read, const char* alphabet, int model) { g_reads[read]->alt_models[0][alphabet] = g_models[model].get(); }
 void nphh_clear() { g_reads.clear(); }
 void nphh_set_indel_bias(double v) { hmm_indel_bias_factor = v; }
+void nphh_set_rna(int rna) { g_raw_is_rna = rna != 0; }        // nucleotide type of the reads nphh_load_from_raw builds
 
 // profile_hmm_score(sequence, data, flags) exactly as a nanopolish caller writes it
 int nphh_profile_hmm_score(int read, int model, const char* seq, uint32_t e_start, uint32_t e_stop, int rc, uint32_t flags, float* out)
@@ -278,6 +280,7 @@ int nphh_load_from_raw(int model, int n, const float* samples, const uint64_t* s
             raw[i].read_sequence.assign(seqs + seq_off[i], seqs + seq_off[i + 1]);
             raw[i].samples.assign(samples + sample_off[i], samples + sample_off[i + 1]);
             raw[i].sample_rate = sample_rate;
+            raw[i].nucleotide_type = g_raw_is_rna ? SRNT_RNA : SRNT_DNA;
         }
         LoadFromRawStats st;
         std::vector<std::unique_ptr<SquiggleRead>> rs = load_from_raw(Engine::thread_default(), *g_models[model], raw, &st);

@@ -1,12 +1,13 @@
 // nph_raw.cpp — see nph_raw.hpp.
 #include "nph_raw.hpp"
 
+#include <algorithm>
 #include <cmath>
 
 namespace nph {
 
-const nph_event_params event_detection_defaults = {3, 6, 1.4f, 9.0f, 0.2f};
-const nph_event_params event_detection_rna = {7, 14, 2.5f, 9.0f, 1.0f};
+const nph_event_params event_detection_defaults = {3, 6, 1.4f, 9.0f, 0.2f, 0};
+const nph_event_params event_detection_rna = {7, 14, 2.5f, 9.0f, 1.0f, 1};      // + events turned around to 5'->3' by load_from_raw
 
 namespace {
 
@@ -70,11 +71,19 @@ std::vector<std::unique_ptr<SquiggleRead>> load_from_raw(Engine& engine, const P
     st.total = n;
     std::vector<std::unique_ptr<SquiggleRead>> reads(n);
     const uint32_t k = base_model.k;
+    // direct RNA (squiggle_read.cpp:192-213): the caller passes the r9.4_70bps u_to_t_rna 5-mer model; the basecall's
+    // U become T, the RNA detector parameters apply and the events are turned around to 5'->3'
+    bool rna = false;
+    for (size_t i = 0; i < n; ++i) rna = rna || raw[i].nucleotide_type == SRNT_RNA;
+    for (size_t i = 0; i < n; ++i)
+        if ((raw[i].nucleotide_type == SRNT_RNA) != rna) throw Error(NPH_ERR_INVALID, "load_from_raw: DNA and RNA reads in one batch (they use different models)");
     for (size_t i = 0; i < n; ++i) {
         reads[i].reset(new SquiggleRead());
         SquiggleRead& sr = *reads[i];
         sr.read_name = raw[i].read_name;
         sr.read_sequence = raw[i].read_sequence;
+        sr.nucleotide_type = raw[i].nucleotide_type;
+        if (rna) std::replace(sr.read_sequence.begin(), sr.read_sequence.end(), 'U', 'T');
         sr.pore_type = PORETYPE_R9;
         sr.base_model[0] = &base_model;
         sr.sample_rate = raw[i].sample_rate;
@@ -85,10 +94,11 @@ std::vector<std::unique_ptr<SquiggleRead>> load_from_raw(Engine& engine, const P
     std::vector<uint32_t> ranks;
     size_t total = 0;
     for (size_t i = 0; i < n; ++i) {
-        if (raw[i].samples.empty() || raw[i].read_sequence.size() < k || !(raw[i].sample_rate > 0.0)) { ++st.empty_after_trim; continue; }
-        const uint32_t n_kmers = (uint32_t)(raw[i].read_sequence.size() - k + 1);
+        const std::string& seq = reads[i]->read_sequence;
+        if (raw[i].samples.empty() || seq.size() < k || !(raw[i].sample_rate > 0.0)) { ++st.empty_after_trim; continue; }
+        const uint32_t n_kmers = (uint32_t)(seq.size() - k + 1);
         jobs.push_back(nph_raw_job{total, ranks.size(), (uint32_t)raw[i].samples.size(), n_kmers, raw[i].sample_rate});
-        for (uint32_t j = 0; j < n_kmers; ++j) ranks.push_back(base_model.pmalphabet->kmer_rank(raw[i].read_sequence.c_str() + j, k));
+        for (uint32_t j = 0; j < n_kmers; ++j) ranks.push_back(base_model.pmalphabet->kmer_rank(seq.c_str() + j, k));
         total += raw[i].samples.size();
         sent.push_back((uint32_t)i);
     }
@@ -103,7 +113,7 @@ std::vector<std::unique_ptr<SquiggleRead>> load_from_raw(Engine& engine, const P
     std::vector<nph_event_range> b2e(ranks.size());
     std::vector<nph_calibration> cal(sent.size());
     engine.check(nph_load_from_raw_batch(engine.ctx(), flat.data(), flat.size(), ranks.data(), ranks.size(), jobs.data(), jobs.size(),
-                                         engine.model_id(&base_model), &event_detection_defaults, off.data(), mean.data(), stdv.data(),
+                                         engine.model_id(&base_model), rna ? &event_detection_rna : &event_detection_defaults, off.data(), mean.data(), stdv.data(),
                                          start.data(), dur.data(), cap, b2e.data(), cal.data()),
                  "nph_load_from_raw_batch");
 

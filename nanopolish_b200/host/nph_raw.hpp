@@ -9,8 +9,8 @@
 //   recalibrate_model + QC                          ref: src/nanopolish_squiggle_read.cpp:304-336
 //
 // The reference does this per read inside the SquiggleRead constructor (one read per OpenMP thread); here the reads
-// of a BamProcessor batch / an AlignmentDB region go through one device call (nph_load_from_raw_batch).  DNA reads only: the RNA
-// branch (different kit, event reversal) is not on the accelerated path.
+// of a BamProcessor batch / an AlignmentDB region go through one device call (nph_load_from_raw_batch).  DNA and direct
+// RNA (squiggle_read.cpp:192-213,262-265: U->T, 5-mer u_to_t_rna model, RNA detector parameters, events reversed to 5'->3').
 #pragma once
 #include "nph_host.hpp"
 
@@ -22,6 +22,7 @@ struct RawRead {
     std::string read_sequence;        // the basecalled sequence
     std::vector<float> samples;       // picoamps, like raw_table::raw
     double sample_rate = 4000.0;
+    SquiggleReadNucleotideType nucleotide_type = SRNT_DNA;   // SRNT_RNA: experiment_type "rna"/"internal_rna" (squiggle_read.cpp:192-195)
 };
 
 // the reference's global counters g_failed_alignment_reads / g_failed_calibration_reads / g_qc_fail_reads

@@ -43,12 +43,12 @@ ALIGN_STATE_DT = np.dtype([("event_idx", "<u4"), ("kmer_idx", "<u4"), ("l_fm", "
 EVENT_DT = np.dtype([("start", "<u8"), ("length", "<f4"), ("mean", "<f4"), ("stdv", "<f4"), ("reserved", "<u4")], align=True)
 RAW_READ_DT = np.dtype([("sample_off", "<u8"), ("event_off", "<u8"), ("n_samples", "<u4"), ("event_cap", "<u4")], align=True)
 EVENT_PARAMS_DT = np.dtype([("window_length1", "<u4"), ("window_length2", "<u4"), ("threshold1", "<f4"), ("threshold2", "<f4"),
-                            ("peak_height", "<f4")], align=True)
+                            ("peak_height", "<f4"), ("reverse_events", "<u4")], align=True)
 RAW_RANGE_DT = np.dtype([("start", "<u4"), ("end", "<u4")], align=True)
 EVENT_RANGE_DT = np.dtype([("start", "<i4"), ("stop", "<i4")], align=True)
 CALIBRATION_DT = np.dtype([("shift", "<f8"), ("scale", "<f8"), ("drift", "<f8"), ("var", "<f8"), ("events_per_base", "<f8"),
                            ("n_used", "<u4"), ("status", "<i4")], align=True)
-assert EVENT_DT.itemsize == 24 and RAW_READ_DT.itemsize == 24 and EVENT_PARAMS_DT.itemsize == 20
+assert EVENT_DT.itemsize == 24 and RAW_READ_DT.itemsize == 24 and EVENT_PARAMS_DT.itemsize == 24
 RAW_JOB_DT = np.dtype([("sample_off", "<u8"), ("rank_off", "<u8"), ("n_samples", "<u4"), ("n_kmers", "<u4"), ("sample_rate", "<f8")], align=True)
 assert RAW_JOB_DT.itemsize == 32
 assert RAW_RANGE_DT.itemsize == 8 and EVENT_RANGE_DT.itemsize == 8 and CALIBRATION_DT.itemsize == 48
@@ -379,7 +379,8 @@ def methylation_jobs(rs: ReadSet, model_id: int = 0, min_separation: int = 10, m
 def event_params(rna: bool = False) -> np.ndarray:
     """scrappie's event_detection_defaults / event_detection_rna (src/thirdparty/scrappie/event_detection.h:15-29)."""
     p = np.zeros(1, EVENT_PARAMS_DT)
-    p[0] = (7, 14, 2.5, 9.0, 1.0) if rna else (3, 6, 1.4, 9.0, 0.2)
+    # reverse_events: load_from_raw turns direct-RNA events around to 5'->3' (src/nanopolish_squiggle_read.cpp:262-265)
+    p[0] = (7, 14, 2.5, 9.0, 1.0, 1) if rna else (3, 6, 1.4, 9.0, 0.2, 0)
     return p
 
 

@@ -12,10 +12,11 @@ def squiggle_events(ev, sample_rate):
     return dur, t
 
 
-def oracle_chain(port, model, signals, seqs, sample_rate=4000.0):
+def oracle_chain(port, model, signals, seqs, sample_rate=4000.0, rna=False):
     """Returns per read a dict: events (EVENT_DT), duration, start_time, and — when the read got that far — mom, cal
-    (CALIBRATION_DT record), b2e, n_pairs."""
-    prm = synth.event_params(False)
+    (CALIBRATION_DT record), b2e, n_pairs.  rna: scrappie's RNA detector parameters, the MoM estimate on the events in
+    acquisition order, then the events turned around to 5'->3' before ABEA (squiggle_read.cpp:204-213,237-240,262-265)."""
+    prm = synth.event_params(rna)
     out = []
     for x, codes in zip(signals, seqs):
         r = {"events": None}
@@ -31,6 +32,10 @@ def oracle_chain(port, model, signals, seqs, sample_rate=4000.0):
         rs = synth.ReadSet(reads, np.ascontiguousarray(ev["mean"]), r["start_time"], [codes], [None], [None], model.k)
         jobs, ranks, total = synth.abea_jobs(rs)
         sh, sc = port.mom(rs.reads, rs.ev_mean, model, ranks, jobs[0])
+        if rna:
+            ev = r["events"] = np.ascontiguousarray(ev[::-1])
+            r["duration"], r["start_time"] = np.ascontiguousarray(r["duration"][::-1]), np.ascontiguousarray(r["start_time"][::-1])
+            rs = synth.ReadSet(reads, np.ascontiguousarray(ev["mean"]), r["start_time"], [codes], [None], [None], model.k)
         reads[0]["shift"], reads[0]["scale"] = sh, sc
         r["mom"] = (sh, sc)
         pairs, res, _ = port.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, model, ranks, jobs, total)

@@ -214,3 +214,38 @@ def test_load_from_raw_in_one_call(engine, nuc, port_oracle):
     oj = hj.jobs.copy(); oj["model_id"] = 0
     wantS, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [model], hj.kmer_ranks, oj)
     assert np.array_equal(got.view(np.uint32), wantS.view(np.uint32))
+
+
+def test_load_from_raw_direct_rna(engine, port_oracle):
+    """The RNA branch of load_from_raw (src/nanopolish_squiggle_read.cpp:204-213,262-265): 5-mer model, scrappie's RNA
+    detector parameters, MoM on the events in acquisition order, events turned around to 5'->3' (start times then
+    descend) before ABEA and calibration — against the same chain through the oracle."""
+    from oracle.prep_chain import oracle_chain
+    # stands in for r9.4_70bps.u_to_t_rna.5mer: the 6-mer table averaged over its last base (neighbouring k-mers keep
+    # correlated levels, which events straddling a boundary need to survive ABEA's emission QC)
+    m6 = synth.load_model("nucleotide")
+    sd5 = m6.level_stdv.reshape(1024, 4).mean(1)
+    model = synth.PoreModel("derived.nucleotide.5mer", 5, "nucleotide", m6.level_mean.reshape(1024, 4).mean(1), sd5, np.log(sd5))
+    mid = engine.model_upload(model)
+    raw, rr, seqs = synth.gen_raw(4, 60000, model, seed=911, mean_dwell=40.0, return_seqs=True)
+    # the pore reads RNA 3'->5': the trace is the basecall's levels back to front
+    signals = [np.ascontiguousarray(raw[int(r["sample_off"]):int(r["sample_off"]) + int(r["n_samples"])][::-1]) for r in rr]
+    want = oracle_chain(port_oracle, model, signals, seqs, sample_rate=3012.0, rna=True)
+    flat, ranks, jobs = _raw_jobs(signals, seqs, model.k, sample_rate=3012.0)
+    prm = synth.event_params(True)
+    assert int(prm[0]["reverse_events"]) == 1
+    off, mean, stdv, start, dur, b2e, cal = engine.load_from_raw_batch(flat, ranks, jobs, mid, prm)
+    for i, w in enumerate(want):
+        o, n = int(off[i]), int(off[i + 1] - off[i])
+        ev = w["events"]
+        assert n == ev.shape[0] and n > 500
+        assert np.array_equal(mean[o:o + n], ev["mean"]) and np.array_equal(stdv[o:o + n], ev["stdv"])
+        assert np.array_equal(dur[o:o + n], w["duration"]) and np.array_equal(start[o:o + n], w["start_time"])
+        assert start[o] > start[o + n - 1]                                  # acquisition-order times on reversed events
+        assert cal[i].tobytes() == w["cal"].tobytes(), f"read {i}: {cal[i]} != {w['cal']}"
+        assert np.array_equal(b2e[int(jobs[i]["rank_off"]):][:int(jobs[i]["n_kmers"])], w["b2e"])
+    assert (cal["status"] == 0).sum() >= 3                                  # the reversed events do align to the basecall
+    # without the reversal the same signals cannot be aligned to the basecall
+    prm_fwd = prm.copy(); prm_fwd[0]["reverse_events"] = 0
+    cal_fwd = engine.load_from_raw_batch(flat, ranks, jobs, mid, prm_fwd)[6]
+    assert (cal_fwd["status"] != 0).all()

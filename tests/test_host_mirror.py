@@ -276,3 +276,50 @@ def test_load_from_raw_like_a_caller(host, port_oracle):
     assert [int(v) for v in stats] == [n, 1, stats[2], stats[3], stats[4]] and int(stats[2] + stats[3] + stats[4]) == dropped
     assert (n_events[:4] > 2000).all() and (n_events[4:] == 0).all()
     assert int(want[4]["cal"]["status"]) == 2 and want[5]["n_pairs"] == 0 and want[6]["events"] is None and [int(v) for v in stats[1:4]] == [1, 2, 1]
+
+
+@pytest.mark.gpu
+def test_load_from_raw_direct_rna_like_a_caller(host, port_oracle):
+    """The RNA branch through nph::load_from_raw: basecalls with U, a 5-mer u_to_t_rna model, RNA detector parameters,
+    events turned around to 5'->3' (src/nanopolish_squiggle_read.cpp:192-213,262-265) — vs the chain through the oracle."""
+    from oracle.prep_chain import oracle_chain
+    m6 = synth.load_model("nucleotide")
+    sd5 = m6.level_stdv.reshape(1024, 4).mean(1)
+    rna = synth.PoreModel("derived.u_to_t_rna.5mer", 5, "nucleotide", m6.level_mean.reshape(1024, 4).mean(1), sd5, np.log(sd5))
+    raw, rr, seqs = synth.gen_raw(3, 50000, rna, seed=431, mean_dwell=40.0, return_seqs=True)
+    signals = [np.ascontiguousarray(raw[int(r["sample_off"]):int(r["sample_off"]) + int(r["n_samples"])][::-1]) for r in rr]
+    n = len(signals)
+    want = oracle_chain(port_oracle, rna, signals, seqs, sample_rate=3012.0, rna=True)
+    mean5, sd = np.ascontiguousarray(rna.level_mean), np.ascontiguousarray(rna.level_stdv)
+    lsd = np.ascontiguousarray(rna.level_log_stdv)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    mh = host.nphh_model_create(b"u_to_t_rna", 5, 1024, p(mean5), p(sd), p(lsd))
+    assert mh >= 0, host.nphh_last_error()
+    soff = np.zeros(n + 1, np.uint64); soff[1:] = np.cumsum([s.shape[0] for s in signals])
+    qoff = np.zeros(n + 1, np.uint64); qoff[1:] = np.cumsum([c.shape[0] for c in seqs])
+    seqbuf = b"".join(synth._CODE2DNA[c].tobytes() for c in seqs).replace(b"T", b"U")        # what an RNA basecaller writes
+    eoff = np.zeros(n, np.uint64); eoff[1:] = np.cumsum([s.shape[0] // 2 + 8 for s in signals])[:-1]
+    room = int(eoff[-1]) + signals[-1].shape[0] // 2 + 8
+    n_events = np.zeros(n, np.uint32); scal = np.zeros((n, 5)); stats = np.zeros(5, np.uint64)
+    mean = np.zeros(room, np.float32); stdv = np.zeros(room, np.float32); start = np.zeros(room, np.float64); dur = np.zeros(room, np.float32)
+    b2e = np.full((int(qoff[-1]), 2), -7, np.int32)
+    flat = np.concatenate(signals)
+    host.nphh_set_rna(1)
+    try:
+        rc = host.nphh_load_from_raw(mh, n, p(flat), p(soff), seqbuf, p(qoff), C.c_double(3012.0), p(n_events), p(scal), p(eoff), p(mean), p(stdv),
+                                     p(start), p(dur), p(b2e), p(stats))
+    finally:
+        host.nphh_set_rna(0)
+    assert rc >= 0, host.nphh_last_error()
+    for i in range(n):
+        w = want[i]
+        assert w["n_pairs"] > 0 and int(w["cal"]["status"]) == 0
+        ev = w["events"]; o = int(eoff[i])
+        assert n_events[i] == ev.shape[0]
+        assert np.array_equal(mean[o:o + ev.shape[0]], ev["mean"]) and np.array_equal(start[o:o + ev.shape[0]], w["start_time"])
+        c = w["cal"]
+        assert tuple(scal[i]) == (c["shift"], c["scale"], c["drift"], c["var"], c["events_per_base"])
+        nk = seqs[i].shape[0] - 5 + 1
+        got = b2e[int(qoff[i]):int(qoff[i]) + nk]
+        assert np.array_equal(got[:, 0], w["b2e"]["start"]) and np.array_equal(got[:, 1], w["b2e"]["stop"])
+    assert [int(v) for v in stats] == [n, 0, 0, 0, 0]
