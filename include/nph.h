@@ -236,6 +236,54 @@ int nph_hmm_align(nph_ctx* ctx,
                   nph_align_state* states_out, const uint64_t* states_off,
                   uint32_t* n_states_out, float* scores_out);
 
+/* ---- eventalign: a read's whole segment chain on the device (section 8f N1) ------------------------------
+ * align_read_to_ref (src/alignment/nanopolish_eventalign.cpp:612-827) walks one BAM-aligned segment of a read in
+ * ~100-base steps: pick the aligned pair ~100 reference bases ahead (get_end_pair :196-207), the event nearest to its
+ * read k-mer (SquiggleRead::get_closest_event_to, src/nanopolish_squiggle_read.cpp:160-186), profile_hmm_align over
+ * that window, emit up to 50 event alignments (all of them in the last section), restart from the last one emitted.
+ * Each step depends on the previous path, so one warp walks one chain from start to end: cursor, Viterbi fill,
+ * backtrack and emission stay on the device, and a batch of reads is ONE launch instead of one per step.
+ * A chain is one BAM segment (the pieces between N operations) of one read strand, already trimmed to the region and
+ * to the read's last k-mer by the caller (trim_aligned_pairs_to_ref_region / _to_kmer, :166-193).
+ * Reads: the batch a preceding nph_reads_load left resident. */
+typedef struct {
+    uint64_t pair_off;        /* this segment's aligned pairs (ref_pos ascending, read_pos = BAM query k-mer) in pairs[] */
+    uint64_t map_off;         /* the read's base_to_event_map[*].indices[strand].start in event_map_start[] (-1: none) */
+    uint64_t rank_off;        /* the record's reference in ref_ranks_fwd[] / ref_ranks_rc[]: entry p = rank of the k-mer at
+                                 reference offset p (fwd) / of its reverse complement as HMMInputSequence resolves it (rc) */
+    uint64_t out_off;         /* where this chain's records go in records_out[] */
+    uint32_t read;            /* index into the resident reads */
+    uint32_t model_id;
+    uint32_t n_pairs;
+    uint32_t map_len;         /* base_to_event_map.size() */
+    uint32_t ref_len;         /* ref_seq.length(); ref_len - k + 1 rank entries */
+    uint32_t read_seq_len;    /* read_sequence.size() (SquiggleRead::flip_k_strand) */
+    uint32_t out_cap;         /* room at out_off; abs(last_event - first_event) + 2 always suffices */
+    int32_t  ref_offset;      /* record->core.pos */
+    int32_t  first_event;     /* get_closest_event_to of the segment's first pair (after flip_k_strand if reversed) */
+    int32_t  last_event;      /* ... of its last pair */
+    uint8_t  do_base_rc;      /* bam_is_rev(record) */
+    uint8_t  rc;              /* HMMInputData::rc == rc_flags[strand] */
+    uint8_t  k;
+    uint8_t  reserved;
+} nph_ea_chain;
+/* one EventAlignment (src/alignment/nanopolish_eventalign.h:54-71) without its strings: ref_kmer and model_kmer are
+ * substrings of the reference at ref_position (model_kmer reverse-complemented for rc reads, NNNNNN for 'B') */
+typedef struct { int32_t ref_position; int32_t event_idx; uint8_t hmm_state; uint8_t reserved[3]; } nph_ea_record;
+#define NPH_EA_OK               0
+#define NPH_EA_WINDOW_TOO_LARGE 1   /* a window has more k-mers or events than the kernel's single-strip scratch holds:
+                                       re-run this read through nph_hmm_align rounds (records so far are valid) */
+#define NPH_EA_RC_STRIDE        2   /* event order disagrees with rc (the reference asserts, profile_hmm_r9.inl:275) */
+#define NPH_EA_OUT_OVERFLOW     4   /* out_cap too small */
+#define NPH_EA_BAD_EVENT        8   /* a cursor event lies outside the read */
+typedef struct { uint32_t n_records; uint32_t n_windows; int32_t status; uint32_t reserved; } nph_ea_result;
+int nph_eventalign_chain(nph_ctx* ctx,
+                         const nph_aligned_pair* pairs, size_t n_pairs_total,
+                         const int32_t* event_map_start, size_t n_map_total,
+                         const uint32_t* ref_ranks_fwd, const uint32_t* ref_ranks_rc, size_t n_ranks_total,
+                         const nph_ea_chain* chains, size_t n_chains, double indel_bias,
+                         nph_ea_record* records_out, size_t records_total, nph_ea_result* results_out);
+
 /* ---- event detection (section 8f N4: the step before ABEA) --------------------------------------
  * scrappie's detect_events as load_from_raw calls it: t-statistics over two windows on prefix sums, a short/long
  * peak detector, events between consecutive boundaries.

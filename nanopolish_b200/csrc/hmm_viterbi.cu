@@ -19,9 +19,7 @@
 //   * the backtrack starts at (last event, MATCH of the last k-mer) and stops at FROM_SOFT, as the
 //     reference does; where the reference would trip an assert (fewer than 2 events, path entering a
 //     -inf cell) the job returns zero states.
-#include "nph_internal.cuh"
-#include "exact_math.cuh"
-#include <math_constants.h>
+#include "hmm_viterbi_kernel.cuh"
 #include <algorithm>
 #include <vector>
 
@@ -31,9 +29,7 @@ namespace {
 
 constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
-constexpr unsigned kFull = 0xffffffffu;
-constexpr int kMinPeriod = 40;
-enum { MV_SAME_M = 0, MV_PREV_M = 1, MV_SAME_B = 2, MV_PREV_B = 3, MV_PREV_K = 4, MV_SOFT = 5 };
+using namespace nph_vit;
 
 struct VitParams {
     const float* level;
@@ -58,27 +54,20 @@ struct VitParams {
     HmmConsts c;
 };
 
-// running max with the reference's tie rule: a later candidate that equals the max takes the label
-__device__ __forceinline__ void vmax(float& mx, int& from, float x, int idx)
-{
-    mx = x > mx ? x : mx;
-    from = (mx == x) ? idx : from;
-}
-
 template <int C>
 __global__ void __launch_bounds__(kThreads, 1) hmm_viterbi_kernel(const VitParams p)
 {
     constexpr int STRIP = 32 * C;
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    float4* const my_params = p.scratch_params + (size_t)warp_global * p.kpad_stride;
-    float* const edge_m = p.scratch_edge + (size_t)warp_global * 3 * p.edge_stride;
-    float* const edge_b = edge_m + p.edge_stride;
-    float* const edge_k = edge_b + p.edge_stride;
-    uint16_t* const trace = p.scratch_trace + (size_t)warp_global * p.trace_stride;
+    VitScratch sc;
+    sc.params = p.scratch_params + (size_t)warp_global * p.kpad_stride;
+    sc.edge_m = p.scratch_edge + (size_t)warp_global * 3 * p.edge_stride;
+    sc.edge_b = sc.edge_m + p.edge_stride;
+    sc.edge_k = sc.edge_b + p.edge_stride;
+    sc.trace = p.scratch_trace + (size_t)warp_global * p.trace_stride;
     const float NEG = -CUDART_INF_F;
-    const float lp_mk = p.c.lp_mk, lp_mb = p.c.lp_mb, lp_bb = p.c.lp_bb, lp_bk = p.c.lp_bk;
-    const float lp_bm_next = p.c.lp_bm_next, lp_bm_self = p.c.lp_bm_self, lp_kk = p.c.lp_kk, lp_km = p.c.lp_km;
+    (void)STRIP;
 
     for (;;) {
         uint32_t slot = 0;
@@ -87,209 +76,29 @@ __global__ void __launch_bounds__(kThreads, 1) hmm_viterbi_kernel(const VitParam
         if (slot >= p.n_jobs) break;
         const uint32_t job_idx = p.order[slot];
         const nph_hmm_job job = p.jobs[job_idx];
-        const DevRead rd = p.reads[job.read];
-        const float2 tr = p.trans[job.read];
-        const float lp_mm_self = tr.x, lp_mm_next = tr.y;
-        const DevModelView mv = p.models[job.model_id];
-        const int K = (int)job.n_kmers;
-        const int E = (int)(job.event_stop > job.event_start ? job.event_stop - job.event_start : job.event_start - job.event_stop) + 1;
-        const int stride = job.stride;
-        const bool pre_clip = (job.flags & NPH_HAF_ALLOW_PRE_CLIP) != 0;
-        const int n_strips = (K + STRIP - 1) / STRIP;
-        const int kpad = n_strips * STRIP;
-        const int P = n_strips > 1 ? max(E, kMinPeriod) : E;
+        VitJob j;
+        j.rd = p.reads[job.read];
+        j.tr = p.trans[job.read];
+        j.mv = p.models[job.model_id];
+        j.lv = p.level + j.rd.event_off;
+        j.rk = p.ranks + job.rank_off;
+        j.K = (int)job.n_kmers;
+        j.E = (int)(job.event_stop > job.event_start ? job.event_stop - job.event_start : job.event_start - job.event_stop) + 1;
+        j.stride = job.stride;
+        j.e_first = (long long)job.event_start;
+        j.pre_clip = (job.flags & NPH_HAF_ALLOW_PRE_CLIP) != 0;
         nph_align_state* const out = p.states + p.states_off[job_idx];
         const int cap = (int)(p.states_off[job_idx + 1] - p.states_off[job_idx]);
 
-        if (E < 2) {                     // the reference asserts n_events >= 2 (profile_hmm_r9.cpp:88)
+        if (j.E < 2) {                   // the reference asserts n_events >= 2 (profile_hmm_r9.cpp:88)
             if (lane == 0) { p.n_states[job_idx] = 0; if (p.scores) p.scores[job_idx] = NEG; }
             continue;
         }
-        {
-            const uint32_t* rk = p.ranks + job.rank_off;
-            for (int i = lane; i < kpad; i += 32) {
-                float4 g = make_float4(0.f, 1.f, 0.f, 1.f);
-                if (i < K) {
-                    const uint32_t r = rk[i];
-                    const float mu = (float)__dadd_rn(__dmul_rn(rd.scale, mv.mean[r]), rd.shift);
-                    const float sd = (float)__dmul_rn(mv.stdv[r], rd.var);
-                    const float lsd = (float)__dadd_rn(mv.log_stdv[r], rd.log_var);
-                    g = make_float4(mu, sd, __fsub_rn(p.c.log_inv_sqrt_2pi, lsd), __frcp_rn(sd));
-                }
-                my_params[i] = g;
-            }
-        }
-        __syncwarp();
-
-        const float* lv = p.level + rd.event_off;
-        const long long e_first = (long long)job.event_start;
-        const int last_strip = n_strips - 1;
-        const int end_lane = ((K - 1) - last_strip * STRIP) / C;
-        const int total_steps = last_strip * P + E + end_lane;
-
-        // ---------------------------------- fill ----------------------------------
-        float mu[C], sd[C], cc[C], ry[C], Mp[C], Bp[C], Kp[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) { mu[c] = 0.f; sd[c] = 1.f; cc[c] = 0.f; ry[c] = 1.f; Mp[c] = NEG; Bp[c] = NEG; Kp[c] = NEG; }
-        float Lm_prev = NEG, Lb_prev = NEG, Lk_prev = NEG;
-        int r = 1 - lane, s = 0;
-        float x_next = 0.f;
-        if (r == 1) x_next = lv[e_first];
-        float em_next = NEG, eb_next = NEG, ek_next = NEG;
-
-        for (int g = 0; g < total_steps; ++g) {
-            float Lm = __shfl_up_sync(kFull, Mp[C - 1], 1);
-            float Lb = __shfl_up_sync(kFull, Bp[C - 1], 1);
-            float Lk = __shfl_up_sync(kFull, Kp[C - 1], 1);
-            if (lane == 0) { Lm = em_next; Lb = eb_next; Lk = ek_next; }
-            const bool in_strip = (r >= 1) && (s < n_strips);
-            const int col0 = s * STRIP + lane * C;
-            const bool live = in_strip && (r <= E) && (col0 < K);
-            const float x = x_next;
-            if (in_strip && r == 1) {
-#pragma unroll
-                for (int c = 0; c < C; ++c) { Mp[c] = NEG; Bp[c] = NEG; Kp[c] = NEG; }
-                Lm_prev = NEG; Lb_prev = NEG; Lk_prev = NEG;
-                if (col0 < K) {
-#pragma unroll
-                    for (int c = 0; c < C; ++c) { const float4 g4 = my_params[col0 + c]; mu[c] = g4.x; sd[c] = g4.y; cc[c] = g4.z; ry[c] = g4.w; }
-                }
-            }
-            {
-                int rn = r + 1, sn = s;
-                if (rn > P) { rn = 1; sn = s + 1; }
-                if (rn >= 1 && rn <= E && sn < n_strips) {
-                    x_next = lv[e_first + (long long)(rn - 1) * stride];
-                    if (lane == 0 && sn > 0) { em_next = edge_m[rn]; eb_next = edge_b[rn]; ek_next = edge_k[rn]; }
-                }
-            }
-            uint16_t tcode[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) tcode[c] = 0;
-            if (live) {
-                float soft = NEG;
-                if (col0 == 0 && (r == 1 || pre_clip)) soft = __fadd_rn(0.0f, p.flank[r - 1]);
-                float lm_prev = Lm_prev, lb_prev = Lb_prev, lk_prev = Lk_prev;
-                float lm_cur = Lm, lb_cur = Lb, lk_cur = Lk;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const float a = div_by_cached_rcp(__fsub_rn(x, mu[c]), sd[c], ry[c]);
-                    const float em = __fadd_rn(cc[c], __fmul_rn(__fmul_rn(-0.5f, a), a));
-                    // MATCH: six candidates in movement order
-                    float m = __fadd_rn(lp_mm_self, Mp[c]);
-                    int fm = MV_SAME_M;
-                    vmax(m, fm, __fadd_rn(lp_mm_next, lm_prev), MV_PREV_M);
-                    vmax(m, fm, __fadd_rn(lp_bm_self, Bp[c]), MV_SAME_B);
-                    vmax(m, fm, __fadd_rn(lp_bm_next, lb_prev), MV_PREV_B);
-                    vmax(m, fm, __fadd_rn(lp_km, lk_prev), MV_PREV_K);
-                    vmax(m, fm, (c == 0) ? soft : NEG, MV_SOFT);
-                    m = __fadd_rn(m, em);
-                    // BAD EVENT: {same M, -inf, same B, -inf, -inf, -inf}
-                    float b = __fadd_rn(lp_mb, Mp[c]);
-                    int fb = MV_SAME_M;
-                    fb = (b == NEG) ? MV_PREV_M : fb;
-                    vmax(b, fb, __fadd_rn(lp_bb, Bp[c]), MV_SAME_B);
-                    fb = (b == NEG) ? MV_SOFT : fb;
-                    // K-MER SKIP: {-inf, prev M, -inf, prev B, prev K, -inf} of the same row
-                    float kk = __fadd_rn(lp_mk, lm_cur);
-                    int fk = MV_PREV_M;
-                    fk = (kk == NEG) ? MV_SAME_B : fk;
-                    vmax(kk, fk, __fadd_rn(lp_bk, lb_cur), MV_PREV_B);
-                    vmax(kk, fk, __fadd_rn(lp_kk, lk_cur), MV_PREV_K);
-                    fk = (kk == NEG) ? MV_SOFT : fk;
-
-                    lm_prev = Mp[c]; lb_prev = Bp[c]; lk_prev = Kp[c];
-                    lm_cur = m; lb_cur = b; lk_cur = kk;
-                    Mp[c] = m; Bp[c] = b; Kp[c] = kk;
-                    tcode[c] = (uint16_t)(fm | (fb << 3) | (fk << 6));
-                }
-                Lm_prev = Lm; Lb_prev = Lb; Lk_prev = Lk;
-                if (lane == 31 && s < last_strip) { edge_m[r] = Mp[C - 1]; edge_b[r] = Bp[C - 1]; edge_k[r] = Kp[C - 1]; }
-            }
-            // trace line of this step: one contiguous 64*C bytes per warp
-#pragma unroll
-            for (int c = 0; c < C; ++c) trace[(size_t)g * STRIP + lane * C + c] = tcode[c];
-            r += 1;
-            if (r > P) { r = 1; s += 1; }
-            if (n_strips > 1) __syncwarp();
-        }
-        __syncwarp();
-
-        // ---------------------------------- backtrack (all lanes walk the same path) ----------------------------------
-        int n = 0, status = 0;
-        {
-            int row = E, kmer = K - 1, st = 2;        // state codes: 0 K, 1 B, 2 M (column % 3 in the reference)
-            while (row > 0) {
-                const int sidx = kmer / STRIP, rel = kmer - sidx * STRIP;
-                const int step = sidx * P + (row - 1) + rel / C;
-                const uint32_t code = __ldcg(trace + (size_t)step * STRIP + rel);
-                const int mvt = (st == 2) ? (code & 7) : (st == 1) ? ((code >> 3) & 7) : ((code >> 6) & 7);
-                if (n >= cap) { status = 3; break; }
-                if (lane == 0) {
-                    nph_align_state a;
-                    a.event_idx = (uint32_t)(e_first + (long long)(row - 1) * stride);
-                    a.kmer_idx = (uint32_t)kmer;
-                    a.l_fm = 0.f;
-                    a.state = (st == 2) ? 'M' : (st == 1) ? 'B' : 'K';
-                    a.reserved[0] = (uint8_t)mvt; a.reserved[1] = 0; a.reserved[2] = 0;
-                    out[cap - 1 - n] = a;
-                }
-                ++n;
-                if (mvt == MV_SOFT) break;
-                int nst = 2;
-                switch (mvt) {
-                    case MV_SAME_M: nst = 2; break;
-                    case MV_PREV_M: kmer -= 1; nst = 2; break;
-                    case MV_SAME_B: nst = 1; break;
-                    case MV_PREV_B: kmer -= 1; nst = 1; break;
-                    case MV_PREV_K: kmer -= 1; nst = 0; break;
-                }
-                if (st != 0) row -= 1;               // a k-mer skip is silent
-                st = nst;
-                if (kmer < 0) { status = 2; break; } // block 0: the reference asserts
-            }
-        }
-        __syncwarp();
-
-        // ---------------------------------- replay forwards: l_fm of every state ----------------------------------
         float last_v = NEG;
-        if (!status && lane == 0) {
-            float v = NEG;
-            for (int i = 0; i < n; ++i) {
-                nph_align_state a = out[cap - n + i];
-                const int mvt = a.reserved[0];
-                const int row = (int)(((long long)a.event_idx - e_first) * stride) + 1;
-                float x5 = NEG;
-                if (mvt == MV_SOFT) {
-                    // legitimate only as the first state: MATCH of k-mer 0 at row 1 or with PRE_CLIP; anything else is a -inf cell
-                    if (i == 0 && a.state == 'M' && a.kmer_idx == 0 && (row == 1 || pre_clip)) x5 = __fadd_rn(0.0f, p.flank[row - 1]);
-                    else { status = 2; break; }
-                }
-                float t;
-                if (a.state == 'M') {
-                    const float tr_ = mvt == MV_SAME_M ? lp_mm_self : mvt == MV_PREV_M ? lp_mm_next : mvt == MV_SAME_B ? lp_bm_self
-                                      : mvt == MV_PREV_B ? lp_bm_next : lp_km;
-                    t = (mvt == MV_SOFT) ? x5 : __fadd_rn(tr_, v);
-                    const float4 g4 = my_params[a.kmer_idx];
-                    const float aa = div_by_cached_rcp(__fsub_rn(lv[a.event_idx], g4.x), g4.y, g4.w);
-                    t = __fadd_rn(t, __fadd_rn(g4.z, __fmul_rn(__fmul_rn(-0.5f, aa), aa)));
-                } else if (a.state == 'B') {
-                    t = __fadd_rn(mvt == MV_SAME_M ? lp_mb : lp_bb, v);
-                } else {
-                    t = __fadd_rn(mvt == MV_PREV_M ? lp_mk : mvt == MV_PREV_B ? lp_bk : lp_kk, v);
-                }
-                if (t == NEG) { status = 2; break; }  // the reference asserts vm != -inf on every visited cell
-                v = t;
-                a.l_fm = v;
-                a.reserved[0] = 0;
-                out[i] = a;                            // compaction to the front: i <= cap - n + i, read before write
-            }
-            last_v = v;
-        }
-        status = __shfl_sync(kFull, status, 0);
+        const int n = viterbi_align<C>(p.c, p.flank, j, sc, out, cap, &last_v, lane);
         if (lane == 0) {
-            p.n_states[job_idx] = status ? 0u : (uint32_t)n;
-            if (p.scores) p.scores[job_idx] = status ? NEG : last_v;
+            p.n_states[job_idx] = (uint32_t)n;
+            if (p.scores) p.scores[job_idx] = n ? last_v : NEG;
         }
         __syncwarp();
     }

@@ -148,6 +148,16 @@ int create_common(nph_ctx** out, int device, bool own_stream, cudaStream_t strea
 
 } // namespace
 
+int nph_upload_read_transitions(nph_ctx* ctx, double indel_bias)
+{
+    std::vector<float2>& trans = ctx->h_stage_trans;
+    trans.resize(ctx->n_reads);
+    for (size_t i = 0; i < ctx->n_reads; ++i) trans[i] = read_transitions(ctx->h_events_per_base[i], indel_bias);
+    NPH_TRY(nph_reserve(ctx, ctx->d_trans, ctx->n_reads));
+    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_trans.p, trans.data(), sizeof(float2) * ctx->n_reads, cudaMemcpyHostToDevice, ctx->stream));
+    return NPH_OK;
+}
+
 extern "C" {
 
 int nph_version(void) { return NPH_VERSION_MAJOR * 1000 + NPH_VERSION_MINOR; }

@@ -140,6 +140,8 @@ int nph_launch_hmm_forward(nph_ctx* ctx, float* scores_dev);
 size_t nph_hmm_scratch_bytes(const nph_ctx* ctx, int* warps_total_out);
 int nph_launch_abea(nph_ctx* ctx);
 int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uint32_t* max_E_out);
+// per-read (lp_mm_self, lp_mm_next) of the resident reads into ctx->d_trans (host libm, like calculate_transitions)
+int nph_upload_read_transitions(nph_ctx* ctx, double indel_bias);
 
 // ---- device-level pieces of the raw-read prologue (event_detect.cu, squiggle_prep.cu, abea.cu), chained by
 // load_from_raw.cu without leaving the device.  Inputs named d_* are device pointers; everything runs on ctx->stream.

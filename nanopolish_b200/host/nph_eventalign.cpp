@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 namespace nph {
 
@@ -194,11 +195,11 @@ size_t EventAligner::add_read(const EventAlignmentParameters& params)
     return m_reads.size() - 1;
 }
 
-// Start on segments[segment_idx] (the head of the reference's per-segment loop body, eventalign.cpp:654-689).
-bool EventAligner::enter_segment(ReadState& rs)
+// The head of the reference's per-segment loop body (eventalign.cpp:654-689): trims, then the events nearest to the
+// segment's first and last aligned k-mer.  Depends only on the record, never on earlier paths.
+bool EventAligner::setup_segment(ReadState& rs, size_t segment_idx, SegmentStart& out)
 {
-    if (rs.segment_idx >= rs.segments.size()) return false;
-    AlignedSegment& aligned_pairs = rs.segments[rs.segment_idx];
+    AlignedSegment& aligned_pairs = rs.segments[segment_idx];
     const EventAlignmentParameters& p = rs.params;
     if (p.region_start != -1 && p.region_end != -1) trim_aligned_pairs_to_ref_region(aligned_pairs, p.region_start, p.region_end);
     const int max_kmer_idx = (int)p.sr->read_sequence.size() - (int)rs.k;
@@ -213,11 +214,21 @@ bool EventAligner::enter_segment(ReadState& rs)
     const int n_map = (int)p.sr->base_to_event_map.size();
     if (read_kidx_start < 0 || read_kidx_end < 0 || read_kidx_start >= n_map || read_kidx_end >= n_map)
         throw Error(NPH_ERR_INVALID, "aligned read position outside the base-to-event map");      // the reference asserts / reads out of bounds
-    const int first_event = p.sr->get_closest_event_to(read_kidx_start, (uint32_t)p.strand_idx);
-    rs.last_event = p.sr->get_closest_event_to(read_kidx_end, (uint32_t)p.strand_idx);
-    rs.forward = first_event < rs.last_event;
-    rs.curr_start_event = first_event;
-    rs.curr_start_ref = aligned_pairs.front().ref_pos;
+    out.first_event = p.sr->get_closest_event_to(read_kidx_start, (uint32_t)p.strand_idx);
+    out.last_event = p.sr->get_closest_event_to(read_kidx_end, (uint32_t)p.strand_idx);
+    out.start_ref = aligned_pairs.front().ref_pos;
+    return true;
+}
+
+bool EventAligner::enter_segment(ReadState& rs)
+{
+    if (rs.segment_idx >= rs.segments.size()) return false;
+    SegmentStart st;
+    if (!setup_segment(rs, rs.segment_idx, st)) return false;
+    rs.last_event = st.last_event;
+    rs.forward = st.first_event < st.last_event;
+    rs.curr_start_event = st.first_event;
+    rs.curr_start_ref = st.start_ref;
     rs.curr_pair_idx = 0;
     rs.in_segment = true;
     return true;
@@ -242,7 +253,8 @@ bool EventAligner::prepare(ReadState& rs, AlignBatch& batch)
                 const int s = rs.curr_start_ref - p.ref_pos;
                 const int l = curr_end_ref - rs.curr_start_ref + 1;
                 const int n = (int)rs.ref_seq.length();
-                if (curr_end_read >= 0 && s >= 0 && l >= 0 && s + l <= n) {   // (outside: std::string::substr would throw in the reference)
+                const int n_map = (int)p.sr->base_to_event_map.size();
+                if (curr_end_read >= 0 && curr_end_read < n_map && s >= 0 && l >= 0 && s + l <= n) {   // (outside: substr throws / the map is read out of bounds in the reference)
                     rs.fwd_subseq = rs.ref_seq.substr(s, l);
                     rs.rc_subseq = rs.rc_ref_seq.substr(n - s - l, l);
                     // require a minimum amount of sequence to align to
@@ -296,8 +308,6 @@ void EventAligner::consume(const std::vector<std::vector<HMMAlignmentState>>& pa
         ReadState& rs = m_reads[m_round[j]];
         const std::vector<HMMAlignmentState>& event_alignment = paths[j];
         const AlignedSegment& aligned_pairs = rs.segments[rs.segment_idx];
-        const EventAlignmentParameters& p = rs.params;
-        HMMInputSequence hmm_sequence(rs.fwd_subseq, rs.rc_subseq, rs.pore_model->pmalphabet);
         rs.pending = false;
         rs.segments_aligned += 1;
 
@@ -309,18 +319,7 @@ void EventAligner::consume(const std::vector<std::vector<HMMAlignmentState>>& pa
         for (size_t idx = 0; idx < event_alignment.size() && (num_output < (size_t)OUTPUT_STRIDE || last_section); idx++) {
             const HMMAlignmentState& as = event_alignment[idx];
             if (as.state != 'K' && (int)as.event_idx != rs.curr_start_event) {
-                EventAlignment ea;
-                ea.ref_name = p.ref_name;
-                ea.ref_position = rs.curr_start_ref + (int)as.kmer_idx;
-                const size_t rp = (size_t)(ea.ref_position - p.ref_pos);
-                ea.ref_kmer = rp <= rs.ref_seq.size() ? rs.ref_seq.substr(rp, rs.k) : std::string();
-                ea.read_idx = (size_t)p.read_idx;
-                ea.strand_idx = (int)p.strand_idx;
-                ea.event_idx = (int)as.event_idx;
-                ea.rc = rs.job_rc != 0;
-                ea.hmm_state = as.state;
-                ea.model_kmer = ea.hmm_state != 'B' ? hmm_sequence.get_kmer(as.kmer_idx, rs.k, ea.rc) : std::string(rs.k, 'N');
-                rs.output.push_back(ea);
+                rs.output.push_back(Rec{rs.curr_start_ref + (int)as.kmer_idx, (int)as.event_idx, as.state});
                 last_event_output = (int)as.event_idx;
                 last_ref_kmer_output = rs.curr_start_ref + (int)as.kmer_idx;
                 num_output += 1;
@@ -338,13 +337,12 @@ void EventAligner::consume(const std::vector<std::vector<HMMAlignmentState>>& pa
     m_round.clear();
 }
 
-size_t EventAligner::run(Engine& engine, double indel_bias)
+size_t EventAligner::run_rounds(Engine& engine, double indel_bias)
 {
     size_t rounds = 0;
     m_batch.clear();
     while (next_round(m_batch)) {
-        // the read table is complete after the first round only if every read issued a job in it; AlignBatch uploads
-        // again whenever a read shows up that was not resident
+        // AlignBatch uploads the read table again whenever a read shows up that was not resident
         consume(m_batch.run(engine, indel_bias, rounds > 0));
         rounds += 1;
     }
@@ -352,9 +350,212 @@ size_t EventAligner::run(Engine& engine, double indel_bias)
     return rounds;
 }
 
+// ref_seq's k-mer at offset pos and what HMMInputSequence::get_kmer hands the model for it: the k-mer itself, or for rc
+// reads rc_subseq.substr(l - kmer_idx - k, k) == rc_ref_seq.substr(n - pos - k, k)
+void EventAligner::kmers_at(const ReadState& rs, const Rec& r, char* ref_kmer, char* model_kmer)
+{
+    const size_t k = rs.k, n = rs.ref_seq.size();
+    const size_t pos = (size_t)(r.ref_position - rs.params.ref_pos);
+    size_t len = pos <= n ? std::min(k, n - pos) : 0;          // std::string::substr clips at the end
+    std::memcpy(ref_kmer, rs.ref_seq.data() + (len ? pos : 0), len);
+    ref_kmer[len] = 0;
+    if (r.state == 'B') {
+        std::memset(model_kmer, 'N', k);
+    } else {
+        const bool rc = rs.params.strand_idx == 0 ? rs.do_base_rc : !rs.do_base_rc;
+        std::memcpy(model_kmer, rc ? rs.rc_ref_seq.data() + (n - pos - k) : rs.ref_seq.data() + pos, k);   // inside the window: always k long
+    }
+    model_kmer[k] = 0;
+}
+
+EventAlignment EventAligner::materialize(const ReadState& rs, const Rec& r) const
+{
+    char ref_kmer[64], model_kmer[64];
+    kmers_at(rs, r, ref_kmer, model_kmer);
+    EventAlignment ea;
+    ea.ref_name = rs.params.ref_name;
+    ea.ref_position = r.ref_position;
+    ea.ref_kmer = ref_kmer;
+    ea.read_idx = (size_t)rs.params.read_idx;
+    ea.strand_idx = (int)rs.params.strand_idx;
+    ea.event_idx = r.event_idx;
+    ea.rc = rs.params.strand_idx == 0 ? rs.do_base_rc : !rs.do_base_rc;
+    ea.model_kmer = model_kmer;
+    ea.hmm_state = r.state;
+    return ea;
+}
+
+std::vector<EventAlignment> EventAligner::alignment(size_t read_idx) const
+{
+    const ReadState& rs = m_reads[read_idx];
+    std::vector<EventAlignment> out;
+    out.reserve(rs.output.size());
+    for (const Rec& r : rs.output) out.push_back(materialize(rs, r));
+    return out;
+}
+
+size_t EventAligner::run(Engine& engine, double indel_bias)
+{
+    // ---- the chains: one per (read, BAM segment), up to the first segment that trims to nothing ----
+    struct ChainRef { size_t read; };
+    std::vector<nph_ea_chain> chains;
+    std::vector<ChainRef> owner;
+    std::vector<nph_aligned_pair> pairs;
+    std::vector<int32_t> map_start;
+    std::vector<uint32_t> ranks_fwd, ranks_rc;
+    std::vector<std::pair<const SquiggleRead*, uint8_t>> read_table;
+    std::map<std::pair<const SquiggleRead*, uint8_t>, std::pair<uint32_t, uint64_t>> read_slot;   // -> (read index, map_off)
+    uint64_t records_total = 0;
+    for (size_t i = 0; i < m_reads.size(); ++i) {
+        ReadState& rs = m_reads[i];
+        if (rs.done) continue;
+        const EventAlignmentParameters& p = rs.params;
+        if (rs.k >= 64) throw Error(NPH_ERR_UNSUPPORTED, "k-mer length");
+        const auto key = std::make_pair((const SquiggleRead*)p.sr, (uint8_t)p.strand_idx);
+        auto it = read_slot.find(key);
+        if (it == read_slot.end()) {
+            const uint64_t off = map_start.size();
+            for (const EventRangeForBase& e : p.sr->base_to_event_map) map_start.push_back(e.indices[p.strand_idx].start);
+            it = read_slot.insert({key, {(uint32_t)read_table.size(), off}}).first;
+            read_table.push_back(key);
+        }
+        const uint64_t rank_off = ranks_fwd.size();
+        const size_t n = rs.ref_seq.size();
+        const Alphabet* alphabet = rs.pore_model->pmalphabet;
+        for (size_t pos = 0; pos + rs.k <= n; ++pos) {
+            ranks_fwd.push_back(alphabet->kmer_rank(rs.ref_seq.c_str() + pos, rs.k));
+            ranks_rc.push_back(alphabet->kmer_rank(rs.rc_ref_seq.c_str() + (n - pos - rs.k), rs.k));
+        }
+        for (size_t sidx = 0; sidx < rs.segments.size(); ++sidx) {
+            SegmentStart st;
+            if (!setup_segment(rs, sidx, st)) break;
+            nph_ea_chain c;
+            std::memset(&c, 0, sizeof(c));
+            c.pair_off = pairs.size();
+            c.n_pairs = (uint32_t)rs.segments[sidx].size();
+            for (const AlignedPair& ap : rs.segments[sidx]) pairs.push_back(nph_aligned_pair{ap.ref_pos, ap.read_pos});
+            c.map_off = it->second.second;
+            c.map_len = (uint32_t)p.sr->base_to_event_map.size();
+            c.rank_off = rank_off;
+            c.ref_len = (uint32_t)n;
+            c.read = it->second.first;
+            c.model_id = engine.model_id(rs.pore_model);
+            c.read_seq_len = (uint32_t)p.sr->read_sequence.size();
+            c.ref_offset = p.ref_pos;
+            c.first_event = st.first_event;
+            c.last_event = st.last_event;
+            c.do_base_rc = rs.do_base_rc;
+            c.rc = p.strand_idx == 0 ? rs.do_base_rc : !rs.do_base_rc;
+            c.k = (uint8_t)rs.k;
+            c.out_cap = (uint32_t)std::abs(st.last_event - st.first_event) + 2;
+            c.out_off = records_total;
+            records_total += c.out_cap;
+            chains.push_back(c);
+            owner.push_back(ChainRef{i});
+        }
+    }
+    for (ReadState& rs : m_reads) rs.done = true;             // nothing left to do for the round driver unless re-armed below
+    if (chains.empty()) return 0;
+
+    std::vector<nph_read> reads;
+    std::vector<float> mean;
+    std::vector<double> time;
+    detail::flatten_reads(read_table, reads, mean, time);
+    engine.check(nph_reads_load(engine.ctx(), reads.data(), reads.size(), mean.data(), time.data(), mean.size()), "nph_reads_load");
+    std::vector<nph_ea_record> records(records_total);
+    std::vector<nph_ea_result> results(chains.size());
+    if (pairs.empty()) pairs.push_back(nph_aligned_pair{0, 0});
+    if (ranks_fwd.empty()) { ranks_fwd.push_back(0); ranks_rc.push_back(0); }
+    engine.check(nph_eventalign_chain(engine.ctx(), pairs.data(), pairs.size(), map_start.data(), map_start.size(), ranks_fwd.data(),
+                                      ranks_rc.data(), ranks_fwd.size(), chains.data(), chains.size(), indel_bias, records.data(),
+                                      records.size(), results.data()),
+                 "nph_eventalign_chain");
+
+    // ---- scatter; a read with a window the chain kernel could not hold goes through the round driver instead ----
+    std::vector<char> redo(m_reads.size(), 0);
+    for (size_t c = 0; c < chains.size(); ++c) {
+        const int st = results[c].status;
+        if (st & NPH_EA_RC_STRIDE) throw Error(NPH_ERR_INVALID, "rc and event_stride disagree");     // ref asserts (profile_hmm_r9.inl:275)
+        if (st & NPH_EA_BAD_EVENT) throw Error(NPH_ERR_INVALID, "event index outside the read");
+        if (st & NPH_EA_OUT_OVERFLOW) throw Error(NPH_ERR_STATE, "eventalign chain: record room exceeded");
+        if (st & NPH_EA_WINDOW_TOO_LARGE) redo[owner[c].read] = 1;
+    }
+    size_t n_redo = 0;
+    for (size_t c = 0; c < chains.size(); ++c) {
+        ReadState& rs = m_reads[owner[c].read];
+        if (redo[owner[c].read]) continue;
+        const nph_ea_record* r = records.data() + chains[c].out_off;
+        for (uint32_t i = 0; i < results[c].n_records; ++i) rs.output.push_back(Rec{r[i].ref_position, r[i].event_idx, (char)r[i].hmm_state});
+        rs.segments_aligned += results[c].n_windows;
+    }
+    for (size_t i = 0; i < m_reads.size(); ++i) {
+        if (!redo[i]) continue;
+        ReadState& rs = m_reads[i];
+        rs.done = false; rs.in_segment = false; rs.segment_idx = 0; rs.pending = false;
+        rs.output.clear(); rs.segments_aligned = 0;
+        ++n_redo;
+    }
+    return 1 + (n_redo ? run_rounds(engine, indel_bias) : 0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // writers
 // ---------------------------------------------------------------------------------------------
+// printf("%.<prec>lf", (double)v) for a float v, prec <= 5, without going through the C library's arbitrary-precision
+// path: v = m * 2^e exactly with m < 2^24, so v * 10^prec = (m * 10^prec) * 2^e fits 64-bit integer arithmetic with an
+// exact remainder, and round-half-to-even on it is the decimal string glibc prints (it rounds the exact value, in the
+// default rounding mode).  Magnitudes of 2^39 and above and non-finite values take snprintf.  Returns the length.
+size_t format_fixed(char* dst, float v, int prec)
+{
+    static const uint64_t pow10[6] = {1, 10, 100, 1000, 10000, 100000};
+    uint32_t bits;
+    std::memcpy(&bits, &v, 4);
+    const uint32_t expo = (bits >> 23) & 0xff;
+    if (expo == 0xff || expo >= 127 + 39 || prec < 0 || prec > 5) return (size_t)snprintf(dst, 64, "%.*lf", prec, (double)v);
+    uint64_t m = bits & 0x7fffff;
+    int e;                                   // v = m * 2^e
+    if (expo == 0) e = -149; else { m |= 0x800000; e = (int)expo - 150; }
+    uint64_t q;
+    const uint64_t N = m * pow10[prec];      // < 2^24 * 10^5 < 2^41
+    if (e >= 0) {
+        q = N << e;                          // e <= 15 here: < 2^56
+    } else {
+        const int sft = -e;
+        if (sft > 62) q = 0;                 // N < 2^41 is far below half an ulp of the last printed digit
+        else {
+            q = N >> sft;
+            const uint64_t rem = N & (((uint64_t)1 << sft) - 1), half = (uint64_t)1 << (sft - 1);
+            if (rem > half || (rem == half && (q & 1))) q += 1;
+        }
+    }
+    char tmp[32];
+    int n = 0;
+    uint64_t ip = q / pow10[prec], fp = q % pow10[prec];
+    do { tmp[n++] = (char)('0' + ip % 10); ip /= 10; } while (ip);
+    char* o = dst;
+    if (bits >> 31) *o++ = '-';
+    while (n) *o++ = tmp[--n];
+    if (prec) {
+        *o++ = '.';
+        for (int i = prec - 1; i >= 0; --i) { o[i] = (char)('0' + fp % 10); fp /= 10; }
+        o += prec;
+    }
+    *o = 0;
+    return (size_t)(o - dst);
+}
+
+static inline char* put_int(char* o, long long v)
+{
+    char tmp[24];
+    int n = 0;
+    unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) *o++ = '-';
+    while (n) *o++ = tmp[--n];
+    return o;
+}
+static inline char* put_str(char* o, const char* s, size_t n) { std::memcpy(o, s, n); return o + n; }
+
 std::string EventAligner::tsv_header(const EventalignOptions& opt)
 {
     std::string h = "contig\tposition\treference_kmer\t";
@@ -369,42 +570,67 @@ std::string EventAligner::tsv(size_t read_idx, const EventalignOptions& opt) con
     const SquiggleRead& sr = *rs.params.sr;
     const PoreModel* pore_model = rs.pore_model;
     const uint32_t k = pore_model->k;
+    const uint32_t strand = (uint32_t)rs.params.strand_idx;
+    const std::string& ref_name = rs.params.ref_name;
+    // the read column: read_idx as %zu, or the read name with -n
+    const std::string who_s = opt.print_read_names ? sr.read_name : std::to_string((size_t)rs.params.read_idx);
+    const double sqrt_var = std::sqrt(sr.scalings[strand].var);
     std::string out;
-    char buf[1024];
-    for (const EventAlignment& ea : rs.output) {
-        if (!opt.print_read_names)
-            snprintf(buf, sizeof(buf), "%s\t%d\t%s\t%zu\t%c\t", ea.ref_name.c_str(), ea.ref_position, ea.ref_kmer.c_str(), ea.read_idx, "tc"[ea.strand_idx]);
-        else
-            snprintf(buf, sizeof(buf), "%s\t%d\t%s\t%s\t%c\t", ea.ref_name.c_str(), ea.ref_position, ea.ref_kmer.c_str(), sr.read_name.c_str(), "tc"[ea.strand_idx]);
-        out += buf;
+    out.resize(rs.output.size() * (ref_name.size() + who_s.size() + 2 * (size_t)k + 340));    // six numbers of at most 47 characters
+    char* const base = &out[0];
+    char* o = base;
+    char ref_kmer[64], model_kmer[64];
+    for (const Rec& r : rs.output) {
+        kmers_at(rs, r, ref_kmer, model_kmer);
+        // contig, position, reference_kmer, read, strand
+        o = put_str(o, ref_name.data(), ref_name.size()); *o++ = '\t';
+        o = put_int(o, r.ref_position); *o++ = '\t';
+        o = put_str(o, ref_kmer, std::strlen(ref_kmer)); *o++ = '\t';
+        o = put_str(o, who_s.data(), who_s.size()); *o++ = '\t';
+        *o++ = "tc"[strand]; *o++ = '\t';
 
-        float event_mean = sr.get_unscaled_level(ea.event_idx, ea.strand_idx);
-        const float event_stdv = sr.get_stdv(ea.event_idx, ea.strand_idx);
-        const float event_duration = sr.get_duration(ea.event_idx, ea.strand_idx);
-        const uint32_t rank = pore_model->pmalphabet->kmer_rank(ea.model_kmer.c_str(), k);
+        float event_mean = sr.get_unscaled_level(r.event_idx, strand);
+        const float event_stdv = sr.get_stdv(r.event_idx, strand);
+        const float event_duration = sr.get_duration(r.event_idx, strand);
         float model_mean = 0.0, model_stdv = 0.0;
         if (opt.scale_events) {
             // scale reads to the model; unscaled model parameters
-            event_mean = sr.get_fully_scaled_level(ea.event_idx, ea.strand_idx);
-            if (ea.hmm_state != 'B') {
-                const PoreModelStateParams model = pore_model->get_parameters(rank);
+            event_mean = sr.get_fully_scaled_level(r.event_idx, strand);
+            if (r.state != 'B') {
+                const PoreModelStateParams model = pore_model->get_parameters(pore_model->pmalphabet->kmer_rank(model_kmer, k));
                 model_mean = (float)model.level_mean;
                 model_stdv = (float)model.level_stdv;
             }
-        } else if (ea.hmm_state != 'B') {
+        } else if (r.state != 'B') {
             // scale model to the reads
-            const GaussianParameters model = sr.get_scaled_gaussian_from_pore_model_state(*pore_model, ea.strand_idx, rank);
+            const GaussianParameters model = sr.get_scaled_gaussian_from_pore_model_state(*pore_model, strand, pore_model->pmalphabet->kmer_rank(model_kmer, k));
             model_mean = model.mean;
             model_stdv = model.stdv;
         }
         // float difference over a double product, narrowed to float (a 'B' state divides by zero: inf, like the reference)
-        const float standard_level = (float)((event_mean - model_mean) / (std::sqrt(sr.scalings[ea.strand_idx].var) * model_stdv));
-        snprintf(buf, sizeof(buf), "%d\t%.2lf\t%.3lf\t%.5lf\t", ea.event_idx, event_mean, event_stdv, event_duration);
-        out += buf;
-        snprintf(buf, sizeof(buf), "%s\t%.2lf\t%.2lf\t%.2lf", ea.model_kmer.c_str(), model_mean, model_stdv, standard_level);
-        out += buf;
-        out += "\n";
+        const float standard_level = (float)((event_mean - model_mean) / (sqrt_var * model_stdv));
+        // event_index %d, event_level_mean %.2lf, event_stdv %.3lf, event_length %.5lf
+        o = put_int(o, r.event_idx); *o++ = '\t';
+        o += format_fixed(o, event_mean, 2); *o++ = '\t';
+        o += format_fixed(o, event_stdv, 3); *o++ = '\t';
+        o += format_fixed(o, event_duration, 5); *o++ = '\t';
+        // model_kmer, model_mean %.2lf, model_stdv %.2lf, standardized_level %.2lf
+        o = put_str(o, model_kmer, k); *o++ = '\t';
+        o += format_fixed(o, model_mean, 2); *o++ = '\t';
+        o += format_fixed(o, model_stdv, 2); *o++ = '\t';
+        o += format_fixed(o, standard_level, 2);
+        *o++ = '\n';
     }
+    out.resize((size_t)(o - base));
+    return out;
+}
+
+std::vector<std::string> EventAligner::tsv_batch(const EventalignOptions& opt) const
+{
+    std::vector<std::string> out(m_reads.size());
+    // rows of different reads are independent; the reference formats them one read at a time inside an omp critical
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long long i = 0; i < (long long)m_reads.size(); ++i) out[i] = tsv((size_t)i, opt);
     return out;
 }
 
@@ -447,18 +673,19 @@ std::string cigar_ops_to_string(const std::vector<uint32_t>& ops)
 
 std::string EventAligner::event_cigar(size_t read_idx) const
 {
-    return cigar_ops_to_string(event_alignment_to_cigar(m_reads[read_idx].output));
+    return cigar_ops_to_string(event_alignment_to_cigar(alignment(read_idx)));
 }
 
 std::string EventAligner::sam(size_t read_idx) const
 {
     const ReadState& rs = m_reads[read_idx];
-    const std::vector<EventAlignment>& al = rs.output;
+    const std::vector<Rec>& al = rs.output;
     if (al.empty()) return std::string();
-    const std::string qname = rs.params.sr->read_name + (al.front().strand_idx == 0 ? ".template" : ".complement");
+    const bool rc = rs.params.strand_idx == 0 ? rs.do_base_rc : !rs.do_base_rc;
+    const std::string qname = rs.params.sr->read_name + (rs.params.strand_idx == 0 ? ".template" : ".complement");
     const int stride = al.front().event_idx < al.back().event_idx ? 1 : -1;
     // QNAME FLAG RNAME POS MAPQ CIGAR RNEXT PNEXT TLEN SEQ QUAL + the event-stride tag
-    return qname + "\t" + std::to_string(al.front().rc ? 16 : 0) + "\t" + rs.params.ref_name + "\t" + std::to_string(al.front().ref_position + 1) + "\t" +
+    return qname + "\t" + std::to_string(rc ? 16 : 0) + "\t" + rs.params.ref_name + "\t" + std::to_string(al.front().ref_position + 1) + "\t" +
            std::to_string((int)rs.params.mapq) + "\t" + event_cigar(read_idx) + "\t*\t0\t0\t*\t*\tES:i:" + std::to_string(stride) + "\n";
 }
 
@@ -468,19 +695,22 @@ EventalignSummary EventAligner::summarize(size_t read_idx) const
     const SquiggleRead& sr = *rs.params.sr;
     EventalignSummary summary;
     uint64_t prev_ref_pos = ~(uint64_t)0;                  // std::string::npos
+    const uint32_t strand = (uint32_t)rs.params.strand_idx;
+    char ref_kmer[64], model_kmer[64];
     for (size_t i = 0; i < rs.output.size(); ++i) {
-        const EventAlignment& ea = rs.output[i];
+        const Rec& ea = rs.output[i];
         summary.num_events += 1;
         const uint64_t ref_move = (uint64_t)(int64_t)ea.ref_position - prev_ref_pos;    // size_t arithmetic, as the reference
         if (ref_move == 0) summary.num_stays += 1;
         else if (i != 0 && ref_move > 1) summary.num_skips += 1;
         else if (i != 0 && ref_move == 1) summary.num_steps += 1;
-        summary.sum_duration += sr.get_duration(ea.event_idx, ea.strand_idx);
-        if (ea.hmm_state == 'M') {
-            const uint32_t rank = rs.pore_model->pmalphabet->kmer_rank(ea.model_kmer.c_str(), rs.k);
+        summary.sum_duration += sr.get_duration(ea.event_idx, strand);
+        if (ea.state == 'M') {
+            kmers_at(rs, ea, ref_kmer, model_kmer);
+            const uint32_t rank = rs.pore_model->pmalphabet->kmer_rank(model_kmer, rs.k);
             // z_score (src/hmm/nanopolish_emissions.h:32-41): float arithmetic
-            const float level = sr.get_drift_scaled_level(ea.event_idx, ea.strand_idx);
-            const GaussianParameters gp = sr.get_scaled_gaussian_from_pore_model_state(*rs.pore_model, ea.strand_idx, rank);
+            const float level = sr.get_drift_scaled_level(ea.event_idx, strand);
+            const GaussianParameters gp = sr.get_scaled_gaussian_from_pore_model_state(*rs.pore_model, strand, rank);
             const float z = (level - gp.mean) / gp.stdv;
             summary.sum_z_score += z;
         }

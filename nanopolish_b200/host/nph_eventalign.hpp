@@ -10,12 +10,14 @@
 //   event_alignment_to_cigar / emit_event_alignment_sam          ref: :256-325, :327-396
 //   summarize_alignment + the summary row                        ref: :486-537, :600-607
 //
-// The reference walks a read in ~100-base reference segments: each profile_hmm_align call starts at the event where
-// the previous segment's output stopped, so the segments of ONE read are sequential, while different reads are
-// independent (its OpenMP loop is over reads).  EventAligner keeps one cursor per read; a round collects the next
-// segment of every unfinished read into one AlignBatch (one launch of the Viterbi kernel, events resident in HBM since
-// the first round), then advances every cursor from its path.  The number of launches is the longest read's segment
-// count, not the number of segments.
+// The reference walks a read in ~100-base reference windows: each profile_hmm_align call starts at the event where
+// the previous window's output stopped, so the windows of ONE read are sequential, while different reads are
+// independent (its OpenMP loop is over reads).  EventAligner::run hands every (read, BAM segment) chain to the chain
+// kernel (nph_eventalign_chain: one warp walks one chain start to end on the device, ONE launch per batch of reads)
+// and gets back 12-byte records; the strings of an EventAlignment are only built when a writer or alignment() asks.
+// run_rounds() is the same computation driven from the host — one cursor per read, a round collects the next window
+// of every unfinished read into one AlignBatch (one Viterbi launch, events resident in HBM since the first round) —
+// kept for windows the chain kernel's scratch cannot hold and as the cross-check of the device cursor logic.
 //
 // BAM/FASTA access stays with the caller, which hands over what the reference pulls out of the record and the index:
 // position, flag, mapping quality, the packed CIGAR and the reference substring.
@@ -125,9 +127,12 @@ public:
     size_t add_read(const EventAlignmentParameters& params);
     size_t num_reads() const { return m_reads.size(); }
 
-    // Drive everything: rounds of (collect next segments -> one Viterbi launch -> advance cursors) until no read has a
-    // segment left.  Returns the number of rounds (= kernel batches).
+    // Align every queued read: one launch of the chain kernel; reads with a window too large for its scratch are
+    // re-run through run_rounds().  Returns the number of kernel batches issued (1 + fallback rounds).
     size_t run(Engine& engine, double indel_bias = hmm_indel_bias_factor);
+    // The host-driven form: rounds of (collect next windows -> one Viterbi launch -> advance cursors) until no read has a
+    // window left.  Returns the number of rounds (= the longest read's window count).
+    size_t run_rounds(Engine& engine, double indel_bias = hmm_indel_bias_factor);
 
     // The two halves of a round, for callers that want to interleave their own work (and for the host-logic tests):
     // next_round() fills `batch` with one job per unfinished read (false = all reads are done); consume() takes the
@@ -136,11 +141,13 @@ public:
     void consume(const std::vector<std::vector<HMMAlignmentState>>& paths);
     const std::vector<size_t>& round_reads() const { return m_round; }     // read index of each job of the open round
 
-    const std::vector<EventAlignment>& alignment(size_t read_idx) const { return m_reads[read_idx].output; }
-    size_t num_segments(size_t read_idx) const { return m_reads[read_idx].segments_aligned; }
+    std::vector<EventAlignment> alignment(size_t read_idx) const;          // materialised from the compact records
+    size_t num_alignments(size_t read_idx) const { return m_reads[read_idx].output.size(); }
+    size_t num_segments(size_t read_idx) const { return m_reads[read_idx].segments_aligned; }   // profile_hmm_align calls made
 
     static std::string tsv_header(const EventalignOptions& opt = EventalignOptions());
     std::string tsv(size_t read_idx, const EventalignOptions& opt = EventalignOptions()) const;
+    std::vector<std::string> tsv_batch(const EventalignOptions& opt = EventalignOptions()) const;   // all reads, formatted in parallel
     // one SAM text line (the reference writes the same record through htslib), "" for an empty alignment
     std::string sam(size_t read_idx) const;
     std::string event_cigar(size_t read_idx) const;
@@ -150,6 +157,8 @@ public:
     void clear();
 
 private:
+    struct Rec { int ref_position; int event_idx; char state; };    // an EventAlignment without its strings
+    struct SegmentStart { int first_event, last_event, start_ref; };
     struct ReadState {
         EventAlignmentParameters params;
         const PoreModel* pore_model = nullptr;
@@ -169,17 +178,22 @@ private:
         uint8_t job_rc = 0;
         std::string fwd_subseq, rc_subseq;
         // results
-        std::vector<EventAlignment> output;
+        std::vector<Rec> output;
         size_t segments_aligned = 0;
     };
     bool prepare(ReadState& rs, AlignBatch& batch);      // true if a job was queued
     bool enter_segment(ReadState& rs);                    // false = the whole read is finished
+    bool setup_segment(ReadState& rs, size_t segment_idx, SegmentStart& out);   // trims + start/stop events; false = no pairs left
+    EventAlignment materialize(const ReadState& rs, const Rec& r) const;
+    static void kmers_at(const ReadState& rs, const Rec& r, char* ref_kmer, char* model_kmer);   // NUL-terminated, k+1 bytes each
     std::vector<ReadState> m_reads;
     std::vector<size_t> m_round;                          // reads with a pending job, in job order
     AlignBatch m_batch;
 };
 
 std::vector<uint32_t> event_alignment_to_cigar(const std::vector<EventAlignment>& alignments);
+// == snprintf(dst, ..., "%.<prec>lf", (double)v) for a float v and prec <= 5, byte for byte; returns the length
+size_t format_fixed(char* dst, float v, int prec);
 std::string cigar_ops_to_string(const std::vector<uint32_t>& ops);
 
 } // namespace nph

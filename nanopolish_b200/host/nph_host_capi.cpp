@@ -5,6 +5,7 @@
 #include "nph_methylation.hpp"
 #include "nph_raw.hpp"
 #include "nph_eventalign.hpp"
+#include <cmath>
 #include <cstring>
 #include <memory>
 
@@ -340,11 +341,19 @@ int nphh_ea_add_read(int read, const char* ref_name, int ref_pos, int flag, int 
     return rc ? rc : idx;
 }
 
-// everything on the GPU: returns the number of rounds (Viterbi launches)
+// everything on the GPU, chains walked by the chain kernel: returns the number of kernel batches (1 + fallback rounds)
 long long nphh_ea_run(double indel_bias)
 {
     long long rounds = -1;
     int rc = guard([&] { rounds = (long long)g_aligner.run(Engine::thread_default(), indel_bias); });
+    return rc ? rc : rounds;
+}
+
+// the host-driven form (one Viterbi launch per round): returns the number of rounds
+long long nphh_ea_run_rounds(double indel_bias)
+{
+    long long rounds = -1;
+    int rc = guard([&] { rounds = (long long)g_aligner.run_rounds(Engine::thread_default(), indel_bias); });
     return rc ? rc : rounds;
 }
 
@@ -401,6 +410,54 @@ long long nphh_ea_text(int idx, int what, char* out, size_t cap)
         n = (long long)s.size();
     });
     return rc ? rc : n;
+}
+
+// every read's TSV rows concatenated in read order, formatted in parallel (EventAligner::tsv_batch)
+long long nphh_ea_tsv_all(char* out, size_t cap)
+{
+    long long n = -1;
+    int rc = guard([&] {
+        const std::vector<std::string> parts = g_aligner.tsv_batch();
+        size_t total = 0;
+        for (const std::string& s : parts) total += s.size();
+        if (total + 1 > cap) throw Error(NPH_ERR_INVALID, "text buffer too small");
+        char* o = out;
+        for (const std::string& s : parts) { std::memcpy(o, s.data(), s.size()); o += s.size(); }
+        *o = 0;
+        n = (long long)total;
+    });
+    return rc ? rc : n;
+}
+
+// format_fixed against the C library on n float bit patterns drawn from `seed` (uniform bit patterns, then values
+// near printed-digit ties): returns the number of mismatches
+long long nphh_format_fixed_check(uint64_t seed, size_t n)
+{
+    long long bad = 0;
+    uint64_t x = seed * 2862933555777941757ull + 3037000493ull;
+    char a[128], b[128];
+    for (size_t i = 0; i < n; ++i) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        float v;
+        uint32_t bits = (uint32_t)(x >> 16);
+        if (i % 3 == 1) {                       // magnitudes eventalign prints: 1e-4 .. 1e3, often an exact multiple of a small power of two
+            const int q = (int)((x >> 8) & 0xffff) - 32768;
+            v = (float)q / (float)(1 << ((x >> 48) & 15));
+            if ((x >> 60) & 1) v = std::nextafterf(v, 1e9f);
+        } else if (i % 3 == 2) {                // decimal ties and their float neighbours
+            const int q = (int)((x >> 8) & 0xfffff);
+            v = (float)((q + 0.5) / 1000.0);
+            if ((x >> 62) & 1) v = -v;
+        } else {
+            std::memcpy(&v, &bits, 4);
+        }
+        for (int prec = 0; prec <= 5; ++prec) {
+            format_fixed(a, v, prec);
+            snprintf(b, sizeof(b), "%.*lf", prec, (double)v);
+            if (std::strcmp(a, b) != 0) { if (bad < 5) g_err = std::string("format_fixed: ") + a + " vs " + b; ++bad; }
+        }
+    }
+    return bad;
 }
 
 long long nphh_ea_num_segments(int idx) { return (long long)g_aligner.num_segments(idx); }

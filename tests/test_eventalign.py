@@ -128,6 +128,10 @@ def _check_outputs(host, cases, restated, golden):
         if _single_segment(c):
             assert _text(host, i, 4) == golden[f"cigar_{i}"]
             assert _text(host, i, 3) == EP.sam(r, al, c["mapq"])
+    host.nphh_ea_tsv_all.restype = C.c_longlong
+    buf = C.create_string_buffer(1 << 22)
+    assert host.nphh_ea_tsv_all(buf, C.c_size_t(1 << 22)) >= 0, host.nphh_last_error()
+    assert buf.value.decode() == "".join(golden[f"tsv_{c['read_idx']}"] for c in cs)           # tsv_batch: all reads, in parallel
     assert _text(host, 0, 6) == ("contig\tposition\treference_kmer\tread_index\tstrand\tevent_index\tevent_level_mean\tevent_stdv\t"
                                  "event_length\tmodel_kmer\tmodel_mean\tmodel_stdv\tstandardized_level\n")
 
@@ -159,6 +163,13 @@ def test_host_chaining_logic_on_cpu(host, cases, restated, golden, port_oracle):
     host.nphh_ea_begin()
 
 
+def test_format_fixed_matches_printf(host):
+    """The TSV writer's %.2lf / %.3lf / %.5lf replacement (exact integer arithmetic on the float) against snprintf on
+    6 x 600k values: uniform bit patterns, dyadic fractions, decimal ties and their neighbours, inf/nan, +-0."""
+    host.nphh_format_fixed_check.restype = C.c_longlong
+    assert host.nphh_format_fixed_check(C.c_uint64(20240923), C.c_size_t(600_000)) == 0, host.nphh_last_error()
+
+
 def test_get_aligned_segments(host):
     ops = [(5, "S"), (10, "M"), (2, "I"), (3, "D"), (4, "="), (7, "N"), (6, "X"), (3, "H")]
     cigar = EP.pack_cigar(ops)
@@ -177,10 +188,83 @@ def test_get_aligned_segments(host):
 
 @pytest.mark.gpu
 def test_eventalign_on_device(host, cases, restated, golden):
-    """The whole thing: every round's segments through hmm_viterbi_kernel, text identical to the reference's."""
+    """The whole thing on the device: every (read, BAM segment) chain walked start to end by one warp of
+    eventalign_chain_kernel in ONE launch; text identical to the reference's."""
     _setup(host, cases)
-    rounds = host.nphh_ea_run(C.c_double(1.0))
+    batches = host.nphh_ea_run(C.c_double(1.0))
+    assert batches == 1, host.nphh_last_error()            # no window needed the host-driven fallback
+    _check_outputs(host, cases, restated, golden)
+    host.nphh_ea_begin()
+
+
+@pytest.mark.gpu
+def test_eventalign_host_rounds_on_device(host, cases, restated, golden):
+    """The host-driven form: one hmm_viterbi_kernel launch per round over the next window of every unfinished read."""
+    _setup(host, cases)
+    rounds = host.nphh_ea_run_rounds(C.c_double(1.0))
     assert rounds >= 0, host.nphh_last_error()
     assert rounds == max(s for _, s in restated)
     _check_outputs(host, cases, restated, golden)
     host.nphh_ea_begin()
+
+
+@pytest.mark.gpu
+def test_eventalign_chain_falls_back_for_large_windows(host, cases, restated, golden):
+    """A window with more events than the chain kernel's scratch holds flags its read; EventAligner re-runs those reads
+    through the round driver and the output does not change."""
+    _setup(host, cases)
+    os.environ["NPH_EA_EVENT_CAP"] = "150"                  # most windows span ~170 events
+    try:
+        batches = host.nphh_ea_run(C.c_double(1.0))
+    finally:
+        del os.environ["NPH_EA_EVENT_CAP"]
+    assert batches > 1, host.nphh_last_error()
+    _check_outputs(host, cases, restated, golden)
+    host.nphh_ea_begin()
+
+
+@pytest.mark.gpu
+def test_eventalign_chain_abi(engine, cases, restated):
+    """nph_eventalign_chain called directly (what EventAligner::run does underneath): records per chain."""
+    model, rs, cs = cases
+    mid = engine.model_upload(model)
+    engine.reads_load(rs.reads, rs.ev_mean, rs.ev_start_time)
+    chains = np.zeros(0, synth.EA_CHAIN_DT)
+    pairs, maps, rf, rr, want = [], [], [], [], []
+    map_off = {}
+    out_off = 0
+    rows = []
+    for c, (al, segs) in zip(cs, restated):
+        if c["flag"] & EP.BAM_FUNMAP or c["region"] != (-1, -1) or not _single_segment(c):
+            continue
+        r, slot = c["read"], EC.read_slot(c, rs.n_reads)
+        if slot not in map_off:
+            map_off[slot] = sum(m.shape[0] for m in maps)
+            maps.append(np.ascontiguousarray(r.b2e_start, np.int32))
+        ref = EP.disambiguate(c["fetched"])
+        codes = synth.encode(ref, "nucleotide")
+        seg = EP.get_aligned_segments(c["ref_pos"], c["cigar"])[0]
+        seg = [p for p in seg if p[1] <= len(r.read_sequence) - EC.K]
+        rev = bool(c["flag"] & EP.BAM_FREVERSE)
+        k0, k1 = seg[0][1], seg[-1][1]
+        if rev:
+            k0, k1 = r.flip_k_strand(k0), r.flip_k_strand(k1)
+        first, last = r.get_closest_event_to(k0), r.get_closest_event_to(k1)
+        rows.append((sum(len(p) for p in pairs), map_off[slot], sum(x.shape[0] for x in rf), out_off, slot, mid, len(seg), r.b2e_start.shape[0],
+                     len(ref), len(r.read_sequence), abs(last - first) + 2, c["ref_pos"], first, last, int(rev), int(rev), EC.K, 0))
+        out_off += abs(last - first) + 2
+        pairs.append(seg)
+        rf.append(synth.kmer_ranks_from_codes(codes, EC.K, 4).astype(np.uint32))
+        rr.append(synth.dna_rc_kmer_ranks(codes, EC.K).astype(np.uint32))
+        want.append((al, segs))
+    chains = np.array(rows, synth.EA_CHAIN_DT)
+    flat_pairs = np.array([p for seg in pairs for p in seg], np.int32).reshape(-1, 2)
+    records, results = engine.eventalign_chain(flat_pairs, np.concatenate(maps), np.concatenate(rf), np.concatenate(rr), chains)
+    assert len(want) >= 3 and (results["status"] == 0).all()
+    for i, (al, segs) in enumerate(want):
+        o, n = int(chains[i]["out_off"]), int(results[i]["n_records"])
+        got = [(int(x["ref_position"]), int(x["event_idx"]), x["hmm_state"].decode()) for x in records[o:o + n]]
+        assert got == [(a.ref_position, a.event_idx, a.hmm_state) for a in al]
+        assert int(results[i]["n_windows"]) == segs
+    ms, launches = engine.last_kernel_ms()
+    assert ms > 0 and launches == 1
