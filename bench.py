@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="scorereads", choices=["scorereads", "methylation", "abea", "events", "prologue"])
+    ap.add_argument("--workload", default="scorereads", choices=["scorereads", "methylation", "abea", "events", "prologue", "eventalign"])
     ap.add_argument("--reads", type=int, default=10000, help="reads per GPU")
     ap.add_argument("--events", type=int, default=4000, help="events per read")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -234,7 +234,8 @@ def run_aux(args, rank, world, local, saved_stdout):
     """Auxiliary single-GPU measurements of the other kernels of the path (not the headline metric):
     --workload abea   : adaptive banded event alignment, reads x 8000 events (BASELINE configs[3] shape), events/s
     --workload events : scrappie event detection, reads x 36000 raw samples, samples/s
-    --workload prologue : SquiggleRead::load_from_raw in one call (trim, events, MoM, ABEA, calibration), samples/s"""
+    --workload prologue : SquiggleRead::load_from_raw in one call (trim, events, MoM, ABEA, calibration), samples/s
+    --workload eventalign : eventalign's segment chains (align_read_to_ref) walked on the device, reads x 4000 events, events/s"""
     if rank != 0:
         return
     import torch
@@ -270,6 +271,64 @@ def run_aux(args, rank, world, local, saved_stdout):
                 "roofline": {"bound": "hbm", "achieved": b_alg / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": b_alg / (t * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel": "abea_kernel",
                              "note": "sequentially dependent bands: issue/latency bound (DESIGN.md section 5)"}}
+    elif args.workload == "eventalign":
+        n_reads = min(args.reads, 4736)
+        rs = synth.gen_reads(n_reads, args.events, nuc, seed=42)
+        pairs, maps, rf, rr, chains = synth.eventalign_chains(rs, mid)
+        ev = int(rs.reads["n_events"].sum())
+        ms, e2e = [], []
+        for it in range(max(3, args.warmup) + args.steps):
+            t0 = time.perf_counter()
+            eng.reads_load(rs.reads, rs.ev_mean, rs.ev_start_time)
+            records, results = eng.eventalign_chain(pairs, maps, rf, rr, chains)
+            dt = time.perf_counter() - t0
+            if it >= max(3, args.warmup):
+                ms.append(eng.last_kernel_ms()[0]); e2e.append(dt)
+        t = float(np.mean(ms))
+        assert (results["status"] == 0).all()
+        n_rec, n_win = int(results["n_records"].sum()), int(results["n_windows"].sum())
+        # algorithmic bytes: event levels once (4 B), pairs (8 B) + map (4 B) + two rank tables (8 B) per k-mer, 12 B per record out
+        nk_total = int(chains["n_pairs"].sum())
+        b_alg = 4 * ev + 20 * nk_total + 12 * n_rec
+        cpu = None
+        if not args.no_cpu_baseline:
+            from concurrent.futures import ThreadPoolExecutor
+            from oracle.oracle_py import RefOracle
+            if RefOracle.available():
+                ro = RefOracle()
+                cores = os.cpu_count() or 1
+                ns = min(n_reads, max(cores, 32) * 2)
+                rh = ro.register_reads(rs.reads[:ns], rs.ev_mean, rs.ev_start_time, ro.builtin_model("nucleotide"))
+                seqs = [synth._CODE2DNA[c].tobytes().decode() for c in rs.seq_codes[:ns]]
+                one = np.ones(args.events + 8, np.float32)
+                for i in range(ns):
+                    o, nk = int(chains[i]["map_off"]), int(chains[i]["map_len"])
+                    ro.read_set_eventalign(rh[i], f"read_{i}", seqs[i], maps[o:o + nk], maps[o:o + nk], one, one)
+                cig = lambda i: np.array([(len(seqs[i]) << 4) | 0], np.uint32)
+                t0 = time.perf_counter()
+                with ThreadPoolExecutor(cores) as ex:       # the compiled reference releases the GIL inside each call
+                    rows = list(ex.map(lambda i: ro.eventalign(rh[i], "contig", seqs[i], 0, 0, cig(i), i, want_cigar=False)[2].shape[0], range(ns)))
+                cs = time.perf_counter() - t0
+                assert rows == [int(v) for v in results["n_records"][:ns]]
+                cpu = {"value": int(rs.reads["n_events"][:ns].sum()) / cs, "unit": "events/s", "cores": cores, "kind": "reference",
+                       "sample": f"{ns} of the {n_reads} reads through the compiled reference's align_read_to_ref + TSV writer, one read per thread"}
+        line = {"metric": "eventalign_events_per_sec", "value": ev / (t * 1e-3), "unit": "events/s", "n_gpus": 1, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"eventalign: {n_reads} synthetic R9.4 reads x {args.events} events aligned to their own reference "
+                                       f"(CIGAR all M), k=6 nucleotide model, 100-base windows, {n_win} Viterbi windows, {n_rec} event alignments",
+                           "reads_per_sec_device": n_reads / (t * 1e-3), "reads_per_sec_e2e": n_reads / float(np.mean(e2e))},
+                "e2e": {"value": ev / float(np.mean(e2e)), "unit": "events/s",
+                        "h2d_bytes_per_step": int(rs.ev_mean.nbytes + pairs.nbytes + maps.nbytes + rf.nbytes + rr.nbytes + chains.nbytes),
+                        "d2h_bytes_per_step": int(records.nbytes + results.nbytes), "steps": args.steps,
+                        "api": "nph_reads_load + nph_eventalign_chain (host buffers in, records out)"},
+                "gpu_launches": args.steps,
+                "roofline": {"bound": "hbm", "achieved": b_alg / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": b_alg / (t * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel": "eventalign_chain_kernel<3>",
+                             "note": "one warp walks one read's sequentially dependent windows: issue/latency bound like K3; "
+                                     "algorithmic bytes = 4 B/event + 20 B/k-mer in, 12 B/record out"}}
+        if cpu:
+            line["cpu_baseline"] = cpu
     elif args.workload == "prologue":
         n_reads = min(args.reads, 2048)
         base = min(n_reads, 256)
@@ -380,7 +439,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.workload in ("abea", "events", "prologue"):
+    if args.workload in ("abea", "events", "prologue", "eventalign"):
         run_aux(args, rank, world, local, saved_stdout)
         return
     if args.impl == "reference":

@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(kThreads, 1) eventalign_chain_kernel(const Cha
     constexpr int STRIP = 32 * C;
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    __shared__ uint16_t s_tile[kWarps][32 * 32];
     VitScratch sc;
+    sc.tile = s_tile[threadIdx.x >> 5];
     sc.params = p.scratch_params + (size_t)warp_global * STRIP;
     sc.edge_m = nullptr; sc.edge_b = nullptr; sc.edge_k = nullptr;       // single strip: never touched
     sc.trace = p.scratch_trace + (size_t)warp_global * p.trace_stride;

@@ -60,7 +60,9 @@ __global__ void __launch_bounds__(kThreads, 1) hmm_viterbi_kernel(const VitParam
     constexpr int STRIP = 32 * C;
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    __shared__ uint16_t s_tile[kWarps][32 * 32];
     VitScratch sc;
+    sc.tile = s_tile[threadIdx.x >> 5];
     sc.params = p.scratch_params + (size_t)warp_global * p.kpad_stride;
     sc.edge_m = p.scratch_edge + (size_t)warp_global * 3 * p.edge_stride;
     sc.edge_b = sc.edge_m + p.edge_stride;

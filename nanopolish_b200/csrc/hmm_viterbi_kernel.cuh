@@ -26,11 +26,12 @@ struct VitJob {
     bool pre_clip;
 };
 // per-warp scratch: Gaussians (kpad float4), strip-edge columns (3 x edge_stride floats; untouched for one strip),
-// movement codes ((steps + 1) * 32 * C uint16)
+// movement codes ((steps + 1) * 32 * C uint16) in global memory; a 2 KB tile in shared memory
 struct VitScratch {
     float4* params;
     float* edge_m; float* edge_b; float* edge_k;
     uint16_t* trace;
+    uint16_t* tile;           // shared memory, 32 x 32 movement codes: the backtrack's staging corner
 };
 
 // running max with the reference's tie rule: a later candidate that equals the max takes the label
@@ -176,10 +177,28 @@ __device__ __forceinline__ int viterbi_align(const HmmConsts& c, const float* __
     int n = 0, status = 0;
     {
         int row = E, kmer = K - 1, st = 2;        // state codes: 0 K, 1 B, 2 M (column % 3 in the reference)
+        // The path moves at most one row up and one k-mer left per state, so the next 32 states lie inside the 32 x 32
+        // corner of the trace that ends at (row, kmer): the warp stages that corner in shared memory with 32
+        // independent loads per lane (lane = k-mer column, 64 contiguous bytes per row) instead of paying one dependent
+        // L2 round trip per state.
+        int row0 = 0, kmer0 = -1;                 // corner currently staged: rows (row0-32, row0], k-mers (kmer0-32, kmer0]
         while (row > 0) {
-            const int sidx = kmer / STRIP, rel = kmer - sidx * STRIP;
-            const int step = sidx * P + (row - 1) + rel / C;
-            const uint32_t code = __ldcg(trace + (size_t)step * STRIP + rel);
+            if (kmer0 < 0 || row <= row0 - 32 || kmer <= kmer0 - 32) {
+                __syncwarp();
+                row0 = row; kmer0 = kmer;
+                const int km = kmer0 - lane;
+                if (km >= 0) {
+                    const int sidx = km / STRIP, rel = km - sidx * STRIP;
+                    const uint16_t* src = trace + ((size_t)sidx * P + rel / C) * STRIP + rel;
+#pragma unroll 8
+                    for (int i = 0; i < 32; ++i) {
+                        const int rw = row0 - i;
+                        if (rw >= 1) sc.tile[i * 32 + lane] = __ldcg(src + (size_t)(rw - 1) * STRIP);
+                    }
+                }
+                __syncwarp();
+            }
+            const uint32_t code = sc.tile[(row0 - row) * 32 + (kmer0 - kmer)];
             const int mvt = (st == 2) ? (code & 7) : (st == 1) ? ((code >> 3) & 7) : ((code >> 6) & 7);
             if (n >= cap) { status = 3; break; }
             if (lane == 0) {

@@ -394,52 +394,128 @@ std::vector<EventAlignment> EventAligner::alignment(size_t read_idx) const
     return out;
 }
 
+// ranks of every k-mer of seq by one rolling pass: rank(pos + 1) = (rank(pos) mod A^(k-1)) * A + rank(seq[pos + k])
+void rolling_kmer_ranks(const Alphabet* alphabet, const std::string& seq, uint32_t k, uint32_t* out)
+{
+    const size_t n = seq.size();
+    if (n < k) return;
+    uint64_t top = 1;
+    for (uint32_t i = 1; i < k; ++i) top *= alphabet->size();
+    uint64_t r = 0;
+    for (uint32_t i = 0; i < k; ++i) r = r * alphabet->size() + alphabet->rank(seq[i]);
+    out[0] = (uint32_t)r;
+    for (size_t pos = 1; pos + k <= n; ++pos) {
+        r = (r % top) * alphabet->size() + alphabet->rank(seq[pos + k - 1]);
+        out[pos] = (uint32_t)r;
+    }
+}
+
 size_t EventAligner::run(Engine& engine, double indel_bias)
 {
-    // ---- the chains: one per (read, BAM segment), up to the first segment that trims to nothing ----
-    struct ChainRef { size_t read; };
-    std::vector<nph_ea_chain> chains;
-    std::vector<ChainRef> owner;
-    std::vector<nph_aligned_pair> pairs;
-    std::vector<int32_t> map_start;
-    std::vector<uint32_t> ranks_fwd, ranks_rc;
-    std::vector<std::pair<const SquiggleRead*, uint8_t>> read_table;
-    std::map<std::pair<const SquiggleRead*, uint8_t>, std::pair<uint32_t, uint64_t>> read_slot;   // -> (read index, map_off)
-    uint64_t records_total = 0;
-    for (size_t i = 0; i < m_reads.size(); ++i) {
+    const size_t nr = m_reads.size();
+    // ---- phase 1 (parallel over reads): trims and start/stop events of every BAM segment, up to the first segment
+    //      that trims to nothing (where the reference returns from align_read_to_ref) ----
+    std::vector<std::vector<SegmentStart>> starts(nr);
+    std::vector<std::string> errors(nr);
+#pragma omp parallel for schedule(dynamic, 8)
+    for (long long i = 0; i < (long long)nr; ++i) {
         ReadState& rs = m_reads[i];
         if (rs.done) continue;
+        try {
+            if (rs.k >= 64) throw Error(NPH_ERR_UNSUPPORTED, "k-mer length");
+            for (size_t sidx = 0; sidx < rs.segments.size(); ++sidx) {
+                SegmentStart st;
+                if (!setup_segment(rs, sidx, st)) break;
+                starts[i].push_back(st);
+            }
+        } catch (const std::exception& e) { errors[i] = e.what(); }
+    }
+    for (size_t i = 0; i < nr; ++i) if (!errors[i].empty()) throw Error(NPH_ERR_INVALID, errors[i]);
+
+    // ---- phase 2 (serial, O(reads)): read table, offsets ----
+    struct Slot { uint32_t read_index; uint64_t map_off; };
+    std::vector<std::pair<const SquiggleRead*, uint8_t>> read_table;
+    std::map<std::pair<const SquiggleRead*, uint8_t>, Slot> read_slot;
+    std::vector<Slot> slot_of(nr);
+    std::vector<char> fills_map(nr, 0);
+    std::vector<uint64_t> rank_off(nr, 0), chain_first(nr + 1, 0);
+    std::vector<uint32_t> model_of(nr, 0);
+    uint64_t n_map = 0, n_ranks = 0, n_pairs = 0, records_total = 0;
+    for (size_t i = 0; i < nr; ++i) {
+        chain_first[i + 1] = chain_first[i] + starts[i].size();
+        if (starts[i].empty()) continue;
+        const ReadState& rs = m_reads[i];
         const EventAlignmentParameters& p = rs.params;
-        if (rs.k >= 64) throw Error(NPH_ERR_UNSUPPORTED, "k-mer length");
         const auto key = std::make_pair((const SquiggleRead*)p.sr, (uint8_t)p.strand_idx);
         auto it = read_slot.find(key);
         if (it == read_slot.end()) {
-            const uint64_t off = map_start.size();
-            for (const EventRangeForBase& e : p.sr->base_to_event_map) map_start.push_back(e.indices[p.strand_idx].start);
-            it = read_slot.insert({key, {(uint32_t)read_table.size(), off}}).first;
+            it = read_slot.insert({key, Slot{(uint32_t)read_table.size(), n_map}}).first;
             read_table.push_back(key);
+            n_map += p.sr->base_to_event_map.size();
+            fills_map[i] = 1;
         }
-        const uint64_t rank_off = ranks_fwd.size();
-        const size_t n = rs.ref_seq.size();
-        const Alphabet* alphabet = rs.pore_model->pmalphabet;
-        for (size_t pos = 0; pos + rs.k <= n; ++pos) {
-            ranks_fwd.push_back(alphabet->kmer_rank(rs.ref_seq.c_str() + pos, rs.k));
-            ranks_rc.push_back(alphabet->kmer_rank(rs.rc_ref_seq.c_str() + (n - pos - rs.k), rs.k));
-        }
-        for (size_t sidx = 0; sidx < rs.segments.size(); ++sidx) {
-            SegmentStart st;
-            if (!setup_segment(rs, sidx, st)) break;
-            nph_ea_chain c;
+        slot_of[i] = it->second;
+        rank_off[i] = n_ranks;
+        n_ranks += rs.ref_seq.size() >= rs.k ? rs.ref_seq.size() - rs.k + 1 : 0;
+        model_of[i] = engine.model_id(rs.pore_model);
+    }
+    const size_t n_chains = (size_t)chain_first[nr];
+    for (ReadState& rs : m_reads) rs.done = true;             // nothing left for the round driver unless re-armed below
+    if (n_chains == 0) return 0;
+    std::vector<nph_ea_chain> chains(n_chains);
+    std::vector<size_t> owner(n_chains);
+    for (size_t i = 0; i < nr; ++i) {
+        const ReadState& rs = m_reads[i];
+        for (size_t sidx = 0; sidx < starts[i].size(); ++sidx) {
+            const SegmentStart& st = starts[i][sidx];
+            nph_ea_chain& c = chains[chain_first[i] + sidx];
             std::memset(&c, 0, sizeof(c));
-            c.pair_off = pairs.size();
+            c.pair_off = n_pairs;
             c.n_pairs = (uint32_t)rs.segments[sidx].size();
-            for (const AlignedPair& ap : rs.segments[sidx]) pairs.push_back(nph_aligned_pair{ap.ref_pos, ap.read_pos});
-            c.map_off = it->second.second;
+            n_pairs += c.n_pairs;
+            c.out_cap = (uint32_t)std::abs(st.last_event - st.first_event) + 2;
+            c.out_off = records_total;
+            records_total += c.out_cap;
+            owner[chain_first[i] + sidx] = i;
+        }
+    }
+
+    // ---- phase 3 (parallel over reads): pairs, event maps, rank tables, chain records ----
+    std::vector<nph_aligned_pair> pairs(std::max<uint64_t>(n_pairs, 1));
+    std::vector<int32_t> map_start(std::max<uint64_t>(n_map, 1));
+    std::vector<uint32_t> ranks_fwd(std::max<uint64_t>(n_ranks, 1)), ranks_rc(std::max<uint64_t>(n_ranks, 1));
+#pragma omp parallel for schedule(dynamic, 8)
+    for (long long i = 0; i < (long long)nr; ++i) {
+        if (starts[i].empty()) continue;
+        const ReadState& rs = m_reads[i];
+        const EventAlignmentParameters& p = rs.params;
+        if (fills_map[i]) {
+            int32_t* m = map_start.data() + slot_of[i].map_off;
+            const std::vector<EventRangeForBase>& b2e = p.sr->base_to_event_map;
+            for (size_t j = 0; j < b2e.size(); ++j) m[j] = b2e[j].indices[p.strand_idx].start;
+        }
+        const size_t n = rs.ref_seq.size();
+        if (n >= rs.k) {
+            const size_t nk = n - rs.k + 1;
+            rolling_kmer_ranks(rs.pore_model->pmalphabet, rs.ref_seq, rs.k, ranks_fwd.data() + rank_off[i]);
+            // entry pos of the rc table = rank of rc_ref_seq's k-mer at n - pos - k (what get_kmer_rank(ki, k, true) resolves to)
+            std::vector<uint32_t> tmp(nk);
+            rolling_kmer_ranks(rs.pore_model->pmalphabet, rs.rc_ref_seq, rs.k, tmp.data());
+            uint32_t* rc = ranks_rc.data() + rank_off[i];
+            for (size_t pos = 0; pos < nk; ++pos) rc[pos] = tmp[nk - 1 - pos];
+        }
+        for (size_t sidx = 0; sidx < starts[i].size(); ++sidx) {
+            const SegmentStart& st = starts[i][sidx];
+            nph_ea_chain& c = chains[chain_first[i] + sidx];
+            nph_aligned_pair* dst = pairs.data() + c.pair_off;
+            const AlignedSegment& seg = rs.segments[sidx];
+            for (size_t j = 0; j < seg.size(); ++j) dst[j] = nph_aligned_pair{seg[j].ref_pos, seg[j].read_pos};
+            c.map_off = slot_of[i].map_off;
             c.map_len = (uint32_t)p.sr->base_to_event_map.size();
-            c.rank_off = rank_off;
+            c.rank_off = rank_off[i];
             c.ref_len = (uint32_t)n;
-            c.read = it->second.first;
-            c.model_id = engine.model_id(rs.pore_model);
+            c.read = slot_of[i].read_index;
+            c.model_id = model_of[i];
             c.read_seq_len = (uint32_t)p.sr->read_sequence.size();
             c.ref_offset = p.ref_pos;
             c.first_event = st.first_event;
@@ -447,48 +523,49 @@ size_t EventAligner::run(Engine& engine, double indel_bias)
             c.do_base_rc = rs.do_base_rc;
             c.rc = p.strand_idx == 0 ? rs.do_base_rc : !rs.do_base_rc;
             c.k = (uint8_t)rs.k;
-            c.out_cap = (uint32_t)std::abs(st.last_event - st.first_event) + 2;
-            c.out_off = records_total;
-            records_total += c.out_cap;
-            chains.push_back(c);
-            owner.push_back(ChainRef{i});
         }
     }
-    for (ReadState& rs : m_reads) rs.done = true;             // nothing left to do for the round driver unless re-armed below
-    if (chains.empty()) return 0;
 
+    // ---- the device: reads up, one launch, records back ----
     std::vector<nph_read> reads;
     std::vector<float> mean;
     std::vector<double> time;
     detail::flatten_reads(read_table, reads, mean, time);
-    engine.check(nph_reads_load(engine.ctx(), reads.data(), reads.size(), mean.data(), time.data(), mean.size()), "nph_reads_load");
-    std::vector<nph_ea_record> records(records_total);
-    std::vector<nph_ea_result> results(chains.size());
-    if (pairs.empty()) pairs.push_back(nph_aligned_pair{0, 0});
-    if (ranks_fwd.empty()) { ranks_fwd.push_back(0); ranks_rc.push_back(0); }
+    bool any_drift = false;
+    for (const nph_read& r : reads) any_drift = any_drift || r.drift != 0.0;
+    engine.check(nph_reads_load(engine.ctx(), reads.data(), reads.size(), mean.data(), any_drift ? time.data() : nullptr, mean.size()), "nph_reads_load");
+    nph_ea_record* const records = static_cast<nph_ea_record*>(engine.pinned(0, sizeof(nph_ea_record) * std::max<uint64_t>(records_total, 1)));
+    std::vector<nph_ea_result> results(n_chains);
     engine.check(nph_eventalign_chain(engine.ctx(), pairs.data(), pairs.size(), map_start.data(), map_start.size(), ranks_fwd.data(),
-                                      ranks_rc.data(), ranks_fwd.size(), chains.data(), chains.size(), indel_bias, records.data(),
-                                      records.size(), results.data()),
+                                      ranks_rc.data(), ranks_fwd.size(), chains.data(), n_chains, indel_bias, records, records_total,
+                                      results.data()),
                  "nph_eventalign_chain");
 
-    // ---- scatter; a read with a window the chain kernel could not hold goes through the round driver instead ----
-    std::vector<char> redo(m_reads.size(), 0);
-    for (size_t c = 0; c < chains.size(); ++c) {
+    // ---- scatter (parallel over reads); a read with a window the chain kernel could not hold goes through the round
+    //      driver instead ----
+    std::vector<char> redo(nr, 0);
+    for (size_t c = 0; c < n_chains; ++c) {
         const int st = results[c].status;
         if (st & NPH_EA_RC_STRIDE) throw Error(NPH_ERR_INVALID, "rc and event_stride disagree");     // ref asserts (profile_hmm_r9.inl:275)
         if (st & NPH_EA_BAD_EVENT) throw Error(NPH_ERR_INVALID, "event index outside the read");
         if (st & NPH_EA_OUT_OVERFLOW) throw Error(NPH_ERR_STATE, "eventalign chain: record room exceeded");
-        if (st & NPH_EA_WINDOW_TOO_LARGE) redo[owner[c].read] = 1;
+        if (st & NPH_EA_WINDOW_TOO_LARGE) redo[owner[c]] = 1;
+    }
+#pragma omp parallel for schedule(dynamic, 8)
+    for (long long i = 0; i < (long long)nr; ++i) {
+        if (redo[i] || starts[i].empty()) continue;
+        ReadState& rs = m_reads[i];
+        size_t total = 0;
+        for (size_t c = chain_first[i]; c < chain_first[i + 1]; ++c) total += results[c].n_records;
+        rs.output.reserve(rs.output.size() + total);
+        for (size_t c = chain_first[i]; c < chain_first[i + 1]; ++c) {
+            const nph_ea_record* r = records + chains[c].out_off;
+            for (uint32_t j = 0; j < results[c].n_records; ++j) rs.output.push_back(Rec{r[j].ref_position, r[j].event_idx, (char)r[j].hmm_state});
+            rs.segments_aligned += results[c].n_windows;
+        }
     }
     size_t n_redo = 0;
-    for (size_t c = 0; c < chains.size(); ++c) {
-        ReadState& rs = m_reads[owner[c].read];
-        if (redo[owner[c].read]) continue;
-        const nph_ea_record* r = records.data() + chains[c].out_off;
-        for (uint32_t i = 0; i < results[c].n_records; ++i) rs.output.push_back(Rec{r[i].ref_position, r[i].event_idx, (char)r[i].hmm_state});
-        rs.segments_aligned += results[c].n_windows;
-    }
-    for (size_t i = 0; i < m_reads.size(); ++i) {
+    for (size_t i = 0; i < nr; ++i) {
         if (!redo[i]) continue;
         ReadState& rs = m_reads[i];
         rs.done = false; rs.in_segment = false; rs.segment_idx = 0; rs.pending = false;

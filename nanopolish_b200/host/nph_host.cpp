@@ -206,7 +206,22 @@ Engine::Engine(int device)
 
 Engine::~Engine()
 {
+    for (Pinned& b : m_pinned) if (b.p) nph_host_free(b.p);
     if (m_ctx) nph_destroy(m_ctx);
+}
+
+void* Engine::pinned(int slot, size_t bytes)
+{
+    if (slot < 0 || slot >= 4) throw Error(NPH_ERR_INVALID, "pinned slot");
+    Pinned& b = m_pinned[slot];
+    if (b.bytes < bytes) {
+        if (b.p) nph_host_free(b.p);
+        b.p = nullptr; b.bytes = 0;
+        const size_t want = bytes + bytes / 4;
+        check(nph_host_alloc(&b.p, want), "nph_host_alloc");
+        b.bytes = want;
+    }
+    return b.p;
 }
 
 Engine& Engine::thread_default()
@@ -249,8 +264,11 @@ void flatten_reads(const std::vector<std::pair<const SquiggleRead*, uint8_t>>& r
     for (auto& r : reads) total += r.first->events[r.second].size();
     mean.resize(total);
     time.resize(total);
-    size_t off = 0;
-    for (size_t i = 0; i < reads.size(); ++i) {
+    std::vector<size_t> offs(reads.size() + 1, 0);
+    for (size_t i = 0; i < reads.size(); ++i) offs[i + 1] = offs[i] + reads[i].first->events[reads[i].second].size();
+#pragma omp parallel for schedule(dynamic, 8) if (total > (size_t)1 << 18)
+    for (long long ii = 0; ii < (long long)reads.size(); ++ii) {
+        const size_t i = (size_t)ii, off = offs[i];
         const SquiggleRead* sr = reads[i].first;
         const uint8_t st = reads[i].second;
         const std::vector<SquiggleEvent>& ev = sr->events[st];
@@ -262,7 +280,6 @@ void flatten_reads(const std::vector<std::pair<const SquiggleRead*, uint8_t>>& r
         o.scale = s.scale; o.shift = s.shift; o.drift = s.drift; o.var = s.var; o.log_var = s.log_var;
         o.events_per_base = sr->events_per_base[st];
         for (size_t e = 0; e < ev.size(); ++e) { mean[off + e] = ev[e].mean; time[off + e] = ev[e].start_time; }
-        off += ev.size();
     }
 }
 } // namespace detail

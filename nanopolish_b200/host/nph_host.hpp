@@ -296,10 +296,14 @@ public:
     void forget_model(const PoreModel* model) { m_models.erase(model); }   // after a model was edited in place
     static Engine& thread_default();                  // lazily created, device from $NPH_DEVICE (default 0)
     void check(int status, const char* what) const;
+    // page-locked host staging owned by the engine, grown on demand and reused across calls (slot = one buffer per use)
+    void* pinned(int slot, size_t bytes);
 
 private:
     nph_ctx* m_ctx = nullptr;
     std::unordered_map<const PoreModel*, uint32_t> m_models;
+    struct Pinned { void* p = nullptr; size_t bytes = 0; };
+    Pinned m_pinned[4];
 };
 
 namespace detail {

@@ -420,11 +420,12 @@ long long nphh_ea_tsv_all(char* out, size_t cap)
         const std::vector<std::string> parts = g_aligner.tsv_batch();
         size_t total = 0;
         for (const std::string& s : parts) total += s.size();
+        n = (long long)total;
+        if (!out) return;                                   // size only (timing the formatter without the copy)
         if (total + 1 > cap) throw Error(NPH_ERR_INVALID, "text buffer too small");
         char* o = out;
         for (const std::string& s : parts) { std::memcpy(o, s.data(), s.size()); o += s.size(); }
         *o = 0;
-        n = (long long)total;
     });
     return rc ? rc : n;
 }
@@ -458,6 +459,21 @@ long long nphh_format_fixed_check(uint64_t seed, size_t n)
         }
     }
     return bad;
+}
+
+// rolling_kmer_ranks against Alphabet::kmer_rank on every k-mer of seq: number of mismatches
+long long nphh_rolling_ranks_check(const char* alphabet, const char* seq, uint32_t k)
+{
+    long long bad = -1;
+    int rc = guard([&] {
+        const Alphabet* a = get_alphabet_by_name(alphabet);
+        const std::string s(seq);
+        std::vector<uint32_t> r(s.size() >= k ? s.size() - k + 1 : 0);
+        rolling_kmer_ranks(a, s, k, r.data());
+        bad = 0;
+        for (size_t i = 0; i < r.size(); ++i) bad += r[i] != a->kmer_rank(s.c_str() + i, k);
+    });
+    return rc ? rc : bad;
 }
 
 long long nphh_ea_num_segments(int idx) { return (long long)g_aligner.num_segments(idx); }

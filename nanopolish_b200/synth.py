@@ -418,3 +418,32 @@ def gen_raw(n_reads: int, n_samples: int, model: PoreModel, seed: int = 42, mean
     if return_seqs:
         return np.concatenate(chunks), reads, seqs
     return np.concatenate(chunks), reads
+
+
+def eventalign_chains(rs: ReadSet, model_id: int = 0):
+    """Inputs of nph_eventalign_chain for reads aligned to the reference they were generated from (forward strand, CIGAR all
+    M, reference = the read's own sequence): one chain per read.  Returns (pairs i4[n, 2], event_map_start i4, ranks_fwd u4,
+    ranks_rc u4, chains EA_CHAIN_DT).  ref: align_read_to_ref's inputs, src/alignment/nanopolish_eventalign.cpp:612-689."""
+    k = rs.k
+    pairs, maps, rf, rr = [], [], [], []
+    chains = np.zeros(rs.n_reads, EA_CHAIN_DT)
+    po = mo = ro = oo = 0
+    for i in range(rs.n_reads):
+        codes = rs.seq_codes[i]
+        nk = codes.shape[0] - k + 1
+        which = rs.ev_kmer[i]
+        first = np.searchsorted(which, np.arange(nk), side="left")
+        last = np.searchsorted(which, np.arange(nk), side="right") - 1
+        start = np.where(last >= first, first, -1).astype(np.int32)
+        has = np.flatnonzero(start >= 0)
+        # get_closest_event_to of the first / last aligned k-mer: nearest k-mer with an event, looking backwards first
+        first_event = int(start[has[0]])
+        last_event = int(start[has[-1]])
+        p = np.arange(nk, dtype=np.int32)
+        pairs.append(np.stack([p, p], 1)); maps.append(start)
+        rf.append(kmer_ranks_from_codes(codes, k, 4)); rr.append(dna_rc_kmer_ranks(codes, k))
+        cap = abs(last_event - first_event) + 2
+        chains[i] = (po, mo, ro, oo, i, model_id, nk, nk, codes.shape[0], codes.shape[0], cap, 0, first_event, last_event, 0, 0, k, 0)
+        po += nk; mo += nk; ro += nk; oo += cap
+    return (np.ascontiguousarray(np.concatenate(pairs)), np.concatenate(maps), np.concatenate(rf).astype(np.uint32),
+            np.concatenate(rr).astype(np.uint32), chains)

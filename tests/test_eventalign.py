@@ -170,6 +170,18 @@ def test_format_fixed_matches_printf(host):
     assert host.nphh_format_fixed_check(C.c_uint64(20240923), C.c_size_t(600_000)) == 0, host.nphh_last_error()
 
 
+def test_rolling_kmer_ranks(host):
+    """the rank tables EventAligner::run hands the chain kernel (one rolling pass per reference) == Alphabet::kmer_rank"""
+    host.nphh_rolling_ranks_check.restype = C.c_longlong
+    rng = np.random.default_rng(4)
+    dna = "".join("ACGT"[c] for c in rng.integers(0, 4, 3000))
+    cpg = "".join("ACGMT"[c] for c in rng.integers(0, 5, 3000))
+    assert host.nphh_rolling_ranks_check(b"nucleotide", dna.encode(), 6) == 0
+    assert host.nphh_rolling_ranks_check(b"nucleotide", dna.encode(), 5) == 0
+    assert host.nphh_rolling_ranks_check(b"cpg", cpg.encode(), 6) == 0
+    assert host.nphh_rolling_ranks_check(b"nucleotide", b"ACGTA", 6) == 0          # shorter than k: no k-mers
+
+
 def test_get_aligned_segments(host):
     ops = [(5, "S"), (10, "M"), (2, "I"), (3, "D"), (4, "="), (7, "N"), (6, "X"), (3, "H")]
     cigar = EP.pack_cigar(ops)
