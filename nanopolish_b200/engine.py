@@ -131,15 +131,19 @@ class Engine:
                                            _p(states), _p(off), _p(counts), _p(scores)), "nph_hmm_align")
         return [states[int(off[j]):int(off[j]) + int(counts[j])] for j in range(n)], scores
 
-    def eventalign_chain(self, pairs, event_map_start, ref_ranks_fwd, ref_ranks_rc, chains, indel_bias: float = 1.0):
+    def eventalign_chain(self, pairs, event_map_start, ref_ranks_fwd, ref_ranks_rc, chains, indel_bias: float = 1.0, out=None):
         """eventalign's segment chains (align_read_to_ref's per-segment loop) walked on the device against the resident
         reads: returns (records EA_RECORD_DT[sum out_cap], results EA_RESULT_DT[n_chains]); chain c's records are
         records[out_off : out_off + n_records]."""
         from .synth import EA_RECORD_DT, EA_RESULT_DT
         n = chains.shape[0]
         total = int((chains["out_off"] + chains["out_cap"]).max()) if n else 0
-        records = np.zeros(total, EA_RECORD_DT)
-        results = np.zeros(n, EA_RESULT_DT)
+        if out is not None:                      # caller-owned (e.g. page-locked) output buffers
+            records, results = out
+            assert records.shape[0] >= total and results.shape[0] >= n
+        else:
+            records = np.zeros(total, EA_RECORD_DT)
+            results = np.zeros(n, EA_RESULT_DT)
         self._check(self.lib.nph_eventalign_chain(self.ctx, _p(pairs), pairs.shape[0], _p(event_map_start), event_map_start.shape[0],
                                                   _p(ref_ranks_fwd), _p(ref_ranks_rc), ref_ranks_fwd.shape[0], _p(chains), n,
                                                   indel_bias, _p(records), total, _p(results)), "nph_eventalign_chain")

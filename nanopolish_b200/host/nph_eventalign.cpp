@@ -417,7 +417,7 @@ size_t EventAligner::run(Engine& engine, double indel_bias)
     //      that trims to nothing (where the reference returns from align_read_to_ref) ----
     std::vector<std::vector<SegmentStart>> starts(nr);
     std::vector<std::string> errors(nr);
-#pragma omp parallel for schedule(dynamic, 8)
+#pragma omp parallel for schedule(dynamic, 8) num_threads(host_threads())
     for (long long i = 0; i < (long long)nr; ++i) {
         ReadState& rs = m_reads[i];
         if (rs.done) continue;
@@ -484,7 +484,7 @@ size_t EventAligner::run(Engine& engine, double indel_bias)
     std::vector<nph_aligned_pair> pairs(std::max<uint64_t>(n_pairs, 1));
     std::vector<int32_t> map_start(std::max<uint64_t>(n_map, 1));
     std::vector<uint32_t> ranks_fwd(std::max<uint64_t>(n_ranks, 1)), ranks_rc(std::max<uint64_t>(n_ranks, 1));
-#pragma omp parallel for schedule(dynamic, 8)
+#pragma omp parallel for schedule(dynamic, 8) num_threads(host_threads())
     for (long long i = 0; i < (long long)nr; ++i) {
         if (starts[i].empty()) continue;
         const ReadState& rs = m_reads[i];
@@ -551,7 +551,7 @@ size_t EventAligner::run(Engine& engine, double indel_bias)
         if (st & NPH_EA_OUT_OVERFLOW) throw Error(NPH_ERR_STATE, "eventalign chain: record room exceeded");
         if (st & NPH_EA_WINDOW_TOO_LARGE) redo[owner[c]] = 1;
     }
-#pragma omp parallel for schedule(dynamic, 8)
+#pragma omp parallel for schedule(dynamic, 8) num_threads(host_threads())
     for (long long i = 0; i < (long long)nr; ++i) {
         if (redo[i] || starts[i].empty()) continue;
         ReadState& rs = m_reads[i];
@@ -706,7 +706,7 @@ std::vector<std::string> EventAligner::tsv_batch(const EventalignOptions& opt) c
 {
     std::vector<std::string> out(m_reads.size());
     // rows of different reads are independent; the reference formats them one read at a time inside an omp critical
-#pragma omp parallel for schedule(dynamic, 4)
+#pragma omp parallel for schedule(dynamic, 4) num_threads(host_threads())
     for (long long i = 0; i < (long long)m_reads.size(); ++i) out[i] = tsv((size_t)i, opt);
     return out;
 }

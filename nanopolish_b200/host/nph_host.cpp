@@ -1,5 +1,8 @@
 // nph_host.cpp — implementation of the C++ host mirror (see nph_host.hpp).
 #include "nph_host.hpp"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include <algorithm>
 #include <cctype>
@@ -255,6 +258,19 @@ uint32_t Engine::model_id(const PoreModel* model)
 // ---------------------------------------------------------------------------------------------
 // Batches
 // ---------------------------------------------------------------------------------------------
+int host_threads()
+{
+    static const int n = [] {
+        int t = 16;
+#ifdef _OPENMP
+        t = std::min(omp_get_max_threads(), 16);
+#endif
+        if (const char* e = std::getenv("NPH_HOST_THREADS")) { const int v = std::atoi(e); if (v > 0) t = v; }
+        return std::max(1, t);
+    }();
+    return n;
+}
+
 namespace detail {
 void flatten_reads(const std::vector<std::pair<const SquiggleRead*, uint8_t>>& reads, std::vector<nph_read>& out,
                    std::vector<float>& mean, std::vector<double>& time)
@@ -266,7 +282,7 @@ void flatten_reads(const std::vector<std::pair<const SquiggleRead*, uint8_t>>& r
     time.resize(total);
     std::vector<size_t> offs(reads.size() + 1, 0);
     for (size_t i = 0; i < reads.size(); ++i) offs[i + 1] = offs[i] + reads[i].first->events[reads[i].second].size();
-#pragma omp parallel for schedule(dynamic, 8) if (total > (size_t)1 << 18)
+#pragma omp parallel for schedule(dynamic, 8) num_threads(host_threads()) if (total > (size_t)1 << 18)
     for (long long ii = 0; ii < (long long)reads.size(); ++ii) {
         const size_t i = (size_t)ii, off = offs[i];
         const SquiggleRead* sr = reads[i].first;

@@ -306,6 +306,11 @@ private:
     Pinned m_pinned[4];
 };
 
+// Threads the host-side batch loops use (chain building, record scatter, TSV formatting): $NPH_HOST_THREADS if set,
+// else min(omp_get_max_threads(), 16) — GPU nodes often expose many more logical CPUs than a container can keep busy,
+// and a parallel region that oversubscribes them pays for it at every barrier.
+int host_threads();
+
 namespace detail {
 // (read, strand) list -> the flat nph_read records + event arrays the C ABI takes
 void flatten_reads(const std::vector<std::pair<const SquiggleRead*, uint8_t>>& reads, std::vector<nph_read>& out,

@@ -46,4 +46,13 @@ evs = eng.detect_events_batch(raw, rr, synth.event_params(False))
 out = eng.load_from_raw_batch(flat, ranks, jobs, mid, synth.event_params(False))
 b2e, cal = eng.recalibrate_batch(rs3.reads, rs3.ev_mean, ar, aj, mid, pairs, res)
 print("prologue ok", [int(c) for c in out[6]["status"]], int(out[0][-1]))
+# eventalign chain kernel (one warp per read walks its windows) and the RNA branch of the fused prologue
+rs4 = synth.gen_reads(5, 1200, nuc, seed=4, drift=True)
+eng.reads_load(rs4.reads, rs4.ev_mean, rs4.ev_start_time)
+pr, mp, rf, rrc, ch = synth.eventalign_chains(rs4, mid)
+recs, resu = eng.eventalign_chain(pr, mp, rf, rrc, ch)
+assert (resu["status"] == 0).all() and (resu["n_records"] > 1000).all()
+prm = synth.event_params(True)
+out_rna = eng.load_from_raw_batch(flat, ranks, jobs, mid, prm)
+print("eventalign chain ok", [int(x) for x in resu["n_windows"]], "rna prologue", [int(c) for c in out_rna[6]["status"]])
 eng.close()
