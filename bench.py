@@ -55,6 +55,22 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def cpu_quota():
+    """CPUs' worth of time the container may use (cgroup v2 cpu.max / v1 cfs quota), or None when unlimited/unknown.
+    The GPU boxes expose 128 logical CPUs under a 16-CPU quota: the CPU arm runs that many threads on that much time."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if q == "max" else float(q) / float(per)
+    except Exception:
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / per
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi sampled every 200 ms DURING the timed region (B200_PROFILING.md clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -185,7 +201,7 @@ class CpuArm:
 
     def report(self, idx, secs):
         ev = int(self.E[idx].sum())
-        return {"value": ev / secs, "unit": UNIT, "cores": self.cores,
+        return {"value": ev / secs, "unit": UNIT, "cores": self.cores, "cpu_quota": cpu_quota(),
                 "kind": "reference" if self.use_ref else "port",
                 "sample": f"{idx.shape[0]} jobs ({ev} scored events, {int(self.cells[idx].sum())} block-cells) of the "
                           f"same job list, {secs:.2f} s per pass, OpenMP over jobs with {self.cores} threads",
@@ -318,7 +334,7 @@ def run_aux(args, rank, world, local, saved_stdout):
                     rows = list(ex.map(lambda i: ro.eventalign(rh[i], "contig", seqs[i], 0, 0, cig(i), i, want_cigar=False)[2].shape[0], range(ns)))
                 cs = time.perf_counter() - t0
                 assert rows == [int(v) for v in results["n_records"][:ns]]
-                cpu = {"value": int(rs.reads["n_events"][:ns].sum()) / cs, "unit": "events/s", "cores": cores, "kind": "reference",
+                cpu = {"value": int(rs.reads["n_events"][:ns].sum()) / cs, "unit": "events/s", "cores": cores, "cpu_quota": cpu_quota(), "kind": "reference",
                        "sample": f"{ns} of the {n_reads} reads through the compiled reference's align_read_to_ref + TSV writer, one read per thread"}
         line = {"metric": "eventalign_events_per_sec", "value": ev / (t * 1e-3), "unit": "events/s", "n_gpus": 1, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -380,7 +396,7 @@ def run_aux(args, rank, world, local, saved_stdout):
             with ThreadPoolExecutor(cores) as ex:       # the C restatement releases the GIL inside each call
                 list(ex.map(lambda i: oracle_chain(port, nuc, [signals[i]], [seqs[i]]), range(ns)))
             cs = time.perf_counter() - t0
-            cpu = {"value": sum(signals[i].shape[0] for i in range(ns)) / cs, "unit": "samples/s", "cores": cores, "kind": "port",
+            cpu = {"value": sum(signals[i].shape[0] for i in range(ns)) / cs, "unit": "samples/s", "cores": cores, "cpu_quota": cpu_quota(), "kind": "port",
                    "sample": f"{ns} of the {jobs.shape[0]} reads through oracle/ (trim, events, MoM, ABEA, calibration), one read per thread"}
         line = {"metric": "load_from_raw_samples_per_sec", "value": flat.shape[0] / (t * 1e-3), "unit": "samples/s", "n_gpus": 1,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t, "higher_is_better": True, "scaling": "weak",

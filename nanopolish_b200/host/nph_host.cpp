@@ -261,9 +261,9 @@ uint32_t Engine::model_id(const PoreModel* model)
 int host_threads()
 {
     static const int n = [] {
-        int t = 16;
+        int t = 32;
 #ifdef _OPENMP
-        t = std::min(omp_get_max_threads(), 16);
+        t = std::min(omp_get_max_threads(), 32);
 #endif
         if (const char* e = std::getenv("NPH_HOST_THREADS")) { const int v = std::atoi(e); if (v > 0) t = v; }
         return std::max(1, t);
