@@ -158,33 +158,45 @@ __global__ void __launch_bounds__(kThreads, 1) eventalign_chain_kernel(const Cha
             j.e_first = (long long)curr_start_event;
 
             float last_v;
-            const int n = viterbi_align<C>(p.c, p.flank, j, sc, states, (int)p.states_stride, &last_v, lane);
+            const int n = viterbi_align<C, false>(p.c, p.flank, j, sc, states, (int)p.states_stride, &last_v, lane);
             n_windows += 1;
 
-            // emission (eventalign.cpp:752-806): lane 0 walks the path, the cursor is broadcast
+            // emission (eventalign.cpp:752-806): the first kOutputStride states (all of them in the last section) that are
+            // not k-mer skips and not on the window's start event, 32 states at a time by ballot + prefix count
             const bool last_section = end_pair_idx == n_pairs - 1;
+            const int limit = last_section ? 0x7fffffff : kOutputStride;
+            const nph_align_state* const path = states + ((int)p.states_stride - n);       // ascending event order
             int num_output = 0, last_event_output = 0, last_ref_kmer_output = 0, overflow = 0;
-            if (lane == 0) {
-                for (int idx = 0; idx < n && (num_output < kOutputStride || last_section); ++idx) {
-                    const nph_align_state as = states[idx];
-                    if (as.state != 'K' && (int)as.event_idx != curr_start_event) {
-                        if (n_rec + (uint32_t)num_output >= ch.out_cap) { overflow = 1; break; }
-                        nph_ea_record r;
-                        r.ref_position = curr_start_ref + (int)as.kmer_idx;
-                        r.event_idx = (int)as.event_idx;
-                        r.hmm_state = (uint8_t)as.state;
-                        r.reserved[0] = 0; r.reserved[1] = 0; r.reserved[2] = 0;
-                        rec[n_rec + num_output] = r;
-                        last_event_output = r.event_idx;
-                        last_ref_kmer_output = r.ref_position;
-                        num_output += 1;
-                    }
+            for (int base = 0; base < n && num_output < limit; base += 32) {
+                const int idx = base + lane;
+                int ev_idx = 0, ref_position = 0;
+                char state = 'K';
+                if (idx < n) {
+                    const nph_align_state as = path[idx];
+                    ev_idx = (int)as.event_idx; ref_position = curr_start_ref + (int)as.kmer_idx; state = as.state;
+                }
+                const bool emit = idx < n && state != 'K' && ev_idx != curr_start_event;
+                const unsigned m = __ballot_sync(kFull, emit);
+                const int pos = num_output + __popc(m & ((1u << lane) - 1u));
+                const bool take = emit && pos < limit;
+                const bool fits = n_rec + (uint32_t)pos < ch.out_cap;
+                if (take && fits) {
+                    nph_ea_record r;
+                    r.ref_position = ref_position;
+                    r.event_idx = ev_idx;
+                    r.hmm_state = (uint8_t)state;
+                    r.reserved[0] = 0; r.reserved[1] = 0; r.reserved[2] = 0;
+                    rec[n_rec + pos] = r;
+                }
+                const unsigned mt = __ballot_sync(kFull, take);
+                overflow |= __ballot_sync(kFull, take && !fits) != 0u;
+                if (mt) {
+                    const int last_lane = 31 - __clz(mt);
+                    last_event_output = __shfl_sync(kFull, ev_idx, last_lane);
+                    last_ref_kmer_output = __shfl_sync(kFull, ref_position, last_lane);
+                    num_output += __popc(mt);
                 }
             }
-            num_output = __shfl_sync(kFull, num_output, 0);
-            last_event_output = __shfl_sync(kFull, last_event_output, 0);
-            last_ref_kmer_output = __shfl_sync(kFull, last_ref_kmer_output, 0);
-            overflow = __shfl_sync(kFull, overflow, 0);
             n_rec += (uint32_t)num_output;
             if (overflow) { status |= NPH_EA_OUT_OVERFLOW; break; }
             // advance the cursor to where the output stopped

@@ -44,7 +44,11 @@ __device__ __forceinline__ void vmax(float& mx, int& from, float x, int idx)
 // Fill, backtrack and forward replay of one job by one warp.  Returns the number of states written to out[0..n) in
 // ascending event order (0 where the reference would trip an assert: the path enters a -inf cell or block 0, or cap is
 // too small); *last_v_out = l_fm of the last state (lane 0's value is the meaningful one).  Requires E >= 2.
-template <int C>
+// REPLAY = false (the eventalign chain, which never reads l_fm): no forward replay; the states stay where the backtrack
+// put them, out[cap - n .. cap) in ascending event order with l_fm = 0, and the one way a path can enter a -inf cell — a
+// FROM_SOFT that is not the legitimate start (every -inf cell records FROM_SOFT, and finite transitions out of finite
+// cells stay finite) — is caught during the backtrack.
+template <int C, bool REPLAY = true>
 __device__ __forceinline__ int viterbi_align(const HmmConsts& c, const float* __restrict__ flank, const VitJob& j, const VitScratch& sc,
                                              nph_align_state* out, int cap, float* last_v_out, int lane)
 {
@@ -181,6 +185,7 @@ __device__ __forceinline__ int viterbi_align(const HmmConsts& c, const float* __
         // corner of the trace that ends at (row, kmer): the warp stages that corner in shared memory with 32
         // independent loads per lane (lane = k-mer column, 64 contiguous bytes per row) instead of paying one dependent
         // L2 round trip per state.
+        bool ended_soft = false;
         int row0 = 0, kmer0 = -1;                 // corner currently staged: rows (row0-32, row0], k-mers (kmer0-32, kmer0]
         while (row > 0) {
             if (kmer0 < 0 || row <= row0 - 32 || kmer <= kmer0 - 32) {
@@ -211,7 +216,11 @@ __device__ __forceinline__ int viterbi_align(const HmmConsts& c, const float* __
                 out[cap - 1 - n] = a;
             }
             ++n;
-            if (mvt == MV_SOFT) break;
+            if (mvt == MV_SOFT) {
+                if (!REPLAY && !(st == 2 && kmer == 0 && (row == 1 || pre_clip))) status = 2;
+                ended_soft = true;
+                break;
+            }
             int nst = 2;
             switch (mvt) {
                 case MV_SAME_M: nst = 2; break;
@@ -224,8 +233,13 @@ __device__ __forceinline__ int viterbi_align(const HmmConsts& c, const float* __
             st = nst;
             if (kmer < 0) { status = 2; break; } // block 0: the reference asserts
         }
+        if (!REPLAY && !status && !ended_soft) status = 2;    // walked off row 1 without reaching the start state
     }
     __syncwarp();
+    if (!REPLAY) {
+        *last_v_out = NEG;
+        return status ? 0 : n;
+    }
 
     // ---------------------------------- replay forwards: l_fm of every state ----------------------------------
     float last_v = NEG;

@@ -42,8 +42,16 @@ def _edit_script(read_seq: str, rng, soft_clip: int, with_skip: bool):
     return "".join(ref), ops
 
 
-def build_cases(n_reads=4, n_events=1500, seed=77):
-    model = synth.load_model("nucleotide")
+def five_mer_model():
+    """a 5-mer table with correlated neighbouring levels: the 6-mer table averaged over its last base"""
+    m6 = synth.load_model("nucleotide")
+    sd5 = m6.level_stdv.reshape(1024, 4).mean(1)
+    return synth.PoreModel("derived.nucleotide.5mer", 5, "nucleotide", m6.level_mean.reshape(1024, 4).mean(1), sd5, np.log(sd5))
+
+
+def build_cases(n_reads=4, n_events=1500, seed=77, model=None):
+    model = model or synth.load_model("nucleotide")
+    K = model.k
     rs = synth.gen_reads(n_reads, n_events, model, seed=seed, drift=True)
     cases = []
     for i in range(rs.n_reads):
@@ -77,7 +85,7 @@ def build_cases(n_reads=4, n_events=1500, seed=77):
         rd = rs.reads[i]
         ear = EP.EARead(name=f"read_{i}", read_sequence=read_sequence, b2e_start=b2e_start, mean=rs.ev_mean[o:o + E],
                         stdv=stdv, duration=duration, start_time=rs.ev_start_time[o:o + E], shift=float(rd["shift"]),
-                        scale=float(rd["scale"]), drift=float(rd["drift"]), var=float(rd["var"]), model=model)
+                        scale=float(rd["scale"]), drift=float(rd["drift"]), var=float(rd["var"]), model=model, k=K)
         cases.append(dict(read=ear, b2e_stop=b2e_stop, contig=contig, contig_name="chr_test", ref_pos=ref_pos,
                           flag=EP.BAM_FREVERSE if reverse else 0, mapq=60 - i, cigar=EP.pack_cigar(ops), fetched=fetched,
                           read_idx=i, region=(-1, -1)))
@@ -95,6 +103,8 @@ def read_slot(case, n_synth_reads):
 
 def port_align_fn(port_oracle, rs, model, slot, indel_bias=1.0):
     """profile_hmm_align through the plain-C oracle for read `slot` of rs."""
+    K = model.k
+
     def fn(fwd, rc_seq, e0, e1, stride, rc):
         assert EP.reverse_complement(fwd) == rc_seq
         codes = synth.encode(fwd, "nucleotide")

@@ -238,7 +238,28 @@ def test_eventalign_chain_falls_back_for_large_windows(host, cases, restated, go
 @pytest.mark.gpu
 def test_eventalign_chain_abi(engine, cases, restated):
     """nph_eventalign_chain called directly (what EventAligner::run does underneath): records per chain."""
+    _chain_abi(engine, cases, restated)
+
+
+@pytest.mark.gpu
+def test_eventalign_chain_abi_5mer(engine, port_oracle):
+    """5-mers (the RNA model's k): a 101-base window holds 97 k-mers, so the chain kernel runs four columns per lane."""
+    model = EC.five_mer_model()
+    cases5 = EC.build_cases(3, 1200, seed=505, model=model)
+    _, rs, cs = cases5
+    restated5 = []
+    for c in cs:
+        st = {}
+        al = EP.align_read_to_ref(c["read"], c["contig_name"], c["fetched"], c["ref_pos"], c["flag"], c["cigar"], c["read_idx"],
+                                  EC.port_align_fn(port_oracle, rs, model, EC.read_slot(c, rs.n_reads)), *c["region"], stats=st)
+        restated5.append((al, st.get("segments", 0)))
+    assert sum(len(al) for al, _ in restated5) > 2000
+    _chain_abi(engine, cases5, restated5)
+
+
+def _chain_abi(engine, cases, restated):
     model, rs, cs = cases
+    K = model.k
     mid = engine.model_upload(model)
     engine.reads_load(rs.reads, rs.ev_mean, rs.ev_start_time)
     chains = np.zeros(0, synth.EA_CHAIN_DT)
@@ -256,18 +277,18 @@ def test_eventalign_chain_abi(engine, cases, restated):
         ref = EP.disambiguate(c["fetched"])
         codes = synth.encode(ref, "nucleotide")
         seg = EP.get_aligned_segments(c["ref_pos"], c["cigar"])[0]
-        seg = [p for p in seg if p[1] <= len(r.read_sequence) - EC.K]
+        seg = [p for p in seg if p[1] <= len(r.read_sequence) - K]
         rev = bool(c["flag"] & EP.BAM_FREVERSE)
         k0, k1 = seg[0][1], seg[-1][1]
         if rev:
             k0, k1 = r.flip_k_strand(k0), r.flip_k_strand(k1)
         first, last = r.get_closest_event_to(k0), r.get_closest_event_to(k1)
         rows.append((sum(len(p) for p in pairs), map_off[slot], sum(x.shape[0] for x in rf), out_off, slot, mid, len(seg), r.b2e_start.shape[0],
-                     len(ref), len(r.read_sequence), abs(last - first) + 2, c["ref_pos"], first, last, int(rev), int(rev), EC.K, 0))
+                     len(ref), len(r.read_sequence), abs(last - first) + 2, c["ref_pos"], first, last, int(rev), int(rev), K, 0))
         out_off += abs(last - first) + 2
         pairs.append(seg)
-        rf.append(synth.kmer_ranks_from_codes(codes, EC.K, 4).astype(np.uint32))
-        rr.append(synth.dna_rc_kmer_ranks(codes, EC.K).astype(np.uint32))
+        rf.append(synth.kmer_ranks_from_codes(codes, K, 4).astype(np.uint32))
+        rr.append(synth.dna_rc_kmer_ranks(codes, K).astype(np.uint32))
         want.append((al, segs))
     chains = np.array(rows, synth.EA_CHAIN_DT)
     flat_pairs = np.array([p for seg in pairs for p in seg], np.int32).reshape(-1, 2)
