@@ -375,6 +375,12 @@ int nph_load_from_raw_batch(nph_ctx* ctx, const float* raw, size_t n_samples_tot
                             float* ev_duration_out, size_t events_cap,
                             nph_event_range* base_to_event_out, nph_calibration* calibrations_out);
 
+/* The surviving sample range [start, end) of each job of the most recent nph_load_from_raw_batch on this context,
+ * relative to the job's sample_off ({0, 0}: nothing survived).  It is what load_from_raw keeps with SRF_LOAD_RAW_SAMPLES
+ * (samples[i] = rt.raw[rt.start + i], sample_start_time = 0; src/nanopolish_squiggle_read.cpp:251-258), which eventalign's
+ * --samples / --signal-index read back.  NPH_ERR_STATE if n_jobs is not that call's job count. */
+int nph_last_trim_ranges(nph_ctx* ctx, nph_raw_range* ranges_out, size_t n_jobs);
+
 /* ---- measurement hooks (used by bench.py; not part of the reference surface) ------------- */
 /* Device time in ms of the most recent nph_hmm_score / nph_abea_run kernel sequence, measured
  * with CUDA events on the context's stream (valid after a sync), and the number of kernel

@@ -144,18 +144,22 @@ __device__ __forceinline__ int viterbi_align(const HmmConsts& c, const float* __
                 vmax(m, fm, __fadd_rn(lp_bm_self, Bp[c]), MV_SAME_B);
                 vmax(m, fm, __fadd_rn(lp_bm_next, lb_prev), MV_PREV_B);
                 vmax(m, fm, __fadd_rn(lp_km, lk_prev), MV_PREV_K);
-                vmax(m, fm, (c == 0) ? soft : NEG, MV_SOFT);
+                // the soft-clip candidate is -inf everywhere but in column 0: there it takes part in the chain, elsewhere it can
+                // only win the label when every candidate is -inf (a later equal candidate takes the label)
+                if (c == 0) vmax(m, fm, soft, MV_SOFT);
+                else fm = (m == NEG) ? MV_SOFT : fm;
                 m = __fadd_rn(m, em);
-                // BAD EVENT: {same M, -inf, same B, -inf, -inf, -inf}
+                // BAD EVENT: {same M, -inf, same B, -inf, -inf, -inf}.  The -inf candidates between and after the live ones
+                // only matter when the running max is still -inf after the last live one: then the last index (SOFT) holds
+                // the label; labels they would take earlier are overwritten by the next live candidate (x >= -inf always
+                // updates an all--inf chain).
                 float b = __fadd_rn(lp_mb, Mp[c]);
                 int fb = MV_SAME_M;
-                fb = (b == NEG) ? MV_PREV_M : fb;
                 vmax(b, fb, __fadd_rn(lp_bb, Bp[c]), MV_SAME_B);
                 fb = (b == NEG) ? MV_SOFT : fb;
                 // K-MER SKIP: {-inf, prev M, -inf, prev B, prev K, -inf} of the same row
                 float kk = __fadd_rn(lp_mk, lm_cur);
                 int fk = MV_PREV_M;
-                fk = (kk == NEG) ? MV_SAME_B : fk;
                 vmax(kk, fk, __fadd_rn(lp_bk, lb_cur), MV_PREV_B);
                 vmax(kk, fk, __fadd_rn(lp_kk, lk_cur), MV_PREV_K);
                 fk = (kk == NEG) ? MV_SOFT : fk;

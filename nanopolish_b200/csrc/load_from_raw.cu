@@ -136,6 +136,7 @@ extern "C" int nph_load_from_raw_batch(nph_ctx* ctx, const float* raw, size_t n_
     float staged_ms = 0.0f, ms = 0.0f;          // device time of the stages, summed (each stage ends in a sync)
     std::vector<nph_raw_range> range(n_jobs);
     NPH_TRY(nph_trim_device(ctx, d_raw, n_samples_total, rr.data(), n_jobs, 200, 10, 100, 0.0f, arena, range.data())); ++launches;
+    ctx->h_last_trim = range;                   // for nph_last_trim_ranges (SRF_LOAD_RAW_SAMPLES keeps rt.raw[rt.start .. rt.end))
     NPH_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); staged_ms += ms;
     const bool verbose = getenv("NPH_TIMING") != nullptr;
     if (verbose) fprintf(stderr, "[nph] load_from_raw: trim %.2f ms", ms);
@@ -280,5 +281,13 @@ extern "C" int nph_load_from_raw_batch(nph_ctx* ctx, const float* raw, size_t n_
     ctx->last_launches = launches;
     ctx->staged_ms = staged_ms;
     ctx->timing_valid = 2;
+    return NPH_OK;
+}
+
+extern "C" int nph_last_trim_ranges(nph_ctx* ctx, nph_raw_range* ranges_out, size_t n_jobs)
+{
+    if (!ctx || !ranges_out) return NPH_ERR_INVALID;
+    if (n_jobs != ctx->h_last_trim.size()) return NPH_ERR_STATE;
+    std::copy(ctx->h_last_trim.begin(), ctx->h_last_trim.end(), ranges_out);
     return NPH_OK;
 }

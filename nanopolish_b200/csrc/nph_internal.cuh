@@ -125,6 +125,7 @@ struct nph_ctx {
     std::vector<DevRead> h_stage_reads;      // host staging that must outlive async copies
     std::vector<double> h_stage_drift;
     std::vector<float2> h_stage_trans;
+    std::vector<nph_raw_range> h_last_trim;  // surviving sample range per job of the last nph_load_from_raw_batch
 
 };
 

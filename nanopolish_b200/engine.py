@@ -228,6 +228,13 @@ class Engine:
         return off, mean[:tot], stdv[:tot], start[:tot], dur[:tot], b2e, cal
 
     # ---- measurement ----------------------------------------------------------------------
+    def last_trim_ranges(self, n_jobs: int) -> np.ndarray:
+        """[start, end) of the samples each job of the last load_from_raw_batch kept (what SRF_LOAD_RAW_SAMPLES stores)."""
+        from .synth import RAW_RANGE_DT
+        out = np.zeros(n_jobs, RAW_RANGE_DT)
+        self._check(self.lib.nph_last_trim_ranges(self.ctx, _p(out), n_jobs), "nph_last_trim_ranges")
+        return out
+
     def sync(self):
         self._check(self.lib.nph_sync(self.ctx), "nph_sync")
 

@@ -637,7 +637,10 @@ std::string EventAligner::tsv_header(const EventalignOptions& opt)
 {
     std::string h = "contig\tposition\treference_kmer\t";
     h += opt.print_read_names ? "read_name" : "read_index";
-    h += "\tstrand\tevent_index\tevent_level_mean\tevent_stdv\tevent_length\tmodel_kmer\tmodel_mean\tmodel_stdv\tstandardized_level\n";
+    h += "\tstrand\tevent_index\tevent_level_mean\tevent_stdv\tevent_length\tmodel_kmer\tmodel_mean\tmodel_stdv\tstandardized_level";
+    if (opt.write_signal_index) h += "\tstart_idx\tend_idx";
+    if (opt.write_samples) h += "\tsamples";
+    h += "\n";
     return h;
 }
 
@@ -652,8 +655,19 @@ std::string EventAligner::tsv(size_t read_idx, const EventalignOptions& opt) con
     // the read column: read_idx as %zu, or the read name with -n
     const std::string who_s = opt.print_read_names ? sr.read_name : std::to_string((size_t)rs.params.read_idx);
     const double sqrt_var = std::sqrt(sr.scalings[strand].var);
+    if ((opt.write_signal_index || opt.write_samples) && sr.samples.empty())
+        throw Error(NPH_ERR_STATE, "--signal-index / --samples need the raw samples on the read (load_from_raw with SRF_LOAD_RAW_SAMPLES)");
+    // room per row: six numbers of at most 47 characters; with the sample columns, 16 characters per raw sample of the
+    // events written (%g, six significant digits) + two indices
+    size_t extra = 0;
+    if (opt.write_signal_index) extra += 48 * rs.output.size();
+    if (opt.write_samples)
+        for (const Rec& r : rs.output) {
+            const std::pair<size_t, size_t> si = sr.get_event_sample_idx(strand, r.event_idx);
+            extra += 2 + 16 * (si.second > si.first ? si.second - si.first : 0);
+        }
     std::string out;
-    out.resize(rs.output.size() * (ref_name.size() + who_s.size() + 2 * (size_t)k + 340));    // six numbers of at most 47 characters
+    out.resize(rs.output.size() * (ref_name.size() + who_s.size() + 2 * (size_t)k + 340) + extra);
     char* const base = &out[0];
     char* o = base;
     char ref_kmer[64], model_kmer[64];
@@ -696,6 +710,20 @@ std::string EventAligner::tsv(size_t read_idx, const EventalignOptions& opt) con
         o += format_fixed(o, model_mean, 2); *o++ = '\t';
         o += format_fixed(o, model_stdv, 2); *o++ = '\t';
         o += format_fixed(o, standard_level, 2);
+        if (opt.write_signal_index) {
+            const std::pair<size_t, size_t> si = sr.get_event_sample_idx(strand, r.event_idx);
+            *o++ = '\t'; o = put_int(o, (long long)si.first); *o++ = '\t'; o = put_int(o, (long long)si.second);
+        }
+        if (opt.write_samples) {
+            // the reference streams the floats through an ostream (%g, 6 significant digits) with ',' after each and
+            // drops the last comma (an event without samples makes it resize() to npos and throw; here: an empty column)
+            const std::vector<float> samples = sr.get_scaled_samples_for_event(strand, r.event_idx);
+            *o++ = '\t';
+            for (size_t i = 0; i < samples.size(); ++i) {
+                if (i) *o++ = ',';
+                o += snprintf(o, 32, "%g", (double)samples[i]);
+            }
+        }
         *o++ = '\n';
     }
     out.resize((size_t)(o - base));

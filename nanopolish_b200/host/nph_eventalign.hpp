@@ -119,6 +119,8 @@ struct EventalignSummary {
 struct EventalignOptions {               // the reference's command-line switches that change the output
     bool print_read_names = false;       // -n
     bool scale_events = false;           // --scale-events
+    bool write_signal_index = false;     // --signal-index: the event's [start, end) raw sample indices
+    bool write_samples = false;          // --samples: the event's scaled raw samples (both need SquiggleRead::samples)
 };
 
 class EventAligner {

@@ -210,6 +210,30 @@ public:
         const int event_after = get_next_event(k_idx, stop_after, 1, strand);
         return event_before == -1 ? event_after : event_before;
     }
+    // ref: src/nanopolish_squiggle_read.cpp:393-428
+    size_t get_sample_index_at_time(size_t sample_time) const { return sample_time - sample_start_time; }
+    std::pair<size_t, size_t> get_event_sample_idx(size_t strand_idx, size_t event_idx) const
+    {
+        const double event_start_time = events[strand_idx][event_idx].start_time;
+        const double event_duration = events[strand_idx][event_idx].duration;
+        const size_t start_idx = get_sample_index_at_time((size_t)(event_start_time * sample_rate));
+        const size_t end_idx = get_sample_index_at_time((size_t)((event_start_time + event_duration) * sample_rate));
+        return std::make_pair(start_idx, end_idx);
+    }
+    std::vector<float> get_scaled_samples_for_event(size_t strand_idx, size_t event_idx) const
+    {
+        const std::pair<size_t, size_t> sample_range = get_event_sample_idx(strand_idx, event_idx);
+        std::vector<float> out;
+        for (size_t i = sample_range.first; i < sample_range.second; ++i) {
+            const double curr_sample_time = (sample_start_time + i) / sample_rate;
+            const double s = samples.at(i);
+            double scaled_s = s - scalings[strand_idx].shift;
+            scaled_s -= (curr_sample_time - (sample_start_time / sample_rate)) * scalings[strand_idx].drift;
+            scaled_s /= scalings[strand_idx].scale;
+            out.push_back((float)scaled_s);
+        }
+        return out;
+    }
     bool has_events_for_strand(size_t strand_idx) const { return !events[strand_idx].empty(); }
     size_t get_model_k(uint32_t strand) const { return base_model[strand]->k; }
     const PoreModel* get_base_model(uint32_t strand) const { return base_model[strand]; }
@@ -234,6 +258,8 @@ public:
     double events_per_base[2];
     std::vector<EventRangeForBase> base_to_event_map;       // filled by nph::load_from_raw (nph_raw.hpp)
     double sample_rate = 0.0;
+    uint64_t sample_start_time = 0;                          // 0 once the raw samples are kept (squiggle_read.cpp:252)
+    std::vector<float> samples;                              // the trimmed raw samples, kept on request (SRF_LOAD_RAW_SAMPLES)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -322,6 +322,17 @@ int nphh_read_set_eventalign(int read, const char* read_name, const char* read_s
     });
 }
 
+// the raw samples load_from_raw keeps with SRF_LOAD_RAW_SAMPLES
+int nphh_read_set_samples(int read, const float* samples, size_t n, double sample_rate)
+{
+    return guard([&] {
+        SquiggleRead& sr = *g_reads[read];
+        sr.samples.assign(samples, samples + n);
+        sr.sample_start_time = 0;
+        sr.sample_rate = sample_rate;
+    });
+}
+
 void nphh_ea_begin() { g_aligner.clear(); g_round_batch.clear(); }
 
 int nphh_ea_add_read(int read, const char* ref_name, int ref_pos, int flag, int mapq, const uint32_t* cigar, int n_cigar, const char* ref_seq,
@@ -388,7 +399,7 @@ int nphh_ea_consume(size_t n_jobs, const uint64_t* state_off, const nph_align_st
 }
 
 // what: 0 = TSV rows, 1 = TSV rows with read names, 2 = TSV rows with --scale-events, 3 = SAM line, 4 = event CIGAR, 5 = summary row,
-// 6 = TSV header
+// 6 = TSV header, 7 = header + rows with --signal-index --samples
 long long nphh_ea_text(int idx, int what, char* out, size_t cap)
 {
     long long n = -1;
@@ -403,6 +414,7 @@ long long nphh_ea_text(int idx, int what, char* out, size_t cap)
             case 4: s = g_aligner.event_cigar(idx); break;
             case 5: s = g_aligner.summary_row(idx, "read.fast5"); break;
             case 6: s = EventAligner::tsv_header(opt); break;
+            case 7: opt.write_signal_index = true; opt.write_samples = true; s = EventAligner::tsv_header(opt) + g_aligner.tsv(idx, opt); break;
             default: throw Error(NPH_ERR_INVALID, "unknown text kind");
         }
         if (s.size() + 1 > cap) throw Error(NPH_ERR_INVALID, "text buffer too small");

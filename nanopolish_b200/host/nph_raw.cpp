@@ -64,7 +64,7 @@ nph_raw_range trim_and_segment_raw(Engine& engine, const std::vector<float>& sam
 }
 
 std::vector<std::unique_ptr<SquiggleRead>> load_from_raw(Engine& engine, const PoreModel& base_model, const std::vector<RawRead>& raw,
-                                                         LoadFromRawStats* stats)
+                                                         LoadFromRawStats* stats, uint32_t flags)
 {
     const size_t n = raw.size();
     LoadFromRawStats st;
@@ -117,6 +117,15 @@ std::vector<std::unique_ptr<SquiggleRead>> load_from_raw(Engine& engine, const P
                                          start.data(), dur.data(), cap, b2e.data(), cal.data()),
                  "nph_load_from_raw_batch");
 
+    if (flags & SRF_LOAD_RAW_SAMPLES) {         // squiggle_read.cpp:251-258, before any of the read's QC
+        std::vector<nph_raw_range> kept(sent.size());
+        engine.check(nph_last_trim_ranges(engine.ctx(), kept.data(), kept.size()), "nph_last_trim_ranges");
+        for (size_t t = 0; t < sent.size(); ++t) {
+            SquiggleRead& sr = *reads[sent[t]];
+            sr.sample_start_time = 0;
+            sr.samples.assign(raw[sent[t]].samples.begin() + kept[t].start, raw[sent[t]].samples.begin() + kept[t].end);
+        }
+    }
     for (size_t t = 0; t < sent.size(); ++t) {
         SquiggleRead& sr = *reads[sent[t]];
         const nph_calibration& c = cal[t];

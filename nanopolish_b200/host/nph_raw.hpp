@@ -35,8 +35,10 @@ struct LoadFromRawStats {
 // load_from_raw leaves them; a read that fails a QC step has its events cleared, exactly like the reference.
 // A signal that trims to nothing aborts the reference (assert et.n > 0); here it yields a read without events and is
 // counted in empty_after_trim.
+enum SquiggleReadFlags { SRF_NO_MODEL = 1, SRF_LOAD_RAW_SAMPLES = 2 };     // ref: src/nanopolish_squiggle_read.h:46-50
+// flags & SRF_LOAD_RAW_SAMPLES: keep the trimmed samples on the read (eventalign --samples / --signal-index)
 std::vector<std::unique_ptr<SquiggleRead>> load_from_raw(Engine& engine, const PoreModel& base_model, const std::vector<RawRead>& raw,
-                                                         LoadFromRawStats* stats = nullptr);
+                                                         LoadFromRawStats* stats = nullptr, uint32_t flags = 0);
 
 // scrappie's detect_events / trim_and_segment_raw for one signal (batch of one; the building blocks above)
 std::vector<nph_event> detect_events(Engine& engine, const std::vector<float>& samples, const nph_event_params& params);

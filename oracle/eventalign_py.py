@@ -220,7 +220,27 @@ def _f(x):
     return float(x)
 
 
-def tsv(read: EARead, alignment, print_read_names=False, scale_events=False) -> str:
+def event_sample_idx(read: EARead, e, sample_rate):
+    """SquiggleRead::get_event_sample_idx with sample_start_time = 0 (src/nanopolish_squiggle_read.cpp:393-428)"""
+    start = np.float64(read.start_time[e])
+    dur = np.float64(np.float32(read.duration[e]))
+    return int(start * sample_rate), int((start + dur) * sample_rate)
+
+
+def scaled_samples(read: EARead, e, samples, sample_rate):
+    a, b = event_sample_idx(read, e, sample_rate)
+    out = []
+    for i in range(a, b):
+        t = i / sample_rate
+        s = np.float64(samples[i]) - read.shift
+        s -= (t - 0.0 / sample_rate) * read.drift
+        s /= read.scale
+        out.append(np.float32(s))
+    return out
+
+
+def tsv(read: EARead, alignment, print_read_names=False, scale_events=False, samples=None, sample_rate=4000.0) -> str:
+    """samples: the read's raw samples -> the --signal-index and --samples columns are appended"""
     rows = []
     sqrt_var = np.sqrt(np.float64(read.var))
     for ea in alignment:
@@ -238,9 +258,13 @@ def tsv(read: EARead, alignment, print_read_names=False, scale_events=False) -> 
         with np.errstate(divide="ignore", invalid="ignore"):
             standard_level = np.float32(np.float64(np.float32(event_mean - model_mean)) / (sqrt_var * np.float64(model_stdv)))
         who = read.name if print_read_names else "%d" % ea.read_idx
-        rows.append("%s\t%d\t%s\t%s\t%s\t%d\t%.2f\t%.3f\t%.5f\t%s\t%.2f\t%.2f\t%.2f\n" % (
+        row = "%s\t%d\t%s\t%s\t%s\t%d\t%.2f\t%.3f\t%.5f\t%s\t%.2f\t%.2f\t%.2f" % (
             ea.ref_name, ea.ref_position, ea.ref_kmer, who, "tc"[ea.strand_idx], ea.event_idx, _f(event_mean), _f(event_stdv),
-            _f(event_duration), ea.model_kmer, _f(model_mean), _f(model_stdv), _f(standard_level)))
+            _f(event_duration), ea.model_kmer, _f(model_mean), _f(model_stdv), _f(standard_level))
+        if samples is not None:
+            a, b = event_sample_idx(read, ea.event_idx, sample_rate)
+            row += "\t%d\t%d\t%s" % (a, b, ",".join("%g" % float(v) for v in scaled_samples(read, ea.event_idx, samples, sample_rate)))
+        rows.append(row + "\n")
     return "".join(rows)
 
 

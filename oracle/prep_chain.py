@@ -22,6 +22,7 @@ def oracle_chain(port, model, signals, seqs, sample_rate=4000.0, rna=False):
         r = {"events": None}
         ok, s, e = port.trim_raw(x)
         out.append(r)
+        r["range"] = (s, e) if ok else (0, 0)
         if not ok:
             continue
         ev = port.detect_events(np.ascontiguousarray(x[s:e]), prm)

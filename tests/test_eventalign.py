@@ -104,14 +104,21 @@ def _setup(host, cases):
         a, b = np.ascontiguousarray(r.b2e_start, np.int32), np.ascontiguousarray(c["b2e_stop"], np.int32)
         assert host.nphh_read_set_eventalign(rh[slot], r.name.encode(), r.read_sequence.encode(), _p(a), _p(b), C.c_size_t(a.shape[0]),
                                              _p(np.ascontiguousarray(r.stdv)), _p(np.ascontiguousarray(r.duration))) == 0
+        smp = _raw_samples(slot)
+        assert host.nphh_read_set_samples(rh[slot], _p(smp), C.c_size_t(smp.shape[0]), C.c_double(4000.0)) == 0
         idx = host.nphh_ea_add_read(rh[slot], c["contig_name"].encode(), c["ref_pos"], c["flag"], c["mapq"], _p(c["cigar"]),
                                     int(c["cigar"].shape[0]), c["fetched"].encode(), c["read_idx"], c["region"][0], c["region"][1])
         assert idx == c["read_idx"], host.nphh_last_error()
 
 
+def _raw_samples(slot):
+    """stand-in for the trimmed raw samples SRF_LOAD_RAW_SAMPLES keeps: enough of them to cover every event's time span"""
+    return np.random.default_rng(900 + slot).normal(90.0, 12.0, 420_000).astype(np.float32)
+
+
 def _text(host, idx, what):
-    buf = C.create_string_buffer(1 << 21)
-    n = host.nphh_ea_text(idx, what, buf, C.c_size_t(1 << 21))
+    buf = C.create_string_buffer(1 << 23)
+    n = host.nphh_ea_text(idx, what, buf, C.c_size_t(1 << 23))
     assert n >= 0, host.nphh_last_error()
     return buf.value.decode()
 
@@ -123,6 +130,8 @@ def _check_outputs(host, cases, restated, golden):
         assert _text(host, i, 0) == golden[f"tsv_{i}"]                                     # the compiled reference's bytes
         assert _text(host, i, 1) == EP.tsv(r, al, print_read_names=True)                   # -n
         assert _text(host, i, 2) == EP.tsv(r, al, scale_events=True)                       # --scale-events
+        hdr = _text(host, 0, 6)[:-1] + "\tstart_idx\tend_idx\tsamples\n"
+        assert _text(host, i, 7) == hdr + EP.tsv(r, al, samples=_raw_samples(EC.read_slot(c, rs.n_reads)), sample_rate=4000.0)   # --signal-index --samples
         assert host.nphh_ea_num_segments(i) == segs
         assert _text(host, i, 5) == EP.summary_row(r, al, i, "read.fast5").replace(r.model_name, "")   # host test models carry no name
         if _single_segment(c):

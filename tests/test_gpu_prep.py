@@ -202,6 +202,11 @@ def test_load_from_raw_in_one_call(engine, nuc, port_oracle):
         assert np.array_equal(b2e[int(jobs[i]["rank_off"]):][:int(jobs[i]["n_kmers"])], w["b2e"])
         kinds.add(int(w["cal"]["status"]))
     assert {"trim", 0, 1} <= kinds
+    # the sample range each read kept (what SRF_LOAD_RAW_SAMPLES stores; eventalign --samples reads it back)
+    kept = engine.last_trim_ranges(len(want))
+    assert [(int(a), int(b)) for a, b in zip(kept["start"], kept["end"])] == [w["range"] for w in want]
+    with pytest.raises(NphError):
+        engine.last_trim_ranges(len(want) + 1)
     ms, launches = engine.last_kernel_ms()
     assert ms > 0 and launches >= 9
     # capacity too small for the events is reported, not overrun
