@@ -17,6 +17,7 @@ std::vector<std::unique_ptr<SquiggleRead>> g_reads;
 EventAligner g_aligner;
 AlignBatch g_round_batch;
 bool g_raw_is_rna = false;
+uint32_t g_load_flags = 0;
 thread_local std::string g_err;
 template <typename F> int guard(F f) { try { f(); return 0; } catch (const Error& e) { g_err = e.what(); return e.status; } catch (const std::exception& e) { g_err = e.what(); return NPH_ERR_INVALID; } }
 }
@@ -108,6 +109,9 @@ void nphh_read_add_model(int read, const char* alphabet, int model) { g_reads[re
 void nphh_clear() { g_reads.clear(); }
 void nphh_set_indel_bias(double v) { hmm_indel_bias_factor = v; }
 void nphh_set_rna(int rna) { g_raw_is_rna = rna != 0; }        // nucleotide type of the reads nphh_load_from_raw builds
+void nphh_set_load_flags(uint32_t flags) { g_load_flags = flags; }   // SquiggleReadFlags for nphh_load_from_raw
+long long nphh_read_num_samples(int read) { return (long long)g_reads[read]->samples.size(); }
+float nphh_read_sample(int read, size_t i) { return g_reads[read]->samples.at(i); }
 
 // profile_hmm_score(sequence, data, flags) exactly as a nanopolish caller writes it
 int nphh_profile_hmm_score(int read, int model, const char* seq, uint32_t e_start, uint32_t e_stop, int rc, uint32_t flags, float* out)
@@ -284,7 +288,7 @@ int nphh_load_from_raw(int model, int n, const float* samples, const uint64_t* s
             raw[i].nucleotide_type = g_raw_is_rna ? SRNT_RNA : SRNT_DNA;
         }
         LoadFromRawStats st;
-        std::vector<std::unique_ptr<SquiggleRead>> rs = load_from_raw(Engine::thread_default(), *g_models[model], raw, &st);
+        std::vector<std::unique_ptr<SquiggleRead>> rs = load_from_raw(Engine::thread_default(), *g_models[model], raw, &st, g_load_flags);
         stats5[0] = st.total; stats5[1] = st.empty_after_trim; stats5[2] = st.failed_alignment; stats5[3] = st.failed_calibration; stats5[4] = st.qc_fail;
         first = (int)g_reads.size();
         for (int i = 0; i < n; ++i) {

@@ -246,9 +246,20 @@ def test_load_from_raw_like_a_caller(host, port_oracle):
     b2e = np.full((int(qoff[-1]), 2), -7, np.int32)
     flat = np.concatenate(signals)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = host.nphh_load_from_raw(mh, n, p(flat), p(soff), seqbuf, p(qoff), C.c_double(4000.0), p(n_events), p(scal), p(eoff), p(mean), p(stdv),
-                                 p(start), p(dur), p(b2e), p(stats))
+    host.nphh_set_load_flags(2)                                 # SRF_LOAD_RAW_SAMPLES: keep the trimmed samples on every read
+    try:
+        rc = host.nphh_load_from_raw(mh, n, p(flat), p(soff), seqbuf, p(qoff), C.c_double(4000.0), p(n_events), p(scal), p(eoff), p(mean), p(stdv),
+                                     p(start), p(dur), p(b2e), p(stats))
+    finally:
+        host.nphh_set_load_flags(0)
     assert rc >= 0, host.nphh_last_error()
+    host.nphh_read_num_samples.restype = C.c_longlong
+    host.nphh_read_sample.restype = C.c_float
+    for i in range(n):                                          # samples[i] = rt.raw[rt.start + i] (squiggle_read.cpp:251-258)
+        s0, s1 = want[i]["range"]
+        assert host.nphh_read_num_samples(rc + i) == s1 - s0
+        if s1 > s0:
+            assert host.nphh_read_sample(rc + i, C.c_size_t(0)) == signals[i][s0] and host.nphh_read_sample(rc + i, C.c_size_t(s1 - s0 - 1)) == signals[i][s1 - 1]
     dropped = 0
     for i in range(n):
         w = want[i]
