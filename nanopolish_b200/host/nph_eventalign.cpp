@@ -43,7 +43,7 @@ size_t AlignBatch::add(const HMMInputSequence& sequence, const HMMInputData& dat
     j.rc = data.rc;
     j.flags = (uint8_t)flags;
     j.reserved = 0;
-    for (uint32_t ki = 0; ki < n_kmers; ++ki) m_ranks.push_back(sequence.get_kmer_rank(ki, k, data.rc != 0));
+    sequence.append_kmer_ranks(k, data.rc != 0, m_ranks);
     m_jobs.push_back(j);
     m_job_models.push_back(data.pore_model);
     return m_jobs.size() - 1;

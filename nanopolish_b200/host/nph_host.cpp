@@ -75,8 +75,9 @@ Alphabet::Match Alphabet::match_to_site(const std::string& str, size_t i, const 
 {
     Match m;
     const size_t rl = recognition_length();
-    const char* p = std::strstr(site.c_str(), str.c_str());
-    if (i == 0 && p != nullptr) {
+    // case (1) needs the whole string inside the site: only strings no longer than the site can qualify, and only at i == 0
+    const char* p = (i == 0 && str.length() <= site.length()) ? std::strstr(site.c_str(), str.c_str()) : nullptr;
+    if (p != nullptr) {
         m.offset = (unsigned)(p - site.c_str());
         m.length = (unsigned)str.length();
     } else {
@@ -87,7 +88,7 @@ Alphabet::Match Alphabet::match_to_site(const std::string& str, size_t i, const 
         }
     }
     if (m.length > 0)
-        m.covers_methylated_site = str.substr(i, m.length).find_first_of(METHYLATED_SYMBOL) != std::string::npos;
+        m.covers_methylated_site = std::memchr(str.data() + i, METHYLATED_SYMBOL, m.length) != nullptr;
     return m;
 }
 
@@ -99,7 +100,10 @@ std::string Alphabet::reverse_complement(const std::string& str) const
     while (i < str.length()) {
         int site = -1;
         Match m;
+        // past position 0 a site can only match where its first symbol stands (match_to_site's case 2 compares from the
+        // site's start); at position 0 a string lying inside a site also counts, so the matcher always runs there
         for (size_t s = 0; s < num_recognition_sites(); ++s) {
+            if (i > 0 && str[i] != m_sites_m[s][0]) continue;
             m = match_to_site(str, i, m_sites_m[s]);
             if (m.length > 0 && m.covers_methylated_site) { site = (int)s; break; }
         }
@@ -152,6 +156,7 @@ std::string Alphabet::methylate(const std::string& str) const
     while (i < out.length()) {
         size_t stride = 1;
         for (size_t s = 0; s < num_recognition_sites(); ++s) {
+            if (i > 0 && str[i] != m_sites[s][0]) continue;          // see reverse_complement
             Match m = match_to_site(str, i, m_sites[s]);
             if (m.length == recognition_length()) {     // only complete sites are methylated
                 out.replace(i, recognition_length(), m_sites_m[s]);
@@ -171,6 +176,7 @@ std::string Alphabet::unmethylate(const std::string& str) const
     while (i < out.length()) {
         size_t stride = 1;
         for (size_t s = 0; s < num_recognition_sites(); ++s) {
+            if (i > 0 && str[i] != m_sites_m[s][0]) continue;        // see reverse_complement
             Match m = match_to_site(str, i, m_sites_m[s]);
             if (m.length > 0) {
                 out.replace(i, m.length, m_sites[s].c_str() + m.offset, m.length);
@@ -186,6 +192,7 @@ std::string Alphabet::unmethylate(const std::string& str) const
 bool Alphabet::is_motif_match(const std::string& str, size_t i) const
 {
     for (size_t s = 0; s < num_recognition_sites(); ++s) {
+        if (i > 0 && str[i] != m_sites[s][0]) continue;              // see reverse_complement
         Match m = match_to_site(str, i, m_sites[s]);
         if (m.length == recognition_length()) return true;
     }
@@ -333,10 +340,50 @@ size_t HmmBatch::add(const HMMInputSequence& sequence, const HMMInputData& data,
     j.rc = data.rc;
     j.flags = (uint8_t)flags;
     j.reserved = 0;
-    for (uint32_t ki = 0; ki < n_kmers; ++ki) m_ranks.push_back(sequence.get_kmer_rank(ki, k, data.rc != 0));
+    sequence.append_kmer_ranks(k, data.rc != 0, m_ranks);
     m_jobs.push_back(j);
     m_job_models.push_back(data.pore_model);
     return m_jobs.size() - 1;
+}
+
+// rank(i + 1) = (rank(i) mod A^(k-1)) * A + rank(next base); with do_rc the i-th rank is that of the rc string's k-mer at
+// length - i - k, i.e. the rc string's ranks read back to front
+void HMMInputSequence::append_kmer_ranks(uint32_t k, bool do_rc, std::vector<uint32_t>& out) const
+{
+    const std::string& s = do_rc ? m_rc_seq : m_seq;
+    const size_t len = s.size();
+    if (len < k) return;
+    const size_t n = len - k + 1, base = out.size();
+    out.resize(base + n);
+    const uint64_t A = m_alphabet->size();
+    uint64_t top = 1;
+    for (uint32_t i = 1; i < k; ++i) top *= A;
+    uint64_t r = 0;
+    for (uint32_t i = 0; i < k; ++i) r = r * A + m_alphabet->rank(s[i]);
+    for (size_t pos = 0;; ++pos) {
+        out[base + (do_rc ? n - 1 - pos : pos)] = (uint32_t)r;
+        if (pos + 1 == n) break;
+        r = (r % top) * A + m_alphabet->rank(s[pos + k]);
+    }
+}
+
+void HmmBatch::append(HmmBatch&& other)
+{
+    const uint64_t rank_base = m_ranks.size();
+    std::vector<uint32_t> remap(other.m_reads.size());
+    for (size_t i = 0; i < other.m_reads.size(); ++i) {
+        auto it = m_read_index.find(other.m_reads[i]);
+        if (it == m_read_index.end()) {
+            it = m_read_index.insert({other.m_reads[i], (uint32_t)m_reads.size()}).first;
+            m_reads.push_back(other.m_reads[i]);
+        }
+        remap[i] = it->second;
+    }
+    m_jobs.reserve(m_jobs.size() + other.m_jobs.size());
+    for (nph_hmm_job j : other.m_jobs) { j.read = remap[j.read]; j.rank_off += rank_base; m_jobs.push_back(j); }
+    m_ranks.insert(m_ranks.end(), other.m_ranks.begin(), other.m_ranks.end());
+    m_job_models.insert(m_job_models.end(), other.m_job_models.begin(), other.m_job_models.end());
+    other.clear();
 }
 
 void HmmBatch::clear()
@@ -348,7 +395,12 @@ std::vector<float> HmmBatch::run(Engine& engine, double indel_bias)
 {
     std::vector<float> scores(m_jobs.size());
     if (m_jobs.empty()) return scores;
-    for (size_t j = 0; j < m_jobs.size(); ++j) m_jobs[j].model_id = engine.model_id(m_job_models[j]);
+    const PoreModel* last_model = nullptr;
+    uint32_t last_id = 0;
+    for (size_t j = 0; j < m_jobs.size(); ++j) {
+        if (m_job_models[j] != last_model) { last_model = m_job_models[j]; last_id = engine.model_id(last_model); }
+        m_jobs[j].model_id = last_id;
+    }
     std::vector<std::pair<const SquiggleRead*, uint8_t>> rl;
     for (auto& r : m_reads) rl.push_back({r.read, r.strand});
     std::vector<nph_read> reads;

@@ -299,6 +299,9 @@ public:
                       : m_alphabet->kmer_rank(m_rc_seq.c_str() + (length() - i - k), k);
     }
 
+    // all n = length() - k + 1 ranks get_kmer_rank(0..n-1, k, do_rc) in one rolling pass (appended to out)
+    void append_kmer_ranks(uint32_t k, bool do_rc, std::vector<uint32_t>& out) const;
+
 private:
     const Alphabet* m_alphabet;
     std::string m_seq, m_rc_seq;
@@ -351,6 +354,11 @@ public:
     size_t size() const { return m_jobs.size(); }
     void clear();
     std::vector<float> run(Engine& engine, double indel_bias = hmm_indel_bias_factor);
+    // Move the jobs of `other` behind this batch's (job j of other becomes job size() + j); other is left empty.
+    // Lets worker threads enumerate into private batches and the owner splice them in a fixed order.
+    void append(HmmBatch&& other);
+    const std::vector<nph_hmm_job>& jobs() const { return m_jobs; }
+    const std::vector<uint32_t>& ranks() const { return m_ranks; }
 
 private:
     struct ReadKey { const SquiggleRead* read; uint8_t strand; bool operator<(const ReadKey& o) const { return read != o.read ? read < o.read : strand < o.strand; } };

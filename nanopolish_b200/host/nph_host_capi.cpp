@@ -6,6 +6,7 @@
 #include "nph_raw.hpp"
 #include "nph_eventalign.hpp"
 #include <cmath>
+#include <chrono>
 #include <cstring>
 #include <memory>
 
@@ -58,6 +59,21 @@ int nphh_lexicographic_next(const char* alphabet, const char* in, char* out)
     get_alphabet_by_name(alphabet)->lexicographic_next(s);
     std::memcpy(out, s.c_str(), s.size() + 1);
     return (int)s.size();
+}
+
+// HMMInputSequence::append_kmer_ranks (the rolling pass HmmBatch::add uses) against get_kmer_rank: mismatching positions
+int nphh_kmer_ranks_rolling_check(const char* alphabet, const char* seq, uint32_t k, int rc)
+{
+    int bad = -1;
+    int st = guard([&] {
+        HMMInputSequence hs(std::string(seq), get_alphabet_by_name(alphabet));
+        std::vector<uint32_t> r;
+        hs.append_kmer_ranks(k, rc != 0, r);
+        const size_t n = hs.length() >= k ? hs.length() - k + 1 : 0;
+        bad = r.size() == n ? 0 : 1;
+        for (size_t i = 0; i < std::min(n, r.size()); ++i) bad += r[i] != hs.get_kmer_rank((uint32_t)i, k, rc != 0);
+    });
+    return st ? st : bad;
 }
 
 // HMMInputSequence::get_kmer_rank for ki = 0..n-1
@@ -245,6 +261,7 @@ long long nphh_call_methylation(int n_reads, const int32_t* read, const char** r
     int st = guard([&] {
         MethylationCallingParameters params;
         MethylationCaller caller(params);
+        std::vector<EventAlignedRead> batch_reads;
         for (int i = 0; i < n_reads; ++i) {
             EventAlignedRead r;
             r.read = g_reads[read[i]].get();
@@ -255,8 +272,9 @@ long long nphh_call_methylation(int n_reads, const int32_t* read, const char** r
             r.ref_seq = ref_seqs[i];
             for (uint64_t p = pair_off[i]; p < pair_off[i + 1]; ++p) r.aligned_events[0].push_back(AlignedPair{pairs[2 * p], pairs[2 * p + 1]});
             r.rc[0] = rc[i];
-            caller.add_read(r);
+            batch_reads.push_back(std::move(r));
         }
+        caller.add_reads(batch_reads);
         *n_jobs_out = caller.num_jobs();
         caller.run(Engine::thread_default(), indel_bias);
         std::string all;
@@ -266,6 +284,45 @@ long long nphh_call_methylation(int n_reads, const int32_t* read, const char** r
         n = (long long)all.size();
     });
     return st ? st : n;
+}
+
+// enumeration only (no device): seconds spent in MethylationCaller::add_read over all reads, and the job count
+// parallel != 0: MethylationCaller::add_reads (host_threads() workers); jobs_out / ranks_out (optional) receive the job list
+double nphh_methylation_enumerate_seconds(int n_reads, const int32_t* read, const char** read_names, const uint8_t* is_rev, const uint8_t* rc,
+                                          const int32_t* ref_start, const char** ref_seqs, const int32_t* pairs, const uint64_t* pair_off,
+                                          const char* contig, uint64_t* n_jobs_out, int parallel, void* jobs_out, size_t cap_jobs,
+                                          uint32_t* ranks_out, size_t cap_ranks, uint64_t* n_ranks_out)
+{
+    double secs = -1.0;
+    guard([&] {
+        MethylationCallingParameters params;
+        MethylationCaller caller(params);
+        std::vector<EventAlignedRead> rs(n_reads);
+        for (int i = 0; i < n_reads; ++i) {
+            EventAlignedRead& r = rs[i];
+            r.read = g_reads[read[i]].get();
+            r.read_name = read_names[i];
+            r.is_reverse = is_rev[i];
+            r.contig = contig;
+            r.ref_start_pos = ref_start[i];
+            r.ref_seq = ref_seqs[i];
+            for (uint64_t p = pair_off[i]; p < pair_off[i + 1]; ++p) r.aligned_events[0].push_back(AlignedPair{pairs[2 * p], pairs[2 * p + 1]});
+            r.rc[0] = rc[i];
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        if (parallel) caller.add_reads(rs);
+        else for (int i = 0; i < n_reads; ++i) caller.add_read(rs[i]);
+        secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        *n_jobs_out = caller.num_jobs();
+        if (jobs_out && ranks_out) {
+            const HmmBatch& b = caller.batch();
+            if (b.jobs().size() > cap_jobs || b.ranks().size() > cap_ranks) throw Error(NPH_ERR_INVALID, "dump buffers too small");
+            std::memcpy(jobs_out, b.jobs().data(), sizeof(nph_hmm_job) * b.jobs().size());
+            std::memcpy(ranks_out, b.ranks().data(), sizeof(uint32_t) * b.ranks().size());
+            *n_ranks_out = b.ranks().size();
+        }
+    });
+    return secs;
 }
 
 // ---- N4: load_from_raw over a batch -----------------------------------------------------------

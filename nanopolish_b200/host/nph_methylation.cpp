@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <memory>
 
 namespace nph {
 
@@ -52,9 +53,13 @@ size_t MethylationCaller::add_read(const EventAlignedRead& r, int region_start, 
         const std::vector<AlignedPair>& aligned_events = r.aligned_events[strand_idx];
 
         // scan for motifs, then batch them into groups separated by more than min_separation
+        // (a site can only start where its first symbol stands — position 0 aside, where the reference's matcher also
+        // accepts a string that lies wholly inside a site — so the full matcher runs on those positions only)
+        bool first_symbol[256] = {false};
+        for (size_t s = 0; s < alphabet->num_recognition_sites(); ++s) first_symbol[(unsigned char)alphabet->get_recognition_site(s)[0]] = true;
         std::vector<int> motif_sites;
         for (size_t i = 0; i + 1 < ref_seq.size(); ++i)
-            if (alphabet->is_motif_match(ref_seq, i)) motif_sites.push_back((int)i);
+            if ((i == 0 || first_symbol[(unsigned char)ref_seq[i]]) && alphabet->is_motif_match(ref_seq, i)) motif_sites.push_back((int)i);
         std::vector<std::pair<size_t, size_t>> groups;
         size_t curr_idx = 0;
         while (curr_idx < motif_sites.size()) {
@@ -123,6 +128,37 @@ size_t MethylationCaller::add_read(const EventAlignedRead& r, int region_start, 
         }
     }
     return read_idx;
+}
+
+size_t MethylationCaller::add_reads(const std::vector<EventAlignedRead>& reads, int region_start, int region_end)
+{
+    const size_t first = m_reads.size();
+    const size_t n = reads.size();
+    const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), (n + 15) / 16));
+    if (T == 1) {
+        for (const EventAlignedRead& r : reads) add_read(r, region_start, region_end);
+        return first;
+    }
+    // contiguous blocks of reads per worker: splicing the workers' lists in worker order reproduces the sequential order
+    std::vector<std::unique_ptr<MethylationCaller>> locals((size_t)T);     // separately allocated: no false sharing of their cursors
+    for (auto& l : locals) l.reset(new MethylationCaller(m_params));
+    std::vector<std::string> errors((size_t)T);
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; ++t) {
+        const size_t b = n * (size_t)t / (size_t)T, e = n * ((size_t)t + 1) / (size_t)T;
+        try {
+            for (size_t i = b; i < e; ++i) locals[t]->add_read(reads[i], region_start, region_end);
+        } catch (const std::exception& ex) { errors[t] = ex.what(); }
+    }
+    for (const std::string& e : errors) if (!e.empty()) throw Error(NPH_ERR_INVALID, e);
+    for (int t = 0; t < T; ++t) {
+        MethylationCaller& l = *locals[t];
+        const size_t read_base = m_reads.size(), job_base = m_batch.size();
+        for (Pending p : l.m_pending) { p.read += read_base; p.job_u += job_base; p.job_m += job_base; m_pending.push_back(p); }
+        for (ReadEntry& re : l.m_reads) m_reads.push_back(std::move(re));
+        m_batch.append(std::move(l.m_batch));
+    }
+    return first;
 }
 
 void MethylationCaller::run(Engine& engine, double indel_bias)

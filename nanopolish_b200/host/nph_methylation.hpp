@@ -58,10 +58,15 @@ public:
     // enumerate the read's motif groups and queue their jobs; returns the read's index in this batch.
     // region_start/region_end = -1 for no window restriction (the reference's -w option).
     size_t add_read(const EventAlignedRead& r, int region_start = -1, int region_end = -1);
+    // The same for a whole BamProcessor batch, enumerated by host_threads() workers into private job lists that are
+    // spliced in read order (so job order, scores and output equal add_read called read by read).  Returns the index of
+    // the first read.  The reference runs this enumeration inside its per-read OpenMP loop too.
+    size_t add_reads(const std::vector<EventAlignedRead>& reads, int region_start = -1, int region_end = -1);
     void run(Engine& engine, double indel_bias = hmm_indel_bias_factor);       // one launch for every queued group
     const std::map<int, ScoredSite>& sites(size_t read_idx) const { return m_reads[read_idx].sites; }
     size_t num_reads() const { return m_reads.size(); }
     size_t num_jobs() const { return m_batch.size(); }
+    const HmmBatch& batch() const { return m_batch; }      // the queued jobs (read-only; for inspection and tests)
     void write_tsv(FILE* fp, size_t read_idx) const;
     std::string tsv(size_t read_idx) const;
     void clear();
