@@ -578,49 +578,6 @@ size_t EventAligner::run(Engine& engine, double indel_bias)
 // ---------------------------------------------------------------------------------------------
 // writers
 // ---------------------------------------------------------------------------------------------
-// printf("%.<prec>lf", (double)v) for a float v, prec <= 5, without going through the C library's arbitrary-precision
-// path: v = m * 2^e exactly with m < 2^24, so v * 10^prec = (m * 10^prec) * 2^e fits 64-bit integer arithmetic with an
-// exact remainder, and round-half-to-even on it is the decimal string glibc prints (it rounds the exact value, in the
-// default rounding mode).  Magnitudes of 2^39 and above and non-finite values take snprintf.  Returns the length.
-size_t format_fixed(char* dst, float v, int prec)
-{
-    static const uint64_t pow10[6] = {1, 10, 100, 1000, 10000, 100000};
-    uint32_t bits;
-    std::memcpy(&bits, &v, 4);
-    const uint32_t expo = (bits >> 23) & 0xff;
-    if (expo == 0xff || expo >= 127 + 39 || prec < 0 || prec > 5) return (size_t)snprintf(dst, 64, "%.*lf", prec, (double)v);
-    uint64_t m = bits & 0x7fffff;
-    int e;                                   // v = m * 2^e
-    if (expo == 0) e = -149; else { m |= 0x800000; e = (int)expo - 150; }
-    uint64_t q;
-    const uint64_t N = m * pow10[prec];      // < 2^24 * 10^5 < 2^41
-    if (e >= 0) {
-        q = N << e;                          // e <= 15 here: < 2^56
-    } else {
-        const int sft = -e;
-        if (sft > 62) q = 0;                 // N < 2^41 is far below half an ulp of the last printed digit
-        else {
-            q = N >> sft;
-            const uint64_t rem = N & (((uint64_t)1 << sft) - 1), half = (uint64_t)1 << (sft - 1);
-            if (rem > half || (rem == half && (q & 1))) q += 1;
-        }
-    }
-    char tmp[32];
-    int n = 0;
-    uint64_t ip = q / pow10[prec], fp = q % pow10[prec];
-    do { tmp[n++] = (char)('0' + ip % 10); ip /= 10; } while (ip);
-    char* o = dst;
-    if (bits >> 31) *o++ = '-';
-    while (n) *o++ = tmp[--n];
-    if (prec) {
-        *o++ = '.';
-        for (int i = prec - 1; i >= 0; --i) { o[i] = (char)('0' + fp % 10); fp /= 10; }
-        o += prec;
-    }
-    *o = 0;
-    return (size_t)(o - dst);
-}
-
 static inline char* put_int(char* o, long long v)
 {
     char tmp[24];

@@ -196,8 +196,7 @@ private:
 std::vector<uint32_t> event_alignment_to_cigar(const std::vector<EventAlignment>& alignments);
 // out[pos] = alphabet->kmer_rank(seq + pos, k) for every k-mer of seq, in one rolling pass
 void rolling_kmer_ranks(const Alphabet* alphabet, const std::string& seq, uint32_t k, uint32_t* out);
-// == snprintf(dst, ..., "%.<prec>lf", (double)v) for a float v and prec <= 5, byte for byte; returns the length
-size_t format_fixed(char* dst, float v, int prec);
+// (format_fixed, the exact %.Nlf replacement the writers use, lives in nph_host.hpp)
 std::string cigar_ops_to_string(const std::vector<uint32_t>& ops);
 
 } // namespace nph

@@ -335,6 +335,12 @@ private:
     Pinned m_pinned[4];
 };
 
+// == snprintf(dst, ..., "%.<prec>lf", v), byte for byte, by exact integer arithmetic on the binary value (round half to
+// even on the exact quotient — what glibc prints in the default rounding mode).  float: prec <= 5; double: prec <= 3.
+// Magnitudes of 2^39 (float) / 2^52 (double) and above and non-finite values take snprintf.  Returns the length.
+size_t format_fixed(char* dst, float v, int prec);
+size_t format_fixed(char* dst, double v, int prec);
+
 // Threads the host-side batch loops use (chain building, record scatter, TSV formatting): $NPH_HOST_THREADS if set,
 // else min(omp_get_max_threads(), 32) — GPU nodes expose many more logical CPUs than a container's CPU quota covers
 // (the B200 boxes of this project: 128 logical CPUs, cgroup quota 16), and a parallel region that oversubscribes them pays

@@ -509,7 +509,7 @@ long long nphh_format_fixed_check(uint64_t seed, size_t n)
 {
     long long bad = 0;
     uint64_t x = seed * 2862933555777941757ull + 3037000493ull;
-    char a[128], b[128];
+    char a[512], b[512];
     for (size_t i = 0; i < n; ++i) {
         x ^= x << 13; x ^= x >> 7; x ^= x << 17;
         float v;
@@ -529,6 +529,16 @@ long long nphh_format_fixed_check(uint64_t seed, size_t n)
             format_fixed(a, v, prec);
             snprintf(b, sizeof(b), "%.*lf", prec, (double)v);
             if (std::strcmp(a, b) != 0) { if (bad < 5) g_err = std::string("format_fixed: ") + a + " vs " + b; ++bad; }
+        }
+        // doubles: sums/differences of floats (the log-likelihood columns), values next to decimal ties, raw bit patterns
+        double d;
+        if (i % 3 == 0) { std::memcpy(&d, &x, 8); }
+        else if (i % 3 == 1) { float w; uint32_t wb = (uint32_t)(x >> 7); std::memcpy(&w, &wb, 4); d = (double)v + (double)w; if (!(std::fabs(d) < 1e15)) d = (double)v - 123.456; }
+        else d = std::nextafter((double)((long long)(x >> 40)) / 1000.0 + 0.0005, (x & 1) ? 1e300 : -1e300);
+        for (int prec = 0; prec <= 3; ++prec) {
+            format_fixed(a, d, prec);
+            snprintf(b, sizeof(b), "%.*lf", prec, d);
+            if (std::strcmp(a, b) != 0) { if (bad < 5) g_err = std::string("format_fixed(double): ") + a + " vs " + b; ++bad; }
         }
     }
     return bad;

@@ -184,12 +184,13 @@ std::string MethylationCaller::tsv(size_t read_idx) const
         const double sum_ll_m = ss.ll_methylated[0] + ss.ll_methylated[1];
         const double sum_ll_u = ss.ll_unmethylated[0] + ss.ll_unmethylated[1];
         const double diff = sum_ll_m - sum_ll_u;
-        snprintf(buf, sizeof(buf), "%s\t%s\t%d\t%d\t", ss.chromosome.c_str(), re.is_reverse ? "-" : "+", ss.start_position, ss.end_position);
-        out += buf;
-        snprintf(buf, sizeof(buf), "%s\t%.2lf\t", re.name.c_str(), diff);
-        out += buf;
-        snprintf(buf, sizeof(buf), "%.2lf\t%.2lf\t", sum_ll_m, sum_ll_u);
-        out += buf;
+        // chromosome, strand, start, end, read_name, log_lik_ratio %.2lf, log_lik_methylated %.2lf, log_lik_unmethylated %.2lf
+        out += ss.chromosome; out += '\t'; out += re.is_reverse ? '-' : '+'; out += '\t';
+        out += std::to_string(ss.start_position); out += '\t'; out += std::to_string(ss.end_position); out += '\t';
+        out += re.name; out += '\t';
+        out.append(buf, format_fixed(buf, diff, 2)); out += '\t';
+        out.append(buf, format_fixed(buf, sum_ll_m, 2)); out += '\t';
+        out.append(buf, format_fixed(buf, sum_ll_u, 2)); out += '\t';
         out += std::to_string(ss.strands_scored) + "\t" + std::to_string(ss.n_motif) + "\t" + ss.sequence + "\n";
     }
     return out;
