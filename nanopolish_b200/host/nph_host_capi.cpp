@@ -253,11 +253,12 @@ int nphh_score_variants_thresholded(int n_reads, const int32_t* read, const uint
 
 // ---- N3: call-methylation for a batch of reads; returns the concatenated TSV ------------------------------
 // aligned pairs are (ref_pos, event_idx) interleaved, pair_off[n_reads+1]
-long long nphh_call_methylation(int n_reads, const int32_t* read, const char** read_names, const uint8_t* is_rev, const uint8_t* rc,
-                                const int32_t* ref_start, const char** ref_seqs, const int32_t* pairs, const uint64_t* pair_off,
-                                const char* contig, double indel_bias, char* tsv_out, size_t cap, uint64_t* n_jobs_out)
+static long long call_methylation_impl(int n_reads, const int32_t* read, const char** read_names, const uint8_t* is_rev, const uint8_t* rc,
+                                       const int32_t* ref_start, const char** ref_seqs, const int32_t* pairs, const uint64_t* pair_off,
+                                       const char* contig, double indel_bias, char* tsv_out, size_t cap, uint64_t* n_jobs_out, double* secs3)
 {
     long long n = -1;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     int st = guard([&] {
         MethylationCallingParameters params;
         MethylationCaller caller(params);
@@ -274,16 +275,36 @@ long long nphh_call_methylation(int n_reads, const int32_t* read, const char** r
             r.rc[0] = rc[i];
             batch_reads.push_back(std::move(r));
         }
+        const double t0 = now();
         caller.add_reads(batch_reads);
         *n_jobs_out = caller.num_jobs();
+        const double t1 = now();
         caller.run(Engine::thread_default(), indel_bias);
+        const double t2 = now();
         std::string all;
         for (int i = 0; i < n_reads; ++i) all += caller.tsv(i);
+        if (secs3) { secs3[0] = t1 - t0; secs3[1] = t2 - t1; secs3[2] = now() - t2; }
         if (all.size() + 1 > cap) throw Error(NPH_ERR_INVALID, "tsv buffer too small");
         std::memcpy(tsv_out, all.c_str(), all.size() + 1);
         n = (long long)all.size();
     });
     return st ? st : n;
+}
+
+long long nphh_call_methylation(int n_reads, const int32_t* read, const char** read_names, const uint8_t* is_rev, const uint8_t* rc,
+                                const int32_t* ref_start, const char** ref_seqs, const int32_t* pairs, const uint64_t* pair_off,
+                                const char* contig, double indel_bias, char* tsv_out, size_t cap, uint64_t* n_jobs_out)
+{
+    return call_methylation_impl(n_reads, read, read_names, is_rev, rc, ref_start, ref_seqs, pairs, pair_off, contig, indel_bias, tsv_out, cap,
+                                 n_jobs_out, nullptr);
+}
+// the same, with the seconds spent in {enumeration, flatten + device call + scatter, TSV formatting}
+long long nphh_call_methylation_timed(int n_reads, const int32_t* read, const char** read_names, const uint8_t* is_rev, const uint8_t* rc,
+                                      const int32_t* ref_start, const char** ref_seqs, const int32_t* pairs, const uint64_t* pair_off,
+                                      const char* contig, double indel_bias, char* tsv_out, size_t cap, uint64_t* n_jobs_out, double* secs3)
+{
+    return call_methylation_impl(n_reads, read, read_names, is_rev, rc, ref_start, ref_seqs, pairs, pair_off, contig, indel_bias, tsv_out, cap,
+                                 n_jobs_out, secs3);
 }
 
 // enumeration only (no device): seconds spent in MethylationCaller::add_read over all reads, and the job count

@@ -1,0 +1,79 @@
+"""Timing of call-methylation through the C++ host (MethylationCaller: parallel enumeration -> one launch -> scatter -> TSV)
+next to the compiled reference scoring the same windows on the host cores (development aid; prints one JSON line).
+
+  python scripts/quick_methylation.py [n_reads] [n_events]
+"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+from nanopolish_b200 import synth  # noqa: E402
+from tests.test_host_mirror import HOST_SO, _register, _register_reads  # noqa: E402
+
+K = 6
+n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+n_events = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
+host = C.CDLL(HOST_SO)
+host.nphh_last_error.restype = C.c_char_p
+host.nphh_call_methylation_timed.restype = C.c_longlong
+nuc, cpg = synth.load_model("nucleotide"), synth.load_model("cpg")
+rs = synth.gen_reads(n_reads, n_events, nuc, seed=2024, cpg_keep=0.3)
+mh, ch = _register(host, nuc), _register(host, cpg)
+rh = _register_reads(host, rs, mh)
+for r in rh:
+    host.nphh_read_add_model(r, b"cpg", ch)
+refs_s, pairs_l = [], []
+for i in range(n_reads):
+    codes = rs.seq_codes[i]
+    nk = codes.shape[0] - K + 1
+    kfe = np.minimum(rs.kmer_first_event[i], int(rs.reads[i]["n_events"]) - 1)
+    refs_s.append(synth._CODE2DNA[codes].tobytes())
+    pairs_l.append(np.stack([10_000 + np.arange(K, nk - K), kfe[K:nk - K]], 1).astype(np.int32))
+flat = np.concatenate(pairs_l).reshape(-1)
+off = np.zeros(n_reads + 1, np.uint64); off[1:] = np.cumsum([p.shape[0] for p in pairs_l])
+names = (C.c_char_p * n_reads)(*[f"read_{i}".encode() for i in range(n_reads)])
+refs = (C.c_char_p * n_reads)(*refs_s)
+p = lambda a: a.ctypes.data_as(C.c_void_p)
+z = np.zeros(n_reads, np.uint8)
+cap = 400 * 45 * n_reads
+buf = C.create_string_buffer(cap)
+best, stages, nj = None, None, C.c_uint64()
+for it in range(4):
+    secs3 = np.zeros(3)
+    t0 = time.perf_counter()
+    n = host.nphh_call_methylation_timed(n_reads, p(np.array(rh, np.int32)), names, p(z), p(z), p(np.full(n_reads, 10_000, np.int32)), refs,
+                                         p(flat), p(off), b"chr1", C.c_double(1.0), buf, C.c_size_t(cap), C.byref(nj), p(secs3))
+    dt = time.perf_counter() - t0
+    assert n >= 0, host.nphh_last_error()
+    print(f"run {it}: {dt * 1e3:.1f} ms  enumerate {secs3[0] * 1e3:.1f}  device+flatten {secs3[1] * 1e3:.1f}  tsv {secs3[2] * 1e3:.1f}", file=sys.stderr)
+    if it and (best is None or dt < best):
+        best, stages = dt, secs3.copy()
+rows = buf.value.count(b"\n")
+jobs = synth.methylation_jobs(rs, model_id=1, keep_seqs=True)   # the same windows, for the event count and the CPU arm
+ref = None
+try:
+    from oracle.oracle_py import RefOracle
+    if RefOracle.available():
+        ro = RefOracle()
+        mhs = [ro.builtin_model("nucleotide"), ro.builtin_model("cpg")]
+        nsub = min(n_reads, 256)
+        rhr = ro.register_reads(rs.reads[:nsub], rs.ev_mean, rs.ev_start_time, mhs[0])
+        sel = np.flatnonzero(jobs.jobs["read"] < nsub)[:40000]
+        sub = np.ascontiguousarray(jobs.jobs[sel])
+        seqs = [jobs.seqs[j] for j in sel] if jobs.seqs else None
+        if seqs is not None:
+            cores = os.cpu_count() or 1
+            _, secs = ro.score_batch(rhr, sub, seqs, mhs, threads=cores)
+            E = np.abs(sub["event_stop"].astype(np.int64) - sub["event_start"].astype(np.int64)) + 1
+            ref = dict(jobs=int(sel.shape[0]), seconds=secs, threads=cores, events_per_sec=float(E.sum() / secs))
+except OSError as e:
+    ref = dict(error=str(e))
+print(json.dumps(dict(workload="call-methylation through the C++ host", reads=n_reads, jobs=int(nj.value), tsv_rows=rows,
+                      scored_events=int(jobs.scored_events), best_ms=best * 1e3, events_per_sec=jobs.scored_events / best,
+                      reads_per_sec=n_reads / best, stage_ms=dict(enumerate=stages[0] * 1e3, device=stages[1] * 1e3, tsv=stages[2] * 1e3),
+                      host_jobs_match_synth=int(nj.value) == int(jobs.jobs.shape[0]), reference=ref)))
