@@ -68,11 +68,8 @@ std::vector<std::vector<HMMAlignmentState>> AlignBatch::run(Engine& engine, doub
     if (!reads_resident || m_reads_uploaded != m_reads.size()) {
         std::vector<std::pair<const SquiggleRead*, uint8_t>> rl;
         for (auto& r : m_reads) rl.push_back({r.read, r.strand});
-        std::vector<nph_read> reads;
-        std::vector<float> mean;
-        std::vector<double> time;
-        detail::flatten_reads(rl, reads, mean, time);
-        engine.check(nph_reads_load(engine.ctx(), reads.data(), reads.size(), mean.data(), time.data(), mean.size()), "nph_reads_load");
+        const detail::FlatReads fr = detail::flatten_reads(engine, rl);
+        engine.check(nph_reads_load(engine.ctx(), fr.reads.data(), fr.reads.size(), fr.mean, fr.time, fr.n_events), "nph_reads_load");
         m_reads_uploaded = m_reads.size();
     }
     std::vector<uint64_t> off(m_jobs.size() + 1, 0);
@@ -527,13 +524,8 @@ size_t EventAligner::run(Engine& engine, double indel_bias)
     }
 
     // ---- the device: reads up, one launch, records back ----
-    std::vector<nph_read> reads;
-    std::vector<float> mean;
-    std::vector<double> time;
-    detail::flatten_reads(read_table, reads, mean, time);
-    bool any_drift = false;
-    for (const nph_read& r : reads) any_drift = any_drift || r.drift != 0.0;
-    engine.check(nph_reads_load(engine.ctx(), reads.data(), reads.size(), mean.data(), any_drift ? time.data() : nullptr, mean.size()), "nph_reads_load");
+    const detail::FlatReads fr = detail::flatten_reads(engine, read_table);
+    engine.check(nph_reads_load(engine.ctx(), fr.reads.data(), fr.reads.size(), fr.mean, fr.time, fr.n_events), "nph_reads_load");
     nph_ea_record* const records = static_cast<nph_ea_record*>(engine.pinned(0, sizeof(nph_ea_record) * std::max<uint64_t>(records_total, 1)));
     std::vector<nph_ea_result> results(n_chains);
     engine.check(nph_eventalign_chain(engine.ctx(), pairs.data(), pairs.size(), map_start.data(), map_start.size(), ranks_fwd.data(),

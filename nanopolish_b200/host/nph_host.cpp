@@ -357,31 +357,39 @@ int host_threads()
 }
 
 namespace detail {
-void flatten_reads(const std::vector<std::pair<const SquiggleRead*, uint8_t>>& reads, std::vector<nph_read>& out,
-                   std::vector<float>& mean, std::vector<double>& time)
+FlatReads flatten_reads(Engine& engine, const std::vector<std::pair<const SquiggleRead*, uint8_t>>& reads)
 {
-    out.resize(reads.size());
-    size_t total = 0;
-    for (auto& r : reads) total += r.first->events[r.second].size();
-    mean.resize(total);
-    time.resize(total);
+    FlatReads fr;
+    fr.reads.resize(reads.size());
     std::vector<size_t> offs(reads.size() + 1, 0);
-    for (size_t i = 0; i < reads.size(); ++i) offs[i + 1] = offs[i] + reads[i].first->events[reads[i].second].size();
+    bool any_drift = false;
+    for (size_t i = 0; i < reads.size(); ++i) {
+        offs[i + 1] = offs[i] + reads[i].first->events[reads[i].second].size();
+        any_drift = any_drift || reads[i].first->scalings[reads[i].second].drift != 0.0;
+    }
+    const size_t total = offs.back();
+    fr.n_events = total;
+    float* const mean = static_cast<float*>(engine.pinned(1, sizeof(float) * std::max<size_t>(total, 1)));
+    double* const time = any_drift ? static_cast<double*>(engine.pinned(2, sizeof(double) * std::max<size_t>(total, 1))) : nullptr;
+    fr.mean = mean;
+    fr.time = time;
 #pragma omp parallel for schedule(dynamic, 8) num_threads(host_threads()) if (total > (size_t)1 << 18)
     for (long long ii = 0; ii < (long long)reads.size(); ++ii) {
         const size_t i = (size_t)ii, off = offs[i];
         const SquiggleRead* sr = reads[i].first;
         const uint8_t st = reads[i].second;
         const std::vector<SquiggleEvent>& ev = sr->events[st];
-        nph_read& o = out[i];
+        nph_read& o = fr.reads[i];
         o.event_off = off;
         o.n_events = (uint32_t)ev.size();
         o.reserved = 0;
         const SquiggleScalings& s = sr->scalings[st];
         o.scale = s.scale; o.shift = s.shift; o.drift = s.drift; o.var = s.var; o.log_var = s.log_var;
         o.events_per_base = sr->events_per_base[st];
-        for (size_t e = 0; e < ev.size(); ++e) { mean[off + e] = ev[e].mean; time[off + e] = ev[e].start_time; }
+        for (size_t e = 0; e < ev.size(); ++e) mean[off + e] = ev[e].mean;
+        if (time) for (size_t e = 0; e < ev.size(); ++e) time[off + e] = ev[e].start_time;
     }
+    return fr;
 }
 } // namespace detail
 using detail::flatten_reads;
@@ -481,11 +489,8 @@ std::vector<float> HmmBatch::run(Engine& engine, double indel_bias)
     }
     std::vector<std::pair<const SquiggleRead*, uint8_t>> rl;
     for (auto& r : m_reads) rl.push_back({r.read, r.strand});
-    std::vector<nph_read> reads;
-    std::vector<float> mean;
-    std::vector<double> time;
-    flatten_reads(rl, reads, mean, time);
-    engine.check(nph_hmm_score_batch(engine.ctx(), reads.data(), reads.size(), mean.data(), time.data(), mean.size(),
+    const detail::FlatReads fr = flatten_reads(engine, rl);
+    engine.check(nph_hmm_score_batch(engine.ctx(), fr.reads.data(), fr.reads.size(), fr.mean, fr.time, fr.n_events,
                                      m_ranks.data(), m_ranks.size(), m_jobs.data(), m_jobs.size(), indel_bias, scores.data()),
                  "nph_hmm_score_batch");
     return scores;
@@ -523,13 +528,10 @@ std::vector<std::vector<AlignedPair>> AbeaBatch::run(Engine& engine)
     if (m_jobs.empty()) return out;
     std::vector<std::pair<const SquiggleRead*, uint8_t>> rl;
     for (auto* r : m_reads) rl.push_back({r, (uint8_t)0});    // strand 0, like the reference (raw_loader.cpp:79)
-    std::vector<nph_read> reads;
-    std::vector<float> mean;
-    std::vector<double> time;
-    flatten_reads(rl, reads, mean, time);
+    const detail::FlatReads fr = flatten_reads(engine, rl);
     std::vector<nph_aligned_pair> pairs(m_pairs_total);
     std::vector<nph_abea_result> res(m_jobs.size());
-    engine.check(nph_abea_batch(engine.ctx(), reads.data(), reads.size(), mean.data(), time.data(), mean.size(),
+    engine.check(nph_abea_batch(engine.ctx(), fr.reads.data(), fr.reads.size(), fr.mean, fr.time, fr.n_events,
                                 m_ranks.data(), m_ranks.size(), m_jobs.data(), m_jobs.size(), engine.model_id(m_model),
                                 pairs.data(), pairs.size(), res.data()),
                  "nph_abea_batch");

@@ -348,9 +348,18 @@ size_t format_fixed(char* dst, double v, int prec);
 int host_threads();
 
 namespace detail {
-// (read, strand) list -> the flat nph_read records + event arrays the C ABI takes
-void flatten_reads(const std::vector<std::pair<const SquiggleRead*, uint8_t>>& reads, std::vector<nph_read>& out,
-                   std::vector<float>& mean, std::vector<double>& time);
+// (read, strand) list -> the flat nph_read records + event arrays the C ABI takes.  The arrays live in the engine's
+// page-locked staging (slots 1 and 2: no page faults after the first batch, full-speed H2D) and stay valid until the next
+// flatten on the same engine; time is nullptr when no read has a drift term (the start times are then not needed).
+struct FlatReads {
+    std::vector<nph_read> reads;
+    const float* mean = nullptr;
+    const double* time = nullptr;
+    size_t n_events = 0;
+};
+}
+namespace detail {
+FlatReads flatten_reads(Engine& engine, const std::vector<std::pair<const SquiggleRead*, uint8_t>>& reads);
 }
 
 // A batch of profile_hmm_score calls.  add() returns the index of the job's score in run()'s result.

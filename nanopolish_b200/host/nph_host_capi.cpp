@@ -282,7 +282,7 @@ static long long call_methylation_impl(int n_reads, const int32_t* read, const c
         caller.run(Engine::thread_default(), indel_bias);
         const double t2 = now();
         std::string all;
-        for (int i = 0; i < n_reads; ++i) all += caller.tsv(i);
+        for (const std::string& part : caller.tsv_batch()) all += part;
         if (secs3) { secs3[0] = t1 - t0; secs3[1] = t2 - t1; secs3[2] = now() - t2; }
         if (all.size() + 1 > cap) throw Error(NPH_ERR_INVALID, "tsv buffer too small");
         std::memcpy(tsv_out, all.c_str(), all.size() + 1);

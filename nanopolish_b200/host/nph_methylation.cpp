@@ -196,6 +196,14 @@ std::string MethylationCaller::tsv(size_t read_idx) const
     return out;
 }
 
+std::vector<std::string> MethylationCaller::tsv_batch() const
+{
+    std::vector<std::string> out(m_reads.size());
+#pragma omp parallel for schedule(dynamic, 16) num_threads(host_threads()) if (m_reads.size() > 64)
+    for (long long i = 0; i < (long long)m_reads.size(); ++i) out[i] = tsv((size_t)i);
+    return out;
+}
+
 void MethylationCaller::write_tsv(FILE* fp, size_t read_idx) const
 {
     const std::string s = tsv(read_idx);

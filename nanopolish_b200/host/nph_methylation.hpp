@@ -69,6 +69,7 @@ public:
     const HmmBatch& batch() const { return m_batch; }      // the queued jobs (read-only; for inspection and tests)
     void write_tsv(FILE* fp, size_t read_idx) const;
     std::string tsv(size_t read_idx) const;
+    std::vector<std::string> tsv_batch() const;            // every read's rows, formatted by host_threads() workers
     void clear();
 
 private:
