@@ -396,6 +396,12 @@ using detail::flatten_reads;
 
 size_t HmmBatch::add(const HMMInputSequence& sequence, const HMMInputData& data, uint32_t flags)
 {
+    RankCache once;
+    return add(sequence, data, flags, once);
+}
+
+size_t HmmBatch::add(const HMMInputSequence& sequence, const HMMInputData& data, uint32_t flags, RankCache& cache)
+{
     if (!data.read || !data.pore_model) throw Error(NPH_ERR_INVALID, "HMMInputData without read or pore_model");
     if (data.read->pore_type != PORETYPE_R9) throw Error(NPH_ERR_UNSUPPORTED, "only R9 reads are supported (load_from_raw always makes R9)");
     const uint32_t k = data.pore_model->k;
@@ -415,8 +421,14 @@ size_t HmmBatch::add(const HMMInputSequence& sequence, const HMMInputData& data,
         ridx = it->second;
     }
     const uint32_t n_kmers = (uint32_t)(sequence.length() - k + 1);
+    const int strand_slot = data.rc != 0 ? 1 : 0;
+    if (cache.k != k) { cache.off[0] = cache.off[1] = ~(uint64_t)0; cache.k = k; }
+    if (cache.off[strand_slot] == ~(uint64_t)0) {
+        cache.off[strand_slot] = m_ranks.size();
+        sequence.append_kmer_ranks(k, data.rc != 0, m_ranks);
+    }
     nph_hmm_job j;
-    j.rank_off = m_ranks.size();
+    j.rank_off = cache.off[strand_slot];
     j.read = ridx;
     j.model_id = 0;   // resolved against the engine in run()
     j.event_start = data.event_start_idx;
@@ -426,7 +438,6 @@ size_t HmmBatch::add(const HMMInputSequence& sequence, const HMMInputData& data,
     j.rc = data.rc;
     j.flags = (uint8_t)flags;
     j.reserved = 0;
-    sequence.append_kmer_ranks(k, data.rc != 0, m_ranks);
     m_jobs.push_back(j);
     m_job_models.push_back(data.pore_model);
     return m_jobs.size() - 1;

@@ -363,9 +363,19 @@ FlatReads flatten_reads(Engine& engine, const std::vector<std::pair<const Squigg
 }
 
 // A batch of profile_hmm_score calls.  add() returns the index of the job's score in run()'s result.
+// Where the k-mer ranks of one HMMInputSequence already sit in a batch (per strand), so that scoring the same sequence
+// against many reads — a haplotype against a pile-up — stores and uploads them once.  One cache per sequence object and
+// batch; a default-constructed cache is empty.
+struct RankCache {
+    uint64_t off[2] = {~(uint64_t)0, ~(uint64_t)0};     // [rc]
+    uint32_t k = 0;
+};
+
 class HmmBatch {
 public:
     size_t add(const HMMInputSequence& sequence, const HMMInputData& data, uint32_t flags = 0);
+    // the same; the ranks are taken from / recorded in `cache`, which must belong to this sequence and this batch
+    size_t add(const HMMInputSequence& sequence, const HMMInputData& data, uint32_t flags, RankCache& cache);
     size_t size() const { return m_jobs.size(); }
     void clear();
     std::vector<float> run(Engine& engine, double indel_bias = hmm_indel_bias_factor);

@@ -65,16 +65,19 @@ std::vector<HMMInputSequence> generate_methylated_alternatives(const HMMInputSeq
 namespace {
 
 // Adds the jobs of profile_hmm_score_set(sequences, data) to the batch; returns (first job, count).
-std::pair<size_t, size_t> add_score_set(HmmBatch& batch, const std::vector<HMMInputSequence>& sequences, const HMMInputData& data,
-                                        uint32_t flags)
+// `ranks` has one RankCache per sequence: a haplotype is scored against every read of the pile-up, its k-mer ranks are
+// computed and shipped once per strand.
+std::pair<size_t, size_t> add_score_set(HmmBatch& batch, const std::vector<HMMInputSequence>& sequences, std::vector<RankCache>& ranks,
+                                        const HMMInputData& data, uint32_t flags)
 {
     const size_t first = batch.size();
-    batch.add(sequences[0], data, flags);
+    ranks.resize(sequences.size());
+    batch.add(sequences[0], data, flags, ranks[0]);
     for (size_t i = 1; i < sequences.size(); ++i) {
         HMMInputData alt = data;
         alt.pore_model = data.read->get_model(data.strand, sequences[i].get_alphabet()->get_name());
         if (!alt.pore_model) throw Error(NPH_ERR_INVALID, std::string("read has no pore model for alphabet ") + sequences[i].get_alphabet()->get_name());
-        batch.add(sequences[i], alt, flags);
+        batch.add(sequences[i], alt, flags, ranks[i]);
     }
     return {first, sequences.size()};
 }
@@ -96,9 +99,10 @@ std::vector<std::vector<double>> score_haplotypes(const std::vector<Haplotype>& 
     HmmBatch batch;
     std::vector<std::vector<HMMInputSequence>> alts;
     for (const Haplotype& h : haplotypes) alts.push_back(generate_methylated_alternatives(HMMInputSequence(h.get_sequence()), methylation_types));
+    std::vector<std::vector<RankCache>> alt_ranks(haplotypes.size());
     std::vector<std::vector<std::pair<size_t, size_t>>> spans(input.size(), std::vector<std::pair<size_t, size_t>>(haplotypes.size()));
     for (size_t ri = 0; ri < input.size(); ++ri)
-        for (size_t hi = 0; hi < haplotypes.size(); ++hi) spans[ri][hi] = add_score_set(batch, alts[hi], input[ri], alignment_flags);
+        for (size_t hi = 0; hi < haplotypes.size(); ++hi) spans[ri][hi] = add_score_set(batch, alts[hi], alt_ranks[hi], input[ri], alignment_flags);
     const std::vector<float> s = batch.run(engine, indel_bias);
     std::vector<std::vector<double>> out(input.size(), std::vector<double>(haplotypes.size()));
     for (size_t ri = 0; ri < input.size(); ++ri)
@@ -116,7 +120,8 @@ std::vector<Variant> score_variants_thresholded(const std::vector<Variant>& inpu
     const std::vector<HMMInputSequence> base_seqs =
         generate_methylated_alternatives(HMMInputSequence(base_haplotype.get_sequence()), methylation_types);
     std::vector<std::pair<size_t, size_t>> base_span(input.size());
-    for (size_t j = 0; j < input.size(); ++j) base_span[j] = add_score_set(batch, base_seqs, input[j], alignment_flags);   // once per read
+    std::vector<RankCache> base_ranks;
+    for (size_t j = 0; j < input.size(); ++j) base_span[j] = add_score_set(batch, base_seqs, base_ranks, input[j], alignment_flags);   // once per read
 
     std::vector<char> applies(input_variants.size(), 0);
     std::vector<std::vector<std::pair<size_t, size_t>>> var_span(input_variants.size());
@@ -128,7 +133,8 @@ std::vector<Variant> score_variants_thresholded(const std::vector<Variant>& inpu
         if (!applies[v]) continue;
         const std::vector<HMMInputSequence> seqs = generate_methylated_alternatives(HMMInputSequence(hap.get_sequence()), methylation_types);
         var_span[v].resize(input.size());
-        for (size_t j = 0; j < input.size(); ++j) var_span[v][j] = add_score_set(batch, seqs, input[j], alignment_flags);
+        std::vector<RankCache> var_ranks;
+        for (size_t j = 0; j < input.size(); ++j) var_span[v][j] = add_score_set(batch, seqs, var_ranks, input[j], alignment_flags);
     }
     const std::vector<float> s = batch.run(engine, indel_bias);
     std::vector<double> base(input.size());
