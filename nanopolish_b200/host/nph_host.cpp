@@ -96,6 +96,13 @@ Alphabet::Match Alphabet::match_to_site(const std::string& str, size_t i, const 
 std::string Alphabet::reverse_complement(const std::string& str) const
 {
     std::string out(str.length(), 'A');
+    // a site is only treated as a unit when the match covers a methylated symbol: without one in the string this is the
+    // plain base-by-base reverse complement
+    if (std::memchr(str.data(), METHYLATED_SYMBOL, str.size()) == nullptr) {
+        const size_t n = str.size();
+        for (size_t t = 0; t < n; ++t) out[n - 1 - t] = complement(str[t]);
+        return out;
+    }
     size_t i = 0;
     int j = (int)str.length() - 1;
     while (i < str.length()) {
@@ -192,6 +199,16 @@ std::string Alphabet::unmethylate(const std::string& str) const
 
 bool Alphabet::is_motif_match(const std::string& str, size_t i) const
 {
+    // a complete site needs recognition_length() symbols from i on; the partial matches match_to_site also reports
+    // (string end, string inside a site) never have that length unless the whole string is the site, which the
+    // comparison below covers too
+    const size_t rl = recognition_length();
+    if (rl > 0 && str.size() >= rl) {
+        if (i + rl > str.size()) return false;
+        for (size_t s = 0; s < num_recognition_sites(); ++s)
+            if (std::memcmp(str.data() + i, m_sites[s].data(), rl) == 0) return true;
+        return false;
+    }
     for (size_t s = 0; s < num_recognition_sites(); ++s) {
         if (i > 0 && str[i] != m_sites[s][0]) continue;              // see reverse_complement
         Match m = match_to_site(str, i, m_sites[s]);
