@@ -172,6 +172,73 @@ def test_host_chaining_logic_on_cpu(host, cases, restated, golden, port_oracle):
     host.nphh_ea_begin()
 
 
+def _drive_rounds(host, cs, rs, model, port_oracle):
+    """pull every round's jobs out of the C++ cursors and feed back the plain-C Viterbi's paths"""
+    jobs = np.zeros(max(len(cs), 1), synth.HMM_JOB_DT)
+    ranks = np.zeros(len(cs) * 400 + 400, np.uint32)
+    n_ranks = C.c_uint64()
+    rounds = 0
+    while True:
+        n = host.nphh_ea_next_round(_p(jobs), C.c_size_t(jobs.shape[0]), _p(ranks), C.c_size_t(ranks.shape[0]), C.byref(n_ranks))
+        assert n >= 0, host.nphh_last_error()
+        if n == 0:
+            return rounds
+        paths, off = [], [0]
+        for j in range(n):
+            jb = jobs[j].copy()
+            jb["read"] = EC.read_slot(cs[int(jb["read"])], rs.n_reads)
+            st, _ = port_oracle.hmm_align(rs.reads, rs.ev_mean, rs.ev_start_time, [model], ranks, jb)
+            paths.append(st); off.append(off[-1] + st.shape[0])
+        flat = np.concatenate(paths) if off[-1] else np.zeros(0, synth.ALIGN_STATE_DT)
+        assert host.nphh_ea_consume(C.c_size_t(n), _p(np.array(off, np.uint64)), _p(flat)) == 0, host.nphh_last_error()
+        rounds += 1
+
+
+def test_eventalign_edge_cases_against_compiled_reference(host, cases, ref_oracle, port_oracle):
+    """Records the seeded cases do not reach: a window outside the alignment, a window that empties a later BAM segment
+    (the reference then returns from align_read_to_ref: later segments are not aligned either), hard clips and =/X
+    operations, a read whose k-mers near the segment ends have no events.  C++ cursors == restatement == compiled reference."""
+    model, rs, base = cases
+    c0, c2 = base[0], base[2]                               # forward single-segment record; forward record with an N
+    assert not _single_segment(c2)
+    variants = []
+    v = dict(c0); v["region"] = (5, 20); variants.append(v)                                    # nothing of the alignment inside
+    seg_pairs = EP.get_aligned_segments(c2["ref_pos"], c2["cigar"])
+    first_end = seg_pairs[0][-1][0]
+    v = dict(c2); v["region"] = (c2["ref_pos"] + 50, first_end - 10); variants.append(v)       # second segment trims to nothing
+    v = dict(c2); v["region"] = (seg_pairs[1][0][0] + 30, seg_pairs[1][-1][0]); variants.append(v)   # FIRST segment empty: nothing at all
+    ops = [(int(x) >> 4, EP.CIGAR_OPS[int(x) & 15]) for x in c0["cigar"]]
+    ops2 = [(7, "H")] + [(n, "=" if (i % 2 and o == "M") else ("X" if (i % 3 == 0 and o == "M") else o)) for i, (n, o) in enumerate(ops)] + [(3, "H")]
+    v = dict(c0); v["cigar"] = EP.pack_cigar(ops2); variants.append(v)
+    holes = c0["read"].b2e_start.copy()                                                       # no events for the first / last k-mers of the read
+    holes[:12] = -1; holes[-9:] = -1
+    stop = c0["b2e_stop"].copy(); stop[:12] = -1; stop[-9:] = -1
+    import dataclasses
+    v = dict(c0); v["read"] = dataclasses.replace(c0["read"], b2e_start=holes); v["b2e_stop"] = stop; variants.append(v)
+    for i, v in enumerate(variants):
+        v["read_idx"] = i
+    # the map with holes needs its own read slot on the C++ side: run that one in a second batch
+    for batch in (variants[:4], variants[4:]):
+        for i, v in enumerate(batch):
+            v["read_idx"] = i
+        _setup(host, (model, rs, batch))
+        _drive_rounds(host, batch, rs, model, port_oracle)
+        ref_oracle.clear_reads()
+        mh = ref_oracle.builtin_model("nucleotide")
+        rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, mh)
+        for v in batch:
+            slot, r = EC.read_slot(v, rs.n_reads), v["read"]
+            ref_oracle.read_set_eventalign(rh[slot], r.name, r.read_sequence, r.b2e_start, v["b2e_stop"], r.stdv, r.duration)
+            want, _, _ = ref_oracle.eventalign(rh[slot], v["contig_name"], v["contig"], v["ref_pos"], v["flag"], v["cigar"], v["read_idx"],
+                                               v["region"], want_cigar=False)
+            al = EP.align_read_to_ref(r, v["contig_name"], v["fetched"], v["ref_pos"], v["flag"], v["cigar"], v["read_idx"],
+                                      EC.port_align_fn(port_oracle, rs, model, slot), *v["region"])
+            assert EP.tsv(r, al) == want
+            assert _text(host, v["read_idx"], 0) == want
+        host.nphh_ea_begin()
+    ref_oracle.clear_reads()
+
+
 def test_format_fixed_matches_printf(host):
     """The TSV writer's %.2lf / %.3lf / %.5lf replacement (exact integer arithmetic on the float) against snprintf on
     6 x 600k values: uniform bit patterns, dyadic fractions, decimal ties and their neighbours, inf/nan, +-0."""
