@@ -199,24 +199,7 @@ def test_eventalign_edge_cases_against_compiled_reference(host, cases, ref_oracl
     (the reference then returns from align_read_to_ref: later segments are not aligned either), hard clips and =/X
     operations, a read whose k-mers near the segment ends have no events.  C++ cursors == restatement == compiled reference."""
     model, rs, base = cases
-    c0, c2 = base[0], base[2]                               # forward single-segment record; forward record with an N
-    assert not _single_segment(c2)
-    variants = []
-    v = dict(c0); v["region"] = (5, 20); variants.append(v)                                    # nothing of the alignment inside
-    seg_pairs = EP.get_aligned_segments(c2["ref_pos"], c2["cigar"])
-    first_end = seg_pairs[0][-1][0]
-    v = dict(c2); v["region"] = (c2["ref_pos"] + 50, first_end - 10); variants.append(v)       # second segment trims to nothing
-    v = dict(c2); v["region"] = (seg_pairs[1][0][0] + 30, seg_pairs[1][-1][0]); variants.append(v)   # FIRST segment empty: nothing at all
-    ops = [(int(x) >> 4, EP.CIGAR_OPS[int(x) & 15]) for x in c0["cigar"]]
-    ops2 = [(7, "H")] + [(n, "=" if (i % 2 and o == "M") else ("X" if (i % 3 == 0 and o == "M") else o)) for i, (n, o) in enumerate(ops)] + [(3, "H")]
-    v = dict(c0); v["cigar"] = EP.pack_cigar(ops2); variants.append(v)
-    holes = c0["read"].b2e_start.copy()                                                       # no events for the first / last k-mers of the read
-    holes[:12] = -1; holes[-9:] = -1
-    stop = c0["b2e_stop"].copy(); stop[:12] = -1; stop[-9:] = -1
-    import dataclasses
-    v = dict(c0); v["read"] = dataclasses.replace(c0["read"], b2e_start=holes); v["b2e_stop"] = stop; variants.append(v)
-    for i, v in enumerate(variants):
-        v["read_idx"] = i
+    variants = _edge_variants(base)
     # the map with holes needs its own read slot on the C++ side: run that one in a second batch
     for batch in (variants[:4], variants[4:]):
         for i, v in enumerate(batch):
@@ -237,6 +220,44 @@ def test_eventalign_edge_cases_against_compiled_reference(host, cases, ref_oracl
             assert _text(host, v["read_idx"], 0) == want
         host.nphh_ea_begin()
     ref_oracle.clear_reads()
+
+
+@pytest.mark.gpu
+def test_eventalign_edge_cases_on_device(host, cases, port_oracle):
+    """the same records through the chain kernel (EventAligner::run)"""
+    model, rs, base = cases
+    variants = _edge_variants(base)
+    for batch in (variants[:4], variants[4:]):
+        for i, v in enumerate(batch):
+            v["read_idx"] = i
+        _setup(host, (model, rs, batch))
+        assert host.nphh_ea_run(C.c_double(1.0)) >= 0, host.nphh_last_error()
+        for v in batch:
+            slot, r = EC.read_slot(v, rs.n_reads), v["read"]
+            al = EP.align_read_to_ref(r, v["contig_name"], v["fetched"], v["ref_pos"], v["flag"], v["cigar"], v["read_idx"],
+                                      EC.port_align_fn(port_oracle, rs, model, slot), *v["region"])
+            assert _text(host, v["read_idx"], 0) == EP.tsv(r, al)
+        host.nphh_ea_begin()
+
+
+def _edge_variants(base):
+    c0, c2 = base[0], base[2]                               # forward single-segment record; forward record with an N
+    assert not _single_segment(c2)
+    variants = []
+    v = dict(c0); v["region"] = (5, 20); variants.append(v)                                    # nothing of the alignment inside
+    seg_pairs = EP.get_aligned_segments(c2["ref_pos"], c2["cigar"])
+    first_end = seg_pairs[0][-1][0]
+    v = dict(c2); v["region"] = (c2["ref_pos"] + 50, first_end - 10); variants.append(v)       # second segment trims to nothing
+    v = dict(c2); v["region"] = (seg_pairs[1][0][0] + 30, seg_pairs[1][-1][0]); variants.append(v)   # FIRST segment empty: nothing at all
+    ops = [(int(x) >> 4, EP.CIGAR_OPS[int(x) & 15]) for x in c0["cigar"]]
+    ops2 = [(7, "H")] + [(n, "=" if (i % 2 and o == "M") else ("X" if (i % 3 == 0 and o == "M") else o)) for i, (n, o) in enumerate(ops)] + [(3, "H")]
+    v = dict(c0); v["cigar"] = EP.pack_cigar(ops2); variants.append(v)
+    holes = c0["read"].b2e_start.copy()                                                       # no events for the first / last k-mers of the read
+    holes[:12] = -1; holes[-9:] = -1
+    stop = c0["b2e_stop"].copy(); stop[:12] = -1; stop[-9:] = -1
+    import dataclasses
+    v = dict(c0); v["read"] = dataclasses.replace(c0["read"], b2e_start=holes); v["b2e_stop"] = stop; variants.append(v)
+    return variants
 
 
 def test_format_fixed_matches_printf(host):
