@@ -71,6 +71,15 @@ def cpu_quota():
         return None
 
 
+def cpu_threads():
+    """Threads for the CPU arm: every logical CPU, unless a cgroup quota makes that oversubscription — measured on the
+    B200 boxes (profiles/r01_cpu_threads.json): 128 threads under a 16-CPU quota run the reference 28 % slower than 32.
+    Twice the quota is the fastest setting there, so that is what the reference gets."""
+    n = os.cpu_count() or 1
+    q = cpu_quota()
+    return n if not q else max(1, min(n, int(round(2 * q))))
+
+
 class ClockSampler:
     """nvidia-smi sampled every 200 ms DURING the timed region (B200_PROFILING.md clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -154,7 +163,7 @@ class CpuArm:
     def __init__(self, rs, jobs, models, want_ref=True):
         from oracle.oracle_py import PortOracle, RefOracle
         self.rs, self.jobs, self.models = rs, jobs, models
-        self.cores = os.cpu_count() or 1
+        self.cores = cpu_threads()
         j = jobs.jobs
         self.E = np.abs(j["event_stop"].astype(np.int64) - j["event_start"].astype(np.int64)) + 1
         self.cells = self.E * j["n_kmers"].astype(np.int64)
@@ -320,7 +329,7 @@ def run_aux(args, rank, world, local, saved_stdout):
             from oracle.oracle_py import RefOracle
             if RefOracle.available():
                 ro = RefOracle()
-                cores = os.cpu_count() or 1
+                cores = cpu_threads()
                 ns = min(n_reads, max(cores, 32) * 2)
                 rh = ro.register_reads(rs.reads[:ns], rs.ev_mean, rs.ev_start_time, ro.builtin_model("nucleotide"))
                 seqs = [synth._CODE2DNA[c].tobytes().decode() for c in rs.seq_codes[:ns]]
@@ -390,7 +399,7 @@ def run_aux(args, rank, world, local, saved_stdout):
             from oracle.oracle_py import PortOracle
             from oracle.prep_chain import oracle_chain
             port = PortOracle()
-            cores = os.cpu_count() or 1
+            cores = cpu_threads()
             ns = min(base, max(cores, 32))
             t0 = time.perf_counter()
             with ThreadPoolExecutor(cores) as ex:       # the C restatement releases the GIL inside each call
