@@ -271,6 +271,7 @@ static long long call_methylation_impl(int n_reads, const int32_t* read, const c
             r.contig = contig;
             r.ref_start_pos = ref_start[i];
             r.ref_seq = ref_seqs[i];
+            r.aligned_events[0].reserve(pair_off[i + 1] - pair_off[i]);
             for (uint64_t p = pair_off[i]; p < pair_off[i + 1]; ++p) r.aligned_events[0].push_back(AlignedPair{pairs[2 * p], pairs[2 * p + 1]});
             r.rc[0] = rc[i];
             batch_reads.push_back(std::move(r));
@@ -327,6 +328,7 @@ double nphh_methylation_enumerate_seconds(int n_reads, const int32_t* read, cons
             r.contig = contig;
             r.ref_start_pos = ref_start[i];
             r.ref_seq = ref_seqs[i];
+            r.aligned_events[0].reserve(pair_off[i + 1] - pair_off[i]);
             for (uint64_t p = pair_off[i]; p < pair_off[i + 1]; ++p) r.aligned_events[0].push_back(AlignedPair{pairs[2 * p], pairs[2 * p + 1]});
             r.rc[0] = rc[i];
         }
