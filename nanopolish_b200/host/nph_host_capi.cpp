@@ -308,6 +308,40 @@ long long nphh_call_methylation_timed(int n_reads, const int32_t* read, const ch
                                  n_jobs_out, secs3);
 }
 
+// modBAM tags of one record from explicit calls (start position, site sequence, strand-0 log-likelihoods); reference_mode:
+// create_reference_modbam_record (seq = reference over the record, aligned pairs unused).  Returns the number of Ml entries.
+long long nphh_modbam_tags(const char* seq, int ref_pos, int flag, const uint32_t* cigar, int n_cigar, int n_calls, const int32_t* start_pos,
+                           const char** site_seqs, const double* ll_m0, const double* ll_u0, int reference_mode, char* mm_out, size_t mm_cap,
+                           uint8_t* ml_out, size_t ml_cap)
+{
+    long long n = -1;
+    int rc = guard([&] {
+        std::map<int, ScoredSite> calls;
+        for (int i = 0; i < n_calls; ++i) {
+            ScoredSite ss;
+            ss.start_position = start_pos[i];
+            ss.sequence = site_seqs[i];
+            ss.ll_methylated[0] = ll_m0[i];
+            ss.ll_unmethylated[0] = ll_u0[i];
+            calls[start_pos[i]] = ss;
+        }
+        MethylationCallingParameters params;
+        ModbamTags t;
+        if (reference_mode) {
+            t = reference_modbam_tags(seq, ref_pos, calls, params);
+        } else {
+            const std::vector<AlignedSegment> segs = get_aligned_segments(ref_pos, std::vector<uint32_t>(cigar, cigar + n_cigar));
+            if (segs.size() > 1) throw Error(NPH_ERR_UNSUPPORTED, "spliced alignment");       // the reference exits
+            t = modbam_tags(seq, segs[0], (flag & NPH_BAM_FREVERSE) != 0, calls, params);
+        }
+        if (t.mm.size() + 1 > mm_cap || t.ml.size() > ml_cap) throw Error(NPH_ERR_INVALID, "tag buffers too small");
+        std::memcpy(mm_out, t.mm.c_str(), t.mm.size() + 1);
+        std::memcpy(ml_out, t.ml.data(), t.ml.size());
+        n = (long long)t.ml.size();
+    });
+    return rc ? rc : n;
+}
+
 // enumeration only (no device): seconds spent in MethylationCaller::add_read over all reads, and the job count
 // parallel != 0: MethylationCaller::add_reads (host_threads() workers); jobs_out / ranks_out (optional) receive the job list
 double nphh_methylation_enumerate_seconds(int n_reads, const int32_t* read, const char** read_names, const uint8_t* is_rev, const uint8_t* rc,

@@ -26,6 +26,111 @@ bool find_by_ref_bounds(const std::vector<AlignedPair>& pairs, int ref_start, in
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// modBAM tags
+// ---------------------------------------------------------------------------------------------
+char unmodified_symbol_of(const Alphabet* alphabet)
+{
+    if (alphabet->num_recognition_sites() != 1) throw Error(NPH_ERR_UNSUPPORTED, "modBAM output needs an alphabet with one recognition site");
+    char unmodified = 'N';
+    const char* modified_motif = alphabet->get_recognition_site_methylated(0);
+    for (size_t i = 0; i < alphabet->recognition_length(); ++i)
+        if (modified_motif[i] == METHYLATED_SYMBOL) unmodified = alphabet->get_recognition_site(0)[i];
+    if (unmodified == 'N') throw Error(NPH_ERR_INVALID, "alphabet without a methylated symbol");
+    return unmodified;
+}
+
+void calculate_call_vectors(const std::map<int, ScoredSite>& calls, const Alphabet* alphabet,
+                            std::vector<size_t>& call_reference_positions, std::vector<uint8_t>& call_probabilities)
+{
+    for (const auto& kv : calls) {
+        const ScoredSite& call = kv.second;
+        // the called positions are where methylate() puts the symbol; start_position is the first site of the group, so
+        // the flank in front of it is subtracted
+        const std::string m_seq = alphabet->methylate(call.sequence);
+        const size_t flank_offset = m_seq.find_first_of(METHYLATED_SYMBOL);
+        if (flank_offset == std::string::npos) throw Error(NPH_ERR_INVALID, "scored site without a motif");      // the reference asserts
+        // shared by every motif of the group; strand 0 only, as in the reference
+        const double methylation_probability = std::exp(call.ll_methylated[0]) / (std::exp(call.ll_methylated[0]) + std::exp(call.ll_unmethylated[0]));
+        const uint8_t code = (uint8_t)std::min(255, (int)(methylation_probability * 255));
+        for (size_t j = 0; j < m_seq.size(); j++) {
+            if (m_seq[j] == METHYLATED_SYMBOL) {
+                call_reference_positions.push_back((size_t)(call.start_position + (int)j - (int)flank_offset));
+                call_probabilities.push_back(code);
+            }
+        }
+    }
+}
+
+std::string generate_mm_tag(char unmodified_symbol, const std::string& sequence, const std::vector<size_t>& call_seq_indices)
+{
+    std::string delta_str;
+    delta_str += unmodified_symbol;
+    delta_str += "+m?";
+    size_t count_start = 0;
+    for (size_t call_index = 0; call_index < call_seq_indices.size(); ++call_index) {
+        // unmodified bases skipped since the previous listed position
+        int count = 0;
+        for (size_t j = count_start; j < call_seq_indices[call_index]; ++j) count += sequence[j] == unmodified_symbol;
+        delta_str += ',';
+        delta_str += std::to_string(count);
+        count_start = call_seq_indices[call_index] + 1;
+    }
+    delta_str += ';';
+    return delta_str;
+}
+
+ModbamTags modbam_tags(const std::string& bam_seq, const std::vector<AlignedPair>& aligned_bases, bool is_reverse,
+                       const std::map<int, ScoredSite>& calls, const MethylationCallingParameters& params)
+{
+    const Alphabet* alphabet = params.alphabet ? params.alphabet : get_alphabet_by_name(params.methylation_type);
+    if (std::string(alphabet->get_name()) != "cpg") throw Error(NPH_ERR_UNSUPPORTED, "modBAM output supports the cpg alphabet only");   // the reference asserts
+    const char unmodified_symbol = unmodified_symbol_of(alphabet);
+    std::vector<size_t> call_reference_positions;
+    std::vector<uint8_t> call_reference_probabilities;
+    calculate_call_vectors(calls, alphabet, call_reference_positions, call_reference_probabilities);
+
+    // reference position -> index into the read as sequenced
+    const std::string original_sequence = !is_reverse ? bam_seq : gDNAAlphabet.reverse_complement(bam_seq);
+    std::map<size_t, size_t> reference_to_read_map;
+    for (const AlignedPair& ap : aligned_bases)
+        reference_to_read_map[(size_t)ap.ref_pos] = !is_reverse ? (size_t)ap.read_pos : original_sequence.length() - (size_t)ap.read_pos - 1;
+    // a CG read from the opposite strand has its C aligned to the reference G
+    const size_t strand_offset = !is_reverse ? 0 : 1;
+    ModbamTags out;
+    std::vector<size_t> call_seq_indices;
+    for (size_t i = 0; i < call_reference_positions.size(); ++i) {
+        auto iter = reference_to_read_map.find(call_reference_positions[i] + strand_offset);
+        if (iter == reference_to_read_map.end()) continue;
+        const size_t read_index = iter->second;
+        if (read_index < original_sequence.size() && original_sequence[read_index] == unmodified_symbol) {
+            call_seq_indices.push_back(read_index);
+            out.ml.push_back(call_reference_probabilities[i]);
+        }
+    }
+    // SEQ is reverse complemented for reverse-strand records: list the calls in the original direction
+    if (is_reverse) {
+        std::reverse(call_seq_indices.begin(), call_seq_indices.end());
+        std::reverse(out.ml.begin(), out.ml.end());
+    }
+    out.mm = generate_mm_tag(unmodified_symbol, original_sequence, call_seq_indices);
+    return out;
+}
+
+ModbamTags reference_modbam_tags(const std::string& ref_seq, int ref_start_pos, const std::map<int, ScoredSite>& calls,
+                                 const MethylationCallingParameters& params)
+{
+    const Alphabet* alphabet = params.alphabet ? params.alphabet : get_alphabet_by_name(params.methylation_type);
+    const char unmodified_symbol = unmodified_symbol_of(alphabet);
+    std::vector<size_t> call_reference_positions;
+    ModbamTags out;
+    calculate_call_vectors(calls, alphabet, call_reference_positions, out.ml);
+    std::vector<size_t> indices;
+    for (size_t pos : call_reference_positions) indices.push_back(pos - (size_t)ref_start_pos);
+    out.mm = generate_mm_tag(unmodified_symbol, ref_seq, indices);
+    return out;
+}
+
 MethylationCaller::MethylationCaller(const MethylationCallingParameters& params) : m_params(params)
 {
     if (!m_params.alphabet) m_params.alphabet = get_alphabet_by_name(m_params.methylation_type);

@@ -5,6 +5,8 @@
 //   ScoredSite, MethylationCallingParameters   ref: src/basemods/nanopolish_basemods.h:45-77
 //   AlignmentDB::_find_by_ref_bounds    ref: src/alignment/nanopolish_alignment_db.cpp:688-731
 //   write_methylation_results_as_tsv    ref: src/nanopolish_call_methylation.cpp:532-550
+//   create_modbam_record / create_reference_modbam_record (the Mm / Ml tags of --modbam-output)
+//                                       ref: src/basemods/nanopolish_basemods.cpp:35-177, 179-238
 //
 // The reference scores two sequences per CpG group with two profile_hmm_score calls inside the per-read OpenMP
 // loop.  Here add_read() only enumerates (motif scan -> groups -> window -> event bounds) and appends two jobs per
@@ -50,6 +52,25 @@ struct EventAlignedRead {
     bool rc[2] = {false, false};
 };
 
+// ---- modBAM tags (SAM specification: Mm = delta-encoded positions of the modified base, Ml = probabilities 0..255) ----
+struct ModbamTags {
+    std::string mm;                // e.g. "C+m?,3,0,12;"
+    std::vector<uint8_t> ml;       // one entry per position listed in mm
+};
+// the unmodified base that the alphabet's methylated symbol replaces ('C' for cpg); the reference asserts one recognition site
+char unmodified_symbol_of(const Alphabet* alphabet);
+// reference position and probability code of every called site (strand-0 likelihoods, like the reference)
+void calculate_call_vectors(const std::map<int, ScoredSite>& calls, const Alphabet* alphabet,
+                            std::vector<size_t>& call_reference_positions, std::vector<uint8_t>& call_probabilities);
+std::string generate_mm_tag(char unmodified_symbol, const std::string& sequence, const std::vector<size_t>& call_seq_indices);
+// create_modbam_record: tags for the read's own BAM record.  bam_seq = SEQ as stored (reference orientation),
+// aligned_bases = get_aligned_segments(record)[0] (nph_eventalign.hpp), is_reverse = bam_is_rev(record).
+ModbamTags modbam_tags(const std::string& bam_seq, const std::vector<AlignedPair>& aligned_bases, bool is_reverse,
+                       const std::map<int, ScoredSite>& calls, const MethylationCallingParameters& params);
+// create_reference_modbam_record: tags against the (disambiguated) reference over the record's span
+ModbamTags reference_modbam_tags(const std::string& ref_seq, int ref_start_pos, const std::map<int, ScoredSite>& calls,
+                                 const MethylationCallingParameters& params);
+
 bool find_by_ref_bounds(const std::vector<AlignedPair>& pairs, int ref_start, int ref_stop, int& read_start, int& read_stop);
 
 class MethylationCaller {
@@ -70,6 +91,12 @@ public:
     void write_tsv(FILE* fp, size_t read_idx) const;
     std::string tsv(size_t read_idx) const;
     std::vector<std::string> tsv_batch() const;            // every read's rows, formatted by host_threads() workers
+    // the Mm / Ml tags of --modbam-output for one read of the batch (after run()): bam_seq and aligned_bases as in
+    // nph::modbam_tags
+    ModbamTags modbam(size_t read_idx, const std::string& bam_seq, const std::vector<AlignedPair>& aligned_bases) const
+    {
+        return modbam_tags(bam_seq, aligned_bases, m_reads[read_idx].is_reverse, m_reads[read_idx].sites, m_params);
+    }
     void clear();
 
 private:

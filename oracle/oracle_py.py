@@ -254,6 +254,21 @@ class RefOracle:
             raise RuntimeError("npref_eventalign: output buffer too small")
         return tsv.value.decode(), cs.value.decode(), ea[:n].copy()
 
+    def modbam(self, seq: str, ref_pos, flag, cigar, calls):
+        """create_modbam_record's Mm / Ml tags; calls = [(start_position, site sequence, ll_methylated[0], ll_unmethylated[0])]."""
+        cg = np.ascontiguousarray(cigar, np.uint32)
+        n = len(calls)
+        sp = np.array([c[0] for c in calls], np.int32)
+        seqs = (C.c_char_p * max(n, 1))(*[c[1].encode() for c in calls])
+        lm = np.array([c[2] for c in calls], np.float64); lu = np.array([c[3] for c in calls], np.float64)
+        mm = C.create_string_buffer(1 << 16); ml = np.zeros(1 << 14, np.uint8)
+        self.lib.npref_modbam.restype = C.c_longlong
+        k = self.lib.npref_modbam(seq.encode(), int(ref_pos), int(flag), _p(cg), int(cg.shape[0]), n, _p(sp), seqs, _p(lm), _p(lu),
+                                  mm, C.c_size_t(1 << 16), _p(ml), C.c_size_t(ml.shape[0]))
+        if k < 0:
+            raise RuntimeError("npref_modbam: output buffer too small")
+        return mm.value.decode(), ml[:k].copy()
+
     def kmer_ranks(self, model_h, seq: bytes, rc: bool):
         out = np.zeros(max(len(seq), 1), np.uint32)
         n = self.lib.npref_kmer_ranks(model_h, C.c_char_p(seq), int(rc), _p(out))

@@ -32,6 +32,7 @@
 #include "logsum.h"
 #include "nanopolish_eventalign.h"   // align_read_to_ref / emit_event_alignment_tsv (8f N1: segment chaining)
 #include "nanopolish_anchor.h"
+#include "nanopolish_basemods.h"     // create_modbam_record (the Mm / Ml tags of call-methylation --modbam-output)
 extern "C" {
 #include "event_detection.h"   // src/thirdparty/scrappie (C99)
 }
@@ -99,6 +100,29 @@ extern "C" hts_pos_t bam_endpos(const bam1_t* b)
     for(uint32_t i = 0; i < b->core.n_cigar; ++i)
         if(bam_cigar_type(bam_cigar_op(cigar[i])) & 2) rlen += bam_cigar_oplen(cigar[i]);
     return b->core.pos + (rlen ? rlen : 1);
+}
+// Three more htslib calls, reached from create_modbam_record / SequenceAlignmentRecord: the 4-bit base table, a record
+// copy, and the two aux-tag writers, which here just keep what the reference hands them.
+extern "C" const char seq_nt16_str[] = "=ACMGRSVTWYHKDBN";
+namespace { thread_local std::string g_mm_tag; thread_local std::vector<uint8_t> g_ml_tag; }
+extern "C" bam1_t* bam_dup1(const bam1_t* b)
+{
+    bam1_t* c = (bam1_t*)calloc(1, sizeof(bam1_t));
+    *c = *b;
+    c->data = (uint8_t*)malloc(b->l_data > 0 ? b->l_data : 1);
+    memcpy(c->data, b->data, b->l_data);
+    c->m_data = b->l_data;
+    return c;
+}
+extern "C" int bam_aux_update_str(bam1_t*, const char tag[2], int len, const char* data)
+{
+    if(tag[0] == 'M' && tag[1] == 'm') g_mm_tag.assign(data, len > 0 ? len - 1 : 0);
+    return 0;
+}
+extern "C" int bam_aux_update_array(bam1_t*, const char tag[2], uint8_t type, uint32_t items, void* data)
+{
+    if(tag[0] == 'M' && tag[1] == 'l' && type == 'C') g_ml_tag.assign((uint8_t*)data, (uint8_t*)data + items);
+    return 0;
 }
 std::vector<uint32_t> event_alignment_to_cigar(const std::vector<EventAlignment>& alignments);   // nanopolish_eventalign.cpp:256
 std::string cigar_ops_to_string(const std::vector<uint32_t>& ops);                                 // :246
@@ -363,6 +387,51 @@ int npref_trim_raw(const float* raw, size_t n, int trim_start, int trim_end, int
 }
 
 int npref_max_threads(void) { return omp_get_max_threads(); }
+
+// ---- modBAM tags: create_modbam_record (src/basemods/nanopolish_basemods.cpp:107-177) on a hand-built record ----
+// seq = SEQ as stored in the BAM; calls = (start_position, site sequence, strand-0 log-likelihoods) of each ScoredSite.
+// Returns the number of Ml entries; mm_out receives the Mm string.
+long long npref_modbam(const char* seq, int ref_pos, int flag, const uint32_t* cigar, int n_cigar, int n_calls, const int32_t* start_pos,
+                       const char** site_seqs, const double* ll_m0, const double* ll_u0, char* mm_out, size_t mm_cap,
+                       uint8_t* ml_out, size_t ml_cap)
+{
+    const size_t l_qseq = strlen(seq);
+    std::vector<uint8_t> data(4 + 4 * (size_t)n_cigar + (l_qseq + 1) / 2 + l_qseq);
+    memcpy(data.data(), "r\0\0\0", 4);
+    memcpy(data.data() + 4, cigar, 4 * (size_t)n_cigar);
+    uint8_t* pseq = data.data() + 4 + 4 * (size_t)n_cigar;
+    for(size_t i = 0; i < l_qseq; ++i) {
+        const char* at = strchr(seq_nt16_str, seq[i]);
+        const uint8_t code = at ? (uint8_t)(at - seq_nt16_str) : 15;
+        pseq[i >> 1] |= code << ((~i & 1) << 2);
+    }
+    bam1_t rec;
+    memset(&rec, 0, sizeof(rec));
+    rec.core.pos = ref_pos; rec.core.tid = 0; rec.core.flag = (uint16_t)flag; rec.core.l_qname = 4; rec.core.l_extranul = 2;
+    rec.core.n_cigar = n_cigar; rec.core.l_qseq = (int32_t)l_qseq; rec.core.mtid = -1; rec.core.mpos = -1;
+    rec.data = data.data(); rec.l_data = (int)data.size(); rec.m_data = (uint32_t)data.size();
+
+    std::map<int, ScoredSite> calls;
+    for(int i = 0; i < n_calls; ++i) {
+        ScoredSite ss;
+        ss.start_position = start_pos[i];
+        ss.end_position = start_pos[i];
+        ss.n_motif = 1;
+        ss.sequence = site_seqs[i];
+        ss.ll_methylated[0] = ll_m0[i];
+        ss.ll_unmethylated[0] = ll_u0[i];
+        calls[start_pos[i]] = ss;
+    }
+    MethylationCallingParameters params;
+    params.alphabet = get_alphabet_by_name(params.methylation_type);
+    g_mm_tag.clear(); g_ml_tag.clear();
+    bam1_t* out = create_modbam_record(&rec, calls, params);
+    free(out->data); free(out);
+    if(g_mm_tag.size() + 1 > mm_cap || g_ml_tag.size() > ml_cap) return -1;
+    memcpy(mm_out, g_mm_tag.c_str(), g_mm_tag.size() + 1);
+    memcpy(ml_out, g_ml_tag.data(), g_ml_tag.size());
+    return (long long)g_ml_tag.size();
+}
 
 // ---- eventalign: segment chaining + TSV (src/alignment/nanopolish_eventalign.cpp:612-827, :398-484, :256-325) ----
 // What SquiggleRead carries beyond the events once load_from_raw has run: the basecalled sequence, the
