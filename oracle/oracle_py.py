@@ -254,6 +254,20 @@ class RefOracle:
             raise RuntimeError("npref_eventalign: output buffer too small")
         return tsv.value.decode(), cs.value.decode(), ea[:n].copy()
 
+    def score_variants_thresholded(self, read_handles, windows, rc, ref_seq: str, ref_position, variants, flags, threshold,
+                                   methylation: bool, indel_bias=1.0):
+        """[score_variant_thresholded(v, Haplotype(ref), reads, flags, threshold, types).quality for v in variants], single thread"""
+        n, nv = len(read_handles), len(variants)
+        rh = np.ascontiguousarray(read_handles, np.int32)
+        es = np.array([w[0] for w in windows], np.uint32); ee = np.array([w[1] for w in windows], np.uint32)
+        rcs = np.ascontiguousarray(rc, np.uint8)
+        pos = (C.c_size_t * nv)(*[v[0] for v in variants])
+        refs = (C.c_char_p * nv)(*[v[1].encode() for v in variants]); alts = (C.c_char_p * nv)(*[v[2].encode() for v in variants])
+        q = np.zeros(nv)
+        self.lib.npref_score_variants_thresholded(n, _p(rh), _p(es), _p(ee), _p(rcs), ref_seq.encode(), C.c_size_t(ref_position), nv, pos, refs,
+                                                  alts, C.c_uint32(flags), C.c_uint32(threshold), int(methylation), C.c_double(indel_bias), _p(q))
+        return q
+
     def modbam(self, seq: str, ref_pos, flag, cigar, calls):
         """create_modbam_record's Mm / Ml tags; calls = [(start_position, site sequence, ll_methylated[0], ll_unmethylated[0])]."""
         cg = np.ascontiguousarray(cigar, np.uint32)

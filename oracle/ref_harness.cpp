@@ -33,6 +33,8 @@
 #include "nanopolish_eventalign.h"   // align_read_to_ref / emit_event_alignment_tsv (8f N1: segment chaining)
 #include "nanopolish_anchor.h"
 #include "nanopolish_basemods.h"     // create_modbam_record (the Mm / Ml tags of call-methylation --modbam-output)
+#include "nanopolish_variant.h"      // score_variant_thresholded (8f N2)
+#include "nanopolish_haplotype.h"
 extern "C" {
 #include "event_detection.h"   // src/thirdparty/scrappie (C99)
 }
@@ -387,6 +389,46 @@ int npref_trim_raw(const float* raw, size_t n, int trim_start, int trim_end, int
 }
 
 int npref_max_threads(void) { return omp_get_max_threads(); }
+
+// ---- variants: score_variant_thresholded (src/common/nanopolish_variant.cpp:765-799) for each candidate, one OpenMP thread
+// so that its early exit (stop adding reads once |sum| >= threshold) follows read order deterministically.
+// Reads: whole-read windows [e_start, e_stop] with the given rc flag, base model = the read's.  methylation: 0 = none, 1 = {"cpg"}.
+int npref_score_variants_thresholded(int n_reads, const int32_t* read_h, const uint32_t* e_start, const uint32_t* e_stop, const uint8_t* rc,
+                                     const char* ref_seq, size_t ref_position, int n_var, const size_t* var_pos, const char** var_ref,
+                                     const char** var_alt, uint32_t alignment_flags, uint32_t score_threshold, int methylation,
+                                     double indel_bias, double* quality_out)
+{
+    const double saved_bias = hmm_indel_bias_factor;
+    hmm_indel_bias_factor = indel_bias;
+    const int saved_threads = omp_get_max_threads();
+    omp_set_num_threads(1);
+    std::vector<HMMInputData> input(n_reads);
+    for(int j = 0; j < n_reads; ++j) {
+        HMMInputData& d = input[j];
+        d.read = g_reads[read_h[j]].get();
+        d.pore_model = d.read->get_base_model(0);
+        d.strand = 0;
+        d.event_start_idx = e_start[j];
+        d.event_stop_idx = e_stop[j];
+        d.rc = rc[j];
+        d.event_stride = d.event_start_idx <= d.event_stop_idx ? 1 : -1;
+    }
+    std::vector<std::string> methylation_types;
+    if(methylation) methylation_types.push_back("cpg");
+    Haplotype base("contig", ref_position, ref_seq);
+    for(int v = 0; v < n_var; ++v) {
+        Variant var;
+        var.ref_name = "contig";
+        var.ref_position = var_pos[v];
+        var.ref_seq = var_ref[v];
+        var.alt_seq = var_alt[v];
+        var.quality = 0.0;
+        quality_out[v] = score_variant_thresholded(var, base, input, alignment_flags, score_threshold, methylation_types).quality;
+    }
+    omp_set_num_threads(saved_threads);
+    hmm_indel_bias_factor = saved_bias;
+    return 0;
+}
 
 // ---- modBAM tags: create_modbam_record (src/basemods/nanopolish_basemods.cpp:107-177) on a hand-built record ----
 // seq = SEQ as stored in the BAM; calls = (start_position, site sequence, strand-0 log-likelihoods) of each ScoredSite.

@@ -70,23 +70,48 @@ def _expected_quality(port_oracle, rs, model_list, jobs_for, variants_seqs, base
     return out
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("meth,threshold", [(False, 100), (True, 30)])
-def test_score_variants_thresholded(host, port_oracle, meth, threshold):
+def _variant_case():
     nuc, cpg = synth.load_model("nucleotide"), synth.load_model("cpg")
     rng = np.random.default_rng(11)
     codes = rng.integers(0, 4, 46, dtype=np.uint8)
     codes[20:22] = [1, 2]                                     # a CpG inside the window
     ref = synth._CODE2DNA[codes].tobytes().decode()
     rs = synth.gen_reads_from_sequence(codes, 14, nuc, seed=500)
+    # candidates: substitutions, a deletion, an insertion, and one that does not apply
+    cands = [(1000 + 10, ref[10], "ACGT".replace(ref[10], "")[0]), (1000 + 20, "C", "T"), (1000 + 30, ref[30:32], ref[30]),
+             (1000 + 15, ref[15], ref[15] + "GA"), (1000 + 25, "ACGT".replace(ref[25], "")[1], "A")]
+    return nuc, cpg, codes, ref, rs, cands
+
+
+@pytest.mark.parametrize("meth,threshold", [(False, 100), (True, 30)])
+def test_expectation_is_the_compiled_reference(host, port_oracle, ref_oracle, meth, threshold):
+    """The expectation the GPU test below holds the C++ batcher to — composed from oracle scores, the score-set logsum and
+    the read-order early exit — equals the COMPILED reference's score_variant_thresholded (src/common/nanopolish_variant.cpp:
+    765-799, one OpenMP thread) for every candidate, including the one that does not apply."""
+    nuc, cpg, codes, ref, rs, cands = _variant_case()
+    windows = [(0, int(rs.reads[j]["n_events"]) - 1) for j in range(rs.n_reads)]
+    vseqs = []
+    for p_, r_, a_ in cands:
+        rc, s_ = _apply(host, ref, 1000, [(p_, r_, a_)])
+        vseqs.append(s_ if rc >= 0 else None)
+    want = _expected_quality(port_oracle, rs, [nuc, cpg], windows, vseqs, ref, threshold, 0.8, meth)
+    ref_oracle.clear_reads()
+    rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, ref_oracle.builtin_model("nucleotide"))
+    got = ref_oracle.score_variants_thresholded(rh, windows, np.zeros(rs.n_reads, np.uint8), ref, 1000, cands, 0, threshold, meth, indel_bias=0.8)
+    ref_oracle.clear_reads()
+    assert list(got) == want, (list(got), want)
+    assert got[-1] == 0.0 and (got[:-1] < 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("meth,threshold", [(False, 100), (True, 30)])
+def test_score_variants_thresholded(host, port_oracle, meth, threshold):
+    nuc, cpg, codes, ref, rs, cands = _variant_case()
     mh, ch = _register(host, nuc), _register(host, cpg)
     rh = _register_reads(host, rs, mh)
     for r in rh:
         host.nphh_read_add_model(r, b"cpg", ch)
     windows = [(0, int(rs.reads[j]["n_events"]) - 1) for j in range(rs.n_reads)]
-    # candidates: substitutions, a deletion, an insertion, and one that does not apply
-    cands = [(1000 + 10, ref[10], "ACGT".replace(ref[10], "")[0]), (1000 + 20, "C", "T"), (1000 + 30, ref[30:32], ref[30]),
-             (1000 + 15, ref[15], ref[15] + "GA"), (1000 + 25, "ACGT".replace(ref[25], "")[1], "A")]
     vseqs = []
     for p, r_, a_ in cands:
         rc, s = _apply(host, ref, 1000, [(p, r_, a_)])
