@@ -239,6 +239,18 @@ class RefOracle:
         sd, du = np.ascontiguousarray(stdv, np.float32), np.ascontiguousarray(duration, np.float32)
         self.lib.npref_read_set_eventalign(int(read_h), name.encode(), read_sequence.encode(), _p(a), _p(b), C.c_size_t(a.shape[0]), _p(sd), _p(du))
 
+    def read_set_samples(self, read_h, samples, sample_rate):
+        a = np.ascontiguousarray(samples, np.float32)
+        self.lib.npref_read_set_samples(int(read_h), _p(a), C.c_size_t(a.shape[0]), C.c_double(sample_rate))
+
+    def event_samples(self, read_h, event_idx):
+        """(start_idx, end_idx, scaled samples) of one event: SquiggleRead::get_event_sample_idx / get_scaled_samples_for_event"""
+        idx = np.zeros(2, np.uint64); out = np.zeros(4096, np.float32)
+        self.lib.npref_event_samples.restype = C.c_longlong
+        n = self.lib.npref_event_samples(int(read_h), C.c_size_t(int(event_idx)), _p(idx), _p(out), C.c_size_t(out.shape[0]))
+        assert n >= 0
+        return int(idx[0]), int(idx[1]), out[:n].copy()
+
     def eventalign(self, read_h, contig_name: str, contig: str, ref_pos, flag, cigar, read_idx, region=(-1, -1), want_cigar=True):
         """align_read_to_ref + emit_event_alignment_tsv (default options) + the SAM writer's event CIGAR.
         Returns (tsv text, cigar string, int32[n, 3] of (ref_position, event_idx, ord(state)))."""

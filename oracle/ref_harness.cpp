@@ -8,7 +8,8 @@
 //   estimate_scalings_using_mom            (src/nanopolish_raw_loader.cpp:17-60)
 //   HMMInputSequence::get_kmer_rank        (src/hmm/nanopolish_hmm_input_sequence.h:76-91)
 //   Alphabet::{reverse_complement,methylate,unmethylate,disambiguate}
-// on flat arrays.  Reads are assembled by hand exactly like the reference's own
+// and (via --gc-sections, see oracle/Makefile) eventalign's align_read_to_ref + TSV writer, create_modbam_record,
+// score_variant_thresholded and SquiggleRead's small members, on flat arrays.  Reads are assembled by hand exactly like the reference's own
 // "scalings" unit test does (src/test/nanopolish_test.cpp:279-311): default-construct a
 // SquiggleRead, set pore_type / base_model / scalings / events_per_base, push events.
 //
@@ -41,43 +42,10 @@ extern "C" {
 
 extern double hmm_indel_bias_factor;   // src/hmm/nanopolish_profile_hmm_r9.cpp:19
 
-// Out-of-line members that live in nanopolish_squiggle_read.cpp, which we do not link
-// (it needs HDF5 + Eigen).  Semantics follow src/nanopolish_squiggle_read.cpp:38-65, :155-158.
-void SquiggleScalings::set6(double _shift, double _scale, double _drift, double _var,
-                            double _scale_sd, double _var_sd)
-{
-    shift = _shift; scale = _scale; drift = _drift; var = _var;
-    scale_sd = _scale_sd; var_sd = _var_sd;
-    log_var = log(var);
-    scaled_var = var / scale;
-    log_scaled_var = log(scaled_var);
-}
-void SquiggleScalings::set4(double _shift, double _scale, double _drift, double _var)
-{
-    set6(_shift, _scale, _drift, _var, 1.0, 1.0);
-}
-SquiggleRead::~SquiggleRead() {}
-// Two more members of nanopolish_squiggle_read.cpp that eventalign's segment chaining calls; semantics follow
-// src/nanopolish_squiggle_read.cpp:160-186 (nearest k-mer with an event, looking backwards first, 1000 k-mers
-// either way).  The two sample accessors are only reached with --signal-index / --samples, which stay off here.
-int SquiggleRead::get_next_event(int start, int stop, int stride, uint32_t strand) const
-{
-    for(; start != stop; start += stride) {
-        int ei = base_to_event_map[start].indices[strand].start;
-        if(ei != -1) return ei;
-    }
-    return -1;
-}
-int SquiggleRead::get_closest_event_to(int k_idx, uint32_t strand) const
-{
-    int stop_before = std::max(0, k_idx - 1000);
-    int stop_after = std::min(k_idx + 1000, (int)base_to_event_map.size() - 1);
-    int event_before = get_next_event(k_idx, stop_before, -1, strand);
-    int event_after = get_next_event(k_idx, stop_after, 1, strand);
-    return event_before == -1 ? event_after : event_before;
-}
-std::pair<size_t, size_t> SquiggleRead::get_event_sample_idx(size_t, size_t) const { abort(); }
-std::vector<float> SquiggleRead::get_scaled_samples_for_event(size_t, size_t) const { abort(); }
+// nanopolish_squiggle_read.cpp itself is compiled in place and linked with --gc-sections (oracle/Makefile): its small
+// members (SquiggleScalings::set4/set6, the destructor, get_closest_event_to, get_event_sample_idx,
+// get_scaled_samples_for_event) are the reference's own; load_from_raw and the constructor that need HDF5, Eigen and the
+// read databases are never referenced and are dropped by the linker.
 
 // htslib is not built here; eventalign needs two of its calls.  Test doubles: the "FASTA index" is a contig held
 // in memory, bam_endpos is pos + reference length of the CIGAR (what htslib computes for a mapped record).
@@ -493,6 +461,27 @@ void npref_read_set_eventalign(int h, const char* read_name, const char* read_se
         sr.events[0][i].stdv = stdv[i];
         sr.events[0][i].duration = duration[i];
     }
+}
+
+// the trimmed raw samples load_from_raw keeps with SRF_LOAD_RAW_SAMPLES (src/nanopolish_squiggle_read.cpp:251-258)
+void npref_read_set_samples(int h, const float* samples, size_t n, double sample_rate)
+{
+    SquiggleRead& sr = *g_reads[h];
+    sr.samples.assign(samples, samples + n);
+    sr.sample_start_time = 0;
+    sr.sample_rate = sample_rate;
+}
+// SquiggleRead::get_event_sample_idx and ::get_scaled_samples_for_event (:399-428) of one event: what eventalign's
+// --signal-index / --samples columns print.  Returns the number of samples.
+long long npref_event_samples(int h, size_t event_idx, uint64_t* idx2_out, float* samples_out, size_t cap)
+{
+    const SquiggleRead& sr = *g_reads[h];
+    const std::pair<size_t, size_t> si = sr.get_event_sample_idx(0, event_idx);
+    idx2_out[0] = si.first; idx2_out[1] = si.second;
+    const std::vector<float> v = sr.get_scaled_samples_for_event(0, event_idx);
+    if(v.size() > cap) return -1;
+    memcpy(samples_out, v.data(), sizeof(float) * v.size());
+    return (long long)v.size();
 }
 
 // align_read_to_ref on a hand-built BAM record (pos, flag, CIGAR), then emit_event_alignment_tsv (default options)

@@ -67,6 +67,26 @@ def test_restatement_matches_compiled_reference(cases, restated, ref_oracle):
     ref_oracle.clear_reads()
 
 
+def test_sample_columns_match_compiled_reference(cases, ref_oracle):
+    """What --signal-index / --samples print per event — SquiggleRead::get_event_sample_idx and
+    get_scaled_samples_for_event — from the reference's own nanopolish_squiggle_read.cpp (compiled into oracle/_ref)
+    against the restatement the writer tests use (drift, shift and scale all non-trivial in these reads)."""
+    model, rs, cs = cases
+    ref_oracle.clear_reads()
+    rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, ref_oracle.builtin_model("nucleotide"))
+    for c in cs[:2]:
+        slot, r = EC.read_slot(c, rs.n_reads), c["read"]
+        ref_oracle.read_set_eventalign(rh[slot], r.name, r.read_sequence, r.b2e_start, c["b2e_stop"], r.stdv, r.duration)
+        smp = _raw_samples(slot)
+        ref_oracle.read_set_samples(rh[slot], smp, 4000.0)
+        for e in (0, 1, 17, 400, int(rs.reads[slot]["n_events"]) - 1):
+            a, b, v = ref_oracle.event_samples(rh[slot], e)
+            assert (a, b) == EP.event_sample_idx(r, e, 4000.0)
+            want = np.array(EP.scaled_samples(r, e, smp, 4000.0), np.float32)
+            assert v.shape == want.shape and np.array_equal(v.view(np.uint32), want.view(np.uint32))
+    ref_oracle.clear_reads()
+
+
 def test_restatement_matches_golden(cases, restated, golden):
     model, rs, cs = cases
     rows = 0
