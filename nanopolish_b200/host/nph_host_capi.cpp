@@ -5,6 +5,7 @@
 #include "nph_methylation.hpp"
 #include "nph_raw.hpp"
 #include "nph_eventalign.hpp"
+#include "nph_scorereads.hpp"
 #include <cmath>
 #include <chrono>
 #include <cstring>
@@ -617,6 +618,37 @@ long long nphh_rolling_ranks_check(const char* alphabet, const char* seq, uint32
 }
 
 long long nphh_ea_num_segments(int idx) { return (long long)g_aligner.num_segments(idx); }
+
+// ---- scorereads: model_score over the reads queued in the aligner (after nphh_ea_run / the CPU round driver) ------------
+// mode 0: enumerate only — jobs_out / ranks_out receive the job list (job.read = aligner read index of each job's read is NOT
+// rewritten: reads are deduplicated by SquiggleRead); mode 1: also run on the device, scores3_out[3 * i] = {score, n_events,
+// n_segments} per read.  ref_seqs[i] / ref_offsets[i]: the fetched reference of read i.  Returns the number of jobs.
+long long nphh_scorereads(int n_reads, const int32_t* read, const char** ref_seqs, const int32_t* ref_offsets, int events_per_segment, int mode,
+                          void* jobs_out, size_t cap_jobs, uint32_t* ranks_out, size_t cap_ranks, uint64_t* n_ranks_out, double* scores3_out)
+{
+    long long n = -1;
+    int rc = guard([&] {
+        ScoreReads sr((size_t)events_per_segment);
+        for (int i = 0; i < n_reads; ++i) sr.add_read(*g_reads[read[i]], 0, g_aligner.alignment((size_t)i), ref_seqs[i], ref_offsets[i]);
+        const HmmBatch& b = sr.batch();
+        n = (long long)b.jobs().size();
+        if (jobs_out && ranks_out) {
+            if (b.jobs().size() > cap_jobs || b.ranks().size() > cap_ranks) throw Error(NPH_ERR_INVALID, "dump buffers too small");
+            std::memcpy(jobs_out, b.jobs().data(), sizeof(nph_hmm_job) * b.jobs().size());
+            std::memcpy(ranks_out, b.ranks().data(), sizeof(uint32_t) * b.ranks().size());
+            *n_ranks_out = b.ranks().size();
+        }
+        if (mode == 1) {
+            sr.run(Engine::thread_default());
+            for (int i = 0; i < n_reads; ++i) {
+                scores3_out[3 * i] = sr.score((size_t)i).score;
+                scores3_out[3 * i + 1] = (double)sr.score((size_t)i).n_events;
+                scores3_out[3 * i + 2] = (double)sr.score((size_t)i).n_segments;
+            }
+        }
+    });
+    return rc ? rc : n;
+}
 
 // get_aligned_segments on a packed CIGAR: pairs_out = (ref_pos, read_pos) interleaved, seg_off[n_segments + 1]
 long long nphh_aligned_segments(int ref_pos, const uint32_t* cigar, int n_cigar, int32_t* pairs_out, size_t cap_pairs, uint64_t* seg_off, size_t cap_segs)
