@@ -282,6 +282,7 @@ public:
     HMMInputSequence(const std::string& seq) : m_alphabet(&gDNAAlphabet), m_seq(seq) { m_rc_seq = m_alphabet->reverse_complement(seq); }
     HMMInputSequence(const std::string& fwd, const Alphabet* alphabet) : m_alphabet(alphabet), m_seq(fwd) { m_rc_seq = m_alphabet->reverse_complement(m_seq); }
     HMMInputSequence(const std::string& fwd, const std::string& rc, const Alphabet* alphabet) : m_alphabet(alphabet), m_seq(fwd), m_rc_seq(rc) {}
+    HMMInputSequence(std::string&& fwd, std::string&& rc, const Alphabet* alphabet) : m_alphabet(alphabet), m_seq(std::move(fwd)), m_rc_seq(std::move(rc)) {}
 
     const std::string& get_sequence() const { return m_seq; }
     const Alphabet* get_alphabet() const { return m_alphabet; }

@@ -184,8 +184,8 @@ size_t MethylationCaller::add_read(const EventAlignedRead& r, int region_start, 
             const int span = motif_sites[end_idx - 1] - motif_sites[start_idx];
             if (sub_start_pos <= m_params.min_separation || span > 200) continue;
 
-            const std::string subseq = ref_seq.substr(sub_start_pos, sub_end_pos - sub_start_pos + 1);
-            const std::string rc_subseq = alphabet->reverse_complement(subseq);
+            std::string subseq = ref_seq.substr(sub_start_pos, sub_end_pos - sub_start_pos + 1);
+            std::string rc_subseq = alphabet->reverse_complement(subseq);
             const int calling_start = sub_start_pos + r.ref_start_pos;
             const int calling_end = sub_end_pos + r.ref_start_pos;
 
@@ -210,10 +210,10 @@ size_t MethylationCaller::add_read(const EventAlignedRead& r, int region_start, 
             // the reference scores first and filters by region afterwards; filtering first yields the same output
             if ((region_start != -1 && start_position < region_start) || (region_end != -1 && end_position >= region_end)) continue;
 
-            HMMInputSequence unmethylated(subseq, rc_subseq, alphabet);
-            const std::string m_subseq = alphabet->methylate(subseq);
-            const std::string rc_m_subseq = alphabet->reverse_complement(m_subseq);
-            HMMInputSequence methylated(m_subseq, rc_m_subseq, alphabet);
+            std::string m_subseq = alphabet->methylate(subseq);
+            std::string rc_m_subseq = alphabet->reverse_complement(m_subseq);
+            HMMInputSequence unmethylated(std::move(subseq), std::move(rc_subseq), alphabet);
+            HMMInputSequence methylated(std::move(m_subseq), std::move(rc_m_subseq), alphabet);
             const size_t ju = m_batch.add(unmethylated, data, hmm_flags);
             const size_t jm = m_batch.add(methylated, data, hmm_flags);
 

@@ -81,3 +81,55 @@ def test_rolling_ranks_equal_get_kmer_rank(host):
             for rc in (0, 1):
                 assert host.nphh_kmer_ranks_rolling_check(alphabet.encode(), seq.encode(), 6, rc) == 0, (alphabet, seq, rc)
     assert host.nphh_kmer_ranks_rolling_check(b"nucleotide", b"ACG", 6, 0) == 0
+
+
+def test_enumeration_equals_python_restatement(host):
+    """The job list itself (event bounds, strands, k-mer ranks of the unmethylated and methylated windows) against an
+    independent restatement of calculate_methylation_for_read's enumeration (src/basemods/nanopolish_basemods.cpp:238-
+    372) — the same one the GPU test scores — so the host-side fast paths are covered without a device."""
+    from tests.test_host_methylation import _find_by_ref_bounds, _ranks
+    nuc, cpg = synth.load_model("nucleotide"), synth.load_model("cpg")
+    rs = synth.gen_reads(9, 2200, nuc, seed=314, cpg_keep=0.3)
+    host.nphh_clear()
+    mh, ch = _register(host, nuc), _register(host, cpg)
+    rh = _register_reads(host, rs, mh)
+    for r in rh:
+        host.nphh_read_add_model(r, b"cpg", ch)
+    metas, want = [], []
+    for i in range(rs.n_reads):
+        codes = rs.seq_codes[i]
+        nk = codes.shape[0] - K + 1
+        kfe = np.minimum(rs.kmer_first_event[i], int(rs.reads[i]["n_events"]) - 1)
+        if i % 2:
+            ref = synth._CODE2DNA[(3 - codes[::-1]).astype(np.uint8)].tobytes().decode()
+            pairs = [(10_000 + p_, int(kfe[nk - 1 - p_])) for p_ in range(K, nk - K)]
+            rc = 1
+        else:
+            ref = synth._CODE2DNA[codes].tobytes().decode()
+            pairs = [(10_000 + p_, int(kfe[p_])) for p_ in range(K, nk - K)]
+            rc = 0
+        metas.append(dict(ref=ref, pairs=np.array(pairs, np.int32), rc=rc))
+        sites = [j for j in range(len(ref) - 1) if ref[j:j + 2] == "CG"]
+        cur = 0
+        while cur < len(sites):
+            end = cur + 1
+            while end < len(sites) and sites[end] - sites[end - 1] <= 10:
+                end += 1
+            first, last = sites[cur], sites[end - 1]
+            cur = end
+            sub_start, sub_end = first - 10, last + 10
+            if sub_start <= 10 or last - first > 200:
+                continue
+            b = _find_by_ref_bounds(pairs, sub_start + 10_000, sub_end + 10_000)
+            if b is None or abs(b[1] - b[0]) <= 10:
+                continue
+            subseq = ref[sub_start:sub_end + 1]
+            for seq in (subseq, subseq.replace("CG", "MG")):
+                want.append((i, b[0], b[1], 1 if b[0] <= b[1] else -1, rc, _ranks(host, "cpg", seq, rc)))
+    jobs, ranks = _enumerate(host, rh, metas, parallel=True)
+    assert jobs.shape[0] == len(want) > 300
+    for jb, (read, e1, e2, stride, rc, rk) in zip(jobs, want):
+        assert (int(jb["read"]), int(jb["event_start"]), int(jb["event_stop"]), int(jb["stride"]), int(jb["rc"]), int(jb["flags"])) == \
+            (read, e1, e2, stride, rc, 3)
+        assert np.array_equal(ranks[int(jb["rank_off"]):int(jb["rank_off"]) + int(jb["n_kmers"])], rk)
+    host.nphh_clear()
