@@ -428,14 +428,18 @@ size_t HmmBatch::add(const HMMInputSequence& sequence, const HMMInputData& data,
         throw Error(NPH_ERR_INVALID, "rc and event_stride disagree");                                       // ref asserts (profile_hmm_r9.inl:275)
     if (sequence.length() < k) throw Error(NPH_ERR_INVALID, "sequence shorter than k");
     ReadKey key{data.read, data.strand};
-    auto it = m_read_index.find(key);
     uint32_t ridx;
-    if (it == m_read_index.end()) {
-        ridx = (uint32_t)m_reads.size();
-        m_read_index[key] = ridx;
-        m_reads.push_back(key);
+    if (!m_reads.empty() && m_reads.back().read == key.read && m_reads.back().strand == key.strand) {
+        ridx = (uint32_t)m_reads.size() - 1;                 // consecutive jobs of one read: the common case
     } else {
-        ridx = it->second;
+        auto it = m_read_index.find(key);
+        if (it == m_read_index.end()) {
+            ridx = (uint32_t)m_reads.size();
+            m_read_index[key] = ridx;
+            m_reads.push_back(key);
+        } else {
+            ridx = it->second;
+        }
     }
     const uint32_t n_kmers = (uint32_t)(sequence.length() - k + 1);
     const int strand_slot = data.rc != 0 ? 1 : 0;
