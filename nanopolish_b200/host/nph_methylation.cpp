@@ -185,7 +185,6 @@ size_t MethylationCaller::add_read(const EventAlignedRead& r, int region_start, 
             if (sub_start_pos <= m_params.min_separation || span > 200) continue;
 
             std::string subseq = ref_seq.substr(sub_start_pos, sub_end_pos - sub_start_pos + 1);
-            std::string rc_subseq = alphabet->reverse_complement(subseq);
             const int calling_start = sub_start_pos + r.ref_start_pos;
             const int calling_end = sub_end_pos + r.ref_start_pos;
 
@@ -211,7 +210,11 @@ size_t MethylationCaller::add_read(const EventAlignedRead& r, int region_start, 
             if ((region_start != -1 && start_position < region_start) || (region_end != -1 && end_position >= region_end)) continue;
 
             std::string m_subseq = alphabet->methylate(subseq);
-            std::string rc_m_subseq = alphabet->reverse_complement(m_subseq);
+            // the jobs of this read only ever ask for the strand data.rc selects: the other strand's strings (the
+            // reference builds all four) are left empty
+            const bool need_rc = data.rc != 0;
+            std::string rc_subseq = need_rc ? alphabet->reverse_complement(subseq) : std::string();
+            std::string rc_m_subseq = need_rc ? alphabet->reverse_complement(m_subseq) : std::string();
             HMMInputSequence unmethylated(std::move(subseq), std::move(rc_subseq), alphabet);
             HMMInputSequence methylated(std::move(m_subseq), std::move(rc_m_subseq), alphabet);
             const size_t ju = m_batch.add(unmethylated, data, hmm_flags);
