@@ -61,6 +61,22 @@ def gather_to_rank0(local, counts: list[int] | None = None, group=None):
     return [b[:n] for b, n in zip(bufs, counts)]
 
 
+def gather_records_to_rank0(records: np.ndarray, device=None, group=None):
+    """The variable-length form: every rank holds a different number of fixed-size records — eventalign's
+    nph_ea_record rows, call-methylation's per-site results — as a numpy structured array.  One tiny all_gather of the
+    byte counts, then ONE padded gather of the raw bytes to rank 0, which gets the list of per-rank record arrays
+    (other ranks: None).  `device`: where the staging tensor lives ("cuda:<local>" under NCCL, None for gloo)."""
+    import torch
+
+    raw = torch.from_numpy(np.ascontiguousarray(records).view(np.uint8).reshape(-1).copy())
+    if device is not None:
+        raw = raw.to(device)
+    parts = gather_to_rank0(raw, None, group)
+    if parts is None:
+        return None
+    return [p.cpu().numpy().view(records.dtype) for p in parts]
+
+
 def scatter_results(parts_scores: list, owner: np.ndarray) -> np.ndarray:
     """Rank-0 reassembly: per-rank result vectors (in each rank's local job order) back to global job order."""
     out = np.empty(owner.shape[0], np.float32)

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from nanopolish_b200 import synth
-from nanopolish_b200.dist import gather_to_rank0, job_owner, partition_reads, scatter_results
+from nanopolish_b200.dist import gather_records_to_rank0, gather_to_rank0, job_owner, partition_reads, scatter_results
 
 
 def _free_port():
@@ -63,3 +63,44 @@ def test_two_rank_gather_matches_single_process(tmp_path):
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     full, want = np.load(out)
     assert np.array_equal(full.view(np.uint32), want.view(np.uint32))
+
+
+def _records_worker(rank, world, port, out_path):
+    """eventalign sharded by read: every rank aligns its reads (restatement + plain-C Viterbi here, the chain kernel on
+    the GPU box) and holds a different number of 12-byte records; rank 0 gets them with one padded gather."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import eventalign_py as EP
+    from oracle.oracle_py import PortOracle
+    from tests import eventalign_cases as EC
+    model, rs, cases = EC.build_cases(5, 700, seed=41)
+    cases = cases[:5]
+    parts = partition_reads(rs.reads["n_events"], world)
+    po = PortOracle()
+
+    def align(c):
+        al = EP.align_read_to_ref(c["read"], c["contig_name"], c["fetched"], c["ref_pos"], c["flag"], c["cigar"], c["read_idx"],
+                                  EC.port_align_fn(po, rs, model, EC.read_slot(c, rs.n_reads)))
+        rec = np.zeros(len(al), synth.EA_RECORD_DT)
+        for i, a in enumerate(al):
+            rec[i] = (a.ref_position, a.event_idx, a.hmm_state.encode(), (c["read_idx"], 0, 0))      # read index rides in the padding
+        return rec
+    mine = np.concatenate([align(cases[i]) for i in parts[rank]]) if parts[rank].size else np.zeros(0, synth.EA_RECORD_DT)
+    got = gather_records_to_rank0(mine)
+    if rank == 0:
+        assert len(got) == world and sum(g.shape[0] for g in got) > 2000 and len({g.shape[0] for g in got}) == world
+        merged = np.concatenate(got)
+        want = np.concatenate([align(c) for c in cases])
+        order = np.argsort(merged["reserved"][:, 0], kind="stable")          # back to read order
+        np.save(out_path, np.stack([merged[order].view(np.uint8).reshape(-1), want.view(np.uint8).reshape(-1)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_of_variable_length_records(tmp_path):
+    out = str(tmp_path / "rec.npy")
+    port = _free_port()
+    mp.spawn(_records_worker, args=(2, port, out), nprocs=2, join=True)
+    merged, want = np.load(out)
+    assert np.array_equal(merged, want)
