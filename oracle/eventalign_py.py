@@ -301,11 +301,10 @@ def sam(read: EARead, alignment, mapq) -> str:
         read.name, 16 if alignment[0].rc else 0, alignment[0].ref_name, alignment[0].ref_position + 1, mapq, event_cigar(alignment), stride)
 
 
-def summary_row(read: EARead, alignment, read_idx, fast5_path="read.fast5") -> str:
-    if not alignment:
-        return ""
+def summarize(read: EARead, alignment) -> dict:
+    """summarize_alignment (:486-537): movement counters in size_t arithmetic from npos, duration and z-score sums"""
     num_events = num_steps = num_stays = num_skips = 0
-    sum_duration = 0.0
+    sum_duration = sum_z = 0.0
     prev = None
     for i, ea in enumerate(alignment):
         num_events += 1
@@ -317,7 +316,21 @@ def summary_row(read: EARead, alignment, read_idx, fast5_path="read.fast5") -> s
         elif i != 0 and ref_move == 1:
             num_steps += 1
         sum_duration += float(np.float32(read.duration[ea.event_idx]))
+        if ea.hmm_state == "M":
+            mean, stdv = read.scaled_gaussian(kmer_rank(ea.model_kmer))
+            sum_z += float(np.float32(np.float32(read.drift_scaled_level(ea.event_idx) - mean) / stdv))     # z_score: float arithmetic
         prev = ea.ref_position
+    span = alignment[-1].ref_position - alignment[0].ref_position + 1 if alignment else 0
+    return dict(num_events=num_events, num_steps=num_steps, num_stays=num_stays, num_skips=num_skips, reference_span=span,
+                sum_duration=sum_duration, sum_z_score=sum_z)
+
+
+def summary_row(read: EARead, alignment, read_idx, fast5_path="read.fast5") -> str:
+    if not alignment:
+        return ""
+    sm = summarize(read, alignment)
+    num_events, num_steps, num_stays, num_skips, sum_duration = (sm["num_events"], sm["num_steps"], sm["num_stays"], sm["num_skips"],
+                                                                sm["sum_duration"])
     return "%d\t%s\t%s\t%s\t%s\t%d\t%d\t%d\t%d\t%.2f\t%.3f\t%.3f\t%.3f\t%.3f\n" % (
         read_idx, read.name, fast5_path, read.model_name, "template", num_events, num_steps, num_skips, num_stays,
         sum_duration, read.shift, read.scale, read.drift, read.var)

@@ -239,6 +239,13 @@ class RefOracle:
         sd, du = np.ascontiguousarray(stdv, np.float32), np.ascontiguousarray(duration, np.float32)
         self.lib.npref_read_set_eventalign(int(read_h), name.encode(), read_sequence.encode(), _p(a), _p(b), C.c_size_t(a.shape[0]), _p(sd), _p(du))
 
+    def eventalign_summary(self):
+        """summarize_alignment of the most recent eventalign() call: dict of its counters"""
+        ints = np.zeros(5, np.int32); dbl = np.zeros(2)
+        self.lib.npref_eventalign_summary(_p(ints), _p(dbl))
+        return dict(num_events=int(ints[0]), num_steps=int(ints[1]), num_stays=int(ints[2]), num_skips=int(ints[3]),
+                    reference_span=int(ints[4]), sum_duration=float(dbl[0]), sum_z_score=float(dbl[1]))
+
     def read_set_samples(self, read_h, samples, sample_rate):
         a = np.ascontiguousarray(samples, np.float32)
         self.lib.npref_read_set_samples(int(read_h), _p(a), C.c_size_t(a.shape[0]), C.c_double(sample_rate))

@@ -94,6 +94,18 @@ extern "C" int bam_aux_update_array(bam1_t*, const char tag[2], uint8_t type, ui
     if(tag[0] == 'M' && tag[1] == 'l' && type == 'C') g_ml_tag.assign((uint8_t*)data, (uint8_t*)data + items);
     return 0;
 }
+// summarize_alignment (nanopolish_eventalign.cpp:486-537) returns a struct that the reference defines inside its .cpp
+// (:131-153); the declaration below mirrors that layout so the function can be called.  It reads the record's NM tag
+// through two more htslib calls, answered here with "no tag" / 0.
+struct EventalignSummary {
+    int num_events, num_steps, num_stays, num_skips;
+    double sum_duration, sum_z_score;
+    int alignment_edit_distance, reference_span;
+};
+EventalignSummary summarize_alignment(const SquiggleRead& sr, uint32_t strand_idx, const EventAlignmentParameters& params,
+                                      const std::vector<EventAlignment>& alignments);
+extern "C" uint8_t* bam_aux_get(const bam1_t*, const char[2]) { return NULL; }
+extern "C" int64_t bam_aux2i(const uint8_t*) { return 0; }
 std::vector<uint32_t> event_alignment_to_cigar(const std::vector<EventAlignment>& alignments);   // nanopolish_eventalign.cpp:256
 std::string cigar_ops_to_string(const std::vector<uint32_t>& ops);                                 // :246
 
@@ -484,6 +496,7 @@ long long npref_event_samples(int h, size_t event_idx, uint64_t* idx2_out, float
     return (long long)v.size();
 }
 
+namespace { thread_local EventalignSummary g_last_summary; }
 // align_read_to_ref on a hand-built BAM record (pos, flag, CIGAR), then emit_event_alignment_tsv (default options)
 // into tsv_out and the event CIGAR of the SAM output into cigar_out.  Returns the number of EventAlignments, or -1
 // when tsv_cap is too small.  ea_out (optional) gets (ref_position, event_idx, hmm_state) triples.
@@ -531,7 +544,17 @@ long long npref_eventalign(int read_h, const char* contig_name, const char* cont
     for(size_t i = 0; i < alignment.size() && 3 * i + 2 < ea_cap; ++i) {
         ea_out[3 * i] = alignment[i].ref_position; ea_out[3 * i + 1] = alignment[i].event_idx; ea_out[3 * i + 2] = alignment[i].hmm_state;
     }
+    g_last_summary = summarize_alignment(*params.sr, 0, params, alignment);
     return (long long)alignment.size();
+}
+
+// the EventalignSummary of the most recent npref_eventalign call on this thread: {events, steps, stays, skips, span} and
+// {sum_duration, sum_z_score}
+void npref_eventalign_summary(int32_t* ints5, double* doubles2)
+{
+    ints5[0] = g_last_summary.num_events; ints5[1] = g_last_summary.num_steps; ints5[2] = g_last_summary.num_stays;
+    ints5[3] = g_last_summary.num_skips; ints5[4] = g_last_summary.reference_span;
+    doubles2[0] = g_last_summary.sum_duration; doubles2[1] = g_last_summary.sum_z_score;
 }
 
 } // extern "C"

@@ -62,6 +62,7 @@ def test_restatement_matches_compiled_reference(cases, restated, ref_oracle):
                                                c["read_idx"], c["region"], want_cigar=_single_segment(c))
         assert EP.tsv(r, al) == tsv
         assert [(a.ref_position, a.event_idx, ord(a.hmm_state)) for a in al] == [tuple(int(v) for v in row) for row in ea]
+        assert ref_oracle.eventalign_summary() == EP.summarize(r, al)                  # summarize_alignment's counters and sums
         if _single_segment(c):
             assert EP.event_cigar(al) == cigar
     ref_oracle.clear_reads()
