@@ -617,6 +617,16 @@ long long nphh_rolling_ranks_check(const char* alphabet, const char* seq, uint32
     return rc ? rc : bad;
 }
 
+// EventAligner::summarize: {events, steps, stays, skips, span} and {sum_duration, sum_z_score}
+int nphh_ea_summary(int idx, int32_t* ints5, double* doubles2)
+{
+    return guard([&] {
+        const EventalignSummary sm = g_aligner.summarize((size_t)idx);
+        ints5[0] = sm.num_events; ints5[1] = sm.num_steps; ints5[2] = sm.num_stays; ints5[3] = sm.num_skips; ints5[4] = sm.reference_span;
+        doubles2[0] = sm.sum_duration; doubles2[1] = sm.sum_z_score;
+    });
+}
+
 long long nphh_ea_num_segments(int idx) { return (long long)g_aligner.num_segments(idx); }
 
 // ---- scorereads: model_score over the reads queued in the aligner (after nphh_ea_run / the CPU round driver) ------------

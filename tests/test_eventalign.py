@@ -153,6 +153,11 @@ def _check_outputs(host, cases, restated, golden):
         assert _text(host, i, 2) == EP.tsv(r, al, scale_events=True)                       # --scale-events
         hdr = _text(host, 0, 6)[:-1] + "\tstart_idx\tend_idx\tsamples\n"
         assert _text(host, i, 7) == hdr + EP.tsv(r, al, samples=_raw_samples(EC.read_slot(c, rs.n_reads)), sample_rate=4000.0)   # --signal-index --samples
+        ints, dbl = np.zeros(5, np.int32), np.zeros(2)
+        assert host.nphh_ea_summary(i, _p(ints), _p(dbl)) == 0
+        sm = EP.summarize(r, al)
+        assert [int(v) for v in ints] == [sm["num_events"], sm["num_steps"], sm["num_stays"], sm["num_skips"], sm["reference_span"]]
+        assert (float(dbl[0]), float(dbl[1])) == (sm["sum_duration"], sm["sum_z_score"])
         assert host.nphh_ea_num_segments(i) == segs
         assert _text(host, i, 5) == EP.summary_row(r, al, i, "read.fast5").replace(r.model_name, "")   # host test models carry no name
         if _single_segment(c):
