@@ -219,6 +219,9 @@ int nph_mom_batch(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
  * event order; states_off has n_jobs + 1 entries and states_off[j+1] - states_off[j] is the room for job j
  * (n_events + n_kmers always suffices).  n_states_out[j] == 0 where the reference would trip an assert (fewer
  * than two events, or the best path runs into a -inf cell).  scores_out (optional) = l_fm of the last state.
+ * Limit: the movement trace of the batch's largest window, 2 * (E + K/C + 1) * 32*C bytes per warp (C = 1..8 columns per
+ * lane), is kept for every resident warp; the number of resident warps shrinks so that the arena stays within 16 GiB, and a
+ * window that needs more than that for a single CTA of 16 warps (E*K beyond ~1.6e7) returns NPH_ERR_UNSUPPORTED.
  * ref: profile_hmm_align_r9, src/hmm/nanopolish_profile_hmm_r9.cpp:73-204. */
 int nph_hmm_align_batch(nph_ctx* ctx,
                         const nph_read* reads, size_t n_reads,
@@ -283,6 +286,88 @@ int nph_eventalign_chain(nph_ctx* ctx,
                          const uint32_t* ref_ranks_fwd, const uint32_t* ref_ranks_rc, size_t n_ranks_total,
                          const nph_ea_chain* chains, size_t n_chains, double indel_bias,
                          nph_ea_record* records_out, size_t records_total, nph_ea_result* results_out);
+
+/* ---- call-methylation: window enumeration + both scores per motif group on the device (section 8f N3) -----
+ * calculate_methylation_for_read (src/basemods/nanopolish_basemods.cpp:238-457) from "Scan the sequence for motifs"
+ * (:301) to the two profile_hmm_score calls (:383-392), for a whole BamProcessor batch in one call: the motif scan,
+ * the grouping of sites closer than min_separation, the window (min_flank either side, span <= max_span, not within
+ * min_separation of the alignment start), AlignmentDB::_find_by_ref_bounds on the read's event alignment
+ * (src/alignment/nanopolish_alignment_db.cpp:688-731), the region filter, the unmethylated / methylated
+ * HMMInputSequence pair (Alphabet::methylate, reverse_complement with its methylated-site units) as k-mer ranks, and the
+ * two forward scores.  Nothing O(bases) or O(groups) is left to the host: it hands over the reference substring and
+ * the event alignment of each (record, strand) and receives one nph_meth_site per scored group.
+ * A record = one BAM record x one strand of its read.  ref_bases holds ref_seq of every record: the reference over
+ * [record->core.pos, bam_endpos], already through gDNAAlphabet.disambiguate() (upper-case ACGT).  aligned_events holds
+ * EventAlignmentRecord::aligned_events (ref_pos ascending, read_pos = event index; alignment_db.cpp:50-91). */
+#define NPH_METH_MAX_SITES 4
+#define NPH_METH_MAX_SITE_LEN 8
+#define NPH_METH_MAX_WINDOW 1024     /* max_span + 2 * min_flank + 1 must not exceed this */
+typedef struct {
+    uint64_t ref_off;         /* first base of this record's ref_seq in ref_bases[] */
+    uint64_t pair_off;        /* first aligned_events entry in aligned_events[] */
+    uint32_t read;            /* index into reads[]: events[strand] of the record's SquiggleRead */
+    uint32_t model_id;        /* sr.get_model(strand, methylation_type): the model over the methylation alphabet */
+    uint32_t ref_len;         /* ref_seq.size() */
+    uint32_t n_pairs;
+    int32_t  ref_start_pos;   /* record->core.pos */
+    uint8_t  rc;              /* EventAlignmentRecord::rc -> HMMInputData::rc */
+    uint8_t  strand;          /* informational (sites of the two strands of one read are merged by the caller) */
+    uint8_t  reserved[2];
+} nph_meth_record;            /* 40 bytes */
+typedef struct {
+    int32_t  min_separation;  /* MethylationCallingParameters::min_separation (10), basemods.h:56 */
+    int32_t  min_flank;       /* ::min_flank (10) */
+    int32_t  max_span;        /* 200: groups spanning more are skipped, basemods.cpp:336 */
+    int32_t  min_event_span;  /* 10: abs(e2 - e1) <= 10 skips the group, :363 */
+    int32_t  region_start;    /* -1: no restriction (the -w window), :398-401 */
+    int32_t  region_end;
+    uint32_t k;               /* sr.get_model_k(strand) */
+    uint32_t alphabet_size;   /* of the methylation alphabet (5 for cpg: ACGMT) */
+    char     bases[8];        /* its symbols in rank order, NUL padded ("ACGMT") */
+    char     complements[8];  /* complement of each symbol, same order ("TGCGA") */
+    uint32_t n_sites;         /* Alphabet::num_recognition_sites() (1 for cpg, 2 for dcm) */
+    uint32_t site_len;        /* Alphabet::recognition_length() */
+    char     sites[NPH_METH_MAX_SITES][NPH_METH_MAX_SITE_LEN];                        /* get_recognition_site(i): "CG" */
+    char     sites_methylated[NPH_METH_MAX_SITES][NPH_METH_MAX_SITE_LEN];             /* ..._methylated(i): "MG" */
+    char     sites_methylated_complement[NPH_METH_MAX_SITES][NPH_METH_MAX_SITE_LEN];  /* ..._methylated_complement(i): "GM" */
+} nph_meth_params;
+/* One scored group of one record == the strand-specific half of a ScoredSite (basemods.h:25-43). */
+typedef struct {
+    int32_t  start_position;  /* first motif site of the group, reference coordinates */
+    int32_t  end_position;    /* last motif site of the group */
+    uint32_t n_motif;
+    uint32_t record;          /* index into records[] */
+    float    ll_unmethylated; /* profile_hmm_score(unmethylated, data, PRE_CLIP | POST_CLIP) */
+    float    ll_methylated;
+} nph_meth_site;              /* 24 bytes */
+/* One-shot: host buffers in, host sites out (synchronous).  site_off_out has n_records + 1 entries: the sites of
+ * record r are sites_out[site_off_out[r] .. site_off_out[r+1]) in ascending start_position.  sites_cap is the room in
+ * sites_out; sum over records of (ref_len / (min_separation + 1) + 2) always suffices, NPH_ERR_INVALID if it was too
+ * small (nph_last_error says how many were needed).  n_scored_events_out (optional): sum over groups of 2 * (abs(e2 - e1) + 1),
+ * the unit of the events/s metric.  A group whose event indices lie outside its read (the reference would read out of
+ * bounds) or whose clamped window is shorter than k yields NPH_ERR_INVALID. */
+int nph_methylation_batch(nph_ctx* ctx,
+                          const nph_read* reads, size_t n_reads,
+                          const float* ev_mean, const double* ev_start_time, size_t n_events_total,
+                          const char* ref_bases, size_t n_ref_total,
+                          const nph_aligned_pair* aligned_events, size_t n_pairs_total,
+                          const nph_meth_record* records, size_t n_records,
+                          const nph_meth_params* params, double indel_bias,
+                          uint64_t* site_off_out, nph_meth_site* sites_out, size_t sites_cap,
+                          uint64_t* n_scored_events_out);
+/* Staged form against the reads a preceding nph_reads_load left resident:
+ *   nph_methylation_load : H2D of the reference bases, event alignments and records
+ *   nph_methylation_run  : enumerate -> schedule -> score -> fill the site records, all on the device
+ *                          (two small read-backs inside: the counts that size the job arrays, the schedule summary)
+ *   nph_methylation_fetch: D2H of the offsets and site records */
+int nph_methylation_load(nph_ctx* ctx, const char* ref_bases, size_t n_ref_total,
+                         const nph_aligned_pair* aligned_events, size_t n_pairs_total,
+                         const nph_meth_record* records, size_t n_records,
+                         const nph_meth_params* params, double indel_bias);
+int nph_methylation_run(nph_ctx* ctx);
+/* counts of the most recent nph_methylation_run: scored groups, forward jobs (2 per group), scored events */
+int nph_methylation_counts(nph_ctx* ctx, uint64_t* n_sites_out, uint64_t* n_jobs_out, uint64_t* n_scored_events_out);
+int nph_methylation_fetch(nph_ctx* ctx, uint64_t* site_off_out, nph_meth_site* sites_out, size_t sites_cap);
 
 /* ---- event detection (section 8f N4: the step before ABEA) --------------------------------------
  * scrappie's detect_events as load_from_raw calls it: t-statistics over two windows on prefix sums, a short/long

@@ -392,8 +392,8 @@ int validate_abea_jobs(nph_ctx* ctx, const nph_abea_job* jobs, size_t n_jobs, si
     for (size_t j = 0; j < n_jobs; ++j) {
         const nph_abea_job& jb = jobs[j];
         if (jb.read >= ctx->n_reads || jb.n_kmers == 0) return NPH_ERR_INVALID;
-        if (jb.rank_off + jb.n_kmers > n_ranks_total) return NPH_ERR_INVALID;
-        if (jb.pairs_off + jb.pairs_cap > pairs_total) return NPH_ERR_INVALID;
+        if (jb.n_kmers > n_ranks_total || jb.rank_off > n_ranks_total - jb.n_kmers) return NPH_ERR_INVALID;      // overflow-safe
+        if (jb.pairs_cap > pairs_total || jb.pairs_off > pairs_total - jb.pairs_cap) return NPH_ERR_INVALID;
     }
     return NPH_OK;
 }
@@ -440,6 +440,7 @@ int nph_launch_abea(nph_ctx* ctx)
 // estimate_scalings_using_mom over the loaded ABEA jobs (reads, ranks and jobs already on the device)
 int nph_launch_mom(nph_ctx* ctx, double* d_shift_scale_out, bool reversed)
 {
+    if (!ctx->ev_mean_resident) return NPH_ERR_STATE;      // the pipelined one-shot score leaves only d_level behind
     MomParams p{};
     p.reversed = reversed ? 1 : 0;
     p.ev_mean = ctx->d_ev_mean.p; p.reads = ctx->d_reads.p; p.models = ctx->d_models.p; p.model_id = ctx->abea_model;
@@ -547,7 +548,7 @@ int nph_mom_batch(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
     NPH_TRY(nph_reads_load(ctx, reads, n_reads, ev_mean, nullptr, n_events_total));
     if (model_id >= ctx->models.size()) return NPH_ERR_INVALID;
     for (size_t j = 0; j < n_jobs; ++j) {
-        if (jobs[j].read >= n_reads || jobs[j].n_kmers == 0 || jobs[j].rank_off + jobs[j].n_kmers > n_ranks_total) return NPH_ERR_INVALID;
+        if (jobs[j].read >= n_reads || jobs[j].n_kmers == 0 || jobs[j].n_kmers > n_ranks_total || jobs[j].rank_off > n_ranks_total - jobs[j].n_kmers) return NPH_ERR_INVALID;
     }
     NPH_TRY(nph_reserve(ctx, ctx->d_abea_jobs, n_jobs));
     NPH_TRY(nph_reserve(ctx, ctx->d_abea_ranks, n_ranks_total));

@@ -32,7 +32,7 @@ __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_jobs; j += gridDim.x * blockDim.x) {
         const nph_hmm_job jb = jobs[j];
         uint32_t chunk = 0;
-        bool ok = jb.read < n_reads && jb.model_id < n_models && jb.n_kmers != 0 && jb.rank_off + jb.n_kmers <= n_ranks;
+        bool ok = jb.read < n_reads && jb.model_id < n_models && jb.n_kmers != 0 && jb.n_kmers <= n_ranks && jb.rank_off <= n_ranks - jb.n_kmers;   // overflow-safe
         ok = ok && (jb.stride == 1 || jb.stride == -1);
         if (ok) {
             const DevRead rd = reads[jb.read];

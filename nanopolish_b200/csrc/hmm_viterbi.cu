@@ -21,6 +21,7 @@
 //     -inf cell) the job returns zero states.
 #include "hmm_viterbi_kernel.cuh"
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #define NPH_TRY(expr) do { int rc__ = (expr); if (rc__ != NPH_OK) return rc__; } while (0)
@@ -107,11 +108,11 @@ __global__ void __launch_bounds__(kThreads, 1) hmm_viterbi_kernel(const VitParam
 }
 
 template <int C>
-int launch_vit(nph_ctx* ctx, const VitParams& base, const uint32_t* order, size_t count, unsigned int* counter)
+int launch_vit(nph_ctx* ctx, const VitParams& base, const uint32_t* order, size_t count, unsigned int* counter, int max_ctas)
 {
     VitParams p = base;
     p.order = order; p.n_jobs = (uint32_t)count; p.counter = counter;
-    int grid = ctx->sm_count;
+    int grid = std::min(ctx->sm_count, max_ctas);
     if ((size_t)grid * kWarps > count) grid = (int)((count + kWarps - 1) / kWarps);
     if (grid < 1) grid = 1;
     hmm_viterbi_kernel<C><<<grid, kThreads, 0, ctx->stream>>>(p);
@@ -187,11 +188,22 @@ extern "C" int nph_hmm_align(nph_ctx* ctx,
     }
     first[kNumVit] = order.size();
 
-    const int warps = ctx->sm_count * kWarps;
+    // The movement trace is per resident warp and sized by the batch's largest job ((steps + 1) x strip uint16 entries),
+    // so one long window must not multiply by every warp of the chip: the number of resident CTAs is capped so that
+    // the trace arena stays within kTraceBudget, and a job whose trace does not fit a single CTA's 16 warps within
+    // that budget is refused with NPH_ERR_UNSUPPORTED (documented in include/nph.h) instead of a NOMEM surprise.
+    const size_t trace_stride = ((max_trace + 63) / 64) * 64;
+    const uint64_t kTraceBudget = 16ull << 30;
+    const uint64_t per_cta = (uint64_t)sizeof(uint16_t) * trace_stride * kWarps;
+    if (per_cta > kTraceBudget) {
+        ctx->last_error = "profile_hmm_align window too large: its movement trace needs " + std::to_string(per_cta >> 20) + " MiB per CTA (limit 16 GiB)";
+        return NPH_ERR_UNSUPPORTED;
+    }
+    const int max_ctas = (int)std::min<uint64_t>((uint64_t)ctx->sm_count, std::max<uint64_t>(1, kTraceBudget / per_cta));
+    const int warps = max_ctas * kWarps;
     const size_t total_states = (size_t)states_off[n_jobs];
     const size_t b_params = sizeof(float4) * (size_t)max_kpad * warps;
     const size_t b_edge = sizeof(float) * 3 * ((size_t)max_period + 8) * warps;
-    const size_t trace_stride = ((max_trace + 63) / 64) * 64;
     const size_t b_trace = sizeof(uint16_t) * trace_stride * warps;
     const size_t b_states = sizeof(nph_align_state) * total_states;
     const size_t b_off = sizeof(uint64_t) * (n_jobs + 1);
@@ -222,12 +234,12 @@ extern "C" int nph_hmm_align(nph_ctx* ctx,
         if (!count) continue;
         int rc = NPH_ERR_STATE;
         switch (kVitCols[i]) {
-            case 1: rc = launch_vit<1>(ctx, p, d_order + first[i], count, ctx->d_counters.p + i); break;
-            case 2: rc = launch_vit<2>(ctx, p, d_order + first[i], count, ctx->d_counters.p + i); break;
-            case 3: rc = launch_vit<3>(ctx, p, d_order + first[i], count, ctx->d_counters.p + i); break;
-            case 4: rc = launch_vit<4>(ctx, p, d_order + first[i], count, ctx->d_counters.p + i); break;
-            case 6: rc = launch_vit<6>(ctx, p, d_order + first[i], count, ctx->d_counters.p + i); break;
-            case 8: rc = launch_vit<8>(ctx, p, d_order + first[i], count, ctx->d_counters.p + i); break;
+            case 1: rc = launch_vit<1>(ctx, p, d_order + first[i], count, ctx->d_counters.p + i, max_ctas); break;
+            case 2: rc = launch_vit<2>(ctx, p, d_order + first[i], count, ctx->d_counters.p + i, max_ctas); break;
+            case 3: rc = launch_vit<3>(ctx, p, d_order + first[i], count, ctx->d_counters.p + i, max_ctas); break;
+            case 4: rc = launch_vit<4>(ctx, p, d_order + first[i], count, ctx->d_counters.p + i, max_ctas); break;
+            case 6: rc = launch_vit<6>(ctx, p, d_order + first[i], count, ctx->d_counters.p + i, max_ctas); break;
+            case 8: rc = launch_vit<8>(ctx, p, d_order + first[i], count, ctx->d_counters.p + i, max_ctas); break;
         }
         if (rc != NPH_OK) return rc;
         ++launches;

@@ -202,6 +202,7 @@ extern "C" int nph_load_from_raw_batch(nph_ctx* ctx, const float* raw, size_t n_
     }
     (void)n_live_ranks;
     NPH_TRY(nph_reserve(ctx, ctx->d_ev_mean, n_events_total));
+    ctx->ev_mean_resident = true;
     NPH_TRY(nph_reserve(ctx, ctx->d_ev_time, n_events_total));
     NPH_TRY(nph_reserve(ctx, ctx->d_level, n_events_total));
     NPH_TRY(nph_reserve(ctx, ctx->d_reads, nl));

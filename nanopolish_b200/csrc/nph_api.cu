@@ -41,8 +41,13 @@ template int nph_reserve<float2>(nph_ctx*, DevBuf<float2>&, size_t);
 template int nph_reserve<nph_abea_job>(nph_ctx*, DevBuf<nph_abea_job>&, size_t);
 template int nph_reserve<nph_aligned_pair>(nph_ctx*, DevBuf<nph_aligned_pair>&, size_t);
 template int nph_reserve<nph_abea_result>(nph_ctx*, DevBuf<nph_abea_result>&, size_t);
+template int nph_reserve<uint64_t>(nph_ctx*, DevBuf<uint64_t>&, size_t);
+template int nph_reserve<nph_meth_record>(nph_ctx*, DevBuf<nph_meth_record>&, size_t);
+template int nph_reserve<nph_meth_site>(nph_ctx*, DevBuf<nph_meth_site>&, size_t);
 
 #define NPH_TRY(expr) do { int rc__ = (expr); if (rc__ != NPH_OK) return rc__; } while (0)
+
+extern "C" int nph_destroy(nph_ctx* ctx);
 
 namespace {
 
@@ -115,33 +120,37 @@ int create_common(nph_ctx** out, int device, bool own_stream, cudaStream_t strea
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return NPH_ERR_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
     if (own_stream) {
-        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return NPH_ERR_CUDA; }
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->stream = nullptr; delete ctx; return NPH_ERR_CUDA; }
         ctx->own_stream = true;
     } else {
         ctx->stream = stream;
     }
-    cudaEventCreate(&ctx->ev0);
-    cudaEventCreate(&ctx->ev1);
-    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->ev_reset, cudaEventDisableTiming);
-    cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking);
-    cudaMalloc((void**)&ctx->d_progress, sizeof(uint32_t));
-    cudaMallocHost((void**)&ctx->h_progress_vals, sizeof(uint32_t) * (nph_ctx::kLevelChunks + 1));
+    // every allocation below is checked; a failure releases what exists so far through nph_destroy
+    auto fail = [&](int rc) { nph_destroy(ctx); return rc; };
+    if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_reset, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking) != cudaSuccess) return fail(NPH_ERR_CUDA);
+    if (cudaMalloc((void**)&ctx->d_progress, sizeof(uint32_t)) != cudaSuccess) return fail(NPH_ERR_NOMEM);
+    if (cudaMallocHost((void**)&ctx->h_progress_vals, sizeof(uint32_t) * (nph_ctx::kLevelChunks + 1)) != cudaSuccess) {
+        ctx->h_progress_vals = nullptr;
+        return fail(NPH_ERR_NOMEM);
+    }
     for (int i = 0; i <= nph_ctx::kLevelChunks; ++i) ctx->h_progress_vals[i] = (uint32_t)(i + 1);
     for (int i = 0; i < nph_ctx::kSideStreams; ++i) {
-        cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
-        cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
+        if (cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess) return fail(NPH_ERR_CUDA);
     }
 
     // quantised log-sum table, built exactly like p7_FLogsumInit (ref: src/common/logsum.cpp:57-69)
     std::vector<float> tbl(NPH_TBL_SMEM);
     for (int i = 0; i < NPH_LOGSUM_CUT; ++i) tbl[i] = (float)log(1. + exp((double)-i / 1000.f));
     tbl[NPH_LOGSUM_CUT] = 0.0f;
-    if (cudaMalloc((void**)&ctx->d_logsum, sizeof(float) * NPH_TBL_SMEM) != cudaSuccess) { delete ctx; return NPH_ERR_NOMEM; }
-    cudaMemcpy(ctx->d_logsum, tbl.data(), sizeof(float) * NPH_TBL_SMEM, cudaMemcpyHostToDevice);
+    if (cudaMalloc((void**)&ctx->d_logsum, sizeof(float) * NPH_TBL_SMEM) != cudaSuccess) return fail(NPH_ERR_NOMEM);
+    if (cudaMemcpy(ctx->d_logsum, tbl.data(), sizeof(float) * NPH_TBL_SMEM, cudaMemcpyHostToDevice) != cudaSuccess) return fail(NPH_ERR_CUDA);
     const_transitions(ctx->consts);
-    if (nph_reserve(ctx, ctx->d_counters, NPH_NUM_COUNTERS) != NPH_OK) { delete ctx; return NPH_ERR_NOMEM; }
-    if (ensure_flank(ctx, 4096) != NPH_OK) { delete ctx; return NPH_ERR_CUDA; }
+    if (nph_reserve(ctx, ctx->d_counters, NPH_NUM_COUNTERS) != NPH_OK) return fail(NPH_ERR_NOMEM);
+    if (ensure_flank(ctx, 4096) != NPH_OK) return fail(NPH_ERR_CUDA);
     *out = ctx;
     return NPH_OK;
 }
@@ -188,13 +197,15 @@ int nph_destroy(nph_ctx* ctx)
 {
     if (!ctx) return NPH_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream || !ctx->own_stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->d_logsum) cudaFree(ctx->d_logsum);
     free_buf(ctx->d_flank); free_buf(ctx->d_models); free_buf(ctx->d_reads); free_buf(ctx->d_ev_mean);
     free_buf(ctx->d_ev_time); free_buf(ctx->d_level); free_buf(ctx->d_drift); free_buf(ctx->d_ranks);
     free_buf(ctx->d_jobs); free_buf(ctx->d_trans); free_buf(ctx->d_order); free_buf(ctx->d_scores);
     free_buf(ctx->d_counters); free_buf(ctx->d_sched_cls); free_buf(ctx->d_sched_bkt); free_buf(ctx->d_sched_hist); free_buf(ctx->d_scratch); free_buf(ctx->d_abea_jobs); free_buf(ctx->d_abea_ranks);
     free_buf(ctx->d_pairs); free_buf(ctx->d_abea_res); free_buf(ctx->d_abea_scratch); free_buf(ctx->d_abea_order); free_buf(ctx->d_abea_consts); free_buf(ctx->d_prep);
+    free_buf(ctx->meth.d_ref); free_buf(ctx->meth.d_pairs); free_buf(ctx->meth.d_records); free_buf(ctx->meth.d_prov_off); free_buf(ctx->meth.d_prov);
+    free_buf(ctx->meth.d_counts); free_buf(ctx->meth.d_sites);
     for (auto& m : ctx->models) { cudaFree(m.mean); cudaFree(m.stdv); cudaFree(m.log_stdv); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -250,7 +261,7 @@ int nph_model_upload(nph_ctx* ctx, const double* level_mean, const double* level
 // Shared by the staged call (pipelined = false: everything on the context's stream, synchronous) and by the
 // one-shot call (pipelined = true: read records on the main stream, event levels in chunks on the copy stream,
 // each chunk followed by a progress word the forward kernel polls — so scoring starts while levels still arrive).
-static int reads_load_impl(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
+int nph_reads_load_impl(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
                            const float* ev_mean, const double* ev_start_time, size_t n_events_total, bool pipelined)
 {
     if (!ctx || !reads || !ev_mean || n_reads == 0) return NPH_ERR_INVALID;
@@ -264,7 +275,7 @@ static int reads_load_impl(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
     bool any_drift = false;
     for (size_t i = 0; i < n_reads; ++i) {
         const nph_read& r = reads[i];
-        if (r.n_events == 0 || r.event_off + r.n_events > n_events_total) return NPH_ERR_INVALID;
+        if (r.n_events == 0 || r.n_events > n_events_total || r.event_off > n_events_total - r.n_events) return NPH_ERR_INVALID;
         hr[i].event_off = r.event_off; hr[i].n_events = r.n_events; hr[i].pad = 0;
         hr[i].scale = r.scale; hr[i].shift = r.shift; hr[i].var = r.var; hr[i].log_var = r.log_var;
         hd[i] = r.drift;
@@ -290,9 +301,11 @@ static int reads_load_impl(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
         NPH_CUDA(ctx, cudaEventRecord(ctx->ev_reset, ctx->cstream));
         NPH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_reset, 0));
         ctx->levels_inflight = true;
+        ctx->ev_mean_resident = false;                        // only d_level is filled on this path
         return NPH_OK;                                         // chunks are queued by upload_level_chunks()
     }
     NPH_TRY(nph_reserve(ctx, ctx->d_ev_mean, n_events_total));
+    ctx->ev_mean_resident = true;
     NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_drift.p, hd.data(), sizeof(double) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ev_mean.p, ev_mean, sizeof(float) * n_events_total, cudaMemcpyHostToDevice, ctx->stream));
     if (any_drift) {
@@ -308,7 +321,7 @@ static int reads_load_impl(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
     return NPH_OK;
 }
 
-static int upload_level_chunks(nph_ctx* ctx, const float* ev_mean)
+int nph_upload_level_chunks(nph_ctx* ctx, const float* ev_mean)
 {
     const size_t chunk = ctx->level_chunk_events, total = ctx->n_events_total;
     uint32_t c = 0;
@@ -320,10 +333,18 @@ static int upload_level_chunks(nph_ctx* ctx, const float* ev_mean)
     return NPH_OK;
 }
 
+void nph_finish_level_upload(nph_ctx* ctx)
+{
+    if (!ctx->levels_inflight) return;
+    cudaStreamSynchronize(ctx->cstream);
+    ctx->levels_inflight = false;
+    ctx->level_chunk_events = 0;
+}
+
 int nph_reads_load(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
                    const float* ev_mean, const double* ev_start_time, size_t n_events_total)
 {
-    NPH_TRY(reads_load_impl(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total, false));
+    NPH_TRY(nph_reads_load_impl(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total, false));
     ctx->reads_loaded = true;
     ctx->jobs_loaded = false;
     ctx->abea_loaded = false;
@@ -352,7 +373,7 @@ static int jobs_upload_async(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_
     return NPH_OK;
 }
 
-static int jobs_schedule(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total)
+int nph_jobs_schedule(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total)
 {
     // validate + classify + schedule on the device (hmm_schedule.cu); synchronises the stream once
     uint32_t max_E = 1;
@@ -372,7 +393,7 @@ int nph_hmm_jobs_load(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_t
     if (n_jobs == 0) { ctx->n_jobs = 0; ctx->classes.clear(); ctx->jobs_loaded = true; return NPH_OK; }   // empty batch: nothing to score
     if (!ctx->reads_loaded) return NPH_ERR_STATE;
     NPH_TRY(jobs_upload_async(ctx, kmer_ranks, n_ranks_total, jobs, n_jobs, indel_bias));
-    return jobs_schedule(ctx, n_jobs, n_ranks_total);
+    return nph_jobs_schedule(ctx, n_jobs, n_ranks_total);
 }
 
 int nph_hmm_score(nph_ctx* ctx, float* scores_dev)
@@ -406,25 +427,22 @@ int nph_hmm_score_batch(nph_ctx* ctx,
     static const bool timing = getenv("NPH_TIMING") != nullptr;   // development aid: per-phase host wall time on stderr
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
-    if (n_jobs == 0) return ctx ? NPH_OK : NPH_ERR_INVALID;      // empty batch
+    if (!ctx) return NPH_ERR_INVALID;
+    if (n_jobs == 0) return NPH_OK;                              // empty batch
     // Order of issue matters: small read records + jobs + ranks first (the scheduler needs only those), then the
     // event levels in chunks on the copy stream; the forward kernels start as soon as the schedule exists and wait
     // per job on the progress word of the chunk that holds their read (hmm_forward_kernel.cuh).
     ctx->levels_inflight = false;
-    int rc = reads_load_impl(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total, true);
+    int rc = nph_reads_load_impl(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total, true);
     if (rc == NPH_OK) { ctx->reads_loaded = true; ctx->jobs_loaded = false; ctx->abea_loaded = false; }
     const double t1 = now();
     if (rc == NPH_OK) rc = jobs_upload_async(ctx, kmer_ranks, n_ranks_total, jobs, n_jobs, indel_bias);
-    if (rc == NPH_OK && ctx->levels_inflight) rc = upload_level_chunks(ctx, ev_mean);
-    if (rc == NPH_OK) rc = jobs_schedule(ctx, n_jobs, n_ranks_total);
+    if (rc == NPH_OK && ctx->levels_inflight) rc = nph_upload_level_chunks(ctx, ev_mean);
+    if (rc == NPH_OK) rc = nph_jobs_schedule(ctx, n_jobs, n_ranks_total);
     const double t2 = now();
     if (rc == NPH_OK) rc = nph_hmm_score(ctx, nullptr);
     if (rc == NPH_OK) rc = nph_hmm_scores_fetch(ctx, scores_out, n_jobs);
-    if (ctx->levels_inflight) {                                  // also on error paths: never leave copies in flight
-        cudaStreamSynchronize(ctx->cstream);
-        ctx->levels_inflight = false;
-        ctx->level_chunk_events = 0;
-    }
+    nph_finish_level_upload(ctx);                                // also on error paths: never leave copies in flight
     const double t3 = now();
     if (timing) fprintf(stderr, "[nph] reads %.2f ms  jobs+schedule %.2f ms  score+fetch %.2f ms\n", t1 - t0, t2 - t1, t3 - t2);
     return rc;
@@ -435,9 +453,13 @@ int nph_hmm_score_batch(nph_ctx* ctx,
 int nph_score_set_combine(const float* scores, size_t n_groups, uint32_t n_alt, float* out)
 {
     if (!scores || !out || n_alt == 0) return NPH_ERR_INVALID;
-    static float tbl[NPH_LOGSUM_TBL];
-    static bool init = false;
-    if (!init) { for (int i = 0; i < NPH_LOGSUM_TBL; ++i) tbl[i] = (float)log(1. + exp((double)-i / 1000.f)); init = true; }
+    // C++11 function-local static: initialised exactly once even when OpenMP threads race into the first call
+    struct Table {
+        float v[NPH_LOGSUM_TBL];
+        Table() { for (int i = 0; i < NPH_LOGSUM_TBL; ++i) v[i] = (float)log(1. + exp((double)-i / 1000.f)); }
+    };
+    static const Table table;
+    const float* tbl = table.v;
     const double pen = log((double)n_alt);
     for (size_t g = 0; g < n_groups; ++g) {
         double score = scores[g * n_alt] - pen;
@@ -445,7 +467,9 @@ int nph_score_set_combine(const float* scores, size_t n_groups, uint32_t n_alt, 
             const double alt = scores[g * n_alt + i] - pen;
             const float a = (float)score, b = (float)alt;
             const float mx = a > b ? a : b, mn = a < b ? a : b;
-            score = (mn == -INFINITY || (mx - mn) >= 15.7f) ? mx : mx + tbl[(int)((mx - mn) * 1000.f)];
+            // !(d < 15.7f) also catches NaN / inf differences (a NaN or +inf score): no out-of-range table index, like the device path's clamp
+            const float d = mx - mn;
+            score = (mn == -INFINITY || !(d < 15.7f)) ? mx : mx + tbl[(int)(d * 1000.f)];
         }
         out[g] = (float)score;
     }

@@ -71,6 +71,7 @@ struct nph_ctx {
     std::vector<double> h_events_per_base;
     std::vector<uint32_t> h_read_n_events;
     bool reads_loaded = false;
+    bool ev_mean_resident = false;   // d_ev_mean holds this batch's raw event means (false after the pipelined one-shot score, which fills d_level only)
 
     // resident HMM jobs
     size_t n_jobs = 0, n_ranks = 0;
@@ -103,6 +104,23 @@ struct nph_ctx {
     uint32_t abea_kmax = 0;
     uint64_t abea_trace_stride = 0;
     bool abea_loaded = false;
+
+    // resident call-methylation batch (methylation.cu)
+    struct MethState {
+        bool loaded = false, ran = false;
+        size_t n_records = 0, n_ref = 0, n_pairs = 0, prov_total = 0;
+        nph_meth_params params{};
+        double indel_bias = 1.0;
+        uint64_t n_sites = 0, n_ranks = 0, n_scored_events = 0;
+        DevBuf<uint8_t> d_ref;
+        DevBuf<nph_aligned_pair> d_pairs;
+        DevBuf<nph_meth_record> d_records;
+        DevBuf<uint64_t> d_prov_off;       // n_records + 1: where each record's provisional group rows start
+        DevBuf<uint8_t> d_prov;            // provisional group rows (MethGroup)
+        DevBuf<uint64_t> d_counts;         // per record: groups, ranks (2 x n_records), then the prefix arrays and the summary
+        DevBuf<nph_meth_site> d_sites;
+        std::vector<uint64_t> h_prov_off;
+    } meth;
 
     // measurement
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -143,6 +161,16 @@ int nph_launch_abea(nph_ctx* ctx);
 int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uint32_t* max_E_out);
 // per-read (lp_mm_self, lp_mm_next) of the resident reads into ctx->d_trans (host libm, like calculate_transitions)
 int nph_upload_read_transitions(nph_ctx* ctx, double indel_bias);
+extern "C" {   // defined inside nph_api.cu's extern "C" block (internal all the same: not in include/nph.h)
+// validate + classify + schedule the n_jobs jobs already sitting in ctx->d_jobs / d_ranks (one stream sync), size the scratch
+int nph_jobs_schedule(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total);
+// nph_reads_load's body; pipelined = true (one-shot calls) leaves the event levels to nph_upload_level_chunks, which queues them
+// on the copy stream behind progress words the forward kernel polls (ctx->levels_inflight says whether that path was taken)
+int nph_reads_load_impl(nph_ctx* ctx, const nph_read* reads, size_t n_reads, const float* ev_mean, const double* ev_start_time, size_t n_events_total, bool pipelined);
+int nph_upload_level_chunks(nph_ctx* ctx, const float* ev_mean);
+// after a one-shot call: wait for the copy stream and leave the pipelined mode
+void nph_finish_level_upload(nph_ctx* ctx);
+}
 
 // ---- device-level pieces of the raw-read prologue (event_detect.cu, squiggle_prep.cu, abea.cu), chained by
 // load_from_raw.cu without leaving the device.  Inputs named d_* are device pointers; everything runs on ctx->stream.

@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .synth import ABEA_RES_DT, ALIGN_STATE_DT, CALIBRATION_DT, EVENT_DT, EVENT_RANGE_DT, PAIR_DT, RAW_RANGE_DT
+from .synth import ABEA_RES_DT, ALIGN_STATE_DT, CALIBRATION_DT, EVENT_DT, EVENT_RANGE_DT, METH_SITE_DT, PAIR_DT, RAW_RANGE_DT
 
 
 def _p(a):
@@ -51,6 +51,41 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    # ---- call-methylation: enumeration + scoring on the device (include/nph.h, section N3) ----
+    @staticmethod
+    def meth_sites_cap(records, params) -> int:
+        return int((records["ref_len"].astype(np.int64) // (int(params[0]["min_separation"]) + 1) + 2).sum())
+
+    def methylation_batch(self, reads, ev_mean, ev_start_time, ref_bases, pairs, records, params, indel_bias: float = 1.0, out=None):
+        """nph_methylation_batch: returns (site_off u8[n_records + 1], sites METH_SITE_DT[n_sites], scored_events)."""
+        n = int(records.shape[0])
+        cap = self.meth_sites_cap(records, params)
+        site_off, sites = out if out is not None else (np.zeros(n + 1, np.uint64), np.zeros(max(cap, 1), METH_SITE_DT))
+        scored = C.c_uint64()
+        self._check(self.lib.nph_methylation_batch(self.ctx, _p(reads), reads.shape[0], _p(ev_mean), _p(ev_start_time), ev_mean.shape[0],
+                                                   _p(ref_bases), ref_bases.shape[0], _p(pairs), pairs.shape[0], _p(records), n, _p(params),
+                                                   indel_bias, _p(site_off), _p(sites), sites.shape[0], C.byref(scored)), "nph_methylation_batch")
+        return site_off, sites[:int(site_off[n])], int(scored.value)
+
+    def methylation_load(self, ref_bases, pairs, records, params, indel_bias: float = 1.0):
+        self._check(self.lib.nph_methylation_load(self.ctx, _p(ref_bases), ref_bases.shape[0], _p(pairs), pairs.shape[0], _p(records),
+                                                  records.shape[0], _p(params), indel_bias), "nph_methylation_load")
+        self._meth_n = int(records.shape[0])
+
+    def methylation_run(self):
+        self._check(self.lib.nph_methylation_run(self.ctx), "nph_methylation_run")
+
+    def methylation_counts(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.nph_methylation_counts(self.ctx, C.byref(a), C.byref(b), C.byref(c)), "nph_methylation_counts")
+        return int(a.value), int(b.value), int(c.value)
+
+    def methylation_fetch(self, out=None):
+        n_sites = self.methylation_counts()[0]
+        site_off, sites = out if out is not None else (np.zeros(self._meth_n + 1, np.uint64), np.zeros(max(n_sites, 1), METH_SITE_DT))
+        self._check(self.lib.nph_methylation_fetch(self.ctx, _p(site_off), _p(sites), sites.shape[0]), "nph_methylation_fetch")
+        return site_off, sites[:n_sites]
 
     # ---- models / reads / jobs ----------------------------------------------------------
     def model_upload(self, model) -> int:

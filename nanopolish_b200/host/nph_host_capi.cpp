@@ -279,16 +279,15 @@ static long long call_methylation_impl(int n_reads, const int32_t* read, const c
         }
         const double t0 = now();
         caller.add_reads(batch_reads);
-        *n_jobs_out = caller.num_jobs();
         const double t1 = now();
         caller.run(Engine::thread_default(), indel_bias);
+        *n_jobs_out = caller.num_jobs();
         const double t2 = now();
-        std::string all;
-        for (const std::string& part : caller.tsv_batch()) all += part;
+        const size_t bytes = caller.tsv_all(tsv_out, cap ? cap - 1 : 0);
         if (secs3) { secs3[0] = t1 - t0; secs3[1] = t2 - t1; secs3[2] = now() - t2; }
-        if (all.size() + 1 > cap) throw Error(NPH_ERR_INVALID, "tsv buffer too small");
-        std::memcpy(tsv_out, all.c_str(), all.size() + 1);
-        n = (long long)all.size();
+        if (bytes + 1 > cap) throw Error(NPH_ERR_INVALID, "tsv buffer too small");
+        tsv_out[bytes] = 0;
+        n = (long long)bytes;
     });
     return st ? st : n;
 }
@@ -307,6 +306,39 @@ long long nphh_call_methylation_timed(int n_reads, const int32_t* read, const ch
 {
     return call_methylation_impl(n_reads, read, read_names, is_rev, rc, ref_start, ref_seqs, pairs, pair_off, contig, indel_bias, tsv_out, cap,
                                  n_jobs_out, secs3);
+}
+
+// call-methylation from flat host buffers (the C-ABI layout) to TSV bytes: what bench.py's end-to-end arm times.
+// host_mode != 0 runs the host-side enumerator instead (reads registered with nphh_read_create; the cross-check path).
+long long nphh_call_methylation_flat(const void* reads, size_t n_reads, const float* ev_mean, const double* ev_start_time, size_t n_events,
+                                     const char* ref_bases, size_t n_ref, const void* aligned_events, size_t n_pairs, void* records, size_t n_records,
+                                     int cpg_model, const char** read_names, const uint8_t* is_reverse, const char* contig, double indel_bias,
+                                     char* tsv_out, size_t cap, uint64_t* n_sites_out, uint64_t* scored_events_out, double* secs2)
+{
+    long long n = -1;
+    int st = guard([&] {
+        Engine& eng = Engine::thread_default();
+        const PoreModel* model = g_models[cpg_model].get();
+        const uint32_t mid = eng.model_id(model);
+        nph_meth_record* recs = static_cast<nph_meth_record*>(records);
+        for (size_t r = 0; r < n_records; ++r) recs[r].model_id = mid;
+        FlatMethylationBatch b;
+        b.reads = static_cast<const nph_read*>(reads); b.n_reads = n_reads; b.ev_mean = ev_mean; b.ev_start_time = ev_start_time; b.n_events = n_events;
+        b.ref_bases = ref_bases; b.n_ref = n_ref; b.aligned_events = static_cast<const nph_aligned_pair*>(aligned_events); b.n_pairs = n_pairs;
+        b.records = recs; b.n_records = n_records; b.read_names = read_names; b.is_reverse = is_reverse; b.contig = contig;
+        MethylationCallingParameters params;
+        params.methylation_type = model->pmalphabet->get_name();
+        params.alphabet = model->pmalphabet;
+        FlatMethylationStats stats;
+        const size_t bytes = call_methylation_flat(eng, b, params, model->k, indel_bias, tsv_out, cap ? cap - 1 : 0, &stats);
+        if (bytes + 1 > cap) throw Error(NPH_ERR_INVALID, "tsv buffer too small");
+        tsv_out[bytes] = 0;
+        if (n_sites_out) *n_sites_out = stats.n_sites;
+        if (scored_events_out) *scored_events_out = stats.scored_events;
+        if (secs2) { secs2[0] = stats.device_seconds; secs2[1] = stats.tsv_seconds; }
+        n = (long long)bytes;
+    });
+    return st ? st : n;
 }
 
 // modBAM tags of one record from explicit calls (start position, site sequence, strand-0 log-likelihoods); reference_mode:
@@ -353,7 +385,7 @@ double nphh_methylation_enumerate_seconds(int n_reads, const int32_t* read, cons
     double secs = -1.0;
     guard([&] {
         MethylationCallingParameters params;
-        MethylationCaller caller(params);
+        MethylationCaller caller(params, MethylationCaller::Mode::HostEnumeration);
         std::vector<EventAlignedRead> rs(n_reads);
         for (int i = 0; i < n_reads; ++i) {
             EventAlignedRead& r = rs[i];

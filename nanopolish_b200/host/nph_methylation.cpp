@@ -3,7 +3,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 
 namespace nph {
@@ -131,7 +133,51 @@ ModbamTags reference_modbam_tags(const std::string& ref_seq, int ref_start_pos, 
     return out;
 }
 
-MethylationCaller::MethylationCaller(const MethylationCallingParameters& params) : m_params(params)
+template <typename T>
+void PinnedArray<T>::resize(size_t n)
+{
+    if (n > m_cap) {
+        const size_t want = std::max<size_t>(n + n / 2, 1024);
+        void* np = nullptr;
+        const int rc = nph_host_alloc(&np, want * sizeof(T));
+        if (rc != NPH_OK) throw Error(rc, "nph_host_alloc (page-locked staging)");
+        if (m_p) { std::memcpy(np, m_p, m_n * sizeof(T)); nph_host_free(m_p); }
+        m_p = static_cast<T*>(np);
+        m_cap = want;
+    }
+    m_n = n;
+}
+template class PinnedArray<char>;
+template class PinnedArray<nph_aligned_pair>;
+template class PinnedArray<nph_meth_site>;
+
+nph_meth_params make_meth_params(const MethylationCallingParameters& params, uint32_t k, int region_start, int region_end)
+{
+    const Alphabet* a = params.alphabet ? params.alphabet : get_alphabet_by_name(params.methylation_type);
+    nph_meth_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.min_separation = params.min_separation;
+    p.min_flank = params.min_flank;
+    p.max_span = 200;                      // basemods.cpp:336
+    p.min_event_span = 10;                 // basemods.cpp:363
+    p.region_start = region_start;
+    p.region_end = region_end;
+    p.k = k;
+    p.alphabet_size = a->size();
+    if (a->size() > 7 || a->num_recognition_sites() > NPH_METH_MAX_SITES || a->recognition_length() >= NPH_METH_MAX_SITE_LEN || a->num_recognition_sites() == 0)
+        throw Error(NPH_ERR_UNSUPPORTED, "alphabet outside nph_meth_params' limits");
+    for (uint32_t i = 0; i < a->size(); ++i) { p.bases[i] = a->base((uint8_t)i); p.complements[i] = a->complement(a->base((uint8_t)i)); }
+    p.n_sites = (uint32_t)a->num_recognition_sites();
+    p.site_len = (uint32_t)a->recognition_length();
+    for (uint32_t s = 0; s < p.n_sites; ++s) {
+        std::memcpy(p.sites[s], a->get_recognition_site(s), p.site_len);
+        std::memcpy(p.sites_methylated[s], a->get_recognition_site_methylated(s), p.site_len);
+        std::memcpy(p.sites_methylated_complement[s], a->get_recognition_site_methylated_complement(s), p.site_len);
+    }
+    return p;
+}
+
+MethylationCaller::MethylationCaller(const MethylationCallingParameters& params, Mode mode) : m_mode(mode), m_params(params)
 {
     if (!m_params.alphabet) m_params.alphabet = get_alphabet_by_name(m_params.methylation_type);
 }
@@ -139,12 +185,84 @@ MethylationCaller::MethylationCaller(const MethylationCallingParameters& params)
 void MethylationCaller::clear()
 {
     m_batch.clear(); m_pending.clear(); m_reads.clear();
+    m_ref.clear(); m_pairs.clear(); m_sites.clear(); m_records.clear(); m_record_meta.clear(); m_site_off.clear();
+    m_n_sites = 0; m_scored_events = 0; m_region_set = false; m_ran = false;
+}
+
+// Device mode: copy what the enumeration reads — the reference substring once per read, the event alignment of each
+// strand that has events and a motif model — into the page-locked batch buffers (parallel over reads), one
+// nph_meth_record per (read, strand).
+void MethylationCaller::stage(const EventAlignedRead* const* reads, size_t n, int region_start, int region_end)
+{
+    if (m_region_set && (region_start != m_region_start || region_end != m_region_end))
+        throw Error(NPH_ERR_UNSUPPORTED, "one output window per batch: call run() before changing region_start / region_end");
+    m_region_start = region_start; m_region_end = region_end; m_region_set = true;
+    m_ran = false;
+    struct Slot { size_t ref_off, pair_off[2]; bool use[2]; };
+    std::vector<Slot> slots(n);
+    size_t ref_total = m_ref.size(), pair_total = m_pairs.size();
+    const size_t first_read = m_reads.size();
+    for (size_t i = 0; i < n; ++i) {
+        const EventAlignedRead& r = *reads[i];
+        ReadEntry re;
+        re.name = r.read_name; re.is_reverse = r.is_reverse; re.contig = r.contig;
+        re.ref_off = ref_total; re.ref_len = r.ref_seq.size(); re.ref_start_pos = r.ref_start_pos;
+        re.first_record = m_records.size();
+        slots[i].ref_off = ref_total;
+        ref_total += r.ref_seq.size();
+        for (size_t strand_idx = 0; strand_idx < 2; ++strand_idx) {
+            slots[i].use[strand_idx] = false;
+            if (r.ref_seq.empty() || !r.read->has_events_for_strand(strand_idx)) continue;
+            const PoreModel* motif_model = r.read->get_model((uint32_t)strand_idx, m_params.methylation_type);
+            if (!motif_model) continue;                                   // no model for this motif on this strand
+            if (r.read->pore_type != PORETYPE_R9) throw Error(NPH_ERR_UNSUPPORTED, "only R9 reads are supported (load_from_raw always makes R9)");
+            const uint32_t k = (uint32_t)r.read->get_model_k((uint32_t)strand_idx);
+            if (re.k && re.k != k) throw Error(NPH_ERR_UNSUPPORTED, "strands with different k in one read");
+            re.k = k;
+            nph_meth_record rec;
+            std::memset(&rec, 0, sizeof(rec));
+            rec.ref_off = slots[i].ref_off; rec.ref_len = (uint32_t)r.ref_seq.size();
+            rec.pair_off = pair_total; rec.n_pairs = (uint32_t)r.aligned_events[strand_idx].size();
+            rec.ref_start_pos = r.ref_start_pos; rec.rc = r.rc[strand_idx] ? 1 : 0; rec.strand = (uint8_t)strand_idx;
+            slots[i].use[strand_idx] = true; slots[i].pair_off[strand_idx] = pair_total;
+            pair_total += rec.n_pairs;
+            m_records.push_back(rec);
+            m_record_meta.push_back(Record{r.read, motif_model, (uint8_t)strand_idx});
+        }
+        re.n_records = m_records.size() - re.first_record;
+        m_reads.push_back(std::move(re));
+    }
+    (void)first_read;
+    m_ref.resize(ref_total);
+    m_pairs.resize(pair_total);
+    char* const ref = m_ref.data();
+    nph_aligned_pair* const pairs = m_pairs.data();
+    static_assert(sizeof(AlignedPair) == sizeof(nph_aligned_pair), "AlignedPair layout");
+#pragma omp parallel for schedule(dynamic, 16) num_threads(host_threads()) if (n > 64)
+    for (long long ii = 0; ii < (long long)n; ++ii) {
+        const EventAlignedRead& r = *reads[(size_t)ii];
+        const Slot& s = slots[(size_t)ii];
+        std::memcpy(ref + s.ref_off, r.ref_seq.data(), r.ref_seq.size());
+        for (int st = 0; st < 2; ++st)
+            if (s.use[st] && !r.aligned_events[st].empty())
+                std::memcpy(pairs + s.pair_off[st], r.aligned_events[st].data(), sizeof(AlignedPair) * r.aligned_events[st].size());
+    }
 }
 
 size_t MethylationCaller::add_read(const EventAlignedRead& r, int region_start, int region_end)
 {
+    if (m_mode == Mode::HostEnumeration) return add_read_host(r, region_start, region_end);
     const size_t read_idx = m_reads.size();
-    m_reads.push_back(ReadEntry{r.read_name, r.is_reverse, {}});
+    const EventAlignedRead* one = &r;
+    stage(&one, 1, region_start, region_end);
+    return read_idx;
+}
+
+size_t MethylationCaller::add_read_host(const EventAlignedRead& r, int region_start, int region_end)
+{
+    const size_t read_idx = m_reads.size();
+    m_reads.emplace_back();
+    m_reads.back().name = r.read_name; m_reads.back().is_reverse = r.is_reverse; m_reads.back().sites_built = true;
     std::map<int, ScoredSite>& site_score_map = m_reads.back().sites;
     const std::string& ref_seq = r.ref_seq;
     if (ref_seq.empty()) return read_idx;
@@ -242,6 +360,12 @@ size_t MethylationCaller::add_reads(const std::vector<EventAlignedRead>& reads, 
 {
     const size_t first = m_reads.size();
     const size_t n = reads.size();
+    if (m_mode == Mode::DeviceEnumeration) {
+        std::vector<const EventAlignedRead*> ptrs(n);
+        for (size_t i = 0; i < n; ++i) ptrs[i] = &reads[i];
+        stage(ptrs.data(), n, region_start, region_end);
+        return first;
+    }
     const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), (n + 15) / 16));
     if (T == 1) {
         for (const EventAlignedRead& r : reads) add_read(r, region_start, region_end);
@@ -249,7 +373,7 @@ size_t MethylationCaller::add_reads(const std::vector<EventAlignedRead>& reads, 
     }
     // contiguous blocks of reads per worker: splicing the workers' lists in worker order reproduces the sequential order
     std::vector<std::unique_ptr<MethylationCaller>> locals((size_t)T);     // separately allocated: no false sharing of their cursors
-    for (auto& l : locals) l.reset(new MethylationCaller(m_params));
+    for (auto& l : locals) l.reset(new MethylationCaller(m_params, Mode::HostEnumeration));
     std::vector<std::string> errors((size_t)T);
 #pragma omp parallel for schedule(static, 1) num_threads(T)
     for (int t = 0; t < T; ++t) {
@@ -271,6 +395,43 @@ size_t MethylationCaller::add_reads(const std::vector<EventAlignedRead>& reads, 
 
 void MethylationCaller::run(Engine& engine, double indel_bias)
 {
+    if (m_mode == Mode::DeviceEnumeration) {
+        m_site_off.assign(m_records.size() + 1, 0);
+        m_n_sites = 0; m_scored_events = 0;
+        for (ReadEntry& re : m_reads) { re.sites.clear(); re.sites_built = false; }
+        m_ran = true;
+        if (m_records.empty()) return;
+        // one nph_read per distinct (SquiggleRead, strand); consecutive records of one read are the common case
+        std::vector<std::pair<const SquiggleRead*, uint8_t>> uniq;
+        std::map<std::pair<const SquiggleRead*, uint8_t>, uint32_t> index;
+        uint32_t k = 0;
+        for (size_t i = 0; i < m_records.size(); ++i) {
+            const Record& rm = m_record_meta[i];
+            const std::pair<const SquiggleRead*, uint8_t> key(rm.read, rm.strand);
+            uint32_t ridx;
+            if (!uniq.empty() && uniq.back() == key) ridx = (uint32_t)uniq.size() - 1;
+            else {
+                auto it = index.find(key);
+                if (it == index.end()) { ridx = (uint32_t)uniq.size(); index[key] = ridx; uniq.push_back(key); }
+                else ridx = it->second;
+            }
+            m_records[i].read = ridx;
+            m_records[i].model_id = engine.model_id(rm.model);
+            if (k && rm.model->k != k) throw Error(NPH_ERR_UNSUPPORTED, "models with different k in one call-methylation batch");
+            k = rm.model->k;
+        }
+        const detail::FlatReads fr = detail::flatten_reads(engine, uniq);
+        const nph_meth_params mp = make_meth_params(m_params, k, m_region_start, m_region_end);
+        size_t cap = 0;
+        for (const nph_meth_record& r : m_records) cap += r.ref_len / (size_t)(m_params.min_separation + 1) + 2;
+        m_sites.resize(cap);
+        engine.check(nph_methylation_batch(engine.ctx(), fr.reads.data(), fr.reads.size(), fr.mean, fr.time, fr.n_events,
+                                           m_ref.data(), m_ref.size(), m_pairs.data(), m_pairs.size(), m_records.data(), m_records.size(),
+                                           &mp, indel_bias, m_site_off.data(), m_sites.data(), cap, &m_scored_events),
+                     "nph_methylation_batch");
+        m_n_sites = m_site_off.back();
+        return;
+    }
     const std::vector<float> ll = m_batch.run(engine, indel_bias);
     for (const Pending& p : m_pending) {
         ScoredSite& ss = m_reads[p.read].sites[p.site_key];
@@ -282,25 +443,100 @@ void MethylationCaller::run(Engine& engine, double indel_bias)
     m_batch.clear();
 }
 
-std::string MethylationCaller::tsv(size_t read_idx) const
+// one TSV row (write_methylation_results_as_tsv, call_methylation.cpp:532-550): chromosome, strand, start, end, read_name,
+// log_lik_ratio %.2lf, log_lik_methylated %.2lf, log_lik_unmethylated %.2lf, num_calling_strands, num_motifs, sequence
+static void append_row(std::string& out, const std::string& chromosome, bool is_reverse, int start_position, int end_position,
+                       const std::string& name, double sum_ll_m, double sum_ll_u, int strands_scored, int n_motif,
+                       const char* sequence, size_t sequence_len)
+{
+    char buf[512];
+    const double diff = sum_ll_m - sum_ll_u;
+    out += chromosome; out += '\t'; out += is_reverse ? '-' : '+'; out += '\t';
+    out.append(buf, (size_t)snprintf(buf, sizeof buf, "%d\t%d\t", start_position, end_position));
+    out += name; out += '\t';
+    out.append(buf, format_fixed(buf, diff, 2)); out += '\t';
+    out.append(buf, format_fixed(buf, sum_ll_m, 2)); out += '\t';
+    out.append(buf, format_fixed(buf, sum_ll_u, 2)); out += '\t';
+    out.append(buf, (size_t)snprintf(buf, sizeof buf, "%d\t%d\t", strands_scored, n_motif));
+    out.append(sequence, sequence_len);
+    out += '\n';
+}
+
+// Device mode: the ScoredSite map of one read from its site records (the strands of a read meet at start_position,
+// exactly as the reference's find-or-insert does, basemods.cpp:403-425).
+void MethylationCaller::build_sites(size_t read_idx) const
 {
     const ReadEntry& re = m_reads[read_idx];
-    std::string out;
-    char buf[512];
-    for (const auto& kv : re.sites) {
-        const ScoredSite& ss = kv.second;
-        const double sum_ll_m = ss.ll_methylated[0] + ss.ll_methylated[1];
-        const double sum_ll_u = ss.ll_unmethylated[0] + ss.ll_unmethylated[1];
-        const double diff = sum_ll_m - sum_ll_u;
-        // chromosome, strand, start, end, read_name, log_lik_ratio %.2lf, log_lik_methylated %.2lf, log_lik_unmethylated %.2lf
-        out += ss.chromosome; out += '\t'; out += re.is_reverse ? '-' : '+'; out += '\t';
-        out += std::to_string(ss.start_position); out += '\t'; out += std::to_string(ss.end_position); out += '\t';
-        out += re.name; out += '\t';
-        out.append(buf, format_fixed(buf, diff, 2)); out += '\t';
-        out.append(buf, format_fixed(buf, sum_ll_m, 2)); out += '\t';
-        out.append(buf, format_fixed(buf, sum_ll_u, 2)); out += '\t';
-        out += std::to_string(ss.strands_scored) + "\t" + std::to_string(ss.n_motif) + "\t" + ss.sequence + "\n";
+    if (re.sites_built) return;
+    if (!m_ran) throw Error(NPH_ERR_STATE, "MethylationCaller::sites before run()");
+    const char* ref = m_ref.data() + re.ref_off;
+    for (size_t rec = re.first_record; rec < re.first_record + re.n_records; ++rec) {
+        const size_t strand = m_records[rec].strand;
+        for (uint64_t s = m_site_off[rec]; s < m_site_off[rec + 1]; ++s) {
+            const nph_meth_site& ms = m_sites.data()[s];
+            auto iter = re.sites.find(ms.start_position);
+            if (iter == re.sites.end()) {
+                ScoredSite ss;
+                ss.chromosome = re.contig;
+                ss.start_position = ms.start_position;
+                ss.end_position = ms.end_position;
+                ss.n_motif = (int)ms.n_motif;
+                // the motif site(s) with a k-mer's worth of context either side (std::string::substr cuts at the end)
+                const size_t site_output_start = (size_t)(ms.start_position - re.ref_start_pos) - re.k + 1;
+                const size_t site_output_end = std::min<size_t>((size_t)(ms.end_position - re.ref_start_pos) + re.k, re.ref_len);
+                ss.sequence.assign(ref + site_output_start, site_output_end - site_output_start);
+                iter = re.sites.insert({ms.start_position, ss}).first;
+            }
+            iter->second.ll_unmethylated[strand] = ms.ll_unmethylated;      // float -> double, like `double s = profile_hmm_score(...)`
+            iter->second.ll_methylated[strand] = ms.ll_methylated;
+            iter->second.strands_scored += 1;
+        }
     }
+    re.sites_built = true;
+}
+
+const std::map<int, ScoredSite>& MethylationCaller::sites(size_t read_idx) const
+{
+    if (m_mode == Mode::DeviceEnumeration) build_sites(read_idx);
+    return m_reads[read_idx].sites;
+}
+
+// rows of a record that is its read's only scored strand: the site records are already the rows, in ascending position
+static void append_single_strand_rows(std::string& out, const std::string& contig, bool is_reverse, const std::string& name, const char* ref,
+                                      size_t ref_len, int ref_start_pos, uint32_t k, size_t strand, const nph_meth_site* sites, size_t n)
+{
+    for (size_t s = 0; s < n; ++s) {
+        const nph_meth_site& ms = sites[s];
+        double ll_m[2] = {0, 0}, ll_u[2] = {0, 0};
+        ll_m[strand] = ms.ll_methylated; ll_u[strand] = ms.ll_unmethylated;       // the other strand's entries stay 0, as in a fresh ScoredSite
+        const size_t b = (size_t)(ms.start_position - ref_start_pos) - k + 1;
+        const size_t e = std::min<size_t>((size_t)(ms.end_position - ref_start_pos) + k, ref_len);
+        append_row(out, contig, is_reverse, ms.start_position, ms.end_position, name, ll_m[0] + ll_m[1], ll_u[0] + ll_u[1], 1, (int)ms.n_motif,
+                   ref + b, e - b);
+    }
+}
+
+void MethylationCaller::append_rows(std::string& out, size_t read_idx) const
+{
+    const ReadEntry& re = m_reads[read_idx];
+    if (m_mode == Mode::DeviceEnumeration && re.n_records == 1 && !re.sites_built) {
+        if (!m_ran) throw Error(NPH_ERR_STATE, "MethylationCaller::tsv before run()");
+        const size_t rec = re.first_record;
+        append_single_strand_rows(out, re.contig, re.is_reverse, re.name, m_ref.data() + re.ref_off, re.ref_len, re.ref_start_pos, re.k,
+                                  m_records[rec].strand, m_sites.data() + m_site_off[rec], (size_t)(m_site_off[rec + 1] - m_site_off[rec]));
+        return;
+    }
+    for (const auto& kv : sites(read_idx)) {
+        const ScoredSite& ss = kv.second;
+        append_row(out, ss.chromosome, re.is_reverse, ss.start_position, ss.end_position, re.name, ss.ll_methylated[0] + ss.ll_methylated[1],
+                   ss.ll_unmethylated[0] + ss.ll_unmethylated[1], ss.strands_scored, ss.n_motif, ss.sequence.data(), ss.sequence.size());
+    }
+}
+
+std::string MethylationCaller::tsv(size_t read_idx) const
+{
+    std::string out;
+    append_rows(out, read_idx);
     return out;
 }
 
@@ -310,6 +546,75 @@ std::vector<std::string> MethylationCaller::tsv_batch() const
 #pragma omp parallel for schedule(dynamic, 16) num_threads(host_threads()) if (m_reads.size() > 64)
     for (long long i = 0; i < (long long)m_reads.size(); ++i) out[i] = tsv((size_t)i);
     return out;
+}
+
+size_t MethylationCaller::tsv_all(char* out, size_t cap) const
+{
+    // contiguous blocks of reads per worker: format into a private string, then copy to the block's offset
+    const size_t n = m_reads.size();
+    const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), (n + 63) / 64));
+    std::vector<std::string> parts((size_t)T);
+    std::vector<std::string> errors((size_t)T);
+#pragma omp parallel for schedule(static, 1) num_threads(T) if (T > 1)
+    for (int t = 0; t < T; ++t) {
+        const size_t b = n * (size_t)t / (size_t)T, e = n * ((size_t)t + 1) / (size_t)T;
+        try {
+            parts[t].reserve((e - b) * 4096);
+            for (size_t i = b; i < e; ++i) append_rows(parts[t], i);
+        } catch (const std::exception& ex) { errors[t] = ex.what(); }
+    }
+    for (const std::string& e : errors) if (!e.empty()) throw Error(NPH_ERR_INVALID, e);
+    std::vector<size_t> off((size_t)T + 1, 0);
+    for (int t = 0; t < T; ++t) off[t + 1] = off[t] + parts[t].size();
+    if (off[T] > cap || !out) return off[T];
+#pragma omp parallel for schedule(static, 1) num_threads(T) if (T > 1)
+    for (int t = 0; t < T; ++t) std::memcpy(out + off[t], parts[t].data(), parts[t].size());
+    return off[T];
+}
+
+// The whole of call-methylation for a batch that already sits in flat host buffers (the layout of nph_methylation_batch):
+// one device call, then the TSV rows formatted by host_threads() workers straight from the site records.
+size_t call_methylation_flat(Engine& engine, const FlatMethylationBatch& b, const MethylationCallingParameters& params, uint32_t k,
+                             double indel_bias, char* tsv_out, size_t cap, FlatMethylationStats* stats)
+{
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    const nph_meth_params mp = make_meth_params(params, k, b.region_start, b.region_end);
+    size_t site_cap = 0;
+    for (size_t r = 0; r < b.n_records; ++r) site_cap += b.records[r].ref_len / (size_t)(params.min_separation + 1) + 2;
+    nph_meth_site* sites = static_cast<nph_meth_site*>(engine.pinned(3, sizeof(nph_meth_site) * std::max<size_t>(site_cap, 1)));
+    std::vector<uint64_t> site_off(b.n_records + 1, 0);
+    uint64_t scored = 0;
+    engine.check(nph_methylation_batch(engine.ctx(), b.reads, b.n_reads, b.ev_mean, b.ev_start_time, b.n_events, b.ref_bases, b.n_ref,
+                                       b.aligned_events, b.n_pairs, b.records, b.n_records, &mp, indel_bias, site_off.data(), sites, site_cap, &scored),
+                 "nph_methylation_batch");
+    const double t1 = now();
+    const size_t n = b.n_records;
+    const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), (n + 63) / 64));
+    std::vector<std::string> parts((size_t)T);
+    const std::string contig(b.contig ? b.contig : "");
+#pragma omp parallel for schedule(static, 1) num_threads(T) if (T > 1)
+    for (int t = 0; t < T; ++t) {
+        const size_t lo = n * (size_t)t / (size_t)T, hi = n * ((size_t)t + 1) / (size_t)T;
+        std::string& out = parts[t];
+        out.reserve((size_t)(site_off[hi] - site_off[lo]) * 96 + 64);
+        std::string name;
+        for (size_t r = lo; r < hi; ++r) {
+            const nph_meth_record& rec = b.records[r];
+            name.assign(b.read_names[r]);
+            append_single_strand_rows(out, contig, b.is_reverse[r] != 0, name, b.ref_bases + rec.ref_off, rec.ref_len, rec.ref_start_pos, k, rec.strand,
+                                      sites + site_off[r], (size_t)(site_off[r + 1] - site_off[r]));
+        }
+    }
+    std::vector<size_t> off((size_t)T + 1, 0);
+    for (int t = 0; t < T; ++t) off[t + 1] = off[t] + parts[t].size();
+    if (stats) { stats->n_sites = site_off[n]; stats->scored_events = scored; }
+    if (tsv_out && off[T] <= cap) {
+#pragma omp parallel for schedule(static, 1) num_threads(T) if (T > 1)
+        for (int t = 0; t < T; ++t) std::memcpy(tsv_out + off[t], parts[t].data(), parts[t].size());
+    }
+    if (stats) { stats->device_seconds = t1 - t0; stats->tsv_seconds = now() - t1; }
+    return off[T];
 }
 
 void MethylationCaller::write_tsv(FILE* fp, size_t read_idx) const

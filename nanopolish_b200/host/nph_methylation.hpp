@@ -9,11 +9,14 @@
 //                                       ref: src/basemods/nanopolish_basemods.cpp:35-177, 179-238
 //
 // The reference scores two sequences per CpG group with two profile_hmm_score calls inside the per-read OpenMP
-// loop.  Here add_read() only enumerates (motif scan -> groups -> window -> event bounds) and appends two jobs per
-// group to one HmmBatch for the whole BamProcessor batch; run() launches once and scatters log-likelihoods back into
-// the ScoredSites; write_tsv() formats them exactly like the reference.  BAM/FASTA access stays with the caller, which
-// hands over what the reference pulls out of them: the reference substring and the (ref_pos, event_idx) pairs of
-// EventAlignmentRecord (src/alignment/nanopolish_alignment_db.cpp:50-91).
+// loop.  Here add_read() only stages what the reference pulls out of the BAM record and the FASTA — the reference
+// substring and the (ref_pos, event_idx) pairs of EventAlignmentRecord (src/alignment/nanopolish_alignment_db.cpp:50-91)
+// — into page-locked buffers; run() hands the whole BamProcessor batch to nph_methylation_batch, where the motif scan,
+// the grouping, the window / event-bound tests, the methylated / unmethylated k-mer ranks and the two scores per group
+// all happen on the device (csrc/methylation.cu); what comes back is one 24-byte record per scored group, from which
+// the ScoredSites and the TSV rows (write_methylation_results_as_tsv) are formed.
+// A host-side enumerator with the same results (Mode::HostEnumeration: jobs queued into an HmmBatch read by read, the
+// round-1 path) is kept as the cross-check of the device enumerator.
 #pragma once
 #include <cstdio>
 #include "nph_host.hpp"
@@ -73,9 +76,49 @@ ModbamTags reference_modbam_tags(const std::string& ref_seq, int ref_start_pos, 
 
 bool find_by_ref_bounds(const std::vector<AlignedPair>& pairs, int ref_start, int ref_stop, int& read_start, int& read_stop);
 
+// nph_meth_params (include/nph.h) for these calling parameters, model k-mer size and output window
+nph_meth_params make_meth_params(const MethylationCallingParameters& params, uint32_t k, int region_start, int region_end);
+
+// page-locked, growable host array (nph_host_alloc): what the batch hands to the C ABI is written once, in place
+template <typename T>
+class PinnedArray {
+public:
+    PinnedArray() {}
+    ~PinnedArray() { if (m_p) nph_host_free(m_p); }
+    PinnedArray(const PinnedArray&) = delete;
+    PinnedArray& operator=(const PinnedArray&) = delete;
+    T* data() { return m_p; }
+    const T* data() const { return m_p; }
+    size_t size() const { return m_n; }
+    void clear() { m_n = 0; }
+    void resize(size_t n);             // keeps the first min(n, size()) elements; new elements are uninitialised
+private:
+    T* m_p = nullptr;
+    size_t m_n = 0, m_cap = 0;
+};
+
+// A BamProcessor batch in the flat layout nph_methylation_batch takes (one record = one read, one strand), plus what the
+// TSV rows need per record.  records[].read / .model_id are already resolved (nph_read index, Engine::model_id).
+struct FlatMethylationBatch {
+    const nph_read* reads = nullptr; size_t n_reads = 0;
+    const float* ev_mean = nullptr; const double* ev_start_time = nullptr; size_t n_events = 0;
+    const char* ref_bases = nullptr; size_t n_ref = 0;
+    const nph_aligned_pair* aligned_events = nullptr; size_t n_pairs = 0;
+    const nph_meth_record* records = nullptr; size_t n_records = 0;
+    const char* const* read_names = nullptr;      // per record
+    const uint8_t* is_reverse = nullptr;          // per record: bam_is_rev
+    const char* contig = nullptr;
+    int region_start = -1, region_end = -1;
+};
+struct FlatMethylationStats { uint64_t n_sites = 0, scored_events = 0; double device_seconds = 0, tsv_seconds = 0; };
+// returns the TSV's byte count (rows are written only if it fits cap)
+size_t call_methylation_flat(Engine& engine, const FlatMethylationBatch& batch, const MethylationCallingParameters& params, uint32_t k,
+                             double indel_bias, char* tsv_out, size_t cap, FlatMethylationStats* stats = nullptr);
+
 class MethylationCaller {
 public:
-    explicit MethylationCaller(const MethylationCallingParameters& params);
+    enum class Mode { DeviceEnumeration, HostEnumeration };
+    explicit MethylationCaller(const MethylationCallingParameters& params, Mode mode = Mode::DeviceEnumeration);
     // enumerate the read's motif groups and queue their jobs; returns the read's index in this batch.
     // region_start/region_end = -1 for no window restriction (the reference's -w option).
     size_t add_read(const EventAlignedRead& r, int region_start = -1, int region_end = -1);
@@ -84,9 +127,14 @@ public:
     // the first read.  The reference runs this enumeration inside its per-read OpenMP loop too.
     size_t add_reads(const std::vector<EventAlignedRead>& reads, int region_start = -1, int region_end = -1);
     void run(Engine& engine, double indel_bias = hmm_indel_bias_factor);       // one launch for every queued group
-    const std::map<int, ScoredSite>& sites(size_t read_idx) const { return m_reads[read_idx].sites; }
+    const std::map<int, ScoredSite>& sites(size_t read_idx) const;            // (device mode: built from the site records on first use)
     size_t num_reads() const { return m_reads.size(); }
-    size_t num_jobs() const { return m_batch.size(); }
+    // forward jobs of the batch: queued so far (host mode) / scored by the last run() (device mode: two per group)
+    size_t num_jobs() const { return m_mode == Mode::HostEnumeration ? m_batch.size() : (size_t)(2 * m_n_sites); }
+    uint64_t scored_events() const { return m_scored_events; }                // device mode, after run()
+    // every read's rows back to back in one buffer (device mode: formatted straight from the site records by
+    // host_threads() workers); returns the byte count, or the required size when cap is too small
+    size_t tsv_all(char* out, size_t cap) const;
     const HmmBatch& batch() const { return m_batch; }      // the queued jobs (read-only; for inspection and tests)
     void write_tsv(FILE* fp, size_t read_idx) const;
     std::string tsv(size_t read_idx) const;
@@ -95,17 +143,39 @@ public:
     // nph::modbam_tags
     ModbamTags modbam(size_t read_idx, const std::string& bam_seq, const std::vector<AlignedPair>& aligned_bases) const
     {
-        return modbam_tags(bam_seq, aligned_bases, m_reads[read_idx].is_reverse, m_reads[read_idx].sites, m_params);
+        return modbam_tags(bam_seq, aligned_bases, m_reads[read_idx].is_reverse, sites(read_idx), m_params);
     }
     void clear();
 
 private:
     struct Pending { size_t read; int site_key; size_t strand; size_t job_u, job_m; };
-    struct ReadEntry { std::string name; bool is_reverse; std::map<int, ScoredSite> sites; };
+    struct ReadEntry {
+        std::string name; bool is_reverse = false;
+        mutable std::map<int, ScoredSite> sites; mutable bool sites_built = false;
+        // device mode
+        std::string contig; size_t ref_off = 0, ref_len = 0; int ref_start_pos = 0; uint32_t k = 0;
+        size_t first_record = 0, n_records = 0;
+    };
+    struct Record { const SquiggleRead* read; const PoreModel* model; uint8_t strand; };
+    size_t add_read_host(const EventAlignedRead& r, int region_start, int region_end);
+    void stage(const EventAlignedRead* const* reads, size_t n, int region_start, int region_end);
+    void build_sites(size_t read_idx) const;
+    void append_rows(std::string& out, size_t read_idx) const;
+    Mode m_mode;
     MethylationCallingParameters m_params;
     HmmBatch m_batch;
     std::vector<Pending> m_pending;
     std::vector<ReadEntry> m_reads;
+    // device mode: the flat batch (page-locked) and its results
+    PinnedArray<char> m_ref;
+    PinnedArray<nph_aligned_pair> m_pairs;
+    PinnedArray<nph_meth_site> m_sites;
+    std::vector<nph_meth_record> m_records;
+    std::vector<Record> m_record_meta;
+    std::vector<uint64_t> m_site_off;
+    uint64_t m_n_sites = 0, m_scored_events = 0;
+    int m_region_start = -1, m_region_end = -1;
+    bool m_region_set = false, m_ran = false;
 };
 
 } // namespace nph

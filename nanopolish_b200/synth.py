@@ -59,6 +59,15 @@ assert EVENT_DT.itemsize == 24 and RAW_READ_DT.itemsize == 24 and EVENT_PARAMS_D
 RAW_JOB_DT = np.dtype([("sample_off", "<u8"), ("rank_off", "<u8"), ("n_samples", "<u4"), ("n_kmers", "<u4"), ("sample_rate", "<f8")], align=True)
 assert RAW_JOB_DT.itemsize == 32
 assert RAW_RANGE_DT.itemsize == 8 and EVENT_RANGE_DT.itemsize == 8 and CALIBRATION_DT.itemsize == 48
+METH_RECORD_DT = np.dtype([("ref_off", "<u8"), ("pair_off", "<u8"), ("read", "<u4"), ("model_id", "<u4"), ("ref_len", "<u4"),
+                           ("n_pairs", "<u4"), ("ref_start_pos", "<i4"), ("rc", "u1"), ("strand", "u1"), ("reserved", "u1", 2)], align=True)
+METH_SITE_DT = np.dtype([("start_position", "<i4"), ("end_position", "<i4"), ("n_motif", "<u4"), ("record", "<u4"),
+                         ("ll_unmethylated", "<f4"), ("ll_methylated", "<f4")], align=True)
+METH_PARAMS_DT = np.dtype([("min_separation", "<i4"), ("min_flank", "<i4"), ("max_span", "<i4"), ("min_event_span", "<i4"),
+                           ("region_start", "<i4"), ("region_end", "<i4"), ("k", "<u4"), ("alphabet_size", "<u4"),
+                           ("bases", "S8"), ("complements", "S8"), ("n_sites", "<u4"), ("site_len", "<u4"),
+                           ("sites", "S8", 4), ("sites_methylated", "S8", 4), ("sites_methylated_complement", "S8", 4)], align=True)
+assert METH_RECORD_DT.itemsize == 40 and METH_SITE_DT.itemsize == 24 and METH_PARAMS_DT.itemsize == 152
 assert ALIGN_STATE_DT.itemsize == 16
 assert READ_DT.itemsize == 64 and HMM_JOB_DT.itemsize == 32 and ABEA_JOB_DT.itemsize == 32
 assert PAIR_DT.itemsize == 8 and ABEA_RES_DT.itemsize == 24
@@ -447,3 +456,54 @@ def eventalign_chains(rs: ReadSet, model_id: int = 0):
         po += nk; mo += nk; ro += nk; oo += cap
     return (np.ascontiguousarray(np.concatenate(pairs)), np.concatenate(maps), np.concatenate(rf).astype(np.uint32),
             np.concatenate(rr).astype(np.uint32), chains)
+
+
+_METH_ALPHABETS = {   # name: (bases, complements, sites, methylated, methylated complement); src/common/nanopolish_alphabet.cpp:15-194
+    "cpg": (b"ACGMT", b"TGCGA", [b"CG"], [b"MG"], [b"GM"]),
+    "gpc": (b"ACGMT", b"TGCGA", [b"GC"], [b"GM"], [b"MG"]),
+    "dam": (b"ACGMT", b"TGCTA", [b"GATC"], [b"GMTC"], [b"CTMG"]),
+    "dcm": (b"ACGMT", b"TGCGA", [b"CCAGG", b"CCTGG"], [b"CMAGG", b"CMTGG"], [b"GGTMC", b"GGAMC"]),
+}
+
+
+def meth_params(alphabet: str = "cpg", k: int = 6, min_separation: int = 10, min_flank: int = 10, max_span: int = 200,
+                min_event_span: int = 10, region_start: int = -1, region_end: int = -1) -> np.ndarray:
+    """nph_meth_params for one of the reference's methylation alphabets (MethylationCallingParameters defaults)."""
+    bases, comps, sites, sm, smc = _METH_ALPHABETS[alphabet]
+    p = np.zeros(1, METH_PARAMS_DT)
+    p[0]["min_separation"], p[0]["min_flank"], p[0]["max_span"], p[0]["min_event_span"] = min_separation, min_flank, max_span, min_event_span
+    p[0]["region_start"], p[0]["region_end"], p[0]["k"], p[0]["alphabet_size"] = region_start, region_end, k, len(bases)
+    p[0]["bases"], p[0]["complements"], p[0]["n_sites"], p[0]["site_len"] = bases, comps, len(sites), len(sites[0])
+    for i in range(len(sites)):
+        p[0]["sites"][i], p[0]["sites_methylated"][i], p[0]["sites_methylated_complement"][i] = sites[i], sm[i], smc[i]
+    return p
+
+
+def methylation_records(rs: ReadSet, model_id: int = 1, ref_start: int = 10_000, rc_every: int = 0):
+    """call-methylation's per-record inputs for reads aligned to the sequence they were generated from: the reference
+    bases (the read's own sequence; reverse complemented for every rc_every-th read, whose events then fall as reference
+    positions rise) and EventAlignmentRecord::aligned_events (reference position of k-mer p, first event at or after that
+    k-mer), boundary k-mers dropped like alignment_db.cpp:60-67.  Returns (ref_bases u8[total], pairs PAIR_DT[total],
+    records METH_RECORD_DT[n_reads])."""
+    k = rs.k
+    refs, prs = [], []
+    recs = np.zeros(rs.n_reads, METH_RECORD_DT)
+    ro = po = 0
+    for i in range(rs.n_reads):
+        codes = rs.seq_codes[i]
+        nk = codes.shape[0] - k + 1
+        kfe = np.minimum(rs.kmer_first_event[i], int(rs.reads[i]["n_events"]) - 1)
+        p = np.arange(k, nk - k)
+        rc = 1 if (rc_every and i % rc_every == rc_every - 1) else 0
+        if rc:
+            ref = _CODE2DNA[(3 - codes[::-1]).astype(np.uint8)]
+            ev = kfe[nk - 1 - p]
+        else:
+            ref = _CODE2DNA[codes]
+            ev = kfe[p]
+        pr = np.zeros(p.shape[0], PAIR_DT)
+        pr["ref_pos"], pr["read_pos"] = ref_start + p, ev
+        recs[i] = (ro, po, i, model_id, ref.shape[0], pr.shape[0], ref_start, rc, 0, (0, 0))
+        refs.append(ref); prs.append(pr)
+        ro += ref.shape[0]; po += pr.shape[0]
+    return np.concatenate(refs), np.concatenate(prs), recs

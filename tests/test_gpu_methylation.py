@@ -1,0 +1,167 @@
+"""SURVEY.md 8(f) row N3 on the device — nph_methylation_batch (csrc/methylation.cu) through the C ABI.
+
+The checker is tests/meth_restatement.py: a plain-Python restatement of calculate_methylation_for_read
+(src/basemods/nanopolish_basemods.cpp:301-417; pinned to the compiled reference in tests/test_oracle_vs_ref.py)
+whose windows are scored by the oracle.  The device must return the same groups (positions, motif counts, order),
+bit-identical scores, and the same scored-event count; edge cases: reverse-strand records, windows cut by the end of
+the reference, records without sites / without an event alignment, region filters, non-default window parameters,
+and a multi-symbol alphabet (dam: GATC -> GMTC) with a random 5^6 model."""
+import numpy as np
+import pytest
+
+from nanopolish_b200 import synth
+from tests import meth_restatement as mr
+
+pytestmark = pytest.mark.gpu
+K = 6
+
+
+def _expected(port_oracle, rs, models, ref_bases, pairs, records, alphabet, **kw):
+    site_rows, jobs, ranks = mr.enumerate_batch(ref_bases, pairs, records, alphabet, K, **kw)
+    if jobs.shape[0]:
+        scores, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, models, ranks, jobs)
+    else:
+        scores = np.zeros(0, np.float32)
+    return site_rows, jobs, scores
+
+
+def _check(engine, port_oracle, rs, models, ref_bases, pairs, records, alphabet, **kw):
+    params = synth.meth_params(alphabet, K, **kw)
+    site_off, sites, scored = engine.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref_bases, pairs, records, params)
+    rows, jobs, scores = _expected(port_oracle, rs, models, ref_bases, pairs, records, alphabet, **kw)
+    assert sites.shape[0] == len(rows)
+    want_off = np.zeros(records.shape[0] + 1, np.uint64)
+    for r in rows:
+        want_off[r[0] + 1] += 1
+    want_off = np.cumsum(want_off).astype(np.uint64)
+    assert np.array_equal(site_off, want_off)
+    if rows:
+        w = np.array([(r[1], r[2], r[3], r[0]) for r in rows], np.int64)
+        assert np.array_equal(sites["start_position"], w[:, 0]) and np.array_equal(sites["end_position"], w[:, 1])
+        assert np.array_equal(sites["n_motif"], w[:, 2]) and np.array_equal(sites["record"], w[:, 3])
+        assert np.array_equal(sites["ll_unmethylated"].view(np.uint32), scores[0::2].view(np.uint32))
+        assert np.array_equal(sites["ll_methylated"].view(np.uint32), scores[1::2].view(np.uint32))
+        E = np.abs(jobs["event_stop"].astype(np.int64) - jobs["event_start"].astype(np.int64)) + 1
+        assert scored == int(E.sum())
+    return sites
+
+
+def _batch(n_reads, n_events, seed, rc_every=3):
+    nuc, cpg = synth.load_model("nucleotide"), synth.load_model("cpg")
+    rs = synth.gen_reads(n_reads, n_events, nuc, seed=seed, cpg_keep=0.3)
+    ref, pairs, recs = synth.methylation_records(rs, model_id=1, rc_every=rc_every)
+    return rs, [nuc, cpg], ref, pairs, recs
+
+
+@pytest.fixture(scope="module")
+def eng2(engine):
+    # engine fixture is shared: models 0 = nucleotide, 1 = cpg must exist in this order for these tests
+    from nanopolish_b200.engine import Engine
+    e = Engine(0)
+    e.model_upload(synth.load_model("nucleotide"))
+    e.model_upload(synth.load_model("cpg"))
+    yield e
+    e.close()
+
+
+def test_cpg_groups_and_scores_identical(eng2, port_oracle):
+    rs, models, ref, pairs, recs = _batch(12, 2500, 77)
+    sites = _check(eng2, port_oracle, rs, models, ref, pairs, recs, "cpg")
+    assert sites.shape[0] > 150 and (sites["n_motif"] > 1).any()
+
+
+def test_edge_records(eng2, port_oracle):
+    rs, models, ref, pairs, recs = _batch(8, 1200, 5)
+    recs = recs.copy()
+    ref = ref.copy()
+    # record 0: no CG at all; record 1: no event alignment; record 2: alignment that stops halfway (unbounded windows);
+    # record 3: reference cut right after a site so that the last window is clipped by substr
+    r0 = recs[0]; seg = ref[int(r0["ref_off"]):int(r0["ref_off"]) + int(r0["ref_len"])]
+    seg[seg == ord("G")] = ord("A")
+    recs[1]["n_pairs"] = 0
+    recs[2]["n_pairs"] = recs[2]["n_pairs"] // 2
+    r3 = recs[3]; seg3 = ref[int(r3["ref_off"]):int(r3["ref_off"]) + int(r3["ref_len"])]
+    cg = np.flatnonzero((seg3[:-1] == ord("C")) & (seg3[1:] == ord("G")))
+    cut = int(cg[len(cg) // 2]) + 2 + 3            # 3 bases after a site: its window (+10) runs past the end
+    recs[3]["ref_len"] = cut
+    _check(eng2, port_oracle, rs, models, ref, pairs, recs, "cpg")
+
+
+def test_region_and_window_parameters(eng2, port_oracle):
+    rs, models, ref, pairs, recs = _batch(6, 2000, 19)
+    _check(eng2, port_oracle, rs, models, ref, pairs, recs, "cpg", region_start=10_300, region_end=10_900)
+    _check(eng2, port_oracle, rs, models, ref, pairs, recs, "cpg", min_separation=5, min_flank=12, max_span=40, min_event_span=20)
+
+
+def test_dam_alphabet(port_oracle):
+    """GATC -> GMTC / CTMG: a four-symbol site whose methylated symbol is not the first one; random 5^6 model."""
+    from nanopolish_b200.engine import Engine
+    nuc = synth.load_model("nucleotide")
+    dam = synth.synthetic_model("cpg", 6, seed=99)          # any ACGMT table serves: the alphabet only fixes the symbols' ranks
+    rng = np.random.default_rng(4)
+    rs = synth.gen_reads(6, 2500, nuc, seed=31)
+    # plant GATC every ~40-70 bases (and some pairs 6 apart) in the read sequences' reference copies
+    ref, pairs, recs = synth.methylation_records(rs, model_id=1, rc_every=2)
+    ref = ref.copy()
+    for r in recs:
+        o, n = int(r["ref_off"]), int(r["ref_len"])
+        pos = 30
+        while pos + 12 < n:
+            ref[o + pos:o + pos + 4] = np.frombuffer(b"GATC", np.uint8)
+            if rng.random() < 0.3:
+                ref[o + pos + 6:o + pos + 10] = np.frombuffer(b"GATC", np.uint8)
+            pos += int(rng.integers(40, 70))
+    e = Engine(0)
+    try:
+        e.model_upload(nuc); e.model_upload(dam)
+        sites = _check(e, port_oracle, rs, [nuc, dam], ref, pairs, recs, "dam")
+        assert sites.shape[0] > 100
+    finally:
+        e.close()
+
+
+def test_staged_form_matches_one_shot(eng2):
+    rs, models, ref, pairs, recs = _batch(10, 1500, 123)
+    params = synth.meth_params("cpg", K)
+    off1, s1, ev1 = eng2.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref, pairs, recs, params)
+    eng2.reads_load(rs.reads, rs.ev_mean, rs.ev_start_time)
+    eng2.methylation_load(ref, pairs, recs, params)
+    for _ in range(2):                                   # repeatable on the resident batch
+        eng2.methylation_run()
+        off2, s2 = eng2.methylation_fetch()
+        n_sites, n_jobs, ev2 = eng2.methylation_counts()
+        assert n_sites == s1.shape[0] and n_jobs == 2 * n_sites and ev2 == ev1
+        assert np.array_equal(off1, off2) and s1.tobytes() == s2.tobytes()
+
+
+def test_large_batch_pipelined_upload(eng2, port_oracle):
+    """> 2^20 events: the one-shot call streams the event levels behind the enumeration (progress words)."""
+    rs, models, ref, pairs, recs = _batch(300, 4000, 999, rc_every=4)
+    params = synth.meth_params("cpg", K)
+    off1, s1, ev1 = eng2.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref, pairs, recs, params)
+    eng2.reads_load(rs.reads, rs.ev_mean, rs.ev_start_time)
+    eng2.methylation_load(ref, pairs, recs, params)
+    eng2.methylation_run()
+    off2, s2 = eng2.methylation_fetch()
+    assert np.array_equal(off1, off2) and s1.tobytes() == s2.tobytes()
+    # and a sample of it against the oracle
+    sub = recs[:5].copy()
+    _check(eng2, port_oracle, rs, models, ref, pairs, sub, "cpg")
+
+
+def test_invalid_inputs(eng2):
+    rs, models, ref, pairs, recs = _batch(3, 800, 8)
+    params = synth.meth_params("cpg", K)
+    from nanopolish_b200._lib import NphError
+    bad = recs.copy(); bad[1]["read"] = 99
+    with pytest.raises(NphError):
+        eng2.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref, pairs, bad, params)
+    bad = recs.copy(); bad[0]["ref_off"] = 2 ** 63
+    with pytest.raises(NphError):
+        eng2.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref, pairs, bad, params)
+    badp = pairs.copy(); badp["read_pos"][5:400] = 10 ** 6          # event indices outside the read: the reference would read out of bounds
+    with pytest.raises(NphError):
+        eng2.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref, badp, recs, params)
+    p5 = synth.meth_params("cpg", 5)                                 # k disagrees with the model
+    with pytest.raises(NphError):
+        eng2.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref, pairs, recs, p5)
