@@ -51,12 +51,21 @@ struct FwdParams {
     uint32_t kpad_stride;
     uint32_t edge_stride;
     uint32_t lsum_bias;           // NPH_LOGSUM_ADDR_BIAS, passed at run time on purpose (exact_math.cuh)
+    uint32_t lsum_scale;          // 4, at run time for the same reason (keeps the table address an IMAD)
     const uint32_t* progress;     // one-shot call: number of level chunks landed so far (nullptr: all resident)
     uint32_t chunk_events;        // events per level chunk (multiple of 32)
     HmmConsts c;
 };
 
+#ifndef NPH_PACKED_F32X2
+#define NPH_PACKED_F32X2 1          // 0: scalar inner loop for every C (the round-1 kernel; kept for A/B measurements)
+#endif
+
 // CHAIN = false: every job of the class fits one strip (K <= W*C), all strip/edge bookkeeping compiles away.
+// Even C: the lane's columns are paired (p, p + C/2) and the row update runs on sm_100's packed FP32 instructions
+// (exact_math.cuh).  With that pairing the "left neighbour" operand of pair p is simply pair p-1, so no half ever has
+// to be moved between register pairs except at the lane boundary; only the skip chain K[c] <- K[c-1], which is
+// sequential across the columns of a row, stays scalar.
 template <int C, int W, bool CHAIN>
 __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdParams p)
 {
@@ -67,7 +76,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
     extern __shared__ float s_tbl[];
     for (int i = threadIdx.x; i < NPH_TBL_SMEM; i += kCtaThreads) s_tbl[i] = p.logsum_g[i];
     __syncthreads();
-    const LogsumTable tb = make_logsum_table(s_tbl, p.lsum_bias);
+    const LogsumTable tb = make_logsum_table(s_tbl, p.lsum_bias, p.lsum_scale);
 
     const int lane = threadIdx.x & 31;
     const int gl = lane & (W - 1);            // lane within the group
@@ -148,10 +157,20 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
         const int my_steps = has_job ? last_strip * P + E + end_lane : 0;
         const int total_steps = (W == 32) ? my_steps : __reduce_max_sync(kFull, my_steps);
 
-        float mu[C], sd[C], cc[C], ry[C];
-        float Mp[C], Bp[C], Kp[C];
+        constexpr bool PACKED = (NPH_PACKED_F32X2 != 0) && (C % 2 == 0);
+        constexpr int H = PACKED ? C / 2 : 1;               // pairs per lane: pair p = columns (p, p + H)
+        constexpr int CS = PACKED ? 1 : C;                  // scalar state arrays collapse to one unused slot when packed
+        float mu[CS], sd[CS], cc[CS], ry[CS];
+        float Mp[CS], Bp[CS], Kp[CS];
+        f32x2 mu2[H], nsd2[H], cc2[H], ry2[H];              // Gaussian of the pair's columns; nsd = -sigma' (division by fma)
+        f32x2 Mp2[H], Bp2[H], Kp2[H];
 #pragma unroll
-        for (int c = 0; c < C; ++c) { mu[c] = 0.f; sd[c] = 1.f; cc[c] = 0.f; ry[c] = 1.f; Mp[c] = NEG; Bp[c] = NEG; Kp[c] = NEG; }
+        for (int c = 0; c < CS; ++c) { mu[c] = 0.f; sd[c] = 1.f; cc[c] = 0.f; ry[c] = 1.f; Mp[c] = NEG; Bp[c] = NEG; Kp[c] = NEG; }
+#pragma unroll
+        for (int q = 0; q < H; ++q) {
+            mu2[q] = bc2(0.f); nsd2[q] = bc2(-1.f); cc2[q] = bc2(0.f); ry2[q] = bc2(1.f);
+            Mp2[q] = bc2(NEG); Bp2[q] = bc2(NEG); Kp2[q] = bc2(NEG);
+        }
         float Lm_prev = NEG, Lb_prev = NEG, Lk_prev = NEG;
         float lp_end = NEG;
         int r = 1 - gl;        // row of this lane at the current step (rows 1..P; <1 = not started)
@@ -162,9 +181,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
 
         for (int g = 0; g < total_steps; ++g) {
             // left neighbour's newest row (its row == my row, computed one step ago)
-            float Lm = __shfl_up_sync(kFull, Mp[C - 1], 1, W);
-            float Lb = __shfl_up_sync(kFull, Bp[C - 1], 1, W);
-            float Lk = __shfl_up_sync(kFull, Kp[C - 1], 1, W);
+            float Lm = __shfl_up_sync(kFull, PACKED ? hi2(Mp2[H - 1]) : Mp[CS - 1], 1, W);
+            float Lb = __shfl_up_sync(kFull, PACKED ? hi2(Bp2[H - 1]) : Bp[CS - 1], 1, W);
+            float Lk = __shfl_up_sync(kFull, PACKED ? hi2(Kp2[H - 1]) : Kp[CS - 1], 1, W);
             if (gl == 0) { Lm = CHAIN ? em_next : NEG; Lb = CHAIN ? eb_next : NEG; Lk = CHAIN ? ek_next : NEG; }
 
             const bool in_strip = (r >= 1) && (s < n_strips);
@@ -175,13 +194,23 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
             if (in_strip && r == 1) {
                 // entering a strip: row 0 and the start column are -inf
 #pragma unroll
-                for (int c = 0; c < C; ++c) { Mp[c] = NEG; Bp[c] = NEG; Kp[c] = NEG; }
+                for (int c = 0; c < CS; ++c) { Mp[c] = NEG; Bp[c] = NEG; Kp[c] = NEG; }
+#pragma unroll
+                for (int q = 0; q < H; ++q) { Mp2[q] = bc2(NEG); Bp2[q] = bc2(NEG); Kp2[q] = bc2(NEG); }
                 Lm_prev = NEG; Lb_prev = NEG; Lk_prev = NEG;
                 if (col0 < K) {
+                    if (PACKED) {
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const float4 g4 = my_params[col0 + c];
-                        mu[c] = g4.x; sd[c] = g4.y; cc[c] = g4.z; ry[c] = g4.w;
+                        for (int q = 0; q < H; ++q) {
+                            const float4 ga = my_params[col0 + q], gb = my_params[col0 + q + H];
+                            mu2[q] = pk2(ga.x, gb.x); nsd2[q] = pk2(-ga.y, -gb.y); cc2[q] = pk2(ga.z, gb.z); ry2[q] = pk2(ga.w, gb.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CS; ++c) {
+                            const float4 g4 = my_params[col0 + c];
+                            mu[c] = g4.x; sd[c] = g4.y; cc[c] = g4.z; ry[c] = g4.w;
+                        }
                     }
                 }
             }
@@ -202,44 +231,98 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
                 float post = 0.f;
                 const bool do_end = (s == last_strip) && (gl == end_lane) && (post_clip || r == E);
                 if (do_end) post = p.flank[E - r];
+                float Me, Be, Ke;                                                  // states of the last k-mer's column (do_end)
 
-                float lm_prev = Lm_prev, lb_prev = Lb_prev, lk_prev = Lk_prev;   // left column, row r-1
-                float lm_cur = Lm, lb_cur = Lb, lk_cur = Lk;                      // left column, row r
+                if (PACKED) {
+                    const f32x2 x2 = bc2(x);
+                    f32x2 mN[H], bN[H], xk[H];
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    // Gaussian log-density, reference operation order (emissions.h:51-55)
-                    const float a = div_by_cached_rcp(__fsub_rn(x, mu[c]), sd[c], ry[c]);
-                    const float em = __fadd_rn(cc[c], __fmul_rn(__fmul_rn(-0.5f, a), a));
-                    // match: left fold over {same M, prev M, same B, prev B, prev K, soft}
-                    float m = __fadd_rn(lp_mm_self, Mp[c]);
-                    m = lsum(m, __fadd_rn(lp_mm_next, lm_prev), tb);
-                    m = lsum(m, __fadd_rn(lp_bm_self, Bp[c]), tb);
-                    m = lsum(m, __fadd_rn(lp_bm_next, lb_prev), tb);
-                    m = lsum(m, __fadd_rn(lp_km, lk_prev), tb);
-                    if (c == 0) m = lsum(m, soft, tb);
-                    m = __fadd_rn(m, em);
-                    // bad event: {same M, same B}
-                    const float b = lsum(__fadd_rn(lp_mb, Mp[c]), __fadd_rn(lp_bb, Bp[c]), tb);
-                    // k-mer skip: {prev M, prev B, prev K} of the SAME row
-                    float kk = lsum(__fadd_rn(lp_mk, lm_cur), __fadd_rn(lp_bk, lb_cur), tb);
-                    kk = lsum(kk, __fadd_rn(lp_kk, lk_cur), tb);
+                    for (int q = 0; q < H; ++q) {
+                        // Gaussian log-density of both columns, reference operation order (emissions.h:51-55)
+                        const f32x2 a = div2_by_cached_rcp(sub2(x2, mu2[q]), nsd2[q], ry2[q]);
+                        const f32x2 em = add2(cc2[q], mul2(mul2(bc2(-0.5f), a), a));
+                        // left column, previous row: pair q-1 as it stands; at the lane boundary the neighbour's value and column H-1
+                        const f32x2 sM = q ? Mp2[q > 0 ? q - 1 : 0] : pk2(Lm_prev, lo2(Mp2[H - 1]));
+                        const f32x2 sB = q ? Bp2[q > 0 ? q - 1 : 0] : pk2(Lb_prev, lo2(Bp2[H - 1]));
+                        const f32x2 sK = q ? Kp2[q > 0 ? q - 1 : 0] : pk2(Lk_prev, lo2(Kp2[H - 1]));
+                        // match: left fold over {same M, prev M, same B, prev B, prev K, soft}
+                        f32x2 m = add2(bc2(lp_mm_self), Mp2[q]);
+                        m = lsum2(m, add2(bc2(lp_mm_next), sM), tb);
+                        m = lsum2(m, add2(bc2(lp_bm_self), Bp2[q]), tb);
+                        m = lsum2(m, add2(bc2(lp_bm_next), sB), tb);
+                        m = lsum2(m, add2(bc2(lp_km), sK), tb);
+                        if (q == 0) m = pk2(lsum(lo2(m), soft, tb), hi2(m));       // column 0 of the lane only
+                        mN[q] = add2(m, em);
+                        // bad event: {same M, same B}
+                        bN[q] = lsum2(add2(bc2(lp_mb), Mp2[q]), add2(bc2(lp_bb), Bp2[q]), tb);
+                    }
+#pragma unroll
+                    for (int q = 0; q < H; ++q) {
+                        // k-mer skip, the part that does not depend on the chain: {prev M, prev B} of the SAME row
+                        const f32x2 cM = q ? mN[q > 0 ? q - 1 : 0] : pk2(Lm, lo2(mN[H - 1]));
+                        const f32x2 cB = q ? bN[q > 0 ? q - 1 : 0] : pk2(Lb, lo2(bN[H - 1]));
+                        xk[q] = lsum2(add2(bc2(lp_mk), cM), add2(bc2(lp_bk), cB), tb);
+                    }
+                    // the chain K[c] = x[c] (+) (lp_kk + K[c-1]) runs through the columns in order: lo halves, then hi halves
+                    float kn[C];
+                    float kprev = Lk;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const float xc = c < H ? lo2(xk[c < H ? c : 0]) : hi2(xk[c >= H ? c - H : 0]);
+                        kn[c] = lsum(xc, __fadd_rn(lp_kk, kprev), tb);
+                        kprev = kn[c];
+                    }
+#pragma unroll
+                    for (int q = 0; q < H; ++q) { Mp2[q] = mN[q]; Bp2[q] = bN[q]; Kp2[q] = pk2(kn[q], kn[q + H]); }
+                    Me = lo2(Mp2[0]); Be = lo2(Bp2[0]); Ke = lo2(Kp2[0]);
+#pragma unroll
+                    for (int c = 1; c < C; ++c)
+                        if (c == end_slot) {
+                            Me = c < H ? lo2(Mp2[c < H ? c : 0]) : hi2(Mp2[c >= H ? c - H : 0]);
+                            Be = c < H ? lo2(Bp2[c < H ? c : 0]) : hi2(Bp2[c >= H ? c - H : 0]);
+                            Ke = c < H ? lo2(Kp2[c < H ? c : 0]) : hi2(Kp2[c >= H ? c - H : 0]);
+                        }
+                } else {
+                    float lm_prev = Lm_prev, lb_prev = Lb_prev, lk_prev = Lk_prev;   // left column, row r-1
+                    float lm_cur = Lm, lb_cur = Lb, lk_cur = Lk;                      // left column, row r
+#pragma unroll
+                    for (int c = 0; c < CS; ++c) {
+                        // Gaussian log-density, reference operation order (emissions.h:51-55)
+                        const float a = div_by_cached_rcp(__fsub_rn(x, mu[c]), sd[c], ry[c]);
+                        const float em = __fadd_rn(cc[c], __fmul_rn(__fmul_rn(-0.5f, a), a));
+                        // match: left fold over {same M, prev M, same B, prev B, prev K, soft}
+                        float m = __fadd_rn(lp_mm_self, Mp[c]);
+                        m = lsum(m, __fadd_rn(lp_mm_next, lm_prev), tb);
+                        m = lsum(m, __fadd_rn(lp_bm_self, Bp[c]), tb);
+                        m = lsum(m, __fadd_rn(lp_bm_next, lb_prev), tb);
+                        m = lsum(m, __fadd_rn(lp_km, lk_prev), tb);
+                        if (c == 0) m = lsum(m, soft, tb);
+                        m = __fadd_rn(m, em);
+                        // bad event: {same M, same B}
+                        const float b = lsum(__fadd_rn(lp_mb, Mp[c]), __fadd_rn(lp_bb, Bp[c]), tb);
+                        // k-mer skip: {prev M, prev B, prev K} of the SAME row
+                        float kk = lsum(__fadd_rn(lp_mk, lm_cur), __fadd_rn(lp_bk, lb_cur), tb);
+                        kk = lsum(kk, __fadd_rn(lp_kk, lk_cur), tb);
 
-                    lm_prev = Mp[c]; lb_prev = Bp[c]; lk_prev = Kp[c];
-                    lm_cur = m; lb_cur = b; lk_cur = kk;
-                    Mp[c] = m; Bp[c] = b; Kp[c] = kk;
+                        lm_prev = Mp[c]; lb_prev = Bp[c]; lk_prev = Kp[c];
+                        lm_cur = m; lb_cur = b; lk_cur = kk;
+                        Mp[c] = m; Bp[c] = b; Kp[c] = kk;
+                    }
+                    Me = Mp[0]; Be = Bp[0]; Ke = Kp[0];
+#pragma unroll
+                    for (int c = 1; c < CS; ++c) if (c == end_slot) { Me = Mp[c]; Be = Bp[c]; Ke = Kp[c]; }
                 }
                 Lm_prev = Lm; Lb_prev = Lb; Lk_prev = Lk;
 
                 if (do_end) {
-                    float Me = Mp[0], Be = Bp[0], Ke = Kp[0];
-#pragma unroll
-                    for (int c = 1; c < C; ++c) if (c == end_slot) { Me = Mp[c]; Be = Bp[c]; Ke = Kp[c]; }
                     lp_end = lsum(lp_end, __fadd_rn(Me, post), tb);
                     lp_end = lsum(lp_end, __fadd_rn(Be, post), tb);
                     lp_end = lsum(lp_end, __fadd_rn(Ke, post), tb);
                 }
                 if (CHAIN && gl == W - 1 && s < last_strip) {
-                    edge_m[r] = Mp[C - 1]; edge_b[r] = Bp[C - 1]; edge_k[r] = Kp[C - 1];
+                    edge_m[r] = PACKED ? hi2(Mp2[H - 1]) : Mp[CS - 1];
+                    edge_b[r] = PACKED ? hi2(Bp2[H - 1]) : Bp[CS - 1];
+                    edge_k[r] = PACKED ? hi2(Kp2[H - 1]) : Kp[CS - 1];
                 }
             }
 

@@ -159,7 +159,7 @@ def test_invalid_inputs(eng2):
     bad = recs.copy(); bad[0]["ref_off"] = 2 ** 63
     with pytest.raises(NphError):
         eng2.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref, pairs, bad, params)
-    badp = pairs.copy(); badp["read_pos"][5:400] = 10 ** 6          # event indices outside the read: the reference would read out of bounds
+    badp = pairs.copy(); badp["read_pos"][5:400:3] = 10 ** 6        # event indices outside the read (one end of some window): the reference would read out of bounds
     with pytest.raises(NphError):
         eng2.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref, badp, recs, params)
     p5 = synth.meth_params("cpg", 5)                                 # k disagrees with the model
