@@ -3,7 +3,8 @@
 // A class is (C columns per lane, W lanes per job); 32/W jobs share a warp.  W < 32 classes hold
 // single-strip jobs (K <= W*C); W == 32 also chains strips for wide jobs.  A job goes to the class that
 // minimises modelled issue slots = steps x (per-step overhead + C x per-cell cost) x W/32, with the
-// constants measured by ncu (profiles/): ~88 instructions per block-cell, ~96 per warp step.
+// constants measured by ncu (profiles/): ~96 per warp step, ~88 instructions per block-cell for odd C and ~66 for
+// even C (whose columns run pairwise on sm_100's packed FP32 instructions).
 #pragma once
 #include <stdint.h>
 
@@ -34,7 +35,9 @@ NPH_HD uint32_t nph_class_steps(uint32_t K, uint32_t E, int C, uint32_t W)
     return (n_strips - 1) * P + E + (last_cols - 1) / (uint32_t)C;
 }
 
-NPH_HD float nph_class_cost(uint32_t steps, int C, uint32_t W) { return (float)steps * (96.0f + 88.0f * C) * (W * (1.0f / 32.0f)); }
+// per-step issue slots: ~96 of per-step work plus the row update — 88 per column in the scalar form (odd C), ~66 where the
+// columns are paired onto packed FP32 instructions (even C; SASS counts in DESIGN.md section 3.4)
+NPH_HD float nph_class_cost(uint32_t steps, int C, uint32_t W) { return (float)steps * (96.0f + ((C & 1) ? 88.0f : 66.0f) * C) * (W * (1.0f / 32.0f)); }
 
 // returns class index; *steps_out = steps in that class
 NPH_HD int nph_choose_class(uint32_t K, uint32_t E, uint32_t* steps_out)

@@ -52,6 +52,7 @@ struct FwdParams {
     uint32_t edge_stride;
     uint32_t lsum_bias;           // NPH_LOGSUM_ADDR_BIAS, passed at run time on purpose (exact_math.cuh)
     uint32_t lsum_scale;          // 4, at run time for the same reason (keeps the table address an IMAD)
+    float neg_zero;               // -0.0f, at run time: see the emission in the packed row update
     const uint32_t* progress;     // one-shot call: number of level chunks landed so far (nullptr: all resident)
     uint32_t chunk_events;        // events per level chunk (multiple of 32)
     HmmConsts c;
@@ -235,12 +236,17 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
 
                 if (PACKED) {
                     const f32x2 x2 = bc2(x);
+                    // ptxas contracts mul.rn.f32x2 feeding add.rn.f32x2 into one FFMA2 (-fmad=false and the .rn modifiers do not
+                    // stop it for the packed forms; seen in SASS, caught by the bit-parity tests).  The product is therefore
+                    // formed as fma(t, a, -0.0) with a -0.0 ptxas cannot see (x*y + -0.0 == RN(x*y) including the sign of zero),
+                    // which leaves FFMA2 -> FADD2, a pair that cannot be fused.
+                    const f32x2 nz2 = bc2(p.neg_zero);
                     f32x2 mN[H], bN[H], xk[H];
 #pragma unroll
                     for (int q = 0; q < H; ++q) {
                         // Gaussian log-density of both columns, reference operation order (emissions.h:51-55)
                         const f32x2 a = div2_by_cached_rcp(sub2(x2, mu2[q]), nsd2[q], ry2[q]);
-                        const f32x2 em = add2(cc2[q], mul2(mul2(bc2(-0.5f), a), a));
+                        const f32x2 em = add2(cc2[q], fma2(mul2(bc2(-0.5f), a), a, nz2));
                         // left column, previous row: pair q-1 as it stands; at the lane boundary the neighbour's value and column H-1
                         const f32x2 sM = q ? Mp2[q > 0 ? q - 1 : 0] : pk2(Lm_prev, lo2(Mp2[H - 1]));
                         const f32x2 sB = q ? Bp2[q > 0 ? q - 1 : 0] : pk2(Lb_prev, lo2(Bp2[H - 1]));

@@ -479,12 +479,33 @@ def meth_params(alphabet: str = "cpg", k: int = 6, min_separation: int = 10, min
     return p
 
 
+def closest_event_map(which: np.ndarray, nk: int):
+    """(base_to_event_map[*].indices[0].start, .stop, closest) per k-mer of a read whose event i was emitted by k-mer which[i]:
+    start/stop = first/last event of the k-mer (-1: none); closest[p] = SquiggleRead::get_closest_event_to(p) — the first event
+    of the nearest k-mer at or before p that has one (within 1000 k-mers), else of the nearest one after it
+    (src/nanopolish_squiggle_read.cpp:160-186)."""
+    first = np.searchsorted(which, np.arange(nk), side="left")
+    last = np.searchsorted(which, np.arange(nk), side="right") - 1
+    has = last >= first
+    start = np.where(has, first, -1).astype(np.int32)
+    stop = np.where(has, last, -1).astype(np.int32)
+    idx = np.arange(nk)
+    prev = np.maximum.accumulate(np.where(has, idx, -1))                 # nearest k-mer <= p with an event
+    nxt = np.minimum.accumulate(np.where(has, idx, nk)[::-1])[::-1]       # nearest k-mer >= p with an event
+    # the backward scan covers [max(0, p - 1000) + 1, p] (its loop stops before stop_before), the forward one [p, min(p + 1000, nk - 1) - 1]
+    stop_before = np.maximum(idx - 1000, 0)
+    stop_after = np.minimum(idx + 1000, nk - 1)
+    before = np.where((prev >= 0) & (prev > stop_before), start[np.maximum(prev, 0)], -1)
+    after = np.where((nxt < nk) & (nxt < stop_after), start[np.minimum(nxt, nk - 1)], -1)
+    return start, stop, np.where(before == -1, after, before).astype(np.int32)
+
+
 def methylation_records(rs: ReadSet, model_id: int = 1, ref_start: int = 10_000, rc_every: int = 0):
-    """call-methylation's per-record inputs for reads aligned to the sequence they were generated from: the reference
-    bases (the read's own sequence; reverse complemented for every rc_every-th read, whose events then fall as reference
-    positions rise) and EventAlignmentRecord::aligned_events (reference position of k-mer p, first event at or after that
-    k-mer), boundary k-mers dropped like alignment_db.cpp:60-67.  Returns (ref_bases u8[total], pairs PAIR_DT[total],
-    records METH_RECORD_DT[n_reads])."""
+    """call-methylation's per-record inputs for reads aligned base for base (CIGAR all M) to the sequence they were generated
+    from: the reference bases (the read's own sequence; its reverse complement for every rc_every-th read, a reverse-strand
+    record whose events fall as reference positions rise) and EventAlignmentRecord::aligned_events exactly as
+    src/alignment/nanopolish_alignment_db.cpp:50-91 builds them (boundary k-mers dropped, get_closest_event_to of the read-strand
+    k-mer).  Returns (ref_bases u8[total], pairs PAIR_DT[total], records METH_RECORD_DT[n_reads])."""
     k = rs.k
     refs, prs = [], []
     recs = np.zeros(rs.n_reads, METH_RECORD_DT)
@@ -492,17 +513,21 @@ def methylation_records(rs: ReadSet, model_id: int = 1, ref_start: int = 10_000,
     for i in range(rs.n_reads):
         codes = rs.seq_codes[i]
         nk = codes.shape[0] - k + 1
-        kfe = np.minimum(rs.kmer_first_event[i], int(rs.reads[i]["n_events"]) - 1)
-        p = np.arange(k, nk - k)
+        read_length = codes.shape[0]
+        _, _, closest = closest_event_map(rs.ev_kmer[i], nk)
+        p = np.arange(k, read_length - k)                      # read_pos >= k and read_pos + k < read_length
+        p = p[p < nk]
         rc = 1 if (rc_every and i % rc_every == rc_every - 1) else 0
         if rc:
             ref = _CODE2DNA[(3 - codes[::-1]).astype(np.uint8)]
-            ev = kfe[nk - 1 - p]
+            ev = closest[read_length - p - k]                  # flip_k_strand
         else:
             ref = _CODE2DNA[codes]
-            ev = kfe[p]
+            ev = closest[p]
         pr = np.zeros(p.shape[0], PAIR_DT)
         pr["ref_pos"], pr["read_pos"] = ref_start + p, ev
+        if pr.shape[0] and pr["read_pos"][0] == pr["read_pos"][-1]:
+            pr = pr[:0]                                        # degenerate alignment: the reference clears it
         recs[i] = (ro, po, i, model_id, ref.shape[0], pr.shape[0], ref_start, rc, 0, (0, 0))
         refs.append(ref); prs.append(pr)
         ro += ref.shape[0]; po += pr.shape[0]

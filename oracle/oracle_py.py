@@ -273,6 +273,22 @@ class RefOracle:
             raise RuntimeError("npref_eventalign: output buffer too small")
         return tsv.value.decode(), cs.value.decode(), ea[:n].copy()
 
+    def call_methylation(self, read_h, read_name: str, contig_name: str, contig: str, ref_pos, flag, cigar, methylation_type="cpg",
+                         region=(-1, -1), indel_bias=1.0):
+        """calculate_methylation_for_read + write_methylation_results_as_tsv on a hand-built record.
+        Returns (tsv text, int32[n, 4] of (start, end, n_motif, strands_scored), float64[n, 2] of strand-0 (ll_unmethylated, ll_methylated))."""
+        cg = np.ascontiguousarray(cigar, np.uint32)
+        cap, scap = 1 << 22, 1 << 15
+        tsv = C.create_string_buffer(cap)
+        sites = np.zeros((scap, 4), np.int32); ll = np.zeros((scap, 2), np.float64)
+        self.lib.npref_call_methylation.restype = C.c_longlong
+        n = self.lib.npref_call_methylation(int(read_h), read_name.encode(), contig_name.encode(), contig.encode(), int(ref_pos), int(flag), _p(cg),
+                                            int(cg.shape[0]), methylation_type.encode(), int(region[0]), int(region[1]), C.c_double(indel_bias),
+                                            tsv, C.c_size_t(cap), _p(sites), _p(ll), C.c_size_t(scap))
+        if n < 0:
+            raise RuntimeError("npref_call_methylation: output buffer too small")
+        return tsv.value.decode(), sites[:n].copy(), ll[:n].copy()
+
     def score_variants_thresholded(self, read_handles, windows, rc, ref_seq: str, ref_position, variants, flags, threshold,
                                    methylation: bool, indel_bias=1.0):
         """[score_variant_thresholded(v, Haplotype(ref), reads, flags, threshold, types).quality for v in variants], single thread"""

@@ -107,6 +107,7 @@ EventalignSummary summarize_alignment(const SquiggleRead& sr, uint32_t strand_id
 extern "C" uint8_t* bam_aux_get(const bam1_t*, const char[2]) { return NULL; }
 extern "C" int64_t bam_aux2i(const uint8_t*) { return 0; }
 std::vector<uint32_t> event_alignment_to_cigar(const std::vector<EventAlignment>& alignments);   // nanopolish_eventalign.cpp:256
+void write_methylation_results_as_tsv(FILE* site_writer, const bam1_t* record, std::map<int, ScoredSite>& site_score_map);   // nanopolish_call_methylation.cpp:532
 std::string cigar_ops_to_string(const std::vector<uint32_t>& ops);                                 // :246
 
 namespace {
@@ -555,6 +556,64 @@ void npref_eventalign_summary(int32_t* ints5, double* doubles2)
     ints5[0] = g_last_summary.num_events; ints5[1] = g_last_summary.num_steps; ints5[2] = g_last_summary.num_stays;
     ints5[3] = g_last_summary.num_skips; ints5[4] = g_last_summary.reference_span;
     doubles2[0] = g_last_summary.sum_duration; doubles2[1] = g_last_summary.sum_z_score;
+}
+
+// ---- call-methylation: calculate_methylation_for_read (src/basemods/nanopolish_basemods.cpp:238-457) followed by
+// write_methylation_results_as_tsv (src/nanopolish_call_methylation.cpp:532-550) on a hand-built BAM record ----
+// The read carries what load_from_raw leaves (events, scalings, read_sequence, base_to_event_map: npref_read_create +
+// npref_read_set_eventalign); the reference comes from the in-memory contig through the faidx test double.  Returns the
+// number of ScoredSites; sites_out gets (start, end, n_motif, strands_scored) and ll_out (ll_unmethylated[0],
+// ll_methylated[0]) per site; tsv_out the rows the reference prints.  -1: a buffer is too small.
+long long npref_call_methylation(int read_h, const char* read_name, const char* contig_name, const char* contig_seq, int ref_pos, int flag,
+                                 const uint32_t* cigar, int n_cigar, const char* methylation_type, int region_start, int region_end,
+                                 double indel_bias, char* tsv_out, size_t tsv_cap, int32_t* sites_out, double* ll_out, size_t site_cap)
+{
+    NprefContig contig{contig_name, contig_seq};
+    bam_hdr_t hdr;
+    memset(&hdr, 0, sizeof(hdr));
+    char* names[1] = { const_cast<char*>(contig.name.c_str()) };
+    uint32_t lens[1] = { (uint32_t)contig.seq.size() };
+    hdr.n_targets = 1; hdr.target_name = names; hdr.target_len = lens;
+    // record data: qname (NUL-terminated, padded to a multiple of four), CIGAR; no SEQ / QUAL (l_qseq = 0)
+    const size_t nl = strlen(read_name) + 1, l_qname = (nl + 3) / 4 * 4;
+    std::vector<uint8_t> data(l_qname + 4 * (size_t)n_cigar, 0);
+    memcpy(data.data(), read_name, nl);
+    memcpy(data.data() + l_qname, cigar, 4 * (size_t)n_cigar);
+    bam1_t rec;
+    memset(&rec, 0, sizeof(rec));
+    rec.core.pos = ref_pos; rec.core.tid = 0; rec.core.flag = (uint16_t)flag; rec.core.l_qname = (uint16_t)l_qname;
+    rec.core.l_extranul = (uint8_t)(l_qname - nl); rec.core.n_cigar = n_cigar; rec.core.mtid = -1; rec.core.mpos = -1;
+    rec.data = data.data(); rec.l_data = (int)data.size(); rec.m_data = (uint32_t)data.size();
+
+    MethylationCallingParameters params;
+    params.methylation_type = methylation_type;
+    params.alphabet = get_alphabet_by_name(params.methylation_type);
+    OutputHandles handles;
+    MethylationCallingResult result;
+    const double saved_bias = hmm_indel_bias_factor;
+    hmm_indel_bias_factor = indel_bias;
+    calculate_methylation_for_read(handles, result, *g_reads[read_h], params, reinterpret_cast<const faidx_t*>(&contig), &hdr, &rec, 0,
+                                   region_start, region_end);
+    hmm_indel_bias_factor = saved_bias;
+    std::map<int, ScoredSite>& sites = result[&rec];
+    char* buf = NULL; size_t len = 0;
+    FILE* fp = open_memstream(&buf, &len);
+    write_methylation_results_as_tsv(fp, &rec, sites);
+    fclose(fp);
+    const bool ok = len < tsv_cap && sites.size() <= site_cap;
+    if(ok) {
+        memcpy(tsv_out, buf, len); tsv_out[len] = 0;
+        size_t i = 0;
+        for(const auto& kv : sites) {
+            const ScoredSite& ss = kv.second;
+            sites_out[4 * i] = ss.start_position; sites_out[4 * i + 1] = ss.end_position; sites_out[4 * i + 2] = ss.n_motif;
+            sites_out[4 * i + 3] = ss.strands_scored;
+            ll_out[2 * i] = ss.ll_unmethylated[0]; ll_out[2 * i + 1] = ss.ll_methylated[0];
+            ++i;
+        }
+    }
+    free(buf);
+    return ok ? (long long)sites.size() : -1;
 }
 
 } // extern "C"

@@ -165,3 +165,46 @@ def test_invalid_inputs(eng2):
     p5 = synth.meth_params("cpg", 5)                                 # k disagrees with the model
     with pytest.raises(NphError):
         eng2.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref, pairs, recs, p5)
+
+
+def test_device_equals_compiled_reference(eng2, ref_oracle):
+    """nph_methylation_batch against the compiled reference's own calculate_methylation_for_read + TSV writer (oracle/_ref,
+    which travels to the GPU box): records built the way BAM / FASTA / SquiggleRead present them (tests/meth_cases.py)."""
+    from tests import meth_cases as mc
+    nuc = synth.load_model("nucleotide")
+    rs = synth.gen_reads(9, 2200, nuc, seed=4242, cpg_keep=0.35)
+    ref_oracle.clear_reads()
+    mh = ref_oracle.builtin_model("nucleotide")
+    ref_oracle.builtin_model("cpg")
+    rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, mh)
+    rng = np.random.default_rng(11)
+    refs, prs, want_tsv, want_ll, cases = [], [], [], [], []
+    recs = np.zeros(rs.n_reads, synth.METH_RECORD_DT)
+    ro = po = 0
+    for i in range(rs.n_reads):
+        case = mc.make_case(i, rs, rng)
+        one = np.ones(int(rs.reads[i]["n_events"]), np.float32)
+        ref_oracle.read_set_eventalign(rh[i], case["name"], case["read_sequence"], case["b2e_start"], case["b2e_stop"], one, one)
+        tsv_ref, sites_ref, ll_ref = ref_oracle.call_methylation(rh[i], case["name"], "chr1", case["contig"], case["ref_pos"], case["flag"], case["cigar"])
+        pairs, rc = mc.event_alignment_record(case)
+        ref = np.frombuffer(mc.fetched_reference(case).encode(), np.uint8)
+        pr = np.zeros(len(pairs), synth.PAIR_DT)
+        if pairs:
+            pr["ref_pos"], pr["read_pos"] = [p[0] for p in pairs], [p[1] for p in pairs]
+        recs[i] = (ro, po, i, 1, ref.shape[0], pr.shape[0], case["ref_pos"], rc, 0, (0, 0))
+        refs.append(ref); prs.append(pr); want_tsv.append(tsv_ref); want_ll.append(ll_ref); cases.append(case)
+        ro += ref.shape[0]; po += pr.shape[0]
+    ref_bases, pairs = np.concatenate(refs), np.concatenate(prs)
+    site_off, sites, _ = eng2.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref_bases, pairs, recs, synth.meth_params("cpg", K))
+    total = 0
+    for i, case in enumerate(cases):
+        s = sites[int(site_off[i]):int(site_off[i + 1])]
+        ll = want_ll[i]
+        assert s.shape[0] == ll.shape[0]
+        assert np.array_equal(s["ll_unmethylated"].astype(np.float64), ll[:, 0]) and np.array_equal(s["ll_methylated"].astype(np.float64), ll[:, 1])
+        fetched = mc.fetched_reference(case)
+        rows = [(int(x["start_position"]), int(x["end_position"]), int(x["n_motif"]), x["ll_unmethylated"], x["ll_methylated"],
+                 fetched[int(x["start_position"]) - case["ref_pos"] - K + 1:int(x["end_position"]) - case["ref_pos"] + K]) for x in s]
+        assert mc.tsv_rows("chr1", "-" if case["flag"] & 16 else "+", case["name"], rows) == want_tsv[i]
+        total += s.shape[0]
+    assert total > 200

@@ -213,3 +213,52 @@ def test_recalibrate_port_solves_the_weighted_least_squares(port_oracle):
         assert cal["events_per_base"] == (int(pr["read_pos"].max()) - int(pr["read_pos"].min())) / rk.shape[0]
         # recovered scalings are close to the ones the read was simulated with
         assert abs(cal["shift"] - rs.reads[j]["shift"]) < 1.5 and abs(cal["scale"] - rs.reads[j]["scale"]) < 0.02
+
+
+def _meth_expected(port_oracle, rs, models, i, case):
+    """the restatement's TSV + (sites, scores) for one case: EventAlignmentRecord -> enumeration -> oracle scores -> rows"""
+    from tests import meth_cases as mc, meth_restatement as mr
+    pairs, rc = mc.event_alignment_record(case)
+    ref = mc.fetched_reference(case)
+    groups = mr.enumerate_record(ref, case["ref_pos"], [p[0] for p in pairs], [p[1] for p in pairs], rc, "cpg", mc.K)
+    rows, lls = [], []
+    for (sp, ep, nm, e1, e2, ru, rm, seq) in groups:
+        jobs = np.zeros(2, synth.HMM_JOB_DT)
+        st = 1 if e1 <= e2 else -1
+        jobs[0] = (0, i, 1, e1, e2, ru.shape[0], st, rc, 3, 0)
+        jobs[1] = (ru.shape[0], i, 1, e1, e2, rm.shape[0], st, rc, 3, 0)
+        sc, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, models, np.concatenate([ru, rm]).astype(np.uint32), jobs)
+        rows.append((sp, ep, nm, sc[0], sc[1], seq)); lls.append((float(sc[0]), float(sc[1])))
+    tsv = mc.tsv_rows("chr1", "-" if case["flag"] & 16 else "+", case["name"], rows)
+    return tsv, rows, np.array(lls, np.float64).reshape(-1, 2)
+
+
+def test_call_methylation_restatement_pinned(port_oracle, ref_oracle):
+    """tests/meth_restatement.py + tests/meth_cases.py (EventAlignmentRecord, reference fetch, TSV row) reproduce the compiled
+    reference's calculate_methylation_for_read + write_methylation_results_as_tsv byte for byte: forward and reverse records,
+    CIGARs with insertions / deletions / soft clips, IUPAC and lower-case reference bases."""
+    from tests import meth_cases as mc
+    nuc, cpg = synth.load_model("nucleotide"), synth.load_model("cpg")
+    rs = synth.gen_reads(6, 2200, nuc, seed=515, cpg_keep=0.35)
+    ref_oracle.clear_reads()
+    mh = ref_oracle.builtin_model("nucleotide")
+    ref_oracle.builtin_model("cpg")
+    rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, mh)
+    rng = np.random.default_rng(7)
+    total = 0
+    for i in range(rs.n_reads):
+        case = mc.make_case(i, rs, rng)
+        one = np.ones(int(rs.reads[i]["n_events"]), np.float32)
+        ref_oracle.read_set_eventalign(rh[i], case["name"], case["read_sequence"], case["b2e_start"], case["b2e_stop"], one, one)
+        tsv_ref, sites_ref, ll_ref = ref_oracle.call_methylation(rh[i], case["name"], "chr1", case["contig"], case["ref_pos"], case["flag"], case["cigar"])
+        tsv, rows, ll = _meth_expected(port_oracle, rs, [nuc, cpg], i, case)
+        assert tsv == tsv_ref
+        assert np.array_equal(sites_ref[:, :3], np.array([r[:3] for r in rows], np.int32).reshape(-1, 3))
+        assert np.array_equal(ll_ref, ll)                      # float scores widened to double: exact
+        total += len(rows)
+    assert total > 120
+    # the output window (-w): the same filter on both sides
+    case = mc.make_case(0, rs, np.random.default_rng(7))
+    lo, hi = case["ref_pos"] + 400, case["ref_pos"] + 1100
+    tsv_ref, sites_ref, _ = ref_oracle.call_methylation(rh[0], case["name"], "chr1", case["contig"], case["ref_pos"], case["flag"], case["cigar"], region=(lo, hi))
+    assert 0 < sites_ref.shape[0] < 40 and (sites_ref[:, 0] >= lo).all() and (sites_ref[:, 1] < hi).all()
