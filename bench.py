@@ -38,7 +38,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="scorereads", choices=["scorereads", "methylation", "abea", "events", "prologue", "eventalign"])
+    ap.add_argument("--workload", default="scorereads",
+                    choices=["scorereads", "methylation", "call_methylation", "abea", "events", "prologue", "eventalign"])
+    ap.add_argument("--meth-reads", type=int, default=0,
+                    help="reads per GPU of the call-methylation block (default 10000 at N=1; 12500 at N>1 = BASELINE configs[2]'s 100k reads at N=8)")
+    ap.add_argument("--no-call-methylation", action="store_true", help="skip the configs.call_methylation block of the default line")
     ap.add_argument("--reads", type=int, default=10000, help="reads per GPU")
     ap.add_argument("--events", type=int, default=4000, help="events per read")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -253,6 +257,221 @@ def workload_config(args, jobs, reads_override=None):
             "reads_per_gpu": reads_override or args.reads, "events_per_read": args.events,
             "mean_E": float(E.mean()), "mean_K": float(j["n_kmers"].mean()),
             "parallelism": f"read-shard x{args.gpus}", "l2": "inputs larger than L2 (levels+ranks+scratch > 126 MB)"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# call-methylation end to end (BASELINE.json's metric names this caller; configs[2]): reference bases + event
+# alignments in, per-site log-likelihood pairs / TSV rows out — enumeration, scheduling and scoring all on the device.
+# ------------------------------------------------------------------------------------------------------------------
+class _DevBytes:
+    """zero-copy view of device memory for torch (CUDA array interface)"""
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def call_methylation_block(args, rank, world, local, steps, warmup):
+    """One step = nph_methylation_run over the resident batch (motif scan, grouping, event bounds, k-mer ranks, schedule,
+    both forward scores per group, site records) and, at N > 1, ONE variable-length NCCL gather of the site records to
+    rank 0 straight from device memory.  e2e = the C++ host's flat entry (libnph_host.so nphh_call_methylation_flat): page-locked
+    host buffers in, methylation_calls.tsv bytes out, plus at N > 1 the gather of the TSV bytes to rank 0."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from nanopolish_b200 import synth
+    from nanopolish_b200.dist import gather_records_to_rank0, gather_to_rank0
+    from nanopolish_b200.engine import Engine
+
+    dev = torch.device("cuda", local)
+    n_reads = args.meth_reads or (10000 if world == 1 else 12500)
+    nuc, cpg = synth.load_model("nucleotide"), synth.load_model("cpg")
+    rs = synth.gen_reads(n_reads, args.events, nuc, seed=7_000_003 + 1_000_003 * rank, cpg_keep=0.3)
+    ref, pairs, recs = synth.methylation_records(rs, model_id=1, rc_every=2)
+    params = synth.meth_params("cpg", 6)
+    stream = torch.cuda.current_stream().cuda_stream
+    eng = Engine(local, stream=stream)
+    eng.model_upload(nuc); eng.model_upload(cpg)
+
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
+        return t, t.numpy().view(a.dtype).reshape(a.shape)
+    keep = []
+    def P(a):
+        t, v = pin(a); keep.append(t); return v
+    h_reads, h_mean, h_ref, h_pairs, h_recs = P(rs.reads), P(rs.ev_mean), P(ref), P(pairs), P(recs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ----
+    eng.reads_load(h_reads, h_mean, rs.ev_start_time)
+    eng.methylation_load(h_ref, h_pairs, h_recs, params)
+
+    def step():
+        eng.methylation_run()
+        if world > 1:
+            ptr, n = eng.methylation_sites_dev()
+            raw = torch.as_tensor(_DevBytes(ptr, max(n, 1) * 24), device=dev)[:n * 24]
+            return gather_to_rank0(raw, None)           # tiny all_gather of the byte counts + ONE padded NCCL gather
+        return None
+
+    for _ in range(max(3, warmup)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        gathered = step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    n_sites, n_jobs, scored = eng.methylation_counts()
+    kern = []
+    for _ in range(5):
+        eng.methylation_run(); eng.sync(); kern.append(eng.last_kernel_ms())
+    kernel_ms, launches = float(np.mean([k[0] for k in kern])), int(kern[-1][1])
+    site_off, sites = eng.methylation_fetch()
+    tot = torch.tensor([float(scored), float(n_sites), float(n_reads)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+        if rank == 0:
+            assert sum(int(g.shape[0]) for g in gathered) == int(tot[1].item()) * 24, "gathered site records"
+    scored_all, sites_all, reads_all = (float(x) for x in tot.tolist())
+    value = scored_all * steps / (total_ms * 1e-3)
+
+    # ---- e2e arm: host buffers -> TSV bytes through the C++ host ----
+    os.environ["NPH_DEVICE"] = str(local)
+    host = C.CDLL(os.path.join(ROOT, "nanopolish_b200", "libnph_host.so"))
+    host.nphh_last_error.restype = C.c_char_p
+    host.nphh_call_methylation_flat.restype = C.c_longlong
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    cm = np.ascontiguousarray(cpg.level_mean); cs = np.ascontiguousarray(cpg.level_stdv); cl = np.ascontiguousarray(cpg.level_log_stdv)
+    mh = host.nphh_model_create(b"cpg", 6, cm.shape[0], vp(cm), vp(cs), vp(cl))
+    names = (C.c_char_p * n_reads)(*[f"read_{rank}_{i}".encode() for i in range(n_reads)])
+    is_rev = np.ascontiguousarray(recs["rc"])
+    cap = 128 * int(n_sites) + 4096
+    t_tsv = torch.empty(cap, dtype=torch.uint8).pin_memory(); keep.append(t_tsv)
+    tsv = t_tsv.numpy()
+    secs2 = np.zeros(2)
+    ns, se = C.c_uint64(), C.c_uint64()
+
+    def e2e_step():
+        n = host.nphh_call_methylation_flat(vp(h_reads), C.c_size_t(n_reads), vp(h_mean), None, C.c_size_t(h_mean.shape[0]),
+                                            vp(h_ref), C.c_size_t(h_ref.shape[0]), vp(h_pairs), C.c_size_t(h_pairs.shape[0]),
+                                            vp(h_recs), C.c_size_t(n_reads), mh, names, vp(is_rev), b"chr1", C.c_double(1.0),
+                                            vp(tsv), C.c_size_t(cap), C.byref(ns), C.byref(se), vp(secs2))
+        if n < 0:
+            raise RuntimeError("nphh_call_methylation_flat: " + host.nphh_last_error().decode())
+        if world > 1:
+            gather_records_to_rank0(tsv[:n], device=dev)
+        return int(n)
+
+    for _ in range(2):
+        tsv_bytes = e2e_step()
+    barrier()
+    e2e_steps = max(3, min(steps, 10))
+    stage = np.zeros(2)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        tsv_bytes = e2e_step(); stage += secs2
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    assert int(ns.value) == n_sites and int(se.value) == scored
+    h2d = h_reads.nbytes + h_mean.nbytes + h_ref.nbytes + h_pairs.nbytes + h_recs.nbytes + 8 * (n_reads + 1) + 8 * n_reads
+    d2h = 24 * n_sites + 8 * (n_reads + 1) + 64
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        # algorithmic bytes of the forward kernels (SURVEY.md 8d: 4E + L + 36 per job); L from the site records
+        span = (sites["end_position"].astype(np.int64) - sites["start_position"].astype(np.int64)) + 21
+        b_alg = 4 * scored + 2 * int(span.sum()) + 36 * n_jobs
+        achieved = b_alg / (kernel_ms * 1e-3) / 1e9
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(3, warmup),
+               "ms_per_step": total_ms / steps, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+               "config": {"workload": f"call-methylation: synthetic R9.4 reads x {args.events} events aligned to their own sequence (CIGAR all M, half "
+                                      "the records reverse strand), CpG groups ~60 bp apart, cpg model (5^6 states), PRE|POST clip; motif scan, "
+                                      "grouping, event bounds, k-mer ranks, scheduling and both scores per group on the device",
+                          "reads_per_gpu": n_reads, "reads_total": reads_all, "events_per_read": args.events, "sites_per_step": sites_all,
+                          "jobs_per_gpu": n_jobs, "scored_events_per_step": scored_all, "parallelism": f"read-shard x{world}",
+                          "multi_gpu": "one variable-length NCCL gather of the 24-byte site records to rank 0 per step" if world > 1 else None,
+                          "l2": "inputs larger than L2 (levels + event alignments + reference > 126 MB)"},
+               "e2e": {"value": scored_all * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "steps": e2e_steps, "tsv_bytes_per_step": tsv_bytes, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                       "stage_ms": {"device_call": float(stage[0] / e2e_steps * 1e3), "tsv": float(stage[1] / e2e_steps * 1e3)},
+                       "api": "libnph_host.so nphh_call_methylation_flat (nph::call_methylation_flat: page-locked host buffers in, TSV bytes out"
+                              + ("; TSV bytes gathered to rank 0 over NCCL)" if world > 1 else ")")},
+               "gpu_launches": launches * steps,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "peak_source": peak_src, "kernel": "hmm_forward_kernel<C,4..32> over the enumerated windows", "kernel_ms": kernel_ms,
+                            "algorithmic_bytes_per_step": int(b_alg),
+                            "note": "kernel_ms = the forward kernels alone (CUDA events around them); the step also holds the enumeration, the "
+                                    "schedule and two small read-backs, see ms_per_step"}}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = call_methylation_cpu(rs, recs, ref, pairs, site_off, sites, tsv[:tsv_bytes].tobytes().decode())
+            except Exception as ex:
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "kind": "unavailable", "sample": f"failed: {ex}"}
+    eng.close()
+    return out
+
+
+def call_methylation_cpu(rs, recs, ref, pairs, site_off, sites, tsv_ours):
+    """The compiled reference's own calculate_methylation_for_read + write_methylation_results_as_tsv over a bounded sample of the
+    same reads, one read per thread like the reference's OpenMP loop; its rows must equal ours for those reads."""
+    from concurrent.futures import ThreadPoolExecutor
+    from nanopolish_b200 import synth
+    from oracle.oracle_py import RefOracle
+    if not RefOracle.available():
+        raise RuntimeError("oracle/_ref/libnpref.so not present")
+    ro = RefOracle()
+    cores = cpu_threads()
+    ns = int(min(rs.n_reads, max(4 * cores, 128)))
+    mh = ro.builtin_model("nucleotide"); ro.builtin_model("cpg")
+    rh = ro.register_reads(rs.reads[:ns], rs.ev_mean, rs.ev_start_time, mh)
+    k = rs.k
+    inputs = []
+    for i in range(ns):
+        codes = rs.seq_codes[i]
+        nk = codes.shape[0] - k + 1
+        st, sp, _ = synth.closest_event_map(rs.ev_kmer[i], nk)
+        seq = synth._CODE2DNA[codes].tobytes().decode()
+        one = np.ones(int(rs.reads[i]["n_events"]), np.float32)
+        ro.read_set_eventalign(rh[i], f"read_0_{i}", seq, st, sp, one, one)
+        R = recs[i]
+        contig = "A" * int(R["ref_start_pos"]) + ref[int(R["ref_off"]):int(R["ref_off"]) + int(R["ref_len"])].tobytes().decode()
+        inputs.append((contig, int(R["ref_start_pos"]), 16 if R["rc"] else 0, np.array([(len(seq) << 4) | 0], np.uint32)))
+    def one_read(i):
+        c = inputs[i]
+        return ro.call_methylation(rh[i], f"read_0_{i}", "chr1", c[0], c[1], c[2], c[3])[0]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:                  # the compiled reference releases the GIL inside each call
+        rows = list(ex.map(one_read, range(ns)))
+    secs = time.perf_counter() - t0
+    # same rows as ours for these reads
+    ours = tsv_ours.split("\n")
+    cut = int(site_off[ns])
+    assert "".join(rows) == "".join(x + "\n" for x in ours[:cut]), "reference TSV differs from ours on the sampled reads"
+    # scored events of the sample: both jobs of a site walk the events between the two lower_bounds of its window
+    ev = 0
+    for i in range(ns):
+        R = recs[i]
+        pr = pairs[int(R["pair_off"]):int(R["pair_off"]) + int(R["n_pairs"])]
+        s_ = sites[int(site_off[i]):int(site_off[i + 1])]
+        a = np.searchsorted(pr["ref_pos"], s_["start_position"] - 10)
+        b = np.searchsorted(pr["ref_pos"], s_["end_position"] + 10)
+        ev += int((2 * (np.abs(pr["read_pos"][b].astype(np.int64) - pr["read_pos"][a].astype(np.int64)) + 1)).sum())
+    return {"value": ev / secs, "unit": UNIT, "cores": cores, "cpu_quota": cpu_quota(), "kind": "reference", "seconds": secs, "sample_sites": cut,
+            "sample": f"{ns} of the reads through the compiled reference's calculate_methylation_for_read + TSV writer, one read per thread "
+                      f"({cores} threads), {cut} sites, rows identical to ours"}
 
 
 def run_aux(args, rank, world, local, saved_stdout):
@@ -475,6 +694,23 @@ def main():
     if args.workload in ("abea", "events", "prologue", "eventalign"):
         run_aux(args, rank, world, local, saved_stdout)
         return
+    if args.workload == "call_methylation" and args.impl != "reference":
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        if world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        blk = call_methylation_block(args, rank, world, local, args.steps, args.warmup)
+        if rank == 0:
+            blk.update({"higher_is_better": True, "vs_baseline": None, "clocks": sampler.stop()})
+            emit(blk, saved_stdout)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
     if args.impl == "reference":
         run_reference(args, rank, world, saved_stdout)
         return
@@ -638,11 +874,21 @@ def main():
             except Exception as ex:   # the baseline is a reported extra; never lose the GPU line over it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable",
                                         "sample": f"failed: {ex}"}
+    eng.close()
+    # ---- the caller BASELINE.json's metric is named after, end to end, in the same line ----
+    cm = None
+    if not args.no_call_methylation:
+        try:
+            cm = call_methylation_block(args, rank, world, local, max(3, min(args.steps, 10)), args.warmup)
+        except Exception as ex:          # never lose the headline line over the extra block
+            cm = {"error": f"{type(ex).__name__}: {ex}"} if rank == 0 else None
+    if rank == 0:
+        if cm is not None:
+            line["configs"] = {"call_methylation": cm}
         emit(line, saved_stdout)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    eng.close()
 
 
 if __name__ == "__main__":

@@ -368,6 +368,10 @@ int nph_methylation_run(nph_ctx* ctx);
 /* counts of the most recent nph_methylation_run: scored groups, forward jobs (2 per group), scored events */
 int nph_methylation_counts(nph_ctx* ctx, uint64_t* n_sites_out, uint64_t* n_jobs_out, uint64_t* n_scored_events_out);
 int nph_methylation_fetch(nph_ctx* ctx, uint64_t* site_off_out, nph_meth_site* sites_out, size_t sites_cap);
+/* The site records of the most recent nph_methylation_run where they lie in device memory (valid until the next call on
+ * this context; ordered behind the run on the context's stream), for a caller that ships them GPU to GPU — a multi-GPU
+ * driver gathering every rank's records with NCCL — without a host hop. */
+int nph_methylation_sites_dev(nph_ctx* ctx, const nph_meth_site** sites_dev_out, uint64_t* n_sites_out);
 
 /* ---- event detection (section 8f N4: the step before ABEA) --------------------------------------
  * scrappie's detect_events as load_from_raw calls it: t-statistics over two windows on prefix sums, a short/long

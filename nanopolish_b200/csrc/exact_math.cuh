@@ -47,7 +47,11 @@ __device__ __forceinline__ float lsum(float a, float b, const LogsumTable tb)
     const float d = __fsub_rn(a, b);
     const float t = fminf(__fmul_rn(fabsf(d), 1000.0f), (float)NPH_LOGSUM_CUT);
     const float u = __fadd_rd(t, 8388608.0f);
+#ifdef NPH_LSUM_LEA
+    const uint32_t adr = (uint32_t)__float_as_int(u) * 4u + tb.biased_base;          // A/B: literal 4 -> LEA on the ALU pipe
+#else
     const uint32_t adr = (uint32_t)__float_as_int(u) * tb.scale + tb.biased_base;
+#endif
     float v;
     asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(adr));
     return __fadd_rn(mx, v);
@@ -98,8 +102,13 @@ __device__ __forceinline__ f32x2 lsum2(f32x2 a, f32x2 b, const LogsumTable tb)
     const f32x2 t = mul2(sub2(a, b), bc2(1000.0f));
     const f32x2 tc = pk2(fminf(fabsf(lo2(t)), (float)NPH_LOGSUM_CUT), fminf(fabsf(hi2(t)), (float)NPH_LOGSUM_CUT));
     const f32x2 u = add2_rd(tc, bc2(8388608.0f));
+#ifdef NPH_LSUM_LEA
+    const uint32_t a0 = (uint32_t)__float_as_int(lo2(u)) * 4u + tb.biased_base;
+    const uint32_t a1 = (uint32_t)__float_as_int(hi2(u)) * 4u + tb.biased_base;
+#else
     const uint32_t a0 = (uint32_t)__float_as_int(lo2(u)) * tb.scale + tb.biased_base;
     const uint32_t a1 = (uint32_t)__float_as_int(hi2(u)) * tb.scale + tb.biased_base;
+#endif
     float v0, v1;
     asm("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(a0));
     asm("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(a1));

@@ -37,7 +37,10 @@ NPH_HD uint32_t nph_class_steps(uint32_t K, uint32_t E, int C, uint32_t W)
 
 // per-step issue slots: ~96 of per-step work plus the row update — 88 per column in the scalar form (odd C), ~66 where the
 // columns are paired onto packed FP32 instructions (even C; SASS counts in DESIGN.md section 3.4)
-NPH_HD float nph_class_cost(uint32_t steps, int C, uint32_t W) { return (float)steps * (96.0f + ((C & 1) ? 88.0f : 66.0f) * C) * (W * (1.0f / 32.0f)); }
+#ifndef NPH_EVEN_CELL_COST
+#define NPH_EVEN_CELL_COST 66.0f
+#endif
+NPH_HD float nph_class_cost(uint32_t steps, int C, uint32_t W) { return (float)steps * (96.0f + ((C & 1) ? 88.0f : NPH_EVEN_CELL_COST) * C) * (W * (1.0f / 32.0f)); }
 
 // returns class index; *steps_out = steps in that class
 NPH_HD int nph_choose_class(uint32_t K, uint32_t E, uint32_t* steps_out)

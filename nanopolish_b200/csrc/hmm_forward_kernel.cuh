@@ -28,6 +28,36 @@
 
 namespace nph_fwd {
 
+// the pair operations of the row update, packed or per half according to the knobs above (same values either way)
+__device__ __forceinline__ f32x2 P_lsum2(f32x2 a, f32x2 b, const LogsumTable tb)
+{
+#if NPH_PACKED_LSUM
+    return lsum2(a, b, tb);
+#else
+    return pk2(lsum(lo2(a), lo2(b), tb), lsum(hi2(a), hi2(b), tb));
+#endif
+}
+__device__ __forceinline__ f32x2 P_add2(f32x2 a, f32x2 b)
+{
+#if NPH_PACKED_ARITH
+    return add2(a, b);
+#else
+    return pk2(__fadd_rn(lo2(a), lo2(b)), __fadd_rn(hi2(a), hi2(b)));
+#endif
+}
+// Gaussian log-density of a pair: cc + (-0.5 * z) * z with z = (x - mu) / sigma (emissions.h:51-55); nz2 = packed -0.0 (see the kernel)
+__device__ __forceinline__ f32x2 P_emission(f32x2 x2, f32x2 mu2, f32x2 nsd2, f32x2 cc2, f32x2 ry2, f32x2 nz2)
+{
+#if NPH_PACKED_ARITH
+    const f32x2 a = div2_by_cached_rcp(sub2(x2, mu2), nsd2, ry2);
+    return add2(cc2, fma2(mul2(bc2(-0.5f), a), a, nz2));
+#else
+    const float a0 = div_by_cached_rcp(__fsub_rn(lo2(x2), lo2(mu2)), -lo2(nsd2), lo2(ry2));
+    const float a1 = div_by_cached_rcp(__fsub_rn(hi2(x2), hi2(mu2)), -hi2(nsd2), hi2(ry2));
+    return pk2(__fadd_rn(lo2(cc2), __fmul_rn(__fmul_rn(-0.5f, a0), a0)), __fadd_rn(hi2(cc2), __fmul_rn(__fmul_rn(-0.5f, a1), a1)));
+#endif
+}
+
 constexpr int kWarpsPerCta = 16;
 constexpr int kCtaThreads = kWarpsPerCta * 32;
 constexpr unsigned kFull = 0xffffffffu;
@@ -60,6 +90,13 @@ struct FwdParams {
 
 #ifndef NPH_PACKED_F32X2
 #define NPH_PACKED_F32X2 1          // 0: scalar inner loop for every C (the round-1 kernel; kept for A/B measurements)
+#endif
+// A/B knobs of the paired row update (measurements in profiles/r02_k1_variants.md): which parts use packed instructions
+#ifndef NPH_PACKED_LSUM
+#define NPH_PACKED_LSUM 1           // 0: the log-sums of a pair as two scalar lsum
+#endif
+#ifndef NPH_PACKED_ARITH
+#define NPH_PACKED_ARITH 1          // 0: transition adds and the Gaussian as scalar instructions on the halves
 #endif
 
 // CHAIN = false: every job of the class fits one strip (K <= W*C), all strip/edge bookkeeping compiles away.
@@ -245,29 +282,28 @@ __global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdPa
 #pragma unroll
                     for (int q = 0; q < H; ++q) {
                         // Gaussian log-density of both columns, reference operation order (emissions.h:51-55)
-                        const f32x2 a = div2_by_cached_rcp(sub2(x2, mu2[q]), nsd2[q], ry2[q]);
-                        const f32x2 em = add2(cc2[q], fma2(mul2(bc2(-0.5f), a), a, nz2));
+                        const f32x2 em = P_emission(x2, mu2[q], nsd2[q], cc2[q], ry2[q], nz2);
                         // left column, previous row: pair q-1 as it stands; at the lane boundary the neighbour's value and column H-1
                         const f32x2 sM = q ? Mp2[q > 0 ? q - 1 : 0] : pk2(Lm_prev, lo2(Mp2[H - 1]));
                         const f32x2 sB = q ? Bp2[q > 0 ? q - 1 : 0] : pk2(Lb_prev, lo2(Bp2[H - 1]));
                         const f32x2 sK = q ? Kp2[q > 0 ? q - 1 : 0] : pk2(Lk_prev, lo2(Kp2[H - 1]));
                         // match: left fold over {same M, prev M, same B, prev B, prev K, soft}
-                        f32x2 m = add2(bc2(lp_mm_self), Mp2[q]);
-                        m = lsum2(m, add2(bc2(lp_mm_next), sM), tb);
-                        m = lsum2(m, add2(bc2(lp_bm_self), Bp2[q]), tb);
-                        m = lsum2(m, add2(bc2(lp_bm_next), sB), tb);
-                        m = lsum2(m, add2(bc2(lp_km), sK), tb);
+                        f32x2 m = P_add2(bc2(lp_mm_self), Mp2[q]);
+                        m = P_lsum2(m, P_add2(bc2(lp_mm_next), sM), tb);
+                        m = P_lsum2(m, P_add2(bc2(lp_bm_self), Bp2[q]), tb);
+                        m = P_lsum2(m, P_add2(bc2(lp_bm_next), sB), tb);
+                        m = P_lsum2(m, P_add2(bc2(lp_km), sK), tb);
                         if (q == 0) m = pk2(lsum(lo2(m), soft, tb), hi2(m));       // column 0 of the lane only
-                        mN[q] = add2(m, em);
+                        mN[q] = P_add2(m, em);
                         // bad event: {same M, same B}
-                        bN[q] = lsum2(add2(bc2(lp_mb), Mp2[q]), add2(bc2(lp_bb), Bp2[q]), tb);
+                        bN[q] = P_lsum2(P_add2(bc2(lp_mb), Mp2[q]), P_add2(bc2(lp_bb), Bp2[q]), tb);
                     }
 #pragma unroll
                     for (int q = 0; q < H; ++q) {
                         // k-mer skip, the part that does not depend on the chain: {prev M, prev B} of the SAME row
                         const f32x2 cM = q ? mN[q > 0 ? q - 1 : 0] : pk2(Lm, lo2(mN[H - 1]));
                         const f32x2 cB = q ? bN[q > 0 ? q - 1 : 0] : pk2(Lb, lo2(bN[H - 1]));
-                        xk[q] = lsum2(add2(bc2(lp_mk), cM), add2(bc2(lp_bk), cB), tb);
+                        xk[q] = P_lsum2(P_add2(bc2(lp_mk), cM), P_add2(bc2(lp_bk), cB), tb);
                     }
                     // the chain K[c] = x[c] (+) (lp_kk + K[c-1]) runs through the columns in order: lo halves, then hi halves
                     float kn[C];

@@ -472,6 +472,15 @@ extern "C" int nph_methylation_counts(nph_ctx* ctx, uint64_t* n_sites_out, uint6
     return NPH_OK;
 }
 
+extern "C" int nph_methylation_sites_dev(nph_ctx* ctx, const nph_meth_site** sites_dev_out, uint64_t* n_sites_out)
+{
+    if (!ctx || !sites_dev_out || !n_sites_out) return NPH_ERR_INVALID;
+    if (!ctx->meth.ran) return NPH_ERR_STATE;
+    *sites_dev_out = ctx->meth.n_sites ? ctx->meth.d_sites.p : nullptr;
+    *n_sites_out = ctx->meth.n_sites;
+    return NPH_OK;
+}
+
 extern "C" int nph_methylation_fetch(nph_ctx* ctx, uint64_t* site_off_out, nph_meth_site* sites_out, size_t sites_cap)
 {
     if (!ctx || !site_off_out) return NPH_ERR_INVALID;

@@ -81,6 +81,12 @@ class Engine:
         self._check(self.lib.nph_methylation_counts(self.ctx, C.byref(a), C.byref(b), C.byref(c)), "nph_methylation_counts")
         return int(a.value), int(b.value), int(c.value)
 
+    def methylation_sites_dev(self):
+        """(device pointer, n_sites) of the last run's site records (nph_methylation_sites_dev)"""
+        ptr, n = C.c_void_p(), C.c_uint64()
+        self._check(self.lib.nph_methylation_sites_dev(self.ctx, C.byref(ptr), C.byref(n)), "nph_methylation_sites_dev")
+        return int(ptr.value or 0), int(n.value)
+
     def methylation_fetch(self, out=None):
         n_sites = self.methylation_counts()[0]
         site_off, sites = out if out is not None else (np.zeros(self._meth_n + 1, np.uint64), np.zeros(max(n_sites, 1), METH_SITE_DT))

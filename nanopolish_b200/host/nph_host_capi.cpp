@@ -252,6 +252,43 @@ int nphh_score_variants_thresholded(int n_reads, const int32_t* read, const uint
     });
 }
 
+// score_variant_group over reads and a variant group: combos_out[c] = bitmask of the variant ids of combination c,
+// scores_out[c * n_reads + r]; returns the number of combinations (or a negative status)
+long long nphh_score_variant_group(int n_reads, const int32_t* read, const uint32_t* e_start, const uint32_t* e_stop, const uint8_t* rc,
+                                   int model, const char* base_seq, size_t ref_position, int n_var, const size_t* pos,
+                                   const char** ref_seq, const char** alt_seq, int max_haplotypes, uint32_t flags,
+                                   int n_meth, const char** meth_types, double indel_bias, uint32_t* combos_out, double* scores_out, size_t cap_comb)
+{
+    long long n = -1;
+    int st = guard([&] {
+        std::vector<HMMInputData> input(n_reads);
+        for (int j = 0; j < n_reads; ++j) {
+            input[j].read = g_reads[read[j]].get();
+            input[j].pore_model = g_models[model].get();
+            input[j].event_start_idx = e_start[j];
+            input[j].event_stop_idx = e_stop[j];
+            input[j].strand = 0;
+            input[j].rc = rc[j];
+            input[j].event_stride = rc[j] ? -1 : 1;
+        }
+        std::vector<Variant> vars(n_var);
+        for (int i = 0; i < n_var; ++i) { vars[i].ref_name = "ctg"; vars[i].ref_position = pos[i]; vars[i].ref_seq = ref_seq[i]; vars[i].alt_seq = alt_seq[i]; }
+        std::vector<std::string> mt;
+        for (int i = 0; i < n_meth; ++i) mt.push_back(meth_types[i]);
+        Haplotype base("ctg", ref_position, base_seq);
+        const VariantGroupScores g = score_variant_group(vars, base, input, max_haplotypes, flags, mt, Engine::thread_default(), indel_bias);
+        if (g.combinations.size() > cap_comb) throw Error(NPH_ERR_INVALID, "combination buffer too small");
+        for (size_t c = 0; c < g.combinations.size(); ++c) {
+            uint32_t mask = 0;
+            for (size_t id : g.combinations[c]) mask |= 1u << id;
+            combos_out[c] = mask;
+            for (int r = 0; r < n_reads; ++r) scores_out[c * (size_t)n_reads + r] = g.scores[c][r];
+        }
+        n = (long long)g.combinations.size();
+    });
+    return st ? st : n;
+}
+
 // ---- N3: call-methylation for a batch of reads; returns the concatenated TSV ------------------------------
 // aligned pairs are (ref_pos, event_idx) interleaved, pair_off[n_reads+1]
 static long long call_methylation_impl(int n_reads, const int32_t* read, const char** read_names, const uint8_t* is_rev, const uint8_t* rc,

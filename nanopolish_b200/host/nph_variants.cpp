@@ -110,6 +110,59 @@ std::vector<std::vector<double>> score_haplotypes(const std::vector<Haplotype>& 
     return out;
 }
 
+size_t nChoosek(size_t n, size_t k)
+{
+    if (k > n) return 0;
+    if (k * 2 > n) k = n - k;
+    if (k == 0) return 1;
+    int result = (int)n;                                       // the reference accumulates in an int
+    for (int i = 2; i <= (int)k; ++i) {
+        result *= (int)(n - i + 1);
+        result /= i;
+    }
+    return (size_t)result;
+}
+
+VariantGroupScores score_variant_group(const std::vector<Variant>& variants, const Haplotype& base_haplotype,
+                                       const std::vector<HMMInputData>& input, int max_haplotypes, uint32_t alignment_flags,
+                                       const std::vector<std::string>& methylation_types, Engine& engine, double indel_bias)
+{
+    const size_t num_variants = variants.size();
+    // the largest number of variants that can be tested jointly without exceeding max_haplotypes
+    size_t sum_num_haplotypes = 0, max_r = 1;
+    while (max_r <= num_variants) {
+        const size_t num_haplotypes_r = nChoosek(num_variants, max_r);
+        if (num_haplotypes_r + sum_num_haplotypes < (size_t)max_haplotypes) sum_num_haplotypes += num_haplotypes_r;
+        else break;
+        max_r += 1;
+    }
+    max_r -= 1;
+    VariantGroupScores out;
+    out.max_r = max_r;
+    std::vector<Haplotype> haplotypes;
+    for (size_t r = 0; r <= max_r; ++r) {
+        std::vector<size_t> idx(r);
+        for (size_t i = 0; i < r; ++i) idx[i] = i;
+        for (;;) {
+            Haplotype current = base_haplotype;
+            std::vector<Variant> subset;
+            for (size_t i : idx) subset.push_back(variants[i]);
+            if (current.apply_variants(subset)) { out.combinations.push_back(idx); haplotypes.push_back(current); }
+            // next r-subset of {0..n-1} in lexicographic order
+            int i = (int)r - 1;
+            while (i >= 0 && idx[i] == num_variants - r + (size_t)i) --i;
+            if (i < 0) break;
+            ++idx[i];
+            for (size_t j = (size_t)i + 1; j < r; ++j) idx[j] = idx[j - 1] + 1;
+        }
+    }
+    const std::vector<std::vector<double>> by_read = score_haplotypes(haplotypes, input, alignment_flags, methylation_types, engine, indel_bias);
+    out.scores.assign(haplotypes.size(), std::vector<double>(input.size()));
+    for (size_t ri = 0; ri < input.size(); ++ri)
+        for (size_t hi = 0; hi < haplotypes.size(); ++hi) out.scores[hi][ri] = by_read[ri][hi];
+    return out;
+}
+
 std::vector<Variant> score_variants_thresholded(const std::vector<Variant>& input_variants, const Haplotype& base_haplotype,
                                                 const std::vector<HMMInputData>& input, uint32_t alignment_flags,
                                                 uint32_t score_threshold, const std::vector<std::string>& methylation_types,

@@ -58,6 +58,23 @@ std::vector<std::vector<double>> score_haplotypes(const std::vector<Haplotype>& 
                                                   uint32_t alignment_flags, const std::vector<std::string>& methylation_types,
                                                   Engine& engine, double indel_bias = hmm_indel_bias_factor);
 
+// score_variant_group (ref: src/common/nanopolish_variant.cpp:182-262): every combination of up to max_r of the group's variants
+// (max_r = the largest r for which the haplotype count stays below max_haplotypes, :193-206) that applies cleanly to the base
+// haplotype — r = 0, the base haplotype, included — scored against every read with profile_hmm_score_set, all as ONE batch.
+// combinations[c] lists the variant ids of combination c (ascending ids, combinations of size r in lexicographic order; the
+// reference's Combinations generator visits the same sets in a different order), scores[c][read] is what
+// VariantGroup::set_combination_read_score receives.
+struct VariantGroupScores {
+    std::vector<std::vector<size_t>> combinations;
+    std::vector<std::vector<double>> scores;
+    size_t max_r = 0;
+};
+size_t nChoosek(size_t n, size_t k);                           // ref: src/common/nanopolish_common.cpp:93-105 (int arithmetic inside)
+VariantGroupScores score_variant_group(const std::vector<Variant>& variants, const Haplotype& base_haplotype,
+                                       const std::vector<HMMInputData>& input, int max_haplotypes, uint32_t alignment_flags,
+                                       const std::vector<std::string>& methylation_types, Engine& engine,
+                                       double indel_bias = hmm_indel_bias_factor);
+
 // score_variant_thresholded for a whole candidate list: quality_i = sum over reads, in input order, of
 // (variant_score - base_score), where a read is skipped once |running total| >= score_threshold — exactly the
 // single-thread behaviour of the reference loop (its OpenMP version makes the skip set racy; the result here is

@@ -289,6 +289,17 @@ class RefOracle:
             raise RuntimeError("npref_call_methylation: output buffer too small")
         return tsv.value.decode(), sites[:n].copy(), ll[:n].copy()
 
+    def calibrate(self, read_h, model_h, read_sequence: bytes, pairs):
+        """The tail of load_from_raw after ABEA (base-to-event map, get_eventalignment_for_1d_basecalls, recalibrate_model):
+        dict(shift, scale, drift, var, events_per_base, calibrated, n_used) or None for an empty alignment."""
+        pr = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        out = np.zeros(6)
+        self.lib.npref_calibrate.restype = C.c_longlong
+        n = self.lib.npref_calibrate(int(read_h), int(model_h), read_sequence, _p(pr), C.c_size_t(pr.shape[0]), _p(out))
+        if n < 0:
+            return None
+        return dict(shift=out[0], scale=out[1], drift=out[2], var=out[3], events_per_base=out[4], calibrated=bool(out[5]), n_used=int(n))
+
     def score_variants_thresholded(self, read_handles, windows, rc, ref_seq: str, ref_position, variants, flags, threshold,
                                    methylation: bool, indel_bias=1.0):
         """[score_variant_thresholded(v, Haplotype(ref), reads, flags, threshold, types).quality for v in variants], single thread"""
@@ -302,6 +313,24 @@ class RefOracle:
         self.lib.npref_score_variants_thresholded(n, _p(rh), _p(es), _p(ee), _p(rcs), ref_seq.encode(), C.c_size_t(ref_position), nv, pos, refs,
                                                   alts, C.c_uint32(flags), C.c_uint32(threshold), int(methylation), C.c_double(indel_bias), _p(q))
         return q
+
+    def score_variant_group(self, read_handles, windows, rc, ref_seq: str, ref_position, variants, max_haplotypes, flags, methylation=False,
+                            indel_bias=1.0):
+        """score_variant_group: dict {frozenset of variant ids: float64[n_reads] scores}; variants = [(pos, ref, alt)]."""
+        n = len(read_handles); nv = len(variants)
+        rh = np.ascontiguousarray(read_handles, np.int32)
+        es = np.array([w[0] for w in windows], np.uint32); ee = np.array([w[1] for w in windows], np.uint32)
+        rcs = np.ascontiguousarray(rc, np.uint8)
+        cap = 1 << 12
+        combos = np.zeros(cap, np.uint32); scores = np.zeros(cap * n, np.float64)
+        self.lib.npref_score_variant_group.restype = C.c_longlong
+        k = self.lib.npref_score_variant_group(n, _p(rh), _p(es), _p(ee), _p(rcs), ref_seq.encode(), C.c_size_t(ref_position), nv,
+                                               (C.c_size_t * nv)(*[v[0] for v in variants]), (C.c_char_p * nv)(*[v[1].encode() for v in variants]),
+                                               (C.c_char_p * nv)(*[v[2].encode() for v in variants]), int(max_haplotypes), int(flags),
+                                               1 if methylation else 0, C.c_double(indel_bias), _p(combos), _p(scores), C.c_size_t(cap))
+        if k < 0:
+            raise RuntimeError("npref_score_variant_group: buffer too small")
+        return {frozenset(i for i in range(nv) if combos[c] >> i & 1): scores[c * n:(c + 1) * n].copy() for c in range(k)}
 
     def modbam(self, seq: str, ref_pos, flag, cigar, calls):
         """create_modbam_record's Mm / Ml tags; calls = [(start_position, site sequence, ll_methylated[0], ll_unmethylated[0])]."""

@@ -17,7 +17,9 @@
 #include <cstdint>
 #include <cstring>
 #include <cmath>
+#include <limits>
 #include <memory>
+#include <sstream>
 #include <string>
 #include <vector>
 #include <chrono>
@@ -36,6 +38,8 @@
 #include "nanopolish_basemods.h"     // create_modbam_record (the Mm / Ml tags of call-methylation --modbam-output)
 #include "nanopolish_variant.h"      // score_variant_thresholded (8f N2)
 #include "nanopolish_haplotype.h"
+#include "nanopolish_variant_db.h"   // VariantGroup / Combinations (score_variant_group, 8f N2)
+#include "nanopolish_methyltrain.h"  // recalibrate_model (8f N4: the calibration after ABEA); its Eigen solve comes from oracle/shim/Eigen/Dense
 extern "C" {
 #include "event_detection.h"   // src/thirdparty/scrappie (C99)
 }
@@ -614,6 +618,102 @@ long long npref_call_methylation(int read_h, const char* read_name, const char* 
     }
     free(buf);
     return ok ? (long long)sites.size() : -1;
+}
+
+// ---- calibration after ABEA: the tail of SquiggleRead::load_from_raw (src/nanopolish_squiggle_read.cpp:272-336) ----
+// load_from_raw itself needs fast5/slow5 input and cannot be called; what it does with the ABEA result is (a) the
+// base-to-event map loop (:272-300), transcribed below because it is inline in that function, (b) the reference's own
+// SquiggleRead::get_eventalignment_for_1d_basecalls (:340-391) and (c) the reference's own recalibrate_model
+// (src/nanopolish_methyltrain.cpp:204-307), both compiled unmodified — recalibrate_model's FullPivLU solve through the
+// restated header oracle/shim/Eigen/Dense (Eigen is not vendored and absent here).
+// pairs = (k-mer, event) AlignedPairs as adaptive_banded_simple_event_align returns them.  out6 = shift, scale, drift, var,
+// events_per_base, calibrated (0/1); returns the number of 'M' events, or -1 for an empty alignment.
+long long npref_calibrate(int read_h, int model_h, const char* read_sequence, const int32_t* pairs, size_t n_pairs, double* out6)
+{
+    SquiggleRead& sr = *g_reads[read_h];
+    const PoreModel& model = *g_models[model_h];
+    const size_t strand_idx = 0;
+    sr.read_sequence = read_sequence;
+    if(n_pairs == 0) return -1;
+    const size_t n_kmers = sr.read_sequence.size() - model.k + 1;
+    sr.base_to_event_map.clear();
+    sr.base_to_event_map.resize(n_kmers);
+    size_t max_event = 0;
+    size_t min_event = std::numeric_limits<size_t>::max();
+    size_t prev_event_idx = -1;
+    for(size_t i = 0; i < n_pairs; ++i) {
+        size_t k_idx = pairs[2 * i];
+        size_t event_idx = pairs[2 * i + 1];
+        IndexPair& elem = sr.base_to_event_map[k_idx].indices[strand_idx];
+        if(event_idx != prev_event_idx) {
+            if(elem.start == -1) elem.start = event_idx;
+            elem.stop = event_idx;
+        }
+        max_event = std::max(max_event, event_idx);
+        min_event = std::min(min_event, event_idx);
+        prev_event_idx = event_idx;
+    }
+    const double events_per_base = (double)(max_event - min_event) / n_kmers;
+    std::vector<EventAlignment> alignment =
+        sr.get_eventalignment_for_1d_basecalls(sr.read_sequence, "nucleotide", sr.base_to_event_map, model.k, strand_idx, 0);
+    long long n_m = 0;
+    for(const EventAlignment& ea : alignment) n_m += ea.hmm_state == 'M';
+    const bool calibrated = recalibrate_model(sr, model, strand_idx, alignment, true, false);
+    const SquiggleScalings& s = sr.scalings[strand_idx];
+    out6[0] = s.shift; out6[1] = s.scale; out6[2] = s.drift; out6[3] = s.var; out6[4] = events_per_base; out6[5] = calibrated ? 1.0 : 0.0;
+    return n_m;
+}
+
+// ---- variants: score_variant_group (src/common/nanopolish_variant.cpp:182-262): every combination of up to max_r of the group's
+// variants applied to the base haplotype, each scored against every read with profile_hmm_score_set.  combos_out[c] = bitmask of
+// the variant ids of combination c (c = VariantGroup's combination index), scores_out[c * n_reads + r] = its score for read r.
+// Returns the number of combinations (-1: cap_comb too small).
+long long npref_score_variant_group(int n_reads, const int32_t* read_h, const uint32_t* e_start, const uint32_t* e_stop, const uint8_t* rc,
+                                    const char* ref_seq, size_t ref_position, int n_var, const size_t* var_pos, const char** var_ref,
+                                    const char** var_alt, int max_haplotypes, uint32_t alignment_flags, int methylation, double indel_bias,
+                                    uint32_t* combos_out, double* scores_out, size_t cap_comb)
+{
+    const double saved_bias = hmm_indel_bias_factor;
+    hmm_indel_bias_factor = indel_bias;
+    std::vector<HMMInputData> input(n_reads);
+    for(int j = 0; j < n_reads; ++j) {
+        HMMInputData& d = input[j];
+        d.read = g_reads[read_h[j]].get();
+        d.read->read_name = "r" + std::to_string(read_h[j]);       // read ids of the group's score table must be distinct
+        d.pore_model = d.read->get_base_model(0);
+        d.strand = 0;
+        d.event_start_idx = e_start[j];
+        d.event_stop_idx = e_stop[j];
+        d.rc = rc[j];
+        d.event_stride = d.event_start_idx <= d.event_stop_idx ? 1 : -1;
+    }
+    std::vector<std::string> methylation_types;
+    if(methylation) methylation_types.push_back("cpg");
+    std::vector<Variant> vars(n_var);
+    for(int v = 0; v < n_var; ++v) {
+        vars[v].ref_name = "contig"; vars[v].ref_position = var_pos[v]; vars[v].ref_seq = var_ref[v]; vars[v].alt_seq = var_alt[v];
+        vars[v].quality = 0.0;
+    }
+    VariantGroup group(0, vars);
+    Haplotype base("contig", ref_position, ref_seq);
+    score_variant_group(group, base, input, max_haplotypes, 1, false, alignment_flags, methylation_types);
+    hmm_indel_bias_factor = saved_bias;
+    const size_t nc = group.get_num_combinations();
+    if(nc > cap_comb) return -1;
+    for(size_t c = 0; c < nc; ++c) {
+        const VariantCombination& vc = group.get_combination(c);
+        uint32_t mask = 0;
+        for(size_t i = 0; i < vc.get_num_variants(); ++i) mask |= 1u << vc.get_variant_id(i);
+        combos_out[c] = mask;
+        for(int r = 0; r < n_reads; ++r)
+        {
+            // the read id score_variant_group forms (:236-238): operator<< of the uint8_t strand writes the CHARACTER with that code
+            std::stringstream ss;
+            ss << input[r].read->read_name << ":" << input[r].strand;
+            scores_out[c * (size_t)n_reads + r] = group.get_combination_read_score(c, ss.str());
+        }
+    }
+    return (long long)nc;
 }
 
 } // extern "C"

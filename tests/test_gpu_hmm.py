@@ -49,35 +49,10 @@ def test_golden_cases(engine, models, port_oracle, name):
     _check(got, want)
 
 
-def _random_jobs(rs, rng, n_jobs, kmin, kmax, emin, emax, flags_choices, model_id=0):
-    rows, ranks = [], []
-    for _ in range(n_jobs):
-        r = int(rng.integers(0, rs.n_reads))
-        E = int(rs.reads[r]["n_events"])
-        nk_all = rs.seq_codes[r].shape[0] - rs.k + 1
-        K = int(rng.integers(kmin, min(kmax, nk_all) + 1))
-        k0 = int(rng.integers(0, nk_all - K + 1))
-        ne = int(rng.integers(emin, min(emax, E) + 1))
-        e0 = int(rng.integers(0, E - ne + 1))
-        e1 = e0 + ne - 1
-        sub = rs.seq_codes[r][k0:k0 + K + rs.k - 1]
-        rc = int(rng.integers(0, 2)) if ne > 1 else 0
-        fl = int(rng.choice(flags_choices))
-        if rc:
-            rcsub = (3 - sub[::-1]).astype(np.uint8)
-            ranks.append(synth.dna_rc_kmer_ranks(rcsub, rs.k)); rows.append((r, model_id, e1, e0, 1, fl))
-        else:
-            ranks.append(synth.kmer_ranks_from_codes(sub, rs.k, 4)); rows.append((r, model_id, e0, e1, 0, fl))
-    return synth._finish_jobs(rows, ranks)
+from tests.random_cases import HMM_SHAPES, random_hmm_jobs as _random_jobs
 
 
-@pytest.mark.parametrize("shape", [
-    dict(kmin=1, kmax=40, emin=1, emax=60, n=400),       # tiny, includes K=1 and E=1
-    dict(kmin=16, kmax=220, emin=11, emax=400, n=300),   # call-methylation window range
-    dict(kmin=250, kmax=330, emin=450, emax=520, n=40),  # scorereads segments
-    dict(kmin=600, kmax=1100, emin=20, emax=45, n=30),   # many strips, fewer rows than the chain period
-    dict(kmin=900, kmax=1400, emin=700, emax=1200, n=12) # wide and tall
-])
+@pytest.mark.parametrize("shape", HMM_SHAPES)
 def test_random_shapes_bit_exact(engine, models, port_oracle, shape):
     nuc = models["nucleotide"][0]
     rs = synth.gen_reads(8, 2600, nuc, seed=900 + shape["kmin"], drift=True)

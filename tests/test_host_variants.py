@@ -134,3 +134,45 @@ def test_score_variants_thresholded(host, port_oracle, meth, threshold):
     assert list(q) == want, (list(q), want)
     # the true sequence wins: every applicable candidate lowers the likelihood
     assert (q[:-1] < 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("meth,max_haplotypes", [(False, 1000), (True, 8)])
+def test_score_variant_group_equals_compiled_reference(host, ref_oracle, meth, max_haplotypes):
+    """nph::score_variant_group (haplotype enumeration + score_haplotypes: ONE launch for every (read, haplotype, alphabet
+    alternative)) against the compiled reference's score_variant_group (src/common/nanopolish_variant.cpp:182-262): the same set
+    of variant combinations survives (max_r from max_haplotypes, incompatible combinations dropped) and every
+    (combination, read) score is the same double."""
+    nuc, cpg, codes, ref, rs, cands = _variant_case()
+    cands = cands[:4] + [(1000 + 20, "C", "A")]                 # the last one collides with candidate 1 (same reference base)
+    mh, ch = _register(host, nuc), _register(host, cpg)
+    rh = _register_reads(host, rs, mh)
+    for r in rh:
+        host.nphh_read_add_model(r, b"cpg", ch)
+    windows = [(0, int(rs.reads[j]["n_events"]) - 1) for j in range(rs.n_reads)]
+    ref_oracle.clear_reads()
+    rrh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, ref_oracle.builtin_model("nucleotide"))
+    want = ref_oracle.score_variant_group(rrh, windows, np.zeros(rs.n_reads, np.uint8), ref, 1000, cands, max_haplotypes, 3, meth, indel_bias=0.9)
+    ref_oracle.clear_reads()
+    n = len(cands)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    reads = np.array(rh, np.int32)
+    es = np.array([w[0] for w in windows], np.uint32); ee = np.array([w[1] for w in windows], np.uint32)
+    rcs = np.zeros(rs.n_reads, np.uint8)
+    mt = (C.c_char_p * 1)(b"cpg")
+    combos = np.zeros(4096, np.uint32); scores = np.zeros(4096 * rs.n_reads)
+    host.nphh_score_variant_group.restype = C.c_longlong
+    k = host.nphh_score_variant_group(rs.n_reads, p(reads), p(es), p(ee), p(rcs), mh, ref.encode(), C.c_size_t(1000), n,
+                                      (C.c_size_t * n)(*[c[0] for c in cands]), (C.c_char_p * n)(*[c[1].encode() for c in cands]),
+                                      (C.c_char_p * n)(*[c[2].encode() for c in cands]), max_haplotypes, 3, 1 if meth else 0, mt,
+                                      C.c_double(0.9), p(combos), p(scores), C.c_size_t(4096))
+    assert k >= 0, host.nphh_last_error()
+    got = {frozenset(i for i in range(n) if combos[c] >> i & 1): scores[c * rs.n_reads:(c + 1) * rs.n_reads] for c in range(k)}
+    assert set(got) == set(want) and frozenset() in got
+    assert frozenset({1, 4}) not in got                          # both rewrite reference base 1020: the combination does not apply
+    if max_haplotypes == 8:
+        assert max(len(c) for c in got) == 1                     # 1 + 5 < 8 but 1 + 5 + 10 is not: single variants only
+    else:
+        assert max(len(c) for c in got) >= 4
+    for c in want:
+        assert np.array_equal(got[c], want[c]), sorted(c)

@@ -262,3 +262,109 @@ def test_call_methylation_restatement_pinned(port_oracle, ref_oracle):
     lo, hi = case["ref_pos"] + 400, case["ref_pos"] + 1100
     tsv_ref, sites_ref, _ = ref_oracle.call_methylation(rh[0], case["name"], "chr1", case["contig"], case["ref_pos"], case["flag"], case["cigar"], region=(lo, hi))
     assert 0 < sites_ref.shape[0] < 40 and (sites_ref[:, 0] >= lo).all() and (sites_ref[:, 1] < hi).all()
+
+
+def test_recalibrate_pinned_to_compiled_reference(port_oracle, ref_oracle):
+    """npo_recalibrate against the reference's own get_eventalignment_for_1d_basecalls + recalibrate_model
+    (src/nanopolish_squiggle_read.cpp:340-391, src/nanopolish_methyltrain.cpp:204-307, compiled unmodified into oracle/_ref):
+    identical doubles for shift, scale, var, events_per_base and the same 'M'-event count.  The one thing that is NOT the
+    reference's object code is Eigen's FullPivLU (un-vendored, absent here): recalibrate_model is compiled against
+    oracle/shim/Eigen/Dense, which restates the published algorithm; the sums that feed it and the residual variance that
+    follows are the reference's own loops."""
+    model = synth.load_model("nucleotide")
+    rs = synth.gen_reads(5, 1500, model, seed=31, rng_scalings=True)
+    jobs, ranks, total = synth.abea_jobs(rs)
+    pairs, res, _ = port_oracle.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, model, ranks, jobs, total)
+    ref_oracle.clear_reads()
+    mh = ref_oracle.builtin_model("nucleotide")
+    rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, mh)
+    for j in range(jobs.shape[0]):
+        n = int(res[j]["n_pairs"])
+        assert n > 0
+        _, cal = port_oracle.recalibrate(rs.reads, rs.ev_mean, model, ranks, jobs[j], pairs, n)
+        pr = pairs[int(jobs[j]["pairs_off"]):int(jobs[j]["pairs_off"]) + n]
+        seq = synth._CODE2DNA[rs.seq_codes[j]].tobytes()
+        want = ref_oracle.calibrate(rh[j], mh, seq, np.stack([pr["ref_pos"], pr["read_pos"]], 1))
+        assert want is not None and want["calibrated"] and want["n_used"] == int(cal["n_used"]) >= 200
+        for key in ("shift", "scale", "drift", "var", "events_per_base"):
+            assert np.float64(want[key]).view(np.uint64) == np.float64(cal[key]).view(np.uint64), key
+    # fewer than 200 'M' events: not recalibrated, scalings untouched
+    short = synth.gen_reads(1, 260, model, seed=5, rng_scalings=True)
+    jobs, ranks, total = synth.abea_jobs(short)
+    pairs, res, _ = port_oracle.abea_batch(short.reads, short.ev_mean, short.ev_start_time, model, ranks, jobs, total)
+    n = int(res[0]["n_pairs"])
+    if n:
+        ref_oracle.clear_reads()
+        rh = ref_oracle.register_reads(short.reads, short.ev_mean, short.ev_start_time, mh)
+        pr = pairs[:n]
+        want = ref_oracle.calibrate(rh[0], mh, synth._CODE2DNA[short.seq_codes[0]].tobytes(), np.stack([pr["ref_pos"], pr["read_pos"]], 1))
+        _, cal = port_oracle.recalibrate(short.reads, short.ev_mean, model, ranks, jobs[0], pairs, n)
+        assert not want["calibrated"] and int(cal["status"]) == 2 and want["n_used"] == int(cal["n_used"]) < 200
+
+
+from tests.random_cases import HMM_SHAPES, random_hmm_jobs
+
+
+@pytest.mark.parametrize("shape", HMM_SHAPES)
+def test_random_hmm_shapes_pinned(port_oracle, ref_oracle, shape):
+    """The shape families the GPU parity test draws (K = 1 and E = 1 jobs, methylation-window sizes, scorereads segments,
+    multi-strip widths with few rows, wide-and-tall, every flag combination, both strands, drift, indel bias 0.9): the port
+    oracle the CUDA path is compared with equals the compiled reference bit for bit on exactly those jobs."""
+    nuc = synth.load_model("nucleotide")
+    rs = synth.gen_reads(8, 2600, nuc, seed=900 + shape["kmin"], drift=True)
+    rng = np.random.default_rng(shape["kmin"] * 7 + 1)
+    jobs = random_hmm_jobs(rs, rng, shape["n"], shape["kmin"], shape["kmax"], shape["emin"], shape["emax"], [0, 1, 2, 3])
+    ref_oracle.clear_reads()
+    h = ref_oracle.builtin_model("nucleotide")
+    rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, h)
+    s_ref, _ = ref_oracle.score_batch(rh, jobs.jobs, jobs.seqs, [h], indel_bias=0.9, threads=8)
+    s_port, _ = port_oracle.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, [nuc], jobs.kmer_ranks, jobs.jobs, indel_bias=0.9, threads=8)
+    assert np.array_equal(_bits(s_ref), _bits(s_port))
+
+
+def _abea_ref_vs_port(port_oracle, ref_oracle, rs, jobs, ranks, total, seqs):
+    model = synth.load_model("nucleotide")
+    ref_oracle.clear_reads()
+    h = ref_oracle.builtin_model("nucleotide")
+    rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, h)
+    pr, poff, npairs, _ = ref_oracle.abea_batch(rh, h, seqs, [int(j["pairs_cap"]) for j in jobs], threads=8)
+    pp, res, _ = port_oracle.abea_batch(rs.reads, rs.ev_mean, rs.ev_start_time, model, ranks, jobs, total, threads=8)
+    assert [int(x) for x in npairs] == [int(x) for x in res["n_pairs"]]
+    for i in range(len(seqs)):
+        n = int(npairs[i])
+        a = pr[int(poff[i]):int(poff[i]) + n]
+        b = pp[int(jobs[i]["pairs_off"]):int(jobs[i]["pairs_off"]) + n]
+        assert np.array_equal(a[:, 0], b["ref_pos"]) and np.array_equal(a[:, 1], b["read_pos"]), f"read {i}"
+    return res
+
+
+@pytest.mark.parametrize("n_events,n_reads,scaled", [(60, 12, False), (900, 10, True), (4000, 6, False), (8000, 3, True)])
+def test_abea_random_reads_pinned(port_oracle, ref_oracle, n_events, n_reads, scaled):
+    """the read families of tests/test_gpu_abea.py::test_random_reads_identical_paths through the compiled reference"""
+    model = synth.load_model("nucleotide")
+    rs = synth.gen_reads(n_reads, n_events, model, seed=7000 + n_events, rng_scalings=scaled)
+    jobs, ranks, total = synth.abea_jobs(rs)
+    res = _abea_ref_vs_port(port_oracle, ref_oracle, rs, jobs, ranks, total, [synth._CODE2DNA[c].tobytes() for c in rs.seq_codes])
+    assert (res["n_pairs"] > 0).all()
+
+
+def test_abea_qc_mixed_and_truncated_pinned(port_oracle, ref_oracle):
+    """test_gpu_abea.py's QC / mixed-batch and truncated-sequence cases through the compiled reference: a read of noise and
+    one with a long stall (empty results where the reference's QC rejects), half a sequence, a 3-k-mer sequence."""
+    model = synth.load_model("nucleotide")
+    rs = synth.gen_reads(6, 500, model, seed=99, rng_scalings=False)
+    rng = np.random.default_rng(1)
+    o, n = int(rs.reads[1]["event_off"]), int(rs.reads[1]["n_events"])
+    rs.ev_mean[o:o + n] = rng.uniform(60, 120, n).astype(np.float32)
+    o, n = int(rs.reads[4]["event_off"]), int(rs.reads[4]["n_events"])
+    rs.ev_mean[o + 100:o + 300] = rs.ev_mean[o + 100]
+    jobs, ranks, total = synth.abea_jobs(rs)
+    res = _abea_ref_vs_port(port_oracle, ref_oracle, rs, jobs, ranks, total, [synth._CODE2DNA[c].tobytes() for c in rs.seq_codes])
+    assert int(res[1]["n_pairs"]) == 0
+    rs = synth.gen_reads(4, 700, model, seed=123, rng_scalings=False)
+    jobs, ranks, total = synth.abea_jobs(rs)
+    jobs = jobs.copy()
+    jobs[0]["n_kmers"] = jobs[0]["n_kmers"] // 2
+    jobs[1]["n_kmers"] = 3
+    seqs = [synth._CODE2DNA[c[:int(j["n_kmers"]) + 5]].tobytes() for c, j in zip(rs.seq_codes, jobs)]
+    _abea_ref_vs_port(port_oracle, ref_oracle, rs, jobs, ranks, total, seqs)
