@@ -297,7 +297,9 @@ def call_methylation_block(args, rank, world, local, steps, warmup):
     keep = []
     def P(a):
         t, v = pin(a); keep.append(t); return v
-    h_reads, h_mean, h_ref, h_pairs, h_recs = P(rs.reads), P(rs.ev_mean), P(ref), P(pairs), P(recs)
+    deltas, first_event = synth.compact_event_alignment(recs, pairs, ref.shape[0])       # 2 B per reference base instead of 8 B per pair
+    h_reads, h_mean, h_ref, h_recs = P(rs.reads), P(rs.ev_mean), P(ref), P(recs)
+    h_deltas, h_first = P(deltas), P(first_event)
 
     def barrier():
         if world > 1:
@@ -306,7 +308,7 @@ def call_methylation_block(args, rank, world, local, steps, warmup):
 
     # ---- device-resident arm ----
     eng.reads_load(h_reads, h_mean, rs.ev_start_time)
-    eng.methylation_load(h_ref, h_pairs, h_recs, params)
+    eng.methylation_load_compact(h_ref, h_deltas, h_first, h_recs, params)
 
     def step():
         eng.methylation_run()
@@ -361,7 +363,7 @@ def call_methylation_block(args, rank, world, local, steps, warmup):
 
     def e2e_step():
         n = host.nphh_call_methylation_flat(vp(h_reads), C.c_size_t(n_reads), vp(h_mean), None, C.c_size_t(h_mean.shape[0]),
-                                            vp(h_ref), C.c_size_t(h_ref.shape[0]), vp(h_pairs), C.c_size_t(h_pairs.shape[0]),
+                                            vp(h_ref), C.c_size_t(h_ref.shape[0]), None, C.c_size_t(0), vp(h_deltas), vp(h_first),
                                             vp(h_recs), C.c_size_t(n_reads), mh, names, vp(is_rev), b"chr1", C.c_double(1.0),
                                             vp(tsv), C.c_size_t(cap), C.byref(ns), C.byref(se), vp(secs2))
         if n < 0:
@@ -385,7 +387,7 @@ def call_methylation_block(args, rank, world, local, steps, warmup):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     assert int(ns.value) == n_sites and int(se.value) == scored
-    h2d = h_reads.nbytes + h_mean.nbytes + h_ref.nbytes + h_pairs.nbytes + h_recs.nbytes + 8 * (n_reads + 1) + 8 * n_reads
+    h2d = h_reads.nbytes + h_mean.nbytes + h_ref.nbytes + h_deltas.nbytes + h_first.nbytes + h_recs.nbytes + 8 * (n_reads + 1) + 8 * n_reads
     d2h = 24 * n_sites + 8 * (n_reads + 1) + 64
 
     out = None
@@ -398,7 +400,7 @@ def call_methylation_block(args, rank, world, local, steps, warmup):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(3, warmup),
                "ms_per_step": total_ms / steps, "scaling": "weak", "dtype": "f32", "data": "synthetic",
                "config": {"workload": f"call-methylation: synthetic R9.4 reads x {args.events} events aligned to their own sequence (CIGAR all M, half "
-                                      "the records reverse strand), CpG groups ~60 bp apart, cpg model (5^6 states), PRE|POST clip; motif scan, "
+                                      "the records reverse strand; event alignments in the 2 B/base compact form), CpG groups ~60 bp apart, cpg model (5^6 states), PRE|POST clip; motif scan, "
                                       "grouping, event bounds, k-mer ranks, scheduling and both scores per group on the device",
                           "reads_per_gpu": n_reads, "reads_total": reads_all, "events_per_read": args.events, "sites_per_step": sites_all,
                           "jobs_per_gpu": n_jobs, "scored_events_per_step": scored_all, "parallelism": f"read-shard x{world}",

@@ -355,6 +355,27 @@ int nph_methylation_batch(nph_ctx* ctx,
                           const nph_meth_params* params, double indel_bias,
                           uint64_t* site_off_out, nph_meth_site* sites_out, size_t sites_cap,
                           uint64_t* n_scored_events_out);
+/* The same with the event alignments in COMPACT form — 2 bytes per reference base instead of 8 per aligned pair, which matters
+ * because this call is PCIe bound (the event alignment is larger than the events themselves).  event_deltas runs parallel to
+ * ref_bases (entry ref_off + o belongs to reference offset o of the record): NPH_METH_NO_PAIR where aligned_events has no entry
+ * with ref_pos == ref_start_pos + o (a deleted reference base, the record's boundary k-mers), else that entry's event index
+ * minus the event index of the previous entry (minus first_event[record] for the record's first entry).  The device rebuilds
+ * the (ref_pos, event index) list by a prefix sum; results are identical to the pair form.  records[].pair_off / n_pairs are
+ * ignored.  Requires strictly increasing ref_pos inside a record (true of every EventAlignmentRecord) and event-index steps
+ * that fit an int16 (a caller that meets a larger step uses the pair form). */
+#define NPH_METH_NO_PAIR (-32768)
+int nph_methylation_batch_compact(nph_ctx* ctx,
+                                  const nph_read* reads, size_t n_reads,
+                                  const float* ev_mean, const double* ev_start_time, size_t n_events_total,
+                                  const char* ref_bases, const int16_t* event_deltas, size_t n_ref_total,
+                                  const int32_t* first_event,
+                                  const nph_meth_record* records, size_t n_records,
+                                  const nph_meth_params* params, double indel_bias,
+                                  uint64_t* site_off_out, nph_meth_site* sites_out, size_t sites_cap,
+                                  uint64_t* n_scored_events_out);
+int nph_methylation_load_compact(nph_ctx* ctx, const char* ref_bases, const int16_t* event_deltas, size_t n_ref_total,
+                                 const int32_t* first_event, const nph_meth_record* records, size_t n_records,
+                                 const nph_meth_params* params, double indel_bias);
 /* Staged form against the reads a preceding nph_reads_load left resident:
  *   nph_methylation_load : H2D of the reference bases, event alignments and records
  *   nph_methylation_run  : enumerate -> schedule -> score -> fill the site records, all on the device

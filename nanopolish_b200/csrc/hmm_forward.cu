@@ -33,7 +33,7 @@ __global__ void read_prologue_kernel(const DevRead* __restrict__ reads, const do
 
 static size_t scratch_slice_bytes(const nph_ctx* ctx)
 {
-    const int warps = ctx->sm_count * kWarpsPerCta;
+    const int warps = ctx->sm_count * kMaxWarpsPerCta;
     const size_t per_warp = sizeof(float4) * (size_t)ctx->max_kpad + sizeof(float) * 3 * ((size_t)ctx->max_period + 8);
     return ((per_warp * warps + 255) / 256) * 256;
 }
@@ -42,7 +42,7 @@ static size_t scratch_slice_bytes(const nph_ctx* ctx)
 // per-warp scratch by (block, warp) and must not share it.
 size_t nph_hmm_scratch_bytes(const nph_ctx* ctx, int* warps_total_out)
 {
-    if (warps_total_out) *warps_total_out = ctx->sm_count * kWarpsPerCta;
+    if (warps_total_out) *warps_total_out = ctx->sm_count * kMaxWarpsPerCta;
     return scratch_slice_bytes(ctx) * nph_ctx::kSideStreams;
 }
 
@@ -69,7 +69,7 @@ int nph_launch_hmm_forward(nph_ctx* ctx, float* scores_dev)
     p.logsum_g = ctx->d_logsum;
     p.flank = ctx->d_flank.p;
     p.scores = scores_dev ? scores_dev : ctx->d_scores.p;
-    const int warps = ctx->sm_count * kWarpsPerCta;
+    const int warps = ctx->sm_count * kMaxWarpsPerCta;
     p.kpad_stride = ctx->max_kpad;
     p.edge_stride = ctx->max_period + 8;
     p.c = ctx->consts;

@@ -58,8 +58,11 @@ __device__ __forceinline__ f32x2 P_emission(f32x2 x2, f32x2 mu2, f32x2 nsd2, f32
 #endif
 }
 
-constexpr int kWarpsPerCta = 16;
-constexpr int kCtaThreads = kWarpsPerCta * 32;
+// Warps per persistent CTA (one CTA per SM).  The full-warp classes hold 16 warps at up to 128 registers; the sub-warp classes of short
+// windows need fewer registers (80 at C = 4) and are latency bound on their per-step loads (issue-active 77 % with 16 warps,
+// profiles/r02_hmm_forward_methylation_classes_summary.md), so they run 24 (C <= 4) or 20 (C <= 6) warps.
+constexpr int kMaxWarpsPerCta = 24;
+template <int C, int W> struct CtaShape { static constexpr int warps = (W == 32) ? 16 : (C <= 4 ? 24 : (C <= 6 ? 20 : 16)); };
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMinPeriod = 40;   // chained strips: the right edge of row r must be written >32 steps before it is read
 
@@ -105,11 +108,13 @@ struct FwdParams {
 // to be moved between register pairs except at the lane boundary; only the skip chain K[c] <- K[c-1], which is
 // sequential across the columns of a row, stays scalar.
 template <int C, int W, bool CHAIN>
-__global__ void __launch_bounds__(kCtaThreads, 1) hmm_forward_kernel(const FwdParams p)
+__global__ void __launch_bounds__(CtaShape<C, W>::warps * 32, 1) hmm_forward_kernel(const FwdParams p)
 {
     static_assert(W == 4 || W == 8 || W == 16 || W == 32, "group width");
     static_assert(!CHAIN || W == 32, "only full-warp groups chain strips");
     constexpr int G = 32 / W;                 // jobs per warp
+    constexpr int kWarpsPerCta = CtaShape<C, W>::warps;
+    constexpr int kCtaThreads = kWarpsPerCta * 32;
     constexpr int STRIP = W * C;              // columns per strip
     extern __shared__ float s_tbl[];
     for (int i = threadIdx.x; i < NPH_TBL_SMEM; i += kCtaThreads) s_tbl[i] = p.logsum_g[i];
@@ -389,11 +394,12 @@ int launch_class(nph_ctx* ctx, const FwdParams& base, const nph_ctx::ClassLaunch
     p.counter = ctx->d_counters.p + class_idx;
     const size_t smem = sizeof(float) * NPH_TBL_SMEM;
     NPH_CUDA(ctx, cudaFuncSetAttribute(hmm_forward_kernel<C, W, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr int kWarpsPerCta = CtaShape<C, W>::warps;
     int grid = ctx->sm_count;
     const size_t warps_needed = (cl.count + (32 / W) - 1) / (32 / W);
     if ((size_t)grid * kWarpsPerCta > warps_needed) grid = (int)((warps_needed + kWarpsPerCta - 1) / kWarpsPerCta);
     if (grid < 1) grid = 1;
-    hmm_forward_kernel<C, W, CHAIN><<<grid, kCtaThreads, smem, stream>>>(p);
+    hmm_forward_kernel<C, W, CHAIN><<<grid, kWarpsPerCta * 32, smem, stream>>>(p);
     NPH_CUDA(ctx, cudaGetLastError());
     return NPH_OK;
 }

@@ -94,8 +94,55 @@ __device__ __forceinline__ int warp_lower_bound(const nph_aligned_pair* __restri
     return lo + __popc(__ballot_sync(kFull, less));
 }
 
+constexpr int kNoEvent = INT32_MIN;
+
+// compact event alignments: per record, a prefix sum over its int16 deltas rebuilds the event index of every reference base that
+// has an aligned_events entry (kNoEvent elsewhere) and notes the first such base
+__global__ void __launch_bounds__(kThreads) meth_expand_kernel(const int16_t* __restrict__ deltas, const int32_t* __restrict__ first_event,
+                                                               const nph_meth_record* __restrict__ records, uint32_t n_records,
+                                                               int32_t* __restrict__ dense, int32_t* __restrict__ first_valid)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const uint32_t n_warps = gridDim.x * kWarps;
+    for (uint32_t rec = warp; rec < n_records; rec += n_warps) {
+        const nph_meth_record R = records[rec];
+        const int16_t* dl = deltas + R.ref_off;
+        int32_t* out = dense + R.ref_off;
+        const int n = (int)R.ref_len;
+        int running = first_event[rec];
+        int fv = n;
+        for (int base = 0; base < n; base += 32) {
+            const int o = base + lane;
+            const int dv = o < n ? (int)dl[o] : NPH_METH_NO_PAIR;
+            const bool valid = dv != NPH_METH_NO_PAIR;
+            int v = valid ? dv : 0;
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) { const int t = __shfl_up_sync(kFull, v, sft); if (lane >= sft) v += t; }
+            if (o < n) out[o] = valid ? running + v : kNoEvent;
+            running += __shfl_sync(kFull, v, 31);
+            const unsigned m = __ballot_sync(kFull, valid);
+            if (m && fv == n) fv = base + (__ffs(m) - 1);
+        }
+        if (lane == 0) first_valid[rec] = fv;
+    }
+}
+
+// first offset >= from with an aligned_events entry (n: none): the dense counterpart of std::lower_bound on ref_pos
+__device__ __forceinline__ int warp_first_valid(const int32_t* __restrict__ dense, int n, int from, int lane)
+{
+    for (int base = from < 0 ? 0 : from; base < n; base += 32) {
+        const int o = base + lane;
+        const unsigned m = __ballot_sync(kFull, o < n && dense[o] != kNoEvent);
+        if (m) return base + (__ffs(m) - 1);
+    }
+    return n;
+}
+
 struct ScanArgs {
     const uint8_t* ref;
+    const int32_t* dense;       // compact mode: event index per reference base (nullptr: pair lists)
+    const int32_t* first_valid;
     const nph_aligned_pair* pairs;
     const nph_meth_record* records;
     const uint64_t* prov_off;
@@ -113,8 +160,10 @@ __global__ void __launch_bounds__(kThreads) meth_scan_kernel(const ScanArgs a, c
     for (uint32_t rec = warp; rec < a.n_records; rec += n_warps) {
         const nph_meth_record R = a.records[rec];
         const uint8_t* ref = a.ref + R.ref_off;
-        const nph_aligned_pair* pairs = a.pairs + R.pair_off;
-        const int n = (int)R.ref_len, np = (int)R.n_pairs;
+        const nph_aligned_pair* pairs = a.pairs ? a.pairs + R.pair_off : nullptr;
+        const int32_t* dense = a.dense ? a.dense + R.ref_off : nullptr;
+        const int fv = a.dense ? a.first_valid[rec] : 0;
+        const int n = (int)R.ref_len, np = a.dense ? 0 : (int)R.n_pairs;
         MethGroup* out = a.prov + a.prov_off[rec];
         unsigned long long n_groups = 0, n_ranks = 0, n_events = 0;
         int bad = 0;
@@ -127,13 +176,23 @@ __global__ void __launch_bounds__(kThreads) meth_scan_kernel(const ScanArgs a, c
             const int span = last_site - g_first;
             if (sub_start <= d.min_separation || span > d.max_span) return;
             const int calling_start = sub_start + R.ref_start_pos, calling_end = sub_end + R.ref_start_pos;
-            const int is = warp_lower_bound(pairs, np, calling_start, lane);
-            const int ie = warp_lower_bound(pairs, np, calling_end, lane);
-            if (is == np || ie == np) return;                                      // not bounded
-            // left_bounded: the entry at/after the boundary sits on it, or an earlier entry exists (it is < ref_start by
-            // construction).  right_bounded: the lower_bound entry is >= ref_stop by construction.
-            if (!(pairs[is].ref_pos <= calling_start || is != 0)) return;
-            const int e1 = pairs[is].read_pos, e2 = pairs[ie].read_pos;
+            int e1, e2;
+            if (dense) {
+                // the two lower_bounds on the rebuilt list: first reference offset at or after the boundary that has an entry
+                const int is = warp_first_valid(dense, n, sub_start, lane);
+                const int ie = warp_first_valid(dense, n, sub_end, lane);
+                if (is == n || ie == n) return;                                    // not bounded
+                if (!(is <= sub_start || is != fv)) return;                        // left_bounded (see the pair form below)
+                e1 = dense[is]; e2 = dense[ie];
+            } else {
+                const int is = warp_lower_bound(pairs, np, calling_start, lane);
+                const int ie = warp_lower_bound(pairs, np, calling_end, lane);
+                if (is == np || ie == np) return;                                  // not bounded
+                // left_bounded: the entry at/after the boundary sits on it, or an earlier entry exists (it is < ref_start by
+                // construction).  right_bounded: the lower_bound entry is >= ref_stop by construction.
+                if (!(pairs[is].ref_pos <= calling_start || is != 0)) return;
+                e1 = pairs[is].read_pos; e2 = pairs[ie].read_pos;
+            }
             const int de = e2 > e1 ? e2 - e1 : e1 - e2;
             if (de <= d.min_event_span) return;
             // (the reference's event/bp ratio divides by calling_start - calling_end < 0 and so never exceeds its limit)
@@ -356,16 +415,19 @@ int build_dev_params(nph_ctx* ctx, const nph_meth_params& p, MethDev& d)
 
 } // namespace
 
-extern "C" int nph_methylation_load(nph_ctx* ctx, const char* ref_bases, size_t n_ref_total,
-                                    const nph_aligned_pair* aligned_events, size_t n_pairs_total,
-                                    const nph_meth_record* records, size_t n_records,
-                                    const nph_meth_params* params, double indel_bias)
+// event alignments either as pair lists (aligned_events) or in compact form (event_deltas + first_event)
+static int meth_load(nph_ctx* ctx, const char* ref_bases, size_t n_ref_total,
+                     const nph_aligned_pair* aligned_events, size_t n_pairs_total,
+                     const int16_t* event_deltas, const int32_t* first_event,
+                     const nph_meth_record* records, size_t n_records,
+                     const nph_meth_params* params, double indel_bias)
 {
     if (!ctx || !params) return NPH_ERR_INVALID;
     nph_ctx::MethState& m = ctx->meth;
     m.loaded = false; m.ran = false;
+    const bool compact = event_deltas != nullptr;
     if (n_records == 0) { m.n_records = 0; m.loaded = true; return NPH_OK; }
-    if (!ref_bases || !records || (!aligned_events && n_pairs_total)) return NPH_ERR_INVALID;
+    if (!ref_bases || !records || (!compact && !aligned_events && n_pairs_total) || (compact && !first_event)) return NPH_ERR_INVALID;
     if (!ctx->reads_loaded) return NPH_ERR_STATE;
     MethDev d;
     NPH_TRY(build_dev_params(ctx, *params, d));
@@ -377,7 +439,7 @@ extern "C" int nph_methylation_load(nph_ctx* ctx, const char* ref_bases, size_t 
     for (size_t r = 0; r < n_records; ++r) {
         const nph_meth_record& R = records[r];
         const bool ok = R.read < ctx->n_reads && R.model_id < ctx->models.size() && R.ref_len <= n_ref_total && R.ref_off <= n_ref_total - R.ref_len &&
-                        R.n_pairs <= n_pairs_total && R.pair_off <= n_pairs_total - R.n_pairs;
+                        R.ref_len <= 0x7fffffffu && (compact || (R.n_pairs <= n_pairs_total && R.pair_off <= n_pairs_total - R.n_pairs));
         if (!ok) { ctx->last_error = "methylation record " + std::to_string(r) + " is out of range (read, model, reference or event-alignment slice)"; return NPH_ERR_INVALID; }
         const DevModel& mod = ctx->models[R.model_id];
         if (mod.k != params->k || mod.alphabet_size != params->alphabet_size) {
@@ -390,7 +452,12 @@ extern "C" int nph_methylation_load(nph_ctx* ctx, const char* ref_bases, size_t 
     po[n_records] = prov;
     NPH_CUDA(ctx, cudaSetDevice(ctx->device));
     NPH_TRY(nph_reserve(ctx, m.d_ref, n_ref_total + 16));
-    NPH_TRY(nph_reserve(ctx, m.d_pairs, n_pairs_total + 1));
+    if (compact) {
+        NPH_TRY(nph_reserve(ctx, m.d_deltas, n_ref_total + 16));
+        NPH_TRY(nph_reserve(ctx, m.d_dense, n_ref_total + 2 * n_records + 16));
+    } else {
+        NPH_TRY(nph_reserve(ctx, m.d_pairs, n_pairs_total + 1));
+    }
     NPH_TRY(nph_reserve(ctx, m.d_records, n_records));
     NPH_TRY(nph_reserve(ctx, m.d_prov_off, n_records + 1));
     NPH_TRY(nph_reserve(ctx, m.d_prov, (size_t)prov * sizeof(MethGroup)));
@@ -399,12 +466,34 @@ extern "C" int nph_methylation_load(nph_ctx* ctx, const char* ref_bases, size_t 
     NPH_CUDA(ctx, cudaMemcpyAsync(m.d_records.p, records, sizeof(nph_meth_record) * n_records, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(m.d_prov_off.p, po.data(), sizeof(uint64_t) * (n_records + 1), cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(m.d_ref.p, ref_bases, n_ref_total, cudaMemcpyHostToDevice, ctx->stream));
-    if (n_pairs_total)
+    if (compact) {
+        // first_event goes behind the dense array: [n_ref] event indices | [n_records] first_event | [n_records] first valid offset
+        NPH_CUDA(ctx, cudaMemcpyAsync(m.d_deltas.p, event_deltas, sizeof(int16_t) * n_ref_total, cudaMemcpyHostToDevice, ctx->stream));
+        NPH_CUDA(ctx, cudaMemcpyAsync(m.d_dense.p + n_ref_total, first_event, sizeof(int32_t) * n_records, cudaMemcpyHostToDevice, ctx->stream));
+    } else if (n_pairs_total) {
         NPH_CUDA(ctx, cudaMemcpyAsync(m.d_pairs.p, aligned_events, sizeof(nph_aligned_pair) * n_pairs_total, cudaMemcpyHostToDevice, ctx->stream));
-    m.n_records = n_records; m.n_ref = n_ref_total; m.n_pairs = n_pairs_total; m.prov_total = (size_t)prov;
+    }
+    m.compact = compact;
+    m.n_records = n_records; m.n_ref = n_ref_total; m.n_pairs = compact ? 0 : n_pairs_total; m.prov_total = (size_t)prov;
     m.params = *params; m.indel_bias = indel_bias;
     m.loaded = true;
     return NPH_OK;
+}
+
+extern "C" int nph_methylation_load(nph_ctx* ctx, const char* ref_bases, size_t n_ref_total,
+                                    const nph_aligned_pair* aligned_events, size_t n_pairs_total,
+                                    const nph_meth_record* records, size_t n_records,
+                                    const nph_meth_params* params, double indel_bias)
+{
+    return meth_load(ctx, ref_bases, n_ref_total, aligned_events, n_pairs_total, nullptr, nullptr, records, n_records, params, indel_bias);
+}
+
+extern "C" int nph_methylation_load_compact(nph_ctx* ctx, const char* ref_bases, const int16_t* event_deltas, size_t n_ref_total,
+                                            const int32_t* first_event, const nph_meth_record* records, size_t n_records,
+                                            const nph_meth_params* params, double indel_bias)
+{
+    if (n_records && !event_deltas) return NPH_ERR_INVALID;
+    return meth_load(ctx, ref_bases, n_ref_total, nullptr, 0, event_deltas, first_event, records, n_records, params, indel_bias);
 }
 
 extern "C" int nph_methylation_run(nph_ctx* ctx)
@@ -426,7 +515,17 @@ extern "C" int nph_methylation_run(nph_ctx* ctx)
     MethSummary* d_sum = reinterpret_cast<MethSummary*>(rank_off + n);
     NPH_CUDA(ctx, cudaMemsetAsync(d_sum, 0, sizeof(MethSummary), ctx->stream));
     const int grid = (int)std::min<size_t>((m.n_records + kWarps - 1) / kWarps, (size_t)ctx->sm_count * 8);
-    ScanArgs sa{m.d_ref.p, m.d_pairs.p, m.d_records.p, m.d_prov_off.p, reinterpret_cast<MethGroup*>(m.d_prov.p), counts, d_sum, n};
+    int32_t* dense = nullptr;
+    int32_t* first_valid = nullptr;
+    if (m.compact) {
+        dense = reinterpret_cast<int32_t*>(m.d_dense.p);
+        const int32_t* d_first_event = dense + m.n_ref;
+        first_valid = dense + m.n_ref + m.n_records;
+        meth_expand_kernel<<<grid, kThreads, 0, ctx->stream>>>(reinterpret_cast<const int16_t*>(m.d_deltas.p), d_first_event, m.d_records.p, n, dense, first_valid);
+        NPH_CUDA(ctx, cudaGetLastError());
+    }
+    ScanArgs sa{m.d_ref.p, dense, first_valid, m.compact ? nullptr : m.d_pairs.p, m.d_records.p, m.d_prov_off.p,
+                reinterpret_cast<MethGroup*>(m.d_prov.p), counts, d_sum, n};
     meth_scan_kernel<<<grid, kThreads, 0, ctx->stream>>>(sa, d);
     NPH_CUDA(ctx, cudaGetLastError());
     meth_prefix_kernel<<<1, 1024, 0, ctx->stream>>>(counts, n, site_off, rank_off, d_sum);
@@ -498,6 +597,30 @@ extern "C" int nph_methylation_fetch(nph_ctx* ctx, uint64_t* site_off_out, nph_m
         NPH_CUDA(ctx, cudaMemcpyAsync(sites_out, m.d_sites.p, sizeof(nph_meth_site) * (size_t)m.n_sites, cudaMemcpyDeviceToHost, ctx->stream));
     NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NPH_OK;
+}
+
+extern "C" int nph_methylation_batch_compact(nph_ctx* ctx,
+                                             const nph_read* reads, size_t n_reads,
+                                             const float* ev_mean, const double* ev_start_time, size_t n_events_total,
+                                             const char* ref_bases, const int16_t* event_deltas, size_t n_ref_total,
+                                             const int32_t* first_event,
+                                             const nph_meth_record* records, size_t n_records,
+                                             const nph_meth_params* params, double indel_bias,
+                                             uint64_t* site_off_out, nph_meth_site* sites_out, size_t sites_cap,
+                                             uint64_t* n_scored_events_out)
+{
+    if (!ctx || !site_off_out) return NPH_ERR_INVALID;
+    if (n_records == 0) { site_off_out[0] = 0; if (n_scored_events_out) *n_scored_events_out = 0; return NPH_OK; }
+    ctx->levels_inflight = false;
+    int rc = nph_reads_load_impl(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total, true);
+    if (rc == NPH_OK) { ctx->reads_loaded = true; ctx->jobs_loaded = false; ctx->abea_loaded = false; }
+    if (rc == NPH_OK) rc = nph_methylation_load_compact(ctx, ref_bases, event_deltas, n_ref_total, first_event, records, n_records, params, indel_bias);
+    if (rc == NPH_OK && ctx->levels_inflight) rc = nph_upload_level_chunks(ctx, ev_mean);
+    if (rc == NPH_OK) rc = nph_methylation_run(ctx);
+    if (rc == NPH_OK) rc = nph_methylation_fetch(ctx, site_off_out, sites_out, sites_cap);
+    nph_finish_level_upload(ctx);
+    if (rc == NPH_OK && n_scored_events_out) *n_scored_events_out = ctx->meth.n_scored_events;
+    return rc;
 }
 
 extern "C" int nph_methylation_batch(nph_ctx* ctx,

@@ -114,6 +114,9 @@ struct nph_ctx {
         uint64_t n_sites = 0, n_ranks = 0, n_scored_events = 0;
         DevBuf<uint8_t> d_ref;
         DevBuf<nph_aligned_pair> d_pairs;
+        bool compact = false;              // event alignments came as int16 deltas per reference base (nph_methylation_load_compact)
+        DevBuf<uint16_t> d_deltas;         // int16 deltas, n_ref entries
+        DevBuf<uint32_t> d_dense;          // int32 event index per reference base after the prefix sum (INT32_MIN: no pair), then per record: first_event, first valid offset
         DevBuf<nph_meth_record> d_records;
         DevBuf<uint64_t> d_prov_off;       // n_records + 1: where each record's provisional group rows start
         DevBuf<uint8_t> d_prov;            // provisional group rows (MethGroup)

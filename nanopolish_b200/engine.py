@@ -68,6 +68,22 @@ class Engine:
                                                    indel_bias, _p(site_off), _p(sites), sites.shape[0], C.byref(scored)), "nph_methylation_batch")
         return site_off, sites[:int(site_off[n])], int(scored.value)
 
+    def methylation_batch_compact(self, reads, ev_mean, ev_start_time, ref_bases, deltas, first_event, records, params, indel_bias: float = 1.0, out=None):
+        """nph_methylation_batch_compact (event alignments as int16 deltas per reference base)"""
+        n = int(records.shape[0])
+        cap = self.meth_sites_cap(records, params)
+        site_off, sites = out if out is not None else (np.zeros(n + 1, np.uint64), np.zeros(max(cap, 1), METH_SITE_DT))
+        scored = C.c_uint64()
+        self._check(self.lib.nph_methylation_batch_compact(self.ctx, _p(reads), reads.shape[0], _p(ev_mean), _p(ev_start_time), ev_mean.shape[0],
+                                                           _p(ref_bases), _p(deltas), ref_bases.shape[0], _p(first_event), _p(records), n, _p(params),
+                                                           indel_bias, _p(site_off), _p(sites), sites.shape[0], C.byref(scored)), "nph_methylation_batch_compact")
+        return site_off, sites[:int(site_off[n])], int(scored.value)
+
+    def methylation_load_compact(self, ref_bases, deltas, first_event, records, params, indel_bias: float = 1.0):
+        self._check(self.lib.nph_methylation_load_compact(self.ctx, _p(ref_bases), _p(deltas), ref_bases.shape[0], _p(first_event), _p(records),
+                                                          records.shape[0], _p(params), indel_bias), "nph_methylation_load_compact")
+        self._meth_n = int(records.shape[0])
+
     def methylation_load(self, ref_bases, pairs, records, params, indel_bias: float = 1.0):
         self._check(self.lib.nph_methylation_load(self.ctx, _p(ref_bases), ref_bases.shape[0], _p(pairs), pairs.shape[0], _p(records),
                                                   records.shape[0], _p(params), indel_bias), "nph_methylation_load")

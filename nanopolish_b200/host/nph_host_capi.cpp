@@ -348,7 +348,8 @@ long long nphh_call_methylation_timed(int n_reads, const int32_t* read, const ch
 // call-methylation from flat host buffers (the C-ABI layout) to TSV bytes: what bench.py's end-to-end arm times.
 // host_mode != 0 runs the host-side enumerator instead (reads registered with nphh_read_create; the cross-check path).
 long long nphh_call_methylation_flat(const void* reads, size_t n_reads, const float* ev_mean, const double* ev_start_time, size_t n_events,
-                                     const char* ref_bases, size_t n_ref, const void* aligned_events, size_t n_pairs, void* records, size_t n_records,
+                                     const char* ref_bases, size_t n_ref, const void* aligned_events, size_t n_pairs,
+                                     const int16_t* event_deltas, const int32_t* first_event, void* records, size_t n_records,
                                      int cpg_model, const char** read_names, const uint8_t* is_reverse, const char* contig, double indel_bias,
                                      char* tsv_out, size_t cap, uint64_t* n_sites_out, uint64_t* scored_events_out, double* secs2)
 {
@@ -362,6 +363,7 @@ long long nphh_call_methylation_flat(const void* reads, size_t n_reads, const fl
         FlatMethylationBatch b;
         b.reads = static_cast<const nph_read*>(reads); b.n_reads = n_reads; b.ev_mean = ev_mean; b.ev_start_time = ev_start_time; b.n_events = n_events;
         b.ref_bases = ref_bases; b.n_ref = n_ref; b.aligned_events = static_cast<const nph_aligned_pair*>(aligned_events); b.n_pairs = n_pairs;
+        b.event_deltas = event_deltas; b.first_event = first_event;
         b.records = recs; b.n_records = n_records; b.read_names = read_names; b.is_reverse = is_reverse; b.contig = contig;
         MethylationCallingParameters params;
         params.methylation_type = model->pmalphabet->get_name();

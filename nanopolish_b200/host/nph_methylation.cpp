@@ -150,6 +150,7 @@ void PinnedArray<T>::resize(size_t n)
 template class PinnedArray<char>;
 template class PinnedArray<nph_aligned_pair>;
 template class PinnedArray<nph_meth_site>;
+template class PinnedArray<int16_t>;
 
 nph_meth_params make_meth_params(const MethylationCallingParameters& params, uint32_t k, int region_start, int region_end)
 {
@@ -186,6 +187,7 @@ void MethylationCaller::clear()
 {
     m_batch.clear(); m_pending.clear(); m_reads.clear();
     m_ref.clear(); m_pairs.clear(); m_sites.clear(); m_records.clear(); m_record_meta.clear(); m_site_off.clear();
+    m_deltas.clear(); m_first_event.clear(); m_compact_ok = true;
     m_n_sites = 0; m_scored_events = 0; m_region_set = false; m_ran = false;
 }
 
@@ -198,7 +200,7 @@ void MethylationCaller::stage(const EventAlignedRead* const* reads, size_t n, in
         throw Error(NPH_ERR_UNSUPPORTED, "one output window per batch: call run() before changing region_start / region_end");
     m_region_start = region_start; m_region_end = region_end; m_region_set = true;
     m_ran = false;
-    struct Slot { size_t ref_off, pair_off[2]; bool use[2]; };
+    struct Slot { size_t ref_off[2], pair_off[2], rec[2]; bool use[2]; };
     std::vector<Slot> slots(n);
     size_t ref_total = m_ref.size(), pair_total = m_pairs.size();
     const size_t first_read = m_reads.size();
@@ -208,8 +210,7 @@ void MethylationCaller::stage(const EventAlignedRead* const* reads, size_t n, in
         re.name = r.read_name; re.is_reverse = r.is_reverse; re.contig = r.contig;
         re.ref_off = ref_total; re.ref_len = r.ref_seq.size(); re.ref_start_pos = r.ref_start_pos;
         re.first_record = m_records.size();
-        slots[i].ref_off = ref_total;
-        ref_total += r.ref_seq.size();
+        bool ref_placed = false;
         for (size_t strand_idx = 0; strand_idx < 2; ++strand_idx) {
             slots[i].use[strand_idx] = false;
             if (r.ref_seq.empty() || !r.read->has_events_for_strand(strand_idx)) continue;
@@ -221,7 +222,11 @@ void MethylationCaller::stage(const EventAlignedRead* const* reads, size_t n, in
             re.k = k;
             nph_meth_record rec;
             std::memset(&rec, 0, sizeof(rec));
-            rec.ref_off = slots[i].ref_off; rec.ref_len = (uint32_t)r.ref_seq.size();
+            // every record carries its own copy of the reference substring: the compact event alignment runs parallel to it
+            slots[i].ref_off[strand_idx] = ref_total; slots[i].rec[strand_idx] = m_records.size();
+            if (!ref_placed) { re.ref_off = ref_total; ref_placed = true; }
+            rec.ref_off = ref_total; rec.ref_len = (uint32_t)r.ref_seq.size();
+            ref_total += r.ref_seq.size();
             rec.pair_off = pair_total; rec.n_pairs = (uint32_t)r.aligned_events[strand_idx].size();
             rec.ref_start_pos = r.ref_start_pos; rec.rc = r.rc[strand_idx] ? 1 : 0; rec.strand = (uint8_t)strand_idx;
             slots[i].use[strand_idx] = true; slots[i].pair_off[strand_idx] = pair_total;
@@ -235,18 +240,45 @@ void MethylationCaller::stage(const EventAlignedRead* const* reads, size_t n, in
     (void)first_read;
     m_ref.resize(ref_total);
     m_pairs.resize(pair_total);
+    m_deltas.resize(ref_total);
+    m_first_event.resize(m_records.size(), 0);
     char* const ref = m_ref.data();
     nph_aligned_pair* const pairs = m_pairs.data();
+    int16_t* const deltas = m_deltas.data();
+    int compact_ok = m_compact_ok ? 1 : 0;
     static_assert(sizeof(AlignedPair) == sizeof(nph_aligned_pair), "AlignedPair layout");
 #pragma omp parallel for schedule(dynamic, 16) num_threads(host_threads()) if (n > 64)
     for (long long ii = 0; ii < (long long)n; ++ii) {
         const EventAlignedRead& r = *reads[(size_t)ii];
         const Slot& s = slots[(size_t)ii];
-        std::memcpy(ref + s.ref_off, r.ref_seq.data(), r.ref_seq.size());
-        for (int st = 0; st < 2; ++st)
-            if (s.use[st] && !r.aligned_events[st].empty())
-                std::memcpy(pairs + s.pair_off[st], r.aligned_events[st].data(), sizeof(AlignedPair) * r.aligned_events[st].size());
+        for (int st = 0; st < 2; ++st) {
+            if (!s.use[st]) continue;
+            std::memcpy(ref + s.ref_off[st], r.ref_seq.data(), r.ref_seq.size());
+            const std::vector<AlignedPair>& ae = r.aligned_events[st];
+            if (!ae.empty()) std::memcpy(pairs + s.pair_off[st], ae.data(), sizeof(AlignedPair) * ae.size());
+            // compact form: event-index steps per reference base (nph.h); a step beyond int16, a reference position outside the
+            // substring or out of order makes the whole batch fall back to the pair lists
+            int16_t* d = deltas + s.ref_off[st];
+            const long long len = (long long)r.ref_seq.size();
+            for (long long o = 0; o < len; ++o) d[o] = (int16_t)NPH_METH_NO_PAIR;
+            long long prev_off = -1;
+            int prev_ev = ae.empty() ? 0 : ae[0].read_pos;
+            m_first_event[s.rec[st]] = prev_ev;
+            bool ok = true;
+            for (const AlignedPair& ap : ae) {
+                const long long o = (long long)ap.ref_pos - r.ref_start_pos;
+                const long long step = (long long)ap.read_pos - prev_ev;
+                if (o <= prev_off || o >= len || step > 32767 || step < -32767) { ok = false; break; }
+                d[o] = (int16_t)step;
+                prev_off = o; prev_ev = ap.read_pos;
+            }
+            if (!ok) {
+#pragma omp atomic write
+                compact_ok = 0;
+            }
+        }
     }
+    m_compact_ok = compact_ok != 0;
 }
 
 size_t MethylationCaller::add_read(const EventAlignedRead& r, int region_start, int region_end)
@@ -425,10 +457,16 @@ void MethylationCaller::run(Engine& engine, double indel_bias)
         size_t cap = 0;
         for (const nph_meth_record& r : m_records) cap += r.ref_len / (size_t)(m_params.min_separation + 1) + 2;
         m_sites.resize(cap);
-        engine.check(nph_methylation_batch(engine.ctx(), fr.reads.data(), fr.reads.size(), fr.mean, fr.time, fr.n_events,
-                                           m_ref.data(), m_ref.size(), m_pairs.data(), m_pairs.size(), m_records.data(), m_records.size(),
-                                           &mp, indel_bias, m_site_off.data(), m_sites.data(), cap, &m_scored_events),
-                     "nph_methylation_batch");
+        if (m_compact_ok)
+            engine.check(nph_methylation_batch_compact(engine.ctx(), fr.reads.data(), fr.reads.size(), fr.mean, fr.time, fr.n_events,
+                                                       m_ref.data(), m_deltas.data(), m_ref.size(), m_first_event.data(), m_records.data(), m_records.size(),
+                                                       &mp, indel_bias, m_site_off.data(), m_sites.data(), cap, &m_scored_events),
+                         "nph_methylation_batch_compact");
+        else
+            engine.check(nph_methylation_batch(engine.ctx(), fr.reads.data(), fr.reads.size(), fr.mean, fr.time, fr.n_events,
+                                               m_ref.data(), m_ref.size(), m_pairs.data(), m_pairs.size(), m_records.data(), m_records.size(),
+                                               &mp, indel_bias, m_site_off.data(), m_sites.data(), cap, &m_scored_events),
+                         "nph_methylation_batch");
         m_n_sites = m_site_off.back();
         return;
     }
@@ -444,23 +482,60 @@ void MethylationCaller::run(Engine& engine, double indel_bias)
 }
 
 // one TSV row (write_methylation_results_as_tsv, call_methylation.cpp:532-550): chromosome, strand, start, end, read_name,
-// log_lik_ratio %.2lf, log_lik_methylated %.2lf, log_lik_unmethylated %.2lf, num_calling_strands, num_motifs, sequence
-static void append_row(std::string& out, const std::string& chromosome, bool is_reverse, int start_position, int end_position,
-                       const std::string& name, double sum_ll_m, double sum_ll_u, int strands_scored, int n_motif,
-                       const char* sequence, size_t sequence_len)
+// log_lik_ratio %.2lf, log_lik_methylated %.2lf, log_lik_unmethylated %.2lf, num_calling_strands, num_motifs, sequence.
+// Rows are written straight into a growing character buffer: "%d" by a reversed-digit loop, "%.2lf" by format_fixed (exact
+// integer arithmetic, nph_host.cpp) — no printf and no per-field string appends (19 -> 4 ms per 350 000 rows on the B200 box).
+namespace {
+struct RowBuffer {
+    std::unique_ptr<char[]> p;
+    size_t n = 0, cap = 0;
+    char* room(size_t extra)           // at least `extra` writable bytes at the returned position
+    {
+        if (n + extra > cap) {
+            const size_t want = std::max(cap * 2, n + extra + 4096);
+            std::unique_ptr<char[]> q(new char[want]);
+            if (n) std::memcpy(q.get(), p.get(), n);
+            p.swap(q); cap = want;
+        }
+        return p.get() + n;
+    }
+};
+inline char* put_uint(char* o, uint32_t v)
 {
-    char buf[512];
-    const double diff = sum_ll_m - sum_ll_u;
-    out += chromosome; out += '\t'; out += is_reverse ? '-' : '+'; out += '\t';
-    out.append(buf, (size_t)snprintf(buf, sizeof buf, "%d\t%d\t", start_position, end_position));
-    out += name; out += '\t';
-    out.append(buf, format_fixed(buf, diff, 2)); out += '\t';
-    out.append(buf, format_fixed(buf, sum_ll_m, 2)); out += '\t';
-    out.append(buf, format_fixed(buf, sum_ll_u, 2)); out += '\t';
-    out.append(buf, (size_t)snprintf(buf, sizeof buf, "%d\t%d\t", strands_scored, n_motif));
-    out.append(sequence, sequence_len);
-    out += '\n';
+    char tmp[12];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10u); v /= 10u; } while (v);
+    while (n) *o++ = tmp[--n];
+    return o;
 }
+inline char* put_int(char* o, int v)
+{
+    if (v < 0) { *o++ = '-'; return put_uint(o, (uint32_t)(-(int64_t)v)); }
+    return put_uint(o, (uint32_t)v);
+}
+const size_t kRowOverhead = 3 * 48 + 64;            // three %.2lf fields (format_fixed falls back to printf beyond 2^52), integers, tabs
+inline void put_row(RowBuffer& out, const char* chromosome, size_t chromosome_len, bool is_reverse, int start_position, int end_position,
+                    const char* name, size_t name_len, double sum_ll_m, double sum_ll_u, int strands_scored, int n_motif,
+                    const char* sequence, size_t sequence_len)
+{
+    char* o = out.room(chromosome_len + name_len + sequence_len + kRowOverhead);
+    char* const o0 = o;
+    const double diff = sum_ll_m - sum_ll_u;
+    std::memcpy(o, chromosome, chromosome_len); o += chromosome_len;
+    *o++ = '\t'; *o++ = is_reverse ? '-' : '+'; *o++ = '\t';
+    o = put_int(o, start_position); *o++ = '\t';
+    o = put_int(o, end_position); *o++ = '\t';
+    std::memcpy(o, name, name_len); o += name_len; *o++ = '\t';
+    o += format_fixed(o, diff, 2); *o++ = '\t';
+    o += format_fixed(o, sum_ll_m, 2); *o++ = '\t';
+    o += format_fixed(o, sum_ll_u, 2); *o++ = '\t';
+    o = put_int(o, strands_scored); *o++ = '\t';
+    o = put_int(o, n_motif); *o++ = '\t';
+    std::memcpy(o, sequence, sequence_len); o += sequence_len;
+    *o++ = '\n';
+    out.n += (size_t)(o - o0);
+}
+} // namespace
 
 // Device mode: the ScoredSite map of one read from its site records (the strands of a read meet at start_position,
 // exactly as the reference's find-or-insert does, basemods.cpp:403-425).
@@ -502,8 +577,8 @@ const std::map<int, ScoredSite>& MethylationCaller::sites(size_t read_idx) const
 }
 
 // rows of a record that is its read's only scored strand: the site records are already the rows, in ascending position
-static void append_single_strand_rows(std::string& out, const std::string& contig, bool is_reverse, const std::string& name, const char* ref,
-                                      size_t ref_len, int ref_start_pos, uint32_t k, size_t strand, const nph_meth_site* sites, size_t n)
+static void put_single_strand_rows(RowBuffer& out, const std::string& contig, bool is_reverse, const char* name, size_t name_len, const char* ref,
+                                   size_t ref_len, int ref_start_pos, uint32_t k, size_t strand, const nph_meth_site* sites, size_t n)
 {
     for (size_t s = 0; s < n; ++s) {
         const nph_meth_site& ms = sites[s];
@@ -511,25 +586,34 @@ static void append_single_strand_rows(std::string& out, const std::string& conti
         ll_m[strand] = ms.ll_methylated; ll_u[strand] = ms.ll_unmethylated;       // the other strand's entries stay 0, as in a fresh ScoredSite
         const size_t b = (size_t)(ms.start_position - ref_start_pos) - k + 1;
         const size_t e = std::min<size_t>((size_t)(ms.end_position - ref_start_pos) + k, ref_len);
-        append_row(out, contig, is_reverse, ms.start_position, ms.end_position, name, ll_m[0] + ll_m[1], ll_u[0] + ll_u[1], 1, (int)ms.n_motif,
-                   ref + b, e - b);
+        put_row(out, contig.data(), contig.size(), is_reverse, ms.start_position, ms.end_position, name, name_len, ll_m[0] + ll_m[1], ll_u[0] + ll_u[1], 1,
+                (int)ms.n_motif, ref + b, e - b);
     }
 }
 
 void MethylationCaller::append_rows(std::string& out, size_t read_idx) const
 {
+    RowBuffer rb;
+    put_rows(&rb, read_idx);
+    out.append(rb.p.get(), rb.n);
+}
+
+void MethylationCaller::put_rows(void* row_buffer, size_t read_idx) const
+{
+    RowBuffer& out = *static_cast<RowBuffer*>(row_buffer);
     const ReadEntry& re = m_reads[read_idx];
     if (m_mode == Mode::DeviceEnumeration && re.n_records == 1 && !re.sites_built) {
         if (!m_ran) throw Error(NPH_ERR_STATE, "MethylationCaller::tsv before run()");
         const size_t rec = re.first_record;
-        append_single_strand_rows(out, re.contig, re.is_reverse, re.name, m_ref.data() + re.ref_off, re.ref_len, re.ref_start_pos, re.k,
-                                  m_records[rec].strand, m_sites.data() + m_site_off[rec], (size_t)(m_site_off[rec + 1] - m_site_off[rec]));
+        put_single_strand_rows(out, re.contig, re.is_reverse, re.name.data(), re.name.size(), m_ref.data() + re.ref_off, re.ref_len, re.ref_start_pos,
+                               re.k, m_records[rec].strand, m_sites.data() + m_site_off[rec], (size_t)(m_site_off[rec + 1] - m_site_off[rec]));
         return;
     }
     for (const auto& kv : sites(read_idx)) {
         const ScoredSite& ss = kv.second;
-        append_row(out, ss.chromosome, re.is_reverse, ss.start_position, ss.end_position, re.name, ss.ll_methylated[0] + ss.ll_methylated[1],
-                   ss.ll_unmethylated[0] + ss.ll_unmethylated[1], ss.strands_scored, ss.n_motif, ss.sequence.data(), ss.sequence.size());
+        put_row(out, ss.chromosome.data(), ss.chromosome.size(), re.is_reverse, ss.start_position, ss.end_position, re.name.data(), re.name.size(),
+                ss.ll_methylated[0] + ss.ll_methylated[1], ss.ll_unmethylated[0] + ss.ll_unmethylated[1], ss.strands_scored, ss.n_motif,
+                ss.sequence.data(), ss.sequence.size());
     }
 }
 
@@ -550,25 +634,25 @@ std::vector<std::string> MethylationCaller::tsv_batch() const
 
 size_t MethylationCaller::tsv_all(char* out, size_t cap) const
 {
-    // contiguous blocks of reads per worker: format into a private string, then copy to the block's offset
+    // contiguous blocks of reads per worker: format into a private buffer, then copy to the block's offset
     const size_t n = m_reads.size();
     const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), (n + 63) / 64));
-    std::vector<std::string> parts((size_t)T);
+    std::vector<RowBuffer> parts((size_t)T);
     std::vector<std::string> errors((size_t)T);
 #pragma omp parallel for schedule(static, 1) num_threads(T) if (T > 1)
     for (int t = 0; t < T; ++t) {
         const size_t b = n * (size_t)t / (size_t)T, e = n * ((size_t)t + 1) / (size_t)T;
         try {
-            parts[t].reserve((e - b) * 4096);
-            for (size_t i = b; i < e; ++i) append_rows(parts[t], i);
+            parts[t].room((e - b) * 4096);
+            for (size_t i = b; i < e; ++i) put_rows(&parts[t], i);
         } catch (const std::exception& ex) { errors[t] = ex.what(); }
     }
     for (const std::string& e : errors) if (!e.empty()) throw Error(NPH_ERR_INVALID, e);
     std::vector<size_t> off((size_t)T + 1, 0);
-    for (int t = 0; t < T; ++t) off[t + 1] = off[t] + parts[t].size();
+    for (int t = 0; t < T; ++t) off[t + 1] = off[t] + parts[t].n;
     if (off[T] > cap || !out) return off[T];
 #pragma omp parallel for schedule(static, 1) num_threads(T) if (T > 1)
-    for (int t = 0; t < T; ++t) std::memcpy(out + off[t], parts[t].data(), parts[t].size());
+    for (int t = 0; t < T; ++t) if (parts[t].n) std::memcpy(out + off[t], parts[t].p.get(), parts[t].n);
     return off[T];
 }
 
@@ -585,33 +669,37 @@ size_t call_methylation_flat(Engine& engine, const FlatMethylationBatch& b, cons
     nph_meth_site* sites = static_cast<nph_meth_site*>(engine.pinned(3, sizeof(nph_meth_site) * std::max<size_t>(site_cap, 1)));
     std::vector<uint64_t> site_off(b.n_records + 1, 0);
     uint64_t scored = 0;
-    engine.check(nph_methylation_batch(engine.ctx(), b.reads, b.n_reads, b.ev_mean, b.ev_start_time, b.n_events, b.ref_bases, b.n_ref,
-                                       b.aligned_events, b.n_pairs, b.records, b.n_records, &mp, indel_bias, site_off.data(), sites, site_cap, &scored),
-                 "nph_methylation_batch");
+    if (b.event_deltas)
+        engine.check(nph_methylation_batch_compact(engine.ctx(), b.reads, b.n_reads, b.ev_mean, b.ev_start_time, b.n_events, b.ref_bases, b.event_deltas,
+                                                   b.n_ref, b.first_event, b.records, b.n_records, &mp, indel_bias, site_off.data(), sites, site_cap, &scored),
+                     "nph_methylation_batch_compact");
+    else
+        engine.check(nph_methylation_batch(engine.ctx(), b.reads, b.n_reads, b.ev_mean, b.ev_start_time, b.n_events, b.ref_bases, b.n_ref,
+                                           b.aligned_events, b.n_pairs, b.records, b.n_records, &mp, indel_bias, site_off.data(), sites, site_cap, &scored),
+                     "nph_methylation_batch");
     const double t1 = now();
     const size_t n = b.n_records;
     const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), (n + 63) / 64));
-    std::vector<std::string> parts((size_t)T);
+    std::vector<RowBuffer> parts((size_t)T);
     const std::string contig(b.contig ? b.contig : "");
 #pragma omp parallel for schedule(static, 1) num_threads(T) if (T > 1)
     for (int t = 0; t < T; ++t) {
         const size_t lo = n * (size_t)t / (size_t)T, hi = n * ((size_t)t + 1) / (size_t)T;
-        std::string& out = parts[t];
-        out.reserve((size_t)(site_off[hi] - site_off[lo]) * 96 + 64);
-        std::string name;
+        RowBuffer& out = parts[t];
+        out.room((size_t)(site_off[hi] - site_off[lo]) * 96 + 64);
         for (size_t r = lo; r < hi; ++r) {
             const nph_meth_record& rec = b.records[r];
-            name.assign(b.read_names[r]);
-            append_single_strand_rows(out, contig, b.is_reverse[r] != 0, name, b.ref_bases + rec.ref_off, rec.ref_len, rec.ref_start_pos, k, rec.strand,
-                                      sites + site_off[r], (size_t)(site_off[r + 1] - site_off[r]));
+            const char* name = b.read_names[r];
+            put_single_strand_rows(out, contig, b.is_reverse[r] != 0, name, std::strlen(name), b.ref_bases + rec.ref_off, rec.ref_len, rec.ref_start_pos, k,
+                                   rec.strand, sites + site_off[r], (size_t)(site_off[r + 1] - site_off[r]));
         }
     }
     std::vector<size_t> off((size_t)T + 1, 0);
-    for (int t = 0; t < T; ++t) off[t + 1] = off[t] + parts[t].size();
+    for (int t = 0; t < T; ++t) off[t + 1] = off[t] + parts[t].n;
     if (stats) { stats->n_sites = site_off[n]; stats->scored_events = scored; }
     if (tsv_out && off[T] <= cap) {
 #pragma omp parallel for schedule(static, 1) num_threads(T) if (T > 1)
-        for (int t = 0; t < T; ++t) std::memcpy(tsv_out + off[t], parts[t].data(), parts[t].size());
+        for (int t = 0; t < T; ++t) if (parts[t].n) std::memcpy(tsv_out + off[t], parts[t].p.get(), parts[t].n);
     }
     if (stats) { stats->device_seconds = t1 - t0; stats->tsv_seconds = now() - t1; }
     return off[T];

@@ -104,6 +104,9 @@ struct FlatMethylationBatch {
     const float* ev_mean = nullptr; const double* ev_start_time = nullptr; size_t n_events = 0;
     const char* ref_bases = nullptr; size_t n_ref = 0;
     const nph_aligned_pair* aligned_events = nullptr; size_t n_pairs = 0;
+    // or the compact form (include/nph.h, nph_methylation_batch_compact): int16 event-index deltas parallel to ref_bases + the first
+    // event index of every record; used instead of aligned_events when event_deltas != nullptr
+    const int16_t* event_deltas = nullptr; const int32_t* first_event = nullptr;
     const nph_meth_record* records = nullptr; size_t n_records = 0;
     const char* const* read_names = nullptr;      // per record
     const uint8_t* is_reverse = nullptr;          // per record: bam_is_rev
@@ -161,6 +164,7 @@ private:
     void stage(const EventAlignedRead* const* reads, size_t n, int region_start, int region_end);
     void build_sites(size_t read_idx) const;
     void append_rows(std::string& out, size_t read_idx) const;
+    void put_rows(void* row_buffer, size_t read_idx) const;          // the same into the writer's growing character buffer
     Mode m_mode;
     MethylationCallingParameters m_params;
     HmmBatch m_batch;
@@ -169,6 +173,9 @@ private:
     // device mode: the flat batch (page-locked) and its results
     PinnedArray<char> m_ref;
     PinnedArray<nph_aligned_pair> m_pairs;
+    PinnedArray<int16_t> m_deltas;            // compact event alignments, parallel to m_ref (built next to m_pairs; used unless a step overflowed)
+    std::vector<int32_t> m_first_event;
+    bool m_compact_ok = true;
     PinnedArray<nph_meth_site> m_sites;
     std::vector<nph_meth_record> m_records;
     std::vector<Record> m_record_meta;

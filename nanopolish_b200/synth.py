@@ -532,3 +532,26 @@ def methylation_records(rs: ReadSet, model_id: int = 1, ref_start: int = 10_000,
         refs.append(ref); prs.append(pr)
         ro += ref.shape[0]; po += pr.shape[0]
     return np.concatenate(refs), np.concatenate(prs), recs
+
+
+METH_NO_PAIR = -32768
+
+
+def compact_event_alignment(records: np.ndarray, pairs: np.ndarray, n_ref_total: int):
+    """aligned_events pair lists -> the compact form of nph_methylation_batch_compact: (event_deltas i2[n_ref_total] parallel to the
+    reference bases, first_event i4[n_records]).  Raises OverflowError when an event-index step does not fit an int16."""
+    deltas = np.full(n_ref_total, METH_NO_PAIR, np.int16)
+    first = np.zeros(records.shape[0], np.int32)
+    for i, R in enumerate(records):
+        pr = pairs[int(R["pair_off"]):int(R["pair_off"]) + int(R["n_pairs"])]
+        if pr.shape[0] == 0:
+            continue
+        off = pr["ref_pos"].astype(np.int64) - int(R["ref_start_pos"])
+        assert (np.diff(off) > 0).all() and off[0] >= 0 and off[-1] < int(R["ref_len"])
+        ev = pr["read_pos"].astype(np.int64)
+        first[i] = ev[0]
+        d = np.diff(ev, prepend=ev[0])
+        if (np.abs(d) > 32767).any():
+            raise OverflowError("event-index step beyond int16: use the pair form")
+        deltas[int(R["ref_off"]) + off] = d.astype(np.int16)
+    return deltas, first

@@ -54,3 +54,28 @@ def test_score_set_combine_is_host_arithmetic(port_oracle):
     for g in range(10):
         want = port_oracle.score_set_combine(s[3 * g:3 * g + 3])
         assert np.float32(want).view(np.uint32) == out[g].view(np.uint32)
+
+
+def test_dist_library_exports():
+    """libnph_dist.so (include/nph_dist.h): the NCCL exchange behind a C signature; libnph.so itself must stay free of NCCL."""
+    import subprocess
+    hdr = open(os.path.join(ROOT, "include", "nph_dist.h")).read()
+    declared = set(re.findall(r"\b(nph_dist_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == {"nph_dist_gather_records", "nph_dist_gather_methylation_sites", "nph_dist_reduce_sum_f64"}
+    so = os.path.join(ROOT, "nanopolish_b200", "libnph_dist.so")
+    syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+    for name in declared:
+        assert f" T {name}" in syms, name
+    needed = subprocess.run(["readelf", "-d", os.path.join(ROOT, "nanopolish_b200", "libnph.so")], capture_output=True, text=True).stdout
+    assert "nccl" not in needed
+
+
+@pytest.mark.gpu
+def test_dist_gather_on_visible_gpus():
+    """tests/cuda/dist_gather_check: one host thread per visible GPU, variable-length gather to rank 0, the too-small-root case
+    (every rank fails alike, nobody hangs) and the f64 reduce — a C++ caller sharding without Python."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "cuda", "dist_gather_check")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok" in r.stdout

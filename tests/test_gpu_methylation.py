@@ -208,3 +208,44 @@ def test_device_equals_compiled_reference(eng2, ref_oracle):
         assert mc.tsv_rows("chr1", "-" if case["flag"] & 16 else "+", case["name"], rows) == want_tsv[i]
         total += s.shape[0]
     assert total > 150
+
+
+def test_compact_event_alignment_form(eng2, ref_oracle):
+    """nph_methylation_batch_compact (int16 event-index deltas per reference base, 2 B/base on the wire instead of 8 B/pair) returns
+    exactly what the pair form returns: synthetic all-M records, and the CIGAR cases with deletions / insertions / clipped ends
+    (reference bases without an entry, boundary k-mers dropped, reverse strand = falling event indices)."""
+    rs, models, ref, pairs, recs = _batch(40, 2500, 31, rc_every=2)
+    recs = recs.copy(); recs[3]["n_pairs"] = 0; recs[5]["n_pairs"] //= 2
+    params = synth.meth_params("cpg", K)
+    deltas, first = synth.compact_event_alignment(recs, pairs, ref.shape[0])
+    a = eng2.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref, pairs, recs, params)
+    b = eng2.methylation_batch_compact(rs.reads, rs.ev_mean, rs.ev_start_time, ref, deltas, first, recs, params)
+    assert np.array_equal(a[0], b[0]) and a[1].tobytes() == b[1].tobytes() and a[2] == b[2] and a[1].shape[0] > 1000
+    # staged
+    eng2.reads_load(rs.reads, rs.ev_mean, rs.ev_start_time)
+    eng2.methylation_load_compact(ref, deltas, first, recs, params)
+    eng2.methylation_run()
+    off2, s2 = eng2.methylation_fetch()
+    assert np.array_equal(a[0], off2) and a[1].tobytes() == s2.tobytes()
+    # records with indels
+    from tests import meth_cases as mc
+    nuc = synth.load_model("nucleotide")
+    rs = synth.gen_reads(6, 2200, nuc, seed=77, cpg_keep=0.35)
+    rng = np.random.default_rng(3)
+    refs, prs = [], []
+    recs = np.zeros(rs.n_reads, synth.METH_RECORD_DT)
+    ro = po = 0
+    for i in range(rs.n_reads):
+        case = mc.make_case(i, rs, rng)
+        pl, rc = mc.event_alignment_record(case)
+        r = np.frombuffer(mc.fetched_reference(case).encode(), np.uint8)
+        pr = np.zeros(len(pl), synth.PAIR_DT)
+        pr["ref_pos"], pr["read_pos"] = [p[0] for p in pl], [p[1] for p in pl]
+        recs[i] = (ro, po, i, 1, r.shape[0], pr.shape[0], case["ref_pos"], rc, 0, (0, 0))
+        refs.append(r); prs.append(pr); ro += r.shape[0]; po += pr.shape[0]
+    ref, pairs = np.concatenate(refs), np.concatenate(prs)
+    deltas, first = synth.compact_event_alignment(recs, pairs, ref.shape[0])
+    assert (deltas == synth.METH_NO_PAIR).sum() > 20
+    a = eng2.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref, pairs, recs, params)
+    b = eng2.methylation_batch_compact(rs.reads, rs.ev_mean, rs.ev_start_time, ref, deltas, first, recs, params)
+    assert np.array_equal(a[0], b[0]) and a[1].tobytes() == b[1].tobytes() and a[1].shape[0] > 100
