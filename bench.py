@@ -742,13 +742,14 @@ def main():
     t_reads, h_reads = pin(rs.reads.view(np.uint8)); keep.append(t_reads); h_reads = h_reads.view(rs.reads.dtype)
     t_mean, h_mean = pin(rs.ev_mean); keep.append(t_mean)
     t_time, h_time = pin(rs.ev_start_time); keep.append(t_time)
-    t_ranks, h_ranks = pin(jobs.kmer_ranks); keep.append(t_ranks)
-    t_jobs, h_jobs = pin(jobs.jobs.view(np.uint8)); keep.append(t_jobs); h_jobs = h_jobs.view(jobs.jobs.dtype)
+    # sequences cross the boundary as base codes (1 B/base; nph_hmm_*_seq), the jobs' rank_off indexing them
+    t_ranks, h_ranks = pin(jobs.seq_codes); keep.append(t_ranks)
+    t_jobs, h_jobs = pin(jobs.code_jobs.view(np.uint8)); keep.append(t_jobs); h_jobs = h_jobs.view(jobs.jobs.dtype)
     t_out = torch.empty(n_jobs, dtype=torch.float32).pin_memory(); h_out = t_out.numpy()
 
     # ---- device-resident arm: inputs already in HBM when the timed region starts ----------
     eng.reads_load(h_reads, h_mean, h_time)
-    eng.hmm_jobs_load(h_ranks, h_jobs)
+    eng.hmm_jobs_load_seq(h_ranks, h_jobs)
     scores = torch.empty(n_jobs, dtype=torch.float32, device=dev)
     counts = None
     gathered = None
@@ -809,7 +810,7 @@ def main():
 
     # ---- e2e arm: the one-shot C-ABI call with HOST buffers, H2D + D2H inside the timed region ----
     def e2e_step():
-        eng.hmm_score_batch(h_reads, h_mean, h_time, h_ranks, h_jobs, out=h_out)
+        eng.hmm_score_batch_seq(h_reads, h_mean, h_time, h_ranks, h_jobs, out=h_out)
 
     for _ in range(2):
         e2e_step()
@@ -826,7 +827,7 @@ def main():
     e2e_s = float(t.item())
     e2e_value = ev_all * e2e_steps / e2e_s
     any_drift = bool((rs.reads["drift"] != 0).any())
-    h2d = rs.reads.nbytes + rs.ev_mean.nbytes + (rs.ev_start_time.nbytes if any_drift else 0) + jobs.kmer_ranks.nbytes \
+    h2d = rs.reads.nbytes + rs.ev_mean.nbytes + (rs.ev_start_time.nbytes if any_drift else 0) + jobs.seq_codes.nbytes \
         + jobs.jobs.nbytes + 4 * n_jobs + 8 * rs.n_reads
     d2h = 4 * n_jobs
 
@@ -851,7 +852,7 @@ def main():
                        "scored_events_per_step": ev_all},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "api": "nph_hmm_score_batch (host buffers in, host scores out)"},
+                    "steps": e2e_steps, "api": "nph_hmm_score_batch_seq (host buffers in: events + 1 B/base sequence codes + jobs; host scores out)"},
             "gpu_launches": int(launches_per_step) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "hmm_forward_kernel<C>",

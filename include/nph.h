@@ -187,6 +187,22 @@ int nph_hmm_jobs_load(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_t
 int nph_hmm_score(nph_ctx* ctx, float* scores_dev);
 int nph_hmm_scores_fetch(nph_ctx* ctx, float* scores_out, size_t n_jobs);
 
+/* The same computation with the sequences as BASE CODES instead of k-mer ranks — one byte per base on the wire and in HBM instead
+ * of four per k-mer; the forward kernel forms each k-mer's rank from the codes while it scales the k-mer's Gaussian.
+ * seq_codes holds, per job, the alphabet ranks Alphabet::rank(c) of the n_kmers + k - 1 symbols of the string the job's strand
+ * reads: HMMInputSequence's m_seq for rc == 0, its m_rc_seq for rc == 1 (so that k-mer i is what get_kmer_rank(i, k, rc)
+ * ranks: the k symbols at i, resp. at length - i - k; src/hmm/nanopolish_hmm_input_sequence.h:76-91).  In these calls
+ * nph_hmm_job::rank_off is the offset of the job's first code in seq_codes, and nph_hmm_job::rc selects the direction.
+ * A code outside the job's model alphabet yields NPH_ERR_INVALID. */
+int nph_hmm_score_batch_seq(nph_ctx* ctx,
+                            const nph_read* reads, size_t n_reads,
+                            const float* ev_mean, const double* ev_start_time, size_t n_events_total,
+                            const uint8_t* seq_codes, size_t n_codes_total,
+                            const nph_hmm_job* jobs, size_t n_jobs,
+                            double indel_bias, float* scores_out);
+int nph_hmm_jobs_load_seq(nph_ctx* ctx, const uint8_t* seq_codes, size_t n_codes_total,
+                          const nph_hmm_job* jobs, size_t n_jobs, double indel_bias);
+
 /* profile_hmm_score_set (ref: src/hmm/nanopolish_profile_hmm.cpp:32-56): combine the per-sequence
  * scores of each group of n_alt consecutive jobs, host side, in double through the table logsum:
  *   out[g] = (+)_i ( scores[g*n_alt + i] - log(n_alt) ).  Pure host arithmetic on fetched scores. */

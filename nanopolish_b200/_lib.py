@@ -45,6 +45,8 @@ def load() -> C.CDLL:
     lib.nph_hmm_score.argtypes = [vp, vp]
     lib.nph_hmm_scores_fetch.argtypes = [vp, vp, sz]
     lib.nph_hmm_score_batch.argtypes = [vp, vp, sz, vp, vp, sz, vp, sz, vp, sz, dbl, vp]
+    lib.nph_hmm_score_batch_seq.argtypes = [vp, vp, sz, vp, vp, sz, vp, sz, vp, sz, dbl, vp]
+    lib.nph_hmm_jobs_load_seq.argtypes = [vp, vp, sz, vp, sz, dbl]
     lib.nph_score_set_combine.argtypes = [vp, sz, u32, vp]
     lib.nph_abea_batch.argtypes = [vp, vp, sz, vp, vp, sz, vp, sz, vp, sz, u32, vp, sz, vp]
     lib.nph_abea_jobs_load.argtypes = [vp, vp, sz, vp, sz, u32, sz]
@@ -76,7 +78,7 @@ def load() -> C.CDLL:
 # every symbol include/nph.h declares (tests check the library exports all of them)
 EXPORTS = [
     "nph_create", "nph_create_on_stream", "nph_destroy", "nph_strerror", "nph_last_error", "nph_version",
-    "nph_sync", "nph_stream", "nph_model_upload", "nph_hmm_score_batch", "nph_reads_load",
+    "nph_sync", "nph_stream", "nph_model_upload", "nph_hmm_score_batch", "nph_hmm_score_batch_seq", "nph_hmm_jobs_load_seq", "nph_reads_load",
     "nph_hmm_jobs_load", "nph_hmm_score", "nph_hmm_scores_fetch", "nph_score_set_combine",
     "nph_abea_batch", "nph_abea_jobs_load", "nph_abea_run", "nph_abea_fetch", "nph_mom_batch",
     "nph_hmm_align_batch", "nph_hmm_align", "nph_eventalign_chain", "nph_detect_events_batch", "nph_trim_raw_batch", "nph_recalibrate_batch", "nph_load_from_raw_batch", "nph_last_trim_ranges", "nph_methylation_batch", "nph_methylation_batch_compact", "nph_methylation_load", "nph_methylation_load_compact", "nph_methylation_run", "nph_methylation_counts", "nph_methylation_fetch", "nph_methylation_sites_dev", "nph_last_kernel_ms", "nph_host_alloc", "nph_host_free",

@@ -19,7 +19,7 @@ struct SchedSummary {
 };
 
 __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n_jobs, const DevRead* __restrict__ reads,
-                                uint32_t n_reads, const DevModelView* __restrict__ models, const uint32_t* __restrict__ ranks,
+                                uint32_t n_reads, const DevModelView* __restrict__ models, const uint32_t* __restrict__ ranks, const uint8_t* __restrict__ codes,
                                 uint32_t n_models, uint64_t n_ranks, uint32_t chunk_events, uint8_t* __restrict__ cls,
                                 uint16_t* __restrict__ bkt, unsigned int* __restrict__ hist, SchedSummary* __restrict__ sum)
 {
@@ -33,6 +33,9 @@ __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n
         const nph_hmm_job jb = jobs[j];
         uint32_t chunk = 0;
         bool ok = jb.read < n_reads && jb.model_id < n_models && jb.n_kmers != 0 && jb.n_kmers <= n_ranks && jb.rank_off <= n_ranks - jb.n_kmers;   // overflow-safe
+        // base-code jobs (nph_hmm_*_seq) read n_kmers + k - 1 codes at rank_off
+        const uint32_t seq_len = (ok && codes) ? jb.n_kmers + models[jb.model_id].k - 1u : 0u;
+        if (ok && codes) ok = seq_len <= n_ranks && jb.rank_off <= n_ranks - seq_len;
         ok = ok && (jb.stride == 1 || jb.stride == -1);
         if (ok) {
             const DevRead rd = reads[jb.read];
@@ -43,11 +46,17 @@ __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n
         }
         if (ok) {
             // every k-mer rank must index the job's model table (the reference would read past PoreModel::states)
-            const uint32_t ns = models[jb.model_id].n_states;
-            const uint32_t* rk = ranks + jb.rank_off;
             uint32_t worst = 0;
-            for (uint32_t i = 0; i < jb.n_kmers; ++i) worst = max(worst, rk[i]);
-            ok = worst < ns;
+            if (codes) {                       // every code must be a symbol of the model's alphabet
+                const uint8_t* cd = codes + jb.rank_off;
+                for (uint32_t i = 0; i < seq_len; ++i) worst = max(worst, (uint32_t)cd[i]);
+                ok = worst < models[jb.model_id].alphabet_size;
+            } else {
+                const uint32_t ns = models[jb.model_id].n_states;
+                const uint32_t* rk = ranks + jb.rank_off;
+                for (uint32_t i = 0; i < jb.n_kmers; ++i) worst = max(worst, rk[i]);
+                ok = worst < ns;
+            }
         }
         if (!ok) { atomicCAS(&sum->error, 0, (int)(j + 1)); cls[j] = 0; bkt[j] = 0; continue; }
         const uint32_t E = (jb.event_stop > jb.event_start ? jb.event_stop - jb.event_start : jb.event_start - jb.event_stop) + 1;
@@ -132,7 +141,7 @@ int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uin
     int blocks = (int)std::min<size_t>((n_jobs + threads - 1) / threads, (size_t)ctx->sm_count * 8);
     if (blocks < 1) blocks = 1;
     classify_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->d_jobs.p, (uint32_t)n_jobs, ctx->d_reads.p, (uint32_t)ctx->n_reads,
-                                                        ctx->d_models.p, ctx->d_ranks.p, (uint32_t)ctx->models.size(), (uint64_t)n_ranks_total,
+                                                        ctx->d_models.p, ctx->d_ranks.p, ctx->codes_mode ? ctx->d_codes.p : nullptr, (uint32_t)ctx->models.size(), (uint64_t)n_ranks_total,
                                                         (uint32_t)(ctx->levels_inflight ? ctx->level_chunk_events : 0), ctx->d_sched_cls.p,
                                                         ctx->d_sched_bkt.p, hist, d_sum);
     NPH_CUDA(ctx, cudaGetLastError());

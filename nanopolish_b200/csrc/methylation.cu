@@ -539,7 +539,7 @@ extern "C" int nph_methylation_run(nph_ctx* ctx)
     }
     m.n_sites = h.n_sites; m.n_ranks = h.n_ranks; m.n_scored_events = h.n_events;
     const size_t n_jobs = 2 * (size_t)h.n_sites;
-    ctx->n_jobs = 0; ctx->jobs_loaded = false;
+    ctx->n_jobs = 0; ctx->jobs_loaded = false; ctx->codes_mode = false;       // the enumerator emits k-mer ranks
     if (n_jobs == 0) { ctx->classes.clear(); ctx->jobs_loaded = true; m.ran = true; return NPH_OK; }
     NPH_TRY(nph_reserve(ctx, ctx->d_ranks, (size_t)h.n_ranks));
     NPH_TRY(nph_reserve(ctx, ctx->d_jobs, n_jobs));

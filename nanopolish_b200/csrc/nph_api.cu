@@ -200,7 +200,7 @@ int nph_destroy(nph_ctx* ctx)
     if (ctx->stream || !ctx->own_stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->d_logsum) cudaFree(ctx->d_logsum);
     free_buf(ctx->d_flank); free_buf(ctx->d_models); free_buf(ctx->d_reads); free_buf(ctx->d_ev_mean);
-    free_buf(ctx->d_ev_time); free_buf(ctx->d_level); free_buf(ctx->d_drift); free_buf(ctx->d_ranks);
+    free_buf(ctx->d_ev_time); free_buf(ctx->d_level); free_buf(ctx->d_drift); free_buf(ctx->d_ranks); free_buf(ctx->d_codes);
     free_buf(ctx->d_jobs); free_buf(ctx->d_trans); free_buf(ctx->d_order); free_buf(ctx->d_scores);
     free_buf(ctx->d_counters); free_buf(ctx->d_sched_cls); free_buf(ctx->d_sched_bkt); free_buf(ctx->d_sched_hist); free_buf(ctx->d_scratch); free_buf(ctx->d_abea_jobs); free_buf(ctx->d_abea_ranks);
     free_buf(ctx->d_pairs); free_buf(ctx->d_abea_res); free_buf(ctx->d_abea_scratch); free_buf(ctx->d_abea_order); free_buf(ctx->d_abea_consts); free_buf(ctx->d_prep);
@@ -236,7 +236,7 @@ int nph_model_upload(nph_ctx* ctx, const double* level_mean, const double* level
     if (!ctx || !level_mean || !level_stdv || !level_log_stdv || !model_id_out || n_states == 0) return NPH_ERR_INVALID;
     uint64_t expect = 1;
     for (uint32_t i = 0; i < k; ++i) expect *= alphabet_size;
-    if (expect != n_states) return NPH_ERR_INVALID;   // ref asserts states.size() == alphabet^k (profile_hmm_r9.inl:305)
+    if (expect != n_states || k == 0 || k > 16 || alphabet_size == 0 || alphabet_size > 255) return NPH_ERR_INVALID;   // ref asserts states.size() == alphabet^k (profile_hmm_r9.inl:305)
     NPH_CUDA(ctx, cudaSetDevice(ctx->device));
     DevModel m;
     const size_t bytes = sizeof(double) * n_states;
@@ -250,7 +250,8 @@ int nph_model_upload(nph_ctx* ctx, const double* level_mean, const double* level
     ctx->models.push_back(m);
     std::vector<DevModelView> views(ctx->models.size());
     for (size_t i = 0; i < views.size(); ++i)
-        views[i] = DevModelView{ctx->models[i].mean, ctx->models[i].stdv, ctx->models[i].log_stdv, ctx->models[i].n_states, 0};
+        views[i] = DevModelView{ctx->models[i].mean, ctx->models[i].stdv, ctx->models[i].log_stdv, ctx->models[i].n_states,
+                                (uint16_t)ctx->models[i].k, (uint16_t)ctx->models[i].alphabet_size};
     NPH_TRY(nph_reserve(ctx, ctx->d_models, views.size()));
     NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_models.p, views.data(), sizeof(DevModelView) * views.size(), cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -351,10 +352,12 @@ int nph_reads_load(nph_ctx* ctx, const nph_read* reads, size_t n_reads,
     return NPH_OK;
 }
 
-static int jobs_upload_async(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_total,
+// kmer_ranks != nullptr: ranks (uint32 per k-mer); else seq_codes (uint8 per base) — n_total counts whichever it is
+static int jobs_upload_async(nph_ctx* ctx, const uint32_t* kmer_ranks, const uint8_t* seq_codes, size_t n_ranks_total,
                              const nph_hmm_job* jobs, size_t n_jobs, double indel_bias)
 {
-    if (!kmer_ranks || !jobs) return NPH_ERR_INVALID;
+    if ((!kmer_ranks && !seq_codes) || !jobs) return NPH_ERR_INVALID;
+    ctx->codes_mode = kmer_ranks == nullptr;
     NPH_CUDA(ctx, cudaSetDevice(ctx->device));
 
     // per-read transition pair (2 logf with the host libm, see read_transitions)
@@ -362,13 +365,15 @@ static int jobs_upload_async(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_
     trans.resize(ctx->n_reads);
     for (size_t i = 0; i < ctx->n_reads; ++i) trans[i] = read_transitions(ctx->h_events_per_base[i], indel_bias);
 
-    NPH_TRY(nph_reserve(ctx, ctx->d_ranks, n_ranks_total));
+    if (ctx->codes_mode) NPH_TRY(nph_reserve(ctx, ctx->d_codes, n_ranks_total + 16));
+    else NPH_TRY(nph_reserve(ctx, ctx->d_ranks, n_ranks_total));
     NPH_TRY(nph_reserve(ctx, ctx->d_jobs, n_jobs));
     NPH_TRY(nph_reserve(ctx, ctx->d_order, n_jobs));
     NPH_TRY(nph_reserve(ctx, ctx->d_trans, ctx->n_reads));
     NPH_TRY(nph_reserve(ctx, ctx->d_scores, n_jobs));
     NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_jobs.p, jobs, sizeof(nph_hmm_job) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
-    NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ranks.p, kmer_ranks, sizeof(uint32_t) * n_ranks_total, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->codes_mode) NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_codes.p, seq_codes, n_ranks_total, cudaMemcpyHostToDevice, ctx->stream));
+    else NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_ranks.p, kmer_ranks, sizeof(uint32_t) * n_ranks_total, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(ctx->d_trans.p, trans.data(), sizeof(float2) * ctx->n_reads, cudaMemcpyHostToDevice, ctx->stream));
     return NPH_OK;
 }
@@ -392,8 +397,19 @@ int nph_hmm_jobs_load(nph_ctx* ctx, const uint32_t* kmer_ranks, size_t n_ranks_t
     if (!ctx) return NPH_ERR_INVALID;
     if (n_jobs == 0) { ctx->n_jobs = 0; ctx->classes.clear(); ctx->jobs_loaded = true; return NPH_OK; }   // empty batch: nothing to score
     if (!ctx->reads_loaded) return NPH_ERR_STATE;
-    NPH_TRY(jobs_upload_async(ctx, kmer_ranks, n_ranks_total, jobs, n_jobs, indel_bias));
+    NPH_TRY(jobs_upload_async(ctx, kmer_ranks, nullptr, n_ranks_total, jobs, n_jobs, indel_bias));
     return nph_jobs_schedule(ctx, n_jobs, n_ranks_total);
+}
+
+int nph_hmm_jobs_load_seq(nph_ctx* ctx, const uint8_t* seq_codes, size_t n_codes_total,
+                          const nph_hmm_job* jobs, size_t n_jobs, double indel_bias)
+{
+    if (!ctx) return NPH_ERR_INVALID;
+    if (n_jobs == 0) { ctx->n_jobs = 0; ctx->classes.clear(); ctx->jobs_loaded = true; return NPH_OK; }
+    if (!ctx->reads_loaded) return NPH_ERR_STATE;
+    if (!seq_codes) return NPH_ERR_INVALID;
+    NPH_TRY(jobs_upload_async(ctx, nullptr, seq_codes, n_codes_total, jobs, n_jobs, indel_bias));
+    return nph_jobs_schedule(ctx, n_jobs, n_codes_total);
 }
 
 int nph_hmm_score(nph_ctx* ctx, float* scores_dev)
@@ -417,12 +433,12 @@ int nph_hmm_scores_fetch(nph_ctx* ctx, float* scores_out, size_t n_jobs)
     return NPH_OK;
 }
 
-int nph_hmm_score_batch(nph_ctx* ctx,
-                        const nph_read* reads, size_t n_reads,
-                        const float* ev_mean, const double* ev_start_time, size_t n_events_total,
-                        const uint32_t* kmer_ranks, size_t n_ranks_total,
-                        const nph_hmm_job* jobs, size_t n_jobs,
-                        double indel_bias, float* scores_out)
+static int hmm_score_batch_impl(nph_ctx* ctx,
+                                const nph_read* reads, size_t n_reads,
+                                const float* ev_mean, const double* ev_start_time, size_t n_events_total,
+                                const uint32_t* kmer_ranks, const uint8_t* seq_codes, size_t n_ranks_total,
+                                const nph_hmm_job* jobs, size_t n_jobs,
+                                double indel_bias, float* scores_out)
 {
     static const bool timing = getenv("NPH_TIMING") != nullptr;   // development aid: per-phase host wall time on stderr
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -436,7 +452,7 @@ int nph_hmm_score_batch(nph_ctx* ctx,
     int rc = nph_reads_load_impl(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total, true);
     if (rc == NPH_OK) { ctx->reads_loaded = true; ctx->jobs_loaded = false; ctx->abea_loaded = false; }
     const double t1 = now();
-    if (rc == NPH_OK) rc = jobs_upload_async(ctx, kmer_ranks, n_ranks_total, jobs, n_jobs, indel_bias);
+    if (rc == NPH_OK) rc = jobs_upload_async(ctx, kmer_ranks, seq_codes, n_ranks_total, jobs, n_jobs, indel_bias);
     if (rc == NPH_OK && ctx->levels_inflight) rc = nph_upload_level_chunks(ctx, ev_mean);
     if (rc == NPH_OK) rc = nph_jobs_schedule(ctx, n_jobs, n_ranks_total);
     const double t2 = now();
@@ -446,6 +462,28 @@ int nph_hmm_score_batch(nph_ctx* ctx,
     const double t3 = now();
     if (timing) fprintf(stderr, "[nph] reads %.2f ms  jobs+schedule %.2f ms  score+fetch %.2f ms\n", t1 - t0, t2 - t1, t3 - t2);
     return rc;
+}
+
+int nph_hmm_score_batch(nph_ctx* ctx,
+                        const nph_read* reads, size_t n_reads,
+                        const float* ev_mean, const double* ev_start_time, size_t n_events_total,
+                        const uint32_t* kmer_ranks, size_t n_ranks_total,
+                        const nph_hmm_job* jobs, size_t n_jobs,
+                        double indel_bias, float* scores_out)
+{
+    if (n_jobs && !kmer_ranks) return NPH_ERR_INVALID;
+    return hmm_score_batch_impl(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total, kmer_ranks, nullptr, n_ranks_total, jobs, n_jobs, indel_bias, scores_out);
+}
+
+int nph_hmm_score_batch_seq(nph_ctx* ctx,
+                            const nph_read* reads, size_t n_reads,
+                            const float* ev_mean, const double* ev_start_time, size_t n_events_total,
+                            const uint8_t* seq_codes, size_t n_codes_total,
+                            const nph_hmm_job* jobs, size_t n_jobs,
+                            double indel_bias, float* scores_out)
+{
+    if (n_jobs && !seq_codes) return NPH_ERR_INVALID;
+    return hmm_score_batch_impl(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total, nullptr, seq_codes, n_codes_total, jobs, n_jobs, indel_bias, scores_out);
 }
 
 // profile_hmm_score_set's combination step (ref: src/hmm/nanopolish_profile_hmm.cpp:32-56): host

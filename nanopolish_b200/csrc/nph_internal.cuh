@@ -36,7 +36,7 @@ struct DevModel {
 };
 
 // Device-side view of the models for kernels (array of pointers)
-struct DevModelView { const double* mean; const double* stdv; const double* log_stdv; uint32_t n_states; uint32_t pad; };
+struct DevModelView { const double* mean; const double* stdv; const double* log_stdv; uint32_t n_states; uint16_t k; uint16_t alphabet_size; };
 
 template <typename T>
 struct DevBuf {
@@ -76,6 +76,8 @@ struct nph_ctx {
     // resident HMM jobs
     size_t n_jobs = 0, n_ranks = 0;
     DevBuf<uint32_t> d_ranks;
+    DevBuf<uint8_t> d_codes;         // jobs loaded through the *_seq calls: base codes instead of k-mer ranks (jobs' rank_off index this)
+    bool codes_mode = false;
     DevBuf<nph_hmm_job> d_jobs;
     DevBuf<float2> d_trans;          // per read: (lp_mm_self, lp_mm_next)
     DevBuf<uint32_t> d_order;        // job indices grouped by kernel class, heavy first

@@ -150,6 +150,22 @@ class Engine:
         self.n_jobs = int(jobs.shape[0])
         return out
 
+    def hmm_score_batch_seq(self, reads, ev_mean, ev_start_time, seq_codes, jobs, indel_bias: float = 1.0,
+                            out: np.ndarray | None = None) -> np.ndarray:
+        """the same with base codes instead of k-mer ranks (nph_hmm_score_batch_seq; jobs' rank_off = code offsets)"""
+        if out is None:
+            out = np.empty(jobs.shape[0], np.float32)
+        self._check(self.lib.nph_hmm_score_batch_seq(self.ctx, _p(reads), reads.shape[0], _p(ev_mean), _p(ev_start_time), ev_mean.shape[0],
+                                                     _p(seq_codes), seq_codes.shape[0], _p(jobs), jobs.shape[0], indel_bias, _p(out)),
+                    "nph_hmm_score_batch_seq")
+        self.n_jobs = int(jobs.shape[0])
+        return out
+
+    def hmm_jobs_load_seq(self, seq_codes, jobs, indel_bias: float = 1.0):
+        self._check(self.lib.nph_hmm_jobs_load_seq(self.ctx, _p(seq_codes), seq_codes.shape[0], _p(jobs), jobs.shape[0], indel_bias),
+                    "nph_hmm_jobs_load_seq")
+        self.n_jobs = int(jobs.shape[0])
+
     def score_set_combine(self, scores: np.ndarray, n_alt: int) -> np.ndarray:
         s = np.ascontiguousarray(scores, np.float32)
         g = s.shape[0] // n_alt

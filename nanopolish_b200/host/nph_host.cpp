@@ -344,12 +344,29 @@ size_t format_fixed(char* dst, double v, int prec)
         const uint64_t rem = N & (((uint64_t)1 << sft) - 1), half = (uint64_t)1 << (sft - 1);
         if (rem > half || (rem == half && (q & 1))) q += 1;
     }                                        // sft >= 64: N < 2^63 is below half a unit of the last printed digit
+    char* o = dst;
+    if (bits >> 63) *o++ = '-';
+    if (prec == 2 && q < 4000000000ull) {
+        // the call-methylation / eventalign fast path: constant divisors (multiply-shift), 32-bit arithmetic, two digits at a time
+        static const char kPairs[201] =
+            "0001020304050607080910111213141516171819202122232425262728293031323334353637383940414243444546474849"
+            "5051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+        const uint32_t q32 = (uint32_t)q;
+        uint32_t ip32 = q32 / 100u;
+        const uint32_t fp32 = q32 % 100u;
+        char tmp2[12];
+        int m = 0;
+        while (ip32 >= 100u) { const uint32_t r = ip32 % 100u; ip32 /= 100u; tmp2[m++] = kPairs[2 * r + 1]; tmp2[m++] = kPairs[2 * r]; }
+        if (ip32 >= 10u) { tmp2[m++] = kPairs[2 * ip32 + 1]; tmp2[m++] = kPairs[2 * ip32]; } else tmp2[m++] = (char)('0' + ip32);
+        while (m) *o++ = tmp2[--m];
+        *o++ = '.'; *o++ = kPairs[2 * fp32]; *o++ = kPairs[2 * fp32 + 1];
+        *o = 0;
+        return (size_t)(o - dst);
+    }
     char tmp[32];
     int n = 0;
     uint64_t ip = q / pow10[prec], fp = q % pow10[prec];
     do { tmp[n++] = (char)('0' + ip % 10); ip /= 10; } while (ip);
-    char* o = dst;
-    if (bits >> 63) *o++ = '-';
     while (n) *o++ = tmp[--n];
     if (prec) {
         *o++ = '.';
@@ -445,8 +462,8 @@ size_t HmmBatch::add(const HMMInputSequence& sequence, const HMMInputData& data,
     const int strand_slot = data.rc != 0 ? 1 : 0;
     if (cache.k != k) { cache.off[0] = cache.off[1] = ~(uint64_t)0; cache.k = k; }
     if (cache.off[strand_slot] == ~(uint64_t)0) {
-        cache.off[strand_slot] = m_ranks.size();
-        sequence.append_kmer_ranks(k, data.rc != 0, m_ranks);
+        cache.off[strand_slot] = m_codes.size();
+        sequence.append_codes(data.rc != 0, m_codes);
     }
     nph_hmm_job j;
     j.rank_off = cache.off[strand_slot];
@@ -485,9 +502,34 @@ void HMMInputSequence::append_kmer_ranks(uint32_t k, bool do_rc, std::vector<uin
     }
 }
 
+void HMMInputSequence::append_codes(bool do_rc, std::vector<uint8_t>& out) const
+{
+    const std::string& s = do_rc ? m_rc_seq : m_seq;
+    const size_t base = out.size();
+    out.resize(base + s.size());
+    for (size_t i = 0; i < s.size(); ++i) out[base + i] = m_alphabet->rank(s[i]);
+}
+
+std::vector<uint32_t> HmmBatch::ranks() const
+{
+    std::vector<uint32_t> out(m_codes.size(), 0);
+    for (size_t j = 0; j < m_jobs.size(); ++j) {
+        const nph_hmm_job& jb = m_jobs[j];
+        const uint32_t k = m_job_models[j]->k, A = m_job_models[j]->pmalphabet->size();
+        const uint8_t* cd = m_codes.data() + jb.rank_off;
+        for (uint32_t i = 0; i < jb.n_kmers; ++i) {
+            const uint8_t* km = cd + (jb.rc ? jb.n_kmers - 1 - i : i);
+            uint32_t r = 0;
+            for (uint32_t t = 0; t < k; ++t) r = r * A + km[t];
+            out[jb.rank_off + i] = r;
+        }
+    }
+    return out;
+}
+
 void HmmBatch::append(HmmBatch&& other)
 {
-    const uint64_t rank_base = m_ranks.size();
+    const uint64_t rank_base = m_codes.size();
     std::vector<uint32_t> remap(other.m_reads.size());
     for (size_t i = 0; i < other.m_reads.size(); ++i) {
         auto it = m_read_index.find(other.m_reads[i]);
@@ -499,14 +541,14 @@ void HmmBatch::append(HmmBatch&& other)
     }
     m_jobs.reserve(m_jobs.size() + other.m_jobs.size());
     for (nph_hmm_job j : other.m_jobs) { j.read = remap[j.read]; j.rank_off += rank_base; m_jobs.push_back(j); }
-    m_ranks.insert(m_ranks.end(), other.m_ranks.begin(), other.m_ranks.end());
+    m_codes.insert(m_codes.end(), other.m_codes.begin(), other.m_codes.end());
     m_job_models.insert(m_job_models.end(), other.m_job_models.begin(), other.m_job_models.end());
     other.clear();
 }
 
 void HmmBatch::clear()
 {
-    m_read_index.clear(); m_reads.clear(); m_job_models.clear(); m_jobs.clear(); m_ranks.clear();
+    m_read_index.clear(); m_reads.clear(); m_job_models.clear(); m_jobs.clear(); m_codes.clear();
 }
 
 std::vector<float> HmmBatch::run(Engine& engine, double indel_bias)
@@ -522,9 +564,9 @@ std::vector<float> HmmBatch::run(Engine& engine, double indel_bias)
     std::vector<std::pair<const SquiggleRead*, uint8_t>> rl;
     for (auto& r : m_reads) rl.push_back({r.read, r.strand});
     const detail::FlatReads fr = flatten_reads(engine, rl);
-    engine.check(nph_hmm_score_batch(engine.ctx(), fr.reads.data(), fr.reads.size(), fr.mean, fr.time, fr.n_events,
-                                     m_ranks.data(), m_ranks.size(), m_jobs.data(), m_jobs.size(), indel_bias, scores.data()),
-                 "nph_hmm_score_batch");
+    engine.check(nph_hmm_score_batch_seq(engine.ctx(), fr.reads.data(), fr.reads.size(), fr.mean, fr.time, fr.n_events,
+                                         m_codes.data(), m_codes.size(), m_jobs.data(), m_jobs.size(), indel_bias, scores.data()),
+                 "nph_hmm_score_batch_seq");
     return scores;
 }
 

@@ -302,6 +302,9 @@ public:
 
     // all n = length() - k + 1 ranks get_kmer_rank(0..n-1, k, do_rc) in one rolling pass (appended to out)
     void append_kmer_ranks(uint32_t k, bool do_rc, std::vector<uint32_t>& out) const;
+    // the alphabet ranks of the symbols of the string the strand reads (m_seq, or m_rc_seq with do_rc): what the *_seq calls of
+    // the C ABI take — k-mer i of a job is then the k codes at i, resp. at length - i - k (appended to out)
+    void append_codes(bool do_rc, std::vector<uint8_t>& out) const;
 
 private:
     const Alphabet* m_alphabet;
@@ -384,7 +387,10 @@ public:
     // Lets worker threads enumerate into private batches and the owner splice them in a fixed order.
     void append(HmmBatch&& other);
     const std::vector<nph_hmm_job>& jobs() const { return m_jobs; }
-    const std::vector<uint32_t>& ranks() const { return m_ranks; }
+    // the k-mer ranks of the queued jobs, ranks()[job.rank_off + i] = get_kmer_rank(i, k, rc) — derived from the codes on request
+    // (the batch itself ships one byte per base; for inspection and tests)
+    std::vector<uint32_t> ranks() const;
+    const std::vector<uint8_t>& codes() const { return m_codes; }
 
 private:
     struct ReadKey { const SquiggleRead* read; uint8_t strand; bool operator<(const ReadKey& o) const { return read != o.read ? read < o.read : strand < o.strand; } };
@@ -392,7 +398,7 @@ private:
     std::vector<ReadKey> m_reads;
     std::vector<const PoreModel*> m_job_models;
     std::vector<nph_hmm_job> m_jobs;
-    std::vector<uint32_t> m_ranks;
+    std::vector<uint8_t> m_codes;           // per distinct (sequence, strand): its symbols' alphabet ranks; jobs' rank_off index this
 };
 
 // A batch of adaptive_banded_simple_event_align calls (one per read).

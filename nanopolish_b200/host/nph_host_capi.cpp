@@ -293,35 +293,41 @@ long long nphh_score_variant_group(int n_reads, const int32_t* read, const uint3
 // aligned pairs are (ref_pos, event_idx) interleaved, pair_off[n_reads+1]
 static long long call_methylation_impl(int n_reads, const int32_t* read, const char** read_names, const uint8_t* is_rev, const uint8_t* rc,
                                        const int32_t* ref_start, const char** ref_seqs, const int32_t* pairs, const uint64_t* pair_off,
-                                       const char* contig, double indel_bias, char* tsv_out, size_t cap, uint64_t* n_jobs_out, double* secs3)
+                                       const char* contig, double indel_bias, char* tsv_out, size_t cap, uint64_t* n_jobs_out, double* secs4)
 {
     long long n = -1;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     int st = guard([&] {
-        MethylationCallingParameters params;
-        MethylationCaller caller(params);
-        std::vector<EventAlignedRead> batch_reads;
+        // one caller for the process, cleared between batches: its page-locked staging is allocated once (what a BamProcessor
+        // integration does: one MethylationCaller per worker, a batch per BamProcessor round)
+        static std::unique_ptr<MethylationCaller> caller;
+        if (!caller) { MethylationCallingParameters params; caller.reset(new MethylationCaller(params)); }
+        caller->clear();
+        const double tm = now();
+        // the shim's own marshalling of the test's flat arrays into the caller-side objects (not part of the product path)
+        std::vector<EventAlignedRead> batch_reads((size_t)n_reads);
+#pragma omp parallel for schedule(dynamic, 16) num_threads(host_threads()) if (n_reads > 64)
         for (int i = 0; i < n_reads; ++i) {
-            EventAlignedRead r;
+            EventAlignedRead& r = batch_reads[(size_t)i];
             r.read = g_reads[read[i]].get();
             r.read_name = read_names[i];
             r.is_reverse = is_rev[i];
             r.contig = contig;
             r.ref_start_pos = ref_start[i];
             r.ref_seq = ref_seqs[i];
-            r.aligned_events[0].reserve(pair_off[i + 1] - pair_off[i]);
-            for (uint64_t p = pair_off[i]; p < pair_off[i + 1]; ++p) r.aligned_events[0].push_back(AlignedPair{pairs[2 * p], pairs[2 * p + 1]});
+            const uint64_t np = pair_off[i + 1] - pair_off[i];
+            r.aligned_events[0].resize(np);
+            if (np) std::memcpy(r.aligned_events[0].data(), pairs + 2 * pair_off[i], sizeof(AlignedPair) * np);
             r.rc[0] = rc[i];
-            batch_reads.push_back(std::move(r));
         }
         const double t0 = now();
-        caller.add_reads(batch_reads);
+        caller->add_reads(batch_reads);
         const double t1 = now();
-        caller.run(Engine::thread_default(), indel_bias);
-        *n_jobs_out = caller.num_jobs();
+        caller->run(Engine::thread_default(), indel_bias);
+        *n_jobs_out = caller->num_jobs();
         const double t2 = now();
-        const size_t bytes = caller.tsv_all(tsv_out, cap ? cap - 1 : 0);
-        if (secs3) { secs3[0] = t1 - t0; secs3[1] = t2 - t1; secs3[2] = now() - t2; }
+        const size_t bytes = caller->tsv_all(tsv_out, cap ? cap - 1 : 0);
+        if (secs4) { secs4[0] = t1 - t0; secs4[1] = t2 - t1; secs4[2] = now() - t2; secs4[3] = t0 - tm; }
         if (bytes + 1 > cap) throw Error(NPH_ERR_INVALID, "tsv buffer too small");
         tsv_out[bytes] = 0;
         n = (long long)bytes;
@@ -336,7 +342,7 @@ long long nphh_call_methylation(int n_reads, const int32_t* read, const char** r
     return call_methylation_impl(n_reads, read, read_names, is_rev, rc, ref_start, ref_seqs, pairs, pair_off, contig, indel_bias, tsv_out, cap,
                                  n_jobs_out, nullptr);
 }
-// the same, with the seconds spent in {enumeration, flatten + device call + scatter, TSV formatting}
+// the same, with the seconds spent in {staging (add_reads), flatten + device call, TSV formatting, the shim's own marshalling}: secs4[4]
 long long nphh_call_methylation_timed(int n_reads, const int32_t* read, const char** read_names, const uint8_t* is_rev, const uint8_t* rc,
                                       const int32_t* ref_start, const char** ref_seqs, const int32_t* pairs, const uint64_t* pair_off,
                                       const char* contig, double indel_bias, char* tsv_out, size_t cap, uint64_t* n_jobs_out, double* secs3)
@@ -445,10 +451,11 @@ double nphh_methylation_enumerate_seconds(int n_reads, const int32_t* read, cons
         *n_jobs_out = caller.num_jobs();
         if (jobs_out && ranks_out) {
             const HmmBatch& b = caller.batch();
-            if (b.jobs().size() > cap_jobs || b.ranks().size() > cap_ranks) throw Error(NPH_ERR_INVALID, "dump buffers too small");
+            const std::vector<uint32_t> rk = b.ranks();
+            if (b.jobs().size() > cap_jobs || rk.size() > cap_ranks) throw Error(NPH_ERR_INVALID, "dump buffers too small");
             std::memcpy(jobs_out, b.jobs().data(), sizeof(nph_hmm_job) * b.jobs().size());
-            std::memcpy(ranks_out, b.ranks().data(), sizeof(uint32_t) * b.ranks().size());
-            *n_ranks_out = b.ranks().size();
+            std::memcpy(ranks_out, rk.data(), sizeof(uint32_t) * rk.size());
+            *n_ranks_out = rk.size();
         }
     });
     return secs;
@@ -714,10 +721,11 @@ long long nphh_scorereads(int n_reads, const int32_t* read, const char** ref_seq
         const HmmBatch& b = sr.batch();
         n = (long long)b.jobs().size();
         if (jobs_out && ranks_out) {
-            if (b.jobs().size() > cap_jobs || b.ranks().size() > cap_ranks) throw Error(NPH_ERR_INVALID, "dump buffers too small");
+            const std::vector<uint32_t> rk = b.ranks();
+            if (b.jobs().size() > cap_jobs || rk.size() > cap_ranks) throw Error(NPH_ERR_INVALID, "dump buffers too small");
             std::memcpy(jobs_out, b.jobs().data(), sizeof(nph_hmm_job) * b.jobs().size());
-            std::memcpy(ranks_out, b.ranks().data(), sizeof(uint32_t) * b.ranks().size());
-            *n_ranks_out = b.ranks().size();
+            std::memcpy(ranks_out, rk.data(), sizeof(uint32_t) * rk.size());
+            *n_ranks_out = rk.size();
         }
         if (mode == 1) {
             sr.run(Engine::thread_default());

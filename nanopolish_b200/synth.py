@@ -269,9 +269,11 @@ class HmmJobs:
     scored_events: int        # sum over jobs of DP rows (the metric's unit)
     block_cells: int          # sum over jobs of E*K
     seqs: list | None = None  # optional per-job sequence strings (bytes) for the reference harness
+    seq_codes: np.ndarray | None = None   # u1: per job the alphabet ranks of the string its strand reads (nph_hmm_*_seq)
+    code_jobs: np.ndarray | None = None   # the same jobs with rank_off = offset of the job's first code in seq_codes
 
 
-def _finish_jobs(rows, ranks_list, seqs=None) -> HmmJobs:
+def _finish_jobs(rows, ranks_list, seqs=None, codes_list=None) -> HmmJobs:
     jobs = np.zeros(len(rows), HMM_JOB_DT)
     off = 0
     ev = 0
@@ -284,7 +286,14 @@ def _finish_jobs(rows, ranks_list, seqs=None) -> HmmJobs:
         ev += E
         cells += E * nk
     kr = np.concatenate(ranks_list).astype(np.uint32) if ranks_list else np.zeros(0, np.uint32)
-    return HmmJobs(jobs, kr, ev, cells, seqs)
+    out = HmmJobs(jobs, kr, ev, cells, seqs)
+    if codes_list is not None:
+        cj = jobs.copy()
+        lens = np.array([c.shape[0] for c in codes_list], np.uint64)
+        cj["rank_off"] = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64) if len(codes_list) else np.zeros(0, np.uint64)
+        out.code_jobs = cj
+        out.seq_codes = np.concatenate(codes_list).astype(np.uint8) if codes_list else np.zeros(0, np.uint8)
+    return out
 
 
 _CODE2DNA = np.frombuffer(b"ACGT", np.uint8)
@@ -296,7 +305,7 @@ def scorereads_jobs(rs: ReadSet, events_per_segment: int = 500, model_id: int = 
     bases spanned by the true alignment of the two boundary events, flags 0
     (ref: model_score, src/nanopolish_scorereads.cpp:116-203).  rc_every=n makes every n-th read a
     reverse-strand job (events walked backwards, rc k-mer ranks) to cover stride -1."""
-    rows, ranks_list, seqs = [], [], []
+    rows, ranks_list, seqs, codes_list = [], [], [], []
     k = rs.k
     for r in range(rs.n_reads):
         E = int(rs.reads[r]["n_events"])
@@ -312,6 +321,7 @@ def scorereads_jobs(rs: ReadSet, events_per_segment: int = 500, model_id: int = 
                 if not rc:
                     ranks_list.append(kmer_ranks_from_codes(sub, k, 4))
                     rows.append((r, model_id, e0, e1, 0, 0))
+                    codes_list.append(sub)                          # m_seq
                     if keep_seqs:
                         seqs.append(_CODE2DNA[sub].tobytes())
                 else:
@@ -320,10 +330,11 @@ def scorereads_jobs(rs: ReadSet, events_per_segment: int = 500, model_id: int = 
                     rcsub = (3 - sub[::-1]).astype(np.uint8)
                     ranks_list.append(dna_rc_kmer_ranks(rcsub, k))
                     rows.append((r, model_id, e1, e0, 1, 0))
+                    codes_list.append(sub)                          # m_rc_seq = reverse complement of the HMM sequence = the bases as sequenced
                     if keep_seqs:
                         seqs.append(_CODE2DNA[rcsub].tobytes())
             s += events_per_segment
-    return _finish_jobs(rows, ranks_list, seqs if keep_seqs else None)
+    return _finish_jobs(rows, ranks_list, seqs if keep_seqs else None, codes_list)
 
 
 def abea_jobs(rs: ReadSet) -> tuple[np.ndarray, np.ndarray, int]:
@@ -352,7 +363,7 @@ def methylation_jobs(rs: ReadSet, model_id: int = 0, min_separation: int = 10, m
     -> window = [first-10, last+10] -> two jobs per group (unmethylated, methylated), both over the
     cpg alphabet (ACGMT, 5^6 states), flags PRE|POST clip.  Jobs 2g, 2g+1 are the u/m pair of group g.
     (ref: calculate_methylation_for_read, src/basemods/nanopolish_basemods.cpp:238-457)"""
-    rows, ranks_list, seqs = [], [], []
+    rows, ranks_list, seqs, codes_list = [], [], [], []
     k = rs.k
     flags = HAF_ALLOW_PRE_CLIP | HAF_ALLOW_POST_CLIP
     for r in range(rs.n_reads):
@@ -384,12 +395,13 @@ def methylation_jobs(rs: ReadSet, model_id: int = 0, min_separation: int = 10, m
             for arr in (u, m):
                 ranks_list.append(kmer_ranks_from_codes(arr, k, 5))
                 rows.append((r, model_id, e1, e2, 0, flags))
+                codes_list.append(arr)
                 if keep_seqs:
                     seqs.append(_CODE2CPG[arr].tobytes())
             n_done += 1
             if max_groups_per_read and n_done >= max_groups_per_read:
                 break
-    return _finish_jobs(rows, ranks_list, seqs if keep_seqs else None)
+    return _finish_jobs(rows, ranks_list, seqs if keep_seqs else None, codes_list)
 
 
 def event_params(rna: bool = False) -> np.ndarray:

@@ -13,7 +13,7 @@ HMM_SHAPES = [
 
 
 def random_hmm_jobs(rs, rng, n_jobs, kmin, kmax, emin, emax, flags_choices, model_id=0):
-    rows, ranks, seqs = [], [], []
+    rows, ranks, seqs, codes = [], [], [], []
     for _ in range(n_jobs):
         r = int(rng.integers(0, rs.n_reads))
         E = int(rs.reads[r]["n_events"])
@@ -28,7 +28,7 @@ def random_hmm_jobs(rs, rng, n_jobs, kmin, kmax, emin, emax, flags_choices, mode
         fl = int(rng.choice(flags_choices))
         if rc:
             rcsub = (3 - sub[::-1]).astype(np.uint8)
-            ranks.append(synth.dna_rc_kmer_ranks(rcsub, rs.k)); rows.append((r, model_id, e1, e0, 1, fl)); seqs.append(synth._CODE2DNA[rcsub].tobytes())
+            ranks.append(synth.dna_rc_kmer_ranks(rcsub, rs.k)); rows.append((r, model_id, e1, e0, 1, fl)); seqs.append(synth._CODE2DNA[rcsub].tobytes()); codes.append(sub)
         else:
-            ranks.append(synth.kmer_ranks_from_codes(sub, rs.k, 4)); rows.append((r, model_id, e0, e1, 0, fl)); seqs.append(synth._CODE2DNA[sub].tobytes())
-    return synth._finish_jobs(rows, ranks, seqs)
+            ranks.append(synth.kmer_ranks_from_codes(sub, rs.k, 4)); rows.append((r, model_id, e0, e1, 0, fl)); seqs.append(synth._CODE2DNA[sub].tobytes()); codes.append(sub)
+    return synth._finish_jobs(rows, ranks, seqs, codes)

@@ -223,3 +223,38 @@ def test_streamed_inputs_one_shot_call(engine, models, port_oracle):
         engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, bad, jobs.jobs)
     again = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, jobs.jobs)   # context still usable
     assert np.array_equal(_bits(again), _bits(got))
+
+
+@pytest.mark.parametrize("shape", HMM_SHAPES[:4])
+def test_base_code_form_equals_rank_form(engine, models, shape):
+    """nph_hmm_score_batch_seq (one byte per base, ranks formed in the kernel prologue, both strands) returns the bits of the rank form;
+    the staged form likewise; a code outside the alphabet is refused."""
+    nuc = models["nucleotide"][0]
+    rs = synth.gen_reads(8, 2600, nuc, seed=900 + shape["kmin"], drift=True)
+    rng = np.random.default_rng(shape["kmin"] * 7 + 1)
+    jobs = _random_jobs(rs, rng, shape["n"], shape["kmin"], shape["kmax"], shape["emin"], shape["emax"], [0, 1, 2, 3])
+    rj = jobs.jobs.copy(); rj["model_id"] = models["nucleotide"][1]
+    cj = jobs.code_jobs.copy(); cj["model_id"] = models["nucleotide"][1]
+    a = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, rj, indel_bias=0.9)
+    b = engine.hmm_score_batch_seq(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.seq_codes, cj, indel_bias=0.9)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and (rj["rc"] == 1).any()
+    engine.reads_load(rs.reads, rs.ev_mean, rs.ev_start_time)
+    engine.hmm_jobs_load_seq(jobs.seq_codes, cj, indel_bias=0.9)
+    engine.hmm_score()
+    assert np.array_equal(engine.hmm_scores_fetch().view(np.uint32), a.view(np.uint32))
+    bad = jobs.seq_codes.copy(); bad[int(cj[0]["rank_off"]) + 1] = 4
+    from nanopolish_b200._lib import NphError
+    with pytest.raises(NphError):
+        engine.hmm_score_batch_seq(rs.reads, rs.ev_mean, rs.ev_start_time, bad, cj, indel_bias=0.9)
+
+
+def test_base_code_form_cpg_alphabet(engine, models, port_oracle):
+    """methylated windows over the cpg alphabet (codes 0..4) through the base-code form"""
+    case = make_hmm_cases()["methylation"]
+    rs, jobs = case["rs"], case["jobs"]
+    ids = np.array([models[a][1] for a in case["alphabets"]], np.uint32)
+    rj = jobs.jobs.copy(); rj["model_id"] = ids[jobs.jobs["model_id"]]
+    cj = jobs.code_jobs.copy(); cj["model_id"] = ids[jobs.jobs["model_id"]]
+    a = engine.hmm_score_batch(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.kmer_ranks, rj, indel_bias=case["indel_bias"])
+    b = engine.hmm_score_batch_seq(rs.reads, rs.ev_mean, rs.ev_start_time, jobs.seq_codes, cj, indel_bias=case["indel_bias"])
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and (jobs.seq_codes == 3).any()
