@@ -517,6 +517,25 @@ def run_aux(args, rank, world, local, saved_stdout):
                 "roofline": {"bound": "hbm", "achieved": b_alg / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": b_alg / (t * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel": "abea_kernel",
                              "note": "sequentially dependent bands: issue/latency bound (DESIGN.md section 5)"}}
+        if not args.no_cpu_baseline:
+            # the compiled reference's adaptive_banded_simple_event_align over a bounded sample of the same reads, OpenMP over reads
+            from oracle.oracle_py import RefOracle
+            if RefOracle.available():
+                ro = RefOracle()
+                cores = cpu_threads()
+                ns = int(min(n_reads, max(2 * cores, 64)))
+                h = ro.builtin_model("nucleotide")
+                rh = ro.register_reads(rs.reads[:ns], rs.ev_mean, rs.ev_start_time, h)
+                seqs = [synth._CODE2DNA[c].tobytes() for c in rs.seq_codes[:ns]]
+                caps = [int(j["pairs_cap"]) for j in jobs[:ns]]
+                ro.abea_batch(rh[:8], h, seqs[:8], caps[:8], threads=cores)
+                pr, poff, npairs, secs = ro.abea_batch(rh, h, seqs, caps, threads=cores)
+                pg, rg = eng.abea_fetch()
+                same = all(int(npairs[i]) == int(rg[i]["n_pairs"]) for i in range(ns))
+                line["cpu_baseline"] = {"value": int(rs.reads["n_events"][:ns].sum()) / secs, "unit": "events/s", "cores": cores, "cpu_quota": cpu_quota(),
+                                        "kind": "reference", "seconds": secs, "same_pair_counts": bool(same),
+                                        "sample": f"{ns} of the {n_reads} reads through the compiled reference's adaptive_banded_simple_event_align, "
+                                                  f"OpenMP over reads with {cores} threads"}
     elif args.workload == "eventalign":
         n_reads = min(args.reads, 4736)
         rs = synth.gen_reads(n_reads, args.events, nuc, seed=42)

@@ -410,6 +410,58 @@ int nph_methylation_fetch(nph_ctx* ctx, uint64_t* site_off_out, nph_meth_site* s
  * driver gathering every rank's records with NCCL — without a host hop. */
 int nph_methylation_sites_dev(nph_ctx* ctx, const nph_meth_site** sites_dev_out, uint64_t* n_sites_out);
 
+/* ---- variants: candidate screening on the device (section 8f N2, BASELINE configs[4]) -----------------------------
+ * generate_candidate_single_base_edits (src/nanopolish_call_variants.cpp:288-361) for a reference region: at every position i
+ * the window [i - flank, i + 1 + flank] (22 bases for flank 10), up to nine candidate edits of base i — for j in ACGT order
+ * the substitution to j and the insertion of j behind it (both skipped when j is the reference base), then the deletion of
+ * base i (skipped when it equals base i - 1) — each scored with score_variant_thresholded
+ * (src/common/nanopolish_variant.cpp:765-799): over the event sequences of the window
+ * (AlignmentDB::get_event_subsequences, src/alignment/nanopolish_alignment_db.cpp:172-221: every record whose event alignment
+ * bounds the window, event span below 20 events per base), in record order,
+ *     if (fabs(total) < score_threshold) total += profile_hmm_score_set(variant) - profile_hmm_score_set(base)
+ * — the reference's single-thread semantics (its `omp parallel for` makes the exit point racy).  The early exit is honoured
+ * in the work done: reads are scored reads_per_round at a time, and only candidates whose total is still inside the
+ * threshold get jobs in the next round (a candidate that leaves it mid-round ignores the rest of that round, exactly like the
+ * sequential loop).  Window enumeration, the k-mer ranks of the ten sequences per position and strand, job emission, the
+ * forward scores and the accumulation all run on the device; the host drives the rounds (one count read-back per round).
+ * No methylation alternatives (opt::methylation_types empty, the default).
+ * Records: nph_meth_record with ref_off = offset of the record's compact event alignment in event_deltas[] (ref_len entries,
+ * entry o <-> reference position ref_start_pos + o; NPH_METH_NO_PAIR / steps as in nph_methylation_batch_compact),
+ * pair_off / n_pairs unused, model_id = the read's base model.  Record order = AlignmentDB's m_event_records order.
+ * ref_bases: the region's reference, ref_bases[p] = base at position region_start + p, n_ref_bases = region_end - region_start + 1
+ * (AlignmentDB's m_region_start .. m_region_end inclusive); positions screened: region_start .. region_end - 1. */
+#define NPH_SCREEN_SLOTS 9          /* per position: j = 0..3 (ACGT): slot 2j = substitution to j, 2j + 1 = insertion of j; slot 8 = deletion */
+typedef struct {
+    int32_t  flank;               /* opt::screen_flanking_sequence (10); the window must fit NPH_SCREEN_MAX_WINDOW */
+    uint32_t score_threshold;     /* opt::screen_score_threshold (100) */
+    uint32_t alignment_flags;     /* NPH_HAF_* handed to profile_hmm_score_set */
+    uint32_t k;                   /* k of the reads' base model (nucleotide alphabet) */
+    uint32_t reads_per_round;     /* reads of a position scored between two early-exit tests (8) */
+    int32_t  region_start;        /* m_region_start */
+} nph_screen_params;
+#define NPH_SCREEN_MAX_WINDOW 64
+/* qualities_out: NPH_SCREEN_SLOTS doubles per screened position (position region_start + p at p * NPH_SCREEN_SLOTS): the
+ * Variant::quality score_variant_thresholded returns; NaN for a candidate the reference does not generate (j == reference base,
+ * redundant deletion) and for positions whose window leaves the region (are_coordinates_valid fails: the reference skips them).
+ * n_reads_out (optional): event sequences per position.  n_scored_events_out (optional): DP rows scored in all rounds. */
+int nph_screen_edits_batch(nph_ctx* ctx,
+                           const nph_read* reads, size_t n_reads,
+                           const float* ev_mean, const double* ev_start_time, size_t n_events_total,
+                           const char* ref_bases, size_t n_ref_bases,
+                           const int16_t* event_deltas, size_t n_deltas_total, const int32_t* first_event,
+                           const nph_meth_record* records, size_t n_records,
+                           const nph_screen_params* params, double indel_bias,
+                           double* qualities_out, uint32_t* n_reads_out, uint64_t* n_scored_events_out);
+/* Staged form (reads resident): load, run (all rounds; asynchronous device work between the per-round read-backs), fetch. */
+int nph_screen_load(nph_ctx* ctx, const char* ref_bases, size_t n_ref_bases, const int16_t* event_deltas, size_t n_deltas_total,
+                    const int32_t* first_event, const nph_meth_record* records, size_t n_records,
+                    const nph_screen_params* params, double indel_bias);
+int nph_screen_run(nph_ctx* ctx);
+/* counters of the most recent nph_screen_run: rounds, forward jobs, scored events (DP rows), and what scoring every read of
+ * every candidate (no early exit) would have cost in jobs */
+int nph_screen_counts(nph_ctx* ctx, uint32_t* n_rounds_out, uint64_t* n_jobs_out, uint64_t* n_scored_events_out, uint64_t* n_jobs_without_exit_out);
+int nph_screen_fetch(nph_ctx* ctx, double* qualities_out, uint32_t* n_reads_out);
+
 /* ---- event detection (section 8f N4: the step before ABEA) --------------------------------------
  * scrappie's detect_events as load_from_raw calls it: t-statistics over two windows on prefix sums, a short/long
  * peak detector, events between consecutive boundaries.

@@ -480,6 +480,16 @@ static int meth_load(nph_ctx* ctx, const char* ref_bases, size_t n_ref_total,
     return NPH_OK;
 }
 
+int nph_expand_event_maps(nph_ctx* ctx, const int16_t* d_deltas, const int32_t* d_first_event, const nph_meth_record* d_records, uint32_t n_records,
+                          int32_t* d_dense, int32_t* d_first_valid)
+{
+    if (n_records == 0) return NPH_OK;
+    const int grid = (int)std::min<size_t>(((size_t)n_records + kWarps - 1) / kWarps, (size_t)ctx->sm_count * 8);
+    meth_expand_kernel<<<grid, kThreads, 0, ctx->stream>>>(d_deltas, d_first_event, d_records, n_records, d_dense, d_first_valid);
+    NPH_CUDA(ctx, cudaGetLastError());
+    return NPH_OK;
+}
+
 extern "C" int nph_methylation_load(nph_ctx* ctx, const char* ref_bases, size_t n_ref_total,
                                     const nph_aligned_pair* aligned_events, size_t n_pairs_total,
                                     const nph_meth_record* records, size_t n_records,

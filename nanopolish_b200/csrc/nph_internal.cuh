@@ -127,6 +127,24 @@ struct nph_ctx {
         std::vector<uint64_t> h_prov_off;
     } meth;
 
+    // resident variant-screening batch (variants.cu)
+    struct ScreenState {
+        bool loaded = false, ran = false;
+        nph_screen_params params{};
+        double indel_bias = 1.0;
+        size_t n_pos = 0, n_records = 0, n_ref = 0, n_deltas = 0;
+        uint32_t n_rounds = 0;
+        uint64_t n_jobs = 0, n_scored_events = 0, n_jobs_no_exit = 0;
+        DevBuf<uint8_t> d_ref;
+        DevBuf<uint16_t> d_deltas;
+        DevBuf<uint32_t> d_dense;          // event index per reference base of every record, then first_event, first valid
+        DevBuf<nph_meth_record> d_records;
+        DevBuf<uint64_t> d_pos_off;        // n_pos + 1: where each position's bounded reads start
+        DevBuf<uint8_t> d_pos_reads;       // {record, e1, e2} per bounded read
+        DevBuf<uint8_t> d_state;           // per position: totals (9 doubles), alive mask, reads done, valid mask
+        DevBuf<uint64_t> d_job_off;        // per position: first job of the round (+ totals)
+    } screen;
+
     // measurement
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // side streams so that the tail of one forward class overlaps the head of the next (fork/join by events)
@@ -166,6 +184,9 @@ int nph_launch_abea(nph_ctx* ctx);
 int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uint32_t* max_E_out);
 // per-read (lp_mm_self, lp_mm_next) of the resident reads into ctx->d_trans (host libm, like calculate_transitions)
 int nph_upload_read_transitions(nph_ctx* ctx, double indel_bias);
+// compact event alignments -> event index per reference base (methylation.cu): dense[ref_off + o] (INT32_MIN: no entry), first_valid[record]
+int nph_expand_event_maps(nph_ctx* ctx, const int16_t* d_deltas, const int32_t* d_first_event, const nph_meth_record* d_records, uint32_t n_records,
+                          int32_t* d_dense, int32_t* d_first_valid);
 extern "C" {   // defined inside nph_api.cu's extern "C" block (internal all the same: not in include/nph.h)
 // validate + classify + schedule the n_jobs jobs already sitting in ctx->d_jobs / d_ranks (one stream sync), size the scratch
 int nph_jobs_schedule(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total);

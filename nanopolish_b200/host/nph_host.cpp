@@ -420,7 +420,9 @@ FlatReads flatten_reads(Engine& engine, const std::vector<std::pair<const Squigg
         const SquiggleScalings& s = sr->scalings[st];
         o.scale = s.scale; o.shift = s.shift; o.drift = s.drift; o.var = s.var; o.log_var = s.log_var;
         o.events_per_base = sr->events_per_base[st];
-        for (size_t e = 0; e < ev.size(); ++e) mean[off + e] = ev[e].mean;
+        const std::vector<float>& cache = sr->event_mean_cache[st];
+        if (cache.size() == ev.size() && !ev.empty()) std::memcpy(mean + off, cache.data(), sizeof(float) * ev.size());
+        else for (size_t e = 0; e < ev.size(); ++e) mean[off + e] = ev[e].mean;
         if (time) for (size_t e = 0; e < ev.size(); ++e) time[off + e] = ev[e].start_time;
     }
     return fr;

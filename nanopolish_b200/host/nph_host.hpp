@@ -252,6 +252,17 @@ public:
     uint32_t read_id = 0;
     std::string read_sequence;
     std::vector<SquiggleEvent> events[2];
+    // contiguous copy of events[strand][*].mean (what the device consumes), so that batching a read is one memcpy instead of a
+    // strided gather over 24-byte SquiggleEvents; valid while its size equals events[strand].size() — nph::load_from_raw fills it,
+    // cache_event_means() refreshes it, code that edits event means afterwards must call it again (or clear the cache)
+    std::vector<float> event_mean_cache[2];
+    void cache_event_means()
+    {
+        for (int st = 0; st < 2; ++st) {
+            event_mean_cache[st].resize(events[st].size());
+            for (size_t i = 0; i < events[st].size(); ++i) event_mean_cache[st][i] = events[st][i].mean;
+        }
+    }
     SquiggleScalings scalings[2];
     const PoreModel* base_model[2];
     std::map<std::string, const PoreModel*> alt_models[2];   // alphabet name -> model (cpg, dam, ...)

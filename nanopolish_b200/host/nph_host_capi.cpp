@@ -118,6 +118,7 @@ int nphh_read_create(uint32_t n_events, const float* mean, const double* start_t
     sr->events_per_base[0] = events_per_base;
     sr->events[0].resize(n_events);
     for (uint32_t i = 0; i < n_events; ++i) sr->events[0][i] = SquiggleEvent{mean[i], 1.0f, start_time[i], 0.0f, 0.0f};
+    sr->cache_event_means();
     g_reads.push_back(std::move(sr));
     return (int)g_reads.size() - 1;
 }

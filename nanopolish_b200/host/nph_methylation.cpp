@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <thread>
 
 namespace nph {
 
@@ -657,30 +658,18 @@ size_t MethylationCaller::tsv_all(char* out, size_t cap) const
 }
 
 // The whole of call-methylation for a batch that already sits in flat host buffers (the layout of nph_methylation_batch):
-// one device call, then the TSV rows formatted by host_threads() workers straight from the site records.
-size_t call_methylation_flat(Engine& engine, const FlatMethylationBatch& b, const MethylationCallingParameters& params, uint32_t k,
-                             double indel_bias, char* tsv_out, size_t cap, FlatMethylationStats* stats)
+// device call(s), then the TSV rows formatted by host_threads() workers straight from the site records.  A large batch whose
+// records map one-to-one onto its reads is cut into four sub-batches and pipelined: while the device scores sub-batch i + 1
+// (the calling thread sits in the driver), the workers format the rows of sub-batch i — the two stages cost about the same,
+// so the batch takes roughly max(device, TSV) + a quarter of each instead of their sum.
+namespace {
+void format_records(const FlatMethylationBatch& b, uint32_t k, size_t rec_lo, size_t rec_hi, const uint64_t* site_off /* relative to rec_lo */,
+                    const nph_meth_site* sites, std::vector<RowBuffer>& parts)
 {
-    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t0 = now();
-    const nph_meth_params mp = make_meth_params(params, k, b.region_start, b.region_end);
-    size_t site_cap = 0;
-    for (size_t r = 0; r < b.n_records; ++r) site_cap += b.records[r].ref_len / (size_t)(params.min_separation + 1) + 2;
-    nph_meth_site* sites = static_cast<nph_meth_site*>(engine.pinned(3, sizeof(nph_meth_site) * std::max<size_t>(site_cap, 1)));
-    std::vector<uint64_t> site_off(b.n_records + 1, 0);
-    uint64_t scored = 0;
-    if (b.event_deltas)
-        engine.check(nph_methylation_batch_compact(engine.ctx(), b.reads, b.n_reads, b.ev_mean, b.ev_start_time, b.n_events, b.ref_bases, b.event_deltas,
-                                                   b.n_ref, b.first_event, b.records, b.n_records, &mp, indel_bias, site_off.data(), sites, site_cap, &scored),
-                     "nph_methylation_batch_compact");
-    else
-        engine.check(nph_methylation_batch(engine.ctx(), b.reads, b.n_reads, b.ev_mean, b.ev_start_time, b.n_events, b.ref_bases, b.n_ref,
-                                           b.aligned_events, b.n_pairs, b.records, b.n_records, &mp, indel_bias, site_off.data(), sites, site_cap, &scored),
-                     "nph_methylation_batch");
-    const double t1 = now();
-    const size_t n = b.n_records;
+    const size_t n = rec_hi - rec_lo;
     const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), (n + 63) / 64));
-    std::vector<RowBuffer> parts((size_t)T);
+    parts.clear();
+    parts.resize((size_t)T);
     const std::string contig(b.contig ? b.contig : "");
 #pragma omp parallel for schedule(static, 1) num_threads(T) if (T > 1)
     for (int t = 0; t < T; ++t) {
@@ -688,21 +677,97 @@ size_t call_methylation_flat(Engine& engine, const FlatMethylationBatch& b, cons
         RowBuffer& out = parts[t];
         out.room((size_t)(site_off[hi] - site_off[lo]) * 96 + 64);
         for (size_t r = lo; r < hi; ++r) {
-            const nph_meth_record& rec = b.records[r];
-            const char* name = b.read_names[r];
-            put_single_strand_rows(out, contig, b.is_reverse[r] != 0, name, std::strlen(name), b.ref_bases + rec.ref_off, rec.ref_len, rec.ref_start_pos, k,
-                                   rec.strand, sites + site_off[r], (size_t)(site_off[r + 1] - site_off[r]));
+            const nph_meth_record& rec = b.records[rec_lo + r];
+            const char* name = b.read_names[rec_lo + r];
+            put_single_strand_rows(out, contig, b.is_reverse[rec_lo + r] != 0, name, std::strlen(name), b.ref_bases + rec.ref_off, rec.ref_len,
+                                   rec.ref_start_pos, k, rec.strand, sites + site_off[r], (size_t)(site_off[r + 1] - site_off[r]));
         }
     }
-    std::vector<size_t> off((size_t)T + 1, 0);
-    for (int t = 0; t < T; ++t) off[t + 1] = off[t] + parts[t].n;
-    if (stats) { stats->n_sites = site_off[n]; stats->scored_events = scored; }
-    if (tsv_out && off[T] <= cap) {
-#pragma omp parallel for schedule(static, 1) num_threads(T) if (T > 1)
-        for (int t = 0; t < T; ++t) if (parts[t].n) std::memcpy(tsv_out + off[t], parts[t].p.get(), parts[t].n);
+}
+} // namespace
+
+size_t call_methylation_flat(Engine& engine, const FlatMethylationBatch& b, const MethylationCallingParameters& params, uint32_t k,
+                             double indel_bias, char* tsv_out, size_t cap, FlatMethylationStats* stats)
+{
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    const nph_meth_params mp = make_meth_params(params, k, b.region_start, b.region_end);
+    const size_t n = b.n_records;
+    // sub-batches need records i <-> reads i with events and (compact) alignments laid out in that order
+    bool identity = b.event_deltas != nullptr && n == b.n_reads && n >= 2048;
+    for (size_t r = 0; identity && r < n; ++r)
+        identity = b.records[r].read == r && (r == 0 || (b.reads[r].event_off == b.reads[r - 1].event_off + b.reads[r - 1].n_events &&
+                                                         b.records[r].ref_off == b.records[r - 1].ref_off + b.records[r - 1].ref_len));
+    const size_t n_chunks = identity ? 4 : 1;
+    std::vector<size_t> cut(n_chunks + 1);
+    for (size_t c = 0; c <= n_chunks; ++c) cut[c] = n * c / n_chunks;
+    std::vector<size_t> site_cap(n_chunks, 0);
+    size_t site_cap_total = 0;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        for (size_t r = cut[c]; r < cut[c + 1]; ++r) site_cap[c] += b.records[r].ref_len / (size_t)(params.min_separation + 1) + 2;
+        site_cap_total += site_cap[c];
     }
-    if (stats) { stats->device_seconds = t1 - t0; stats->tsv_seconds = now() - t1; }
-    return off[T];
+    nph_meth_site* sites = static_cast<nph_meth_site*>(engine.pinned(3, sizeof(nph_meth_site) * std::max<size_t>(site_cap_total, 1)));
+    std::vector<std::vector<uint64_t>> site_off(n_chunks);
+    std::vector<std::vector<RowBuffer>> parts(n_chunks);
+    std::vector<nph_read> sub_reads;
+    std::vector<nph_meth_record> sub_recs;
+    uint64_t scored_total = 0, sites_total = 0;
+    double device_s = 0.0;
+    std::string error;
+    std::thread formatter;
+    size_t site_base = 0;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        const size_t lo = cut[c], hi = cut[c + 1], m = hi - lo;
+        site_off[c].assign(m + 1, 0);
+        uint64_t scored = 0;
+        const double td = now();
+        int rc;
+        if (n_chunks == 1) {
+            rc = b.event_deltas
+                ? nph_methylation_batch_compact(engine.ctx(), b.reads, b.n_reads, b.ev_mean, b.ev_start_time, b.n_events, b.ref_bases, b.event_deltas,
+                                                b.n_ref, b.first_event, b.records, n, &mp, indel_bias, site_off[c].data(), sites, site_cap_total, &scored)
+                : nph_methylation_batch(engine.ctx(), b.reads, b.n_reads, b.ev_mean, b.ev_start_time, b.n_events, b.ref_bases, b.n_ref,
+                                        b.aligned_events, b.n_pairs, b.records, n, &mp, indel_bias, site_off[c].data(), sites, site_cap_total, &scored);
+        } else {
+            // the sub-batch's slices of the event, reference and alignment arrays, offsets rebased to the slice
+            const uint64_t ev0 = b.reads[lo].event_off, ref0 = b.records[lo].ref_off;
+            const uint64_t ev1 = b.reads[hi - 1].event_off + b.reads[hi - 1].n_events, ref1 = b.records[hi - 1].ref_off + b.records[hi - 1].ref_len;
+            sub_reads.assign(b.reads + lo, b.reads + hi);
+            sub_recs.assign(b.records + lo, b.records + hi);
+            for (size_t i = 0; i < m; ++i) { sub_reads[i].event_off -= ev0; sub_recs[i].ref_off -= ref0; sub_recs[i].read = (uint32_t)i; }
+            rc = nph_methylation_batch_compact(engine.ctx(), sub_reads.data(), m, b.ev_mean + ev0, b.ev_start_time ? b.ev_start_time + ev0 : nullptr,
+                                               (size_t)(ev1 - ev0), b.ref_bases + ref0, b.event_deltas + ref0, (size_t)(ref1 - ref0), b.first_event + lo,
+                                               sub_recs.data(), m, &mp, indel_bias, site_off[c].data(), sites + site_base, site_cap[c], &scored);
+        }
+        device_s += now() - td;
+        if (formatter.joinable()) formatter.join();
+        engine.check(rc, b.event_deltas ? "nph_methylation_batch_compact" : "nph_methylation_batch");
+        scored_total += scored; sites_total += site_off[c][m];
+        const nph_meth_site* chunk_sites = sites + site_base;
+        // (the site records of a sub-batch carry sub-batch record numbers; the formatter only needs them per record, by offset)
+        formatter = std::thread([&, c, lo, hi, chunk_sites] {
+            try { format_records(b, k, lo, hi, site_off[c].data(), chunk_sites, parts[c]); }
+            catch (const std::exception& ex) { error = ex.what(); }
+        });
+        site_base += site_cap[c];
+    }
+    if (formatter.joinable()) formatter.join();
+    if (!error.empty()) throw Error(NPH_ERR_INVALID, error);
+    const double t1 = now();
+    size_t total = 0;
+    std::vector<std::pair<const RowBuffer*, size_t>> pieces;
+    for (size_t c = 0; c < n_chunks; ++c) for (const RowBuffer& rb : parts[c]) { pieces.push_back({&rb, total}); total += rb.n; }
+    if (stats) { stats->n_sites = sites_total; stats->scored_events = scored_total; }
+    if (tsv_out && total <= cap) {
+#pragma omp parallel for schedule(static, 1) num_threads(host_threads()) if (pieces.size() > 1)
+        for (long long i = 0; i < (long long)pieces.size(); ++i)
+            if (pieces[(size_t)i].first->n) std::memcpy(tsv_out + pieces[(size_t)i].second, pieces[(size_t)i].first->p.get(), pieces[(size_t)i].first->n);
+    }
+    // device_seconds: time inside the device calls (the formatter of the previous sub-batch runs concurrently); tsv_seconds: what the
+    // formatting added on top — the last sub-batch's rows and the final copy
+    if (stats) { stats->device_seconds = device_s; stats->tsv_seconds = (now() - t0) - device_s; (void)t1; }
+    return total;
 }
 
 void MethylationCaller::write_tsv(FILE* fp, size_t read_idx) const

@@ -151,6 +151,7 @@ std::vector<std::unique_ptr<SquiggleRead>> load_from_raw(Engine& engine, const P
             const size_t g = off[t] + e;
             sr.events[0][e] = SquiggleEvent{mean[g], stdv[g], start[g], dur[g], logf(stdv[g])};
         }
+        sr.event_mean_cache[0].assign(mean.begin() + (long)off[t], mean.begin() + (long)(off[t] + ne));        // the contiguous copy batching reads from (nph_host.hpp)
     }
     if (stats) *stats = st;
     return reads;

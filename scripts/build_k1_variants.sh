@@ -2,7 +2,7 @@
 # A/B builds of K1's row update (development aid): libnph_<name>.so under nanopolish_b200/csrc/build/variants/
 set -e
 cd "$(dirname "$0")/../nanopolish_b200/csrc"
-SRCS="nph_api.cu hmm_schedule.cu hmm_forward.cu hmm_forward_w4.cu hmm_forward_w8.cu hmm_forward_w16.cu hmm_forward_w32.cu hmm_forward_w32c.cu hmm_viterbi.cu eventalign_chain.cu abea.cu event_detect.cu squiggle_prep.cu load_from_raw.cu methylation.cu"
+SRCS="nph_api.cu hmm_schedule.cu hmm_forward.cu hmm_forward_w4.cu hmm_forward_w8.cu hmm_forward_w16.cu hmm_forward_w32.cu hmm_forward_w32c.cu hmm_viterbi.cu eventalign_chain.cu abea.cu event_detect.cu squiggle_prep.cu load_from_raw.cu methylation.cu variants.cu"
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC"
 build() {   # name, extra flags
   local name=$1; shift
