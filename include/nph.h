@@ -457,9 +457,13 @@ int nph_screen_load(nph_ctx* ctx, const char* ref_bases, size_t n_ref_bases, con
                     const int32_t* first_event, const nph_meth_record* records, size_t n_records,
                     const nph_screen_params* params, double indel_bias);
 int nph_screen_run(nph_ctx* ctx);
-/* counters of the most recent nph_screen_run: rounds, forward jobs, scored events (DP rows), and what scoring every read of
- * every candidate (no early exit) would have cost in jobs */
-int nph_screen_counts(nph_ctx* ctx, uint32_t* n_rounds_out, uint64_t* n_jobs_out, uint64_t* n_scored_events_out, uint64_t* n_jobs_without_exit_out);
+/* counters of the most recent nph_screen_run: rounds; forward jobs and scored events (DP rows) actually run; what scoring every
+ * read of every candidate (no early exit) would have cost in jobs (valid after nph_screen_fetch); and the DP rows the reference's
+ * own loop scores for the same result — base and variant sequence per (candidate, read) until the candidate's total leaves the
+ * threshold — the unit in which this workload's throughput is compared with the CPU arm (here the base haplotype of a read is
+ * scored once per round for all its candidates, the reference scores it once per candidate) */
+int nph_screen_counts(nph_ctx* ctx, uint32_t* n_rounds_out, uint64_t* n_jobs_out, uint64_t* n_scored_events_out, uint64_t* n_jobs_without_exit_out,
+                      uint64_t* n_reference_events_out);
 int nph_screen_fetch(nph_ctx* ctx, double* qualities_out, uint32_t* n_reads_out);
 
 /* ---- event detection (section 8f N4: the step before ABEA) --------------------------------------

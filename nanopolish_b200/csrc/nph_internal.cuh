@@ -134,7 +134,7 @@ struct nph_ctx {
         double indel_bias = 1.0;
         size_t n_pos = 0, n_records = 0, n_ref = 0, n_deltas = 0;
         uint32_t n_rounds = 0;
-        uint64_t n_jobs = 0, n_scored_events = 0, n_jobs_no_exit = 0;
+        uint64_t n_jobs = 0, n_scored_events = 0, n_jobs_no_exit = 0, n_reference_events = 0;
         DevBuf<uint8_t> d_ref;
         DevBuf<uint16_t> d_deltas;
         DevBuf<uint32_t> d_dense;          // event index per reference base of every record, then first_event, first valid

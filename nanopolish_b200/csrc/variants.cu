@@ -33,7 +33,6 @@ namespace {
 
 constexpr int kNoEvent = INT32_MIN;
 constexpr int kSeqs = NPH_SCREEN_SLOTS + 1;      // nine candidates + the base haplotype (slot 9)
-constexpr int kMaxRanks = NPH_SCREEN_MAX_WINDOW; // rank slots per (position, sequence, strand)
 constexpr int kBlock = 256;
 constexpr int kListCap = 2048;                   // records overlapping one block of positions, kept in shared memory
 
@@ -51,6 +50,7 @@ struct VarDev {
     int flank, region_start, n_pos, n_ref, k, rpr;
     uint32_t flags, threshold;
     int win;              // 2 * flank + 2
+    int stride;           // rank slots per (position, sequence, strand): the insertion's win + 1 - k + 1 k-mers
 };
 
 // first offset >= from with an event-alignment entry (n: none)
@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(kBlock) var_ranks_kernel(const VarDev d, const
     for (int t = 0; t < d.win; ++t) w[t] = dna_code(ref[cs - d.region_start + t]);
     const int L = edited_window(w, d.win, d.flank, seq, sq);
     const int nk = L - d.k + 1;
-    uint32_t* fw = pool + ((size_t)pi * kSeqs + seq) * 2 * kMaxRanks;
-    uint32_t* rc = fw + kMaxRanks;
+    uint32_t* fw = pool + ((size_t)pi * kSeqs + seq) * 2 * d.stride;
+    uint32_t* rc = fw + d.stride;
     for (int q = 0; q < nk; ++q) {
         uint32_t rf = 0, rr = 0;
         for (int t = 0; t < d.k; ++t) {
@@ -263,7 +263,7 @@ __global__ void var_emit_kernel(const VarDev d, const PosState* __restrict__ sta
                 for (int seq = NPH_SCREEN_SLOTS; ; ) {
                     const int L = seq == NPH_SCREEN_SLOTS ? d.win : (seq == 8 ? d.win - 1 : ((seq & 1) ? d.win + 1 : d.win));
                     jb.n_kmers = (uint32_t)(L - d.k + 1);
-                    jb.rank_off = ((uint64_t)pi * kSeqs + (uint64_t)seq) * 2 * kMaxRanks + (R.rc ? kMaxRanks : 0);
+                    jb.rank_off = ((uint64_t)pi * kSeqs + (uint64_t)seq) * 2 * d.stride + (R.rc ? d.stride : 0);
                     *out++ = jb;
                     ev += E;
                     if (seq == NPH_SCREEN_SLOTS) seq = -1;
@@ -279,22 +279,30 @@ __global__ void var_emit_kernel(const VarDev d, const PosState* __restrict__ sta
 }
 
 __global__ void var_accumulate_kernel(const VarDev d, PosState* __restrict__ state, const uint64_t* __restrict__ job_off,
-                                      const float* __restrict__ scores, unsigned int* __restrict__ any_left, const uint64_t* __restrict__ pos_off)
+                                      const float* __restrict__ scores, unsigned int* __restrict__ any_left, const uint64_t* __restrict__ pos_off,
+                                      const PosRead* __restrict__ pos_reads, unsigned long long* __restrict__ ref_events)
 {
     const int pi = blockIdx.x * blockDim.x + threadIdx.x;
     if (pi >= d.n_pos) return;
     PosState st = state[pi];
     if (!st.chunk) return;
     const float* s = scores + job_off[pi];
+    const PosRead* rd = pos_reads + pos_off[pi] + st.done;
     const double thr = (double)d.threshold;
+    unsigned long long ref_ev = 0;
     for (uint32_t r = 0; r < st.chunk; ++r) {
         const double base_score = (double)*s++;                 // double base_score = profile_hmm_score_set(...) (a float)
+        const unsigned long long E = (unsigned long long)(rd[r].e1 > rd[r].e2 ? rd[r].e1 - rd[r].e2 : rd[r].e2 - rd[r].e1) + 1ull;
         for (int c = 0; c < NPH_SCREEN_SLOTS; ++c) {
             if (!((st.alive >> c) & 1u)) continue;
             const double variant_score = (double)*s++;
-            if (fabs(st.total[c]) < thr) st.total[c] = __dadd_rn(st.total[c], __dsub_rn(variant_score, base_score));
+            if (fabs(st.total[c]) < thr) {
+                st.total[c] = __dadd_rn(st.total[c], __dsub_rn(variant_score, base_score));
+                ref_ev += 2ull * E;                              // what the reference's loop scores here: the base AND the variant sequence
+            }
         }
     }
+    if (ref_ev) atomicAdd(ref_events, ref_ev);
     st.done += st.chunk;
     uint32_t alive = 0;
     for (int c = 0; c < NPH_SCREEN_SLOTS; ++c) if (((st.alive >> c) & 1u) && fabs(st.total[c]) < thr) alive |= 1u << c;
@@ -322,6 +330,7 @@ int make_dev(nph_ctx* ctx, const nph_screen_params& p, size_t n_ref, VarDev& d)
     d.flank = p.flank; d.region_start = p.region_start; d.n_ref = (int)n_ref; d.n_pos = (int)n_ref - 1;
     d.k = (int)p.k; d.rpr = (int)p.reads_per_round; d.flags = p.alignment_flags; d.threshold = p.score_threshold;
     d.win = 2 * p.flank + 2;
+    d.stride = d.win + 1 - d.k + 1;
     return NPH_OK;
 }
 
@@ -367,7 +376,7 @@ extern "C" int nph_screen_run(nph_ctx* ctx)
     if (!ctx) return NPH_ERR_INVALID;
     nph_ctx::ScreenState& m = ctx->screen;
     if (!m.loaded || !ctx->reads_loaded) return NPH_ERR_STATE;
-    m.ran = false; m.n_rounds = 0; m.n_jobs = 0; m.n_scored_events = 0; m.n_jobs_no_exit = 0;
+    m.ran = false; m.n_rounds = 0; m.n_jobs = 0; m.n_scored_events = 0; m.n_jobs_no_exit = 0; m.n_reference_events = 0;
     NPH_CUDA(ctx, cudaSetDevice(ctx->device));
     VarDev d;
     NPH_TRY(make_dev(ctx, m.params, m.n_ref, d));
@@ -394,9 +403,9 @@ extern "C" int nph_screen_run(nph_ctx* ctx)
     var_bounds_kernel<true><<<pgrid, kBlock, 0, st>>>(d, m.d_records.p, n_rec, dense, first_valid, nullptr, m.d_pos_off.p, pos_reads);
     NPH_CUDA(ctx, cudaGetLastError());
     // rank pool (K1's d_ranks for this batch) and position state
-    const size_t pool = (size_t)n_pos * kSeqs * 2 * kMaxRanks;
+    const size_t pool = (size_t)n_pos * kSeqs * 2 * (size_t)d.stride;
     NPH_TRY(nph_reserve(ctx, ctx->d_ranks, pool));
-    NPH_TRY(nph_reserve(ctx, m.d_state, sizeof(PosState) * (size_t)n_pos + 64));
+    NPH_TRY(nph_reserve(ctx, m.d_state, sizeof(PosState) * (size_t)n_pos + 64));      // + the counters: our DP rows, a flag, the reference's DP rows
     PosState* state = reinterpret_cast<PosState*>(m.d_state.p);
     NPH_CUDA(ctx, cudaMemsetAsync(ctx->d_ranks.p, 0, sizeof(uint32_t) * pool, st));
     const long long n_thr = (long long)n_pos * kSeqs;
@@ -408,7 +417,7 @@ extern "C" int nph_screen_run(nph_ctx* ctx)
     // counted on the host side from the totals: sum over positions of reads x (1 + candidates) — filled at the end from the state
     unsigned long long* d_events = reinterpret_cast<unsigned long long*>(m.d_state.p + sizeof(PosState) * (size_t)n_pos);
     unsigned int* d_any = reinterpret_cast<unsigned int*>(d_events + 1);
-    NPH_CUDA(ctx, cudaMemsetAsync(d_events, 0, 16, st));
+    NPH_CUDA(ctx, cudaMemsetAsync(d_events, 0, 24, st));
     float kernel_ms_total = 0.f;
     int launches_total = 0;
     for (;;) {
@@ -429,23 +438,25 @@ extern "C" int nph_screen_run(nph_ctx* ctx)
         NPH_TRY(nph_jobs_schedule(ctx, (size_t)n_jobs, pool));            // validation + schedule (one more read-back)
         NPH_TRY(nph_launch_hmm_forward(ctx, nullptr));
         NPH_CUDA(ctx, cudaMemsetAsync(d_any, 0, sizeof(unsigned int), st));
-        var_accumulate_kernel<<<pgrid, kBlock, 0, st>>>(d, state, job_off, ctx->d_scores.p, d_any, m.d_pos_off.p);
+        var_accumulate_kernel<<<pgrid, kBlock, 0, st>>>(d, state, job_off, ctx->d_scores.p, d_any, m.d_pos_off.p, pos_reads, d_events + 2);
         NPH_CUDA(ctx, cudaGetLastError());
         float ms = 0.f; int nl = 0;
         if (nph_last_kernel_ms(ctx, &ms, &nl) == NPH_OK) { kernel_ms_total += ms; launches_total += nl + 6; }
         m.n_rounds += 1;
         m.n_jobs += n_jobs;
     }
-    unsigned long long ev = 0;
-    NPH_CUDA(ctx, cudaMemcpyAsync(&ev, d_events, sizeof(ev), cudaMemcpyDeviceToHost, st));
+    unsigned long long ev[3] = {0, 0, 0};
+    NPH_CUDA(ctx, cudaMemcpyAsync(ev, d_events, sizeof(ev), cudaMemcpyDeviceToHost, st));
     NPH_CUDA(ctx, cudaStreamSynchronize(st));
-    m.n_scored_events = ev;
+    m.n_scored_events = ev[0];
+    m.n_reference_events = ev[2];
     ctx->staged_ms = kernel_ms_total; ctx->timing_valid = 2; ctx->last_launches = launches_total;
     m.ran = true;
     return NPH_OK;
 }
 
-extern "C" int nph_screen_counts(nph_ctx* ctx, uint32_t* n_rounds_out, uint64_t* n_jobs_out, uint64_t* n_scored_events_out, uint64_t* n_jobs_without_exit_out)
+extern "C" int nph_screen_counts(nph_ctx* ctx, uint32_t* n_rounds_out, uint64_t* n_jobs_out, uint64_t* n_scored_events_out, uint64_t* n_jobs_without_exit_out,
+                                 uint64_t* n_reference_events_out)
 {
     if (!ctx) return NPH_ERR_INVALID;
     nph_ctx::ScreenState& m = ctx->screen;
@@ -454,6 +465,7 @@ extern "C" int nph_screen_counts(nph_ctx* ctx, uint32_t* n_rounds_out, uint64_t*
     if (n_jobs_out) *n_jobs_out = m.n_jobs;
     if (n_scored_events_out) *n_scored_events_out = m.n_scored_events;
     if (n_jobs_without_exit_out) *n_jobs_without_exit_out = m.n_jobs_no_exit;
+    if (n_reference_events_out) *n_reference_events_out = m.n_reference_events;
     return NPH_OK;
 }
 

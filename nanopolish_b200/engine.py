@@ -109,6 +109,35 @@ class Engine:
         self._check(self.lib.nph_methylation_fetch(self.ctx, _p(site_off), _p(sites), sites.shape[0]), "nph_methylation_fetch")
         return site_off, sites[:n_sites]
 
+    # ---- variants: candidate screening on the device (include/nph.h, section N2) ----
+    def screen_edits_batch(self, reads, ev_mean, ev_start_time, ref_bases, deltas, first_event, records, params, indel_bias: float = 1.0):
+        """nph_screen_edits_batch: returns (qualities f8[n_pos, 9], n_reads u4[n_pos], scored_events)."""
+        n_pos = int(ref_bases.shape[0]) - 1
+        q = np.zeros((n_pos, 9), np.float64); nr = np.zeros(n_pos, np.uint32)
+        scored = C.c_uint64()
+        self._check(self.lib.nph_screen_edits_batch(self.ctx, _p(reads), reads.shape[0], _p(ev_mean), _p(ev_start_time), ev_mean.shape[0],
+                                                    _p(ref_bases), ref_bases.shape[0], _p(deltas), deltas.shape[0], _p(first_event), _p(records),
+                                                    records.shape[0], _p(params), indel_bias, _p(q), _p(nr), C.byref(scored)), "nph_screen_edits_batch")
+        return q, nr, int(scored.value)
+
+    def screen_load(self, ref_bases, deltas, first_event, records, params, indel_bias: float = 1.0):
+        self._check(self.lib.nph_screen_load(self.ctx, _p(ref_bases), ref_bases.shape[0], _p(deltas), deltas.shape[0], _p(first_event), _p(records),
+                                             records.shape[0], _p(params), indel_bias), "nph_screen_load")
+        self._screen_n = int(ref_bases.shape[0]) - 1
+
+    def screen_run(self):
+        self._check(self.lib.nph_screen_run(self.ctx), "nph_screen_run")
+
+    def screen_counts(self):
+        a, b, c, d, e = C.c_uint32(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.nph_screen_counts(self.ctx, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e)), "nph_screen_counts")
+        return dict(rounds=int(a.value), jobs=int(b.value), scored_events=int(c.value), jobs_without_exit=int(d.value), reference_events=int(e.value))
+
+    def screen_fetch(self):
+        q = np.zeros((self._screen_n, 9), np.float64); nr = np.zeros(self._screen_n, np.uint32)
+        self._check(self.lib.nph_screen_fetch(self.ctx, _p(q), _p(nr)), "nph_screen_fetch")
+        return q, nr
+
     # ---- models / reads / jobs ----------------------------------------------------------
     def model_upload(self, model) -> int:
         mid = C.c_uint32()

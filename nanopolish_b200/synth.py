@@ -567,3 +567,68 @@ def compact_event_alignment(records: np.ndarray, pairs: np.ndarray, n_ref_total:
             raise OverflowError("event-index step beyond int16: use the pair form")
         deltas[int(R["ref_off"]) + off] = d.astype(np.int16)
     return deltas, first
+
+
+SCREEN_PARAMS_DT = np.dtype([("flank", "<i4"), ("score_threshold", "<u4"), ("alignment_flags", "<u4"), ("k", "<u4"), ("reads_per_round", "<u4"),
+                             ("region_start", "<i4")], align=True)
+assert SCREEN_PARAMS_DT.itemsize == 24
+SCREEN_SLOTS = 9
+
+
+def screen_params(region_start: int, k: int = 6, flank: int = 10, threshold: int = 100, flags: int = 0, reads_per_round: int = 8) -> np.ndarray:
+    p = np.zeros(1, SCREEN_PARAMS_DT)
+    p[0] = (flank, threshold, flags, k, reads_per_round, region_start)
+    return p
+
+
+def gen_pileup(ref_len: int, depth: int, read_bases: int, model: PoreModel, seed: int = 42, region_start: int = 5000, n_true_variants: int = 0,
+               rc_every: int = 2):
+    """A draft reference of ref_len bases and ~depth-fold coverage by reads of read_bases bases sampled from the TRUTH (the draft with
+    n_true_variants substitutions), aligned base for base (CIGAR all M) — the input shape of `variants --consensus` screening
+    (SURVEY.md 8d, config 5).  Returns (ref_codes u1, ReadSet, records METH_RECORD_DT, pairs PAIR_DT): record r = read r, its
+    EventAlignmentRecord::aligned_events built like src/alignment/nanopolish_alignment_db.cpp:50-91 (ref_off = offset of the record's
+    slice in the compact event alignment, see compact_event_alignment)."""
+    rng = np.random.default_rng(seed)
+    k = model.k
+    ref = rng.integers(0, 4, ref_len, dtype=np.uint8)
+    truth = ref.copy()
+    if n_true_variants:
+        pos = rng.choice(np.arange(40, ref_len - 40), n_true_variants, replace=False)
+        truth[pos] = (truth[pos] + rng.integers(1, 4, n_true_variants)) % 4
+    n_reads = max(1, int(round(depth * ref_len / read_bases)))
+    starts = np.sort(rng.integers(0, ref_len - read_bases + 1, n_reads))
+    reads = np.zeros(n_reads, READ_DT)
+    recs = np.zeros(n_reads, METH_RECORD_DT)
+    means, times, seqs, evk, kfe, prs = [], [], [], [], [], []
+    p_nev = np.array([0.03, 0.35, 0.45, 0.17])
+    eoff = doff = poff = 0
+    for r in range(n_reads):
+        rr = np.random.default_rng(seed * 7919 + r)
+        s0 = int(starts[r])
+        seg = truth[s0:s0 + read_bases]
+        rc = 1 if (rc_every and r % rc_every == rc_every - 1) else 0
+        codes = (3 - seg[::-1]).astype(np.uint8) if rc else seg.copy()          # the bases as the pore saw them
+        nk = codes.shape[0] - k + 1
+        ranks = kmer_ranks_from_codes(codes, k, 4)
+        nev = rr.choice(4, nk, p=p_nev)
+        nev[0] = max(nev[0], 1); nev[-1] = max(nev[-1], 1)
+        which = np.repeat(np.arange(nk, dtype=np.int32), nev)
+        E = which.shape[0]
+        shift, scale, var = rr.uniform(-5.0, 5.0), rr.uniform(0.9, 1.1), rr.uniform(0.9, 1.3)
+        t = np.arange(E, dtype=np.float64) * 0.002 + rr.uniform(0.0, 100.0)
+        m = (scale * model.level_mean[ranks[which]] + shift + var * model.level_stdv[ranks[which]] * rr.standard_normal(E)).astype(np.float32)
+        reads[r] = (eoff, E, 0, scale, shift, 0.0, var, np.log(var), E / float(nk))
+        _, _, closest = closest_event_map(which, nk)
+        q = np.arange(k, read_bases - k)
+        q = q[q < nk]
+        ev = closest[read_bases - q - k] if rc else closest[q]
+        pr = np.zeros(q.shape[0], PAIR_DT)
+        pr["ref_pos"], pr["read_pos"] = region_start + s0 + q, ev
+        if pr.shape[0] and pr["read_pos"][0] == pr["read_pos"][-1]:
+            pr = pr[:0]
+        recs[r] = (doff, poff, r, 0, read_bases, pr.shape[0], region_start + s0, rc, 0, (0, 0))
+        means.append(m); times.append(t); seqs.append(codes); evk.append(which)
+        kfe.append(np.searchsorted(which, np.arange(nk), side="left").astype(np.int32)); prs.append(pr)
+        eoff += E; doff += read_bases; poff += pr.shape[0]
+    rs = ReadSet(reads, np.concatenate(means), np.concatenate(times), seqs, evk, kfe, k)
+    return ref, rs, recs, np.concatenate(prs)

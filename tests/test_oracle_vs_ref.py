@@ -368,3 +368,32 @@ def test_abea_qc_mixed_and_truncated_pinned(port_oracle, ref_oracle):
     jobs[1]["n_kmers"] = 3
     seqs = [synth._CODE2DNA[c[:int(j["n_kmers"]) + 5]].tobytes() for c, j in zip(rs.seq_codes, jobs)]
     _abea_ref_vs_port(port_oracle, ref_oracle, rs, jobs, ranks, total, seqs)
+
+
+def test_variant_screening_restatement_pinned(port_oracle, ref_oracle):
+    """tests/var_restatement.py (candidate list, the windows' event sequences, the read-order early exit) gives, for every candidate of
+    sampled positions, the double the compiled reference's score_variant_thresholded returns (src/common/nanopolish_variant.cpp:765-799,
+    one OpenMP thread): substitutions, insertions and the deletion, forward and reverse-strand reads, PRE|POST clip, indel bias 0.9."""
+    from tests import var_restatement as vr
+    nuc = synth.load_model("nucleotide")
+    REGION = 5000
+    ref, rs, recs, pairs = synth.gen_pileup(150, 14, 110, nuc, seed=11, region_start=REGION, n_true_variants=3)
+    ref_s = synth._CODE2DNA[ref].tobytes().decode()
+    ref_oracle.clear_reads()
+    rh = ref_oracle.register_reads(rs.reads, rs.ev_mean, rs.ev_start_time, ref_oracle.builtin_model("nucleotide"))
+    checked = exited = 0
+    for pi in range(20, 128, 6):
+        i = REGION + pi
+        cs, ce = i - 10, i + 11
+        want, n_seq, seqs = vr.screen_position(port_oracle, rs, nuc, ref_s, REGION, i, recs, pairs, 10, 40, 3, 0.9, 6)
+        if n_seq == 0:
+            continue
+        cands = vr.candidates(ref_s, pi)
+        got = ref_oracle.score_variants_thresholded([rh[r] for r, _, _ in seqs], [(e1, e2) for _, e1, e2 in seqs],
+                                                    np.array([recs[r]["rc"] for r, _, _ in seqs], np.uint8), ref_s[cs - REGION:ce - REGION + 1], cs,
+                                                    [(REGION + off, rseq, aseq) for _, off, rseq, aseq in cands], 3, 40, False, indel_bias=0.9)
+        for (slot, _, _, _), v in zip(cands, got):
+            assert want[slot] == float(v), (pi, slot, want[slot], float(v))
+            checked += 1; exited += abs(float(v)) >= 40
+    ref_oracle.clear_reads()
+    assert checked > 80 and exited > 40
