@@ -39,7 +39,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="scorereads",
-                    choices=["scorereads", "methylation", "call_methylation", "abea", "events", "prologue", "eventalign"])
+                    choices=["scorereads", "methylation", "call_methylation", "variants", "abea", "events", "prologue", "eventalign"])
+    ap.add_argument("--region", type=int, default=200000, help="--workload variants: reference positions per GPU (50x coverage by 2300-base reads)")
     ap.add_argument("--meth-reads", type=int, default=0,
                     help="reads per GPU of the call-methylation block (default 10000 at N=1; 12500 at N>1 = BASELINE configs[2]'s 100k reads at N=8)")
     ap.add_argument("--no-call-methylation", action="store_true", help="skip the configs.call_methylation block of the default line")
@@ -476,6 +477,185 @@ def call_methylation_cpu(rs, recs, ref, pairs, site_off, sites, tsv_ours):
                       f"({cores} threads), {cut} sites, rows identical to ours"}
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# variants --consensus candidate screening (BASELINE configs[4]): every single-base edit of every position of a region scored
+# against the pile-up with the reference's early-exit rule; enumeration, rounds and accumulation on the device.
+# ------------------------------------------------------------------------------------------------------------------
+def variants_block(args, rank, world, local, steps, warmup):
+    """One step = nph_screen_run over the resident pile-up (windows' event sequences, edited-window ranks, rounds of
+    reads_per_round reads with the early exit applied between rounds, qualities) + fetch of the 9 qualities per position; at N > 1
+    the region is cut into one slice per rank (positions are independent: no data-path collective) and the slices' qualities are
+    gathered to rank 0 with one NCCL gather.  Unit: the DP rows the reference's own loop scores for the same result (base and
+    variant sequence per candidate and read until its total leaves the threshold), so that our rate and the CPU arm's are
+    comparable; `our_dp_rows` is what the device actually ran (the base haplotype once per read and round, not once per candidate)."""
+    import torch
+    import torch.distributed as dist
+    from nanopolish_b200 import synth
+    from nanopolish_b200.dist import gather_to_rank0
+    from nanopolish_b200.engine import Engine
+
+    dev = torch.device("cuda", local)
+    nuc = synth.load_model("nucleotide")
+    region_start = 1_000_000 + rank * args.region
+    ref, rs, recs, pairs = synth.gen_pileup(args.region, 50, 2300, nuc, seed=424_243 + rank, region_start=region_start,
+                                            n_true_variants=max(1, args.region // 2000))
+    deltas, first = synth.compact_event_alignment(recs, pairs, int(recs["ref_len"].sum()))
+    ref_chars = synth._CODE2DNA[ref]
+    params = synth.screen_params(region_start, 6, 10, 100, 3, 8)
+    indel_bias = 0.9                                   # nanopolish variants' hmm_indel_bias_factor for the screening pass
+    eng = Engine(local, stream=torch.cuda.current_stream().cuda_stream)
+    eng.model_upload(nuc)
+    keep = []
+    def P(a):
+        t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory(); keep.append(t)
+        return t.numpy().view(a.dtype).reshape(a.shape)
+    h_reads, h_mean, h_ref, h_deltas, h_first, h_recs = P(rs.reads), P(rs.ev_mean), P(ref_chars), P(deltas), P(first), P(recs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.reads_load(h_reads, h_mean, rs.ev_start_time)
+    eng.screen_load(h_ref, h_deltas, h_first, h_recs, params, indel_bias)
+
+    def step():
+        eng.screen_run()
+        q, nr = eng.screen_fetch()
+        if world > 1:
+            gather_to_rank0(torch.from_numpy(q.reshape(-1)).to(dev), None)
+        return q, nr
+
+    for _ in range(max(3, warmup)):
+        q, nr = step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    kms = []
+    for _ in range(steps):
+        q, nr = step(); kms.append(eng.last_kernel_ms())
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    cnt = eng.screen_counts()
+    kernel_ms, launches = float(np.mean([k[0] for k in kms])), int(kms[-1][1])
+    tot = torch.tensor([float(cnt["reference_events"]), float(cnt["scored_events"]), float(cnt["jobs"]), float(cnt["jobs_without_exit"])],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    ref_events_all, our_rows_all, jobs_all, jobs_noexit_all = (float(x) for x in tot.tolist())
+    value = ref_events_all * steps / (total_ms * 1e-3)
+
+    # ---- e2e: the one-shot call with host buffers (events, reference, compact event alignments up; qualities back) ----
+    def e2e_step():
+        return eng.screen_edits_batch(h_reads, h_mean, rs.ev_start_time, h_ref, h_deltas, h_first, h_recs, params, indel_bias)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_steps = max(3, min(steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        q2, nr2, _ = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    assert np.array_equal(np.nan_to_num(q, nan=-1e300), np.nan_to_num(q2, nan=-1e300))
+    h2d = h_reads.nbytes + h_mean.nbytes + h_ref.nbytes + h_deltas.nbytes + h_first.nbytes + h_recs.nbytes
+    d2h = q.nbytes + nr.nbytes
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        b_alg = 4 * cnt["scored_events"] + (22 + 36) * cnt["jobs"]          # SURVEY.md 8d per job: 4E + L + 36
+        achieved = b_alg / (kernel_ms * 1e-3) / 1e9
+        n_pos_q = int((~np.isnan(q)).any(axis=1).sum())
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(3, warmup),
+               "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": f"variants --consensus candidate screening: {args.region} reference positions per GPU, 50x coverage by 2300-base "
+                                      "reads (~4000 events) aligned base for base, up to 9 single-base edits per position, 22-base windows, "
+                                      "threshold 100, PRE|POST clip, indel bias 0.9; reads scored 8 at a time with the early exit applied between rounds",
+                          "positions_per_gpu": args.region, "positions_screened": n_pos_q, "reads_per_gpu": int(rs.n_reads),
+                          "mean_event_sequences_per_position": float(nr.mean()), "rounds": cnt["rounds"],
+                          "unit_definition": "DP rows the reference's loop scores for the same qualities (2 sequences per candidate and read until exit)",
+                          "reference_dp_rows_per_step": ref_events_all, "our_dp_rows_per_step": our_rows_all, "jobs_per_step": jobs_all,
+                          "jobs_without_early_exit": jobs_noexit_all, "parallelism": f"region-slice x{world}",
+                          "multi_gpu": "positions are independent: one region slice per rank, one NCCL gather of the qualities" if world > 1 else None,
+                          "l2": "inputs larger than L2 (events + rank pool > 126 MB)"},
+               "e2e": {"value": ref_events_all * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "api": "nph_screen_edits_batch (host buffers in, qualities out)"},
+               "gpu_launches": launches * steps,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "peak_source": peak_src, "kernel": "hmm_forward_kernel<C,4> over the rounds' jobs", "kernel_ms": kernel_ms,
+                            "algorithmic_bytes_per_step": int(b_alg),
+                            "note": "kernel_ms = the forward kernels of all rounds (CUDA events around each); the step also holds the window / rank / "
+                                    "job kernels and two read-backs per round"}}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                eng.screen_run()
+                _, _, ref_rows = eng.screen_fetch(with_reference_rows=True)
+                out["cpu_baseline"] = variants_cpu(rs, recs, pairs, ref_chars, region_start, q, ref_rows, indel_bias)
+            except Exception as ex:
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "kind": "unavailable", "sample": f"failed: {type(ex).__name__}: {ex}"}
+    eng.close()
+    return out
+
+
+def variants_cpu(rs, recs, pairs, ref_chars, region_start, q_ours, ref_rows, indel_bias):
+    """The compiled reference's score_variant_thresholded for every candidate of a bounded sample of positions (one position per
+    thread, each call single-threaded so that its early exit follows read order); the qualities must equal ours exactly."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.oracle_py import RefOracle
+    from tests import var_restatement as vr
+    if not RefOracle.available():
+        raise RuntimeError("oracle/_ref/libnpref.so not present")
+    ro = RefOracle()
+    cores = cpu_threads()
+    ref_s = ref_chars.tobytes().decode()
+    n_pos = len(ref_s) - 1
+    # positions inside the first 40 kb (only the reads that can reach them are registered with the harness)
+    span = min(n_pos, 40_000)
+    sel = np.flatnonzero(recs["ref_start_pos"] - region_start < span + 64)
+    ro.clear_reads()
+    rh = ro.register_reads(rs.reads[:int(sel.max()) + 1], rs.ev_mean, rs.ev_start_time, ro.builtin_model("nucleotide"))
+    sub_recs = recs[:int(sel.max()) + 1]
+    sample = list(range(2000, span - 200, max(1, (span - 2200) // max(64, 24 * cores))))
+    work = []
+    for pi in sample:
+        i = region_start + pi
+        cs, ce = i - 10, i + 11
+        seqs = vr.event_sequences(sub_recs, pairs, cs, ce)
+        cands = vr.candidates(ref_s, pi)
+        work.append((pi, cs, seqs, cands, ref_s[cs - region_start:ce - region_start + 1]))
+    def one(w):
+        pi, cs, seqs, cands, window = w
+        return ro.score_variants_thresholded([rh[r] for r, _, _ in seqs], [(e1, e2) for _, e1, e2 in seqs],
+                                             np.array([sub_recs[r]["rc"] for r, _, _ in seqs], np.uint8), window, cs,
+                                             [(region_start + off, a, b) for _, off, a, b in cands], 3, 100, False, indel_bias=indel_bias)
+    one(work[0])
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        got = list(ex.map(one, work))
+    secs = time.perf_counter() - t0
+    same = True
+    for (pi, cs, seqs, cands, window), g in zip(work, got):
+        for (slot, _, _, _), v in zip(cands, g):
+            same &= float(q_ours[pi, slot]) == float(v)
+    # identical qualities mean identical exit points, so the DP rows the reference scored at these positions are the device's
+    # per-position account of the reference's loop (nph_screen_fetch: reference_rows)
+    rows = int(ref_rows[[w[0] for w in work]].sum())
+    ro.clear_reads()
+    return {"value": rows / secs, "unit": UNIT, "cores": cores, "cpu_quota": cpu_quota(), "kind": "reference", "seconds": secs, "positions": len(work),
+            "candidates": int(sum(len(w[3]) for w in work)), "qualities_identical": bool(same), "dp_rows": rows,
+            "sample": f"{len(work)} positions ({sum(len(w[3]) for w in work)} candidates) through the compiled reference's score_variant_thresholded, "
+                      f"one position per thread ({cores} threads), each call single-threaded"}
+
+
 def run_aux(args, rank, world, local, saved_stdout):
     """Auxiliary single-GPU measurements of the other kernels of the path (not the headline metric):
     --workload abea   : adaptive banded event alignment, reads x 8000 events (BASELINE configs[3] shape), events/s
@@ -714,6 +894,23 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload in ("abea", "events", "prologue", "eventalign"):
         run_aux(args, rank, world, local, saved_stdout)
+        return
+    if args.workload == "variants" and args.impl != "reference":
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        if world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        blk = variants_block(args, rank, world, local, args.steps, args.warmup)
+        if rank == 0:
+            blk["clocks"] = sampler.stop()
+            emit(blk, saved_stdout)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
         return
     if args.workload == "call_methylation" and args.impl != "reference":
         import torch

@@ -464,7 +464,8 @@ int nph_screen_run(nph_ctx* ctx);
  * scored once per round for all its candidates, the reference scores it once per candidate) */
 int nph_screen_counts(nph_ctx* ctx, uint32_t* n_rounds_out, uint64_t* n_jobs_out, uint64_t* n_scored_events_out, uint64_t* n_jobs_without_exit_out,
                       uint64_t* n_reference_events_out);
-int nph_screen_fetch(nph_ctx* ctx, double* qualities_out, uint32_t* n_reads_out);
+/* reference_rows_out (optional, one per position): the position's share of nph_screen_counts' n_reference_events */
+int nph_screen_fetch(nph_ctx* ctx, double* qualities_out, uint32_t* n_reads_out, uint64_t* reference_rows_out);
 
 /* ---- event detection (section 8f N4: the step before ABEA) --------------------------------------
  * scrappie's detect_events as load_from_raw calls it: t-statistics over two windows on prefix sums, a short/long

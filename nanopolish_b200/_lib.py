@@ -73,7 +73,7 @@ def load() -> C.CDLL:
     lib.nph_screen_load.argtypes = [vp, vp, sz, vp, sz, vp, vp, sz, vp, dbl]
     lib.nph_screen_run.argtypes = [vp]
     lib.nph_screen_counts.argtypes = [vp, vp, vp, vp, vp, vp]
-    lib.nph_screen_fetch.argtypes = [vp, vp, vp]
+    lib.nph_screen_fetch.argtypes = [vp, vp, vp, vp]
     lib.nph_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.nph_host_alloc.argtypes = [C.POINTER(vp), sz]
     lib.nph_host_free.argtypes = [vp]

@@ -44,6 +44,7 @@ struct PosState {
     uint32_t alive;       // bit c: |total_c| < threshold so far
     uint32_t done;        // reads consumed
     uint32_t chunk;       // reads of the current round
+    unsigned long long ref_rows;   // DP rows the reference's loop scores at this position (2 sequences per candidate and read until exit)
 };
 
 struct VarDev {
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kBlock) var_ranks_kernel(const VarDev d, const
         // the base-haplotype thread also initialises the position's state
         PosState st;
         for (int c = 0; c < NPH_SCREEN_SLOTS; ++c) st.total[c] = 0.0;
-        st.valid = 0; st.alive = 0; st.done = 0; st.chunk = 0;
+        st.valid = 0; st.alive = 0; st.done = 0; st.chunk = 0; st.ref_rows = 0;
         if (pos_ok) {
             const uint8_t b = dna_code(ref[cs - d.region_start + d.flank]), bp = dna_code(ref[cs - d.region_start + d.flank - 1]);
             uint32_t v = 0x80000000u;
@@ -303,6 +304,7 @@ __global__ void var_accumulate_kernel(const VarDev d, PosState* __restrict__ sta
         }
     }
     if (ref_ev) atomicAdd(ref_events, ref_ev);
+    st.ref_rows += ref_ev;
     st.done += st.chunk;
     uint32_t alive = 0;
     for (int c = 0; c < NPH_SCREEN_SLOTS; ++c) if (((st.alive >> c) & 1u) && fabs(st.total[c]) < thr) alive |= 1u << c;
@@ -313,11 +315,12 @@ __global__ void var_accumulate_kernel(const VarDev d, PosState* __restrict__ sta
 }
 
 __global__ void var_output_kernel(const VarDev d, const PosState* __restrict__ state, const uint64_t* __restrict__ pos_off,
-                                  double* __restrict__ qual, uint32_t* __restrict__ n_reads)
+                                  double* __restrict__ qual, uint32_t* __restrict__ n_reads, unsigned long long* __restrict__ ref_rows)
 {
     const int pi = blockIdx.x * blockDim.x + threadIdx.x;
     if (pi >= d.n_pos) return;
     const PosState st = state[pi];
+    ref_rows[pi] = st.ref_rows;
     for (int c = 0; c < NPH_SCREEN_SLOTS; ++c)
         qual[(size_t)pi * NPH_SCREEN_SLOTS + c] = ((st.valid >> c) & 1u) ? st.total[c] : __longlong_as_double(0x7ff8000000000000ll);
     n_reads[pi] = (uint32_t)(pos_off[pi + 1] - pos_off[pi]);
@@ -469,7 +472,7 @@ extern "C" int nph_screen_counts(nph_ctx* ctx, uint32_t* n_rounds_out, uint64_t*
     return NPH_OK;
 }
 
-extern "C" int nph_screen_fetch(nph_ctx* ctx, double* qualities_out, uint32_t* n_reads_out)
+extern "C" int nph_screen_fetch(nph_ctx* ctx, double* qualities_out, uint32_t* n_reads_out, uint64_t* reference_rows_out)
 {
     if (!ctx || !qualities_out) return NPH_ERR_INVALID;
     nph_ctx::ScreenState& m = ctx->screen;
@@ -480,16 +483,19 @@ extern "C" int nph_screen_fetch(nph_ctx* ctx, double* qualities_out, uint32_t* n
     // outputs staged in the (now idle) score buffer region: 9 doubles + 1 uint32 per position
     DevBuf<uint8_t>& scratch = ctx->d_prep;
     const size_t b_q = sizeof(double) * NPH_SCREEN_SLOTS * (size_t)n_pos, b_n = sizeof(uint32_t) * (size_t)n_pos;
-    NPH_TRY(nph_reserve(ctx, scratch, b_q + b_n + 256));
+    const size_t b_r = sizeof(unsigned long long) * (size_t)n_pos;
+    NPH_TRY(nph_reserve(ctx, scratch, b_q + b_r + b_n + 256));
     double* d_q = reinterpret_cast<double*>(scratch.p);
-    uint32_t* d_n = reinterpret_cast<uint32_t*>(scratch.p + b_q);
-    var_output_kernel<<<(n_pos + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(d, reinterpret_cast<const PosState*>(m.d_state.p), m.d_pos_off.p, d_q, d_n);
+    unsigned long long* d_r = reinterpret_cast<unsigned long long*>(scratch.p + b_q);
+    uint32_t* d_n = reinterpret_cast<uint32_t*>(scratch.p + b_q + b_r);
+    var_output_kernel<<<(n_pos + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(d, reinterpret_cast<const PosState*>(m.d_state.p), m.d_pos_off.p, d_q, d_n, d_r);
     NPH_CUDA(ctx, cudaGetLastError());
     NPH_CUDA(ctx, cudaMemcpyAsync(qualities_out, d_q, b_q, cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<uint32_t> tmp;
     uint32_t* n_dst = n_reads_out;
     if (!n_dst) { tmp.resize(n_pos); n_dst = tmp.data(); }
     NPH_CUDA(ctx, cudaMemcpyAsync(n_dst, d_n, b_n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (reference_rows_out) NPH_CUDA(ctx, cudaMemcpyAsync(reference_rows_out, d_r, b_r, cudaMemcpyDeviceToHost, ctx->stream));
     NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     // jobs a screening without early exit would have run: per position reads x (1 + candidates)
     uint64_t full = 0;
@@ -515,7 +521,7 @@ extern "C" int nph_screen_edits_batch(nph_ctx* ctx,
     NPH_TRY(nph_reads_load(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total));
     NPH_TRY(nph_screen_load(ctx, ref_bases, n_ref_bases, event_deltas, n_deltas_total, first_event, records, n_records, params, indel_bias));
     NPH_TRY(nph_screen_run(ctx));
-    NPH_TRY(nph_screen_fetch(ctx, qualities_out, n_reads_out));
+    NPH_TRY(nph_screen_fetch(ctx, qualities_out, n_reads_out, nullptr));
     if (n_scored_events_out) *n_scored_events_out = ctx->screen.n_scored_events;
     return NPH_OK;
 }

@@ -133,10 +133,11 @@ class Engine:
         self._check(self.lib.nph_screen_counts(self.ctx, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e)), "nph_screen_counts")
         return dict(rounds=int(a.value), jobs=int(b.value), scored_events=int(c.value), jobs_without_exit=int(d.value), reference_events=int(e.value))
 
-    def screen_fetch(self):
+    def screen_fetch(self, with_reference_rows: bool = False):
         q = np.zeros((self._screen_n, 9), np.float64); nr = np.zeros(self._screen_n, np.uint32)
-        self._check(self.lib.nph_screen_fetch(self.ctx, _p(q), _p(nr)), "nph_screen_fetch")
-        return q, nr
+        rows = np.zeros(self._screen_n, np.uint64) if with_reference_rows else None
+        self._check(self.lib.nph_screen_fetch(self.ctx, _p(q), _p(nr), _p(rows)), "nph_screen_fetch")
+        return (q, nr, rows) if with_reference_rows else (q, nr)
 
     # ---- models / reads / jobs ----------------------------------------------------------
     def model_upload(self, model) -> int:

@@ -64,8 +64,8 @@ def test_positions_outside_the_region_and_empty_pileup(eng):
     nuc, ref, ref_chars, rs, recs, pairs, deltas, first = _pileup(120, 6, 100, seed=3, n_true=0)
     params = synth.screen_params(REGION, K, 10, 100, 0, 8)
     q, nr, _ = eng.screen_edits_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref_chars, deltas, first, recs, params)
-    assert np.isnan(q[:10]).all() and np.isnan(q[-11:]).all()          # windows that leave the region: the reference skips the position
-    assert not np.isnan(q[10:-11]).all(axis=1).any()
+    assert np.isnan(q[:10]).all() and np.isnan(q[-10:]).all()          # windows that leave the region: the reference skips the position
+    assert not np.isnan(q[10:-10]).all(axis=1).any()
     # no records at all: every candidate keeps quality 0
     none = recs[:0]
     q0, nr0, ev0 = eng.screen_edits_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref_chars, deltas[:0], first[:0], none, params)
