@@ -637,11 +637,13 @@ def variants_cpu(rs, recs, pairs, ref_chars, region_start, q_ours, ref_rows, ind
         return ro.score_variants_thresholded([rh[r] for r, _, _ in seqs], [(e1, e2) for _, e1, e2 in seqs],
                                              np.array([sub_recs[r]["rc"] for r, _, _ in seqs], np.uint8), window, cs,
                                              [(region_start + off, a, b) for _, off, a, b in cands], 3, 100, False, indel_bias=indel_bias)
+    ro.set_globals(indel_bias, 1)          # the calls below run concurrently: each must find the globals it sets already in place
     one(work[0])
     t0 = time.perf_counter()
     with ThreadPoolExecutor(cores) as ex:
         got = list(ex.map(one, work))
     secs = time.perf_counter() - t0
+    ro.set_globals(1.0, cores)
     same = True
     for (pi, cs, seqs, cands, window), g in zip(work, got):
         for (slot, _, _, _), v in zip(cands, g):

@@ -300,6 +300,10 @@ class RefOracle:
             return None
         return dict(shift=out[0], scale=out[1], drift=out[2], var=out[3], events_per_base=out[4], calibrated=bool(out[5]), n_used=int(n))
 
+    def set_globals(self, indel_bias: float, omp_threads: int):
+        """hmm_indel_bias_factor and the OpenMP thread count, process-wide (for callers that run harness calls from their own threads)"""
+        self.lib.npref_set_globals(C.c_double(indel_bias), int(omp_threads))
+
     def score_variants_thresholded(self, read_handles, windows, rc, ref_seq: str, ref_position, variants, flags, threshold,
                                    methylation: bool, indel_bias=1.0):
         """[score_variant_thresholded(v, Haplotype(ref), reads, flags, threshold, types).quality for v in variants], single thread"""

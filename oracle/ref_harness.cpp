@@ -374,6 +374,10 @@ int npref_trim_raw(const float* raw, size_t n, int trim_start, int trim_end, int
 }
 
 int npref_max_threads(void) { return omp_get_max_threads(); }
+// process-wide settings for callers that drive several harness calls from their own threads: the entry points below save / set /
+// restore hmm_indel_bias_factor and the OpenMP thread count around each call, which is only safe concurrently when every call sets
+// the values that are already in place
+void npref_set_globals(double indel_bias, int omp_threads) { hmm_indel_bias_factor = indel_bias; omp_set_num_threads(omp_threads); }
 
 // ---- variants: score_variant_thresholded (src/common/nanopolish_variant.cpp:765-799) for each candidate, one OpenMP thread
 // so that its early exit (stop adding reads once |sum| >= threshold) follows read order deterministically.
