@@ -152,6 +152,32 @@ def build_workload(args, rank):
     return rs, jobs, models
 
 
+def k1_rooflines(args, jobs, kernel_ms, clocks):
+    """The two rooflines that do bound K1, from MEASURED counters: profiles/r02_k1_counters.json holds ncu's executed
+    warp instructions and shared-memory wavefronts of one pass of the forward kernels over this workload (same reads, same job list);
+    per block-cell they do not depend on the clock, so the live kernel time turns them into rates.
+      issue : warp instructions per second against 148 SMs x 4 schedulers x SM clock
+      shared: shared-memory wavefronts per second against 148 SMs x 1 wavefront per clock (the table look-ups replay on bank conflicts)"""
+    out = {}
+    try:
+        c = json.load(open(os.path.join(ROOT, "profiles", "r02_k1_counters.json"))).get(args.workload)
+    except Exception:
+        c = None
+    clk = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+    if c and c.get("reads") == args.reads and args.events == 4000:
+        inst_per_cell = c["inst_executed"] * 32.0 / float(jobs.block_cells)       # lane-instructions per block-cell, as ncu counted them
+        issue = c["inst_executed"] / (kernel_ms * 1e-3)
+        shared = c["lds_wavefronts"] / (kernel_ms * 1e-3)
+        out["issue"] = {"achieved": issue, "unit": "warp-instructions/s", "peak": 148 * 4 * clk, "frac": issue / (148 * 4 * clk),
+                        "instructions_per_block_cell": inst_per_cell, "source": "measured: smsp__inst_executed (profiles/r02_k1_counters.json) / live kernel time"}
+        out["shared_memory"] = {"achieved": shared, "unit": "wavefronts/s", "peak": 148 * clk, "frac": shared / (148 * clk),
+                                "bank_conflict_share": c["lds_conflict_wavefronts"] / c["lds_wavefronts"],
+                                "source": "measured: l1tex__data_pipe_lsu_wavefronts_mem_shared / live kernel time"}
+        if c.get("dram_bytes"):
+            out["traffic"] = c["dram_bytes"]
+    return out
+
+
 def algorithmic_bytes(jobs, k=6):
     """B_alg = 4*E + L + 36 bytes per job (event levels as f32, base codes, job record, score)."""
     j = jobs.jobs
@@ -1053,15 +1079,7 @@ def main():
         peak, peak_src = peaks()
         b_alg = algorithmic_bytes(jobs)
         achieved = b_alg / (kernel_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_hmm_forward_traffic.json")
-        if os.path.exists(tp):
-            try:
-                tj = json.load(open(tp))
-                if tj.get("workload") == args.workload and tj.get("reads") == args.reads:
-                    traffic = tj.get("dram_bytes_per_step")
-            except Exception:
-                pass
+        traffic = None          # filled from profiles/r02_k1_counters.json by k1_rooflines when the workload matches the capture
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -1077,16 +1095,9 @@ def main():
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_step": b_alg,
                          "note": "scalar log-semiring DP: issue/shared-memory bound, not HBM bound (DESIGN.md); "
                                  "block-cells/s below is the figure that moves",
-                         "block_cells_per_sec_per_gpu": float(jobs.block_cells) / (kernel_ms * 1e-3),
-                         "issue_bound_estimate_cells_per_sec": 2.5e11,
-                         # the roofline that does bound this kernel: warp-instruction issue.  81 SASS instructions per block-cell is
-                         # the structural count of the steady-state loop (7 table log-sums x 8 + 13 FADD + 3 FMUL + 4 FFMA + 1, DESIGN.md
-                         # section 4; profiles/r01_hmm_forward_summary.md has ncu's measured issue-active figure)
-                         "issue": {"achieved": float(jobs.block_cells) / (kernel_ms * 1e-3) * 81 / 32, "unit": "warp-instructions/s",
-                                   "peak": 148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6,
-                                   "frac": float(jobs.block_cells) / (kernel_ms * 1e-3) * 81 / 32 / (148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
-                                   "instructions_per_block_cell": 81}},
+                         "block_cells_per_sec_per_gpu": float(jobs.block_cells) / (kernel_ms * 1e-3)},
         }
+        line["roofline"].update(k1_rooflines(args, jobs, kernel_ms, clocks))
         if world == 1 and not args.no_cpu_baseline:
             try:
                 arm = CpuArm(rs, jobs, models)

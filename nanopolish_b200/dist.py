@@ -45,10 +45,11 @@ def gather_to_rank0(local, counts: list[int] | None = None, group=None):
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     if counts is None:
+        # one collective and ONE host read-back for all the counts
         c = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-        allc = [torch.zeros_like(c) for _ in range(world)]
-        dist.all_gather(allc, c, group=group)
-        counts = [int(x.item()) for x in allc]
+        allc = torch.empty(world, dtype=torch.int64, device=local.device)
+        dist.all_gather_into_tensor(allc, c, group=group)
+        counts = [int(x) for x in allc.tolist()]
     maxc = max(counts)
     if local.shape[0] != maxc:
         pad = torch.zeros(maxc, dtype=local.dtype, device=local.device)
