@@ -987,13 +987,14 @@ def main():
     t_mean, h_mean = pin(rs.ev_mean); keep.append(t_mean)
     t_time, h_time = pin(rs.ev_start_time); keep.append(t_time)
     # sequences cross the boundary as base codes (1 B/base; nph_hmm_*_seq), the jobs' rank_off indexing them
-    t_ranks, h_ranks = pin(jobs.seq_codes); keep.append(t_ranks)
-    t_jobs, h_jobs = pin(jobs.code_jobs.view(np.uint8)); keep.append(t_jobs); h_jobs = h_jobs.view(jobs.jobs.dtype)
+    use_ranks = bool(os.environ.get("NPH_BENCH_RANKS"))          # development A/B: the uint32-rank form of the same calls
+    t_ranks, h_ranks = pin(jobs.kmer_ranks if use_ranks else jobs.seq_codes); keep.append(t_ranks)
+    t_jobs, h_jobs = pin((jobs.jobs if use_ranks else jobs.code_jobs).view(np.uint8)); keep.append(t_jobs); h_jobs = h_jobs.view(jobs.jobs.dtype)
     t_out = torch.empty(n_jobs, dtype=torch.float32).pin_memory(); h_out = t_out.numpy()
 
     # ---- device-resident arm: inputs already in HBM when the timed region starts ----------
     eng.reads_load(h_reads, h_mean, h_time)
-    eng.hmm_jobs_load_seq(h_ranks, h_jobs)
+    (eng.hmm_jobs_load if use_ranks else eng.hmm_jobs_load_seq)(h_ranks, h_jobs)
     scores = torch.empty(n_jobs, dtype=torch.float32, device=dev)
     counts = None
     gathered = None
@@ -1054,7 +1055,7 @@ def main():
 
     # ---- e2e arm: the one-shot C-ABI call with HOST buffers, H2D + D2H inside the timed region ----
     def e2e_step():
-        eng.hmm_score_batch_seq(h_reads, h_mean, h_time, h_ranks, h_jobs, out=h_out)
+        (eng.hmm_score_batch if use_ranks else eng.hmm_score_batch_seq)(h_reads, h_mean, h_time, h_ranks, h_jobs, out=h_out)
 
     for _ in range(2):
         e2e_step()

@@ -175,7 +175,11 @@ __global__ void __launch_bounds__(CtaShape<C, W>::warps * 32, 1) hmm_forward_ker
         // get_scaled_gaussian_from_pore_model_state does, then narrowed; plus RN(1/sigma') ----
         if (has_job) {
             const uint32_t* rk = p.ranks + job.rank_off;
+#ifdef NPH_NO_CODES
+            const uint8_t* cd = nullptr;                 // A/B: the base-code prologue compiled out
+#else
             const uint8_t* cd = p.codes ? p.codes + job.rank_off : nullptr;
+#endif
             const int mk = (int)mv.k;
             const uint32_t A = mv.alphabet_size;
             for (int i = gl; i < kpad; i += W) {

@@ -17,6 +17,11 @@ build() {   # name, extra flags
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o build/variants/libnph_$name.so $objs
   echo "built $name"
 }
+if [ "$1" = "codes" ]; then
+  build cur
+  build nocodes -DNPH_NO_CODES
+  exit 0
+fi
 build scalar_lea   -DNPH_PACKED_F32X2=0 -DNPH_EVEN_CELL_COST=88.0f -DNPH_LSUM_LEA
 build scalar_imad  -DNPH_PACKED_F32X2=0 -DNPH_EVEN_CELL_COST=88.0f
 build packed_all
