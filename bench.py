@@ -253,8 +253,8 @@ def run_reference(args, rank, world, saved_stdout):
     Rank 0 alone runs it; each step is one pass over a bounded sample of the workload's job list."""
     if rank != 0:
         return
-    small = argparse.Namespace(**{**vars(args), "reads": min(args.reads, 2048)})
-    rs, jobs, models = build_workload(small, 0)
+    # rank 0's full job list of the own arm (same generator, same seed): the sample is drawn from it, and `config` is the own arm's
+    rs, jobs, models = build_workload(args, 0)
     arm = CpuArm(rs, jobs, models)
     steps, warm = args.steps, args.warmup
     per_step = max(0.5, min(6.0, 120.0 / max(1, steps + warm)))   # whole run within a few minutes
@@ -268,7 +268,8 @@ def run_reference(args, rank, world, saved_stdout):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": mean_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(full, jobs, reads_override=args.reads),
+            "config": {**workload_config(full, jobs), "jobs_per_gpu": int(jobs.jobs.shape[0]),
+                       "scored_events_per_step": float(jobs.scored_events) * args.gpus},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

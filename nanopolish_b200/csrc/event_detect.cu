@@ -16,6 +16,7 @@
 // algorithmic minimum: 4 B per sample in, 24 B per event out.  Every float/double operation mirrors the C source's
 // promotions (float products, double quotient, double sqrt) so boundaries, means and stdvs are bit-identical.
 #include "nph_internal.cuh"
+#include "exact_math.cuh"
 #include <cfloat>
 #include <algorithm>
 #include <vector>
@@ -206,6 +207,7 @@ struct FastParams {
     nph_event* events;
     uint32_t* n_events;
     int* overflow;
+    uint32_t* stats;             // [0] repair walks, [1] reads sent to the streaming fallback (diagnostics: $NPH_EVENTS_STATS)
     uint32_t w1, w2;
     float t1, t2, peak_height;
     uint32_t warm;
@@ -463,6 +465,220 @@ __global__ void __launch_bounds__(kPeakWarps * 32) ed_peaks_kernel(const FastPar
     }
 }
 
+// =============================================================================================================
+// Fused form of guard + t-statistics + peaks: ONE pass over the samples, nothing but the boundaries written.
+// The warp that owns a read walks it as 32 segments like ed_peaks_kernel, but the 32x32 tile of t-statistics each
+// lane consumes is COMPUTED by the warp from the raw samples (row rr = the next 32 positions of lane rr's range, one
+// lane per position: coalesced loads, the 2*w2 neighbours out of L1) instead of being read back from HBM, and the
+// exactness guard rides along on the samples the warp touches anyway.  Differences from the three-kernel form:
+//   * divisions by the window length are Markstein divisions by a cached reciprocal (exact_math.cuh), the final
+//     |delta| / sqrt(v) is D * rsqrt(v) in FP64 (<= 2 ulp) rounded to float, accepted only when that FP64 value is
+//     more than 2^10 ulps away from a float rounding boundary (so the correctly rounded chain dsqrt -> ddiv -> float
+//     provably rounds to the same float); otherwise that position takes the reference's operations one by one
+//   * boundaries are recorded during the counting walk into a per-lane slice of the read's peak array and compacted
+//     afterwards: no second walk
+//   * a segment whose warm-up did not reach the true state is re-walked from its left neighbour's final state until
+//     the chain verifies (induction from lane 0), instead of handing the whole read to one lane
+// A read that fails the guard (or overflows a lane's slice) is flagged for the streaming fallback as before.
+// =============================================================================================================
+struct TsConsts {
+    uint32_t w1, w2;
+    float w1f, w2f, r1f, r2f;        // window lengths as float, RN(1/w) in float
+    double w1d, w2d, r1d, r2d;       // ... and in double
+};
+
+struct GuardAcc { uint32_t vmin, vmax, qmin, qmax; };     // min / max of |x| and |x*x| bit patterns over nonzero values
+
+__device__ __forceinline__ double ddiv_by_cached_rcp(double a, double b, double y)
+{
+    const double q0 = __dmul_rn(a, y);
+    const double r0 = __fma_rn(-q0, b, a);
+    const double q1 = __fma_rn(r0, y, q0);
+    const double r1 = __fma_rn(-q1, b, a);
+    return __fma_rn(r1, y, q1);
+}
+
+// compute_tstat's loop body (event_detection.c:91-112) for one window, from the exact left/right window sums
+__device__ __forceinline__ float tstat_windows(double sl, double ql, double sr, double qr, float wf, float rf, double wd, double rd)
+{
+    const float sum2 = (float)sr, sumsq2 = (float)qr;
+    const float mean1 = (float)ddiv_by_cached_rcp(sl, wd, rd);
+    const float mean2 = div_by_cached_rcp(sum2, wf, rf);
+    double cv = __dsub_rn(ddiv_by_cached_rcp(ql, wd, rd), (double)__fmul_rn(mean1, mean1));
+    cv = __dadd_rn(cv, (double)div_by_cached_rcp(sumsq2, wf, rf));
+    cv = __dsub_rn(cv, (double)__fmul_rn(mean2, mean2));
+    const float combined_var = fmaxf((float)cv, FLT_MIN);
+    const float delta_mean = __fsub_rn(mean2, mean1);
+    if (combined_var >= 8.6736174e-19f /*2^-60*/ && combined_var <= 1.1529215e18f /*2^60*/) {
+        if (delta_mean == 0.0f) return 0.0f;
+        const float v = div_by_cached_rcp(combined_var, wf, rf);
+        const double y = __dmul_rn(fabs((double)delta_mean), rsqrt((double)v));
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(y);
+        const uint32_t lo = (uint32_t)bits & 0x1FFFFFFFu, ex = (uint32_t)(bits >> 52);
+        if ((lo - 0x10000000u + 1024u) >= 2048u && (ex - 923u) < 200u) return (float)y;
+    }
+    return (float)__ddiv_rn(fabs((double)delta_mean), __dsqrt_rn((double)__fdiv_rn(combined_var, wf)));
+}
+
+// both t-statistics at position pos of a read (0 where compute_tstat leaves its zeros), and the guard's view of x[pos]
+template <int W1, int W2>
+__device__ __forceinline__ void tstat_pair(const float* __restrict__ x, uint32_t n, uint32_t pos, const TsConsts& tc, float& a, float& b, GuardAcc& ga)
+{
+    const uint32_t w1 = W1 ? (uint32_t)W1 : tc.w1, w2 = W2 ? (uint32_t)W2 : tc.w2;
+    // compute_tstat leaves zeros when the signal is shorter than two windows or the window shorter than 2 (:73-:76), and at the ends
+    const bool v1 = w1 >= 2 && n >= 2 * w1 && pos >= w1 && pos <= n - w1, v2 = w2 >= 2 && n >= 2 * w2 && pos >= w2 && pos <= n - w2;
+    const float xc = x[pos];
+    {
+        const uint32_t vb = __float_as_uint(xc) & 0x7fffffffu, qb = __float_as_uint(__fmul_rn(xc, xc));
+        ga.vmax = max(ga.vmax, vb); ga.qmax = max(ga.qmax, qb);
+        ga.vmin = min(ga.vmin, vb ? vb : 0xffffffffu); ga.qmin = min(ga.qmin, qb ? qb : 0xffffffffu);
+    }
+    a = 0.0f; b = 0.0f;
+    if (!(v1 || v2)) return;
+    double sl = 0.0, ql = 0.0, sr = 0.0, qr = 0.0;
+#pragma unroll
+    for (uint32_t j = 0; j < w1; ++j) {
+        const float xl = x[pos - 1 - j], xr = j == 0 ? xc : x[pos + j];
+        sl = __dadd_rn(sl, (double)xl); ql = __dadd_rn(ql, (double)__fmul_rn(xl, xl));
+        sr = __dadd_rn(sr, (double)xr); qr = __dadd_rn(qr, (double)__fmul_rn(xr, xr));
+    }
+    if (v1) a = tstat_windows(sl, ql, sr, qr, tc.w1f, tc.r1f, tc.w1d, tc.r1d);
+    if (v2) {
+#pragma unroll
+        for (uint32_t j = w1; j < w2; ++j) {
+            const float xl = x[pos - 1 - j], xr = x[pos + j];
+            sl = __dadd_rn(sl, (double)xl); ql = __dadd_rn(ql, (double)__fmul_rn(xl, xl));
+            sr = __dadd_rn(sr, (double)xr); qr = __dadd_rn(qr, (double)__fmul_rn(xr, xr));
+        }
+        b = tstat_windows(sl, ql, sr, qr, tc.w2f, tc.r2f, tc.w2d, tc.r2d);
+    }
+}
+
+// One cooperative walk: lane l walks [from_l, from_l + len_l), the first wlen_l steps being warm-up (state only); at
+// step wlen_l the state is snapshotted and from there boundaries are counted and recorded into region[0..R).
+template <int W1, int W2>
+__device__ __forceinline__ uint32_t fused_walk(PeakState& st, PeakState& snap, const TsConsts& tc, const PeakConsts& k,
+                                               const float* __restrict__ x, uint32_t n, uint32_t from, uint32_t len, uint32_t wlen,
+                                               uint32_t* __restrict__ region, uint32_t R, GuardAcc& ga, float (*sa)[33], float (*sb)[33], int lane)
+{
+    uint32_t maxlen = len;
+    for (int o = 16; o; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    uint32_t cnt = 0;
+    for (uint32_t c = 0; c < maxlen; c += 32) {
+        for (int rr = 0; rr < 32; ++rr) {
+            const uint32_t fr = __shfl_sync(0xffffffffu, from, rr), ln = __shfl_sync(0xffffffffu, len, rr);
+            if (c >= ln) continue;                                       // warp-uniform
+            float a = 0.0f, b = 0.0f;
+            if (c + lane < ln) tstat_pair<W1, W2>(x, n, fr + c + lane, tc, a, b, ga);
+            sa[rr][lane] = a; sb[rr][lane] = b;
+        }
+        __syncwarp();
+        if (c == wlen) snap = st;
+        const bool rec = c >= wlen;
+        const uint32_t steps = len > c ? min(32u, len - c) : 0u;
+        for (uint32_t t = 0; t < steps; ++t) {
+            int e0, e1;
+            peak_step(st, k, from + c + t, sa[lane][t], sb[lane][t], e0, e1);
+            if (rec && e0 >= 0) { if (cnt < R) region[cnt] = (uint32_t)e0; ++cnt; }
+            if (rec && e1 >= 0) { if (cnt < R) region[cnt] = (uint32_t)e1; ++cnt; }
+        }
+        __syncwarp();
+    }
+    return cnt;
+}
+
+constexpr uint32_t kFusedWarm = 128;      // multiple of 32; $NPH_EVENTS_WARMUP overrides (rounded up to 32)
+
+template <int W1, int W2>
+__global__ void __launch_bounds__(kPeakWarps * 32) ed_fused_kernel(const FastParams p, const TsConsts tc)
+{
+    __shared__ float s_a[kPeakWarps][32][33], s_b[kPeakWarps][32][33];
+    const int wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t slot = blockIdx.x * kPeakWarps + (threadIdx.x >> 5);
+    if (slot >= p.n_reads) return;
+    const uint32_t ridx = p.order[slot];
+    const nph_raw_read rd = p.reads[ridx];
+    const uint32_t n = rd.n_samples;
+    const float* __restrict__ x = p.raw + rd.sample_off;
+    uint32_t* peaks = p.peaks + rd.event_off;
+    const uint32_t cap_peaks = rd.event_cap ? rd.event_cap - 1 : 0;       // events = boundaries + 1
+    const uint32_t R = cap_peaks / 32;                                    // a lane's slice of the peak array
+    uint32_t* region = peaks + (size_t)lane * R;
+    const PeakConsts k{p.t1, p.t2, p.peak_height, p.w1, p.w1 / 2, p.w2 / 2};
+
+    const uint32_t seg = ((n + 31) / 32 + 31) / 32 * 32;                   // segment length, multiple of 32
+    const uint32_t b0 = min(n, (uint32_t)lane * seg), b1 = min(n, b0 + seg);
+    const bool mine = b0 < n;                                              // lanes past the end of the read own nothing
+    const uint32_t a0 = b0 > p.warm ? b0 - p.warm : 0;                     // b0, warm multiples of 32: so is the warm-up length
+    GuardAcc ga{0xffffffffu, 0u, 0xffffffffu, 0u};
+    PeakState st = fresh_state(), snap = st;
+    uint32_t cnt = fused_walk<W1, W2>(st, snap, tc, k, x, n, mine ? a0 : 0u, mine ? b1 - a0 : 0u, mine ? b0 - a0 : 0u, region, R, ga,
+                                      s_a[wib], s_b[wib], lane);
+    // ---- the guard (ed_guard_kernel's test, plus the operand range the cached-reciprocal divisions are proven for) ----
+    for (int o = 16; o; o >>= 1) {
+        ga.vmin = min(ga.vmin, __shfl_xor_sync(0xffffffffu, ga.vmin, o)); ga.vmax = max(ga.vmax, __shfl_xor_sync(0xffffffffu, ga.vmax, o));
+        ga.qmin = min(ga.qmin, __shfl_xor_sync(0xffffffffu, ga.qmin, o)); ga.qmax = max(ga.qmax, __shfl_xor_sync(0xffffffffu, ga.qmax, o));
+    }
+    bool exact;
+    {
+        int lg = 0;
+        while ((1ull << lg) < (unsigned long long)n + 1) ++lg;             // ceil(log2(n + 1))
+        // biased exponents; ulp exponent = e - 150, top = e - 127: span = lg + (emax - 127) + 1 - (emin - 150)
+        const int evx = (int)(ga.vmax >> 23), evn = (int)(ga.vmin >> 23), eqx = (int)(ga.qmax >> 23), eqn = (int)(ga.qmin >> 23);
+        const bool okx = ga.vmax == 0u || (evn >= 97 && evx <= 157 && lg + evx + 24 - evn <= 53);       // |x| in [2^-30, 2^31)
+        const bool okq = ga.qmax == 0u || (eqn >= 66 && eqx <= 188 && lg + eqx + 24 - eqn <= 53);       // x*x in [2^-61, 2^62)
+        exact = okx && okq;
+    }
+    // ---- verification and repair: my snapshot must equal the final state of the lane to my left ----
+    bool over = false;
+    uint32_t repairs = 0;
+    for (int round = 0; exact && round < 32; ++round) {
+        PeakState left;
+        left.m0 = __shfl_up_sync(0xffffffffu, st.m0, 1); left.m1 = __shfl_up_sync(0xffffffffu, st.m1, 1);
+        left.pp0 = __shfl_up_sync(0xffffffffu, st.pp0, 1); left.pp1 = __shfl_up_sync(0xffffffffu, st.pp1, 1);
+        left.pv0 = __shfl_up_sync(0xffffffffu, st.pv0, 1); left.pv1 = __shfl_up_sync(0xffffffffu, st.pv1, 1);
+        left.v0 = __shfl_up_sync(0xffffffffu, st.v0, 1); left.v1 = __shfl_up_sync(0xffffffffu, st.v1, 1);
+        const bool ok = !mine || lane == 0 || same_state(snap, left);
+        if (__all_sync(0xffffffffu, ok)) break;
+        // re-walk the segments that started from a wrong state, now from the neighbour's final state (lanes 0..round are right)
+        PeakState s2 = ok ? st : left, sn2 = s2;
+        GuardAcc g2{0xffffffffu, 0u, 0xffffffffu, 0u};
+        const uint32_t c2 = fused_walk<W1, W2>(s2, sn2, tc, k, x, n, ok ? 0u : b0, ok ? 0u : b1 - b0, 0u, region, R, g2, s_a[wib], s_b[wib], lane);
+        if (!ok) { st = s2; snap = left; cnt = c2; }
+        ++repairs;
+    }
+    over = cnt > R;
+    if (__any_sync(0xffffffffu, over)) exact = false;                      // a lane's slice was too small: streaming fallback
+    uint32_t incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (exact && total <= cap_peaks) {
+        // compact the 32 slices (lane 0's is in place); destinations never pass their sources, chunks go left to right
+        for (int s = 1; s < 32; ++s) {
+            const uint32_t cs = __shfl_sync(0xffffffffu, cnt, s), ds = __shfl_sync(0xffffffffu, incl - cnt, s);
+            const uint32_t* src = peaks + (size_t)s * R;
+            if (ds == (uint32_t)s * R) continue;
+            for (uint32_t q = 0; q < cs; q += 32) {
+                uint32_t v = 0;
+                if (q + lane < cs) v = src[q + lane];
+                __syncwarp();
+                if (q + lane < cs) peaks[ds + q + lane] = v;
+                __syncwarp();
+            }
+        }
+    }
+    if (lane == 0) {
+        p.exact[ridx] = exact ? 1 : 0;
+        if (repairs) atomicAdd(&p.stats[0], repairs);
+        if (!exact) atomicAdd(&p.stats[1], 1u);
+        if (exact) {
+            if (total > cap_peaks) { *p.overflow = 1; p.n_peaks[ridx] = 0; p.n_events[ridx] = 0; }
+            else { p.n_peaks[ridx] = total; p.n_events[ridx] = total + 1; }
+        }
+    }
+}
+
 // block per read, thread per event
 __global__ void __launch_bounds__(256) ed_events_kernel(const FastParams p)
 {
@@ -548,32 +764,48 @@ int nph_detect_events_device(nph_ctx* ctx, const float* d_raw, size_t n_samples_
     p.ring = 2 * p.w2 + 1;
     NPH_CUDA(ctx, cudaMemcpyAsync(d_reads, reads, sizeof(nph_raw_read) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(d_order, order.data(), sizeof(uint32_t) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
-    NPH_CUDA(ctx, cudaMemsetAsync(p.overflow, 0, sizeof(int), ctx->stream));
+    NPH_CUDA(ctx, cudaMemsetAsync(p.overflow, 0, 64, ctx->stream));
     // fast path first (guard -> t-statistics -> peaks -> events); reads that fail the exactness guard take the stream kernel
     FastParams f{};
     f.raw = d_raw; f.reads = d_reads; f.order = d_order; f.n_reads = (uint32_t)n_reads;
     f.ts1 = d_ts1; f.ts2 = d_ts2; f.peaks = d_peaks; f.n_peaks = d_npeaks; f.exact = d_exact;
     f.events = p.events; f.n_events = p.n_events; f.overflow = p.overflow;
+    f.stats = reinterpret_cast<uint32_t*>(p.overflow) + 2;
     f.w1 = p.w1; f.w2 = p.w2; f.t1 = p.t1; f.t2 = p.t2; f.peak_height = p.peak_height;
     f.warm = getenv("NPH_EVENTS_WARMUP") ? (uint32_t)atoi(getenv("NPH_EVENTS_WARMUP")) : kWarm;
     int launches = 0;
-    ed_guard_kernel<<<(unsigned)std::min<size_t>(n_reads, (size_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(f); ++launches;
-    NPH_CUDA(ctx, cudaGetLastError());
-    {
-        const uint32_t max_n = keyed[0].first;
-        dim3 grid((unsigned)std::min<size_t>((max_n + 255) / 256, 64), (unsigned)n_reads);
-        if (n_reads <= 65535) { ed_tstat_kernel<<<grid, 256, 0, ctx->stream>>>(f); ++launches; }
-        else {
-            for (size_t r0 = 0; r0 < n_reads; r0 += 65535) {         // gridDim.y limit
-                FastParams g = f; g.reads = d_reads + r0; g.exact = d_exact + r0;
-                dim3 gg(grid.x, (unsigned)std::min<size_t>(65535, n_reads - r0));
-                ed_tstat_kernel<<<gg, 256, 0, ctx->stream>>>(g); ++launches;
+    if (!getenv("NPH_EVENTS_UNFUSED")) {
+        // one pass over the samples: guard + t-statistics + peaks (ed_fused_kernel)
+        TsConsts tc{};
+        tc.w1 = p.w1; tc.w2 = p.w2;
+        tc.w1f = (float)p.w1; tc.w2f = (float)p.w2; tc.r1f = 1.0f / tc.w1f; tc.r2f = 1.0f / tc.w2f;
+        tc.w1d = (double)p.w1; tc.w2d = (double)p.w2; tc.r1d = 1.0 / tc.w1d; tc.r2d = 1.0 / tc.w2d;
+        f.warm = getenv("NPH_EVENTS_WARMUP") ? ((uint32_t)atoi(getenv("NPH_EVENTS_WARMUP")) + 31u) / 32u * 32u : kFusedWarm;
+        const unsigned blocks = (unsigned)((n_reads + kPeakWarps - 1) / kPeakWarps);
+        if (p.w1 == 3 && p.w2 == 6) ed_fused_kernel<3, 6><<<blocks, kPeakWarps * 32, 0, ctx->stream>>>(f, tc);
+        else if (p.w1 == 7 && p.w2 == 14) ed_fused_kernel<7, 14><<<blocks, kPeakWarps * 32, 0, ctx->stream>>>(f, tc);
+        else ed_fused_kernel<0, 0><<<blocks, kPeakWarps * 32, 0, ctx->stream>>>(f, tc);
+        ++launches;
+        NPH_CUDA(ctx, cudaGetLastError());
+    } else {
+        ed_guard_kernel<<<(unsigned)std::min<size_t>(n_reads, (size_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(f); ++launches;
+        NPH_CUDA(ctx, cudaGetLastError());
+        {
+            const uint32_t max_n = keyed[0].first;
+            dim3 grid((unsigned)std::min<size_t>((max_n + 255) / 256, 64), (unsigned)n_reads);
+            if (n_reads <= 65535) { ed_tstat_kernel<<<grid, 256, 0, ctx->stream>>>(f); ++launches; }
+            else {
+                for (size_t r0 = 0; r0 < n_reads; r0 += 65535) {         // gridDim.y limit
+                    FastParams g = f; g.reads = d_reads + r0; g.exact = d_exact + r0;
+                    dim3 gg(grid.x, (unsigned)std::min<size_t>(65535, n_reads - r0));
+                    ed_tstat_kernel<<<gg, 256, 0, ctx->stream>>>(g); ++launches;
+                }
             }
+            NPH_CUDA(ctx, cudaGetLastError());
         }
+        ed_peaks_kernel<<<(unsigned)((n_reads + kPeakWarps - 1) / kPeakWarps), kPeakWarps * 32, 0, ctx->stream>>>(f); ++launches;
         NPH_CUDA(ctx, cudaGetLastError());
     }
-    ed_peaks_kernel<<<(unsigned)((n_reads + kPeakWarps - 1) / kPeakWarps), kPeakWarps * 32, 0, ctx->stream>>>(f); ++launches;
-    NPH_CUDA(ctx, cudaGetLastError());
     ed_events_kernel<<<(unsigned)std::min<size_t>(n_reads, (size_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(f); ++launches;
     NPH_CUDA(ctx, cudaGetLastError());
     // fallback list
@@ -596,6 +828,11 @@ int nph_detect_events_device(nph_ctx* ctx, const float* d_raw, size_t n_samples_
     NPH_CUDA(ctx, cudaMemcpyAsync(h_n_events.data(), p.n_events, sizeof(uint32_t) * n_reads, cudaMemcpyDeviceToHost, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(&overflow, p.overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (getenv("NPH_EVENTS_STATS")) {
+        uint32_t st[2] = {0, 0};
+        cudaMemcpy(st, f.stats, sizeof(st), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[nph events] reads %zu  repair walks %u  streaming fallback %zu (guard/slice %u)\n", n_reads, st[0], slow.size(), st[1]);
+    }
     *d_events_out = p.events;
     *d_n_events_out = p.n_events;
     if (launches_out) *launches_out = launches;

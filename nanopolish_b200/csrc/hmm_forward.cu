@@ -65,7 +65,6 @@ int nph_launch_hmm_forward(nph_ctx* ctx, float* scores_dev)
     p.trans = ctx->d_trans.p;
     p.models = ctx->d_models.p;
     p.ranks = ctx->d_ranks.p;
-    p.codes = ctx->codes_mode ? ctx->d_codes.p : nullptr;
     p.jobs = ctx->d_jobs.p;
     p.logsum_g = ctx->d_logsum;
     p.flank = ctx->d_flank.p;

@@ -72,7 +72,6 @@ struct FwdParams {
     const float2* trans;          // per read (lp_mm_self, lp_mm_next)
     const DevModelView* models;
     const uint32_t* ranks;
-    const uint8_t* codes;         // base codes instead of ranks (nph_hmm_*_seq): the prologue forms each k-mer's rank itself
     const nph_hmm_job* jobs;
     const uint32_t* order;        // this class's slice of the schedule
     uint32_t n_jobs;
@@ -175,25 +174,10 @@ __global__ void __launch_bounds__(CtaShape<C, W>::warps * 32, 1) hmm_forward_ker
         // get_scaled_gaussian_from_pore_model_state does, then narrowed; plus RN(1/sigma') ----
         if (has_job) {
             const uint32_t* rk = p.ranks + job.rank_off;
-#ifdef NPH_NO_CODES
-            const uint8_t* cd = nullptr;                 // A/B: the base-code prologue compiled out
-#else
-            const uint8_t* cd = p.codes ? p.codes + job.rank_off : nullptr;
-#endif
-            const int mk = (int)mv.k;
-            const uint32_t A = mv.alphabet_size;
             for (int i = gl; i < kpad; i += W) {
                 float4 g = make_float4(0.f, 1.f, 0.f, 1.f);
                 if (i < K) {
-                    uint32_t r;
-                    if (cd) {
-                        // k-mer i of the strand's string: at i, or (rc) at length - i - k — HMMInputSequence::get_kmer_rank
-                        const uint8_t* km = cd + (job.rc ? K - 1 - i : i);
-                        r = 0;
-                        for (int j = 0; j < mk; ++j) r = r * A + km[j];
-                    } else {
-                        r = rk[i];
-                    }
+                    const uint32_t r = rk[i];
                     const float mu = (float)__dadd_rn(__dmul_rn(rd.scale, mv.mean[r]), rd.shift);
                     const float sd = (float)__dmul_rn(mv.stdv[r], rd.var);
                     const float lsd = (float)__dadd_rn(mv.log_stdv[r], rd.log_var);

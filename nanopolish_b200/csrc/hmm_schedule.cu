@@ -16,12 +16,14 @@ struct SchedSummary {
     uint32_t max_kpad, max_period, max_E;
     unsigned long long class_count[NPH_NUM_CLASSES];
     float class_cost[NPH_NUM_CLASSES];
+    unsigned long long rank_cursor;   // base-code jobs: k-mer ranks handed out so far (codes_to_ranks_kernel fills them)
 };
 
 __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n_jobs, const DevRead* __restrict__ reads,
                                 uint32_t n_reads, const DevModelView* __restrict__ models, const uint32_t* __restrict__ ranks, const uint8_t* __restrict__ codes,
                                 uint32_t n_models, uint64_t n_ranks, uint32_t chunk_events, uint8_t* __restrict__ cls,
-                                uint16_t* __restrict__ bkt, unsigned int* __restrict__ hist, SchedSummary* __restrict__ sum)
+                                uint16_t* __restrict__ bkt, unsigned int* __restrict__ hist, SchedSummary* __restrict__ sum,
+                                uint64_t* __restrict__ rank_base)
 {
     __shared__ unsigned int s_count[NPH_NUM_CLASSES];
     __shared__ float s_cost[NPH_NUM_CLASSES];
@@ -61,6 +63,7 @@ __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n
         if (!ok) { atomicCAS(&sum->error, 0, (int)(j + 1)); cls[j] = 0; bkt[j] = 0; continue; }
         const uint32_t E = (jb.event_stop > jb.event_start ? jb.event_stop - jb.event_start : jb.event_start - jb.event_stop) + 1;
         const uint32_t K = jb.n_kmers;
+        if (codes) rank_base[j] = atomicAdd(&sum->rank_cursor, (unsigned long long)K);     // where this job's ranks will live
         uint32_t steps;
         const int c = nph_choose_class(K, E, &steps);
         const int C = c % NPH_MAX_COLS + 1;
@@ -112,6 +115,32 @@ __global__ void __launch_bounds__(1024) scan_kernel(const unsigned int* __restri
     for (int i = lo; i < hi; ++i) { o[i] = run; run += h[i]; }
 }
 
+// Base-code jobs (nph_hmm_*_seq): one warp per job turns the job's codes into its k-mer ranks — k-mer i of the strand's
+// string sits at i, or (rc) at length - i - k, HMMInputSequence::get_kmer_rank (nanopolish_hmm_input_sequence.h:60-66) —
+// at the slot classify_kernel reserved, then points the device copy of the job at them.  Every kernel after this one
+// (forward, Viterbi) reads ranks only.
+__global__ void __launch_bounds__(256) codes_to_ranks_kernel(nph_hmm_job* __restrict__ jobs, uint32_t n_jobs, const DevModelView* __restrict__ models,
+                                                             const uint8_t* __restrict__ codes, const uint64_t* __restrict__ rank_base,
+                                                             uint32_t* __restrict__ ranks)
+{
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_jobs; j += warps) {
+        const nph_hmm_job jb = jobs[j];
+        const uint8_t* __restrict__ cd = codes + jb.rank_off;
+        const uint32_t K = jb.n_kmers, mk = models[jb.model_id].k, A = models[jb.model_id].alphabet_size;
+        uint32_t* out = ranks + rank_base[j];
+        for (uint32_t i = lane; i < K; i += 32) {
+            const uint8_t* km = cd + (jb.rc ? K - 1 - i : i);
+            uint32_t r = 0;
+            for (uint32_t t = 0; t < mk; ++t) r = r * A + km[t];
+            out[i] = r;
+        }
+        __syncwarp();
+        if (lane == 0) jobs[j].rank_off = rank_base[j];
+    }
+}
+
 __global__ void scatter_kernel(uint32_t n_jobs, const uint8_t* __restrict__ cls, const uint16_t* __restrict__ bkt,
                                unsigned int* __restrict__ offs, uint32_t* __restrict__ order)
 {
@@ -132,6 +161,7 @@ int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uin
     if ((rc = nph_reserve(ctx, ctx->d_sched_cls, n_jobs)) != NPH_OK) return rc;
     if ((rc = nph_reserve(ctx, ctx->d_sched_bkt, n_jobs)) != NPH_OK) return rc;
     if ((rc = nph_reserve(ctx, ctx->d_sched_hist, 2 * hist_n + 1024)) != NPH_OK) return rc;
+    if (ctx->codes_mode && (rc = nph_reserve(ctx, ctx->d_rank_base, n_jobs)) != NPH_OK) return rc;
     unsigned int* hist = ctx->d_sched_hist.p;
     unsigned int* offs = hist + hist_n;
     SchedSummary* d_sum = reinterpret_cast<SchedSummary*>(offs + hist_n);
@@ -143,7 +173,7 @@ int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uin
     classify_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->d_jobs.p, (uint32_t)n_jobs, ctx->d_reads.p, (uint32_t)ctx->n_reads,
                                                         ctx->d_models.p, ctx->d_ranks.p, ctx->codes_mode ? ctx->d_codes.p : nullptr, (uint32_t)ctx->models.size(), (uint64_t)n_ranks_total,
                                                         (uint32_t)(ctx->levels_inflight ? ctx->level_chunk_events : 0), ctx->d_sched_cls.p,
-                                                        ctx->d_sched_bkt.p, hist, d_sum);
+                                                        ctx->d_sched_bkt.p, hist, d_sum, ctx->codes_mode ? ctx->d_rank_base.p : nullptr);
     NPH_CUDA(ctx, cudaGetLastError());
     scan_kernel<<<NPH_NUM_CLASSES, 1024, 0, ctx->stream>>>(hist, offs, d_sum);
     NPH_CUDA(ctx, cudaGetLastError());
@@ -155,6 +185,13 @@ int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uin
     if (h.error != 0) {
         ctx->last_error = "job " + std::to_string(h.error - 1) + " fails validation (read/model index, event range, stride, rank range or a k-mer rank outside the model)";
         return NPH_ERR_INVALID;
+    }
+    if (ctx->codes_mode) {
+        // the ranks the kernels read: formed here, once, from the codes (the jobs' device copies now index d_ranks)
+        if ((rc = nph_reserve(ctx, ctx->d_ranks, (size_t)h.rank_cursor)) != NPH_OK) return rc;
+        const int wblocks = (int)std::min<size_t>((n_jobs + 7) / 8, (size_t)ctx->sm_count * 8);
+        codes_to_ranks_kernel<<<wblocks, 256, 0, ctx->stream>>>(ctx->d_jobs.p, (uint32_t)n_jobs, ctx->d_models.p, ctx->d_codes.p, ctx->d_rank_base.p, ctx->d_ranks.p);
+        NPH_CUDA(ctx, cudaGetLastError());
     }
     ctx->classes.clear();
     size_t first = 0;

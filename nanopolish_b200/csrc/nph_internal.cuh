@@ -78,6 +78,7 @@ struct nph_ctx {
     DevBuf<uint32_t> d_ranks;
     DevBuf<uint8_t> d_codes;         // jobs loaded through the *_seq calls: base codes instead of k-mer ranks (jobs' rank_off index this)
     bool codes_mode = false;
+    DevBuf<uint64_t> d_rank_base;    // base-code jobs: where each job's ranks start in d_ranks (hmm_schedule.cu)
     DevBuf<nph_hmm_job> d_jobs;
     DevBuf<float2> d_trans;          // per read: (lp_mm_self, lp_mm_next)
     DevBuf<uint32_t> d_order;        // job indices grouped by kernel class, heavy first
