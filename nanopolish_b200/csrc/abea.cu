@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
         // Band 1 (the state we start from): lo = -50, only cell (event 0, trim column) = lp_trim.
         int lo = -kBW / 2;                       // band 1: kmer_idx = -1 - 50
         int cs[4];                               // column currently held by each register slot
-        float b1[4], dg[4];                      // own column in band bi-1 ; left column in band bi-2
+        float b1[4];                             // own column in band bi-1
+        double b1d[4], dgd[4];                   // the same widened (every band value enters three sums as a double: widen it once) ; left column in band bi-2
         float mu[4], sd[4], cc[4], ry[4], xn[4];
         {
             const int ulo = lo + 128;
@@ -133,7 +134,8 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
             for (int s = 0; s < 4; ++s) {
                 cs[s] = base + 32 * ((s - s0) & 3) - 128;
                 b1[s] = (cs[s] == 0) ? (float)lp_trim : NEG;      // band 1, trim cell of event 0
-                dg[s] = (cs[s] == 1) ? 0.0f : NEG;                // band 0: start cell (-1,-1) = 0 is left-diag of column 1
+                b1d[s] = (double)b1[s];
+                dgd[s] = (cs[s] == 1) ? 0.0 : (double)NEG;        // band 0: start cell (-1,-1) = 0 is left-diag of column 1
                 mu[s] = 0.f; sd[s] = 1.f; cc[s] = 0.f; ry[s] = 1.f; xn[s] = 0.f;
                 if (cs[s] >= 1 && cs[s] <= K) {
                     const float4 g = prm[cs[s] - 1];
@@ -160,11 +162,11 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
                 right = (ll == NEG && ur == NEG) ? ((bi & 1) == 1) : (ll < ur);
             }
             // left neighbour column in band bi-1 (lane 0's neighbour lives in lane 31, previous slot)
-            float lf[4];
+            double lfd[4];
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-                const float send = (lane == 31) ? b1[(s + 3) & 3] : b1[s];
-                lf[s] = __shfl_sync(kFull, send, (lane + 31) & 31);
+                const double send = (lane == 31) ? b1d[(s + 3) & 3] : b1d[s];
+                lfd[s] = __shfl_sync(kFull, send, (lane + 31) & 31);
             }
             if (right) {
                 // column `lo` leaves the band for good: exactly one (lane, slot) owns it; that slot now follows
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
                     const float4 g = g_next;
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
-                        if (s == sl) { cs[s] = cn; b1[s] = NEG; dg[s] = NEG; lf[s] = NEG; mu[s] = g.x; sd[s] = g.y; cc[s] = g.z; ry[s] = g.w; }
+                        if (s == sl) { cs[s] = cn; b1[s] = NEG; b1d[s] = (double)NEG; dgd[s] = (double)NEG; lfd[s] = (double)NEG; mu[s] = g.x; sd[s] = g.y; cc[s] = g.z; ry[s] = g.w; }
                     }
                 }
                 lo += 1;
@@ -197,17 +199,18 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
                 const float a = div_by_cached_rcp(__fsub_rn(x, mu[s]), sd[s], ry[s]);
                 const float em = __fadd_rn(cc[s], __fmul_rn(__fmul_rn(-0.5f, a), a));
                 const double emd = (double)em;
-                const float score_d = (float)__dadd_rn(__dadd_rn((double)dg[s], lp_step), emd);
-                const float score_u = (float)__dadd_rn(__dadd_rn((double)b1[s], lp_stay), emd);
-                const float score_l = (float)__dadd_rn((double)lf[s], lp_skip);
+                const float score_d = (float)__dadd_rn(__dadd_rn(dgd[s], lp_step), emd);
+                const float score_u = (float)__dadd_rn(__dadd_rn(b1d[s], lp_stay), emd);
+                const float score_l = (float)__dadd_rn(lfd[s], lp_skip);
                 float mx = score_d;
                 int from = kFromD;
                 mx = score_u > mx ? score_u : mx;
                 from = (mx == score_u) ? kFromU : from;
                 mx = score_l > mx ? score_l : mx;
                 from = (mx == score_l) ? kFromL : from;
-                dg[s] = lf[s];
+                dgd[s] = lfd[s];
                 b1[s] = cell ? mx : NEG;
+                b1d[s] = (double)b1[s];
                 tbyte |= (uint32_t)(cell ? from : 0) << (2 * s);
                 // next band's event for this column (clamped: the value is unused when the cell does not exist)
                 xn[s] = lv[min(max(e + 1, 0), E - 1)];
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
                     const int e = bi - 1;
-                    if (cs[s] == 0 && e < E) { b1[s] = (float)__dmul_rn(lp_trim, (double)(e + 1)); tbyte |= (uint32_t)kFromU << (2 * s); }
+                    if (cs[s] == 0 && e < E) { b1[s] = (float)__dmul_rn(lp_trim, (double)(e + 1)); b1d[s] = (double)b1[s]; tbyte |= (uint32_t)kFromU << (2 * s); }
                 }
             }
             trace[(size_t)bi * 32 + lane] = (uint8_t)tbyte;

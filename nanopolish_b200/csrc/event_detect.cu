@@ -498,8 +498,12 @@ __device__ __forceinline__ double ddiv_by_cached_rcp(double a, double b, double 
     return __fma_rn(r1, y, q1);
 }
 
-// compute_tstat's loop body (event_detection.c:91-112) for one window, from the exact left/right window sums
-__device__ __forceinline__ float tstat_windows(double sl, double ql, double sr, double qr, float wf, float rf, double wd, double rd)
+// compute_tstat's loop body (event_detection.c:91-112) for one window, from the exact left/right window sums.
+// Branch-free fast form: returns the candidate and whether it is proven (see the header); the caller runs
+// tstat_windows_exact for the rare unproven position.  Straight-line so the two windows of a position interleave.
+struct TsCand { float t; float combined_var, delta_mean; bool proven; };
+
+__device__ __forceinline__ TsCand tstat_windows(double sl, double ql, double sr, double qr, float wf, float rf, double wd, double rd)
 {
     const float sum2 = (float)sr, sumsq2 = (float)qr;
     const float mean1 = (float)ddiv_by_cached_rcp(sl, wd, rd);
@@ -507,78 +511,136 @@ __device__ __forceinline__ float tstat_windows(double sl, double ql, double sr, 
     double cv = __dsub_rn(ddiv_by_cached_rcp(ql, wd, rd), (double)__fmul_rn(mean1, mean1));
     cv = __dadd_rn(cv, (double)div_by_cached_rcp(sumsq2, wf, rf));
     cv = __dsub_rn(cv, (double)__fmul_rn(mean2, mean2));
-    const float combined_var = fmaxf((float)cv, FLT_MIN);
-    const float delta_mean = __fsub_rn(mean2, mean1);
-    if (combined_var >= 8.6736174e-19f /*2^-60*/ && combined_var <= 1.1529215e18f /*2^60*/) {
-        if (delta_mean == 0.0f) return 0.0f;
-        const float v = div_by_cached_rcp(combined_var, wf, rf);
-        const double y = __dmul_rn(fabs((double)delta_mean), rsqrt((double)v));
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(y);
-        const uint32_t lo = (uint32_t)bits & 0x1FFFFFFFu, ex = (uint32_t)(bits >> 52);
-        if ((lo - 0x10000000u + 1024u) >= 2048u && (ex - 923u) < 200u) return (float)y;
-    }
+    TsCand c;
+    c.combined_var = fmaxf((float)cv, FLT_MIN);
+    c.delta_mean = __fsub_rn(mean2, mean1);
+    const bool in_range = c.combined_var >= 8.6736174e-19f /*2^-60*/ && c.combined_var <= 1.1529215e18f /*2^60*/;
+    const float v = div_by_cached_rcp(c.combined_var, wf, rf);
+    const double y = __dmul_rn(fabs((double)c.delta_mean), rsqrt((double)v));
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(y);
+    const uint32_t lo = (uint32_t)bits & 0x1FFFFFFFu, ex = (uint32_t)(bits >> 52);
+    // a zero difference of means is exactly 0 (v > 0); otherwise y must be a normal float well away from a rounding boundary
+    c.proven = in_range && (c.delta_mean == 0.0f || ((lo - 0x10000000u + 1024u) >= 2048u && (ex - 923u) < 200u));
+    c.t = (float)y;
+    return c;
+}
+
+__device__ __noinline__ float tstat_windows_exact(float combined_var, float delta_mean, float wf)
+{
     return (float)__ddiv_rn(fabs((double)delta_mean), __dsqrt_rn((double)__fdiv_rn(combined_var, wf)));
 }
 
-// both t-statistics at position pos of a read (0 where compute_tstat leaves its zeros), and the guard's view of x[pos]
+// A row of the tile: the 32 positions [p0 + w2, p0 + w2 + 32) of one lane's range.  The warp first stages the row and its
+// halo (32 + 2*w2 samples from p0; zeros outside the read) in shared memory as doubles — x and the float product x*x,
+// each sample converted ONCE (the float->double conversion is the scarce resource here: 8.5 clk per warp instruction,
+// profiles/r02_ubench_cvt.txt) — and feeds the exactness guard with the samples it touches.
+constexpr int kRowBuf = 32 + 2 * kMaxW2;
+
+struct RowRegs { float v0, v1; };          // the two samples of a row this lane stages: slots lane and lane + 32
+
+// issue the global loads of a row (p0 = first staged position; it may have wrapped below 0: such positions fail p < n)
+__device__ __forceinline__ RowRegs load_row(const float* __restrict__ x, uint32_t n, uint32_t p0, uint32_t w2, int lane)
+{
+    RowRegs r{0.0f, 0.0f};
+    const uint32_t pa = p0 + (uint32_t)lane, pb = pa + 32u;
+    if (pa < n) r.v0 = x[pa];
+    if ((uint32_t)lane < 2u * w2 && pb < n) r.v1 = x[pb];
+    return r;
+}
+
+__device__ __forceinline__ void stage_row(const RowRegs& r, uint32_t w2, double* __restrict__ sdx, double* __restrict__ sdq, GuardAcc& ga, int lane)
+{
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t s = (uint32_t)lane + 32u * h;
+        if (h == 1 && s >= 32u + 2u * w2) break;
+        const float v = h ? r.v1 : r.v0;
+        const float q = __fmul_rn(v, v);
+        const uint32_t vb = __float_as_uint(v) & 0x7fffffffu, qb = __float_as_uint(q);
+        ga.vmax = max(ga.vmax, vb); ga.qmax = max(ga.qmax, qb);
+        ga.vmin = min(ga.vmin, vb ? vb : 0xffffffffu); ga.qmin = min(ga.qmin, qb ? qb : 0xffffffffu);
+        sdx[s] = (double)v; sdq[s] = (double)q;
+    }
+}
+
+// both t-statistics at position pos (staged slot lane + w2) of a read; 0 where compute_tstat leaves its zeros
 template <int W1, int W2>
-__device__ __forceinline__ void tstat_pair(const float* __restrict__ x, uint32_t n, uint32_t pos, const TsConsts& tc, float& a, float& b, GuardAcc& ga)
+__device__ __forceinline__ void tstat_pair(const double* __restrict__ sdx, const double* __restrict__ sdq, uint32_t n, uint32_t pos,
+                                           const TsConsts& tc, int lane, float& a, float& b)
 {
     const uint32_t w1 = W1 ? (uint32_t)W1 : tc.w1, w2 = W2 ? (uint32_t)W2 : tc.w2;
     // compute_tstat leaves zeros when the signal is shorter than two windows or the window shorter than 2 (:73-:76), and at the ends
     const bool v1 = w1 >= 2 && n >= 2 * w1 && pos >= w1 && pos <= n - w1, v2 = w2 >= 2 && n >= 2 * w2 && pos >= w2 && pos <= n - w2;
-    const float xc = x[pos];
-    {
-        const uint32_t vb = __float_as_uint(xc) & 0x7fffffffu, qb = __float_as_uint(__fmul_rn(xc, xc));
-        ga.vmax = max(ga.vmax, vb); ga.qmax = max(ga.qmax, qb);
-        ga.vmin = min(ga.vmin, vb ? vb : 0xffffffffu); ga.qmin = min(ga.qmin, qb ? qb : 0xffffffffu);
-    }
     a = 0.0f; b = 0.0f;
     if (!(v1 || v2)) return;
+    const double* cx = sdx + lane + w2;                                  // cx[0] = x[pos]; cx[-1-j] left window, cx[j] right window
+    const double* cq = sdq + lane + w2;
+    // both windows unconditionally (the staged row has the halo; a window that does not apply is discarded below)
     double sl = 0.0, ql = 0.0, sr = 0.0, qr = 0.0;
 #pragma unroll
-    for (uint32_t j = 0; j < w1; ++j) {
-        const float xl = x[pos - 1 - j], xr = j == 0 ? xc : x[pos + j];
-        sl = __dadd_rn(sl, (double)xl); ql = __dadd_rn(ql, (double)__fmul_rn(xl, xl));
-        sr = __dadd_rn(sr, (double)xr); qr = __dadd_rn(qr, (double)__fmul_rn(xr, xr));
+    for (int j = 0; j < (int)w1; ++j) {
+        sl = __dadd_rn(sl, cx[-1 - j]); ql = __dadd_rn(ql, cq[-1 - j]);
+        sr = __dadd_rn(sr, cx[j]); qr = __dadd_rn(qr, cq[j]);
     }
-    if (v1) a = tstat_windows(sl, ql, sr, qr, tc.w1f, tc.r1f, tc.w1d, tc.r1d);
-    if (v2) {
+    const TsCand ca = tstat_windows(sl, ql, sr, qr, tc.w1f, tc.r1f, tc.w1d, tc.r1d);
 #pragma unroll
-        for (uint32_t j = w1; j < w2; ++j) {
-            const float xl = x[pos - 1 - j], xr = x[pos + j];
-            sl = __dadd_rn(sl, (double)xl); ql = __dadd_rn(ql, (double)__fmul_rn(xl, xl));
-            sr = __dadd_rn(sr, (double)xr); qr = __dadd_rn(qr, (double)__fmul_rn(xr, xr));
-        }
-        b = tstat_windows(sl, ql, sr, qr, tc.w2f, tc.r2f, tc.w2d, tc.r2d);
+    for (int j = (int)w1; j < (int)w2; ++j) {
+        sl = __dadd_rn(sl, cx[-1 - j]); ql = __dadd_rn(ql, cq[-1 - j]);
+        sr = __dadd_rn(sr, cx[j]); qr = __dadd_rn(qr, cq[j]);
     }
+    const TsCand cb = tstat_windows(sl, ql, sr, qr, tc.w2f, tc.r2f, tc.w2d, tc.r2d);
+    a = ca.t; b = cb.t;
+    if (v1 && !ca.proven) a = tstat_windows_exact(ca.combined_var, ca.delta_mean, tc.w1f);
+    if (v2 && !cb.proven) b = tstat_windows_exact(cb.combined_var, cb.delta_mean, tc.w2f);
+    if (!v1) a = 0.0f;
+    if (!v2) b = 0.0f;
 }
+
+struct FusedSmem {
+    float a[32][33], b[32][33];          // the tile of t-statistics: row = lane that will consume it
+    double dx[kRowBuf], dq[kRowBuf];     // one staged row: samples and their float squares, widened
+};
 
 // One cooperative walk: lane l walks [from_l, from_l + len_l), the first wlen_l steps being warm-up (state only); at
 // step wlen_l the state is snapshotted and from there boundaries are counted and recorded into region[0..R).
 template <int W1, int W2>
 __device__ __forceinline__ uint32_t fused_walk(PeakState& st, PeakState& snap, const TsConsts& tc, const PeakConsts& k,
                                                const float* __restrict__ x, uint32_t n, uint32_t from, uint32_t len, uint32_t wlen,
-                                               uint32_t* __restrict__ region, uint32_t R, GuardAcc& ga, float (*sa)[33], float (*sb)[33], int lane)
+                                               uint32_t* __restrict__ region, uint32_t R, GuardAcc& ga, FusedSmem& sm, int lane)
 {
+    const uint32_t w2 = W2 ? (uint32_t)W2 : tc.w2;
     uint32_t maxlen = len;
     for (int o = 16; o; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
     uint32_t cnt = 0;
     for (uint32_t c = 0; c < maxlen; c += 32) {
-        for (int rr = 0; rr < 32; ++rr) {
-            const uint32_t fr = __shfl_sync(0xffffffffu, from, rr), ln = __shfl_sync(0xffffffffu, len, rr);
-            if (c >= ln) continue;                                       // warp-uniform
-            float a = 0.0f, b = 0.0f;
-            if (c + lane < ln) tstat_pair<W1, W2>(x, n, fr + c + lane, tc, a, b, ga);
-            sa[rr][lane] = a; sb[rr][lane] = b;
+        // rows are software-pipelined: the samples of the next row are in flight while this row's statistics are computed.
+        // The loop starts one row early (rr = -1 only loads) so that `cur` is never the direct target of a load: a load into it
+        // on the entry path would make ptxas encode a scoreboard wait at its first use that, inside the loop, also waits for
+        // the prefetch just issued (measured: 24 % of all stall samples sat on that one instruction).
+        if (c + 32 < len) asm volatile("prefetch.global.L2 [%0];" :: "l"(x + from + c + 32 + w2));     // my next tile's line
+        uint32_t fr = 0, ln = 0;
+        RowRegs cur{0.0f, 0.0f};
+#pragma unroll 1
+        for (int rr = -1; rr < 32; ++rr) {
+            const uint32_t fr_n = __shfl_sync(0xffffffffu, from, (rr + 1) & 31), ln_n = __shfl_sync(0xffffffffu, len, (rr + 1) & 31);
+            RowRegs nxt{0.0f, 0.0f};
+            if (rr < 31 && c < ln_n) nxt = load_row(x, n, fr_n + c - w2, w2, lane);
+            if (rr >= 0 && c < ln) {                                     // warp-uniform
+                stage_row(cur, w2, sm.dx, sm.dq, ga, lane);
+                __syncwarp();
+                float a = 0.0f, b = 0.0f;
+                if (c + lane < ln) tstat_pair<W1, W2>(sm.dx, sm.dq, n, fr + c + lane, tc, lane, a, b);
+                sm.a[rr][lane] = a; sm.b[rr][lane] = b;
+                __syncwarp();
+            }
+            cur = nxt; fr = fr_n; ln = ln_n;
         }
-        __syncwarp();
         if (c == wlen) snap = st;
         const bool rec = c >= wlen;
         const uint32_t steps = len > c ? min(32u, len - c) : 0u;
         for (uint32_t t = 0; t < steps; ++t) {
             int e0, e1;
-            peak_step(st, k, from + c + t, sa[lane][t], sb[lane][t], e0, e1);
+            peak_step(st, k, from + c + t, sm.a[lane][t], sm.b[lane][t], e0, e1);
             if (rec && e0 >= 0) { if (cnt < R) region[cnt] = (uint32_t)e0; ++cnt; }
             if (rec && e1 >= 0) { if (cnt < R) region[cnt] = (uint32_t)e1; ++cnt; }
         }
@@ -589,36 +651,55 @@ __device__ __forceinline__ uint32_t fused_walk(PeakState& st, PeakState& snap, c
 
 constexpr uint32_t kFusedWarm = 128;      // multiple of 32; $NPH_EVENTS_WARMUP overrides (rounded up to 32)
 
-template <int W1, int W2>
-__global__ void __launch_bounds__(kPeakWarps * 32) ed_fused_kernel(const FastParams p, const TsConsts tc)
+__device__ __forceinline__ void read_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
+
+// WPR warps walk one read as 32*WPR segments (a CTA of kPeakWarps warps holds kPeakWarps / WPR reads): small batches
+// and the tail of a large one get WPR times the parallelism for warm / segment more work.
+template <int W1, int W2, int WPR>
+__global__ void __launch_bounds__(kPeakWarps * 32, 5) ed_fused_kernel(const FastParams p, const TsConsts tc)
 {
-    __shared__ float s_a[kPeakWarps][32][33], s_b[kPeakWarps][32][33];
+    constexpr int LANES = 32 * WPR;
+    __shared__ FusedSmem s_mem[kPeakWarps];
+    __shared__ PeakState s_last[kPeakWarps];               // final state of each warp's lane 31
+    __shared__ GuardAcc s_guard[kPeakWarps];
+    __shared__ uint32_t s_flag[kPeakWarps], s_over[kPeakWarps], s_cnt[kPeakWarps * 32];
     const int wib = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t slot = blockIdx.x * kPeakWarps + (threadIdx.x >> 5);
+    const int rslot = wib / WPR, part = wib % WPR, w0 = rslot * WPR;          // this warp's read within the CTA, its part of it
+    const uint32_t slot = blockIdx.x * (kPeakWarps / WPR) + rslot;
     if (slot >= p.n_reads) return;
+    const int bar_id = 1 + rslot;                                          // named barrier of the read's WPR warps
     const uint32_t ridx = p.order[slot];
     const nph_raw_read rd = p.reads[ridx];
     const uint32_t n = rd.n_samples;
     const float* __restrict__ x = p.raw + rd.sample_off;
     uint32_t* peaks = p.peaks + rd.event_off;
     const uint32_t cap_peaks = rd.event_cap ? rd.event_cap - 1 : 0;       // events = boundaries + 1
-    const uint32_t R = cap_peaks / 32;                                    // a lane's slice of the peak array
-    uint32_t* region = peaks + (size_t)lane * R;
+    const uint32_t R = cap_peaks / LANES;                                 // a lane's slice of the peak array
+    const uint32_t gl = (uint32_t)part * 32u + (uint32_t)lane;             // lane within the read
+    uint32_t* region = peaks + (size_t)gl * R;
     const PeakConsts k{p.t1, p.t2, p.peak_height, p.w1, p.w1 / 2, p.w2 / 2};
 
-    const uint32_t seg = ((n + 31) / 32 + 31) / 32 * 32;                   // segment length, multiple of 32
-    const uint32_t b0 = min(n, (uint32_t)lane * seg), b1 = min(n, b0 + seg);
+    const uint32_t seg = ((n + LANES - 1) / LANES + 31) / 32 * 32;         // segment length, multiple of 32
+    const uint32_t b0 = (unsigned long long)gl * seg < n ? gl * seg : n, b1 = min(n, b0 + seg);
     const bool mine = b0 < n;                                              // lanes past the end of the read own nothing
     const uint32_t a0 = b0 > p.warm ? b0 - p.warm : 0;                     // b0, warm multiples of 32: so is the warm-up length
     GuardAcc ga{0xffffffffu, 0u, 0xffffffffu, 0u};
     PeakState st = fresh_state(), snap = st;
     uint32_t cnt = fused_walk<W1, W2>(st, snap, tc, k, x, n, mine ? a0 : 0u, mine ? b1 - a0 : 0u, mine ? b0 - a0 : 0u, region, R, ga,
-                                      s_a[wib], s_b[wib], lane);
+                                      s_mem[wib], lane);
     // ---- the guard (ed_guard_kernel's test, plus the operand range the cached-reciprocal divisions are proven for) ----
     for (int o = 16; o; o >>= 1) {
         ga.vmin = min(ga.vmin, __shfl_xor_sync(0xffffffffu, ga.vmin, o)); ga.vmax = max(ga.vmax, __shfl_xor_sync(0xffffffffu, ga.vmax, o));
         ga.qmin = min(ga.qmin, __shfl_xor_sync(0xffffffffu, ga.qmin, o)); ga.qmax = max(ga.qmax, __shfl_xor_sync(0xffffffffu, ga.qmax, o));
+    }
+    if (WPR > 1) {
+        if (lane == 0) s_guard[wib] = ga;
+        read_barrier(bar_id, LANES);
+        for (int w = 0; w < WPR; ++w) {
+            const GuardAcc g = s_guard[w0 + w];
+            ga.vmin = min(ga.vmin, g.vmin); ga.vmax = max(ga.vmax, g.vmax); ga.qmin = min(ga.qmin, g.qmin); ga.qmax = max(ga.qmax, g.qmax);
+        }
     }
     bool exact;
     {
@@ -628,44 +709,63 @@ __global__ void __launch_bounds__(kPeakWarps * 32) ed_fused_kernel(const FastPar
         const int evx = (int)(ga.vmax >> 23), evn = (int)(ga.vmin >> 23), eqx = (int)(ga.qmax >> 23), eqn = (int)(ga.qmin >> 23);
         const bool okx = ga.vmax == 0u || (evn >= 97 && evx <= 157 && lg + evx + 24 - evn <= 53);       // |x| in [2^-30, 2^31)
         const bool okq = ga.qmax == 0u || (eqn >= 66 && eqx <= 188 && lg + eqx + 24 - eqn <= 53);       // x*x in [2^-61, 2^62)
-        exact = okx && okq;
+        exact = okx && okq;                                                // the same in every warp of the read
     }
     // ---- verification and repair: my snapshot must equal the final state of the lane to my left ----
-    bool over = false;
     uint32_t repairs = 0;
-    for (int round = 0; exact && round < 32; ++round) {
+    for (int round = 0; exact && round < LANES; ++round) {
+        if (WPR > 1) {
+            if (lane == 31) s_last[wib] = st;
+            read_barrier(bar_id, LANES);
+        }
         PeakState left;
         left.m0 = __shfl_up_sync(0xffffffffu, st.m0, 1); left.m1 = __shfl_up_sync(0xffffffffu, st.m1, 1);
         left.pp0 = __shfl_up_sync(0xffffffffu, st.pp0, 1); left.pp1 = __shfl_up_sync(0xffffffffu, st.pp1, 1);
         left.pv0 = __shfl_up_sync(0xffffffffu, st.pv0, 1); left.pv1 = __shfl_up_sync(0xffffffffu, st.pv1, 1);
         left.v0 = __shfl_up_sync(0xffffffffu, st.v0, 1); left.v1 = __shfl_up_sync(0xffffffffu, st.v1, 1);
-        const bool ok = !mine || lane == 0 || same_state(snap, left);
-        if (__all_sync(0xffffffffu, ok)) break;
+        if (WPR > 1 && lane == 0 && part > 0) left = s_last[wib - 1];
+        const bool ok = !mine || gl == 0 || same_state(snap, left);
+        bool all_ok = __all_sync(0xffffffffu, ok);
+        if (WPR > 1) {
+            if (lane == 0) s_flag[wib] = all_ok ? 1u : 0u;
+            read_barrier(bar_id, LANES);
+            all_ok = true;
+            for (int w = 0; w < WPR; ++w) all_ok = all_ok && s_flag[w0 + w] != 0u;
+        }
+        if (all_ok) break;
         // re-walk the segments that started from a wrong state, now from the neighbour's final state (lanes 0..round are right)
         PeakState s2 = ok ? st : left, sn2 = s2;
         GuardAcc g2{0xffffffffu, 0u, 0xffffffffu, 0u};
-        const uint32_t c2 = fused_walk<W1, W2>(s2, sn2, tc, k, x, n, ok ? 0u : b0, ok ? 0u : b1 - b0, 0u, region, R, g2, s_a[wib], s_b[wib], lane);
+        const uint32_t c2 = fused_walk<W1, W2>(s2, sn2, tc, k, x, n, ok ? 0u : b0, ok ? 0u : b1 - b0, 0u, region, R, g2, s_mem[wib], lane);
         if (!ok) { st = s2; snap = left; cnt = c2; }
         ++repairs;
     }
-    over = cnt > R;
-    if (__any_sync(0xffffffffu, over)) exact = false;                      // a lane's slice was too small: streaming fallback
-    uint32_t incl = cnt;
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    // ---- counts of all the read's lanes, then its first warp compacts the slices ----
+    const bool over = __any_sync(0xffffffffu, cnt > R);                    // a lane's slice was too small: streaming fallback
+    s_cnt[w0 * 32 + gl] = cnt;
+    if (lane == 0) s_over[wib] = over ? 1u : 0u;
+    if (WPR > 1) read_barrier(bar_id, LANES); else __syncwarp();
+    if (part != 0) return;
+    for (int w = 0; w < WPR; ++w) if (s_over[w0 + w]) exact = false;
+    const uint32_t* cnts = s_cnt + w0 * 32;
+    uint32_t total = 0;
+    for (int s = 0; s < LANES; ++s) total += cnts[s];
     if (exact && total <= cap_peaks) {
-        // compact the 32 slices (lane 0's is in place); destinations never pass their sources, chunks go left to right
-        for (int s = 1; s < 32; ++s) {
-            const uint32_t cs = __shfl_sync(0xffffffffu, cnt, s), ds = __shfl_sync(0xffffffffu, incl - cnt, s);
+        // slice 0 is in place; destinations never pass their sources, slices and chunks go left to right
+        uint32_t ds = cnts[0];
+        for (int s = 1; s < LANES; ++s) {
+            const uint32_t cs = cnts[s];
             const uint32_t* src = peaks + (size_t)s * R;
-            if (ds == (uint32_t)s * R) continue;
-            for (uint32_t q = 0; q < cs; q += 32) {
-                uint32_t v = 0;
-                if (q + lane < cs) v = src[q + lane];
-                __syncwarp();
-                if (q + lane < cs) peaks[ds + q + lane] = v;
-                __syncwarp();
+            if (ds != (uint32_t)s * R) {
+                for (uint32_t q = 0; q < cs; q += 32) {
+                    uint32_t v = 0;
+                    if (q + lane < cs) v = src[q + lane];
+                    __syncwarp();
+                    if (q + lane < cs) peaks[ds + q + lane] = v;
+                    __syncwarp();
+                }
             }
+            ds += cs;
         }
     }
     if (lane == 0) {
@@ -677,6 +777,18 @@ __global__ void __launch_bounds__(kPeakWarps * 32) ed_fused_kernel(const FastPar
             else { p.n_peaks[ridx] = total; p.n_events[ridx] = total + 1; }
         }
     }
+}
+
+template <int WPR>
+static void launch_fused(const FastParams& f, const TsConsts& tc, size_t n_reads, cudaStream_t stream)
+{
+    const unsigned blocks = (unsigned)((n_reads + kPeakWarps / WPR - 1) / (kPeakWarps / WPR));
+    void (*kern)(const FastParams, const TsConsts) = ed_fused_kernel<0, 0, WPR>;
+    if (f.w1 == 3 && f.w2 == 6) kern = ed_fused_kernel<3, 6, WPR>;
+    else if (f.w1 == 7 && f.w2 == 14) kern = ed_fused_kernel<7, 14, WPR>;
+    // five CTAs per SM need the large shared-memory carve-out (static shared memory alone does not ask for it)
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    kern<<<blocks, kPeakWarps * 32, 0, stream>>>(f, tc);
 }
 
 // block per read, thread per event
@@ -736,6 +848,7 @@ int nph_detect_events_device(nph_ctx* ctx, const float* d_raw, size_t n_samples_
         const nph_raw_read& r = reads[i];
         if (r.n_samples == 0 || r.sample_off + r.n_samples > n_samples_total || r.event_off + r.event_cap > events_total || r.event_cap == 0)
             return NPH_ERR_INVALID;
+        if (r.n_samples > 0xFFFFFF00u) return NPH_ERR_UNSUPPORTED;      // position arithmetic is 32-bit with a 2*w2 halo
         keyed[i] = {r.n_samples, (uint32_t)i};
     }
     // threads of a warp walk reads of similar length: longest first
@@ -781,10 +894,14 @@ int nph_detect_events_device(nph_ctx* ctx, const float* d_raw, size_t n_samples_
         tc.w1f = (float)p.w1; tc.w2f = (float)p.w2; tc.r1f = 1.0f / tc.w1f; tc.r2f = 1.0f / tc.w2f;
         tc.w1d = (double)p.w1; tc.w2d = (double)p.w2; tc.r1d = 1.0 / tc.w1d; tc.r2d = 1.0 / tc.w2d;
         f.warm = getenv("NPH_EVENTS_WARMUP") ? ((uint32_t)atoi(getenv("NPH_EVENTS_WARMUP")) + 31u) / 32u * 32u : kFusedWarm;
-        const unsigned blocks = (unsigned)((n_reads + kPeakWarps - 1) / kPeakWarps);
-        if (p.w1 == 3 && p.w2 == 6) ed_fused_kernel<3, 6><<<blocks, kPeakWarps * 32, 0, ctx->stream>>>(f, tc);
-        else if (p.w1 == 7 && p.w2 == 14) ed_fused_kernel<7, 14><<<blocks, kPeakWarps * 32, 0, ctx->stream>>>(f, tc);
-        else ed_fused_kernel<0, 0><<<blocks, kPeakWarps * 32, 0, ctx->stream>>>(f, tc);
+        // warps per read: enough warps to fill the machine a few times over (20 resident per SM), capped by the read length
+        int wpr = 1;
+        const size_t want = (size_t)ctx->sm_count * 20 * 3;
+        while (wpr < 4 && n_reads * wpr < want && keyed[0].first / (64u * wpr) >= 4 * f.warm) wpr *= 2;
+        if (getenv("NPH_EVENTS_WPR")) wpr = atoi(getenv("NPH_EVENTS_WPR"));
+        if (wpr >= 4) launch_fused<4>(f, tc, n_reads, ctx->stream);
+        else if (wpr == 2) launch_fused<2>(f, tc, n_reads, ctx->stream);
+        else launch_fused<1>(f, tc, n_reads, ctx->stream);
         ++launches;
         NPH_CUDA(ctx, cudaGetLastError());
     } else {

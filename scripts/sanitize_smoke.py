@@ -55,4 +55,25 @@ assert (resu["status"] == 0).all() and (resu["n_records"] > 1000).all()
 prm = synth.event_params(True)
 out_rna = eng.load_from_raw_batch(flat, ranks, jobs, mid, prm)
 print("eventalign chain ok", [int(x) for x in resu["n_windows"]], "rna prologue", [int(c) for c in out_rna[6]["status"]])
+# round 2: base-code jobs (ranks formed by the scheduler's pre-pass), call-methylation enumerated on the device (pair and compact forms),
+# variant screening rounds, and the fused event detector with 1 / 2 / 4 warps per read and the repair path (no warm-up)
+e = eng.hmm_score_batch_seq(rs.reads, rs.ev_mean, rs.ev_start_time, j1.seq_codes, j1.code_jobs)
+assert np.array_equal(e.view(np.uint32), a.view(np.uint32))
+ref_b, prs, recs = synth.methylation_records(rs, model_id=cid, rc_every=3)
+mp = synth.meth_params("cpg", 6)
+so1, sites1, sc1 = eng.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref_b, prs, recs, mp)
+dl, fe = synth.compact_event_alignment(recs, prs, int(recs["ref_len"].sum()))
+so2, sites2, sc2 = eng.methylation_batch_compact(rs.reads, rs.ev_mean, rs.ev_start_time, ref_b, dl, fe, recs, mp)
+assert sites1.shape[0] > 0 and sites1.tobytes() == sites2.tobytes()
+pref, prs_, precs, ppairs = synth.gen_pileup(150, 10, 110, nuc, seed=5, region_start=5000, n_true_variants=2)
+pdl, pfe = synth.compact_event_alignment(precs, ppairs, int(precs["ref_len"].sum()))
+q, nr, scored = eng.screen_edits_batch(prs_.reads, prs_.ev_mean, prs_.ev_start_time, synth._CODE2DNA[pref], pdl, pfe, precs,
+                                       synth.screen_params(5000, 6, 10, 30, 0, 4), indel_bias=0.9)
+assert np.isfinite(q[20:100]).any() and scored > 0
+for env in ({"NPH_EVENTS_WPR": "1"}, {"NPH_EVENTS_WPR": "2"}, {"NPH_EVENTS_WPR": "4"}, {"NPH_EVENTS_WPR": "2", "NPH_EVENTS_WARMUP": "0"}):
+    os.environ.update(env)
+    ev2 = eng.detect_events_batch(raw, rr, synth.event_params(False))
+    assert all(x.tobytes() == y.tobytes() for x, y in zip(evs, ev2))
+    for k_ in env: del os.environ[k_]
+print("round-2 kernels ok", sites1.shape[0], int(np.isfinite(q).sum()), [x.shape[0] for x in evs])
 eng.close()
