@@ -86,7 +86,7 @@ __device__ __forceinline__ void emit_event(nph_event* out, uint32_t& count, uint
     ++count;
 }
 
-// Fallback for reads whose prefix sums are not provably exact (see ed_guard_kernel): one thread streams one read.
+// Fallback for reads whose prefix sums are not provably exact (the guard of ed_fused_kernel): one thread streams one read.
 __global__ void __launch_bounds__(kThreads) detect_events_stream_kernel(const DetParams p)
 {
     extern __shared__ double s_ring[];                                // [2][ring][kThreads]: S then Q
@@ -185,13 +185,11 @@ __global__ void __launch_bounds__(kThreads) detect_events_stream_kernel(const De
 // which no parallel algorithm reproduces in general.  But when every partial sum is EXACTLY representable nothing
 // is ever rounded, so any summation order gives the same doubles, and every quantity the detector derives from
 // the prefix arrays (window sums of the t-statistics, segment sums of the events) equals the exact sum of the
-// samples involved.  ed_guard_kernel proves that per read: all samples are integer multiples of 2^L (L = smallest
-// ulp exponent present) and |partial sum| <= n * max|x| < 2^(ceil(log2 n) + Emax + 1); if that span fits 53 bits
-// (and likewise for the float squares) the read takes the parallel path, otherwise the streaming fallback.
+// samples involved.  The guard proves that per read: all samples are integer multiples of 2^L (L = smallest ulp
+// exponent present) and |partial sum| <= n * max|x| < 2^(ceil(log2 n) + Emax + 1); if that span fits 53 bits (and
+// likewise for the float squares) the read takes the parallel path, otherwise the streaming fallback above.
 // Real traces (40-200 pA) pass with ~10 bits to spare.
-//   ed_tstat_kernel : thread per sample, both windows from a 2*w2-sample stencil (exact FP64 window sums)
-//   ed_peaks_kernel : the short/long peak detector, a register state machine; lane per read, the t-statistics of
-//                     32 reads x 32 positions staged through shared memory so global loads stay coalesced
+//   ed_fused_kernel : guard + both t-statistics + the short/long peak detector in ONE pass over the samples
 //   ed_events_kernel: thread per event, exact FP64 segment sums -> start / length / mean / stdv
 // =============================================================================================================
 struct FastParams {
@@ -199,8 +197,6 @@ struct FastParams {
     const nph_raw_read* reads;
     const uint32_t* order;       // reads sorted by length (desc)
     uint32_t n_reads;
-    float* ts1;                  // per sample
-    float* ts2;
     uint32_t* peaks;             // per read at event_off, event_cap entries
     uint32_t* n_peaks;           // per read
     uint8_t* exact;              // per read: 1 = fast path
@@ -213,87 +209,15 @@ struct FastParams {
     uint32_t warm;
 };
 
-__device__ __forceinline__ int ulp_exp(float x)      // exponent of ulp(x) for finite nonzero x
-{
-    const int e = (int)((__float_as_uint(x) >> 23) & 0xff);
-    return (e == 0 ? -126 : e - 127) - 23;
-}
-
-__global__ void __launch_bounds__(256) ed_guard_kernel(const FastParams p)
-{
-    __shared__ int s_lx[8], s_ex[8], s_lp[8], s_ep[8], s_bad[8];
-    for (uint32_t r = blockIdx.x; r < p.n_reads; r += gridDim.x) {
-        const nph_raw_read rd = p.reads[r];
-        const float* x = p.raw + rd.sample_off;
-        int lx = 1000, ex = -1000, lp = 1000, ep = -1000, bad = 0;
-        for (uint32_t i = threadIdx.x; i < rd.n_samples; i += blockDim.x) {
-            const float v = x[i];
-            const float q = __fmul_rn(v, v);
-            if (!(fabsf(v) <= FLT_MAX) || !(q <= FLT_MAX)) { bad = 1; continue; }
-            if (v != 0.0f) { lx = min(lx, ulp_exp(v)); ex = max(ex, ulp_exp(v) + 23); }
-            if (q != 0.0f) { lp = min(lp, ulp_exp(q)); ep = max(ep, ulp_exp(q) + 23); }
-        }
-        for (int o = 16; o; o >>= 1) {
-            lx = min(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ex = max(ex, __shfl_xor_sync(0xffffffffu, ex, o));
-            lp = min(lp, __shfl_xor_sync(0xffffffffu, lp, o)); ep = max(ep, __shfl_xor_sync(0xffffffffu, ep, o));
-            bad |= __shfl_xor_sync(0xffffffffu, bad, o);
-        }
-        const int w = threadIdx.x >> 5;
-        if ((threadIdx.x & 31) == 0) { s_lx[w] = lx; s_ex[w] = ex; s_lp[w] = lp; s_ep[w] = ep; s_bad[w] = bad; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int k = 1; k < 8; ++k) { lx = min(lx, s_lx[k]); ex = max(ex, s_ex[k]); lp = min(lp, s_lp[k]); ep = max(ep, s_ep[k]); bad |= s_bad[k]; }
-            int lg = 0;
-            while ((1ull << lg) < (unsigned long long)rd.n_samples + 1) ++lg;      // ceil(log2(n + 1))
-            const bool okx = (ex < -500) || (lg + ex + 1 - lx <= 53);               // all zero, or span fits 53 bits
-            const bool okp = (ep < -500) || (lg + ep + 1 - lp <= 53);
-            p.exact[r] = (!bad && okx && okp) ? 1 : 0;
-        }
-        __syncthreads();
-    }
-}
-
-// grid: (tiles, reads).  thread -> position i of read blockIdx.y
-__global__ void __launch_bounds__(256) ed_tstat_kernel(const FastParams p)
-{
-    const uint32_t r = blockIdx.y;
-    if (!p.exact[r]) return;
-    const nph_raw_read rd = p.reads[r];
-    const unsigned long long n = rd.n_samples;
-    const float* __restrict__ x = p.raw + rd.sample_off;
-    const uint32_t w1 = p.w1, w2 = p.w2;
-    const bool on1 = !(n < 2ull * w1 || w1 < 2), on2 = !(n < 2ull * w2 || w2 < 2);
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        float a = 0.0f, b = 0.0f;
-        const bool v1 = on1 && i >= w1 && i <= n - w1, v2 = on2 && i >= w2 && i <= n - w2;
-        if (v1 || v2) {
-            // exact window sums: left = samples i-1, i-2, ...; right = samples i, i+1, ... (nested: w1 inside w2)
-            double sl = 0.0, ql = 0.0, sr = 0.0, qr = 0.0;
-            double sl1 = 0.0, ql1 = 0.0, sr1 = 0.0, qr1 = 0.0;
-            const uint32_t wmax = v2 ? w2 : w1;
-            for (uint32_t j = 0; j < wmax; ++j) {
-                const float xl = x[i - 1 - j], xr = x[i + j];
-                sl = __dadd_rn(sl, (double)xl); ql = __dadd_rn(ql, (double)__fmul_rn(xl, xl));
-                sr = __dadd_rn(sr, (double)xr); qr = __dadd_rn(qr, (double)__fmul_rn(xr, xr));
-                if (j + 1 == w1) { sl1 = sl; ql1 = ql; sr1 = sr; qr1 = qr; }
-            }
-            if (v1) a = tstat_at(0.0, 0.0, sl1, ql1, __dadd_rn(sl1, sr1), __dadd_rn(ql1, qr1), (float)w1);
-            if (v2) b = tstat_at(0.0, 0.0, sl, ql, __dadd_rn(sl, sr), __dadd_rn(ql, qr), (float)w2);
-        }
-        p.ts1[rd.sample_off + i] = a;
-        p.ts2[rd.sample_off + i] = b;
-    }
-}
-
 // ---- peak detector -------------------------------------------------------------------------------------------
 // short_long_peak_detector (event_detection.c:122-201) is a sequential state machine over the two t-statistic
 // vectors, ~36 000 dependent steps per read.  Its state is tiny and re-synchronises quickly (both detectors reset at
-// every boundary they emit, about every 9 samples), so a warp runs ONE read as 32 segments in parallel: lane k warms
-// up on the kWarm samples before its segment from a fresh state, snapshots the state at its segment start, runs the
-// segment counting boundaries; then every lane's snapshot is compared with its left neighbour's final state.  If all
-// 31 comparisons agree bit for bit, each lane provably started from the true sequential state (induction from lane 0,
-// which starts at sample 0), the counts are scanned and a second pass from the snapshots writes the boundaries in
-// order.  If any comparison fails the read is walked sequentially by one lane — exact either way.
+// every boundary they emit, about every 9 samples), so a read is walked as 32 (or 64, 128) segments in parallel: each
+// lane warms up on the samples before its segment from a fresh state, snapshots the state at its segment start and
+// runs the segment recording boundaries; then every lane's snapshot is compared with its left neighbour's final
+// state.  If all comparisons agree bit for bit, each lane provably started from the true sequential state (induction
+// from lane 0, which starts at sample 0).  A lane whose comparison fails re-walks its segment from the neighbour's
+// final state, and the check repeats — exact either way.
 struct PeakState {
     uint32_t m0, m1;         // masked_to
     int pp0, pp1;            // peak_pos (-1 = none yet)
@@ -351,135 +275,24 @@ __device__ __forceinline__ void peak_step(PeakState& st, const PeakConsts& k, ui
 }
 
 constexpr int kPeakWarps = 4;
-constexpr uint32_t kWarm = 512;      // default warm-up; $NPH_EVENTS_WARMUP overrides (0 forces the sequential walk: test hook)
-
-// walks [from, to) from state st; counts boundaries, and writes them at out[pos++] when WRITE
-template <bool WRITE>
-__device__ __forceinline__ uint32_t peak_walk(PeakState& st, const PeakConsts& k, const float* __restrict__ t1, const float* __restrict__ t2,
-                                              uint32_t from, uint32_t to, uint32_t* out, uint32_t pos, uint32_t cap_peaks)
-{
-    uint32_t cnt = 0;
-    for (uint32_t i = from; i < to; ++i) {
-        int e0, e1;
-        peak_step(st, k, i, t1[i], t2[i], e0, e1);
-        if (e0 >= 0) { if (WRITE && pos + cnt < cap_peaks) out[pos + cnt] = (uint32_t)e0; ++cnt; }
-        if (e1 >= 0) { if (WRITE && pos + cnt < cap_peaks) out[pos + cnt] = (uint32_t)e1; ++cnt; }
-    }
-    return cnt;
-}
-
-// Warp-cooperative walk: lane l walks [from_l, to_l) of the read, but the t-statistics are fetched as 32x32 tiles
-// (row rr = the next 32 positions of lane rr's range: one coalesced 128-byte load per row and vector), staged through
-// shared memory, with the next tile already in flight in registers while the state machines consume the current one.
-template <bool WRITE>
-__device__ __forceinline__ uint32_t peak_walk_tiled(PeakState& st, const PeakConsts& k, const float* __restrict__ t1,
-                                                    const float* __restrict__ t2, uint32_t from, uint32_t to, uint32_t* out,
-                                                    uint32_t pos, uint32_t cap_peaks, float (*sa)[33], float (*sb)[33], int lane)
-{
-    const uint32_t len = to > from ? to - from : 0;
-    uint32_t maxlen = len;
-    for (int o = 16; o; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-    uint32_t froms[32], lens[32];
-#pragma unroll
-    for (int rr = 0; rr < 32; ++rr) { froms[rr] = __shfl_sync(0xffffffffu, from, rr); lens[rr] = __shfl_sync(0xffffffffu, len, rr); }
-    float ra[32], rb[32];
-#pragma unroll
-    for (int rr = 0; rr < 32; ++rr) {
-        ra[rr] = 0.f; rb[rr] = 0.f;
-        if ((uint32_t)lane < lens[rr]) { ra[rr] = t1[froms[rr] + lane]; rb[rr] = t2[froms[rr] + lane]; }
-    }
-    uint32_t cnt = 0;
-    for (uint32_t c = 0; c < maxlen; c += 32) {
-#pragma unroll
-        for (int rr = 0; rr < 32; ++rr) { sa[rr][lane] = ra[rr]; sb[rr][lane] = rb[rr]; }
-        __syncwarp();
-        if (c + 32 < maxlen) {
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr) {
-                ra[rr] = 0.f; rb[rr] = 0.f;
-                if (c + 32 + lane < lens[rr]) { ra[rr] = t1[froms[rr] + c + 32 + lane]; rb[rr] = t2[froms[rr] + c + 32 + lane]; }
-            }
-        }
-        const uint32_t steps = len > c ? min(32u, len - c) : 0u;
-        for (uint32_t t = 0; t < steps; ++t) {
-            int e0, e1;
-            peak_step(st, k, from + c + t, sa[lane][t], sb[lane][t], e0, e1);
-            if (e0 >= 0) { if (WRITE && pos + cnt < cap_peaks) out[pos + cnt] = (uint32_t)e0; ++cnt; }
-            if (e1 >= 0) { if (WRITE && pos + cnt < cap_peaks) out[pos + cnt] = (uint32_t)e1; ++cnt; }
-        }
-        __syncwarp();
-    }
-    return cnt;
-}
-
-__global__ void __launch_bounds__(kPeakWarps * 32) ed_peaks_kernel(const FastParams p)
-{
-    __shared__ float s_a[kPeakWarps][32][33], s_b[kPeakWarps][32][33];
-    const int wib = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const uint32_t slot = blockIdx.x * kPeakWarps + (threadIdx.x >> 5);
-    if (slot >= p.n_reads) return;
-    const uint32_t ridx = p.order[slot];
-    if (!p.exact[ridx]) return;
-    const nph_raw_read rd = p.reads[ridx];
-    const uint32_t n = rd.n_samples;
-    const float* __restrict__ t1 = p.ts1 + rd.sample_off;
-    const float* __restrict__ t2 = p.ts2 + rd.sample_off;
-    uint32_t* peaks = p.peaks + rd.event_off;
-    const uint32_t cap_peaks = rd.event_cap ? rd.event_cap - 1 : 0;       // events = boundaries + 1
-    const PeakConsts k{p.t1, p.t2, p.peak_height, p.w1, p.w1 / 2, p.w2 / 2};
-
-    const uint32_t seg = ((n + 31) / 32 + 31) / 32 * 32;                   // segment length, multiple of 32
-    const uint32_t b0 = min(n, (uint32_t)lane * seg), b1 = min(n, b0 + seg);
-    const bool mine = b0 < n;                                              // lanes past the end of the read own nothing
-    const uint32_t a0 = b0 > p.warm ? b0 - p.warm : 0;
-    PeakState st = fresh_state();
-    // warm-up (lane 0 and early lanes: from sample 0); lanes past the end get empty ranges
-    peak_walk_tiled<false>(st, k, t1, t2, mine ? a0 : 0u, mine ? b0 : 0u, nullptr, 0, 0, s_a[wib], s_b[wib], lane);
-    const PeakState snap = st;
-    const uint32_t cnt = peak_walk_tiled<false>(st, k, t1, t2, mine ? b0 : 0u, mine ? b1 : 0u, nullptr, 0, 0, s_a[wib], s_b[wib], lane);
-    // verification: my snapshot must equal the final state of the lane to my left
-    PeakState left;
-    left.m0 = __shfl_up_sync(0xffffffffu, st.m0, 1); left.m1 = __shfl_up_sync(0xffffffffu, st.m1, 1);
-    left.pp0 = __shfl_up_sync(0xffffffffu, st.pp0, 1); left.pp1 = __shfl_up_sync(0xffffffffu, st.pp1, 1);
-    left.pv0 = __shfl_up_sync(0xffffffffu, st.pv0, 1); left.pv1 = __shfl_up_sync(0xffffffffu, st.pv1, 1);
-    left.v0 = __shfl_up_sync(0xffffffffu, st.v0, 1); left.v1 = __shfl_up_sync(0xffffffffu, st.v1, 1);
-    const bool ok = !mine || (a0 == 0) || same_state(snap, left);
-    const bool all_ok = __all_sync(0xffffffffu, ok);
-    uint32_t total;
-    if (all_ok) {
-        uint32_t incl = cnt;
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        total = __shfl_sync(0xffffffffu, incl, 31);
-        PeakState s2 = snap;
-        peak_walk_tiled<true>(s2, k, t1, t2, mine ? b0 : 0u, mine ? b1 : 0u, peaks, incl - cnt, cap_peaks, s_a[wib], s_b[wib], lane);
-    } else {
-        // some segment did not re-synchronise inside its warm-up: walk the read in order (exact, slow, rare)
-        total = 0;
-        if (lane == 0) { PeakState s2 = fresh_state(); total = peak_walk<true>(s2, k, t1, t2, 0, n, peaks, 0, cap_peaks); }
-        total = __shfl_sync(0xffffffffu, total, 0);
-    }
-    if (lane == 0) {
-        if (total > cap_peaks) { *p.overflow = 1; p.n_peaks[ridx] = 0; p.n_events[ridx] = 0; }
-        else { p.n_peaks[ridx] = total; p.n_events[ridx] = total + 1; }
-    }
-}
 
 // =============================================================================================================
-// Fused form of guard + t-statistics + peaks: ONE pass over the samples, nothing but the boundaries written.
-// The warp that owns a read walks it as 32 segments like ed_peaks_kernel, but the 32x32 tile of t-statistics each
-// lane consumes is COMPUTED by the warp from the raw samples (row rr = the next 32 positions of lane rr's range, one
-// lane per position: coalesced loads, the 2*w2 neighbours out of L1) instead of being read back from HBM, and the
-// exactness guard rides along on the samples the warp touches anyway.  Differences from the three-kernel form:
-//   * divisions by the window length are Markstein divisions by a cached reciprocal (exact_math.cuh), the final
+// ed_fused_kernel: guard + t-statistics + peaks in ONE pass over the samples; only the boundaries are written.
+// The warp(s) that own a read walk it as 32 (64, 128) segments; the 32x32 tile of t-statistics the lanes consume is
+// COMPUTED by the warp from the raw samples (row rr = the next 32 positions of lane rr's range, one lane per position:
+// the row and its 2*w2 halo are loaded coalesced one row ahead, widened ONCE and staged in shared memory), and the
+// exactness guard rides along on the samples the warp touches anyway.
+//   * what bounds it is not HBM but the float<->double conversion unit: compute_tstat needs >= 10 conversions per
+//     window and position however it is arranged (float sums, float means, float variance, double quotient), and a
+//     conversion costs 8.5 clk per warp instruction (scripts/ubench_cvt.cu, profiles/r02_ubench_cvt.txt)
+//   * divisions by the window length are Markstein divisions by a cached reciprocal (exact_math.cuh); the final
 //     |delta| / sqrt(v) is D * rsqrt(v) in FP64 (<= 2 ulp) rounded to float, accepted only when that FP64 value is
 //     more than 2^10 ulps away from a float rounding boundary (so the correctly rounded chain dsqrt -> ddiv -> float
 //     provably rounds to the same float); otherwise that position takes the reference's operations one by one
-//   * boundaries are recorded during the counting walk into a per-lane slice of the read's peak array and compacted
-//     afterwards: no second walk
+//   * boundaries are recorded during the walk into a per-lane slice of the read's peak array and compacted afterwards
 //   * a segment whose warm-up did not reach the true state is re-walked from its left neighbour's final state until
-//     the chain verifies (induction from lane 0), instead of handing the whole read to one lane
-// A read that fails the guard (or overflows a lane's slice) is flagged for the streaming fallback as before.
+//     the chain verifies (induction from lane 0)
+// A read that fails the guard (or overflows a lane's slice) is flagged for the streaming fallback.
 // =============================================================================================================
 struct TsConsts {
     uint32_t w1, w2;
@@ -688,7 +501,7 @@ __global__ void __launch_bounds__(kPeakWarps * 32, 5) ed_fused_kernel(const Fast
     PeakState st = fresh_state(), snap = st;
     uint32_t cnt = fused_walk<W1, W2>(st, snap, tc, k, x, n, mine ? a0 : 0u, mine ? b1 - a0 : 0u, mine ? b0 - a0 : 0u, region, R, ga,
                                       s_mem[wib], lane);
-    // ---- the guard (ed_guard_kernel's test, plus the operand range the cached-reciprocal divisions are proven for) ----
+    // ---- the guard (the exactness test of the header, plus the operand range the cached-reciprocal divisions are proven for) ----
     for (int o = 16; o; o >>= 1) {
         ga.vmin = min(ga.vmin, __shfl_xor_sync(0xffffffffu, ga.vmin, o)); ga.vmax = max(ga.vmax, __shfl_xor_sync(0xffffffffu, ga.vmax, o));
         ga.qmin = min(ga.qmin, __shfl_xor_sync(0xffffffffu, ga.qmin, o)); ga.qmax = max(ga.qmax, __shfl_xor_sync(0xffffffffu, ga.qmax, o));
@@ -830,9 +643,10 @@ static inline size_t ed_al(size_t v) { return (v + 255) / 256 * 256; }
 // Scratch the detector needs next to the raw samples (which the caller keeps on the device).
 size_t nph_ed_scratch_bytes(size_t n_samples_total, size_t n_reads, size_t events_total)
 {
-    const size_t b_raw = ed_al(sizeof(float) * n_samples_total), b_n = ed_al(sizeof(uint32_t) * n_reads);
+    (void)n_samples_total;                 // nothing per sample any more: the t-statistics never leave the SM
+    const size_t b_n = ed_al(sizeof(uint32_t) * n_reads);
     return ed_al(sizeof(nph_raw_read) * n_reads) + b_n /*order*/ + ed_al(sizeof(nph_event) * events_total) + 2 * b_n /*n_events, n_peaks*/ + 256 +
-           2 * b_raw /*ts1, ts2*/ + ed_al(sizeof(uint32_t) * events_total) /*peaks*/ + ed_al(n_reads) /*exact*/;
+           ed_al(sizeof(uint32_t) * events_total) /*peaks*/ + ed_al(n_reads) /*exact*/;
 }
 
 // Event detection over reads whose samples are already on the device.  Leaves the events (at each read's event_off)
@@ -857,7 +671,7 @@ int nph_detect_events_device(nph_ctx* ctx, const float* d_raw, size_t n_samples_
     std::vector<uint32_t> order(n_reads);
     for (size_t i = 0; i < n_reads; ++i) order[i] = keyed[i].second;
 
-    const size_t b_raw = ed_al(sizeof(float) * n_samples_total), b_reads = ed_al(sizeof(nph_raw_read) * n_reads), b_n = ed_al(sizeof(uint32_t) * n_reads);
+    const size_t b_reads = ed_al(sizeof(nph_raw_read) * n_reads), b_n = ed_al(sizeof(uint32_t) * n_reads);
     const size_t b_ev = ed_al(sizeof(nph_event) * events_total), b_pk = ed_al(sizeof(uint32_t) * events_total);
     uint8_t* base = scratch;
     DetParams p{};
@@ -866,8 +680,6 @@ int nph_detect_events_device(nph_ctx* ctx, const float* d_raw, size_t n_samples_
     p.events = reinterpret_cast<nph_event*>(base); base += b_ev;
     p.n_events = reinterpret_cast<uint32_t*>(base); base += b_n;
     p.overflow = reinterpret_cast<int*>(base); base += 256;
-    float* d_ts1 = reinterpret_cast<float*>(base); base += b_raw;
-    float* d_ts2 = reinterpret_cast<float*>(base); base += b_raw;
     uint32_t* d_peaks = reinterpret_cast<uint32_t*>(base); base += b_pk;
     uint32_t* d_npeaks = reinterpret_cast<uint32_t*>(base); base += b_n;
     uint8_t* d_exact = reinterpret_cast<uint8_t*>(base);
@@ -878,49 +690,31 @@ int nph_detect_events_device(nph_ctx* ctx, const float* d_raw, size_t n_samples_
     NPH_CUDA(ctx, cudaMemcpyAsync(d_reads, reads, sizeof(nph_raw_read) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(d_order, order.data(), sizeof(uint32_t) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
     NPH_CUDA(ctx, cudaMemsetAsync(p.overflow, 0, 64, ctx->stream));
-    // fast path first (guard -> t-statistics -> peaks -> events); reads that fail the exactness guard take the stream kernel
+    // fast path first (fused guard + t-statistics + peaks, then events); reads that fail the exactness guard take the stream kernel
     FastParams f{};
     f.raw = d_raw; f.reads = d_reads; f.order = d_order; f.n_reads = (uint32_t)n_reads;
-    f.ts1 = d_ts1; f.ts2 = d_ts2; f.peaks = d_peaks; f.n_peaks = d_npeaks; f.exact = d_exact;
+    f.peaks = d_peaks; f.n_peaks = d_npeaks; f.exact = d_exact;
     f.events = p.events; f.n_events = p.n_events; f.overflow = p.overflow;
     f.stats = reinterpret_cast<uint32_t*>(p.overflow) + 2;
     f.w1 = p.w1; f.w2 = p.w2; f.t1 = p.t1; f.t2 = p.t2; f.peak_height = p.peak_height;
-    f.warm = getenv("NPH_EVENTS_WARMUP") ? (uint32_t)atoi(getenv("NPH_EVENTS_WARMUP")) : kWarm;
     int launches = 0;
-    if (!getenv("NPH_EVENTS_UNFUSED")) {
+    {
         // one pass over the samples: guard + t-statistics + peaks (ed_fused_kernel)
         TsConsts tc{};
         tc.w1 = p.w1; tc.w2 = p.w2;
         tc.w1f = (float)p.w1; tc.w2f = (float)p.w2; tc.r1f = 1.0f / tc.w1f; tc.r2f = 1.0f / tc.w2f;
         tc.w1d = (double)p.w1; tc.w2d = (double)p.w2; tc.r1d = 1.0 / tc.w1d; tc.r2d = 1.0 / tc.w2d;
         f.warm = getenv("NPH_EVENTS_WARMUP") ? ((uint32_t)atoi(getenv("NPH_EVENTS_WARMUP")) + 31u) / 32u * 32u : kFusedWarm;
-        // warps per read: enough warps to fill the machine a few times over (20 resident per SM), capped by the read length
+        // warps per read: one when the batch alone fills the machine (20 resident warps per SM; measured 4 096 reads: 4.3 / 4.8 / 5.0 ms
+        // with 1 / 2 / 4), more for small batches (512 reads: 1.46 / 1.02 / 0.86 ms) as long as a segment stays >= 2 warm-ups long
         int wpr = 1;
-        const size_t want = (size_t)ctx->sm_count * 20 * 3;
-        while (wpr < 4 && n_reads * wpr < want && keyed[0].first / (64u * wpr) >= 4 * f.warm) wpr *= 2;
+        const size_t want = (size_t)ctx->sm_count * 20;
+        while (wpr < 4 && n_reads * wpr < want && keyed[0].first / (64u * wpr) >= 2 * f.warm) wpr *= 2;
         if (getenv("NPH_EVENTS_WPR")) wpr = atoi(getenv("NPH_EVENTS_WPR"));
         if (wpr >= 4) launch_fused<4>(f, tc, n_reads, ctx->stream);
         else if (wpr == 2) launch_fused<2>(f, tc, n_reads, ctx->stream);
         else launch_fused<1>(f, tc, n_reads, ctx->stream);
         ++launches;
-        NPH_CUDA(ctx, cudaGetLastError());
-    } else {
-        ed_guard_kernel<<<(unsigned)std::min<size_t>(n_reads, (size_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(f); ++launches;
-        NPH_CUDA(ctx, cudaGetLastError());
-        {
-            const uint32_t max_n = keyed[0].first;
-            dim3 grid((unsigned)std::min<size_t>((max_n + 255) / 256, 64), (unsigned)n_reads);
-            if (n_reads <= 65535) { ed_tstat_kernel<<<grid, 256, 0, ctx->stream>>>(f); ++launches; }
-            else {
-                for (size_t r0 = 0; r0 < n_reads; r0 += 65535) {         // gridDim.y limit
-                    FastParams g = f; g.reads = d_reads + r0; g.exact = d_exact + r0;
-                    dim3 gg(grid.x, (unsigned)std::min<size_t>(65535, n_reads - r0));
-                    ed_tstat_kernel<<<gg, 256, 0, ctx->stream>>>(g); ++launches;
-                }
-            }
-            NPH_CUDA(ctx, cudaGetLastError());
-        }
-        ed_peaks_kernel<<<(unsigned)((n_reads + kPeakWarps - 1) / kPeakWarps), kPeakWarps * 32, 0, ctx->stream>>>(f); ++launches;
         NPH_CUDA(ctx, cudaGetLastError());
     }
     ed_events_kernel<<<(unsigned)std::min<size_t>(n_reads, (size_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(f); ++launches;
