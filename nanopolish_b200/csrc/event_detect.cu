@@ -275,6 +275,10 @@ __device__ __forceinline__ void peak_step(PeakState& st, const PeakConsts& k, ui
 }
 
 constexpr int kPeakWarps = 4;
+#ifndef NPH_ED_CTAS
+#define NPH_ED_CTAS 5          // resident CTAs per SM the fused kernel is compiled for (registers <= 65536 / (128 * NPH_ED_CTAS)); six fit the
+                              // shared memory but cost spills: 4.46 ms against 4.37 ms for 4 096 reads x 36 000 samples
+#endif
 
 // =============================================================================================================
 // ed_fused_kernel: guard + t-statistics + peaks in ONE pass over the samples; only the boundaries are written.
@@ -347,7 +351,8 @@ __device__ __noinline__ float tstat_windows_exact(float combined_var, float delt
 // halo (32 + 2*w2 samples from p0; zeros outside the read) in shared memory as doubles — x and the float product x*x,
 // each sample converted ONCE (the float->double conversion is the scarce resource here: 8.5 clk per warp instruction,
 // profiles/r02_ubench_cvt.txt) — and feeds the exactness guard with the samples it touches.
-constexpr int kRowBuf = 32 + 2 * kMaxW2;
+constexpr int kFusedMaxW2 = 14;                   // scrappie: 6 (DNA), 14 (RNA); wider windows take the streaming kernel
+constexpr int kRowBuf = 32 + 2 * kFusedMaxW2;
 
 struct RowRegs { float v0, v1; };          // the two samples of a row this lane stages: slots lane and lane + 32
 
@@ -409,10 +414,17 @@ __device__ __forceinline__ void tstat_pair(const double* __restrict__ sdx, const
     if (!v2) b = 0.0f;
 }
 
-struct FusedSmem {
-    float a[32][33], b[32][33];          // the tile of t-statistics: row = lane that will consume it
-    double dx[kRowBuf], dq[kRowBuf];     // one staged row: samples and their float squares, widened
+struct FusedSmem {                       // per warp, 9 216 bytes: six CTAs of four warps fit an SM
+    float a[32][32], b[32][32];          // the tile of t-statistics: row = lane that will consume it, column XOR row (bank-conflict free
+                                         // for the row-wise producer and the column-wise consumer without padding); after the walks
+                                         // the first 32 words of `a` carry the lanes' boundary counts to the read's first warp
+    double dx[kRowBuf];                  // one staged row: the samples, widened
+    PeakState last;                      // final state of the warp's lane 31 (for the next warp of the same read)
+    double dq[kRowBuf];                  // ... and their float squares, widened
+    GuardAcc guard;                      // the warp's guard extrema
+    uint32_t flag, over, pad[2];         // chain verified / some slice overflowed
 };
+static_assert(sizeof(FusedSmem) == 9216, "FusedSmem layout");
 
 // One cooperative walk: lane l walks [from_l, from_l + len_l), the first wlen_l steps being warm-up (state only); at
 // step wlen_l the state is snapshotted and from there boundaries are counted and recorded into region[0..R).
@@ -443,7 +455,7 @@ __device__ __forceinline__ uint32_t fused_walk(PeakState& st, PeakState& snap, c
                 __syncwarp();
                 float a = 0.0f, b = 0.0f;
                 if (c + lane < ln) tstat_pair<W1, W2>(sm.dx, sm.dq, n, fr + c + lane, tc, lane, a, b);
-                sm.a[rr][lane] = a; sm.b[rr][lane] = b;
+                sm.a[rr][lane ^ rr] = a; sm.b[rr][lane ^ rr] = b;
                 __syncwarp();
             }
             cur = nxt; fr = fr_n; ln = ln_n;
@@ -453,7 +465,7 @@ __device__ __forceinline__ uint32_t fused_walk(PeakState& st, PeakState& snap, c
         const uint32_t steps = len > c ? min(32u, len - c) : 0u;
         for (uint32_t t = 0; t < steps; ++t) {
             int e0, e1;
-            peak_step(st, k, from + c + t, sm.a[lane][t], sm.b[lane][t], e0, e1);
+            peak_step(st, k, from + c + t, sm.a[lane][t ^ lane], sm.b[lane][t ^ lane], e0, e1);
             if (rec && e0 >= 0) { if (cnt < R) region[cnt] = (uint32_t)e0; ++cnt; }
             if (rec && e1 >= 0) { if (cnt < R) region[cnt] = (uint32_t)e1; ++cnt; }
         }
@@ -469,13 +481,10 @@ __device__ __forceinline__ void read_barrier(int id, int threads) { asm volatile
 // WPR warps walk one read as 32*WPR segments (a CTA of kPeakWarps warps holds kPeakWarps / WPR reads): small batches
 // and the tail of a large one get WPR times the parallelism for warm / segment more work.
 template <int W1, int W2, int WPR>
-__global__ void __launch_bounds__(kPeakWarps * 32, 5) ed_fused_kernel(const FastParams p, const TsConsts tc)
+__global__ void __launch_bounds__(kPeakWarps * 32, NPH_ED_CTAS) ed_fused_kernel(const FastParams p, const TsConsts tc)
 {
     constexpr int LANES = 32 * WPR;
     __shared__ FusedSmem s_mem[kPeakWarps];
-    __shared__ PeakState s_last[kPeakWarps];               // final state of each warp's lane 31
-    __shared__ GuardAcc s_guard[kPeakWarps];
-    __shared__ uint32_t s_flag[kPeakWarps], s_over[kPeakWarps], s_cnt[kPeakWarps * 32];
     const int wib = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int rslot = wib / WPR, part = wib % WPR, w0 = rslot * WPR;          // this warp's read within the CTA, its part of it
@@ -507,10 +516,10 @@ __global__ void __launch_bounds__(kPeakWarps * 32, 5) ed_fused_kernel(const Fast
         ga.qmin = min(ga.qmin, __shfl_xor_sync(0xffffffffu, ga.qmin, o)); ga.qmax = max(ga.qmax, __shfl_xor_sync(0xffffffffu, ga.qmax, o));
     }
     if (WPR > 1) {
-        if (lane == 0) s_guard[wib] = ga;
+        if (lane == 0) s_mem[wib].guard = ga;
         read_barrier(bar_id, LANES);
         for (int w = 0; w < WPR; ++w) {
-            const GuardAcc g = s_guard[w0 + w];
+            const GuardAcc g = s_mem[w0 + w].guard;
             ga.vmin = min(ga.vmin, g.vmin); ga.vmax = max(ga.vmax, g.vmax); ga.qmin = min(ga.qmin, g.qmin); ga.qmax = max(ga.qmax, g.qmax);
         }
     }
@@ -528,7 +537,7 @@ __global__ void __launch_bounds__(kPeakWarps * 32, 5) ed_fused_kernel(const Fast
     uint32_t repairs = 0;
     for (int round = 0; exact && round < LANES; ++round) {
         if (WPR > 1) {
-            if (lane == 31) s_last[wib] = st;
+            if (lane == 31) s_mem[wib].last = st;
             read_barrier(bar_id, LANES);
         }
         PeakState left;
@@ -536,14 +545,14 @@ __global__ void __launch_bounds__(kPeakWarps * 32, 5) ed_fused_kernel(const Fast
         left.pp0 = __shfl_up_sync(0xffffffffu, st.pp0, 1); left.pp1 = __shfl_up_sync(0xffffffffu, st.pp1, 1);
         left.pv0 = __shfl_up_sync(0xffffffffu, st.pv0, 1); left.pv1 = __shfl_up_sync(0xffffffffu, st.pv1, 1);
         left.v0 = __shfl_up_sync(0xffffffffu, st.v0, 1); left.v1 = __shfl_up_sync(0xffffffffu, st.v1, 1);
-        if (WPR > 1 && lane == 0 && part > 0) left = s_last[wib - 1];
+        if (WPR > 1 && lane == 0 && part > 0) left = s_mem[wib - 1].last;
         const bool ok = !mine || gl == 0 || same_state(snap, left);
         bool all_ok = __all_sync(0xffffffffu, ok);
         if (WPR > 1) {
-            if (lane == 0) s_flag[wib] = all_ok ? 1u : 0u;
+            if (lane == 0) s_mem[wib].flag = all_ok ? 1u : 0u;
             read_barrier(bar_id, LANES);
             all_ok = true;
-            for (int w = 0; w < WPR; ++w) all_ok = all_ok && s_flag[w0 + w] != 0u;
+            for (int w = 0; w < WPR; ++w) all_ok = all_ok && s_mem[w0 + w].flag != 0u;
         }
         if (all_ok) break;
         // re-walk the segments that started from a wrong state, now from the neighbour's final state (lanes 0..round are right)
@@ -555,19 +564,20 @@ __global__ void __launch_bounds__(kPeakWarps * 32, 5) ed_fused_kernel(const Fast
     }
     // ---- counts of all the read's lanes, then its first warp compacts the slices ----
     const bool over = __any_sync(0xffffffffu, cnt > R);                    // a lane's slice was too small: streaming fallback
-    s_cnt[w0 * 32 + gl] = cnt;
-    if (lane == 0) s_over[wib] = over ? 1u : 0u;
+    __syncwarp();                                                          // the tile is free now
+    reinterpret_cast<uint32_t*>(&s_mem[wib].a[0][0])[lane] = cnt;
+    if (lane == 0) s_mem[wib].over = over ? 1u : 0u;
     if (WPR > 1) read_barrier(bar_id, LANES); else __syncwarp();
     if (part != 0) return;
-    for (int w = 0; w < WPR; ++w) if (s_over[w0 + w]) exact = false;
-    const uint32_t* cnts = s_cnt + w0 * 32;
+    for (int w = 0; w < WPR; ++w) if (s_mem[w0 + w].over) exact = false;
+    auto cnt_of = [&](int s) { return reinterpret_cast<const uint32_t*>(&s_mem[w0 + (s >> 5)].a[0][0])[s & 31]; };
     uint32_t total = 0;
-    for (int s = 0; s < LANES; ++s) total += cnts[s];
+    for (int s = 0; s < LANES; ++s) total += cnt_of(s);
     if (exact && total <= cap_peaks) {
         // slice 0 is in place; destinations never pass their sources, slices and chunks go left to right
-        uint32_t ds = cnts[0];
+        uint32_t ds = cnt_of(0);
         for (int s = 1; s < LANES; ++s) {
-            const uint32_t cs = cnts[s];
+            const uint32_t cs = cnt_of(s);
             const uint32_t* src = peaks + (size_t)s * R;
             if (ds != (uint32_t)s * R) {
                 for (uint32_t q = 0; q < cs; q += 32) {
@@ -698,7 +708,9 @@ int nph_detect_events_device(nph_ctx* ctx, const float* d_raw, size_t n_samples_
     f.stats = reinterpret_cast<uint32_t*>(p.overflow) + 2;
     f.w1 = p.w1; f.w2 = p.w2; f.t1 = p.t1; f.t2 = p.t2; f.peak_height = p.peak_height;
     int launches = 0;
-    {
+    if (p.w2 > (uint32_t)kFusedMaxW2) {
+        NPH_CUDA(ctx, cudaMemsetAsync(d_exact, 0, n_reads, ctx->stream));   // windows wider than the staged row: every read streams
+    } else {
         // one pass over the samples: guard + t-statistics + peaks (ed_fused_kernel)
         TsConsts tc{};
         tc.w1 = p.w1; tc.w2 = p.w2;
