@@ -375,6 +375,10 @@ def call_methylation_block(args, rank, world, local, steps, warmup):
 
     # ---- e2e arm: host buffers -> TSV bytes through the C++ host ----
     os.environ["NPH_DEVICE"] = str(local)
+    # the C++ host formats rows with an OpenMP team; torchrun exports OMP_NUM_THREADS=1 to every rank, which would serialise it
+    # (measured at N=2: 44 ms of TSV instead of 7) — each rank takes its share of the box's CPUs, as a multi-GPU caller would set it
+    host_threads = max(1, min(32, cpu_threads() // max(1, world)))
+    os.environ.setdefault("NPH_HOST_THREADS", str(host_threads))
     host = C.CDLL(os.path.join(ROOT, "nanopolish_b200", "libnph_host.so"))
     host.nphh_last_error.restype = C.c_char_p
     host.nphh_call_methylation_flat.restype = C.c_longlong
@@ -437,6 +441,7 @@ def call_methylation_block(args, rank, world, local, steps, warmup):
                "e2e": {"value": scored_all * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                        "steps": e2e_steps, "tsv_bytes_per_step": tsv_bytes, "ms_per_step": e2e_s / e2e_steps * 1e3,
                        "stage_ms": {"device_call": float(stage[0] / e2e_steps * 1e3), "tsv": float(stage[1] / e2e_steps * 1e3)},
+                       "host_threads_per_rank": int(os.environ["NPH_HOST_THREADS"]),
                        "api": "libnph_host.so nphh_call_methylation_flat (nph::call_methylation_flat: page-locked host buffers in, TSV bytes out"
                               + ("; TSV bytes gathered to rank 0 over NCCL)" if world > 1 else ")")},
                "gpu_launches": launches * steps,
