@@ -393,6 +393,13 @@ def call_methylation_block(args, rank, world, local, steps, warmup):
     secs2 = np.zeros(2)
     ns, se = C.c_uint64(), C.c_uint64()
 
+    from nanopolish_b200.dist import ByteGather
+    tsv_gather = None
+    if world > 1:
+        cap_t = torch.tensor([cap], dtype=torch.int64, device=dev)
+        dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
+        tsv_gather = ByteGather(int(cap_t.item()), device=dev)            # page-locked staging, allocated once
+
     def e2e_step():
         n = host.nphh_call_methylation_flat(vp(h_reads), C.c_size_t(n_reads), vp(h_mean), None, C.c_size_t(h_mean.shape[0]),
                                             vp(h_ref), C.c_size_t(h_ref.shape[0]), None, C.c_size_t(0), vp(h_deltas), vp(h_first),
@@ -401,7 +408,7 @@ def call_methylation_block(args, rank, world, local, steps, warmup):
         if n < 0:
             raise RuntimeError("nphh_call_methylation_flat: " + host.nphh_last_error().decode())
         if world > 1:
-            gather_records_to_rank0(tsv[:n], device=dev)
+            tsv_gather.gather(t_tsv, int(n))
         return int(n)
 
     for _ in range(2):

@@ -78,6 +78,44 @@ def gather_records_to_rank0(records: np.ndarray, device=None, group=None):
     return [p.cpu().numpy().view(records.dtype) for p in parts]
 
 
+class ByteGather:
+    """The same exchange for a caller that repeats it with page-locked buffers (bench.py's call-methylation e2e: every rank's TSV
+    bytes to rank 0): staging on the device and the page-locked landing area on rank 0 are allocated once, the copies are
+    asynchronous, and each call is one tiny all_gather of the byte counts plus ONE padded gather.  `device` None: CPU tensors (gloo)."""
+
+    def __init__(self, cap_bytes: int, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+        self.group, self.device, self.cap = group, device, int(cap_bytes)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = device if device is not None else "cpu"
+        self.local = torch.empty(self.cap, dtype=torch.uint8, device=dev)
+        self.counts_dev = torch.empty(self.world, dtype=torch.int64, device=dev)
+        self.bufs = [torch.empty(self.cap, dtype=torch.uint8, device=dev) for _ in range(self.world)] if self.rank == 0 else None
+        pin = device is not None and torch.cuda.is_available()
+        self.out = torch.empty((self.world, self.cap), dtype=torch.uint8, pin_memory=pin) if self.rank == 0 else None
+
+    def gather(self, host_bytes, n: int):
+        """host_bytes: 1-D uint8 torch tensor (page-locked for an asynchronous copy), n valid bytes.  Rank 0 gets the list of per-rank
+        numpy views into its landing area (valid until the next call); other ranks None."""
+        import torch
+        import torch.distributed as dist
+        assert n <= self.cap
+        self.local[:n].copy_(host_bytes[:n], non_blocking=True)
+        c = torch.tensor([n], dtype=torch.int64).to(self.local.device, non_blocking=True)
+        dist.all_gather_into_tensor(self.counts_dev, c, group=self.group)
+        counts = [int(x) for x in self.counts_dev.tolist()]
+        maxc = max(counts)
+        dist.gather(self.local[:maxc], [b[:maxc] for b in self.bufs] if self.rank == 0 else None, dst=0, group=self.group)
+        if self.rank != 0:
+            return None
+        for r, k in enumerate(counts):
+            self.out[r, :k].copy_(self.bufs[r][:k], non_blocking=True)
+        if self.local.is_cuda:
+            torch.cuda.current_stream(self.local.device).synchronize()
+        return [self.out[r, :k].numpy() for r, k in enumerate(counts)]
+
+
 def scatter_results(parts_scores: list, owner: np.ndarray) -> np.ndarray:
     """Rank-0 reassembly: per-rank result vectors (in each rank's local job order) back to global job order."""
     out = np.empty(owner.shape[0], np.float32)

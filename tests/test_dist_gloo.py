@@ -104,3 +104,33 @@ def test_two_rank_gather_of_variable_length_records(tmp_path):
     mp.spawn(_records_worker, args=(2, port, out), nprocs=2, join=True)
     merged, want = np.load(out)
     assert np.array_equal(merged, want)
+
+
+def _bytes_worker(rank, world, port, out_path):
+    """ByteGather (the page-locked, allocate-once form bench.py uses for the TSV bytes): three rounds with different lengths per rank."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nanopolish_b200.dist import ByteGather
+    g = ByteGather(5000)
+    ok = True
+    for rnd in range(3):
+        n = 1000 * (rnd + 1) + 37 * rank + (0 if rnd < 2 else -1000 * 3 + 5)        # last round: 5 + 37 * rank bytes
+        mine = torch.from_numpy(((np.arange(5000) * (rank + 3) + rnd) % 251).astype(np.uint8))
+        got = g.gather(mine, n)
+        if rank == 0:
+            for r, part in enumerate(got):
+                want_n = 1000 * (rnd + 1) + 37 * r + (0 if rnd < 2 else -1000 * 3 + 5)
+                want = ((np.arange(5000) * (r + 3) + rnd) % 251).astype(np.uint8)[:want_n]
+                ok = ok and part.shape[0] == want_n and np.array_equal(part, want)
+    if rank == 0:
+        np.save(out_path, np.array([ok]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_byte_gather_with_reused_staging(tmp_path):
+    out = str(tmp_path / "bytes.npy")
+    port = _free_port()
+    mp.spawn(_bytes_worker, args=(2, port, out), nprocs=2, join=True)
+    assert bool(np.load(out)[0])
