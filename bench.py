@@ -427,7 +427,10 @@ def call_methylation_block(args, rank, world, local, steps, warmup):
     e2e_s = float(t.item())
     assert int(ns.value) == n_sites and int(se.value) == scored
     h2d = h_reads.nbytes + h_mean.nbytes + h_ref.nbytes + h_deltas.nbytes + h_first.nbytes + h_recs.nbytes + 8 * (n_reads + 1) + 8 * n_reads
-    d2h = 24 * n_sites + 8 * (n_reads + 1) + 64
+    device_tsv = not os.environ.get("NPH_METH_HOST_TSV")
+    # rows formatted on the device (nph_methylation_batch_compact_tsv): the TSV bytes are what comes back; with the host formatter the
+    # 24-byte site records and their offsets do
+    d2h = (tsv_bytes + 16) if device_tsv else (24 * n_sites + 8 * (n_reads + 1) + 64)
 
     out = None
     if rank == 0:
@@ -447,7 +450,8 @@ def call_methylation_block(args, rank, world, local, steps, warmup):
                           "l2": "inputs larger than L2 (levels + event alignments + reference > 126 MB)"},
                "e2e": {"value": scored_all * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                        "steps": e2e_steps, "tsv_bytes_per_step": tsv_bytes, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                       "stage_ms": {"device_call": float(stage[0] / e2e_steps * 1e3), "tsv": float(stage[1] / e2e_steps * 1e3)},
+                       "stage_ms": {"device_call": float(stage[0] / e2e_steps * 1e3), "host_side": float(stage[1] / e2e_steps * 1e3)},
+                       "rows_formatted_on": "device (nph_methylation_tsv)" if device_tsv else "host (OpenMP formatter)",
                        "host_threads_per_rank": int(os.environ["NPH_HOST_THREADS"]),
                        "api": "libnph_host.so nphh_call_methylation_flat (nph::call_methylation_flat: page-locked host buffers in, TSV bytes out"
                               + ("; TSV bytes gathered to rank 0 over NCCL)" if world > 1 else ")")},

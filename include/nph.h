@@ -409,6 +409,29 @@ int nph_methylation_fetch(nph_ctx* ctx, uint64_t* site_off_out, nph_meth_site* s
  * this context; ordered behind the run on the context's stream), for a caller that ships them GPU to GPU — a multi-GPU
  * driver gathering every rank's records with NCCL — without a host hop. */
 int nph_methylation_sites_dev(nph_ctx* ctx, const nph_meth_site** sites_dev_out, uint64_t* n_sites_out);
+/* The rows of methylation_calls.tsv for the most recent nph_methylation_run, formatted on the device — the reference's writer
+ * (src/nanopolish_call_methylation.cpp:113-140: chromosome, strand, start, end, read_name, log_lik_ratio, log_lik_methylated,
+ * log_lik_unmethylated, num_calling_strands, num_motifs, sequence; "%.2lf" for the three likelihoods) applied to every site
+ * record in record order, for records that are their read's only scored strand (num_calling_strands 1; every 1D read).
+ * contig: the chromosome name of the batch; read_names + name_off (n_records + 1 offsets into read_names, no terminators):
+ * the read name of each record; is_reverse[n_records]: bam1_is_rev of each record ('-' / '+').  tsv_out receives
+ * *n_bytes_out bytes (no terminator).  NPH_ERR_INVALID with *n_bytes_out set if cap was too small; NPH_ERR_UNSUPPORTED if a
+ * likelihood is not finite or beyond 2^52 (the C library's arbitrary-precision path: fetch the sites and format on the host). */
+int nph_methylation_tsv(nph_ctx* ctx, const char* contig, const char* read_names, const uint32_t* name_off,
+                        const uint8_t* is_reverse, char* tsv_out, size_t cap, uint64_t* n_bytes_out);
+/* One-shot of the whole caller: nph_methylation_batch_compact's inputs in, methylation_calls.tsv rows out (the site
+ * records never cross PCIe).  On NPH_ERR_UNSUPPORTED (see nph_methylation_tsv) the batch has been scored: the caller
+ * may nph_methylation_fetch the records and format them itself. */
+int nph_methylation_batch_compact_tsv(nph_ctx* ctx,
+                                      const nph_read* reads, size_t n_reads,
+                                      const float* ev_mean, const double* ev_start_time, size_t n_events_total,
+                                      const char* ref_bases, const int16_t* event_deltas, size_t n_ref_total,
+                                      const int32_t* first_event,
+                                      const nph_meth_record* records, size_t n_records,
+                                      const nph_meth_params* params, double indel_bias,
+                                      const char* contig, const char* read_names, const uint32_t* name_off, const uint8_t* is_reverse,
+                                      char* tsv_out, size_t cap, uint64_t* n_bytes_out,
+                                      uint64_t* n_sites_out, uint64_t* n_scored_events_out);
 
 /* ---- variants: candidate screening on the device (section 8f N2, BASELINE configs[4]) -----------------------------
  * generate_candidate_single_base_edits (src/nanopolish_call_variants.cpp:288-361) for a reference region: at every position i

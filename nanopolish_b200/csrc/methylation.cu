@@ -23,6 +23,7 @@
 // then hmm_schedule.cu + the forward kernels run unchanged, and meth_fill_kernel copies the two scores of each group
 // into its site record.  The host sees O(records) work only.
 #include "nph_internal.cuh"
+#include "tsv_format.cuh"
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -571,6 +572,190 @@ extern "C" int nph_methylation_run(nph_ctx* ctx)
     return NPH_OK;
 }
 
+// ---- methylation_calls.tsv on the device -------------------------------------------------------------------------
+// One row per site record of a record that is its read's only scored strand (1D reads: every read of a call-methylation
+// run today), the fields of the reference's writer (src/nanopolish_call_methylation.cpp:113-140 and the ScoredSite it
+// prints, basemods.cpp:403-425): chromosome, strand, start, end, read_name, log_lik_ratio, log_lik_methylated,
+// log_lik_unmethylated ("%.2lf" of the strand sums; the other strand's entries stay 0), num_calling_strands (1),
+// num_motifs, sequence (the group with k - 1 bases of context before it and k after it, cut at the end of the record's
+// reference).  The host's part of call-methylation was the formatting of these rows (6-9 ms per 10 000 reads on the box's
+// 16-CPU quota, as long as the PCIe transfer); here a warp formats a record's rows straight from the site records.
+namespace {
+
+struct TsvArgs {
+    const nph_meth_site* sites;
+    const uint64_t* site_off;          // n_records + 1
+    const nph_meth_record* records;
+    const uint8_t* ref;
+    const char* contig; uint32_t contig_len;
+    const char* names; const uint32_t* name_off;       // n_records + 1
+    const uint8_t* is_reverse;
+    uint32_t k, n_records;
+    uint64_t* rec_bytes;               // per record: bytes of its rows (len pass), then exclusive prefix in rec_off
+    const uint64_t* rec_off;
+    char* out;
+    int* refused;                      // set when a value needs the C library (non-finite, |v| >= 2^52)
+};
+
+struct RowNums { nph_tsv::Fixed2 diff, m, u; uint32_t seq_b, seq_len; };
+
+__device__ __forceinline__ RowNums row_numbers(const nph_meth_site& ms, const nph_meth_record& R, uint32_t k)
+{
+    RowNums r;
+    // ScoredSite: ll_*[strand] = the float score, the other strand 0.0; the writer sums the two strands in double
+    const double sum_m = __dadd_rn((double)ms.ll_methylated, 0.0), sum_u = __dadd_rn((double)ms.ll_unmethylated, 0.0);
+    r.diff = nph_tsv::fixed2_of(__dsub_rn(sum_m, sum_u));
+    r.m = nph_tsv::fixed2_of(sum_m);
+    r.u = nph_tsv::fixed2_of(sum_u);
+    const uint32_t b = (uint32_t)(ms.start_position - R.ref_start_pos) - k + 1u;
+    const uint32_t e = min((uint32_t)(ms.end_position - R.ref_start_pos) + k, R.ref_len);
+    r.seq_b = b; r.seq_len = e - b;
+    return r;
+}
+
+__device__ __forceinline__ uint32_t row_len(const TsvArgs& a, const nph_meth_site& ms, const RowNums& r, uint32_t name_len)
+{
+    return a.contig_len + 3u + (uint32_t)nph_tsv::int_len(ms.start_position) + 1u + (uint32_t)nph_tsv::int_len(ms.end_position) + 1u + name_len + 1u +
+           (uint32_t)nph_tsv::fixed2_len(r.diff) + 1u + (uint32_t)nph_tsv::fixed2_len(r.m) + 1u + (uint32_t)nph_tsv::fixed2_len(r.u) + 1u + 2u +
+           (uint32_t)nph_tsv::ndigits(ms.n_motif) + 1u + r.seq_len + 1u;
+}
+
+// pass 1 (WRITE = false): bytes per record; pass 2 (WRITE = true): the rows at rec_off[record]
+template <bool WRITE>
+__global__ void __launch_bounds__(kThreads) meth_tsv_kernel(const TsvArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const uint32_t n_warps = gridDim.x * kWarps;
+    for (uint32_t rec = warp; rec < a.n_records; rec += n_warps) {
+        const uint64_t s0 = a.site_off[rec], s1 = a.site_off[rec + 1];
+        if (s0 == s1) { if (!WRITE && lane == 0) a.rec_bytes[rec] = 0; continue; }
+        const nph_meth_record R = a.records[rec];
+        const uint32_t nb = a.name_off[rec], name_len = a.name_off[rec + 1] - nb;
+        unsigned long long run = WRITE ? a.rec_off[rec] : 0ull;        // WRITE: where the next chunk of rows starts
+        for (uint64_t base = s0; base < s1; base += 32) {
+            const uint64_t s = base + lane;
+            const bool have = s < s1;
+            nph_meth_site ms{};
+            RowNums r{};
+            uint32_t len = 0;
+            if (have) {
+                ms = a.sites[s];
+                r = row_numbers(ms, R, a.k);
+                if (!(r.diff.ok && r.m.ok && r.u.ok)) *a.refused = 1;
+                len = row_len(a, ms, r, name_len);
+            }
+            uint32_t incl = len;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+            if (WRITE && have) {
+                char* o = a.out + run + (incl - len);
+                for (uint32_t i = 0; i < a.contig_len; ++i) *o++ = a.contig[i];
+                *o++ = '\t'; *o++ = a.is_reverse[rec] ? '-' : '+'; *o++ = '\t';
+                o = nph_tsv::put_int(o, ms.start_position); *o++ = '\t';
+                o = nph_tsv::put_int(o, ms.end_position); *o++ = '\t';
+                for (uint32_t i = 0; i < name_len; ++i) *o++ = a.names[nb + i];
+                *o++ = '\t';
+                o = nph_tsv::put_fixed2(o, r.diff); *o++ = '\t';
+                o = nph_tsv::put_fixed2(o, r.m); *o++ = '\t';
+                o = nph_tsv::put_fixed2(o, r.u); *o++ = '\t';
+                *o++ = '1'; *o++ = '\t';
+                o = nph_tsv::put_u64(o, ms.n_motif); *o++ = '\t';
+                const uint8_t* sq = a.ref + R.ref_off + r.seq_b;
+                for (uint32_t i = 0; i < r.seq_len; ++i) *o++ = (char)sq[i];
+                *o++ = '\n';
+            }
+            run += __shfl_sync(kFull, incl, 31);
+        }
+        if (!WRITE && lane == 0) a.rec_bytes[rec] = run;
+    }
+}
+
+// exclusive prefix of the per-record byte counts (one block; n + 1 entries out)
+__global__ void __launch_bounds__(1024) meth_tsv_prefix_kernel(const uint64_t* __restrict__ bytes, uint32_t n, uint64_t* __restrict__ off)
+{
+    __shared__ unsigned long long s_a[1024];
+    __shared__ unsigned long long carry;
+    const int t = threadIdx.x;
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t r = base + t;
+        const unsigned long long v = r < n ? bytes[r] : 0ull;
+        s_a[t] = v;
+        __syncthreads();
+        for (int dlt = 1; dlt < 1024; dlt <<= 1) {
+            const unsigned long long x = t >= dlt ? s_a[t - dlt] : 0ull;
+            __syncthreads();
+            s_a[t] += x;
+            __syncthreads();
+        }
+        if (r < n) off[r] = carry + s_a[t] - v;
+        __syncthreads();
+        if (t == 1023) carry += s_a[1023];
+        __syncthreads();
+    }
+    if (t == 0) off[n] = carry;
+}
+
+} // namespace
+
+extern "C" int nph_methylation_tsv(nph_ctx* ctx, const char* contig, const char* read_names, const uint32_t* name_off,
+                                   const uint8_t* is_reverse, char* tsv_out, size_t cap, uint64_t* n_bytes_out)
+{
+    if (!ctx || !n_bytes_out) return NPH_ERR_INVALID;
+    nph_ctx::MethState& m = ctx->meth;
+    if (!m.ran) return NPH_ERR_STATE;
+    *n_bytes_out = 0;
+    if (m.n_records == 0 || m.n_sites == 0) return NPH_OK;
+    if (!contig || !read_names || !name_off || !is_reverse) return NPH_ERR_INVALID;
+    NPH_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = m.n_records, contig_len = std::strlen(contig), names_len = name_off[n];
+    // one staging block: contig | names | name offsets | strand flags
+    auto al = [](size_t v) { return (v + 15) / 16 * 16; };
+    const size_t o_names = al(contig_len + 1), o_noff = o_names + al(names_len + 1), o_rev = o_noff + al(sizeof(uint32_t) * (n + 1));
+    NPH_TRY(nph_reserve(ctx, m.d_tsv_in, o_rev + al(n)));
+    NPH_TRY(nph_reserve(ctx, m.d_tsv_off, 2 * n + 4));
+    uint8_t* in = m.d_tsv_in.p;
+    NPH_CUDA(ctx, cudaMemcpyAsync(in, contig, contig_len, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(in + o_names, read_names, names_len, cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(in + o_noff, name_off, sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(in + o_rev, is_reverse, n, cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t* rec_bytes = m.d_tsv_off.p;
+    uint64_t* rec_off = rec_bytes + n;                                  // n + 1 entries
+    int* d_refused = reinterpret_cast<int*>(rec_off + n + 1);
+    NPH_CUDA(ctx, cudaMemsetAsync(d_refused, 0, sizeof(int), ctx->stream));
+    TsvArgs a{m.d_sites.p, m.d_counts.p + 3 * n, m.d_records.p, m.d_ref.p, reinterpret_cast<const char*>(in), (uint32_t)contig_len,
+              reinterpret_cast<const char*>(in + o_names), reinterpret_cast<const uint32_t*>(in + o_noff), in + o_rev, m.params.k, (uint32_t)n,
+              rec_bytes, rec_off, nullptr, d_refused};
+    const int grid = (int)std::min<size_t>((n + kWarps - 1) / kWarps, (size_t)ctx->sm_count * 8);
+    meth_tsv_kernel<false><<<grid, kThreads, 0, ctx->stream>>>(a);
+    NPH_CUDA(ctx, cudaGetLastError());
+    meth_tsv_prefix_kernel<<<1, 1024, 0, ctx->stream>>>(rec_bytes, (uint32_t)n, rec_off);
+    NPH_CUDA(ctx, cudaGetLastError());
+    uint64_t total = 0;
+    int refused = 0;
+    NPH_CUDA(ctx, cudaMemcpyAsync(&total, rec_off + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    NPH_CUDA(ctx, cudaMemcpyAsync(&refused, d_refused, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (refused) {
+        ctx->last_error = "a log-likelihood is not finite or beyond 2^52: these rows need the C library's formatting (nph_methylation_fetch + host formatter)";
+        return NPH_ERR_UNSUPPORTED;
+    }
+    *n_bytes_out = total;
+    if (total > cap || !tsv_out) {
+        ctx->last_error = "tsv_out too small: " + std::to_string(total) + " bytes";
+        return NPH_ERR_INVALID;
+    }
+    NPH_TRY(nph_reserve(ctx, m.d_tsv, (size_t)total));
+    a.out = reinterpret_cast<char*>(m.d_tsv.p);
+    meth_tsv_kernel<true><<<grid, kThreads, 0, ctx->stream>>>(a);
+    NPH_CUDA(ctx, cudaGetLastError());
+    NPH_CUDA(ctx, cudaMemcpyAsync(tsv_out, m.d_tsv.p, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->last_launches += 3;
+    return NPH_OK;
+}
+
 extern "C" int nph_methylation_counts(nph_ctx* ctx, uint64_t* n_sites_out, uint64_t* n_jobs_out, uint64_t* n_scored_events_out)
 {
     if (!ctx) return NPH_ERR_INVALID;
@@ -630,6 +815,35 @@ extern "C" int nph_methylation_batch_compact(nph_ctx* ctx,
     if (rc == NPH_OK) rc = nph_methylation_fetch(ctx, site_off_out, sites_out, sites_cap);
     nph_finish_level_upload(ctx);
     if (rc == NPH_OK && n_scored_events_out) *n_scored_events_out = ctx->meth.n_scored_events;
+    return rc;
+}
+
+extern "C" int nph_methylation_batch_compact_tsv(nph_ctx* ctx,
+                                                 const nph_read* reads, size_t n_reads,
+                                                 const float* ev_mean, const double* ev_start_time, size_t n_events_total,
+                                                 const char* ref_bases, const int16_t* event_deltas, size_t n_ref_total,
+                                                 const int32_t* first_event,
+                                                 const nph_meth_record* records, size_t n_records,
+                                                 const nph_meth_params* params, double indel_bias,
+                                                 const char* contig, const char* read_names, const uint32_t* name_off, const uint8_t* is_reverse,
+                                                 char* tsv_out, size_t cap, uint64_t* n_bytes_out,
+                                                 uint64_t* n_sites_out, uint64_t* n_scored_events_out)
+{
+    if (!ctx || !n_bytes_out) return NPH_ERR_INVALID;
+    *n_bytes_out = 0;
+    if (n_sites_out) *n_sites_out = 0;
+    if (n_scored_events_out) *n_scored_events_out = 0;
+    if (n_records == 0) return NPH_OK;
+    ctx->levels_inflight = false;
+    int rc = nph_reads_load_impl(ctx, reads, n_reads, ev_mean, ev_start_time, n_events_total, true);
+    if (rc == NPH_OK) { ctx->reads_loaded = true; ctx->jobs_loaded = false; ctx->abea_loaded = false; }
+    if (rc == NPH_OK) rc = nph_methylation_load_compact(ctx, ref_bases, event_deltas, n_ref_total, first_event, records, n_records, params, indel_bias);
+    if (rc == NPH_OK && ctx->levels_inflight) rc = nph_upload_level_chunks(ctx, ev_mean);
+    if (rc == NPH_OK) rc = nph_methylation_run(ctx);
+    if (rc == NPH_OK) rc = nph_methylation_tsv(ctx, contig, read_names, name_off, is_reverse, tsv_out, cap, n_bytes_out);
+    nph_finish_level_upload(ctx);
+    if (n_sites_out) *n_sites_out = ctx->meth.n_sites;
+    if (n_scored_events_out) *n_scored_events_out = ctx->meth.n_scored_events;
     return rc;
 }
 

@@ -125,6 +125,9 @@ struct nph_ctx {
         DevBuf<uint8_t> d_prov;            // provisional group rows (MethGroup)
         DevBuf<uint64_t> d_counts;         // per record: groups, ranks (2 x n_records), then the prefix arrays and the summary
         DevBuf<nph_meth_site> d_sites;
+        DevBuf<uint8_t> d_tsv_in;          // nph_methylation_tsv: contig, read names, name offsets, strand flags
+        DevBuf<uint64_t> d_tsv_off;        // bytes of each record's rows, then their exclusive prefix (n_records + 1) and the flags word
+        DevBuf<uint8_t> d_tsv;             // the rows
         std::vector<uint64_t> h_prov_off;
     } meth;
 

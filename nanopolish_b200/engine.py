@@ -103,6 +103,19 @@ class Engine:
         self._check(self.lib.nph_methylation_sites_dev(self.ctx, C.byref(ptr), C.byref(n)), "nph_methylation_sites_dev")
         return int(ptr.value or 0), int(n.value)
 
+    def methylation_tsv(self, contig: str, names: list, is_reverse: np.ndarray, cap: int | None = None) -> bytes:
+        """nph_methylation_tsv: the methylation_calls.tsv rows of the last run, formatted on the device."""
+        blob = "".join(names).encode()
+        off = np.zeros(len(names) + 1, np.uint32)
+        off[1:] = np.cumsum([len(n.encode()) for n in names])
+        rev = np.ascontiguousarray(is_reverse, np.uint8)
+        if cap is None:
+            cap = 256 * max(1, self.methylation_counts()[0]) + 4096
+        out = np.empty(cap, np.uint8)
+        n = C.c_uint64()
+        self._check(self.lib.nph_methylation_tsv(self.ctx, contig.encode(), blob, _p(off), _p(rev), _p(out), cap, C.byref(n)), "nph_methylation_tsv")
+        return out[:int(n.value)].tobytes()
+
     def methylation_fetch(self, out=None):
         n_sites = self.methylation_counts()[0]
         site_off, sites = out if out is not None else (np.zeros(self._meth_n + 1, np.uint64), np.zeros(max(n_sites, 1), METH_SITE_DT))

@@ -702,6 +702,27 @@ size_t call_methylation_flat(Engine& engine, const FlatMethylationBatch& b, cons
     // call's fixed costs (two read-backs, ten class launches, the scheduler) and the formatter's thread teams compete with the driver
     // thread for the container's CPU quota.  One call it is; the sub-batch path stays behind $NPH_METH_PIPELINE for larger batches.
     static const bool want_pipeline = std::getenv("NPH_METH_PIPELINE") != nullptr;
+    // Rows formatted on the device (nph_methylation_batch_compact_tsv): the site records never leave it and the host's share of the call
+    // is the name table.  Needs the compact event alignment and a destination; $NPH_METH_HOST_TSV keeps the host formatter (A/B, tests).
+    static const bool host_tsv = std::getenv("NPH_METH_HOST_TSV") != nullptr;
+    if (b.event_deltas && tsv_out && !host_tsv && !want_pipeline && n > 0) {
+        std::vector<uint32_t> name_off(n + 1, 0);
+        for (size_t r = 0; r < n; ++r) name_off[r + 1] = name_off[r] + (uint32_t)std::strlen(b.read_names[r]);
+        std::string names((size_t)name_off[n], '\0');
+        for (size_t r = 0; r < n; ++r) std::memcpy(&names[name_off[r]], b.read_names[r], name_off[r + 1] - name_off[r]);
+        uint64_t n_bytes = 0, n_sites = 0, scored = 0;
+        const double td = now();
+        const int rc = nph_methylation_batch_compact_tsv(engine.ctx(), b.reads, b.n_reads, b.ev_mean, b.ev_start_time, b.n_events, b.ref_bases,
+                                                         b.event_deltas, b.n_ref, b.first_event, b.records, n, &mp, indel_bias,
+                                                         b.contig ? b.contig : "", names.data(), name_off.data(), b.is_reverse,
+                                                         tsv_out, cap, &n_bytes, &n_sites, &scored);
+        if (rc == NPH_OK || (rc == NPH_ERR_INVALID && n_bytes > cap)) {          // too small a destination: report the size, like the host path
+            if (stats) { stats->n_sites = n_sites; stats->scored_events = scored; stats->device_seconds = now() - td; stats->tsv_seconds = (now() - t0) - stats->device_seconds; }
+            return (size_t)n_bytes;
+        }
+        if (rc != NPH_ERR_UNSUPPORTED) engine.check(rc, "nph_methylation_batch_compact_tsv");
+        // a value the device formatter refuses (not finite, beyond 2^52): score again through the record path and format here
+    }
     const size_t n_chunks = (identity && want_pipeline) ? 4 : 1;
     std::vector<size_t> cut(n_chunks + 1);
     for (size_t c = 0; c <= n_chunks; ++c) cut[c] = n * c / n_chunks;

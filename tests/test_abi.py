@@ -79,3 +79,12 @@ def test_dist_gather_on_visible_gpus():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ok" in r.stdout
+
+
+def test_tsv_number_formatting_on_host():
+    """the host copy of csrc/tsv_format.cuh against snprintf (the device copy runs in the gpu tests)"""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "cuda", "check_tsv_format")
+    r = subprocess.run([exe, "--host-only"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert ", 0 bad" in r.stdout

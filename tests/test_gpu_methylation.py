@@ -249,3 +249,54 @@ def test_compact_event_alignment_form(eng2, ref_oracle):
     a = eng2.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref, pairs, recs, params)
     b = eng2.methylation_batch_compact(rs.reads, rs.ev_mean, rs.ev_start_time, ref, deltas, first, recs, params)
     assert np.array_equal(a[0], b[0]) and a[1].tobytes() == b[1].tobytes() and a[1].shape[0] > 100
+
+
+def _expected_rows(sites, site_off, recs, ref, names, is_rev, contig, k):
+    """the reference's writer (src/nanopolish_call_methylation.cpp:113-140) over site records, formatted by Python's correctly
+    rounded %.2f — the C library's %.2lf"""
+    out = []
+    for r in range(recs.shape[0]):
+        R = recs[r]
+        seg = ref[int(R["ref_off"]):int(R["ref_off"]) + int(R["ref_len"])].tobytes().decode()
+        for s in sites[int(site_off[r]):int(site_off[r + 1])]:
+            ll_m, ll_u = float(s["ll_methylated"]) + 0.0, float(s["ll_unmethylated"]) + 0.0
+            b = int(s["start_position"]) - int(R["ref_start_pos"]) - k + 1
+            e = min(int(s["end_position"]) - int(R["ref_start_pos"]) + k, int(R["ref_len"]))
+            out.append("%s\t%s\t%d\t%d\t%s\t%.2f\t%.2f\t%.2f\t%d\t%d\t%s\n" % (
+                contig, "-" if is_rev[r] else "+", int(s["start_position"]), int(s["end_position"]), names[r], ll_m - ll_u, ll_m, ll_u, 1,
+                int(s["n_motif"]), seg[b:e]))
+    return "".join(out)
+
+
+def test_tsv_rows_formatted_on_the_device(eng2):
+    """nph_methylation_tsv: every field of every row, against Python's formatting of the same site records (forward and reverse records,
+    a record without sites, a window clipped by the end of the record's reference, read names of different lengths)."""
+    rs, models, ref, pairs, recs = _batch(14, 2500, 4242, rc_every=3)
+    recs = recs.copy(); ref = ref.copy()
+    r0 = recs[0]; seg = ref[int(r0["ref_off"]):int(r0["ref_off"]) + int(r0["ref_len"])]
+    seg[seg == ord("G")] = ord("A")                                      # record 0: no site at all
+    r3 = recs[3]; seg3 = ref[int(r3["ref_off"]):int(r3["ref_off"]) + int(r3["ref_len"])]
+    cg = np.flatnonzero((seg3[:-1] == ord("C")) & (seg3[1:] == ord("G")))
+    recs[3]["ref_len"] = int(cg[len(cg) // 2]) + 2 + 3                   # the sequence column of the last row is cut by the end
+    params = synth.meth_params("cpg", K)
+    site_off, sites, _ = eng2.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref, pairs, recs, params)
+    names = ["r%d_%s" % (i, "x" * (i % 7)) for i in range(recs.shape[0])]
+    is_rev = (np.arange(recs.shape[0]) % 2).astype(np.uint8)
+    got = eng2.methylation_tsv("chr20", names, is_rev).decode()
+    want = _expected_rows(sites, site_off, recs, ref, names, is_rev, "chr20", K)
+    assert want.count("\n") == sites.shape[0] > 150
+    assert got == want
+    # a destination that is too small reports the size needed
+    from nanopolish_b200._lib import NphError
+    with pytest.raises(NphError):
+        eng2.methylation_tsv("chr20", names, is_rev, cap=100)
+
+
+def test_tsv_number_formatting_on_device():
+    """csrc/tsv_format.cuh == printf("%.2lf") / printf("%d") on 6.6e6 doubles (scores, differences, exact halves at the second decimal,
+    every binade, random bit patterns, refusals beyond 2^52) — host and device copies of the same functions."""
+    import os, subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda", "check_tsv_format")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "device: 0 bad" in r.stdout

@@ -118,3 +118,42 @@ def test_call_methylation_tsv_identical(host, port_oracle):
     assert got >= 0, host.nphh_last_error()
     assert njobs.value == 2 * want.count("\n")                    # two jobs per scored group, one launch for all reads
     assert buf.value.decode() == want
+
+
+def test_flat_call_formats_its_rows_on_the_device(host):
+    """nph::call_methylation_flat with the compact event alignment: one C call, methylation_calls.tsv bytes out, the rows formatted by
+    nph_methylation_tsv — against Python's formatting of the site records of the same batch."""
+    from nanopolish_b200.engine import Engine
+    from tests.test_gpu_methylation import _expected_rows
+    nuc, cpg = synth.load_model("nucleotide"), synth.load_model("cpg")
+    rs = synth.gen_reads(40, 2500, nuc, seed=808, cpg_keep=0.3)
+    ref, pairs, recs = synth.methylation_records(rs, model_id=1, rc_every=2)
+    deltas, first = synth.compact_event_alignment(recs, pairs, ref.shape[0])
+    params = synth.meth_params("cpg", K)
+    eng = Engine(0)
+    try:
+        eng.model_upload(nuc); eng.model_upload(cpg)
+        site_off, sites, scored = eng.methylation_batch_compact(rs.reads, rs.ev_mean, rs.ev_start_time, ref, deltas, first, recs, params)
+    finally:
+        eng.close()
+    n = rs.n_reads
+    names_py = [f"read_{i}" for i in range(n)]
+    is_rev = np.ascontiguousarray(recs["rc"]).astype(np.uint8)
+    want = _expected_rows(sites, site_off, recs, ref, names_py, is_rev, "chr1", K)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    cm, cs, cl = (np.ascontiguousarray(x) for x in (cpg.level_mean, cpg.level_stdv, cpg.level_log_stdv))
+    host.nphh_model_create.restype = C.c_int
+    mh = host.nphh_model_create(b"cpg", 6, cm.shape[0], vp(cm), vp(cs), vp(cl))
+    names = (C.c_char_p * n)(*[s.encode() for s in names_py])
+    host.nphh_call_methylation_flat.restype = C.c_longlong
+    buf = np.zeros(len(want) + 4096, np.uint8)
+    ns, se = C.c_uint64(), C.c_uint64()
+    secs = np.zeros(2)
+    recs2 = recs.copy()
+    got = host.nphh_call_methylation_flat(vp(rs.reads), C.c_size_t(n), vp(rs.ev_mean), None, C.c_size_t(rs.ev_mean.shape[0]),
+                                          vp(ref), C.c_size_t(ref.shape[0]), None, C.c_size_t(0), vp(deltas), vp(first),
+                                          vp(recs2), C.c_size_t(n), mh, names, vp(is_rev), b"chr1", C.c_double(1.0),
+                                          vp(buf), C.c_size_t(buf.shape[0]), C.byref(ns), C.byref(se), vp(secs))
+    assert got >= 0, host.nphh_last_error()
+    assert int(ns.value) == sites.shape[0] and int(se.value) == scored
+    assert buf[:got].tobytes().decode() == want
