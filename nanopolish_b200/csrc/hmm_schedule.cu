@@ -23,7 +23,7 @@ __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n
                                 uint32_t n_reads, const DevModelView* __restrict__ models, const uint32_t* __restrict__ ranks, const uint8_t* __restrict__ codes,
                                 uint32_t n_models, uint64_t n_ranks, uint32_t chunk_events, uint8_t* __restrict__ cls,
                                 uint16_t* __restrict__ bkt, unsigned int* __restrict__ hist, SchedSummary* __restrict__ sum,
-                                uint64_t* __restrict__ rank_base)
+                                uint64_t* __restrict__ rank_base, int trusted_ranks)
 {
     __shared__ unsigned int s_count[NPH_NUM_CLASSES];
     __shared__ float s_cost[NPH_NUM_CLASSES];
@@ -31,10 +31,13 @@ __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n
     for (int i = threadIdx.x; i < NPH_NUM_CLASSES; i += blockDim.x) { s_count[i] = 0; s_cost[i] = 0.f; }
     if (threadIdx.x == 0) { s_kpad = 0; s_period = 0; s_E = 0; }
     __syncthreads();
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_jobs; j += gridDim.x * blockDim.x) {
-        const nph_hmm_job jb = jobs[j];
+    // every warp walks whole rounds of 32 jobs (lanes past the end idle) so that the warp-wide votes below see all lanes
+    const uint32_t n_round = (n_jobs + 31u) & ~31u;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
+        const bool have = j < n_jobs;
+        const nph_hmm_job jb = have ? jobs[j] : nph_hmm_job{};
         uint32_t chunk = 0;
-        bool ok = jb.read < n_reads && jb.model_id < n_models && jb.n_kmers != 0 && jb.n_kmers <= n_ranks && jb.rank_off <= n_ranks - jb.n_kmers;   // overflow-safe
+        bool ok = have && jb.read < n_reads && jb.model_id < n_models && jb.n_kmers != 0 && jb.n_kmers <= n_ranks && jb.rank_off <= n_ranks - jb.n_kmers;   // overflow-safe
         // base-code jobs (nph_hmm_*_seq) read n_kmers + k - 1 codes at rank_off
         const uint32_t seq_len = (ok && codes) ? jb.n_kmers + models[jb.model_id].k - 1u : 0u;
         if (ok && codes) ok = seq_len <= n_ranks && jb.rank_off <= n_ranks - seq_len;
@@ -46,8 +49,9 @@ __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n
             ok = jb.event_start < ne && jb.event_stop < ne;
             ok = ok && !(jb.event_stop > jb.event_start && jb.stride != 1) && !(jb.event_stop < jb.event_start && jb.stride != -1);
         }
-        if (ok) {
-            // every k-mer rank must index the job's model table (the reference would read past PoreModel::states)
+        if (ok && !(trusted_ranks && !codes)) {
+            // every k-mer rank must index the job's model table (the reference would read past PoreModel::states); jobs whose ranks
+            // a kernel of ours just wrote (call-methylation, variant screening) skip the walk over their ranks
             uint32_t worst = 0;
             if (codes) {                       // every code must be a symbol of the model's alphabet
                 const uint8_t* cd = codes + jb.rank_off;
@@ -60,24 +64,42 @@ __global__ void classify_kernel(const nph_hmm_job* __restrict__ jobs, uint32_t n
                 ok = worst < ns;
             }
         }
-        if (!ok) { atomicCAS(&sum->error, 0, (int)(j + 1)); cls[j] = 0; bkt[j] = 0; continue; }
-        const uint32_t E = (jb.event_stop > jb.event_start ? jb.event_stop - jb.event_start : jb.event_start - jb.event_stop) + 1;
-        const uint32_t K = jb.n_kmers;
-        if (codes) rank_base[j] = atomicAdd(&sum->rank_cursor, (unsigned long long)K);     // where this job's ranks will live
-        uint32_t steps;
-        const int c = nph_choose_class(K, E, &steps);
+        if (have && !ok) { atomicCAS(&sum->error, 0, (int)(j + 1)); cls[j] = 0; bkt[j] = 0; }
+        uint32_t key = 0xffffffffu, steps = 0, K = jb.n_kmers, E = 0;
+        int c = 0;
+        if (ok) {
+            E = (jb.event_stop > jb.event_start ? jb.event_stop - jb.event_start : jb.event_start - jb.event_stop) + 1;
+            if (codes) rank_base[j] = atomicAdd(&sum->rank_cursor, (unsigned long long)K);     // where this job's ranks will live
+            c = nph_choose_class(K, E, &steps);
+            const uint32_t b = nph_key_bucket(steps, chunk);
+            cls[j] = (uint8_t)c;
+            bkt[j] = (uint16_t)b;
+            key = (uint32_t)c * NPH_KEY_BUCKETS + b;
+        }
+        // one atomic per (class, bucket) present in the warp instead of one per job: batches of equal windows (call-methylation,
+        // variant screening: millions of jobs on a handful of keys) serialised on those few addresses otherwise
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int lane = threadIdx.x & 31;
+        const bool leader = lane == __ffs(peers) - 1;
         const int C = c % NPH_MAX_COLS + 1;
         const uint32_t W = nph_class_width(c / NPH_MAX_COLS);
-        const uint32_t b = nph_key_bucket(steps, chunk);
-        cls[j] = (uint8_t)c;
-        bkt[j] = (uint16_t)b;
-        atomicAdd(&hist[(size_t)c * NPH_KEY_BUCKETS + b], 1u);
-        atomicAdd(&s_count[c], 1u);
-        atomicAdd(&s_cost[c], nph_class_cost(steps, C, W));
-        const uint32_t strip = W * C;
-        atomicMax(&s_kpad, ((K + strip - 1) / strip) * strip);
-        atomicMax(&s_period, E > 40u ? E : 40u);
-        atomicMax(&s_E, E);
+        float cost = ok ? nph_class_cost(steps, C, W) : 0.0f;
+        // the class totals: sum the costs of the peers (same key => same class) through the leader
+        for (unsigned rest = peers & ~(1u << (__ffs(peers) - 1)); rest; rest &= rest - 1) {
+            const float v = __shfl_sync(peers, cost, __ffs(rest) - 1);
+            if (leader) cost += v;
+        }
+        if (ok && leader) {
+            atomicAdd(&hist[key], (unsigned int)__popc(peers));
+            atomicAdd(&s_count[c], (unsigned int)__popc(peers));
+            atomicAdd(&s_cost[c], cost);
+        }
+        if (ok) {
+            const uint32_t strip = W * C;
+            atomicMax(&s_kpad, ((K + strip - 1) / strip) * strip);
+            atomicMax(&s_period, E > 40u ? E : 40u);
+            atomicMax(&s_E, E);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < NPH_NUM_CLASSES; i += blockDim.x) {
@@ -144,9 +166,17 @@ __global__ void __launch_bounds__(256) codes_to_ranks_kernel(nph_hmm_job* __rest
 __global__ void scatter_kernel(uint32_t n_jobs, const uint8_t* __restrict__ cls, const uint16_t* __restrict__ bkt,
                                unsigned int* __restrict__ offs, uint32_t* __restrict__ order)
 {
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_jobs; j += gridDim.x * blockDim.x) {
-        const unsigned int pos = atomicAdd(&offs[(size_t)cls[j] * NPH_KEY_BUCKETS + bkt[j]], 1u);
-        order[pos] = j;
+    const uint32_t n_round = (n_jobs + 31u) & ~31u;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
+        const bool have = j < n_jobs;
+        const uint32_t key = have ? (uint32_t)cls[j] * NPH_KEY_BUCKETS + bkt[j] : 0xffffffffu;
+        // a slot range per key and warp (one atomic), handed out to the peers in lane order
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int lane = threadIdx.x & 31, lead = __ffs(peers) - 1;
+        unsigned int base = 0;
+        if (have && lane == lead) base = atomicAdd(&offs[key], (unsigned int)__popc(peers));
+        base = __shfl_sync(peers, base, lead);
+        if (have) order[base + __popc(peers & ((1u << lane) - 1u))] = j;
     }
 }
 
@@ -173,7 +203,8 @@ int nph_schedule_hmm_jobs(nph_ctx* ctx, size_t n_jobs, size_t n_ranks_total, uin
     classify_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->d_jobs.p, (uint32_t)n_jobs, ctx->d_reads.p, (uint32_t)ctx->n_reads,
                                                         ctx->d_models.p, ctx->d_ranks.p, ctx->codes_mode ? ctx->d_codes.p : nullptr, (uint32_t)ctx->models.size(), (uint64_t)n_ranks_total,
                                                         (uint32_t)(ctx->levels_inflight ? ctx->level_chunk_events : 0), ctx->d_sched_cls.p,
-                                                        ctx->d_sched_bkt.p, hist, d_sum, ctx->codes_mode ? ctx->d_rank_base.p : nullptr);
+                                                        ctx->d_sched_bkt.p, hist, d_sum, ctx->codes_mode ? ctx->d_rank_base.p : nullptr,
+                                                        ctx->jobs_trusted ? 1 : 0);
     NPH_CUDA(ctx, cudaGetLastError());
     scan_kernel<<<NPH_NUM_CLASSES, 1024, 0, ctx->stream>>>(hist, offs, d_sum);
     NPH_CUDA(ctx, cudaGetLastError());

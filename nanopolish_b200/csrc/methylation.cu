@@ -562,7 +562,10 @@ extern "C" int nph_methylation_run(nph_ctx* ctx)
                 ctx->d_jobs.p, ctx->d_ranks.p, m.d_sites.p, n};
     meth_emit_kernel<<<grid, kThreads, 0, ctx->stream>>>(ea, d);
     NPH_CUDA(ctx, cudaGetLastError());
-    NPH_TRY(nph_jobs_schedule(ctx, n_jobs, (size_t)h.n_ranks));   // read-back 2 of 2: validation + schedule summary
+    ctx->jobs_trusted = true;                                     // meth_emit_kernel wrote these ranks: the scheduler need not walk them
+    const int rc_sched = nph_jobs_schedule(ctx, n_jobs, (size_t)h.n_ranks);   // read-back 2 of 2: validation + schedule summary
+    ctx->jobs_trusted = false;
+    NPH_TRY(rc_sched);
     NPH_TRY(nph_launch_hmm_forward(ctx, nullptr));
     const int fgrid = (int)std::min<size_t>(((size_t)h.n_sites + 255) / 256, (size_t)ctx->sm_count * 8);
     meth_fill_kernel<<<fgrid, 256, 0, ctx->stream>>>(m.d_sites.p, ctx->d_scores.p, h.n_sites);

@@ -78,6 +78,8 @@ struct nph_ctx {
     DevBuf<uint32_t> d_ranks;
     DevBuf<uint8_t> d_codes;         // jobs loaded through the *_seq calls: base codes instead of k-mer ranks (jobs' rank_off index this)
     bool codes_mode = false;
+    bool jobs_trusted = false;       // the resident jobs and their ranks were written by a kernel of ours (methylation.cu, variants.cu): the
+                                     // scheduler validates the jobs' read / event ranges but does not walk their ranks again
     DevBuf<uint64_t> d_rank_base;    // base-code jobs: where each job's ranks start in d_ranks (hmm_schedule.cu)
     DevBuf<nph_hmm_job> d_jobs;
     DevBuf<float2> d_trans;          // per read: (lp_mm_self, lp_mm_next)
