@@ -8,6 +8,11 @@ TSV / SAM / summary writers).
   * the C++ cursor logic on the CPU: rounds are pulled out of EventAligner, the paths come from the plain-C Viterbi
     oracle and are fed back — the text it then writes must equal the reference's, byte for byte;
   * on the GPU the same through EventAligner::run (one Viterbi launch per round, events resident after round one).
+
+Pin status of what is compared here: the default TSV, the event CIGAR and the summary NUMBERS are pinned to the compiled reference;
+`-n` (read names), `--scale-events`, the SAM text around the CIGAR and the formatting of the summary row / `--samples` columns are
+checked against the restatement only (oracle/eventalign_py.py follows eventalign.cpp:398-484 for them; the harness does not drive
+those writer options).
 """
 import ctypes as C
 import os

@@ -1,7 +1,11 @@
 """`nanopolish scorereads` — model_score (src/nanopolish_scorereads.cpp:116-203) as a batch generator over
 profile_hmm_score (nanopolish_b200/host/nph_scorereads.*): the segments it cuts out of a read's event alignment, and the
 per-read score = sum(segment scores) / sum(events).  The enumeration is checked on the CPU (the event alignments come
-from the C++ cursors fed by the plain-C Viterbi), the scores on the GPU against the oracle's profile_hmm_score."""
+from the C++ cursors fed by the plain-C Viterbi), the scores on the GPU against the oracle's profile_hmm_score.
+
+Pin status: profile_hmm_score and align_read_to_ref are pinned to the compiled reference (tests/test_oracle_vs_ref.py); model_score's own
+segment cutting and normalisation are checked against a restatement of nanopolish_scorereads.cpp:116-203 only (scorereads' main() reads
+fast5 files, which the harness cannot supply)."""
 import ctypes as C
 
 import numpy as np
