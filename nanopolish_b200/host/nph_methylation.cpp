@@ -65,22 +65,24 @@ void calculate_call_vectors(const std::map<int, ScoredSite>& calls, const Alphab
     }
 }
 
+// The MM tag (SAM tags specification, base modifications): "<base>+m?" then, per listed call, how many unmodified <base>s of the
+// sequence lie between the previous listed position and this one, comma separated, ';' at the end.  One walk over the sequence with a
+// running count of the unmodified symbol; the listed indices ascend (modbam_tags orders them), and an index that steps backwards
+// restarts the walk there, which is what counting "from the previous position + 1" means for it (nothing in between: 0).
 std::string generate_mm_tag(char unmodified_symbol, const std::string& sequence, const std::vector<size_t>& call_seq_indices)
 {
-    std::string delta_str;
-    delta_str += unmodified_symbol;
-    delta_str += "+m?";
-    size_t count_start = 0;
-    for (size_t call_index = 0; call_index < call_seq_indices.size(); ++call_index) {
-        // unmodified bases skipped since the previous listed position
-        int count = 0;
-        for (size_t j = count_start; j < call_seq_indices[call_index]; ++j) count += sequence[j] == unmodified_symbol;
-        delta_str += ',';
-        delta_str += std::to_string(count);
-        count_start = call_seq_indices[call_index] + 1;
+    std::string tag(1, unmodified_symbol);
+    tag += "+m?";
+    size_t cursor = 0;            // first base not yet accounted for
+    for (const size_t at : call_seq_indices) {
+        size_t skipped = 0;
+        for (; cursor < at; ++cursor) skipped += sequence[cursor] == unmodified_symbol ? 1u : 0u;
+        tag += ',';
+        tag += std::to_string(skipped);
+        cursor = at + 1;
     }
-    delta_str += ';';
-    return delta_str;
+    tag += ';';
+    return tag;
 }
 
 ModbamTags modbam_tags(const std::string& bam_seq, const std::vector<AlignedPair>& aligned_bases, bool is_reverse,
