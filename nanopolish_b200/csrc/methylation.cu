@@ -600,7 +600,7 @@ struct TsvArgs {
     int* refused;                      // set when a value needs the C library (non-finite, |v| >= 2^52)
 };
 
-struct RowNums { nph_tsv::Fixed2 diff, m, u; uint32_t seq_b, seq_len; };
+struct RowNums { nph_tsv::Fixed2 diff, m, u; uint32_t seq_b, seq_len; bool seq_ok; };
 
 __device__ __forceinline__ RowNums row_numbers(const nph_meth_site& ms, const nph_meth_record& R, uint32_t k)
 {
@@ -610,9 +610,12 @@ __device__ __forceinline__ RowNums row_numbers(const nph_meth_site& ms, const np
     r.diff = nph_tsv::fixed2_of(__dsub_rn(sum_m, sum_u));
     r.m = nph_tsv::fixed2_of(sum_m);
     r.u = nph_tsv::fixed2_of(sum_u);
-    const uint32_t b = (uint32_t)(ms.start_position - R.ref_start_pos) - k + 1u;
+    // the sequence column starts k - 1 bases before the first site: a window parameter set that lets a group start closer to the
+    // beginning of the record's reference than that makes the reference's substr throw; here the call is refused
+    const int bs = (ms.start_position - R.ref_start_pos) - (int)k + 1;
     const uint32_t e = min((uint32_t)(ms.end_position - R.ref_start_pos) + k, R.ref_len);
-    r.seq_b = b; r.seq_len = e - b;
+    r.seq_ok = bs >= 0 && (uint32_t)bs <= e;
+    r.seq_b = r.seq_ok ? (uint32_t)bs : 0u; r.seq_len = r.seq_ok ? e - (uint32_t)bs : 0u;
     return r;
 }
 
@@ -645,7 +648,8 @@ __global__ void __launch_bounds__(kThreads) meth_tsv_kernel(const TsvArgs a)
             if (have) {
                 ms = a.sites[s];
                 r = row_numbers(ms, R, a.k);
-                if (!(r.diff.ok && r.m.ok && r.u.ok)) *a.refused = 1;
+                if (!(r.diff.ok && r.m.ok && r.u.ok)) atomicMax(a.refused, 1);
+                if (!r.seq_ok) atomicMax(a.refused, 2);
                 len = row_len(a, ms, r, name_len);
             }
             uint32_t incl = len;
@@ -713,6 +717,7 @@ extern "C" int nph_methylation_tsv(nph_ctx* ctx, const char* contig, const char*
     if (!contig || !read_names || !name_off || !is_reverse) return NPH_ERR_INVALID;
     NPH_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n = m.n_records, contig_len = std::strlen(contig), names_len = name_off[n];
+    for (size_t r = 0; r < n; ++r) if (name_off[r] > name_off[r + 1]) { ctx->last_error = "name_off must ascend"; return NPH_ERR_INVALID; }
     // one staging block: contig | names | name offsets | strand flags
     auto al = [](size_t v) { return (v + 15) / 16 * 16; };
     const size_t o_names = al(contig_len + 1), o_noff = o_names + al(names_len + 1), o_rev = o_noff + al(sizeof(uint32_t) * (n + 1));
@@ -740,6 +745,10 @@ extern "C" int nph_methylation_tsv(nph_ctx* ctx, const char* contig, const char*
     NPH_CUDA(ctx, cudaMemcpyAsync(&total, rec_off + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     NPH_CUDA(ctx, cudaMemcpyAsync(&refused, d_refused, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (refused == 2) {
+        ctx->last_error = "a group starts fewer than k - 1 bases into its record's reference: the sequence column of its row is undefined (min_flank too small for k)";
+        return NPH_ERR_INVALID;
+    }
     if (refused) {
         ctx->last_error = "a log-likelihood is not finite or beyond 2^52: these rows need the C library's formatting (nph_methylation_fetch + host formatter)";
         return NPH_ERR_UNSUPPORTED;
