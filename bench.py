@@ -914,11 +914,19 @@ def run_aux(args, rank, world, local, saved_stdout):
                 "e2e": {"value": raw.shape[0] / float(np.mean(e2e)), "unit": "samples/s", "h2d_bytes_per_step": int(raw.nbytes),
                         "d2h_bytes_per_step": int(24 * (reads["event_off"][-1] + reads["event_cap"][-1])), "steps": args.steps,
                         "api": "nph_detect_events_batch"},
-                "gpu_launches": 4 * args.steps,
+                "gpu_launches": 2 * args.steps,
                 "roofline": {"bound": "hbm", "achieved": b_alg / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": b_alg / (t * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                             "kernel": "ed_guard+ed_tstat+ed_peaks+ed_events",
-                             "note": "algorithmic bytes = 4 B/sample in + 24 B/event out"}}
+                             "frac": b_alg / (t * 1e-3) / 1e9 / peak,
+                             # DRAM bytes of the two kernels for the 4 096-read shape (profiles/r02_events_summary.md: 1.07 GB + 1.35 GB)
+                             "traffic": 2.42e9 if reads.shape[0] == 4096 else None, "peak_source": peak_src,
+                             "kernel": "ed_fused_kernel + ed_events_kernel",
+                             "note": "algorithmic bytes = 4 B/sample in + 24 B/event out; the fused kernel is bound by the float<->double "
+                                     "conversion unit and FP64 latency, not by HBM (DESIGN.md section 11)",
+                             # compute_tstat needs >= 24 conversions per sample position (after staging each sample once), 8.5 clk per
+                             # warp instruction and sub-partition (profiles/r02_ubench_cvt.txt), x 1.11 for the 128-sample warm-ups
+                             "conversion_unit": {"floor_ms": raw.shape[0] / 32 * 24 * 1.11 * 8.5 / (148 * 4 * 1.965e6),
+                                                 "frac": raw.shape[0] / 32 * 24 * 1.11 * 8.5 / (148 * 4 * 1.965e6) / t,
+                                                 "unit": "share of the step the conversion unit alone would need"}}}
     emit(line, saved_stdout)
     eng.close()
 
