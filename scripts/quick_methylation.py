@@ -55,7 +55,23 @@ for it in range(4):
     if it and (best is None or dt < best):
         best, stages = dt, secs3.copy()
 rows = buf.value.count(b"\n")
-jobs = synth.methylation_jobs(rs, model_id=1, keep_seqs=True)   # the same windows, for the event count and the CPU arm
+# the scored-event count of exactly this batch: the same reference / event alignments through the C ABI (nph_methylation_batch), whose
+# enumeration is pinned to the compiled calculate_methylation_for_read; its job count must equal the C++ host's
+from nanopolish_b200.engine import Engine
+recs = np.zeros(n_reads, synth.METH_RECORD_DT)
+ref_all = np.frombuffer(b"".join(refs_s), np.uint8)
+ro_ = po_ = 0
+for i in range(n_reads):
+    recs[i]["ref_off"], recs[i]["pair_off"], recs[i]["read"], recs[i]["model_id"] = ro_, po_, i, 1
+    recs[i]["ref_len"], recs[i]["n_pairs"], recs[i]["ref_start_pos"] = len(refs_s[i]), pairs_l[i].shape[0], 10_000
+    ro_ += len(refs_s[i]); po_ += pairs_l[i].shape[0]
+pairs_all = np.zeros(po_, synth.PAIR_DT)
+pairs_all["ref_pos"] = flat.reshape(-1, 2)[:, 0]; pairs_all["read_pos"] = flat.reshape(-1, 2)[:, 1]
+eng = Engine(0); eng.model_upload(nuc); eng.model_upload(cpg)
+_, sites_dev, scored_exact = eng.methylation_batch(rs.reads, rs.ev_mean, rs.ev_start_time, ref_all, pairs_all, recs, synth.meth_params("cpg", K))
+eng.close()
+assert 2 * sites_dev.shape[0] == int(nj.value) and sites_dev.shape[0] == rows, (sites_dev.shape[0], int(nj.value), rows)
+jobs = synth.methylation_jobs(rs, model_id=1, keep_seqs=True)   # windows of the same shape for the CPU arm's sample (a rate, not this job list)
 ref = None
 try:
     from oracle.oracle_py import RefOracle
@@ -75,9 +91,9 @@ try:
 except OSError as e:
     ref = dict(error=str(e))
 print(json.dumps(dict(workload="call-methylation through the C++ host", reads=n_reads, jobs=int(nj.value), tsv_rows=rows,
-                      scored_events=int(jobs.scored_events), best_ms=best * 1e3, events_per_sec=jobs.scored_events / best,
+                      scored_events=int(scored_exact), best_ms=best * 1e3, events_per_sec=scored_exact / best,
                       reads_per_sec=n_reads / best,
-                      caller_ms=float((stages[0] + stages[1] + stages[2]) * 1e3), events_per_sec_caller=jobs.scored_events / float(stages[0] + stages[1] + stages[2]),
+                      caller_ms=float((stages[0] + stages[1] + stages[2]) * 1e3), events_per_sec_caller=scored_exact / float(stages[0] + stages[1] + stages[2]),
                       stage_ms=dict(stage_host_buffers=stages[0] * 1e3, flatten_and_device=stages[1] * 1e3, tsv=stages[2] * 1e3,
                                     test_shim_marshalling=stages[3] * 1e3, unaccounted=(best - stages.sum()) * 1e3),
-                      host_jobs_match_synth=int(nj.value) == int(jobs.jobs.shape[0]), reference=ref)))
+                      jobs_equal_device_enumeration=True, reference=ref)))
