@@ -414,51 +414,6 @@ __device__ __forceinline__ void tstat_pair(const double* __restrict__ sdx, const
     if (!v2) b = 0.0f;
 }
 
-// The same in two phases, for two rows in flight (NPH_ED_ROWS == 2): tstat_fast is straight-line (no early return: the staged
-// buffer is always readable, a position that has no statistic computes on whatever is there and is discarded), so two calls back
-// to back give the scheduler four independent FP64 chains to interleave; tstat_finish applies the validity rules and the exact
-// path for unproven candidates.
-struct TsPos { TsCand ca, cb; };
-
-template <int W1, int W2>
-__device__ __forceinline__ TsPos tstat_fast(const double* __restrict__ sdx, const double* __restrict__ sdq, const TsConsts& tc, int lane)
-{
-    const uint32_t w1 = W1 ? (uint32_t)W1 : tc.w1, w2 = W2 ? (uint32_t)W2 : tc.w2;
-    const double* cx = sdx + lane + w2;
-    const double* cq = sdq + lane + w2;
-    double sl = 0.0, ql = 0.0, sr = 0.0, qr = 0.0;
-#pragma unroll
-    for (int j = 0; j < (int)w1; ++j) {
-        sl = __dadd_rn(sl, cx[-1 - j]); ql = __dadd_rn(ql, cq[-1 - j]);
-        sr = __dadd_rn(sr, cx[j]); qr = __dadd_rn(qr, cq[j]);
-    }
-    TsPos p;
-    p.ca = tstat_windows(sl, ql, sr, qr, tc.w1f, tc.r1f, tc.w1d, tc.r1d);
-#pragma unroll
-    for (int j = (int)w1; j < (int)w2; ++j) {
-        sl = __dadd_rn(sl, cx[-1 - j]); ql = __dadd_rn(ql, cq[-1 - j]);
-        sr = __dadd_rn(sr, cx[j]); qr = __dadd_rn(qr, cq[j]);
-    }
-    p.cb = tstat_windows(sl, ql, sr, qr, tc.w2f, tc.r2f, tc.w2d, tc.r2d);
-    return p;
-}
-
-template <int W1, int W2>
-__device__ __forceinline__ void tstat_finish(const TsPos& p, bool active, uint32_t n, uint32_t pos, const TsConsts& tc, float& a, float& b)
-{
-    const uint32_t w1 = W1 ? (uint32_t)W1 : tc.w1, w2 = W2 ? (uint32_t)W2 : tc.w2;
-    const bool v1 = active && w1 >= 2 && n >= 2 * w1 && pos >= w1 && pos <= n - w1, v2 = active && w2 >= 2 && n >= 2 * w2 && pos >= w2 && pos <= n - w2;
-    a = p.ca.t; b = p.cb.t;
-    if (v1 && !p.ca.proven) a = tstat_windows_exact(p.ca.combined_var, p.ca.delta_mean, tc.w1f);
-    if (v2 && !p.cb.proven) b = tstat_windows_exact(p.cb.combined_var, p.cb.delta_mean, tc.w2f);
-    if (!v1) a = 0.0f;
-    if (!v2) b = 0.0f;
-}
-
-#ifndef NPH_ED_ROWS
-#define NPH_ED_ROWS 1         // rows of the tile computed together (1 or 2)
-#endif
-
 struct FusedSmem {                       // per warp, 9 216 bytes: six CTAs of four warps fit an SM
     float a[32][32], b[32][32];          // the tile of t-statistics: row = lane that will consume it, column XOR row (bank-conflict free
                                          // for the row-wise producer and the column-wise consumer without padding); after the walks
@@ -468,13 +423,8 @@ struct FusedSmem {                       // per warp, 9 216 bytes: six CTAs of f
     double dq[kRowBuf];                  // ... and their float squares, widened
     GuardAcc guard;                      // the warp's guard extrema
     uint32_t flag, over, pad[2];         // chain verified / some slice overflowed
-#if NPH_ED_ROWS == 2
-    double dx1[kRowBuf + 4], dq1[kRowBuf + 4];      // the second row in flight
-#endif
 };
-#if NPH_ED_ROWS == 1
 static_assert(sizeof(FusedSmem) == 9216, "FusedSmem layout");
-#endif
 
 // One cooperative walk: lane l walks [from_l, from_l + len_l), the first wlen_l steps being warm-up (state only); at
 // step wlen_l the state is snapshotted and from there boundaries are counted and recorded into region[0..R).
@@ -493,34 +443,6 @@ __device__ __forceinline__ uint32_t fused_walk(PeakState& st, PeakState& snap, c
         // on the entry path would make ptxas encode a scoreboard wait at its first use that, inside the loop, also waits for
         // the prefetch just issued (measured: 24 % of all stall samples sat on that one instruction).
         if (c + 32 < len) asm volatile("prefetch.global.L2 [%0];" :: "l"(x + from + c + 32 + w2));     // my next tile's line
-#if NPH_ED_ROWS == 2
-        // two rows per iteration: their samples arrive one iteration ahead, their four statistics are computed interleaved
-        uint32_t fr0 = 0, ln0 = 0, fr1 = 0, ln1 = 0;
-        RowRegs cur0{0.0f, 0.0f}, cur1{0.0f, 0.0f};
-#pragma unroll 1
-        for (int rr = -2; rr < 32; rr += 2) {
-            const uint32_t fr0_n = __shfl_sync(0xffffffffu, from, (rr + 2) & 31), ln0_n = __shfl_sync(0xffffffffu, len, (rr + 2) & 31);
-            const uint32_t fr1_n = __shfl_sync(0xffffffffu, from, (rr + 3) & 31), ln1_n = __shfl_sync(0xffffffffu, len, (rr + 3) & 31);
-            RowRegs nxt0{0.0f, 0.0f}, nxt1{0.0f, 0.0f};
-            if (rr < 30 && c < ln0_n) nxt0 = load_row(x, n, fr0_n + c - w2, w2, lane);
-            if (rr < 30 && c < ln1_n) nxt1 = load_row(x, n, fr1_n + c - w2, w2, lane);
-            const bool act0 = rr >= 0 && c < ln0, act1 = rr >= 0 && c < ln1;            // warp-uniform
-            if (act0 || act1) {
-                if (act0) stage_row(cur0, w2, sm.dx, sm.dq, ga, lane);
-                if (act1) stage_row(cur1, w2, sm.dx1, sm.dq1, ga, lane);
-                __syncwarp();
-                const TsPos p0 = tstat_fast<W1, W2>(sm.dx, sm.dq, tc, lane);
-                const TsPos p1 = tstat_fast<W1, W2>(sm.dx1, sm.dq1, tc, lane);
-                float a0, b0, a1, b1;
-                tstat_finish<W1, W2>(p0, act0 && c + lane < ln0, n, fr0 + c + lane, tc, a0, b0);
-                tstat_finish<W1, W2>(p1, act1 && c + lane < ln1, n, fr1 + c + lane, tc, a1, b1);
-                if (act0) { sm.a[rr][lane ^ rr] = a0; sm.b[rr][lane ^ rr] = b0; }
-                if (act1) { sm.a[rr + 1][lane ^ (rr + 1)] = a1; sm.b[rr + 1][lane ^ (rr + 1)] = b1; }
-                __syncwarp();
-            }
-            cur0 = nxt0; fr0 = fr0_n; ln0 = ln0_n; cur1 = nxt1; fr1 = fr1_n; ln1 = ln1_n;
-        }
-#else
         uint32_t fr = 0, ln = 0;
         RowRegs cur{0.0f, 0.0f};
 #pragma unroll 1
@@ -538,7 +460,6 @@ __device__ __forceinline__ uint32_t fused_walk(PeakState& st, PeakState& snap, c
             }
             cur = nxt; fr = fr_n; ln = ln_n;
         }
-#endif
         if (c == wlen) snap = st;
         const bool rec = c >= wlen;
         const uint32_t steps = len > c ? min(32u, len - c) : 0u;
