@@ -912,7 +912,7 @@ def run_aux(args, rank, world, local, saved_stdout):
                 "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
                 "config": {"workload": f"events: {reads.shape[0]} synthetic raw reads x 36000 samples, scrappie DNA parameters"},
                 "e2e": {"value": raw.shape[0] / float(np.mean(e2e)), "unit": "samples/s", "h2d_bytes_per_step": int(raw.nbytes),
-                        "d2h_bytes_per_step": int(24 * (reads["event_off"][-1] + reads["event_cap"][-1])), "steps": args.steps,
+                        "d2h_bytes_per_step": int(24 * n_ev), "steps": args.steps,
                         "api": "nph_detect_events_batch"},
                 "gpu_launches": 2 * args.steps,
                 "roofline": {"bound": "hbm", "achieved": b_alg / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

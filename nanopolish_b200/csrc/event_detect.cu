@@ -785,7 +785,18 @@ extern "C" int nph_detect_events_batch(nph_ctx* ctx, const float* raw, size_t n_
     if (!d_events) return rc;                       // parameters refused before anything ran
     ctx->last_launches = launches;
     ctx->timing_valid = true;
-    NPH_CUDA(ctx, cudaMemcpyAsync(events_out, d_events, sizeof(nph_event) * events_total, cudaMemcpyDeviceToHost, ctx->stream));
+    // only the events that exist cross PCIe: a read's room (n_samples / 2 in practice) is ~4.5 x what it fills, and the room of a
+    // 4 096-read batch is 1.8 GB.  One copy per read when that saves more than the copies' launch cost, else the whole arena.
+    size_t used = 0;
+    for (size_t i = 0; i < n_reads; ++i) used += counts[i];
+    if (used * 2 < events_total && n_reads <= 65536) {
+        for (size_t i = 0; i < n_reads; ++i)
+            if (counts[i])
+                NPH_CUDA(ctx, cudaMemcpyAsync(events_out + reads[i].event_off, d_events + reads[i].event_off, sizeof(nph_event) * counts[i],
+                                              cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        NPH_CUDA(ctx, cudaMemcpyAsync(events_out, d_events, sizeof(nph_event) * events_total, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     NPH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::copy(counts.begin(), counts.end(), n_events_out);
     return rc;
