@@ -299,11 +299,12 @@ class Engine:
         return out
 
     # ---- event detection (scrappie detect_events) ---------------------------------------------
-    def detect_events_batch(self, raw, reads, params):
-        """== [detect_events(read_i)]: list of EVENT_DT arrays, one per raw read."""
+    def detect_events_batch(self, raw, reads, params, out=None):
+        """== [detect_events(read_i)]: list of EVENT_DT arrays, one per raw read.  out: (events EVENT_DT[room], counts u4[n_reads]) to
+        reuse (page-locked) buffers across calls."""
         total = int((reads["event_off"] + reads["event_cap"]).max()) if reads.shape[0] else 0
-        events = np.zeros(total, EVENT_DT)
-        counts = np.zeros(reads.shape[0], np.uint32)
+        events, counts = out if out is not None else (np.zeros(total, EVENT_DT), np.zeros(reads.shape[0], np.uint32))
+        assert events.shape[0] >= total and counts.shape[0] >= reads.shape[0]
         self._check(self.lib.nph_detect_events_batch(self.ctx, _p(raw), raw.shape[0], _p(reads), reads.shape[0], _p(params),
                                                      _p(events), total, _p(counts)), "nph_detect_events_batch")
         return [events[int(r["event_off"]):int(r["event_off"]) + int(c)] for r, c in zip(reads, counts)]
