@@ -208,6 +208,10 @@ def test_device_equals_compiled_reference(eng2, ref_oracle):
         assert mc.tsv_rows("chr1", "-" if case["flag"] & 16 else "+", case["name"], rows) == want_tsv[i]
         total += s.shape[0]
     assert total > 150
+    # the rows the DEVICE formats (nph_methylation_tsv) are the compiled reference's TSV, byte for byte: records with insertions /
+    # deletions / soft clips, reverse strand, IUPAC and lower-case reference bases
+    got = eng2.methylation_tsv("chr1", [c["name"] for c in cases], np.array([1 if c["flag"] & 16 else 0 for c in cases], np.uint8))
+    assert got.decode() == "".join(want_tsv)
 
 
 def test_compact_event_alignment_form(eng2, ref_oracle):
