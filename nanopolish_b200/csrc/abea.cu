@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
         const int laneK = uK & 31, slotK = (uK >> 5) & 3;
 
         float4 g_next = (lo + 128 <= K) ? prm[lo + 128 - 1] : make_float4(0.f, 1.f, 0.f, 1.f);   // Gaussian of the next column to enter a slot
+        float x_down = lv[min(max(1 - lo, 0), E - 1)];       // level the lowest column meets in band 2 (already loaded above: a down move rewrites the same value)
         for (int bi = 2; bi < n_bands; ++bi) {
             // Suzuki's rule on the two ends of band bi-1 (offset 0 = column lo, offset 99 = column lo+99)
             bool right;
@@ -174,17 +175,32 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
                 // (its Gaussian was fetched at the previous right move, so no load sits on this band's critical path; the
                 // slot's event level is refreshed below like every other slot's and is not used before the band arrives)
                 const int u = lo + 128;
-                if (lane == (u & 31)) {
-                    const int sl = (u >> 5) & 3;
-                    const int cn = lo + 128;
-                    const float4 g = g_next;
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        if (s == sl) { cs[s] = cn; b1[s] = NEG; b1d[s] = (double)NEG; dgd[s] = (double)NEG; lfd[s] = (double)NEG; mu[s] = g.x; sd[s] = g.y; cc[s] = g.z; ry[s] = g.w; }
-                    }
+                const bool own = lane == (u & 31);
+                const int cn = lo + 128;
+                const float4 g = g_next;
+                // the slot is the same for the whole warp: branch on it once instead of predicating the four slots' copies
+#define NPH_ABEA_NEW_COLUMN(S) if (own) { cs[S] = cn; b1[S] = NEG; b1d[S] = (double)NEG; dgd[S] = (double)NEG; lfd[S] = (double)NEG; \
+                                          mu[S] = g.x; sd[S] = g.y; cc[S] = g.z; ry[S] = g.w; }
+                switch ((u >> 5) & 3) {
+                    case 0: NPH_ABEA_NEW_COLUMN(0) break;
+                    case 1: NPH_ABEA_NEW_COLUMN(1) break;
+                    case 2: NPH_ABEA_NEW_COLUMN(2) break;
+                    default: NPH_ABEA_NEW_COLUMN(3) break;
                 }
+#undef NPH_ABEA_NEW_COLUMN
                 lo += 1;
                 g_next = (lo + 128 <= K) ? prm[lo + 128 - 1] : make_float4(0.f, 1.f, 0.f, 1.f);
+            } else {
+                // the band moved down: its lowest column meets a new event (fetched one band ahead); every other column's event
+                // level came from its left neighbour, and after a right move the column that entered the window got its own that way
+                const int u = lo + 128;
+                const bool own = lane == (u & 31);
+                switch ((u >> 5) & 3) {
+                    case 0: if (own) xn[0] = x_down; break;
+                    case 1: if (own) xn[1] = x_down; break;
+                    case 2: if (own) xn[2] = x_down; break;
+                    default: if (own) xn[3] = x_down; break;
+                }
             }
             uint32_t tbyte = 0;
             const int hi = lo + (kBW - 1);
@@ -212,8 +228,20 @@ __global__ void __launch_bounds__(kThreads, 1) abea_kernel(const AbeaParams p)
                 b1[s] = cell ? mx : NEG;
                 b1d[s] = (double)b1[s];
                 tbyte |= (uint32_t)(cell ? from : 0) << (2 * s);
-                // next band's event for this column (clamped: the value is unused when the cell does not exist)
-                xn[s] = lv[min(max(e + 1, 0), E - 1)];
+            }
+            // next band's event levels: column c meets event bi - c, which column c - 1 met in this band — shift the levels one
+            // column up (lane 0's neighbour lives in lane 31, previous slot) instead of four clamped loads; the level the lowest
+            // column would meet after a down move is fetched now (one broadcast load), a band ahead of its use
+            {
+                float xs[4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const float send = (lane == 31) ? xn[(s + 3) & 3] : xn[s];
+                    xs[s] = __shfl_sync(kFull, send, (lane + 31) & 31);
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) xn[s] = xs[s];
+                x_down = lv[min(max(bi - lo, 0), E - 1)];
             }
             if (lo <= 0) {
                 // the trim column (c == 0, k-mer -1) is still inside the band: lp_trim * (event + 1), from = U (:206-216)
